@@ -1,0 +1,85 @@
+"""CPU mirror of the counter-based dropout generator used by the CUDA kernels.
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).
+
+The reference draws dropout masks from PyTorch's Philox stream
+(``nn.Dropout`` at MFT/multiTransformer.py:17,45,101,158-174), which a fused
+kernel cannot reproduce bit-for-bit.  The CUDA path therefore defines its own
+stateless generator -- ``keep = hash(seed, site, element_index) >= p * 2**32`` --
+and train-mode parity is "same result given the same masks": this file
+restates that generator (csrc/mt_common.cuh: mt_rand_u32) with torch int64
+arithmetic so the oracle can apply *identical* masks.
+"""
+import torch
+
+_M32 = 0xFFFFFFFF
+
+
+def _mix32(x):
+    x = x & _M32
+    x = x ^ (x >> 16)
+    x = (x * 0x7FEB352D) & _M32
+    x = x ^ (x >> 15)
+    x = (x * 0x846CA68B) & _M32
+    x = x ^ (x >> 16)
+    return x
+
+
+def rand_u32(seed, site, idx):
+    """idx: int64 tensor of element indices (>= 0).  Returns int64 tensor in [0, 2**32)."""
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    seed_lo, seed_hi = seed & _M32, (seed >> 32) & _M32
+    lo = idx & _M32
+    hi = (idx >> 32) & _M32
+    h = _mix32(lo ^ seed_lo)
+    add = (0x9E3779B9 * (int(site) + 1) + seed_hi) & _M32
+    h = _mix32((h + add + ((hi * 0x85EBCA6B) & _M32)) & _M32)
+    return h
+
+
+def threshold(p):
+    t = int(float(p) * 4294967296.0)
+    return max(0, min(t, _M32))
+
+
+def keep_mask(seed, site, shape, p):
+    """Boolean keep-mask of `shape` (row-major element index)."""
+    n = 1
+    for s in shape:
+        n *= int(s)
+    idx = torch.arange(n, dtype=torch.int64)
+    return (rand_u32(seed, site, idx) >= threshold(p)).reshape(tuple(shape))
+
+
+class Dropper:
+    """Applies dropout exactly as the CUDA kernels do.
+
+    seed=None  -> identity (eval mode / p = 0)
+    """
+
+    def __init__(self, seed=None):
+        self.seed = seed
+
+    def __call__(self, x, p, site):
+        if self.seed is None or p <= 0.0:
+            return x
+        keep = keep_mask(self.seed, site, x.shape, p).to(x.device)
+        return x * keep.to(x.dtype) * (1.0 / (1.0 - p))
+
+
+# ---- site ids (shared with csrc/mt_common.cuh) -------------------------------------------
+# encoder stack `s`, layer `l`:  base = (s * 64 + l) * 8
+SITE_ATTN_P = 0      # attention probabilities  [B, h, T, T]
+SITE_SUB0 = 1        # sublayer-0 output        [B*T, d]
+SITE_FFN_H = 2       # FFN hidden               [B*T, d_ff]
+SITE_SUB1 = 3        # sublayer-1 output        [B*T, d]
+# MFN
+SITE_MFN_G1 = 0x4000  # gamma1 hidden  [T, B, 64]
+SITE_MFN_G2 = 0x4001  # gamma2 hidden  [T, B, 64]
+SITE_MFN_OUT = 0x4002  # out hidden    [T, B, 64]
+# SFT embed input dropout [B*T, in]
+SITE_SFT_EMBED = 0x5000
+
+
+def enc_site(stack, layer, k):
+    return (stack * 64 + layer) * 8 + k
