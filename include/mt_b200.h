@@ -1,0 +1,211 @@
+/*
+ * mt_b200.h -- C ABI of libmt_b200.so: the B200 (sm_100a) implementation of the fusion-model hot path of
+ * frankaging/Multimodal-Transformer (per-modality Transformer encoder stacks + Memory-Fusion recurrence,
+ * forward and backward).
+ *
+ * The reference has no FFI (it is pure PyTorch); each entry point below names the reference Python code it
+ * replaces (paths relative to /root/reference/transformer/).  Conventions:
+ *   - every pointer is a DEVICE pointer unless stated otherwise; the caller owns every buffer; nothing here
+ *     allocates device memory.  Scratch is passed in as `ws` with the size returned by *_ws_bytes().
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises.
+ *   - return value: 0 = ok, otherwise an MT_ERR_* code (mt_error_string() gives text).  Never throws/exits.
+ *   - dtype MT_F32: activations and weights fp32 (FFMA GEMMs; the 1e-5 parity mode).
+ *     dtype MT_BF16: GEMM operands bf16 (tcgen05/TMEM GEMMs fed by TMA), fp32 accumulation, fp32 residual
+ *     stream / LayerNorm / softmax statistics / LSTM state.  Biases and LayerNorm parameters are always fp32.
+ *   - parameter blocks are FLAT arrays in the canonical orders documented at each call; `params_lp` is the
+ *     same layout in bf16 (only read when dtype == MT_BF16).  Gradients are fp32 in the same layout.
+ */
+#ifndef MT_B200_H
+#define MT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MT_F32 0
+#define MT_BF16 1
+
+#define MT_OK 0
+#define MT_ERR_ARG 1        /* bad shape / null pointer / unsupported size */
+#define MT_ERR_ALIGN 2      /* pointer or leading dimension not aligned as required */
+#define MT_ERR_CUDA 3       /* a CUDA runtime call failed (see mt_last_cuda_error) */
+#define MT_ERR_WS 4         /* workspace too small */
+#define MT_ERR_UNSUPPORTED 5
+
+#define MT_ACT_NONE 0
+#define MT_ACT_RELU 1
+#define MT_ACT_TANH 2
+
+#define MT_MAX_MODS 4
+
+const char* mt_error_string(int code);
+const char* mt_last_cuda_error(void);
+/* library / device probe: returns MT_OK when device `dev` is an sm_100 part. */
+int mt_check_device(int dev);
+int mt_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches). */
+uint64_t mt_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Linear:  y[M,N] = act(x[M,K] W[N,K]^T + b) [* rowmask[m]]        replaces nn.Linear call sites
+ * MFT/multiTransformer.py:270,296 (embed), SFT/models.py:137-138 (fusionLayer + tanh), SFT/multiTransformer.py:
+ * 431-433 (Dropout -> Linear -> ReLU; in_drop_p > 0 applies the input dropout).  x,y in `dtype` (x_f32 != 0: x is
+ * fp32 and is cast on the fly -- the hot-path inputs arrive as fp32); W is ALWAYS the fp32 master weight; b fp32.
+ * y_f32 != 0: y is written as fp32 even in bf16 mode (residual-stream input of an encoder stack).
+ * ------------------------------------------------------------------------------------------------- */
+int mt_linear_fwd(int dtype, int M, int N, int K, const void* x, int x_f32, const float* W, const float* b, void* y, int y_f32,
+                  int act, const float* rowmask, float in_drop_p, uint64_t seed, uint32_t site, void* ws, size_t ws_bytes,
+                  void* stream);
+size_t mt_linear_ws_bytes(int dtype, int M, int N, int K, int x_f32, float in_drop_p);
+/* backward: dy[M,N] (dtype, or fp32 when dy_f32), y = forward output (needed when act != NONE; fp32 when y_f32) ->
+ * dx[M,K] (dtype; may be NULL), dW[N,K] fp32, db[N] fp32 (all overwritten). */
+int mt_linear_bwd(int dtype, int M, int N, int K, const void* x, int x_f32, const float* W, const void* y, int y_f32, const void* dy,
+                  int dy_f32, int act, const float* rowmask, float in_drop_p, uint64_t seed, uint32_t site, void* dx, float* dW,
+                  float* db, void* ws, size_t ws_bytes, void* stream);
+size_t mt_linear_bwd_ws_bytes(int dtype, int M, int N, int K, int x_f32, float in_drop_p);
+
+/* ---------------------------------------------------------------------------------------------------
+ * LayerNorm (unbiased std, eps added to std):  MFT/multiTransformer.py:81-91.
+ * x fp32 [M,d]; y in `dtype` (y_f32 forces fp32).  d % 128 == 0, d <= 1024.
+ * ------------------------------------------------------------------------------------------------- */
+int mt_layernorm_fwd(int dtype, int M, int d, const float* x, const float* a_2, const float* b_2, float eps, void* y,
+                     int y_f32, void* stream);
+/* dx = (dres ? dres : 0) + LN'(dy); da/db are ACCUMULATED into (caller zeroes). dy in `dtype` (dy_f32 forces fp32). */
+int mt_layernorm_bwd(int dtype, int M, int d, const float* x, const float* a_2, float eps, const void* dy, int dy_f32,
+                     const float* dres, float* dx, float* da, float* db, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Fused multi-head self-attention core (scores, query-row mask, softmax, dropout, PV, head merge):
+ * attention() MFT/multiTransformer.py:22-34 + the head split/merge of MultiHeadedAttention.forward :54-64.
+ * qkv [B,T,3d] (q | k | v along the last dim, head hd at columns hd*dk), mask fp32 [B,T] (0 => the whole
+ * query row is filled with -1e9, i.e. uniform attention over ALL T keys), out [B,T,d].
+ * lse fp32 [B,h,T] is written when non-NULL (needed by backward).  dk = d/h in {16,32,64,128}.
+ * ------------------------------------------------------------------------------------------------- */
+int mt_attention_fwd(int dtype, int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse,
+                     float p_drop, uint64_t seed, uint32_t site, void* stream);
+/* dqkv [B,T,3d] overwritten.  ws: mt_attention_bwd_ws_bytes (B*h*T floats). */
+int mt_attention_bwd(int dtype, int B, int T, int d, int h, const void* qkv, const float* mask, const void* out,
+                     const float* lse, const void* dout, void* dqkv, float p_drop, uint64_t seed, uint32_t site,
+                     void* ws, size_t ws_bytes, void* stream);
+size_t mt_attention_bwd_ws_bytes(int B, int T, int h);
+/* materialise p_attn [B,h,T,T] fp32 (the reference keeps it as MultiHeadedAttention.attn, :59); debug/inspection. */
+int mt_attention_probs(int dtype, int B, int T, int d, int h, const void* qkv, const float* mask, float* probs,
+                       void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Encoder stack: Encoder.forward MFT/multiTransformer.py:73-76 over N EncoderLayer (:106-116) =
+ * SublayerConnection (:103-104) around MultiHeadedAttention (:47-65) and PositionwiseFeedForward (:19-20),
+ * then the final LayerNorm.
+ * Flat parameter layout (floats), per layer l = 0..N-1:
+ *   w_qkv[3d*d] (linears.0/1/2 weights stacked on the output dim), b_qkv[3d], w_o[d*d], b_o[d],
+ *   w_1[dff*d], b_1[dff], w_2[d*dff], b_2[d], ln1_a[d], ln1_b[d], ln2_a[d], ln2_b[d];
+ * then ln_f_a[d], ln_f_b[d].                                   mt_encoder_param_count() floats in total.
+ * x fp32 [B,T,d] (residual stream in), mask fp32 [B,T], y [B,T,d] in `dtype` (y_f32 forces fp32).
+ * training != 0 keeps the activations backward needs inside `ws` (pass the same ws to mt_encoder_bwd).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int B, T, d, h, dff, n_layers;
+  int dtype;
+  int training;      /* keep the activation stash backward needs (independent of dropout) */
+  float p_drop;      /* dropout probability applied in this call; pass 0 in eval mode */
+  uint64_t seed;
+  int stack_id;      /* selects the dropout sites: site = (stack_id*64 + layer)*8 + k */
+  int y_f32;
+} MtEncoderCfg;
+
+size_t mt_encoder_param_count(int d, int dff, int n_layers);
+size_t mt_encoder_ws_bytes(const MtEncoderCfg* cfg);
+int mt_encoder_fwd(const MtEncoderCfg* cfg, const float* params, const void* params_lp, const float* x,
+                   const float* mask, void* y, void* ws, size_t ws_bytes, void* stream);
+/* dy [B,T,d] (dtype / fp32 per cfg->y_f32) -> dx fp32 [B,T,d]; grads (fp32, flat layout) are OVERWRITTEN. */
+int mt_encoder_bwd(const MtEncoderCfg* cfg, const float* params, const void* params_lp, const float* x,
+                   const float* mask, const void* dy, float* dx, float* grads, void* ws, size_t ws_bytes,
+                   void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Memory Fusion Network: MFN.forward MFT/multiTransformer.py:181-248 (LSTHM cells :208, delta-memory
+ * attention over [c_{t-1} || c_t] :210-219, cHat :220, gamma gates + memory update :221-224, output
+ * head :237-248) with the x-projection hoisted into one GEMM, the recurrence in one persistent kernel and
+ * the head batched over all steps.
+ * Flat parameter layout: for each modality m (in order): w_ih[4H_m*D_m], w_hh[4H_m*H_m], b_ih[4H_m],
+ * b_hh[4H_m]; then (W,b) of att1_fc1 [A1,2H], att1_fc2 [2H,A1], att2_fc1 [A2,2H], att2_fc2 [MEM,A2],
+ * gamma1_fc1 [G,2H+MEM], gamma1_fc2 [MEM,G], gamma2_fc1, gamma2_fc2, out_fc1 [O,H+MEM], out_fc2 [1,O].
+ * Inputs x[m]: [B,T,D_m] in `dtype` addressed as x[m] + b*stride_b[m] + t*stride_t[m] (elements), last dim
+ * contiguous -- so the reference's [T,B,D] permuted views need no copy.  out fp32 [B,T] = head * mask.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int B, T, n_mods;
+  int in_dim[MT_MAX_MODS];
+  int hid[MT_MAX_MODS];
+  int mem_dim, h_att1, h_att2, h_gamma, h_out;
+  int dtype;
+  int training;           /* keep the stash backward needs */
+  float p_gamma, p_out;   /* dropout probs applied in this call (0.2, 0.5 in train mode; pass 0 in eval) */
+  uint64_t seed;
+} MtMfnCfg;
+
+size_t mt_mfn_param_count(const MtMfnCfg* cfg);
+size_t mt_mfn_ws_bytes(const MtMfnCfg* cfg);
+int mt_mfn_fwd(const MtMfnCfg* cfg, const float* params, const void* params_lp, const void* const* x,
+               const int64_t* stride_b, const int64_t* stride_t, const float* mask, float* out, float* h_last,
+               float* c_last, float* mem_last, void* ws, size_t ws_bytes, void* stream);
+/* dout fp32 [B,T] -> dx[m] [B,T,D_m] (dtype, contiguous), grads fp32 flat (OVERWRITTEN). */
+int mt_mfn_bwd(const MtMfnCfg* cfg, const float* params, const void* params_lp, const void* const* x,
+               const int64_t* stride_b, const int64_t* stride_t, const float* mask, const float* dout, void* const* dx,
+               float* grads, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Step-wise LSTM decoder with output feedback + MLP head: SFT/multiTransformer.py:465-483 (NLPTransformer)
+ * and MFT/multiTransformer.py:357-375 (UniTransformer).
+ * Flat layout: w_ih[4E*2E], w_hh[4E*E], b_ih[4E], b_hh[4E], h0[E], c0[E], w_out0[Hd*E], b_out0[Hd], w_out2[Hd], b_out2[1].
+ * enc [B,T,E] in `dtype`; out fp32 [B,T] = head * mask.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int B, T, E, Hd;
+  int dtype;
+  int training;
+} MtLstmHeadCfg;
+size_t mt_lstm_head_param_count(const MtLstmHeadCfg* cfg);
+size_t mt_lstm_head_ws_bytes(const MtLstmHeadCfg* cfg);
+int mt_lstm_head_fwd(const MtLstmHeadCfg* cfg, const float* params, const void* params_lp, const void* enc,
+                     const float* mask, float* out, void* ws, size_t ws_bytes, void* stream);
+int mt_lstm_head_bwd(const MtLstmHeadCfg* cfg, const float* params, const void* params_lp, const void* enc,
+                     const float* mask, const float* dout, void* denc, float* grads, void* ws, size_t ws_bytes,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Utilities on flat buffers.
+ * ------------------------------------------------------------------------------------------------- */
+/* out = x + dropout(y) (SublayerConnection.forward MFT/multiTransformer.py:103-104, stand-alone path; x may be NULL)
+ * and its gradient wrt y: out = g * dropout_factor.  fp32, element index = flat index. */
+int mt_residual_dropout_fwd(const float* x, const float* y, float* out, size_t n, float p, uint64_t seed, uint32_t site,
+                            void* stream);
+int mt_dropout_bwd(const float* g, float* out, size_t n, float p, uint64_t seed, uint32_t site, void* stream);
+/* fp32 -> bf16 shadow copy of a parameter arena. */
+int mt_cast_f32_to_bf16(const float* src, void* dst, size_t n, void* stream);
+int mt_cast_bf16_to_f32(const void* src, float* dst, size_t n, void* stream);
+/* loss = sum((pred-target)^2) * inv_norm ; dpred = 2*(pred-target)*inv_norm   (MFT/train.py:135-139).
+ * loss is ACCUMULATED into *loss (caller zeroes). */
+int mt_mse_loss_fwd_bwd(const float* pred, const float* target, size_t n, float inv_norm, float* loss, float* dpred,
+                        void* stream);
+/* Adam with L2 weight decay folded into the gradient (torch.optim.Adam semantics, MFT/train.py:557) on a flat
+ * arena: one launch for all parameters.  step >= 1. */
+int mt_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
+                 float weight_decay, int step, void* stream);
+
+/* Generic GEMM (exposed for tests and profiling):  C[M,N] = A·B^T-style contraction, see csrc/mt_gemm.cuh.
+ * a_kmajor: A element (m,k) at A[m*lda+k] (else A[k*lda+m]); b_kmajor: B element (n,k) at B[n*ldb+k] (else B[k*ldb+n]). */
+int mt_gemm(int dtype, int M, int N, int K, const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor,
+            void* C, int ldc, int c_f32, const float* bias, int act, int split_k_atomic, void* stream);
+/* which engine a (dtype, shape) GEMM would use: 0 = FFMA SIMT, 1 = tcgen05 */
+int mt_gemm_engine(int dtype, int M, int N, int K, int a_kmajor, int b_kmajor);
+/* test hook: route every GEMM through the FFMA engine (A/B the tensor-core engine); returns the previous setting. */
+int mt_gemm_force_simt(int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MT_B200_H */

@@ -1,0 +1,125 @@
+// Shared device/host helpers for libmt_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mt_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing ----------------------------------------------------------------------------------
+extern char g_mt_cuda_err[512];
+extern unsigned long long g_mt_launches;
+int mt_set_cuda_error(cudaError_t e, const char* file, int line);
+#define MT_CUDA(x)                                                        \
+  do {                                                                    \
+    cudaError_t _e = (x);                                                 \
+    if (_e != cudaSuccess) return mt_set_cuda_error(_e, __FILE__, __LINE__); \
+  } while (0)
+#define MT_LAUNCH_CHECK()                                                 \
+  do {                                                                    \
+    ++g_mt_launches;                                                      \
+    cudaError_t _e = cudaGetLastError();                                  \
+    if (_e != cudaSuccess) return mt_set_cuda_error(_e, __FILE__, __LINE__); \
+  } while (0)
+#define MT_TRY(x)            \
+  do {                       \
+    int _r = (x);            \
+    if (_r != MT_OK) return _r; \
+  } while (0)
+
+static inline size_t mt_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- typed loads / stores ----------------------------------------------------------------------------
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f(float v);
+template <>
+__device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16(v); }
+
+// 4 consecutive elements <-> float4
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const bf16* p) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&u.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&u.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(bf16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// ---- warp reductions ---------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- counter-based dropout generator (mirrored by oracle/dropout_rng.py) -----------------------------
+__host__ __device__ __forceinline__ uint32_t mt_mix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7FEB352Du;
+  x ^= x >> 15;
+  x *= 0x846CA68Bu;
+  x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t mt_rand_u32(uint64_t seed, uint32_t site, uint64_t idx) {
+  uint32_t lo = (uint32_t)idx, hi = (uint32_t)(idx >> 32);
+  uint32_t h = mt_mix32(lo ^ (uint32_t)seed);
+  uint32_t add = 0x9E3779B9u * (site + 1u) + (uint32_t)(seed >> 32);
+  return mt_mix32(h + add + hi * 0x85EBCA6Bu);
+}
+static inline uint32_t mt_drop_threshold(float p) {
+  double t = (double)p * 4294967296.0;
+  if (t <= 0) return 0u;
+  if (t >= 4294967295.0) return 0xFFFFFFFFu;
+  return (uint32_t)t;
+}
+struct DropCfg {
+  uint32_t thresh;   // 0 => dropout disabled
+  float scale;       // 1/(1-p)
+  uint64_t seed;
+  uint32_t site;
+};
+static inline DropCfg mt_make_drop(float p, uint64_t seed, uint32_t site) {
+  DropCfg d;
+  d.thresh = (p > 0.f) ? mt_drop_threshold(p) : 0u;
+  d.scale = (p > 0.f) ? 1.0f / (1.0f - p) : 1.0f;
+  d.seed = seed;
+  d.site = site;
+  return d;
+}
+__device__ __forceinline__ float mt_drop_factor(const DropCfg& d, uint64_t idx) {
+  if (d.thresh == 0u) return 1.0f;
+  return mt_rand_u32(d.seed, d.site, idx) >= d.thresh ? d.scale : 0.0f;
+}
+
+// dropout site ids (oracle/dropout_rng.py)
+#define MT_SITE_ATTN_P 0
+#define MT_SITE_SUB0 1
+#define MT_SITE_FFN_H 2
+#define MT_SITE_SUB1 3
+#define MT_SITE_MFN_G1 0x4000u
+#define MT_SITE_MFN_G2 0x4001u
+#define MT_SITE_MFN_OUT 0x4002u
+static inline uint32_t mt_enc_site(int stack, int layer, int k) { return (uint32_t)((stack * 64 + layer) * 8 + k); }
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }

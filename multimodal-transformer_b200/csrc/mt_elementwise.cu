@@ -1,0 +1,414 @@
+// HBM-bound row-wise / element-wise kernels: LayerNorm (reference semantics: unbiased std, eps on std),
+// dropout-gradient, casts, activation backward, MSE loss, Adam, transposed weight packs.
+// All of them are one pass over their operands with 16-byte vector accesses; warp-shuffle reductions.
+#include "mt_ops.cuh"
+
+namespace {
+
+constexpr int LN_WARPS = 8;
+
+// ------------------------------------------------------------------------------------------------------
+// LayerNorm forward: one warp per row, NCH float4 chunks per lane (d = NCH * 128).
+//   y = a * (x - mean) / (std_unbiased + eps) + b                    MFT/multiTransformer.py:88-91
+// ------------------------------------------------------------------------------------------------------
+template <typename TY, int NCH>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(int M, const float* __restrict__ x, const float* __restrict__ a,
+                                                               const float* __restrict__ b, float eps, TY* __restrict__ y) {
+  constexpr int d = NCH * 128;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 av[NCH], bv[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    av[c] = ld4(a + c * 128 + lane * 4);
+    bv[c] = ld4(b + c * 128 + lane * 4);
+  }
+  for (int row = blockIdx.x * LN_WARPS + warp; row < M; row += gridDim.x * LN_WARPS) {
+    const float* xr = x + (size_t)row * d;
+    float4 v[NCH];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      v[c] = ld4(xr + c * 128 + lane * 4);
+      s += (v[c].x + v[c].y) + (v[c].z + v[c].w);
+    }
+    const float mean = warp_sum(s) * (1.0f / d);
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      v[c].x -= mean; v[c].y -= mean; v[c].z -= mean; v[c].w -= mean;
+      q += (v[c].x * v[c].x + v[c].y * v[c].y) + (v[c].z * v[c].z + v[c].w * v[c].w);
+    }
+    const float sd = sqrtf(warp_sum(q) * (1.0f / (d - 1)));
+    const float inv = 1.0f / (sd + eps);
+    TY* yr = y + (size_t)row * d;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      float4 o;
+      o.x = av[c].x * v[c].x * inv + bv[c].x;
+      o.y = av[c].y * v[c].y * inv + bv[c].y;
+      o.z = av[c].z * v[c].z * inv + bv[c].z;
+      o.w = av[c].w * v[c].w * inv + bv[c].w;
+      st4(yr + c * 128 + lane * 4, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// LayerNorm backward (checked against autograd in tests/test_oracle_golden.py):
+//   g = dy*a;  dx = (g - mean(g) - xc * sum(g*xc) / ((d-1) * s * (s+eps))) / (s+eps)  [+ dres]
+//   da += sum_rows dy * xhat ; db += sum_rows dy        (register partials -> smem -> one atomic per column per CTA)
+// ------------------------------------------------------------------------------------------------------
+template <typename TY, int NCH>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(int M, const float* __restrict__ x, const float* __restrict__ a, float eps,
+                                                               const TY* __restrict__ dy, const float* __restrict__ dres,
+                                                               float* __restrict__ dx, float* __restrict__ da, float* __restrict__ db) {
+  constexpr int d = NCH * 128;
+  __shared__ float s_da[d], s_db[d];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) { s_da[i] = 0.f; s_db[i] = 0.f; }
+  __syncthreads();
+  float4 av[NCH], pa[NCH], pb[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    av[c] = ld4(a + c * 128 + lane * 4);
+    pa[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    pb[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int row = blockIdx.x * LN_WARPS + warp; row < M; row += gridDim.x * LN_WARPS) {
+    const float* xr = x + (size_t)row * d;
+    const TY* gr = dy + (size_t)row * d;
+    float4 v[NCH], g[NCH];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      v[c] = ld4(xr + c * 128 + lane * 4);
+      g[c] = ld4(gr + c * 128 + lane * 4);
+      s += (v[c].x + v[c].y) + (v[c].z + v[c].w);
+    }
+    const float mean = warp_sum(s) * (1.0f / d);
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      v[c].x -= mean; v[c].y -= mean; v[c].z -= mean; v[c].w -= mean;
+      q += (v[c].x * v[c].x + v[c].y * v[c].y) + (v[c].z * v[c].z + v[c].w * v[c].w);
+    }
+    const float sd = sqrtf(warp_sum(q) * (1.0f / (d - 1)));
+    const float inv = 1.0f / (sd + eps);
+    float gs = 0.f, dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      // parameter-gradient partials use the raw dy
+      pb[c].x += g[c].x; pb[c].y += g[c].y; pb[c].z += g[c].z; pb[c].w += g[c].w;
+      pa[c].x += g[c].x * v[c].x * inv; pa[c].y += g[c].y * v[c].y * inv;
+      pa[c].z += g[c].z * v[c].z * inv; pa[c].w += g[c].w * v[c].w * inv;
+      g[c].x *= av[c].x; g[c].y *= av[c].y; g[c].z *= av[c].z; g[c].w *= av[c].w;
+      gs += (g[c].x + g[c].y) + (g[c].z + g[c].w);
+      dot += (g[c].x * v[c].x + g[c].y * v[c].y) + (g[c].z * v[c].z + g[c].w * v[c].w);
+    }
+    const float gm = warp_sum(gs) * (1.0f / d);
+    dot = warp_sum(dot);
+    const float k = dot / ((float)(d - 1) * sd * (sd + eps));
+    float* dxr = dx + (size_t)row * d;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      float4 o;
+      o.x = (g[c].x - gm - v[c].x * k) * inv;
+      o.y = (g[c].y - gm - v[c].y * k) * inv;
+      o.z = (g[c].z - gm - v[c].z * k) * inv;
+      o.w = (g[c].w - gm - v[c].w * k) * inv;
+      if (dres) {
+        float4 r = ld4(dres + (size_t)row * d + c * 128 + lane * 4);
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      st4(dxr + c * 128 + lane * 4, o);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    int col = c * 128 + lane * 4;
+    atomicAdd(&s_da[col + 0], pa[c].x); atomicAdd(&s_da[col + 1], pa[c].y);
+    atomicAdd(&s_da[col + 2], pa[c].z); atomicAdd(&s_da[col + 3], pa[c].w);
+    atomicAdd(&s_db[col + 0], pb[c].x); atomicAdd(&s_db[col + 1], pb[c].y);
+    atomicAdd(&s_db[col + 2], pb[c].z); atomicAdd(&s_db[col + 3], pb[c].w);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    atomicAdd(da + i, s_da[i]);
+    atomicAdd(db + i, s_db[i]);
+  }
+}
+
+template <typename TO>
+__global__ void drop_grad_kernel(size_t n4, const float* __restrict__ g, TO* __restrict__ out, DropCfg drop) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = ld4(g + i * 4);
+    v.x *= mt_drop_factor(drop, i * 4 + 0);
+    v.y *= mt_drop_factor(drop, i * 4 + 1);
+    v.z *= mt_drop_factor(drop, i * 4 + 2);
+    v.w *= mt_drop_factor(drop, i * 4 + 3);
+    st4(out + i * 4, v);
+  }
+}
+
+// out = x + y * dropout_factor   (SublayerConnection residual, stand-alone path)
+__global__ void residual_dropout_kernel(size_t n, const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out,
+                                        DropCfg drop) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = (x ? x[i] : 0.f) + y[i] * mt_drop_factor(drop, i);
+}
+
+template <typename TS, typename TD>
+__global__ void cast2d_kernel(const TS* __restrict__ src, int lds, TD* __restrict__ dst, int ldd, int rows, int cols, DropCfg drop) {
+  size_t n = (size_t)rows * ldd;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int r = (int)(i / ldd), c = (int)(i % ldd);
+    float v = 0.f;
+    if (c < cols) v = to_f(src[(size_t)r * lds + c]) * mt_drop_factor(drop, (uint64_t)r * cols + c);
+    dst[i] = from_f<TD>(v);
+  }
+}
+
+template <typename TG, typename TY, typename TZ>
+__global__ void act_bwd_kernel(size_t n, int N, const TG* __restrict__ dy, const TY* __restrict__ y, int act,
+                               const float* __restrict__ rowmask, TZ* __restrict__ dz) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float g = to_f(dy[i]);
+    if (rowmask) g *= rowmask[i / N];
+    if (act == MT_ACT_RELU) g = to_f(y[i]) > 0.f ? g : 0.f;
+    else if (act == MT_ACT_TANH) { float t = to_f(y[i]); g *= (1.0f - t * t); }
+    dz[i] = from_f<TZ>(g);
+  }
+}
+
+struct TransposeJobs { TransposeJob j[16]; };
+template <typename TD>
+__global__ void transpose_pack_kernel(TransposeJobs jobs) {
+  const TransposeJob jb = jobs.j[blockIdx.y];
+  const int n = jb.R * jb.C;
+  TD* dst = reinterpret_cast<TD*>(jb.dst);
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    int c = e / jb.R, r = e % jb.R;
+    dst[(size_t)c * jb.ldd + r] = from_f<TD>(jb.src[(size_t)r * jb.C + c]);
+  }
+}
+
+__global__ void cast_f2b_kernel(const float* __restrict__ s, bf16* __restrict__ d, size_t n) {
+  size_t n4 = n / 4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) st4(d + i * 4, ld4(s + i * 4));
+  for (size_t i = n4 * 4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d[i] = __float2bfloat16(s[i]);
+}
+__global__ void cast_b2f_kernel(const bf16* __restrict__ s, float* __restrict__ d, size_t n) {
+  size_t n4 = n / 4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) st4(d + i * 4, ld4(s + i * 4));
+  for (size_t i = n4 * 4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d[i] = __bfloat162float(s[i]);
+}
+
+__global__ void mse_kernel(const float* __restrict__ pred, const float* __restrict__ target, size_t n, float inv_norm,
+                           float* __restrict__ loss, float* __restrict__ dpred) {
+  float acc = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float e = pred[i] - target[i];
+    acc += e * e;
+    if (dpred) dpred[i] = 2.0f * e * inv_norm;
+  }
+  acc = warp_sum(acc);
+  __shared__ float s[32];
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) s[w] = acc;
+  __syncthreads();
+  if (w == 0) {
+    acc = lane < (blockDim.x >> 5) ? s[lane] : 0.f;
+    acc = warp_sum(acc);
+    if (lane == 0) atomicAdd(loss, acc * inv_norm);
+  }
+}
+
+// torch.optim.Adam (L2 weight decay added to the gradient, bias-corrected), MFT/train.py:557
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
+                            float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+  const float step = lr / bc1;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float pi = p[i];
+    float gi = g[i] + wd * pi;
+    float mi = b1 * m[i] + (1.0f - b1) * gi;
+    float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - step * (mi / denom);
+  }
+}
+
+inline int ew_grid(size_t n, int threads) {
+  size_t b = (n + threads - 1) / threads;
+  size_t cap = 148 * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+template <typename TY>
+int ln_fwd_dispatch(int M, int d, const float* x, const float* a, const float* b, float eps, TY* y, cudaStream_t st) {
+  int grid = (M + LN_WARPS - 1) / LN_WARPS;
+  if (grid > 148 * 8) grid = 148 * 8;
+  switch (d / 128) {
+    case 1: ln_fwd_kernel<TY, 1><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, b, eps, y); break;
+    case 2: ln_fwd_kernel<TY, 2><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, b, eps, y); break;
+    case 3: ln_fwd_kernel<TY, 3><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, b, eps, y); break;
+    case 4: ln_fwd_kernel<TY, 4><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, b, eps, y); break;
+    case 6: ln_fwd_kernel<TY, 6><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, b, eps, y); break;
+    case 8: ln_fwd_kernel<TY, 8><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, b, eps, y); break;
+    default: return MT_ERR_UNSUPPORTED;
+  }
+  MT_LAUNCH_CHECK();
+  return MT_OK;
+}
+
+template <typename TY>
+int ln_bwd_dispatch(int M, int d, const float* x, const float* a, float eps, const TY* dy, const float* dres, float* dx, float* da,
+                    float* db, cudaStream_t st) {
+  int grid = (M + LN_WARPS - 1) / LN_WARPS;
+  if (grid > 148 * 4) grid = 148 * 4;
+  switch (d / 128) {
+    case 1: ln_bwd_kernel<TY, 1><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, eps, dy, dres, dx, da, db); break;
+    case 2: ln_bwd_kernel<TY, 2><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, eps, dy, dres, dx, da, db); break;
+    case 3: ln_bwd_kernel<TY, 3><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, eps, dy, dres, dx, da, db); break;
+    case 4: ln_bwd_kernel<TY, 4><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, eps, dy, dres, dx, da, db); break;
+    case 6: ln_bwd_kernel<TY, 6><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, eps, dy, dres, dx, da, db); break;
+    case 8: ln_bwd_kernel<TY, 8><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, eps, dy, dres, dx, da, db); break;
+    default: return MT_ERR_UNSUPPORTED;
+  }
+  MT_LAUNCH_CHECK();
+  return MT_OK;
+}
+
+}  // namespace
+
+int mt_ln_fwd_run(int M, int d, const float* x, const float* a, const float* b, float eps, void* y, bool y_bf16, cudaStream_t st) {
+  if (M <= 0 || d <= 0 || d % 128 != 0 || d > 1024 || !x || !a || !b || !y) return MT_ERR_ARG;
+  if (y_bf16) return ln_fwd_dispatch<bf16>(M, d, x, a, b, eps, (bf16*)y, st);
+  return ln_fwd_dispatch<float>(M, d, x, a, b, eps, (float*)y, st);
+}
+
+int mt_ln_bwd_run(int M, int d, const float* x, const float* a, float eps, const void* dy, bool dy_bf16, const float* dres, float* dx,
+                  float* da, float* db, cudaStream_t st) {
+  if (M <= 0 || d <= 0 || d % 128 != 0 || d > 1024 || !x || !a || !dy || !dx || !da || !db) return MT_ERR_ARG;
+  if (dy_bf16) return ln_bwd_dispatch<bf16>(M, d, x, a, eps, (const bf16*)dy, dres, dx, da, db, st);
+  return ln_bwd_dispatch<float>(M, d, x, a, eps, (const float*)dy, dres, dx, da, db, st);
+}
+
+int mt_drop_grad_run(int M, int N, const float* g, void* out, bool out_bf16, DropCfg drop, cudaStream_t st) {
+  size_t n = (size_t)M * N;
+  if (n == 0 || n % 4 != 0) return MT_ERR_ARG;
+  if (out_bf16) drop_grad_kernel<bf16><<<ew_grid(n / 4, 256), 256, 0, st>>>(n / 4, g, (bf16*)out, drop);
+  else drop_grad_kernel<float><<<ew_grid(n / 4, 256), 256, 0, st>>>(n / 4, g, (float*)out, drop);
+  MT_LAUNCH_CHECK();
+  return MT_OK;
+}
+
+int mt_cast2d_run(const void* src, bool src_bf16, int lds, void* dst, bool dst_bf16, int ldd, int rows, int cols, DropCfg drop,
+                  cudaStream_t st) {
+  if (rows <= 0 || cols <= 0 || ldd < cols || lds < cols) return MT_ERR_ARG;
+  size_t n = (size_t)rows * ldd;
+  int grid = ew_grid(n, 256);
+  if (!src_bf16 && dst_bf16) cast2d_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)src, lds, (bf16*)dst, ldd, rows, cols, drop);
+  else if (!src_bf16 && !dst_bf16) cast2d_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, lds, (float*)dst, ldd, rows, cols, drop);
+  else if (src_bf16 && dst_bf16) cast2d_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)src, lds, (bf16*)dst, ldd, rows, cols, drop);
+  else cast2d_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)src, lds, (float*)dst, ldd, rows, cols, drop);
+  MT_LAUNCH_CHECK();
+  return MT_OK;
+}
+
+int mt_act_bwd_run(int M, int N, const void* dy, bool dy_bf16, const void* y, bool y_bf16, int act, const float* rowmask, void* dz,
+                   bool dz_bf16, cudaStream_t st) {
+  size_t n = (size_t)M * N;
+  if (n == 0) return MT_ERR_ARG;
+  if (act != MT_ACT_NONE && !y) return MT_ERR_ARG;
+  int grid = ew_grid(n, 256);
+#define MT_AB(TG, TYY, TZ) act_bwd_kernel<TG, TYY, TZ><<<grid, 256, 0, st>>>(n, N, (const TG*)dy, (const TYY*)y, act, rowmask, (TZ*)dz)
+  if (dy_bf16) {
+    if (y_bf16) { if (dz_bf16) MT_AB(bf16, bf16, bf16); else MT_AB(bf16, bf16, float); }
+    else { if (dz_bf16) MT_AB(bf16, float, bf16); else MT_AB(bf16, float, float); }
+  } else {
+    if (y_bf16) { if (dz_bf16) MT_AB(float, bf16, bf16); else MT_AB(float, bf16, float); }
+    else { if (dz_bf16) MT_AB(float, float, bf16); else MT_AB(float, float, float); }
+  }
+#undef MT_AB
+  MT_LAUNCH_CHECK();
+  return MT_OK;
+}
+
+int mt_transpose_pack_run(const TransposeJob* jobs, int n_jobs, bool dst_bf16, cudaStream_t st) {
+  if (n_jobs <= 0 || n_jobs > 16) return MT_ERR_ARG;
+  TransposeJobs J;
+  int mx = 0;
+  for (int i = 0; i < n_jobs; ++i) { J.j[i] = jobs[i]; mx = max(mx, jobs[i].R * jobs[i].C); }
+  dim3 grid(min((mx + 255) / 256, 64), n_jobs);
+  if (dst_bf16) transpose_pack_kernel<bf16><<<grid, 256, 0, st>>>(J);
+  else transpose_pack_kernel<float><<<grid, 256, 0, st>>>(J);
+  MT_LAUNCH_CHECK();
+  return MT_OK;
+}
+
+extern "C" {
+
+int mt_layernorm_fwd(int dtype, int M, int d, const float* x, const float* a_2, const float* b_2, float eps, void* y, int y_f32,
+                     void* stream) {
+  return mt_ln_fwd_run(M, d, x, a_2, b_2, eps, y, dtype == MT_BF16 && !y_f32, (cudaStream_t)stream);
+}
+
+int mt_layernorm_bwd(int dtype, int M, int d, const float* x, const float* a_2, float eps, const void* dy, int dy_f32,
+                     const float* dres, float* dx, float* da, float* db, void* stream) {
+  return mt_ln_bwd_run(M, d, x, a_2, eps, dy, dtype == MT_BF16 && !dy_f32, dres, dx, da, db, (cudaStream_t)stream);
+}
+
+int mt_residual_dropout_fwd(const float* x, const float* y, float* out, size_t n, float p, uint64_t seed, uint32_t site, void* stream) {
+  if (!y || !out || n == 0) return MT_ERR_ARG;
+  residual_dropout_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(n, x, y, out, mt_make_drop(p, seed, site));
+  MT_LAUNCH_CHECK();
+  return MT_OK;
+}
+
+int mt_dropout_bwd(const float* g, float* out, size_t n, float p, uint64_t seed, uint32_t site, void* stream) {
+  if (!g || !out || n == 0) return MT_ERR_ARG;
+  residual_dropout_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(n, nullptr, g, out, mt_make_drop(p, seed, site));
+  MT_LAUNCH_CHECK();
+  return MT_OK;
+}
+
+int mt_cast_f32_to_bf16(const float* src, void* dst, size_t n, void* stream) {
+  if (!src || !dst) return MT_ERR_ARG;
+  if (n == 0) return MT_OK;
+  if (((uintptr_t)src & 15) || ((uintptr_t)dst & 7)) return MT_ERR_ALIGN;
+  cast_f2b_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
+  MT_LAUNCH_CHECK();
+  return MT_OK;
+}
+
+int mt_cast_bf16_to_f32(const void* src, float* dst, size_t n, void* stream) {
+  if (!src || !dst) return MT_ERR_ARG;
+  if (n == 0) return MT_OK;
+  if (((uintptr_t)src & 7) || ((uintptr_t)dst & 15)) return MT_ERR_ALIGN;
+  cast_b2f_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)src, dst, n);
+  MT_LAUNCH_CHECK();
+  return MT_OK;
+}
+
+int mt_mse_loss_fwd_bwd(const float* pred, const float* target, size_t n, float inv_norm, float* loss, float* dpred, void* stream) {
+  if (!pred || !target || !loss || n == 0) return MT_ERR_ARG;
+  int grid = ew_grid(n, 256);
+  if (grid > 148) grid = 148;
+  mse_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pred, target, n, inv_norm, loss, dpred);
+  MT_LAUNCH_CHECK();
+  return MT_OK;
+}
+
+int mt_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
+                 float weight_decay, int step, void* stream) {
+  if (!p || !g || !m || !v || step < 1) return MT_ERR_ARG;
+  if (n == 0) return MT_OK;
+  float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  float bc2 = (float)(1.0 - pow((double)beta2, (double)step));
+  adam_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2));
+  MT_LAUNCH_CHECK();
+  return MT_OK;
+}
+
+}  // extern "C"

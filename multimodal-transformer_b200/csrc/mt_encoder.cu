@@ -1,0 +1,354 @@
+// Encoder stack (Encoder.forward MFT/multiTransformer.py:73-76 over EncoderLayer :106-116) and the stand-alone
+// Linear (embed / fusion layers), forward and backward, as sequences of GEMMs with fused epilogues, fused
+// attention and row-wise LayerNorm kernels.  The residual stream stays fp32; GEMM operands are `dtype`.
+#include "mt_ops.cuh"
+
+namespace {
+
+struct EncParams {
+  // offsets (floats) inside one layer's block of the flat layout documented in include/mt_b200.h
+  size_t w_qkv, b_qkv, w_o, b_o, w_1, b_1, w_2, b_2, ln1_a, ln1_b, ln2_a, ln2_b, layer_stride;
+  size_t lnf_a, lnf_b, total;
+};
+
+EncParams enc_params(int d, int dff, int n_layers) {
+  EncParams p;
+  size_t o = 0;
+  p.w_qkv = o; o += (size_t)3 * d * d;
+  p.b_qkv = o; o += (size_t)3 * d;
+  p.w_o = o; o += (size_t)d * d;
+  p.b_o = o; o += d;
+  p.w_1 = o; o += (size_t)dff * d;
+  p.b_1 = o; o += dff;
+  p.w_2 = o; o += (size_t)d * dff;
+  p.b_2 = o; o += d;
+  p.ln1_a = o; o += d;
+  p.ln1_b = o; o += d;
+  p.ln2_a = o; o += d;
+  p.ln2_b = o; o += d;
+  p.layer_stride = o;
+  p.lnf_a = o * n_layers;
+  p.lnf_b = p.lnf_a + d;
+  p.total = p.lnf_b + d;
+  return p;
+}
+
+// Activations kept per layer for backward (training) or reused across layers (inference).
+struct LayerBufs {
+  float* x_out;   // fp32 [M,d] residual stream after the layer
+  void* u;        // LN1(x)            [M,d]   dtype
+  void* qkv;      //                   [M,3d]  dtype
+  float* lse;     //                   [B,h,T]
+  void* att;      // merged heads      [M,d]   dtype
+  float* xp;      // x + attn sublayer [M,d]   fp32
+  void* v;        // LN2(xp)           [M,d]   dtype
+  void* hid;      // relu/dropout FFN hidden [M,dff] dtype
+};
+
+struct EncWs {
+  LayerBufs L[64];
+  // backward scratch
+  float* g0; float* g1;      // fp32 [M,d] gradient of the residual stream (ping-pong)
+  void* dact;                // [M,d] dtype (dropout-applied sublayer gradient; later du / dv)
+  void* dact2;               // [M,d] dtype
+  void* dhid;                // [M,dff] dtype
+  void* dqkv;                // [M,3d] dtype
+  float* Dws;                // [B,h,T]
+  size_t bytes;
+};
+
+int carve(const MtEncoderCfg& c, void* ws, EncWs& w) {
+  if (c.n_layers < 1 || c.n_layers > 64) return MT_ERR_ARG;
+  const size_t M = (size_t)c.B * c.T, d = c.d, es = mt_esize(c.dtype);
+  WsCarver k(ws);
+  const int sets = c.training ? c.n_layers : 1;
+  for (int s = 0; s < sets; ++s) {
+    LayerBufs& b = w.L[s];
+    b.x_out = k.take<float>(M * d);
+    b.u = k.take_bytes(M * d * es);
+    b.qkv = k.take_bytes(M * 3 * d * es);
+    b.lse = k.take<float>((size_t)c.B * c.h * c.T);
+    b.att = k.take_bytes(M * d * es);
+    b.xp = k.take<float>(M * d);
+    b.v = k.take_bytes(M * d * es);
+    b.hid = k.take_bytes(M * c.dff * es);
+  }
+  float* x_alt = c.training ? nullptr : k.take<float>(M * d);   // inference ping-pong of the residual stream
+  for (int l = sets; l < c.n_layers; ++l) {
+    w.L[l] = w.L[0];
+    if ((l & 1) && x_alt) w.L[l].x_out = x_alt;
+  }
+  if (c.training) {
+    w.g0 = k.take<float>(M * d);
+    w.g1 = k.take<float>(M * d);
+    w.dact = k.take_bytes(M * d * es);
+    w.dact2 = k.take_bytes(M * d * es);
+    w.dhid = k.take_bytes(M * c.dff * es);
+    w.dqkv = k.take_bytes(M * 3 * d * es);
+    w.Dws = k.take<float>((size_t)c.B * c.h * c.T);
+  }
+  w.bytes = k.total();
+  return MT_OK;
+}
+
+int check_cfg(const MtEncoderCfg* c) {
+  if (!c) return MT_ERR_ARG;
+  if (c->B <= 0 || c->T <= 0 || c->d <= 0 || c->h <= 0 || c->dff <= 0 || c->n_layers <= 0) return MT_ERR_ARG;
+  if (c->d % c->h != 0 || c->d % 128 != 0 || c->d > 1024 || c->dff % 4 != 0) return MT_ERR_ARG;
+  if (c->dtype != MT_F32 && c->dtype != MT_BF16) return MT_ERR_ARG;
+  if ((size_t)c->B * c->T > 0x7fffffffull / (3 * (size_t)c->d)) return MT_ERR_ARG;   // 32-bit row*ld products inside the GEMMs
+  return MT_OK;
+}
+
+inline const void* wptr(const MtEncoderCfg& c, const float* params, const void* params_lp, size_t off) {
+  return c.dtype == MT_BF16 ? (const void*)((const bf16*)params_lp + off) : (const void*)(params + off);
+}
+
+// y = epi(x W^T): A = x [M,K] k-major, B = W [N,K] k-major
+GemmDesc fwd_gemm(int M, int N, int K, const void* x, const void* W, void* y, bool y_f32) {
+  GemmDesc g;
+  g.M = M; g.N = N; g.K = K;
+  g.A = x; g.lda = K; g.a_kmajor = true;
+  g.B = W; g.ldb = K; g.b_kmajor = true;
+  g.C = y; g.ldc = N; g.c_f32 = y_f32;
+  return g;
+}
+// dx = dy W: A = dy [M,Nout] k-major, B = W [Nout,Kin] read as B(n = kin, k = nout) -> mn-major
+GemmDesc dgrad_gemm(int M, int Nout, int Kin, const void* dy, const void* W, void* dx, bool dx_f32) {
+  GemmDesc g;
+  g.M = M; g.N = Kin; g.K = Nout;
+  g.A = dy; g.lda = Nout; g.a_kmajor = true;
+  g.B = W; g.ldb = Kin; g.b_kmajor = false;
+  g.C = dx; g.ldc = Kin; g.c_f32 = dx_f32;
+  return g;
+}
+// dW[Nout,Kin] = dy^T x : contraction over the M tokens, both operands mn-major, split-K with fp32 atomics
+GemmDesc wgrad_gemm(int M, int Nout, int Kin, const void* dy, int ldy, const void* x, int ldx, float* dW, int ldw) {
+  GemmDesc g;
+  g.M = Nout; g.N = Kin; g.K = M;
+  g.A = dy; g.lda = ldy; g.a_kmajor = false;
+  g.B = x; g.ldb = ldx; g.b_kmajor = false;
+  g.C = dW; g.ldc = ldw; g.c_f32 = true;
+  size_t tiles = (size_t)((Nout + 63) / 64) * ((Kin + 63) / 64);
+  int split = (int)((148 * 4 + tiles - 1) / tiles);
+  int max_split = (M + 255) / 256;
+  if (split > max_split) split = max_split;
+  g.split_k = split < 2 ? 2 : split;          // always the atomic epilogue: dW is zero-initialised by the caller
+  return g;
+}
+
+}  // namespace
+
+// shared with mt_mfn.cu
+GemmDesc mt_wgrad_desc(int M, int Nout, int Kin, const void* dy, int ldy, const void* x, int ldx, float* dW, int ldw) {
+  return wgrad_gemm(M, Nout, Kin, dy, ldy, x, ldx, dW, ldw);
+}
+
+extern "C" {
+
+size_t mt_encoder_param_count(int d, int dff, int n_layers) { return enc_params(d, dff, n_layers).total; }
+
+size_t mt_encoder_ws_bytes(const MtEncoderCfg* cfg) {
+  if (check_cfg(cfg) != MT_OK) return 0;
+  EncWs w;
+  if (carve(*cfg, nullptr, w) != MT_OK) return 0;
+  return w.bytes;
+}
+
+int mt_encoder_fwd(const MtEncoderCfg* cfg, const float* params, const void* params_lp, const float* x, const float* mask, void* y,
+                   void* ws, size_t ws_bytes, void* stream) {
+  MT_TRY(check_cfg(cfg));
+  const MtEncoderCfg& c = *cfg;
+  if (!params || !x || !y || !ws || (c.dtype == MT_BF16 && !params_lp)) return MT_ERR_ARG;
+  EncWs w;
+  MT_TRY(carve(c, ws, w));
+  if (ws_bytes < w.bytes) return MT_ERR_WS;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int M = c.B * c.T, d = c.d, dff = c.dff;
+  const bool lp = c.dtype == MT_BF16;
+  const EncParams P = enc_params(d, dff, c.n_layers);
+  const float p = c.p_drop;
+  const float* xin = x;
+  for (int l = 0; l < c.n_layers; ++l) {
+    const size_t base = P.layer_stride * l;
+    const float* pf = params + base;
+    LayerBufs& b = w.L[l];
+    // sublayer 0: x + dropout(self_attn(LN(x)))
+    MT_TRY(mt_ln_fwd_run(M, d, xin, pf + P.ln1_a, pf + P.ln1_b, 1e-6f, b.u, lp, st));
+    GemmDesc g = fwd_gemm(M, 3 * d, d, b.u, wptr(c, params, params_lp, base + P.w_qkv), b.qkv, !lp);
+    g.epi.bias = pf + P.b_qkv;
+    MT_TRY(mt_gemm_run(c.dtype, g, st));
+    MT_TRY(mt_attn_fwd_run(c.dtype, c.B, c.T, d, c.h, b.qkv, mask, b.att, b.lse,
+                           mt_make_drop(p, c.seed, mt_enc_site(c.stack_id, l, MT_SITE_ATTN_P)), st));
+    g = fwd_gemm(M, d, d, b.att, wptr(c, params, params_lp, base + P.w_o), b.xp, true);
+    g.epi.bias = pf + P.b_o;
+    g.epi.drop = mt_make_drop(p, c.seed, mt_enc_site(c.stack_id, l, MT_SITE_SUB0));
+    g.epi.residual = xin; g.epi.ldr = d;
+    MT_TRY(mt_gemm_run(c.dtype, g, st));
+    // sublayer 1: x + dropout(w_2(dropout(relu(w_1(LN(x))))))
+    MT_TRY(mt_ln_fwd_run(M, d, b.xp, pf + P.ln2_a, pf + P.ln2_b, 1e-6f, b.v, lp, st));
+    g = fwd_gemm(M, dff, d, b.v, wptr(c, params, params_lp, base + P.w_1), b.hid, !lp);
+    g.epi.bias = pf + P.b_1;
+    g.epi.act = MT_ACT_RELU;
+    g.epi.drop = mt_make_drop(p, c.seed, mt_enc_site(c.stack_id, l, MT_SITE_FFN_H));
+    MT_TRY(mt_gemm_run(c.dtype, g, st));
+    g = fwd_gemm(M, d, dff, b.hid, wptr(c, params, params_lp, base + P.w_2), b.x_out, true);
+    g.epi.bias = pf + P.b_2;
+    g.epi.drop = mt_make_drop(p, c.seed, mt_enc_site(c.stack_id, l, MT_SITE_SUB1));
+    g.epi.residual = b.xp; g.epi.ldr = d;
+    MT_TRY(mt_gemm_run(c.dtype, g, st));
+    xin = b.x_out;
+  }
+  return mt_ln_fwd_run(M, d, xin, params + P.lnf_a, params + P.lnf_b, 1e-6f, y, lp && !c.y_f32, st);
+}
+
+int mt_encoder_bwd(const MtEncoderCfg* cfg, const float* params, const void* params_lp, const float* x, const float* mask,
+                   const void* dy, float* dx, float* grads, void* ws, size_t ws_bytes, void* stream) {
+  MT_TRY(check_cfg(cfg));
+  const MtEncoderCfg& c = *cfg;
+  if (!c.training) return MT_ERR_ARG;
+  if (!params || !x || !dy || !dx || !grads || !ws || (c.dtype == MT_BF16 && !params_lp)) return MT_ERR_ARG;
+  EncWs w;
+  MT_TRY(carve(c, ws, w));
+  if (ws_bytes < w.bytes) return MT_ERR_WS;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int M = c.B * c.T, d = c.d, dff = c.dff;
+  const bool lp = c.dtype == MT_BF16;
+  const EncParams P = enc_params(d, dff, c.n_layers);
+  const float p = c.p_drop;
+  const float keep_scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+  MT_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * P.total, st));
+
+  float* g_cur = w.g0;
+  float* g_nxt = w.g1;
+  const float* x_last = w.L[c.n_layers - 1].x_out;
+  MT_TRY(mt_ln_bwd_run(M, d, x_last, params + P.lnf_a, 1e-6f, dy, lp && !c.y_f32, nullptr, g_cur, grads + P.lnf_a, grads + P.lnf_b, st));
+
+  for (int l = c.n_layers - 1; l >= 0; --l) {
+    const size_t base = P.layer_stride * l;
+    const float* pf = params + base;
+    float* gf = grads + base;
+    LayerBufs& b = w.L[l];
+    const float* x_l = l == 0 ? x : w.L[l - 1].x_out;
+    // ---- FFN sublayer: x_out = xp + drop(w_2 hid + b_2) -------------------------------------------
+    MT_TRY(mt_drop_grad_run(M, d, g_cur, w.dact, lp, mt_make_drop(p, c.seed, mt_enc_site(c.stack_id, l, MT_SITE_SUB1)), st));
+    MT_TRY(mt_gemm_run(c.dtype, wgrad_gemm(M, d, dff, w.dact, d, b.hid, dff, gf + P.w_2, dff), st));
+    MT_TRY(mt_colsum_run(lp, M, d, w.dact, d, gf + P.b_2, 1, st));
+    GemmDesc g = dgrad_gemm(M, d, dff, w.dact, wptr(c, params, params_lp, base + P.w_2), w.dhid, !lp);
+    g.epi.gate = b.hid; g.epi.ldg = dff; g.epi.gate_scale = keep_scale;   // relu' and the hidden dropout mask in one test
+    MT_TRY(mt_gemm_run(c.dtype, g, st));
+    MT_TRY(mt_gemm_run(c.dtype, wgrad_gemm(M, dff, d, w.dhid, dff, b.v, d, gf + P.w_1, d), st));
+    MT_TRY(mt_colsum_run(lp, M, dff, w.dhid, dff, gf + P.b_1, 1, st));
+    MT_TRY(mt_gemm_run(c.dtype, dgrad_gemm(M, dff, d, w.dhid, wptr(c, params, params_lp, base + P.w_1), w.dact2, !lp), st));
+    MT_TRY(mt_ln_bwd_run(M, d, b.xp, pf + P.ln2_a, 1e-6f, w.dact2, lp, g_cur, g_nxt, gf + P.ln2_a, gf + P.ln2_b, st));
+    // ---- attention sublayer: xp = x + drop(att w_o + b_o) -----------------------------------------
+    MT_TRY(mt_drop_grad_run(M, d, g_nxt, w.dact, lp, mt_make_drop(p, c.seed, mt_enc_site(c.stack_id, l, MT_SITE_SUB0)), st));
+    MT_TRY(mt_gemm_run(c.dtype, wgrad_gemm(M, d, d, w.dact, d, b.att, d, gf + P.w_o, d), st));
+    MT_TRY(mt_colsum_run(lp, M, d, w.dact, d, gf + P.b_o, 1, st));
+    MT_TRY(mt_gemm_run(c.dtype, dgrad_gemm(M, d, d, w.dact, wptr(c, params, params_lp, base + P.w_o), w.dact2, !lp), st));
+    MT_TRY(mt_attn_bwd_run(c.dtype, c.B, c.T, d, c.h, b.qkv, mask, b.att, b.lse, w.dact2, w.dqkv,
+                           mt_make_drop(p, c.seed, mt_enc_site(c.stack_id, l, MT_SITE_ATTN_P)), w.Dws, st));
+    MT_TRY(mt_gemm_run(c.dtype, wgrad_gemm(M, 3 * d, d, w.dqkv, 3 * d, b.u, d, gf + P.w_qkv, d), st));
+    MT_TRY(mt_colsum_run(lp, M, 3 * d, w.dqkv, 3 * d, gf + P.b_qkv, 1, st));
+    MT_TRY(mt_gemm_run(c.dtype, dgrad_gemm(M, 3 * d, d, w.dqkv, wptr(c, params, params_lp, base + P.w_qkv), w.dact, !lp), st));
+    float* out = l == 0 ? dx : g_cur;
+    MT_TRY(mt_ln_bwd_run(M, d, x_l, pf + P.ln1_a, 1e-6f, w.dact, lp, g_nxt, out, gf + P.ln1_a, gf + P.ln1_b, st));
+    // g_cur now holds dL/dx_l (g_nxt is free again)
+  }
+  return MT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Linear.  W is always the fp32 master weight [N,K]; in bf16 mode it is cast (and K-padded to a multiple of 8
+// so rows are 16-byte aligned for TMA) into the workspace on every call -- these matrices are tiny.
+// ------------------------------------------------------------------------------------------------------
+static inline int lin_kp(int dtype, int K) { return dtype == MT_BF16 ? (K + 7) / 8 * 8 : K; }
+static inline bool lin_stage_x(int dtype, int K, int x_f32, float in_drop_p) {
+  return in_drop_p > 0.f || (dtype == MT_BF16 && ((K % 8) != 0 || x_f32));
+}
+
+size_t mt_linear_ws_bytes(int dtype, int M, int N, int K, int x_f32, float in_drop_p) {
+  const int Kp = lin_kp(dtype, K);
+  WsCarver k(nullptr);
+  if (lin_stage_x(dtype, K, x_f32, in_drop_p)) k.take_bytes((size_t)M * Kp * mt_esize(dtype));
+  if (dtype == MT_BF16) k.take_bytes((size_t)N * Kp * 2);
+  k.take_bytes(256);
+  return k.total();
+}
+
+int mt_linear_fwd(int dtype, int M, int N, int K, const void* x, int x_f32, const float* W, const float* b, void* y, int y_f32,
+                  int act, const float* rowmask, float in_drop_p, uint64_t seed, uint32_t site, void* ws, size_t ws_bytes,
+                  void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || !x || !W || !y) return MT_ERR_ARG;
+  if (dtype != MT_F32 && dtype != MT_BF16) return MT_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool lp = dtype == MT_BF16;
+  if (!ws || ws_bytes < mt_linear_ws_bytes(dtype, M, N, K, x_f32, in_drop_p)) return MT_ERR_WS;
+  const int Kp = lin_kp(dtype, K);
+  WsCarver k(ws);
+  const void* xa = x; const void* wa = W;
+  if (lin_stage_x(dtype, K, x_f32, in_drop_p)) {
+    void* xs = k.take_bytes((size_t)M * Kp * mt_esize(dtype));
+    MT_TRY(mt_cast2d_run(x, lp && !x_f32, K, xs, lp, Kp, M, K, mt_make_drop(in_drop_p, seed, site), st));
+    xa = xs;
+  }
+  if (lp) {
+    void* wsb = k.take_bytes((size_t)N * Kp * 2);
+    MT_TRY(mt_cast2d_run(W, false, K, wsb, true, Kp, N, K, mt_make_drop(0.f, 0, 0), st));
+    wa = wsb;
+  }
+  GemmDesc g = fwd_gemm(M, N, Kp, xa, wa, y, !lp || y_f32);
+  g.epi.bias = b; g.epi.act = act; g.epi.rowmask = rowmask;
+  return mt_gemm_run(dtype, g, st);
+}
+
+size_t mt_linear_bwd_ws_bytes(int dtype, int M, int N, int K, int x_f32, float in_drop_p) {
+  WsCarver k(nullptr);
+  k.take_bytes((size_t)M * N * mt_esize(dtype));
+  k.take_bytes((size_t)M * K * mt_esize(dtype));
+  if (dtype == MT_BF16) k.take_bytes((size_t)N * K * 2);
+  return k.total();
+}
+
+/* y: the forward output (needed when act != NONE), stored fp32 when y_f32 else `dtype`; dy likewise per dy_f32. */
+int mt_linear_bwd(int dtype, int M, int N, int K, const void* x, int x_f32, const float* W, const void* y, int y_f32, const void* dy,
+                  int dy_f32, int act, const float* rowmask, float in_drop_p, uint64_t seed, uint32_t site, void* dx, float* dW,
+                  float* db, void* ws, size_t ws_bytes, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || !x || !W || !dy || !dW) return MT_ERR_ARG;
+  if (dtype != MT_F32 && dtype != MT_BF16) return MT_ERR_ARG;
+  if (act != MT_ACT_NONE && !y) return MT_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool lp = dtype == MT_BF16;
+  if (!ws || ws_bytes < mt_linear_bwd_ws_bytes(dtype, M, N, K, x_f32, in_drop_p)) return MT_ERR_WS;
+  WsCarver k(ws);
+  void* dz = k.take_bytes((size_t)M * N * mt_esize(dtype));
+  void* xs = k.take_bytes((size_t)M * K * mt_esize(dtype));
+  void* wl = lp ? k.take_bytes((size_t)N * K * 2) : nullptr;
+  const bool dy_lp = lp && !dy_f32;
+  const void* dzp = dy;
+  if (act != MT_ACT_NONE || rowmask != nullptr || (lp && dy_f32)) {
+    MT_TRY(mt_act_bwd_run(M, N, dy, dy_lp, y, lp && !y_f32, act, rowmask, dz, lp, st));
+    dzp = dz;
+  }
+  const void* xa = x;
+  if (in_drop_p > 0.f || (lp && x_f32)) {
+    MT_TRY(mt_cast2d_run(x, lp && !x_f32, K, xs, lp, K, M, K, mt_make_drop(in_drop_p, seed, site), st));
+    xa = xs;
+  }
+  MT_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)N * K, st));
+  MT_TRY(mt_gemm_run(dtype, wgrad_gemm(M, N, K, dzp, N, xa, K, dW, K), st));
+  if (db) MT_TRY(mt_colsum_run(lp, M, N, dzp, N, db, 0, st));
+  if (dx) {
+    const void* wa = W;
+    if (lp) {
+      MT_TRY(mt_cast2d_run(W, false, K, wl, true, K, N, K, mt_make_drop(0.f, 0, 0), st));
+      wa = wl;
+    }
+    GemmDesc g = dgrad_gemm(M, N, K, dzp, wa, dx, !lp);
+    g.epi.drop = mt_make_drop(in_drop_p, seed, site);      // element index m*K + k == the forward's input-dropout index
+    MT_TRY(mt_gemm_run(dtype, g, st));
+  }
+  return MT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,49 @@
+// GEMM dispatcher: picks the tcgen05 engine (bf16 operands, shapes inside its envelope) or the FFMA engine.
+#include "mt_gemm.cuh"
+
+#ifndef MT_NO_TC
+#define MT_HAVE_TC 1
+#else
+#define MT_HAVE_TC 0
+#endif
+
+static int g_force_simt = 0;
+
+int mt_gemm_run(int dtype, const GemmDesc& g, cudaStream_t st) {
+#if MT_HAVE_TC
+  if (dtype == MT_BF16 && !g_force_simt && mt_gemm_tc_supported(g)) return mt_gemm_tc_run(g, st);
+#endif
+  return mt_gemm_simt_run(dtype, g, st);
+}
+
+extern "C" {
+
+int mt_gemm(int dtype, int M, int N, int K, const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor, void* C,
+            int ldc, int c_f32, const float* bias, int act, int split_k_atomic, void* stream) {
+  GemmDesc g;
+  g.M = M; g.N = N; g.K = K;
+  g.A = A; g.lda = lda; g.a_kmajor = a_kmajor != 0;
+  g.B = B; g.ldb = ldb; g.b_kmajor = b_kmajor != 0;
+  g.C = C; g.ldc = ldc; g.c_f32 = (c_f32 != 0) || dtype == MT_F32;
+  g.split_k = split_k_atomic > 1 ? split_k_atomic : 1;
+  g.epi.bias = bias; g.epi.act = act;
+  return mt_gemm_run(dtype, g, (cudaStream_t)stream);
+}
+
+int mt_gemm_engine(int dtype, int M, int N, int K, int a_kmajor, int b_kmajor) {
+#if MT_HAVE_TC
+  if (dtype != MT_BF16 || g_force_simt) return 0;
+  GemmDesc g;
+  g.M = M; g.N = N; g.K = K; g.a_kmajor = a_kmajor != 0; g.b_kmajor = b_kmajor != 0;
+  g.lda = a_kmajor ? K : M; g.ldb = b_kmajor ? K : N; g.ldc = N;
+  g.A = g.B = (const void*)0x1000; g.C = (void*)0x1000;
+  return mt_gemm_tc_supported(g) ? 1 : 0;
+#else
+  return 0;
+#endif
+}
+
+/* test hook: route every GEMM through the FFMA engine (used to A/B the tensor-core engine) */
+int mt_gemm_force_simt(int on) { int old = g_force_simt; g_force_simt = on; return old; }
+
+}  // extern "C"

@@ -1,0 +1,43 @@
+// Internal (non-ABI) entry points shared between the translation units of libmt_b200.
+#pragma once
+#include "mt_gemm.cuh"
+
+// ---- workspace carving: the same sequence of take() calls yields the same offsets in fwd and bwd ------
+struct WsCarver {
+  char* base;
+  size_t off = 0;
+  explicit WsCarver(void* p) : base(reinterpret_cast<char*>(p)) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = mt_align_up(off, 256);
+    T* r = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return r;
+  }
+  void* take_bytes(size_t nbytes) { return take<char>(nbytes); }
+  size_t total() const { return mt_align_up(off, 256); }
+};
+
+static inline size_t mt_esize(int dtype) { return dtype == MT_BF16 ? 2 : 4; }
+
+// ---- element-wise / row-wise kernels (mt_elementwise.cu) ---------------------------------------------
+int mt_ln_fwd_run(int M, int d, const float* x, const float* a, const float* b, float eps, void* y, bool y_bf16, cudaStream_t st);
+int mt_ln_bwd_run(int M, int d, const float* x, const float* a, float eps, const void* dy, bool dy_bf16, const float* dres,
+                  float* dx, float* da, float* db, cudaStream_t st);
+// out[M,N] (bf16 or f32) = g[M,N] (f32) * dropout_factor(site, m*N+n)      (gradient through an output dropout)
+int mt_drop_grad_run(int M, int N, const float* g, void* out, bool out_bf16, DropCfg drop, cudaStream_t st);
+// 2-D cast with zero padding / optional input dropout: dst[r, c] = c < cols ? src[r*lds + c] * drop(r*cols + c) : 0
+int mt_cast2d_run(const void* src, bool src_bf16, int lds, void* dst, bool dst_bf16, int ldd, int rows, int cols, DropCfg drop,
+                  cudaStream_t st);
+// dz = dy * act'(y) * rowmask   (y = post-activation output)
+int mt_act_bwd_run(int M, int N, const void* dy, bool dy_bf16, const void* y, bool y_bf16, int act, const float* rowmask, void* dz,
+                   bool dz_bf16, cudaStream_t st);
+// batched transposes for the MFN forward weight pack: dst[c*ldd + r] = src[r*C + c]
+struct TransposeJob { const float* src; void* dst; int R, C, ldd; };
+int mt_transpose_pack_run(const TransposeJob* jobs, int n_jobs, bool dst_bf16, cudaStream_t st);
+
+// ---- attention (mt_attention.cu) ---------------------------------------------------------------------
+int mt_attn_fwd_run(int dtype, int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop,
+                    cudaStream_t st);
+int mt_attn_bwd_run(int dtype, int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse,
+                    const void* dout, void* dqkv, DropCfg drop, float* Dws, cudaStream_t st);

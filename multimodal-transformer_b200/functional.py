@@ -1,0 +1,501 @@
+"""torch.autograd glue over the C ABI: every forward/backward here is ONE call into libmt_b200.so.
+
+Compute dtype is a process-wide switch (`set_compute_dtype`): 'fp32' (FFMA GEMMs, the 1e-5 parity mode, default)
+or 'bf16' (bf16 GEMM operands, fp32 accumulation / residual stream / statistics / recurrent state).
+Dropout is counter-based: keep = hash(seed, site, element) >= p * 2^32 (csrc/mt_common.cuh), one fresh seed per
+forward call drawn from `next_seed()`; `manual_seed` makes runs reproducible and lets tests inject known masks.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ACT_NONE, ACT_RELU, ACT_TANH, MT_BF16, MT_F32, check, lib, ptr, require, stream
+
+_state = {'dtype': MT_F32, 'seed': 0x5EED0000, 'counter': 0, 'fixed_seed': None}
+
+
+def set_compute_dtype(name):
+    name = {'float32': 'fp32', 'bfloat16': 'bf16'}.get(str(name).replace('torch.', ''), name)
+    if name not in ('fp32', 'bf16'):
+        raise ValueError("compute dtype must be 'fp32' or 'bf16'")
+    _state['dtype'] = MT_F32 if name == 'fp32' else MT_BF16
+
+
+def get_compute_dtype():
+    return 'fp32' if _state['dtype'] == MT_F32 else 'bf16'
+
+
+def manual_seed(seed):
+    _state['seed'] = int(seed) & 0xFFFFFFFFFFFFFFFF
+    _state['counter'] = 0
+
+
+def fix_seed(seed):
+    """Every subsequent forward uses exactly this dropout seed (tests); None restores the counter."""
+    _state['fixed_seed'] = None if seed is None else int(seed)
+
+
+def next_seed():
+    if _state['fixed_seed'] is not None:
+        return _state['fixed_seed']
+    _state['counter'] += 1
+    return (_state['seed'] * 0x9E3779B97F4A7C15 + _state['counter']) & 0xFFFFFFFFFFFFFFFF
+
+
+def _adt():
+    return torch.float32 if _state['dtype'] == MT_F32 else torch.bfloat16
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def mask2d(mask, B, T, device):
+    """[B,T,1] / [B,T] mask of any dtype -> contiguous fp32 [B,T] (None stays None)."""
+    if mask is None:
+        return None
+    m = mask.reshape(B, T)
+    if m.dtype != torch.float32:
+        m = m.float()
+    if m.device != device:
+        raise RuntimeError('mask must live on the same device as the inputs')
+    return m.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = act(dropout_in(x) W^T + b) [* rowmask]   (nn.Linear call sites; mt_linear_fwd / mt_linear_bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, act, rowmask, in_drop_p, out_f32):
+        dt = _state['dtype']
+        shp = x.shape
+        K = shp[-1]
+        N = W.shape[0]
+        x2 = x.reshape(-1, K)
+        x2 = require(x2 if x2.is_contiguous() else x2.contiguous(), name='x')
+        if x2.dtype not in (torch.float32, torch.bfloat16) or (dt == MT_F32 and x2.dtype != torch.float32):
+            raise RuntimeError(f'Linear input dtype {x2.dtype} does not match compute dtype {get_compute_dtype()}')
+        require(W, torch.float32, 'weight')
+        if b is not None:
+            require(b, torch.float32, 'bias')
+        _lib.check_device(x2.device.index)
+        M = x2.shape[0]
+        x_f32 = int(x2.dtype == torch.float32)
+        y_f32 = int(out_f32 or dt == MT_F32)
+        y = torch.empty((M, N), dtype=torch.float32 if y_f32 else torch.bfloat16, device=x2.device)
+        seed = next_seed() if in_drop_p > 0 else 0
+        L = lib()
+        ws = _ws(L.mt_linear_ws_bytes(dt, M, N, K, x_f32, in_drop_p), x2.device)
+        check(L.mt_linear_fwd(dt, M, N, K, ptr(x2), x_f32, ptr(W), ptr(b), ptr(y), y_f32, act, ptr(rowmask), in_drop_p, seed, 0x5000,
+                              ptr(ws), ws.numel(), stream()))
+        ctx.save_for_backward(x2, W, y if act != ACT_NONE else None, rowmask)
+        ctx.meta = (dt, M, N, K, x_f32, y_f32, act, in_drop_p, seed, shp, b is not None)
+        return y.view(*shp[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, W, y, rowmask = ctx.saved_tensors
+        dt, M, N, K, x_f32, y_f32, act, in_drop_p, seed, shp, has_b = ctx.meta
+        dy2 = dy.reshape(M, N)
+        dy2 = require(dy2 if dy2.is_contiguous() else dy2.contiguous(), name='dy')
+        dy_f32 = int(dy2.dtype == torch.float32)
+        need_dx = ctx.needs_input_grad[0]
+        dx = torch.empty((M, K), dtype=torch.float32 if dt == MT_F32 else torch.bfloat16, device=dy2.device) if need_dx else None
+        dW = torch.empty_like(W)
+        db = torch.empty(N, dtype=torch.float32, device=dy2.device) if has_b else None
+        L = lib()
+        ws = _ws(L.mt_linear_bwd_ws_bytes(dt, M, N, K, x_f32, in_drop_p), dy2.device)
+        check(L.mt_linear_bwd(dt, M, N, K, ptr(x2), x_f32, ptr(W), ptr(y), y_f32, ptr(dy2), dy_f32, act, ptr(rowmask), in_drop_p, seed,
+                              0x5000, ptr(dx), ptr(dW), ptr(db), ptr(ws), ws.numel(), stream()))
+        if dx is not None:
+            dx = dx.view(shp)
+            if x_f32 and dx.dtype != torch.float32:
+                dx = dx.float()
+        return dx, dW, db, None, None, None, None
+
+
+def linear(x, W, b=None, act=ACT_NONE, rowmask=None, in_drop_p=0.0, out_f32=False):
+    return LinearFn.apply(x, W, b, act, rowmask, float(in_drop_p), out_f32)
+
+
+# ---------------------------------------------------------------------------------------------------------
+class LayerNormFn(torch.autograd.Function):
+    """a_2 * (x - mean) / (std_unbiased + eps) + b_2   (LayerNorm.forward MFT/multiTransformer.py:88-91)."""
+
+    @staticmethod
+    def forward(ctx, x, a, b, eps):
+        d = x.shape[-1]
+        x2 = x.reshape(-1, d)
+        x2 = require(x2 if x2.is_contiguous() else x2.contiguous(), torch.float32, 'x')
+        require(a, torch.float32, 'a_2'); require(b, torch.float32, 'b_2')
+        _lib.check_device(x2.device.index)
+        y = torch.empty_like(x2)
+        check(lib().mt_layernorm_fwd(MT_F32, x2.shape[0], d, ptr(x2), ptr(a), ptr(b), eps, ptr(y), 1, stream()))
+        ctx.save_for_backward(x2, a)
+        ctx.eps = eps
+        ctx.shp = x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, a = ctx.saved_tensors
+        d = x2.shape[1]
+        dy2 = dy.reshape(-1, d)
+        dy2 = require(dy2 if dy2.is_contiguous() else dy2.contiguous(), torch.float32, 'dy')
+        dx = torch.empty_like(x2)
+        da = torch.zeros_like(a); db = torch.zeros_like(a)
+        check(lib().mt_layernorm_bwd(MT_F32, x2.shape[0], d, ptr(x2), ptr(a), ctx.eps, ptr(dy2), 1, None, ptr(dx), ptr(da), ptr(db),
+                                     stream()))
+        return dx.view(ctx.shp), da, db, None
+
+
+def layer_norm(x, a, b, eps=1e-6):
+    return LayerNormFn.apply(x, a, b, float(eps))
+
+
+# ---------------------------------------------------------------------------------------------------------
+class AttentionFn(torch.autograd.Function):
+    """Fused scores / query-row mask / softmax / dropout / PV / head merge on packed qkv [B,T,3d]."""
+
+    @staticmethod
+    def forward(ctx, qkv, mask, h, p_drop):
+        dt = _state['dtype']
+        B, T, d3 = qkv.shape
+        d = d3 // 3
+        require(qkv, _adt(), 'qkv')
+        _lib.check_device(qkv.device.index)
+        m = mask2d(mask, B, T, qkv.device)
+        out = torch.empty((B, T, d), dtype=qkv.dtype, device=qkv.device)
+        lse = torch.empty((B, h, T), dtype=torch.float32, device=qkv.device)
+        seed = next_seed() if p_drop > 0 else 0
+        check(lib().mt_attention_fwd(dt, B, T, d, h, ptr(qkv), ptr(m), ptr(out), ptr(lse), p_drop, seed, 0, stream()))
+        ctx.save_for_backward(qkv, m, out, lse)
+        ctx.meta = (dt, B, T, d, h, p_drop, seed)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, m, out, lse = ctx.saved_tensors
+        dt, B, T, d, h, p_drop, seed = ctx.meta
+        dout = require(dout if dout.is_contiguous() else dout.contiguous(), qkv.dtype, 'dout')
+        dqkv = torch.empty_like(qkv)
+        L = lib()
+        ws = _ws(L.mt_attention_bwd_ws_bytes(B, T, h), qkv.device)
+        check(L.mt_attention_bwd(dt, B, T, d, h, ptr(qkv), ptr(m), ptr(out), ptr(lse), ptr(dout), ptr(dqkv), p_drop, seed, 0, ptr(ws),
+                                 ws.numel(), stream()))
+        return dqkv, None, None, None
+
+
+def attention_packed(qkv, mask, h, p_drop=0.0):
+    return AttentionFn.apply(qkv, mask, h, float(p_drop))
+
+
+def attention_probs(qkv, mask, h):
+    B, T, d3 = qkv.shape
+    require(qkv, _adt(), 'qkv')
+    m = mask2d(mask, B, T, qkv.device)
+    probs = torch.empty((B, h, T, T), dtype=torch.float32, device=qkv.device)
+    check(lib().mt_attention_probs(_state['dtype'], B, T, d3 // 3, h, ptr(qkv), ptr(m), ptr(probs), stream()))
+    return probs
+
+
+# ---------------------------------------------------------------------------------------------------------
+class ResidualDropoutFn(torch.autograd.Function):
+    """x + dropout(y)   (SublayerConnection, stand-alone path); fp32."""
+
+    @staticmethod
+    def forward(ctx, x, y, p):
+        require(x, torch.float32, 'x')
+        y = require(y if y.is_contiguous() else y.contiguous(), torch.float32, 'y')
+        out = torch.empty_like(x)
+        seed = next_seed() if p > 0 else 0
+        check(lib().mt_residual_dropout_fwd(ptr(x), ptr(y), ptr(out), x.numel(), p, seed, 0x6000, stream()))
+        ctx.meta = (p, seed)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        p, seed = ctx.meta
+        g = require(g if g.is_contiguous() else g.contiguous(), torch.float32, 'g')
+        if p <= 0:
+            return g, g, None
+        gy = torch.empty_like(g)
+        check(lib().mt_dropout_bwd(ptr(g), ptr(gy), g.numel(), p, seed, 0x6000, stream()))
+        return g, gy, None
+
+
+def residual_dropout(x, y, p):
+    if not x.is_contiguous():
+        x = x.contiguous()
+    return ResidualDropoutFn.apply(x, y, float(p))
+
+
+# ---------------------------------------------------------------------------------------------------------
+class Arena:
+    """A flat fp32 buffer that OWNS the storage of a list of nn.Parameters (each parameter's .data is a view),
+    in the canonical order of a C-ABI parameter block, plus its bf16 shadow."""
+
+    def __init__(self, params):
+        self.params = list(params)
+        self.sizes = [p.numel() for p in self.params]
+        self.offsets = []
+        o = 0
+        for n in self.sizes:
+            self.offsets.append(o)
+            o += n
+        self.total = o
+        self.flat = None
+        self.lp = None
+        self._lp_key = None
+
+    def bound(self):
+        f = self.flat
+        if f is None:
+            return False
+        base = f.data_ptr()
+        for p, o in zip(self.params, self.offsets):
+            if p.data_ptr() != base + 4 * o or p.dtype != torch.float32:
+                return False
+        return True
+
+    def bind(self):
+        """(Re)point every parameter at the flat buffer; values are preserved.  Cheap no-op when already bound."""
+        if self.bound():
+            return self.flat
+        dev = self.params[0].device
+        if dev.type != 'cuda':
+            raise RuntimeError('parameters must be on a CUDA device (no CPU fallback); call .to("cuda") first')
+        flat = torch.empty(self.total, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, o, n in zip(self.params, self.offsets, self.sizes):
+                v = flat[o:o + n].view(p.shape)
+                v.copy_(p.data)
+                p.data = v
+        self.flat = flat
+        self.lp = None
+        self._lp_key = None
+        return flat
+
+    def shadow(self):
+        """bf16 copy of the arena, refreshed when any parameter changed (version counters)."""
+        key = sum(p._version for p in self.params)
+        if self.lp is None or self.lp.device != self.flat.device:
+            self.lp = torch.empty(self.total, dtype=torch.bfloat16, device=self.flat.device)
+            self._lp_key = None
+        if key != self._lp_key:
+            check(lib().mt_cast_f32_to_bf16(ptr(self.flat), ptr(self.lp), self.total, stream()))
+            self._lp_key = key
+        return self.lp
+
+    def grad_views(self, gflat):
+        return [gflat[o:o + n].view(p.shape) for p, o, n in zip(self.params, self.offsets, self.sizes)]
+
+    def flat_grad(self):
+        """The flat gradient buffer if every .grad is still the view handed out by backward, else None."""
+        g0 = self.params[0].grad
+        if g0 is None:
+            return None
+        base = g0.data_ptr()
+        for p, o in zip(self.params, self.offsets):
+            if p.grad is None or p.grad.data_ptr() != base + 4 * o:
+                return None
+        return g0.as_strided((self.total,), (1,), g0.storage_offset())
+
+
+# ---------------------------------------------------------------------------------------------------------
+class EncoderFn(torch.autograd.Function):
+    """Whole encoder stack (N pre-norm layers + final LayerNorm) in one C call each way."""
+
+    @staticmethod
+    def forward(ctx, x, mask, arena, cfgd, *params):
+        dt = _state['dtype']
+        B, T, d = x.shape
+        x = require(x if x.is_contiguous() else x.contiguous(), torch.float32, 'encoder input (fp32 residual stream)')
+        _lib.check_device(x.device.index)
+        flat = arena.bind()
+        lp = arena.shadow() if dt == MT_BF16 else None
+        m = mask2d(mask, B, T, x.device)
+        need_grad = any(ctx.needs_input_grad)
+        p_drop = float(cfgd['p_drop'])
+        cfg = _lib.MtEncoderCfg(B, T, d, cfgd['h'], cfgd['dff'], cfgd['n_layers'], dt, int(need_grad), p_drop,
+                                next_seed() if p_drop > 0 else 0, cfgd['stack_id'], int(cfgd.get('y_f32', dt == MT_F32)))
+        L = lib()
+        nws = L.mt_encoder_ws_bytes(ctypes.byref(cfg))
+        if nws == 0:
+            raise RuntimeError(f'unsupported encoder configuration {cfgd} for input {tuple(x.shape)}')
+        ws = _ws(nws, x.device)
+        y = torch.empty((B, T, d), dtype=torch.float32 if cfg.y_f32 else torch.bfloat16, device=x.device)
+        check(L.mt_encoder_fwd(ctypes.byref(cfg), ptr(flat), ptr(lp), ptr(x), ptr(m), ptr(y), ptr(ws), ws.numel(), stream()))
+        if need_grad:
+            ctx.save_for_backward(x, m, ws, flat, lp)
+            ctx.cfg = cfg
+            ctx.arena = arena
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, m, ws, flat, lp = ctx.saved_tensors
+        cfg = ctx.cfg
+        dy = dy if dy.is_contiguous() else dy.contiguous()
+        want = torch.float32 if cfg.y_f32 else torch.bfloat16
+        if dy.dtype != want:
+            dy = dy.to(want)
+        dx = torch.empty_like(x)
+        g = torch.empty(ctx.arena.total, dtype=torch.float32, device=x.device)
+        check(lib().mt_encoder_bwd(ctypes.byref(cfg), ptr(flat), ptr(lp), ptr(x), ptr(m), ptr(dy), ptr(dx), ptr(g), ptr(ws), ws.numel(),
+                                   stream()))
+        return (dx, None, None, None, *ctx.arena.grad_views(g))
+
+
+def encoder_stack(x, mask, arena, cfgd):
+    return EncoderFn.apply(x, mask, arena, cfgd, *arena.params)
+
+
+# ---------------------------------------------------------------------------------------------------------
+class MfnFn(torch.autograd.Function):
+    """MFN.forward (hoisted input projections + persistent recurrence kernel + head) and its BPTT."""
+
+    @staticmethod
+    def forward(ctx, mask, arena, cfgd, t_major, n_mods, *rest):
+        dt = _state['dtype']
+        xs = list(rest[:n_mods])
+        adt = _adt()
+        xs = [require(x if x.is_contiguous() else x.contiguous(), adt, 'MFN input') for x in xs]
+        if t_major:
+            T, B = xs[0].shape[0], xs[0].shape[1]
+        else:
+            B, T = xs[0].shape[0], xs[0].shape[1]
+        dev = xs[0].device
+        _lib.check_device(dev.index)
+        flat = arena.bind()
+        lp = arena.shadow() if dt == MT_BF16 else None
+        m = mask2d(mask, B, T, dev)
+        need_grad = any(ctx.needs_input_grad)
+        cfg = _lib.MtMfnCfg()
+        cfg.B, cfg.T, cfg.n_mods = B, T, n_mods
+        for i in range(n_mods):
+            cfg.in_dim[i] = xs[i].shape[2]
+            cfg.hid[i] = cfgd['hid'][i]
+        cfg.mem_dim, cfg.h_att1, cfg.h_att2, cfg.h_gamma, cfg.h_out = cfgd['mem'], cfgd['a1'], cfgd['a2'], cfgd['g'], cfgd['o']
+        cfg.dtype, cfg.training = dt, int(need_grad)
+        cfg.p_gamma, cfg.p_out = float(cfgd['p_gamma']), float(cfgd['p_out'])
+        cfg.seed = next_seed() if (cfg.p_gamma > 0 or cfg.p_out > 0) else 0
+        L = lib()
+        nws = L.mt_mfn_ws_bytes(ctypes.byref(cfg))
+        if nws == 0 or L.mt_mfn_param_count(ctypes.byref(cfg)) != arena.total:
+            raise RuntimeError('unsupported MFN configuration')
+        ws = _ws(nws, dev)
+        xp = (ctypes.c_void_p * n_mods)(*[x.data_ptr() for x in xs])
+        if t_major:
+            sb = (ctypes.c_int64 * n_mods)(*[x.shape[2] for x in xs])
+            st = (ctypes.c_int64 * n_mods)(*[x.shape[2] * B for x in xs])
+        else:
+            sb = (ctypes.c_int64 * n_mods)(*[x.shape[2] * T for x in xs])
+            st = (ctypes.c_int64 * n_mods)(*[x.shape[2] for x in xs])
+        out = torch.empty((B, T), dtype=torch.float32, device=dev)
+        Hs = sum(cfgd['hid'])
+        h_last = torch.empty((B, Hs), dtype=torch.float32, device=dev)
+        c_last = torch.empty((B, Hs), dtype=torch.float32, device=dev)
+        mem_last = torch.empty((B, cfgd['mem']), dtype=torch.float32, device=dev)
+        check(L.mt_mfn_fwd(ctypes.byref(cfg), ptr(flat), ptr(lp), xp, sb, st, ptr(m), ptr(out), ptr(h_last), ptr(c_last), ptr(mem_last),
+                           ptr(ws), ws.numel(), stream()))
+        if need_grad:
+            ctx.save_for_backward(m, ws, flat, lp, *xs)
+            ctx.cfg, ctx.arena, ctx.t_major, ctx.n_mods = cfg, arena, t_major, n_mods
+            ctx.x_need = ctx.needs_input_grad[5:5 + n_mods]
+        ctx.mark_non_differentiable(h_last, c_last, mem_last)
+        return out.unsqueeze(-1), h_last, c_last, mem_last
+
+    @staticmethod
+    def backward(ctx, dout, *_unused):
+        m, ws, flat, lp, *xs = ctx.saved_tensors
+        cfg, n_mods = ctx.cfg, ctx.n_mods
+        B, T = cfg.B, cfg.T
+        dev = xs[0].device
+        dout = dout.reshape(B, T)
+        dout = dout if dout.is_contiguous() else dout.contiguous()
+        if dout.dtype != torch.float32:
+            dout = dout.float()
+        dxs = [torch.empty_like(x) if need else None for x, need in zip(xs, ctx.x_need)]
+        dxp = (ctypes.c_void_p * n_mods)(*[None if d is None else d.data_ptr() for d in dxs])
+        xp = (ctypes.c_void_p * n_mods)(*[x.data_ptr() for x in xs])
+        if ctx.t_major:
+            sb = (ctypes.c_int64 * n_mods)(*[x.shape[2] for x in xs])
+            st = (ctypes.c_int64 * n_mods)(*[x.shape[2] * B for x in xs])
+        else:
+            sb = (ctypes.c_int64 * n_mods)(*[x.shape[2] * T for x in xs])
+            st = (ctypes.c_int64 * n_mods)(*[x.shape[2] for x in xs])
+        g = torch.empty(ctx.arena.total, dtype=torch.float32, device=dev)
+        check(lib().mt_mfn_bwd(ctypes.byref(cfg), ptr(flat), ptr(lp), xp, sb, st, ptr(m), ptr(dout), dxp, ptr(g), ptr(ws), ws.numel(),
+                               stream()))
+        return (None, None, None, None, None, *dxs, *ctx.arena.grad_views(g))
+
+
+def mfn_forward(xs, mask, arena, cfgd, t_major):
+    return MfnFn.apply(mask, arena, cfgd, bool(t_major), len(xs), *xs, *arena.params)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def mse_loss_sum_normalised(pred, target, norm):
+    """sum((pred-target)^2) / norm and d/dpred, in one kernel (MFT/train.py:135-139).  Returns (loss[1], dpred)."""
+    p = require(pred if pred.is_contiguous() else pred.contiguous(), torch.float32, 'pred')
+    t = require(target if target.is_contiguous() else target.contiguous(), torch.float32, 'target')
+    loss = torch.zeros(1, dtype=torch.float32, device=p.device)
+    dp = torch.empty_like(p)
+    check(lib().mt_mse_loss_fwd_bwd(ptr(p), ptr(t), p.numel(), 1.0 / float(norm), ptr(loss), ptr(dp), stream()))
+    return loss, dp
+
+
+def adam_step_flat(p, g, m, v, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    for t_, nm in ((p, 'p'), (g, 'g'), (m, 'm'), (v, 'v')):
+        require(t_, torch.float32, nm)
+    check(lib().mt_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr, betas[0], betas[1], eps, weight_decay, int(step), stream()))
+
+
+# ---------------------------------------------------------------------------------------------------------
+class LstmHeadFn(torch.autograd.Function):
+    """Step-wise LSTM decoder with output feedback + MLP head (SFT/multiTransformer.py:465-483) in one persistent
+    kernel each way."""
+
+    @staticmethod
+    def forward(ctx, enc, mask, arena, E, Hd, *params):
+        dt = _state['dtype']
+        B, T, _ = enc.shape
+        enc = require(enc if enc.is_contiguous() else enc.contiguous(), _adt(), 'decoder input')
+        _lib.check_device(enc.device.index)
+        flat = arena.bind()
+        lp = arena.shadow() if dt == MT_BF16 else None
+        m = mask2d(mask, B, T, enc.device)
+        need_grad = any(ctx.needs_input_grad)
+        cfg = _lib.MtLstmHeadCfg(B, T, E, Hd, dt, int(need_grad))
+        L = lib()
+        nws = L.mt_lstm_head_ws_bytes(ctypes.byref(cfg))
+        if nws == 0 or L.mt_lstm_head_param_count(ctypes.byref(cfg)) != arena.total:
+            raise RuntimeError('unsupported LSTM decoder configuration')
+        ws = _ws(nws, enc.device)
+        out = torch.empty((B, T), dtype=torch.float32, device=enc.device)
+        check(L.mt_lstm_head_fwd(ctypes.byref(cfg), ptr(flat), ptr(lp), ptr(enc), ptr(m), ptr(out), ptr(ws), ws.numel(), stream()))
+        if need_grad:
+            ctx.save_for_backward(enc, m, ws, flat, lp)
+            ctx.cfg, ctx.arena = cfg, arena
+        return out.unsqueeze(-1)
+
+    @staticmethod
+    def backward(ctx, dout):
+        enc, m, ws, flat, lp = ctx.saved_tensors
+        cfg = ctx.cfg
+        dout = dout.reshape(cfg.B, cfg.T)
+        dout = dout if dout.is_contiguous() else dout.contiguous()
+        if dout.dtype != torch.float32:
+            dout = dout.float()
+        denc = torch.empty_like(enc) if ctx.needs_input_grad[0] else None
+        g = torch.empty(ctx.arena.total, dtype=torch.float32, device=enc.device)
+        check(lib().mt_lstm_head_bwd(ctypes.byref(cfg), ptr(flat), ptr(lp), ptr(enc), ptr(m), ptr(dout), ptr(denc), ptr(g), ptr(ws),
+                                     ws.numel(), stream()))
+        return (denc, None, None, None, None, *ctx.arena.grad_views(g))
+
+
+def lstm_head(enc, mask, arena, E, Hd):
+    return LstmHeadFn.apply(enc, mask, arena, E, Hd, *arena.params)

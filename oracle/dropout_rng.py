@@ -38,7 +38,8 @@ def rand_u32(seed, site, idx):
 
 
 def threshold(p):
-    t = int(float(p) * 4294967296.0)
+    import numpy as np
+    t = int(float(np.float32(p)) * 4294967296.0)      # the kernels receive p as a C float
     return max(0, min(t, _M32))
 
 

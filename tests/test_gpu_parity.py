@@ -1,0 +1,407 @@
+"""GPU (B200): the CUDA path -- called through the drop-in modules, i.e. through the C ABI -- against the CPU oracle
+on identical weights and inputs, and against the golden outputs of the imported reference (tests/golden).
+
+Tolerances: fp32 mode 1e-5 relative (north star); bf16 mode 2e-2 absolute on valence."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import multimodal_transformer_b200 as mtb
+from multimodal_transformer_b200 import _lib, functional as K
+from oracle import fill, mt_oracle as O
+from oracle.dropout_rng import Dropper
+from tests import util
+
+pytestmark = pytest.mark.gpu
+MODS = ['acoustic', 'image', 'linguistic']
+DEV = 'cuda:0'
+
+
+def t(x):
+    return torch.from_numpy(x)
+
+
+@pytest.fixture(autouse=True)
+def _fp32_mode():
+    mtb.set_compute_dtype('fp32')
+    mtb.fix_seed(None)
+    yield
+    mtb.set_compute_dtype('fp32')
+    mtb.fix_seed(None)
+
+
+def relerr(got, want):
+    got = got.detach().double().cpu(); want = want.detach().double().cpu()
+    return ((got - want).abs().max() / want.abs().max().clamp_min(1e-30)).item()
+
+
+def assert_close(got, want, tol, name=''):
+    e = relerr(got, want)
+    assert e <= tol, f'{name}: max err / max |ref| = {e:.3e} > {tol}'
+
+
+# ---- GEMM engine --------------------------------------------------------------------------------------
+@pytest.mark.parametrize('M,N,K', [(64, 64, 16), (37, 45, 19), (300, 130, 88), (128, 768, 256), (5, 1, 64)])
+@pytest.mark.parametrize('akm,bkm', [(1, 1), (1, 0), (0, 0), (0, 1)])
+def test_gemm_fp32_layouts(M, N, K, akm, bkm):
+    g = torch.Generator().manual_seed(M * 7 + N)
+    A = torch.randn(M, K, generator=g); B = torch.randn(N, K, generator=g); bias = torch.randn(N, generator=g)
+    want = A.double() @ B.double().t() + bias.double()
+    Ad = (A if akm else A.t().contiguous()).to(DEV); Bd = (B if bkm else B.t().contiguous()).to(DEV)
+    C = torch.empty(M, N, device=DEV)
+    _lib.check(_lib.lib().mt_gemm(0, M, N, K, _lib.ptr(Ad), K if akm else M, akm, _lib.ptr(Bd), K if bkm else N, bkm, _lib.ptr(C), N, 1,
+                                  _lib.ptr(bias.to(DEV)), 0, 1, None))
+    torch.cuda.synchronize()
+    assert_close(C, want, 2e-6)
+
+
+def test_gemm_split_k_atomic_and_bf16_operands():
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 96, 80, 1000
+    A = torch.randn(K, M, generator=g); B = torch.randn(K, N, generator=g)          # both mn-major (wgrad form)
+    want = A.double().t() @ B.double()
+    C = torch.zeros(M, N, device=DEV)
+    _lib.check(_lib.lib().mt_gemm(0, M, N, K, _lib.ptr(A.to(DEV)), M, 0, _lib.ptr(B.to(DEV)), N, 0, _lib.ptr(C), N, 1, None, 0, 8, None))
+    assert_close(C, want, 2e-6)
+    Ab, Bb = A.to(DEV).bfloat16(), B.to(DEV).bfloat16()
+    C2 = torch.zeros(M, N, device=DEV)
+    _lib.check(_lib.lib().mt_gemm(1, M, N, K, _lib.ptr(Ab), M, 0, _lib.ptr(Bb), N, 0, _lib.ptr(C2), N, 1, None, 0, 8, None))
+    assert_close(C2, Ab.double().t() @ Bb.double(), 1e-5)
+
+
+# ---- LayerNorm ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('d', [128, 256, 512])
+def test_layernorm_fwd_bwd(d):
+    g = torch.Generator().manual_seed(d)
+    x = (torch.randn(37, 5, d, generator=g) * 3 + 0.7)
+    a = torch.randn(d, generator=g); b = torch.randn(d, generator=g); dy = torch.randn(37, 5, d, generator=g)
+    xr = x.double().requires_grad_(True); ar = a.double().requires_grad_(True); br = b.double().requires_grad_(True)
+    yr = O.layer_norm(xr, ar, br); yr.backward(dy.double())
+    ln = mtb.LayerNorm(d).to(DEV)
+    with torch.no_grad():
+        ln.a_2.copy_(a); ln.b_2.copy_(b)
+    xd = x.to(DEV).requires_grad_(True)
+    y = ln(xd); y.backward(dy.to(DEV))
+    assert_close(y, yr, 1e-5, 'y'); assert_close(xd.grad, xr.grad, 1e-5, 'dx')
+    assert_close(ln.a_2.grad, ar.grad, 1e-5, 'da'); assert_close(ln.b_2.grad, br.grad, 1e-5, 'db')
+
+
+def test_layernorm_golden():
+    gold = util.gold('ln')
+    sd = util.filled_sd({'a_2': (256,), 'b_2': (256,)}, 3)
+    ln = mtb.LayerNorm(256).to(DEV); ln.load_state_dict(sd)
+    x = t(fill.fill_array('ln_x', (3, 5, 256), 3)) * 20.0 + 1.5
+    np.testing.assert_allclose(ln(x.to(DEV)).cpu().numpy(), gold['y'], rtol=1e-5, atol=1e-5)
+
+
+# ---- attention core ------------------------------------------------------------------------------------------
+def _attn_ref(qkv, mask, h, drop=None, p=0.0, site=0):
+    B, T, d3 = qkv.shape; d = d3 // 3; dk = d // h
+    q, k, v = [qkv[..., i * d:(i + 1) * d].view(B, T, h, dk).transpose(1, 2) for i in range(3)]
+    out, pa = O.attention(q, k, v, mask.view(B, 1, T, 1), drop or Dropper(None), p, site)
+    return out.transpose(1, 2).reshape(B, T, d), pa
+
+
+@pytest.mark.parametrize('B,T,d,h,p', [(3, 7, 256, 8, 0.0), (2, 150, 256, 8, 0.0), (2, 70, 128, 8, 0.0), (2, 33, 512, 8, 0.0),
+                                       (2, 40, 256, 8, 0.1)])
+def test_attention_fwd_bwd(B, T, d, h, p):
+    g = torch.Generator().manual_seed(B * 100 + T)
+    qkv = torch.randn(B, T, 3 * d, generator=g) * 0.7
+    mask = torch.ones(B, T); mask[-1, T // 2:] = 0
+    dout = torch.randn(B, T, d, generator=g)
+    seed = 991
+    qr = qkv.double().requires_grad_(True)
+    outr, par = _attn_ref(qr, mask.double(), h, Dropper(seed) if p > 0 else None, p, 0)
+    outr.backward(dout.double())
+    mtb.fix_seed(seed)
+    qd = qkv.to(DEV).requires_grad_(True)
+    out = K.attention_packed(qd, mask.to(DEV), h, p)
+    out.backward(dout.to(DEV))
+    assert_close(out, outr, 1e-5, 'out'); assert_close(qd.grad, qr.grad, 2e-5, 'dqkv')
+    if p == 0:
+        probs = K.attention_probs(qkv.to(DEV), mask.to(DEV), h)
+        assert_close(probs, par, 1e-5, 'p_attn')
+        assert torch.allclose(probs[-1, :, T // 2:, :], torch.full_like(probs[-1, :, T // 2:, :], 1.0 / T), rtol=1e-6)   # trap A.1
+
+
+def test_mha_golden_and_attn_attribute():
+    gold = util.gold('mha')
+    shapes = {f'linears.{i}.{p}': s for i in range(4) for p, s in (('weight', (256, 256)), ('bias', (256,)))}
+    m = mtb.MultiHeadedAttention(8, 256).to(DEV).eval(); m.load_state_dict(util.filled_sd(shapes, 4))
+    inputs, mask, _, _ = fill.make_batch(3, 7, {'x': 256}, 4)
+    x = t(inputs['x']).to(DEV)
+    y = m(x, x, x, t(mask).to(DEV))
+    np.testing.assert_allclose(y.cpu().numpy(), gold['y'], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(m.attn.cpu().numpy(), gold['attn'], rtol=2e-5, atol=1e-7)
+
+
+# ---- encoder stack -------------------------------------------------------------------------------------------
+def _enc_shapes(N):
+    return util.strip_prefix(util.mods_shapes('MFT.MultiTransformer', N), 'transformer_acoustic.')
+
+
+def _make_encoder(N, seed, d=256, dff=128, h=8, p=0.1):
+    from multimodal_transformer_b200.multiTransformer import _make_encoder as mk
+    enc = mk(d, dff, h, p, N).to(DEV)
+    sd = util.filled_sd(_enc_shapes(N), seed)
+    enc.load_state_dict(sd)
+    return enc, sd
+
+
+@pytest.mark.parametrize('train', [False, True])
+def test_encoder_fwd_bwd_vs_oracle(train):
+    N = 2
+    enc, sd = _make_encoder(N, 5)
+    inputs, mask, _, _ = fill.make_batch(3, 9, {'x': 256}, 5)
+    w = t(fill.fill_array('enc_w', (3, 9, 256), 5))
+    seed = 4242
+    sdr = {'e.' + k: v.double().requires_grad_(True) for k, v in sd.items()}
+    xr = t(inputs['x']).double().requires_grad_(True)
+    yr = O.encoder(sdr, 'e', xr, t(mask).double(), N, 8, Dropper(seed if train else None), 0.1, stack=0)
+    (yr * w.double()).sum().backward()
+    enc.train(train); mtb.fix_seed(seed)
+    xd = t(inputs['x']).to(DEV).requires_grad_(True)
+    y = enc(xd, t(mask).to(DEV))
+    (y * w.to(DEV)).sum().backward()
+    assert_close(y, yr, 1e-5, 'y'); assert_close(xd.grad, xr.grad, 2e-5, 'dx')
+    for k, p in enc.named_parameters():
+        ref = sdr['e.' + k].grad
+        scale = max(ref.abs().max().item(), 1e-6 * yr.abs().max().item())
+        err = (p.grad.double().cpu() - ref).abs().max().item()
+        assert err <= 3e-5 * scale + 1e-7, f'{k}: {err:.3e} vs scale {scale:.3e}'
+    if not train:
+        gold = util.gold('encoder')
+        np.testing.assert_allclose(y.detach().cpu().numpy(), gold['y'], rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(xd.grad.cpu().numpy(), gold['dx'], rtol=1e-4, atol=1e-5)
+
+
+def test_encoder_standalone_layers_equal_fused_stack():
+    enc, _ = _make_encoder(2, 15)
+    enc.eval()
+    inputs, mask, _, _ = fill.make_batch(2, 11, {'x': 256}, 15)
+    x = t(inputs['x']).to(DEV); m = t(mask).to(DEV)
+    fused = enc(x, m)
+    y = x
+    for layer in enc.layers:
+        y = layer(y, m)
+    assert_close(enc.norm(y), fused, 1e-5)
+
+
+# ---- MFN -----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('train,B,T', [(False, 3, 6), (True, 5, 7), (False, 9, 3)])
+def test_mfn_fwd_bwd_vs_oracle(train, B, T):
+    shapes = util.strip_prefix(util.mods_shapes('MFT.MultiTransformer'), 'mfn.')
+    sd = util.filled_sd(shapes, 6)
+    mfn = mtb.MFN(MODS, {m: 256 for m in MODS}, 1).to(DEV); mfn.load_state_dict(sd); mfn.train(train)
+    inputs, _, _, _ = fill.make_batch(B, T, {m: 256 for m in MODS}, 6)
+    w = t(fill.fill_array('mfn_w', (B, T, 1), 6))
+    seed = 77
+    sdr = {'mfn.' + k: v.double().requires_grad_(True) for k, v in sd.items()}
+    xr = {m: t(inputs[m]).double().permute(1, 0, 2).contiguous().requires_grad_(True) for m in MODS}
+    yr, hr, cr, memr = O.mfn(sdr, 'mfn', xr, MODS, Dropper(seed if train else None), return_states=True)
+    (yr * w.double()).sum().backward()
+    mtb.fix_seed(seed)
+    xd = {m: t(inputs[m]).permute(1, 0, 2).contiguous().to(DEV).requires_grad_(True) for m in MODS}
+    y = mfn(xd)                                   # the reference's [T,B,D] interface
+    (y * w.to(DEV)).sum().backward()
+    assert y.shape == (B, T, 1)
+    assert_close(y, yr, 1e-5, 'y')
+    for m in MODS:
+        assert_close(xd[m].grad, xr[m].grad, 3e-5, 'dx_' + m)
+        assert_close(mfn.h[m], hr[m], 1e-5, 'h'); assert_close(mfn.c[m], cr[m], 1e-5, 'c')
+    assert_close(mfn.mem, memr, 1e-5, 'mem')
+    for k, p in mfn.named_parameters():
+        assert_close(p.grad, sdr['mfn.' + k].grad, 5e-5, k)
+    if not train and (B, T) == (3, 6):
+        np.testing.assert_allclose(y.detach().cpu().numpy(), util.gold('mfn')['y'], rtol=2e-5, atol=2e-6)
+
+
+# ---- whole models against the golden outputs of the imported reference ---------------------------------------
+def _check_grads(model, gold, rtol):
+    n = 0
+    for k, p in model.named_parameters():
+        if 'grad:' + k in gold:
+            util.assert_digest_close(util.grad_digest(p.grad), gold['grad:' + k], rtol, k); n += 1
+        else:
+            assert p.grad is None and k.startswith(('attn', 'ff')), k
+    return n
+
+
+@pytest.mark.parametrize('name,N', [('mft_n2', 2), ('mft_n6', 6)])
+def test_mft_golden(name, N):
+    gold = util.gold(name); m = util.meta()[name]
+    model = mtb.MultiTransformer(MODS, m['dims'], N=N).eval()
+    model.load_state_dict(util.filled_sd(util.mods_shapes('MFT.MultiTransformer', N), m['seed']))
+    inputs, mask, target, lengths = fill.make_batch(m['B'], m['T'], m['dims'], m['seed'])
+    pred = model({k: t(v).to(DEV) for k, v in inputs.items()}, t(mask).to(DEV), lengths)
+    np.testing.assert_allclose(pred.detach().cpu().numpy(), gold['pred'], rtol=1e-4, atol=2e-6)
+    assert pred.shape == (m['B'], m['T'], 1)
+    assert (pred.detach().cpu()[t(mask) == 0] == 0).all()
+    if 'loss' in gold:
+        loss = ((pred - t(target).to(DEV)) ** 2).sum() / sum(lengths)
+        loss.backward()
+        assert abs(loss.item() - float(gold['loss'])) <= 2e-5 * abs(float(gold['loss']))
+        assert _check_grads(model, gold, 3e-4) > 20
+
+
+def test_b3_golden():
+    gold = util.gold('b3'); m = util.meta()['b3']
+    model = mtb.B3MultiTransformer(MODS, m['dims']).eval()
+    model.load_state_dict(util.filled_sd(util.mods_shapes('B3.MultiTransformer'), m['seed']))
+    inputs, mask, target, lengths = fill.make_batch(m['B'], m['T'], m['dims'], m['seed'])
+    pred = model({k: t(v).to(DEV) for k, v in inputs.items()}, t(mask).to(DEV), lengths)
+    np.testing.assert_allclose(pred.detach().cpu().numpy(), gold['pred'], rtol=1e-4, atol=2e-6)
+    loss = ((pred - t(target).to(DEV)) ** 2).sum() / sum(lengths)
+    loss.backward()
+    _check_grads(model, gold, 3e-4)
+
+
+@pytest.mark.parametrize('name,cls,fin', [('unifull', 'UniFullTransformer', 556), ('uni', 'UniTransformer', 300)])
+def test_uni_golden(name, cls, fin):
+    gold = util.gold(name); m = util.meta()[name]
+    model = getattr(mtb, cls)(fin, N=2).eval()
+    model.load_state_dict(util.filled_sd(util.mods_shapes('MFT.' + cls, 2), m['seed']))
+    inputs, mask, target, lengths = fill.make_batch(3, 8, {'x': fin}, m['seed'])
+    pred = model(t(inputs['x']).to(DEV), t(mask).to(DEV), lengths)
+    np.testing.assert_allclose(pred.detach().cpu().numpy(), gold['pred'], rtol=1e-4, atol=2e-6)
+    loss = ((pred - t(target).to(DEV)) ** 2).sum() / sum(lengths)
+    loss.backward()
+    _check_grads(model, gold, 3e-4)
+
+
+def test_sft_golden():
+    gold = util.gold('sft'); m = util.meta()['sft']
+    body = mtb.NLPTransformer(512, N=2).eval()
+    sd = util.filled_sd({**{'Transformer.' + k: v for k, v in util.mods_shapes('SFT.NLPTransformer', 2).items()},
+                         'fusionLayer.weight': (512, 556), 'fusionLayer.bias': (512,)}, 10)
+    body.load_state_dict({k[len('Transformer.'):]: v for k, v in sd.items() if k.startswith('Transformer.')})
+    fw = sd['fusionLayer.weight'].to(DEV).requires_grad_(True); fb = sd['fusionLayer.bias'].to(DEV).requires_grad_(True)
+    inputs, mask, target, lengths = fill.make_batch(3, 8, m['dims'], 10)
+    fused = mtb.fusion_layer([t(inputs['image']).to(DEV), t(inputs['linguistic']).to(DEV)], fw, fb)
+    pred = body(fused, t(mask).to(DEV), lengths)
+    np.testing.assert_allclose(pred.detach().cpu().numpy(), gold['pred'], rtol=1e-4, atol=2e-6)
+    loss = ((pred - t(target).to(DEV)) ** 2).sum() / sum(lengths)
+    loss.backward()
+    assert abs(loss.item() - float(gold['loss'])) <= 2e-5 * abs(float(gold['loss']))
+    for k, p in body.named_parameters():
+        util.assert_digest_close(util.grad_digest(p.grad), gold['grad:Transformer.' + k], 3e-4, k)
+    util.assert_digest_close(util.grad_digest(fw.grad), gold['grad:fusionLayer.weight'], 3e-4, 'fusion.w')
+    util.assert_digest_close(util.grad_digest(fb.grad), gold['grad:fusionLayer.bias'], 3e-4, 'fusion.b')
+
+
+# ---- train mode with injected masks, bf16 mode, DP-style invariants --------------------------------------------
+def test_mft_train_mode_matches_oracle_with_same_masks():
+    N, B, T, seed = 2, 4, 12, 31337
+    dims = {'acoustic': 88, 'image': 256, 'linguistic': 300}
+    sd = util.filled_sd(util.mods_shapes('MFT.MultiTransformer', N), 21)
+    model = mtb.MultiTransformer(MODS, dims, N=N).train(); model.load_state_dict(sd)
+    inputs, mask, target, lengths = fill.make_batch(B, T, dims, 21)
+    sdr = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    predr = O.multi_transformer(sdr, '', {k: t(v).double() for k, v in inputs.items()}, t(mask).double(), MODS, N=N, drop=Dropper(seed))
+    lossr = O.train_loss(predr, t(target).double(), lengths); lossr.backward()
+    mtb.fix_seed(seed)
+    pred = model({k: t(v).to(DEV) for k, v in inputs.items()}, t(mask).to(DEV), lengths)
+    loss = ((pred - t(target).to(DEV)) ** 2).sum() / sum(lengths); loss.backward()
+    assert_close(pred, predr, 2e-5, 'pred')
+    # dropout really happened: eval-mode output differs
+    model.eval()
+    pe = model({k: t(v).to(DEV) for k, v in inputs.items()}, t(mask).to(DEV), lengths)
+    assert relerr(pe, predr) > 1e-3
+    for k, p in model.named_parameters():
+        if sdr[k].grad is None:
+            assert p.grad is None
+            continue
+        assert_close(p.grad, sdr[k].grad, 2e-4, k)
+
+
+def test_bf16_mode_valence_within_2e2_and_ccc():
+    from oracle.ccc import eval_ccc
+    N, B, T = 6, 6, 40
+    dims = {'acoustic': 88, 'image': 256, 'linguistic': 300}
+    sd = util.filled_sd(util.mods_shapes('MFT.MultiTransformer', N), 33)
+    model = mtb.MultiTransformer(MODS, dims, N=N).eval(); model.load_state_dict(sd)
+    inputs, mask, _, lengths = fill.make_batch(B, T, dims, 33)
+    with torch.no_grad():
+        predr = O.multi_transformer(sd, '', {k: t(v) for k, v in inputs.items()}, t(mask), MODS, N=N)
+        p32 = model({k: t(v).to(DEV) for k, v in inputs.items()}, t(mask).to(DEV), lengths).cpu()
+        mtb.set_compute_dtype('bf16')
+        p16 = model({k: t(v).to(DEV) for k, v in inputs.items()}, t(mask).to(DEV), lengths).cpu()
+    assert (p32 - predr).abs().max() <= 1e-5 * predr.abs().max() + 1e-7
+    assert (p16 - predr).abs().max() <= 2e-2, (p16 - predr).abs().max()
+    # CCC against a synthetic target correlated with the reference prediction (CCC parity needs signal)
+    rs = np.random.RandomState(0)
+    for b, l in enumerate(lengths):
+        ref = predr[b, :l, 0].numpy()
+        target = 0.5 + 8.0 * (ref - ref.mean()) + 0.02 * rs.standard_normal(l)
+        c_ref, c_16 = eval_ccc(target, ref), eval_ccc(target, p16[b, :l, 0].numpy())
+        assert abs(c_ref - c_16) < 1.5e-3, (b, c_ref, c_16)
+
+
+def test_bf16_train_step_runs_and_grads_are_close():
+    N, B, T = 2, 4, 16
+    dims = {'acoustic': 88, 'image': 256, 'linguistic': 300}
+    sd = util.filled_sd(util.mods_shapes('MFT.MultiTransformer', N), 41)
+    inputs, mask, target, lengths = fill.make_batch(B, T, dims, 41)
+    grads = {}
+    for mode in ('fp32', 'bf16'):
+        mtb.set_compute_dtype(mode)
+        model = mtb.MultiTransformer(MODS, dims, N=N).eval(); model.load_state_dict(sd)
+        pred = model({k: t(v).to(DEV) for k, v in inputs.items()}, t(mask).to(DEV), lengths)
+        (((pred - t(target).to(DEV)) ** 2).sum() / sum(lengths)).backward()
+        grads[mode] = {k: p.grad.detach().cpu() for k, p in model.named_parameters() if p.grad is not None}
+    bad = []
+    for k, g in grads['fp32'].items():
+        cos = torch.nn.functional.cosine_similarity(g.flatten(), grads['bf16'][k].flatten(), dim=0).item()
+        if cos < 0.98 and g.norm() > 1e-6:
+            bad.append((k, cos))
+    assert not bad, bad[:5]
+
+
+def test_batch_sharding_is_exact():
+    """Data parallelism over narratives: running halves of the batch separately gives the same predictions (no
+    cross-sample op on the path) and gradients that sum to the full-batch gradient."""
+    N, B, T = 2, 6, 10
+    dims = {'acoustic': 88, 'image': 256, 'linguistic': 300}
+    sd = util.filled_sd(util.mods_shapes('MFT.MultiTransformer', N), 51)
+    inputs, mask, target, lengths = fill.make_batch(B, T, dims, 51)
+    norm = float(sum(lengths))
+
+    def run(sl):
+        model = mtb.MultiTransformer(MODS, dims, N=N).eval(); model.load_state_dict(sd)
+        pred = model({k: t(v[sl]).to(DEV) for k, v in inputs.items()}, t(mask[sl]).to(DEV), lengths[sl])
+        (((pred - t(target[sl]).to(DEV)) ** 2).sum() / norm).backward()
+        return pred.detach().cpu(), {k: p.grad.detach().cpu() for k, p in model.named_parameters() if p.grad is not None}
+
+    pf, gf = run(slice(0, B))
+    p0, g0 = run(slice(0, B, 2)); p1, g1 = run(slice(1, B, 2))
+    assert torch.equal(pf[0::2], p0) and torch.equal(pf[1::2], p1)
+    for k in gf:
+        assert_close(g0[k] + g1[k], gf[k], 1e-4, k)
+
+
+def test_fused_loss_and_adam_match_torch():
+    g = torch.Generator().manual_seed(0)
+    pred = torch.rand(7, 13, 1, generator=g).to(DEV); target = torch.rand(7, 13, 1, generator=g).to(DEV)
+    loss, dp = K.mse_loss_sum_normalised(pred, target, 55.0)
+    pr = pred.clone().requires_grad_(True)
+    lr_ = ((pr - target) ** 2).sum() / 55.0; lr_.backward()
+    assert abs(loss.item() - lr_.item()) < 1e-6 * abs(lr_.item()) + 1e-9
+    assert_close(dp, pr.grad, 1e-6)
+    p = torch.randn(1000, generator=g).to(DEV); p_ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p_ref], lr=1e-4, weight_decay=1e-4)
+    m = torch.zeros_like(p); v = torch.zeros_like(p)
+    for step in range(1, 4):
+        grad = torch.randn(1000, generator=g).to(DEV)
+        p_ref.grad = grad.clone(); opt.step()
+        K.adam_step_flat(p, grad, m, v, step, 1e-4, (0.9, 0.999), 1e-8, 1e-4)
+    assert_close(p, p_ref, 1e-6)
+
+
+def test_launch_counter_counts_our_kernels():
+    L = _lib.lib()
+    before = L.mt_launch_count()
+    ln = mtb.LayerNorm(256).to(DEV)
+    ln(torch.randn(8, 256, device=DEV))
+    assert L.mt_launch_count() == before + 1
