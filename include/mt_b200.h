@@ -49,6 +49,14 @@ int mt_version(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches). */
 uint64_t mt_launch_count(void);
 
+/* Per-launch profiler (bench.py's roofline leg): after mt_prof_start every kernel launch of the library is followed
+ * by an event record on its stream; record i's duration is the time since record i-1 (kernels of one stream
+ * serialise).  name = "<host launch function>:<line>"; flops / bytes = the ALGORITHMIC work of that launch as annotated
+ * at the launch site (0 when not annotated).  mt_prof_stop returns the number of records. */
+int mt_prof_start(int max_records, void* stream);
+int mt_prof_stop(void);
+int mt_prof_get(int i, char* name, int name_cap, float* ms, double* flops, double* bytes);
+
 /* ---------------------------------------------------------------------------------------------------
  * Linear:  y[M,N] = act(x[M,K] W[N,K]^T + b) [* rowmask[m]]        replaces nn.Linear call sites
  * MFT/multiTransformer.py:270,296 (embed), SFT/models.py:137-138 (fusionLayer + tanh), SFT/multiTransformer.py:

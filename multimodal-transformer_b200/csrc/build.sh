@@ -18,5 +18,5 @@ done
 for p in "${pids[@]}"; do wait $p; done
 OBJS=""
 for f in $SRCS; do [ -f "$f" ] && OBJS="$OBJS build/${f%.cu}.o"; done
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $OUT $OBJS -lcuda
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $OUT $OBJS
 echo "built $OUT"

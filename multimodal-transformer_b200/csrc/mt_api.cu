@@ -1,4 +1,6 @@
 // Library-level entry points of libmt_b200: error text, device probe, launch counter.
+#include <stdlib.h>
+
 #include "mt_common.cuh"
 
 char g_mt_cuda_err[512] = "";
@@ -9,7 +11,63 @@ int mt_set_cuda_error(cudaError_t e, const char* file, int line) {
   return MT_ERR_CUDA;
 }
 
+// ---- per-launch profiler ---------------------------------------------------------------------------------
+int g_mt_prof_on = 0;
+namespace {
+struct ProfRec { char name[48]; double flops, bytes; cudaEvent_t ev; };
+ProfRec* g_recs = nullptr;
+int g_prof_cap = 0, g_prof_n = 0;
+cudaEvent_t g_prof_base = nullptr;
+double g_pending_flops = 0.0, g_pending_bytes = 0.0;
+}  // namespace
+
+void mt_prof_work(double flops, double bytes) {
+  if (!g_mt_prof_on) return;
+  g_pending_flops = flops;
+  g_pending_bytes = bytes;
+}
+
+void mt_prof_record(const char* func, int line, cudaStream_t st) {
+  if (g_prof_n >= g_prof_cap) { g_pending_flops = g_pending_bytes = 0.0; return; }
+  ProfRec& r = g_recs[g_prof_n];
+  snprintf(r.name, sizeof(r.name), "%s:%d", func, line);
+  r.flops = g_pending_flops; r.bytes = g_pending_bytes;
+  g_pending_flops = g_pending_bytes = 0.0;
+  if (cudaEventRecord(r.ev, st) == cudaSuccess) ++g_prof_n;
+}
+
 extern "C" {
+
+int mt_prof_start(int max_records, void* stream) {
+  if (max_records <= 0) return MT_ERR_ARG;
+  if (max_records > g_prof_cap) {
+    ProfRec* n = (ProfRec*)realloc(g_recs, sizeof(ProfRec) * (size_t)max_records);
+    if (!n) return MT_ERR_ARG;
+    g_recs = n;
+    for (int i = g_prof_cap; i < max_records; ++i) MT_CUDA(cudaEventCreate(&g_recs[i].ev));
+    g_prof_cap = max_records;
+  }
+  if (!g_prof_base) MT_CUDA(cudaEventCreate(&g_prof_base));
+  g_prof_n = 0;
+  MT_CUDA(cudaEventRecord(g_prof_base, (cudaStream_t)stream));
+  g_mt_prof_on = 1;
+  return MT_OK;
+}
+
+int mt_prof_stop(void) {
+  g_mt_prof_on = 0;
+  return g_prof_n;
+}
+
+int mt_prof_get(int i, char* name, int name_cap, float* ms, double* flops, double* bytes) {
+  if (i < 0 || i >= g_prof_n || !name || name_cap <= 0 || !ms) return MT_ERR_ARG;
+  MT_CUDA(cudaEventSynchronize(g_recs[i].ev));
+  MT_CUDA(cudaEventElapsedTime(ms, i == 0 ? g_prof_base : g_recs[i - 1].ev, g_recs[i].ev));
+  snprintf(name, (size_t)name_cap, "%s", g_recs[i].name);
+  if (flops) *flops = g_recs[i].flops;
+  if (bytes) *bytes = g_recs[i].bytes;
+  return MT_OK;
+}
 
 const char* mt_error_string(int code) {
   switch (code) {

@@ -280,6 +280,7 @@ int fwd_dispatch(int B, int T_, int d, int h, const void* qkv, const float* mask
   const int dk = d / h;
   const float scale = 1.0f / sqrtf((float)dk);
   dim3 grid((T_ + AT_THREADS - 1) / AT_THREADS, h, B);
+  mt_prof_work(4.0 * B * (double)T_ * T_ * d, (double)B * T_ * d * 4.0 * sizeof(T));
   switch (dk) {
     case 16: attn_fwd_kernel<T, 16><<<grid, AT_THREADS, 0, st>>>(B, T_, d, h, (const T*)qkv, mask, (T*)out, lse, drop, scale); break;
     case 32: attn_fwd_kernel<T, 32><<<grid, AT_THREADS, 0, st>>>(B, T_, d, h, (const T*)qkv, mask, (T*)out, lse, drop, scale); break;
@@ -297,9 +298,11 @@ int bwd_dispatch(int B, int T_, int d, int h, const void* qkv, const float* mask
   const float scale = 1.0f / sqrtf((float)dk);
   dim3 grid((T_ + AT_THREADS - 1) / AT_THREADS, h, B);
 #define MT_BWD(DK)                                                                                                             \
+  mt_prof_work(6.0 * B * (double)T_ * T_ * d, (double)B * T_ * d * 6.0 * sizeof(T));                                            \
   attn_bwd_dq_kernel<T, DK><<<grid, AT_THREADS, 0, st>>>(B, T_, d, h, (const T*)qkv, mask, (const T*)out, lse, (const T*)dout,  \
                                                          (T*)dqkv, Dws, drop, scale);                                          \
   MT_LAUNCH_CHECK();                                                                                                           \
+  mt_prof_work(8.0 * B * (double)T_ * T_ * d, (double)B * T_ * d * 6.0 * sizeof(T));                                            \
   attn_bwd_dkv_kernel<T, DK><<<grid, AT_THREADS, 0, st>>>(B, T_, d, h, (const T*)qkv, mask, lse, (const T*)dout, (T*)dqkv, Dws, \
                                                           drop, scale);                                                        \
   MT_LAUNCH_CHECK();
@@ -364,7 +367,7 @@ int mt_attention_probs(int dtype, int B, int T, int d, int h, const void* qkv, c
   int grid = (int)((rows + 7) / 8);
   if (dtype == MT_BF16) attn_probs_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>(B, T, d, h, dk, (const bf16*)qkv, mask, probs, scale);
   else attn_probs_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(B, T, d, h, dk, (const float*)qkv, mask, probs, scale);
-  MT_LAUNCH_CHECK();
+  MT_LAUNCH_CHECK_S((cudaStream_t)stream);
   return MT_OK;
 }
 

@@ -18,12 +18,18 @@ int mt_set_cuda_error(cudaError_t e, const char* file, int line);
     cudaError_t _e = (x);                                                 \
     if (_e != cudaSuccess) return mt_set_cuda_error(_e, __FILE__, __LINE__); \
   } while (0)
-#define MT_LAUNCH_CHECK()                                                 \
+// per-launch profiling (mt_prof_* in include/mt_b200.h): when enabled, an event is recorded after every launch
+extern int g_mt_prof_on;
+void mt_prof_record(const char* func, int line, cudaStream_t st);
+void mt_prof_work(double flops, double bytes);      // annotates the NEXT launch with its algorithmic work
+#define MT_LAUNCH_CHECK_S(stream_)                                        \
   do {                                                                    \
     ++g_mt_launches;                                                      \
     cudaError_t _e = cudaGetLastError();                                  \
     if (_e != cudaSuccess) return mt_set_cuda_error(_e, __FILE__, __LINE__); \
+    if (g_mt_prof_on) mt_prof_record(__func__, __LINE__, (stream_));      \
   } while (0)
+#define MT_LAUNCH_CHECK() MT_LAUNCH_CHECK_S(st)
 #define MT_TRY(x)            \
   do {                       \
     int _r = (x);            \

@@ -248,6 +248,7 @@ template <typename TY>
 int ln_fwd_dispatch(int M, int d, const float* x, const float* a, const float* b, float eps, TY* y, cudaStream_t st) {
   int grid = (M + LN_WARPS - 1) / LN_WARPS;
   if (grid > 148 * 8) grid = 148 * 8;
+  mt_prof_work(0.0, (double)M * d * (4.0 + sizeof(TY)));
   switch (d / 128) {
     case 1: ln_fwd_kernel<TY, 1><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, b, eps, y); break;
     case 2: ln_fwd_kernel<TY, 2><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, b, eps, y); break;
@@ -266,6 +267,7 @@ int ln_bwd_dispatch(int M, int d, const float* x, const float* a, float eps, con
                     float* db, cudaStream_t st) {
   int grid = (M + LN_WARPS - 1) / LN_WARPS;
   if (grid > 148 * 4) grid = 148 * 4;
+  mt_prof_work(0.0, (double)M * d * (8.0 + sizeof(TY) + (dres ? 4.0 : 0.0)));
   switch (d / 128) {
     case 1: ln_bwd_kernel<TY, 1><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, eps, dy, dres, dx, da, db); break;
     case 2: ln_bwd_kernel<TY, 2><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, eps, dy, dres, dx, da, db); break;
@@ -297,6 +299,7 @@ int mt_ln_bwd_run(int M, int d, const float* x, const float* a, float eps, const
 int mt_drop_grad_run(int M, int N, const float* g, void* out, bool out_bf16, DropCfg drop, cudaStream_t st) {
   size_t n = (size_t)M * N;
   if (n == 0 || n % 4 != 0) return MT_ERR_ARG;
+  mt_prof_work(0.0, (double)n * (4.0 + (out_bf16 ? 2.0 : 4.0)));
   if (out_bf16) drop_grad_kernel<bf16><<<ew_grid(n / 4, 256), 256, 0, st>>>(n / 4, g, (bf16*)out, drop);
   else drop_grad_kernel<float><<<ew_grid(n / 4, 256), 256, 0, st>>>(n / 4, g, (float*)out, drop);
   MT_LAUNCH_CHECK();
@@ -362,14 +365,14 @@ int mt_layernorm_bwd(int dtype, int M, int d, const float* x, const float* a_2, 
 int mt_residual_dropout_fwd(const float* x, const float* y, float* out, size_t n, float p, uint64_t seed, uint32_t site, void* stream) {
   if (!y || !out || n == 0) return MT_ERR_ARG;
   residual_dropout_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(n, x, y, out, mt_make_drop(p, seed, site));
-  MT_LAUNCH_CHECK();
+  MT_LAUNCH_CHECK_S((cudaStream_t)stream);
   return MT_OK;
 }
 
 int mt_dropout_bwd(const float* g, float* out, size_t n, float p, uint64_t seed, uint32_t site, void* stream) {
   if (!g || !out || n == 0) return MT_ERR_ARG;
   residual_dropout_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(n, nullptr, g, out, mt_make_drop(p, seed, site));
-  MT_LAUNCH_CHECK();
+  MT_LAUNCH_CHECK_S((cudaStream_t)stream);
   return MT_OK;
 }
 
@@ -378,7 +381,7 @@ int mt_cast_f32_to_bf16(const float* src, void* dst, size_t n, void* stream) {
   if (n == 0) return MT_OK;
   if (((uintptr_t)src & 15) || ((uintptr_t)dst & 7)) return MT_ERR_ALIGN;
   cast_f2b_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
-  MT_LAUNCH_CHECK();
+  MT_LAUNCH_CHECK_S((cudaStream_t)stream);
   return MT_OK;
 }
 
@@ -387,7 +390,7 @@ int mt_cast_bf16_to_f32(const void* src, float* dst, size_t n, void* stream) {
   if (n == 0) return MT_OK;
   if (((uintptr_t)src & 7) || ((uintptr_t)dst & 15)) return MT_ERR_ALIGN;
   cast_b2f_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)src, dst, n);
-  MT_LAUNCH_CHECK();
+  MT_LAUNCH_CHECK_S((cudaStream_t)stream);
   return MT_OK;
 }
 
@@ -396,7 +399,7 @@ int mt_mse_loss_fwd_bwd(const float* pred, const float* target, size_t n, float 
   int grid = ew_grid(n, 256);
   if (grid > 148) grid = 148;
   mse_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pred, target, n, inv_norm, loss, dpred);
-  MT_LAUNCH_CHECK();
+  MT_LAUNCH_CHECK_S((cudaStream_t)stream);
   return MT_OK;
 }
 
@@ -407,7 +410,7 @@ int mt_adam_step(float* p, const float* g, float* m, float* v, size_t n, float l
   float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
   float bc2 = (float)(1.0 - pow((double)beta2, (double)step));
   adam_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2));
-  MT_LAUNCH_CHECK();
+  MT_LAUNCH_CHECK_S((cudaStream_t)stream);
   return MT_OK;
 }
 

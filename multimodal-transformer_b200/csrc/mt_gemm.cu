@@ -10,6 +10,11 @@
 static int g_force_simt = 0;
 
 int mt_gemm_run(int dtype, const GemmDesc& g, cudaStream_t st) {
+  if (g_mt_prof_on) {
+    const double es = dtype == MT_BF16 ? 2.0 : 4.0, cs = (g.c_f32 || dtype == MT_F32) ? 4.0 : 2.0;
+    mt_prof_work(2.0 * g.M * (double)g.N * g.K, ((double)g.M * g.K + (double)g.N * g.K) * es + (double)g.M * g.N * cs +
+                                                    (g.epi.residual ? 4.0 * g.M * g.N : 0.0) + (g.epi.gate ? es * g.M * g.N : 0.0));
+  }
 #if MT_HAVE_TC
   if (dtype == MT_BF16 && !g_force_simt && mt_gemm_tc_supported(g)) return mt_gemm_tc_run(g, st);
 #endif

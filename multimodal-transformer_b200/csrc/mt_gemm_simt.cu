@@ -188,6 +188,7 @@ int mt_gemm_simt_run(int dtype, const GemmDesc& d, cudaStream_t st) {
 
 int mt_colsum_run(int x_is_bf16, int M, int N, const void* X, int ldx, float* out, int accumulate, cudaStream_t st) {
   if (!accumulate) MT_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N, st));
+  mt_prof_work(0.0, (double)M * N * (x_is_bf16 ? 2.0 : 4.0));
   int rpb = 256;
   // enough row blocks to fill the machine without drowning in atomics
   while ((size_t)((M + rpb - 1) / rpb) * ((N + 127) / 128) > 148 * 8 && rpb < 4096) rpb *= 2;

@@ -634,6 +634,7 @@ int mt_mfn_fwd(const MtMfnCfg* cfg, const float* params, const void* params_lp, 
   a.drop_g2 = mt_make_drop(pg, c.seed, MT_SITE_MFN_G2);
   a.drop_out = mt_make_drop(po, c.seed, MT_SITE_MFN_OUT);
   const size_t smem = fwd_smem_floats(D) * sizeof(float);
+  mt_prof_work(2.0 * (double)D.t_total * c.B * c.T, 0.0);
   const int grid = (c.B + BT - 1) / BT;
   if (lp) {
     MT_TRY(set_smem(mfn_fwd_kernel<bf16>, smem));
@@ -674,6 +675,7 @@ int mt_mfn_bwd(const MtMfnCfg* cfg, const float* params, const void* params_lp, 
   a.drop_g2 = mt_make_drop(c.p_gamma, c.seed, MT_SITE_MFN_G2);
   a.drop_out = mt_make_drop(c.p_out, c.seed, MT_SITE_MFN_OUT);
   const size_t smem = bwd_smem_floats(D) * sizeof(float);
+  mt_prof_work(2.0 * (double)D.t_total * c.B * c.T, 0.0);
   const int grid = (c.B + BT - 1) / BT;
   if (lp) {
     MT_TRY(set_smem(mfn_bwd_kernel<bf16>, smem));
