@@ -41,6 +41,9 @@ _PROTOS = {
     'mt_check_device': (c_int, [c_int]),
     'mt_version': (c_int, []),
     'mt_launch_count': (c_uint64, []),
+    'mt_prof_start': (c_int, [c_int, P]),
+    'mt_prof_stop': (c_int, []),
+    'mt_prof_get': (c_int, [c_int, c_char_p, c_int, POINTER(c_float), POINTER(ctypes.c_double), POINTER(ctypes.c_double)]),
     'mt_linear_fwd': (c_int, [c_int, c_int, c_int, c_int, P, c_int, P, P, P, c_int, c_int, P, c_float, c_uint64, c_uint32, P, c_size_t, P]),
     'mt_linear_ws_bytes': (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_float]),
     'mt_linear_bwd': (c_int, [c_int, c_int, c_int, c_int, P, c_int, P, P, c_int, P, c_int, c_int, P, c_float, c_uint64, c_uint32, P, P, P,
