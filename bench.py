@@ -256,10 +256,10 @@ def run_ours(args, rank, local_rank, world):
         n = L.mt_prof_stop()
         import ctypes
         agg = {}
-        name = ctypes.create_string_buffer(64)
+        name = ctypes.create_string_buffer(128)
         ms, fl, by = ctypes.c_float(), ctypes.c_double(), ctypes.c_double()
         for i in range(n):
-            _lib.check(L.mt_prof_get(i, name, 64, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(by)))
+            _lib.check(L.mt_prof_get(i, name, 128, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(by)))
             a = agg.setdefault(name.value.decode(), [0.0, 0.0, 0.0, 0])
             a[0] += ms.value; a[1] += fl.value; a[2] += by.value; a[3] += 1
         tot = sum(a[0] for a in agg.values())
@@ -282,7 +282,7 @@ def run_ours(args, rank, local_rank, world):
             roofline = dict(bound='hbm', achieved=top.get('gbs', 0.0), peak=P['hbm'], unit='GB/s', frac=f_h)
         roofline.update(kernel=top['site'], avg_launch_ms=a[0] / a[3], share_of_step=top['share'], peak_source=P['src'], traffic=None,
                         how='algorithmic work annotated at the launch site / CUDA-event duration between consecutive launches on the launching stream')
-        kernels = kernels[:12]
+        kernels = kernels[:40]
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

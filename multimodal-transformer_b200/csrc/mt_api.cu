@@ -14,12 +14,17 @@ int mt_set_cuda_error(cudaError_t e, const char* file, int line) {
 // ---- per-launch profiler ---------------------------------------------------------------------------------
 int g_mt_prof_on = 0;
 namespace {
-struct ProfRec { char name[48]; double flops, bytes; cudaEvent_t ev; };
+struct ProfRec { char name[96]; double flops, bytes; cudaEvent_t ev; };
 ProfRec* g_recs = nullptr;
 int g_prof_cap = 0, g_prof_n = 0;
 cudaEvent_t g_prof_base = nullptr;
 double g_pending_flops = 0.0, g_pending_bytes = 0.0;
+char g_pending_tag[40] = "";
 }  // namespace
+
+void mt_prof_tag(const char* tag) {
+  if (g_mt_prof_on) snprintf(g_pending_tag, sizeof(g_pending_tag), "%s", tag);
+}
 
 void mt_prof_work(double flops, double bytes) {
   if (!g_mt_prof_on) return;
@@ -30,7 +35,8 @@ void mt_prof_work(double flops, double bytes) {
 void mt_prof_record(const char* func, int line, cudaStream_t st) {
   if (g_prof_n >= g_prof_cap) { g_pending_flops = g_pending_bytes = 0.0; return; }
   ProfRec& r = g_recs[g_prof_n];
-  snprintf(r.name, sizeof(r.name), "%s:%d", func, line);
+  snprintf(r.name, sizeof(r.name), g_pending_tag[0] ? "%s:%d %s" : "%s:%d", func, line, g_pending_tag);
+  g_pending_tag[0] = 0;
   r.flops = g_pending_flops; r.bytes = g_pending_bytes;
   g_pending_flops = g_pending_bytes = 0.0;
   if (cudaEventRecord(r.ev, st) == cudaSuccess) ++g_prof_n;

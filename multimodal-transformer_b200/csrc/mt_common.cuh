@@ -22,6 +22,7 @@ int mt_set_cuda_error(cudaError_t e, const char* file, int line);
 extern int g_mt_prof_on;
 void mt_prof_record(const char* func, int line, cudaStream_t st);
 void mt_prof_work(double flops, double bytes);      // annotates the NEXT launch with its algorithmic work
+void mt_prof_tag(const char* tag);                   // ... and with a shape tag appended to the site name
 #define MT_LAUNCH_CHECK_S(stream_)                                        \
   do {                                                                    \
     ++g_mt_launches;                                                      \

@@ -12,6 +12,9 @@ static int g_force_simt = 0;
 int mt_gemm_run(int dtype, const GemmDesc& g, cudaStream_t st) {
   if (g_mt_prof_on) {
     const double es = dtype == MT_BF16 ? 2.0 : 4.0, cs = (g.c_f32 || dtype == MT_F32) ? 4.0 : 2.0;
+    char tag[40];
+    snprintf(tag, sizeof(tag), "m%d n%d k%d %c%c%s", g.M, g.N, g.K, g.a_kmajor ? 'K' : 'M', g.b_kmajor ? 'K' : 'M', g.split_k > 1 ? " splitk" : "");
+    mt_prof_tag(tag);
     mt_prof_work(2.0 * g.M * (double)g.N * g.K, ((double)g.M * g.K + (double)g.N * g.K) * es + (double)g.M * g.N * cs +
                                                     (g.epi.residual ? 4.0 * g.M * g.N : 0.0) + (g.epi.gate ? es * g.M * g.N : 0.0));
   }

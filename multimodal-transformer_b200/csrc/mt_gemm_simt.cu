@@ -176,6 +176,37 @@ __global__ void colsum_kernel_bf16(int M, int N, const bf16* __restrict__ X, int
   atomicAdd(out + n, s);
 }
 
+// vectorised column sums: 32 column-quads x 8 row lanes per CTA, rows strided over the grid's y dimension
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(int M, int N, const T* __restrict__ X, int ldx, float* __restrict__ out,
+                                                          int rows_per_block) {
+  __shared__ float4 red[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 128 + tx * 4;
+  const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n < N) {
+    int m = m0 + ty;
+    for (; m + 24 < m1; m += 32) {            // 4 independent 16-byte loads in flight
+      float4 a = ld4(X + (size_t)m * ldx + n), b = ld4(X + (size_t)(m + 8) * ldx + n);
+      float4 c = ld4(X + (size_t)(m + 16) * ldx + n), d = ld4(X + (size_t)(m + 24) * ldx + n);
+      s.x += (a.x + b.x) + (c.x + d.x); s.y += (a.y + b.y) + (c.y + d.y);
+      s.z += (a.z + b.z) + (c.z + d.z); s.w += (a.w + b.w) + (c.w + d.w);
+    }
+    for (; m < m1; m += 8) {
+      float4 a = ld4(X + (size_t)m * ldx + n);
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+    }
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+#pragma unroll
+    for (int q = 1; q < 8; ++q) { float4 o = red[q][tx]; s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w; }
+    atomicAdd(out + n, s.x); atomicAdd(out + n + 1, s.y); atomicAdd(out + n + 2, s.z); atomicAdd(out + n + 3, s.w);
+  }
+}
+
 }  // namespace
 
 int mt_gemm_simt_run(int dtype, const GemmDesc& d, cudaStream_t st) {
@@ -189,6 +220,18 @@ int mt_gemm_simt_run(int dtype, const GemmDesc& d, cudaStream_t st) {
 int mt_colsum_run(int x_is_bf16, int M, int N, const void* X, int ldx, float* out, int accumulate, cudaStream_t st) {
   if (!accumulate) MT_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N, st));
   mt_prof_work(0.0, (double)M * N * (x_is_bf16 ? 2.0 : 4.0));
+  const size_t es = x_is_bf16 ? 2 : 4;
+  if (N % 4 == 0 && ldx % 4 == 0 && ((uintptr_t)X % (4 * es)) == 0) {
+    const int gx = (N + 127) / 128;
+    int gy = (148 * 4 + gx - 1) / gx;
+    int rpbv = ((M + gy - 1) / gy + 31) / 32 * 32;
+    if (rpbv < 64) rpbv = 64;
+    dim3 gridv(gx, (M + rpbv - 1) / rpbv);
+    if (x_is_bf16) colsum_vec_kernel<bf16><<<gridv, 256, 0, st>>>(M, N, (const bf16*)X, ldx, out, rpbv);
+    else colsum_vec_kernel<float><<<gridv, 256, 0, st>>>(M, N, (const float*)X, ldx, out, rpbv);
+    MT_LAUNCH_CHECK();
+    return MT_OK;
+  }
   int rpb = 256;
   // enough row blocks to fill the machine without drowning in atomics
   while ((size_t)((M + rpb - 1) / rpb) * ((N + 127) / 128) > 148 * 8 && rpb < 4096) rpb *= 2;

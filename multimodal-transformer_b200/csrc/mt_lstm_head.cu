@@ -283,7 +283,7 @@ int mt_lstm_head_fwd(const MtLstmHeadCfg* cfg, const float* params, const void* 
   g.C = a.S.gates; g.ldc = 4 * E; g.c_f32 = true;
   g.epi.bias = params + a.O.b_ih;
   MT_TRY(mt_gemm_run(c.dtype, g, st));
-  const size_t smem = ((size_t)(E * 3 + 4 * E + c.Hd) * BT + (size_t)NTHREADS * BT) * sizeof(float);
+  const size_t smem = ((size_t)(E * 3 + 4 * E + c.Hd) * BT + (size_t)PART_FLOATS) * sizeof(float);
   const int grid = (c.B + BT - 1) / BT;
   if (lp) { MT_TRY(set_smem(head_fwd_kernel<bf16>, smem)); head_fwd_kernel<bf16><<<grid, NTHREADS, smem, st>>>(a); }
   else { MT_TRY(set_smem(head_fwd_kernel<float>, smem)); head_fwd_kernel<float><<<grid, NTHREADS, smem, st>>>(a); }
@@ -307,7 +307,7 @@ int mt_lstm_head_bwd(const MtLstmHeadCfg* cfg, const float* params, const void* 
   a.B = c.B; a.T = c.T; a.E = c.E; a.Hd = c.Hd;
   const int M = c.B * c.T, E = c.E, Hd = c.Hd;
   MT_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * a.O.total, st));
-  const size_t smem = ((size_t)(E * 4 + 8 * E + 2 * Hd) * BT + (size_t)NTHREADS * BT) * sizeof(float);
+  const size_t smem = ((size_t)(E * 4 + 8 * E + 2 * Hd) * BT + (size_t)PART_FLOATS) * sizeof(float);
   const int grid = (c.B + BT - 1) / BT;
   if (lp) { MT_TRY(set_smem(head_bwd_kernel<bf16>, smem)); head_bwd_kernel<bf16><<<grid, NTHREADS, smem, st>>>(a); }
   else { MT_TRY(set_smem(head_bwd_kernel<float>, smem)); head_bwd_kernel<float><<<grid, NTHREADS, smem, st>>>(a); }

@@ -532,12 +532,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) mfn_bwd_kernel(const __grid_const
 size_t fwd_smem_floats(const Dims& D) {
   const int Hs = D.Hs, H2 = 2 * D.Hs;
   size_t f = (size_t)Hs * 2 + D.MEM + 4 * Hs + H2 + D.A1 + H2 + (H2 + D.MEM) + D.A2 + D.MEM + 2 * D.G + 2 * D.MEM + (Hs + D.MEM) + D.O;
-  return f * BT + (size_t)NTHREADS * BT;
+  return f * BT + (size_t)PART_FLOATS;
 }
 size_t bwd_smem_floats(const Dims& D) {
   const int Hs = D.Hs, H2 = 2 * D.Hs;
   size_t f = (size_t)Hs * 3 + D.MEM + D.O + 4 * D.MEM + 4 * D.G + 2 * (H2 + D.MEM) + 2 * D.MEM + 2 * D.A2 + 4 * H2 + 2 * D.A1 + 8 * Hs + D.O;
-  return f * BT + (size_t)NTHREADS * BT;
+  return f * BT + (size_t)PART_FLOATS;
 }
 
 int layout_strides(const MtMfnCfg& c, const Dims& D, const int64_t* stride_b, const int64_t* stride_t, long long& sb, long long& st) {
