@@ -325,10 +325,13 @@ int check_shape(int B, int T_, int d, int h) {
 
 }  // namespace
 
+static int g_attn_force_ffma = 0;
+
 int mt_attn_fwd_run(int dtype, int B, int T_, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop,
                     cudaStream_t st) {
   MT_TRY(check_shape(B, T_, d, h));
   if (!qkv || !out) return MT_ERR_ARG;
+  if (dtype == MT_BF16 && !g_attn_force_ffma && mt_attn_mma_supported(B, T_, d, h)) return mt_attn_mma_fwd_run(B, T_, d, h, qkv, mask, out, lse, drop, st);
   if (dtype == MT_BF16) return fwd_dispatch<bf16>(B, T_, d, h, qkv, mask, out, lse, drop, st);
   return fwd_dispatch<float>(B, T_, d, h, qkv, mask, out, lse, drop, st);
 }
@@ -337,11 +340,16 @@ int mt_attn_bwd_run(int dtype, int B, int T_, int d, int h, const void* qkv, con
                     const void* dout, void* dqkv, DropCfg drop, float* Dws, cudaStream_t st) {
   MT_TRY(check_shape(B, T_, d, h));
   if (!qkv || !out || !lse || !dout || !dqkv || !Dws) return MT_ERR_ARG;
+  if (dtype == MT_BF16 && !g_attn_force_ffma && mt_attn_mma_supported(B, T_, d, h))
+    return mt_attn_mma_bwd_run(B, T_, d, h, qkv, mask, out, lse, dout, dqkv, drop, st);
   if (dtype == MT_BF16) return bwd_dispatch<bf16>(B, T_, d, h, qkv, mask, out, lse, dout, dqkv, drop, Dws, st);
   return bwd_dispatch<float>(B, T_, d, h, qkv, mask, out, lse, dout, dqkv, drop, Dws, st);
 }
 
 extern "C" {
+
+/* test hook: run bf16 attention on the FFMA engine instead of the tensor-core engine; returns the previous setting */
+int mt_attention_force_ffma(int on) { int old = g_attn_force_ffma; g_attn_force_ffma = on; return old; }
 
 int mt_attention_fwd(int dtype, int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, float p_drop,
                      uint64_t seed, uint32_t site, void* stream) {

@@ -6,10 +6,12 @@
 //   warp 0  : TMA producer   -- cp.async.bulk.tensor 2-D boxes (128-byte swizzle) into a 4-stage shared-memory ring
 //   warp 1  : MMA issuer     -- one elected lane issues tcgen05.mma (M=128, N=BN, K=16) from shared-memory
 //                               descriptors; tcgen05.commit releases ring slots and publishes accumulators
-//   warps 2-5: epilogue      -- tcgen05.ld the fp32 accumulator (double-buffered in TMEM so the next tile's MMAs
-//                               overlap this tile's epilogue), transpose through shared memory and apply
-//                               bias / activation / dropout / gate / residual / row-mask with coalesced 16-byte
-//                               global accesses, or fp32 atomics for split-K (wgrad) work items.
+//   warps 2-9: epilogue      -- each owns a TMEM lane quarter x a column half: tcgen05.ld the fp32 accumulator
+//                               (double-buffered in TMEM so the next tile's MMAs overlap this tile's epilogue),
+//                               release it, transpose through shared memory, then stream rows: the residual /
+//                               gate loads of four row groups are issued back to back before any is consumed, and
+//                               bias / activation / dropout / gate / residual / row-mask are applied on fully
+//                               coalesced 128-256-byte row segments (fp32 atomics for split-K wgrad work items).
 // Work items are (tile_m, tile_n, k_split) triples enumerated identically by all three roles.
 // Out-of-bounds rows / columns / k are zero-filled by TMA and predicated in the epilogue.
 #include <cuda.h>
@@ -21,8 +23,7 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;                 // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int STAGES = 4;
-constexpr int TC_THREADS = 192;
-constexpr int EPI_LD = 36;             // floats per staged row (32 + pad, keeps 16-byte alignment, conflict-free)
+constexpr int TC_THREADS = 320;            // TMA warp, MMA warp, 8 epilogue warps
 constexpr uint32_t SPIN_LIMIT = 1u << 27;
 
 struct TcArgs {
@@ -110,7 +111,7 @@ struct Smem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
+  static constexpr int EPI_BYTES = 8 * 32 * (BN / 2 + 4) * 4;      // 8 epilogue warps x 32 rows x (BN/2 + 4) floats
   static constexpr int BAR_BYTES = 256;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024 /* alignment slack */;
 };
@@ -138,7 +139,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -213,85 +214,95 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ===== epilogue warps (TMEM lane quarter = warp % 4) =====
-    const int q = warp & 3;
-    float* stg = epi_stage + q * 32 * EPI_LD;
+    // ===== epilogue warps: warp w owns TMEM lane quarter (w % 4) and column half (w - 2) / 4 of every tile =====
+    constexpr int HN = BN / 2;                 // columns per epilogue warp
+    constexpr int LDS = HN + 4;                // staged row stride in floats (16-byte aligned, conflict-free both ways)
+    constexpr int LPR = HN / 4;                // lanes per output row (16-byte column quads)
+    constexpr int RPI = 32 / LPR;              // rows covered by one warp-wide access
+    constexpr int ITERS = 32 / RPI;
+    constexpr int U = 4;                       // row-iterations whose global loads are issued back to back
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    float* stg = epi_stage + (warp - 2) * 32 * LDS;
     const GemmEpi& e = g.epi;
+    const int lr = lane / LPR, lc = (lane % LPR) * 4;
     int it = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
       const int tile = w % tiles;
-      const int m0 = (tile / g.tiles_n) * BM, n0 = (tile % g.tiles_n) * BN;
+      const int m0 = (tile / g.tiles_n) * BM, n0 = (tile % g.tiles_n) * BN + half * HN;
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1;
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const int row_base = m0 + q * 32;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      __syncwarp();                             // previous tile's reads of `stg` are complete
+#pragma unroll
+      for (int c0 = 0; c0 < HN; c0 += 32) {
         uint32_t v[32];
-        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-        if (c0 + 32 >= BN) {
-          // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[acc]);
-        }
-        if (n0 + c0 >= g.N || row_base >= g.M) continue;
-        __syncwarp();
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * HN + c0), v);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(stg + lane * EPI_LD + j * 4) =
+          *reinterpret_cast<float4*>(stg + lane * LDS + c0 + j * 4) =
               make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-        __syncwarp();
-        const int cc = (lane & 7) * 4;
-        const int n = n0 + c0 + cc;
-        if (n < g.N) {
-          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (e.bias && !g.atomic) bias4 = *reinterpret_cast<const float4*>(e.bias + n);
+      }
+      // all TMEM reads of this accumulator are done: hand it back to the MMA warp before touching global memory
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      const int n = n0 + lc;
+      if (n >= g.N || row_base >= g.M) continue;
+      if (g.atomic) {
+#pragma unroll 4
+        for (int i = 0; i < ITERS; ++i) {
+          const int r = i * RPI + lr, m = row_base + r;
+          if (m >= g.M) continue;
+          const float4 a4 = *reinterpret_cast<const float4*>(stg + r * LDS + lc);
+          float* cp = reinterpret_cast<float*>(g.C) + (size_t)m * g.ldc + n;
+          atomicAdd(cp, a4.x * e.alpha); atomicAdd(cp + 1, a4.y * e.alpha); atomicAdd(cp + 2, a4.z * e.alpha); atomicAdd(cp + 3, a4.w * e.alpha);
+        }
+        continue;
+      }
+      float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e.bias) bias4 = *reinterpret_cast<const float4*>(e.bias + n);
+#pragma unroll 1
+      for (int i0 = 0; i0 < ITERS; i0 += U) {
+        float4 res[U], gt[U];
+        float rm[U];
 #pragma unroll
-          for (int rr = 0; rr < 8; ++rr) {
-            const int r = rr * 4 + (lane >> 3);
-            const int m = row_base + r;
-            if (m >= g.M) continue;
-            float4 a4 = *reinterpret_cast<const float4*>(stg + r * EPI_LD + cc);
-            float o[4] = {a4.x * e.alpha, a4.y * e.alpha, a4.z * e.alpha, a4.w * e.alpha};
-            if (g.atomic) {
-              float* cp = reinterpret_cast<float*>(g.C) + (size_t)m * g.ldc + n;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) atomicAdd(cp + i, o[i]);
-              continue;
-            }
-            o[0] += bias4.x; o[1] += bias4.y; o[2] += bias4.z; o[3] += bias4.w;
-            if (e.act == MT_ACT_RELU) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) o[i] = fmaxf(o[i], 0.f);
-            } else if (e.act == MT_ACT_TANH) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) o[i] = tanhf(o[i]);
-            }
-            if (e.drop.thresh != 0u) {
-              const uint64_t idx = (uint64_t)m * (uint64_t)g.N + (uint64_t)n;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) o[i] *= mt_drop_factor(e.drop, idx + i);
-            }
-            if (e.gate) {
-              float4 gt;
-              if (g.gate_bf16) gt = ld4(reinterpret_cast<const bf16*>(e.gate) + (size_t)m * e.ldg + n);
-              else gt = ld4(reinterpret_cast<const float*>(e.gate) + (size_t)m * e.ldg + n);
-              o[0] = gt.x > 0.f ? o[0] * e.gate_scale : 0.f; o[1] = gt.y > 0.f ? o[1] * e.gate_scale : 0.f;
-              o[2] = gt.z > 0.f ? o[2] * e.gate_scale : 0.f; o[3] = gt.w > 0.f ? o[3] * e.gate_scale : 0.f;
-            }
-            if (e.residual) {
-              float4 r4 = *reinterpret_cast<const float4*>(e.residual + (size_t)m * e.ldr + n);
-              o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
-            }
-            if (e.rowmask) {
-              const float rm = e.rowmask[m];
-              o[0] *= rm; o[1] *= rm; o[2] *= rm; o[3] *= rm;
-            }
-            if (g.c_f32) st4(reinterpret_cast<float*>(g.C) + (size_t)m * g.ldc + n, make_float4(o[0], o[1], o[2], o[3]));
-            else st4(reinterpret_cast<bf16*>(g.C) + (size_t)m * g.ldc + n, make_float4(o[0], o[1], o[2], o[3]));
+        for (int u = 0; u < U; ++u) {            // issue every global load of this batch first
+          const int m = row_base + (i0 + u) * RPI + lr;
+          res[u] = make_float4(0.f, 0.f, 0.f, 0.f); gt[u] = make_float4(1.f, 1.f, 1.f, 1.f); rm[u] = 1.f;
+          if (m < g.M) {
+            if (e.residual) res[u] = *reinterpret_cast<const float4*>(e.residual + (size_t)m * e.ldr + n);
+            if (e.gate) gt[u] = ld4(reinterpret_cast<const bf16*>(e.gate) + (size_t)m * e.ldg + n);
+            if (e.rowmask) rm[u] = e.rowmask[m];
           }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int r = (i0 + u) * RPI + lr, m = row_base + r;
+          if (m >= g.M) continue;
+          const float4 a4 = *reinterpret_cast<const float4*>(stg + r * LDS + lc);
+          float o[4] = {a4.x * e.alpha + bias4.x, a4.y * e.alpha + bias4.y, a4.z * e.alpha + bias4.z, a4.w * e.alpha + bias4.w};
+          if (e.act == MT_ACT_RELU) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = fmaxf(o[k], 0.f);
+          } else if (e.act == MT_ACT_TANH) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = tanhf(o[k]);
+          }
+          if (e.drop.thresh != 0u) {
+            const uint64_t idx = (uint64_t)m * (uint64_t)g.N + (uint64_t)n;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] *= mt_drop_factor(e.drop, idx + k);
+          }
+          if (e.gate) {
+            o[0] = gt[u].x > 0.f ? o[0] * e.gate_scale : 0.f; o[1] = gt[u].y > 0.f ? o[1] * e.gate_scale : 0.f;
+            o[2] = gt[u].z > 0.f ? o[2] * e.gate_scale : 0.f; o[3] = gt[u].w > 0.f ? o[3] * e.gate_scale : 0.f;
+          }
+          o[0] = (o[0] + res[u].x) * rm[u]; o[1] = (o[1] + res[u].y) * rm[u];
+          o[2] = (o[2] + res[u].z) * rm[u]; o[3] = (o[3] + res[u].w) * rm[u];
+          if (g.c_f32) st4(reinterpret_cast<float*>(g.C) + (size_t)m * g.ldc + n, make_float4(o[0], o[1], o[2], o[3]));
+          else st4(reinterpret_cast<bf16*>(g.C) + (size_t)m * g.ldc + n, make_float4(o[0], o[1], o[2], o[3]));
         }
       }
     }

@@ -79,6 +79,7 @@ struct HArgs {
   const float* dout;
   float* grads;
   int B, T, E, Hd;
+  StreamTable tab;
 };
 
 // pack: t_hh = W_hh^T, t_sum = (W_a + W_hh)^T, r_sum = W_a + W_hh, t_w0 = W_0^T
@@ -105,35 +106,44 @@ __global__ void head_pack_kernel(HArgs a) {
   }
 }
 
-template <typename WT>
-__global__ void __launch_bounds__(NTHREADS, 1) head_fwd_kernel(const __grid_constant__ HArgs a) {
-  extern __shared__ __align__(16) float smem[];
+template <bool STREAM, typename WT>
+__global__ void __launch_bounds__(NTHREADS + 32, 1) head_fwd_kernel(const __grid_constant__ HArgs a) {
+  extern __shared__ __align__(128) float smem[];
   const int E = a.E, Hd = a.Hd;
-  float* h = smem; float* c = h + E * BT; float* z = c + E * BT; float* oh = z + 4 * E * BT; float* zero = oh + Hd * BT;
+  float* h = smem + (STREAM ? RING_BYTES / sizeof(float) : 0); float* c = h + E * BT; float* z = c + E * BT; float* oh = z + 4 * E * BT; float* zero = oh + Hd * BT;
   float* part = zero + E * BT;
   __shared__ long long rows[BT];
+  // weight ring (STREAM): barriers + slots live at the start of the dynamic shared memory block
+  WRing ring = ring_setup(reinterpret_cast<uint8_t*>(smem), STREAM && threadIdx.x == 0);
+  if (STREAM) {
+    __syncthreads();                              // the only CTA-wide barrier that includes the producer warp
+    if (threadIdx.x >= NTHREADS) {
+      if (threadIdx.x == NTHREADS) stream_producer<WT>(a.tab, a.T, 0, ring);
+      return;
+    }
+  }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b0 = blockIdx.x * BT, nb = min(BT, a.B - b0);
   const float* P = a.params;
   for (int e = tid; e < E * BT; e += NTHREADS) {
     h[e] = P[a.O.h0 + e / BT]; c[e] = P[a.O.c0 + e / BT]; zero[e] = 0.f;
   }
-  __syncthreads();
+  cta_sync();
   for (int t = 0; t < a.T; ++t) {
     if (tid < BT) rows[tid] = (long long)(b0 + min(tid, nb - 1)) * a.T + t;
-    __syncthreads();
+    cta_sync();
     load_rows(z, 4 * E, a.S.gates, rows, nb);
     stash_rows(a.S.hprev, E, h, rows, nb);
     stash_rows(a.S.oprev, E, t == 0 ? zero : h, rows, nb);
     stash_rows(a.S.cprev, E, c, rows, nb);
-    __syncthreads();
+    cta_sync();
     const WT* Wr = reinterpret_cast<const WT*>(t == 0 ? a.S.t_hh : a.S.t_sum);
-    dense<WT>(Wr, 4 * E, E, 4 * E, h, part, [&](int n, float* acc) {
+    dense<STREAM, WT>(ring, Wr, E, 4 * E, h, part, [&](int n, float* acc) {
       const float bias = P[a.O.b_hh + n];
 #pragma unroll
       for (int b = 0; b < BT; ++b) z[n * BT + b] += acc[b] + bias;
     });
-    __syncthreads();
+    cta_sync();
     for (int e = tid; e < E * BT; e += NTHREADS) {
       const int j = e / BT, b = e % BT;
       float gi = sigmoidf_(z[(0 * E + j) * BT + b]), gf = sigmoidf_(z[(1 * E + j) * BT + b]);
@@ -143,15 +153,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) head_fwd_kernel(const __grid_cons
       c[e] = cn;
       h[e] = go * tanhf(cn);
     }
-    __syncthreads();
+    cta_sync();
     stash_rows(a.S.hcur ? a.S.gates : nullptr, 4 * E, z, rows, nb);
     stash_rows(a.S.hcur, E, h, rows, nb);
-    dense<WT>(reinterpret_cast<const WT*>(a.S.t_w0), Hd, E, Hd, h, part, [&](int n, float* acc) {
+    dense<STREAM, WT>(ring, reinterpret_cast<const WT*>(a.S.t_w0), E, Hd, h, part, [&](int n, float* acc) {
       const float bias = P[a.O.b0 + n];
 #pragma unroll
       for (int b = 0; b < BT; ++b) oh[n * BT + b] = fmaxf(acc[b] + bias, 0.f);
     });
-    __syncthreads();
+    cta_sync();
     stash_rows(a.S.oh, Hd, oh, rows, nb);
     if (warp < BT) {
       float acc = 0.f;
@@ -164,24 +174,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) head_fwd_kernel(const __grid_cons
         a.out[r] = y;
       }
     }
-    __syncthreads();
+    cta_sync();
   }
 }
 
-template <typename WT>
-__global__ void __launch_bounds__(NTHREADS, 1) head_bwd_kernel(const __grid_constant__ HArgs a) {
-  extern __shared__ __align__(16) float smem[];
+template <bool STREAM, typename WT>
+__global__ void __launch_bounds__(NTHREADS + 32, 1) head_bwd_kernel(const __grid_constant__ HArgs a) {
+  extern __shared__ __align__(128) float smem[];
   const int E = a.E, Hd = a.Hd;
-  float* dh = smem; float* dc = dh + E * BT; float* dhp = dc + E * BT; float* gates = dhp + E * BT; float* dz = gates + 4 * E * BT;
+  float* dh = smem + (STREAM ? RING_BYTES / sizeof(float) : 0); float* dc = dh + E * BT; float* dhp = dc + E * BT; float* gates = dhp + E * BT; float* dz = gates + 4 * E * BT;
   float* cprev = dz + 4 * E * BT; float* oh = cprev + E * BT; float* doh = oh + Hd * BT; float* part = doh + Hd * BT;
   __shared__ long long rows[BT];
   __shared__ float dyv[BT];
+  // weight ring (STREAM): barriers + slots live at the start of the dynamic shared memory block
+  WRing ring = ring_setup(reinterpret_cast<uint8_t*>(smem), STREAM && threadIdx.x == 0);
+  if (STREAM) {
+    __syncthreads();                              // the only CTA-wide barrier that includes the producer warp
+    if (threadIdx.x >= NTHREADS) {
+      if (threadIdx.x == NTHREADS) stream_producer<WT>(a.tab, a.T, a.T - 1, ring);
+      return;
+    }
+  }
   const int tid = threadIdx.x;
   const int b0 = blockIdx.x * BT, nb = min(BT, a.B - b0);
   const float* P = a.params;
   const WT* W = reinterpret_cast<const WT*>(a.params_w);
   for (int e = tid; e < E * BT; e += NTHREADS) { dh[e] = 0.f; dc[e] = 0.f; }
-  __syncthreads();
+  cta_sync();
   for (int t = a.T - 1; t >= 0; --t) {
     if (tid < BT) {
       const size_t r = (size_t)(b0 + min(tid, nb - 1)) * a.T + t;
@@ -191,19 +210,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) head_bwd_kernel(const __grid_cons
       dyv[tid] = g;
       if (tid < nb) a.S.dyv[r] = g;
     }
-    __syncthreads();
+    cta_sync();
     load_rows(gates, 4 * E, a.S.gates, rows, nb);
     load_rows(cprev, E, a.S.cprev, rows, nb);
     load_rows(oh, Hd, a.S.oh, rows, nb);
-    __syncthreads();
+    cta_sync();
     for (int e = tid; e < Hd * BT; e += NTHREADS) doh[e] = oh[e] > 0.f ? dyv[e % BT] * P[a.O.w2 + e / BT] : 0.f;
-    __syncthreads();
+    cta_sync();
     stash_rows(a.S.doh, Hd, doh, rows, nb);
-    dense<WT>(W + a.O.w0, E, Hd, E, doh, part, [&](int n, float* acc) {
+    dense<STREAM, WT>(ring, W + a.O.w0, Hd, E, doh, part, [&](int n, float* acc) {
 #pragma unroll
       for (int b = 0; b < BT; ++b) dh[n * BT + b] += acc[b];
     });
-    __syncthreads();
+    cta_sync();
     for (int e = tid; e < E * BT; e += NTHREADS) {
       const int j = e / BT, b = e % BT;
       const float gi = gates[(0 * E + j) * BT + b], gf = gates[(1 * E + j) * BT + b];
@@ -218,17 +237,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) head_bwd_kernel(const __grid_cons
       dz[(3 * E + j) * BT + b] = dhv * tc * go * (1.f - go);
       dc[e] = dcv * gf;
     }
-    __syncthreads();
+    cta_sync();
     stash_rows(a.S.dz, 4 * E, dz, rows, nb);
     // gradient wrt h_{t-1}: through W_hh always, and through W_ih[:, :E] (as o_{t-1}) for t >= 1
     const WT* Wr = t == 0 ? W + a.O.w_hh : reinterpret_cast<const WT*>(a.S.r_sum);
-    dense<WT>(Wr, E, 4 * E, E, dz, part, [&](int n, float* acc) {
+    dense<STREAM, WT>(ring, Wr, 4 * E, E, dz, part, [&](int n, float* acc) {
 #pragma unroll
       for (int b = 0; b < BT; ++b) dhp[n * BT + b] = acc[b];
     });
-    __syncthreads();
+    cta_sync();
     for (int e = tid; e < E * BT; e += NTHREADS) dh[e] = dhp[e];
-    __syncthreads();
+    cta_sync();
   }
   // dec_h0 / dec_c0 are broadcast over the batch (:465-466): their gradient is the batch sum of the t = 0 carries
   for (int j = tid; j < E; j += NTHREADS) {
@@ -283,10 +302,22 @@ int mt_lstm_head_fwd(const MtLstmHeadCfg* cfg, const float* params, const void* 
   g.C = a.S.gates; g.ldc = 4 * E; g.c_f32 = true;
   g.epi.bias = params + a.O.b_ih;
   MT_TRY(mt_gemm_run(c.dtype, g, st));
-  const size_t smem = ((size_t)(E * 3 + 4 * E + c.Hd) * BT + (size_t)PART_FLOATS) * sizeof(float);
+  const size_t smem = ((size_t)(E * 3 + 4 * E + c.Hd) * BT + (size_t)PART_FLOATS) * sizeof(float) + RING_BYTES;
   const int grid = (c.B + BT - 1) / BT;
-  if (lp) { MT_TRY(set_smem(head_fwd_kernel<bf16>, smem)); head_fwd_kernel<bf16><<<grid, NTHREADS, smem, st>>>(a); }
-  else { MT_TRY(set_smem(head_fwd_kernel<float>, smem)); head_fwd_kernel<float><<<grid, NTHREADS, smem, st>>>(a); }
+  a.tab.n = 2;
+  a.tab.L[0] = StreamLayer{a.S.t_sum, a.S.t_hh, E, 4 * E};          // step 0 applies W_hh only (o_{-1} = 0)
+  a.tab.L[1] = StreamLayer{a.S.t_w0, nullptr, E, c.Hd};
+#define MT_HEAD_LAUNCH(KERNEL, WT_)                                                       \
+  do {                                                                                     \
+    if (stream_table_ok<WT_>(a.tab)) {                                                     \
+      MT_TRY(set_smem(KERNEL<true, WT_>, smem));                                           \
+      KERNEL<true, WT_><<<grid, NTHREADS + 32, smem, st>>>(a);                             \
+    } else {                                                                               \
+      MT_TRY(set_smem(KERNEL<false, WT_>, smem));                                          \
+      KERNEL<false, WT_><<<grid, NTHREADS, smem, st>>>(a);                                 \
+    }                                                                                      \
+  } while (0)
+  if (lp) MT_HEAD_LAUNCH(head_fwd_kernel, bf16); else MT_HEAD_LAUNCH(head_fwd_kernel, float);
   MT_LAUNCH_CHECK();
   return MT_OK;
 }
@@ -307,10 +338,16 @@ int mt_lstm_head_bwd(const MtLstmHeadCfg* cfg, const float* params, const void* 
   a.B = c.B; a.T = c.T; a.E = c.E; a.Hd = c.Hd;
   const int M = c.B * c.T, E = c.E, Hd = c.Hd;
   MT_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * a.O.total, st));
-  const size_t smem = ((size_t)(E * 4 + 8 * E + 2 * Hd) * BT + (size_t)PART_FLOATS) * sizeof(float);
+  const size_t smem = ((size_t)(E * 4 + 8 * E + 2 * Hd) * BT + (size_t)PART_FLOATS) * sizeof(float) + RING_BYTES;
   const int grid = (c.B + BT - 1) / BT;
-  if (lp) { MT_TRY(set_smem(head_bwd_kernel<bf16>, smem)); head_bwd_kernel<bf16><<<grid, NTHREADS, smem, st>>>(a); }
-  else { MT_TRY(set_smem(head_bwd_kernel<float>, smem)); head_bwd_kernel<float><<<grid, NTHREADS, smem, st>>>(a); }
+  {
+    const size_t wsz = mt_esize(c.dtype);
+    const char* pw = reinterpret_cast<const char*>(a.params_w);
+    a.tab.n = 2;
+    a.tab.L[0] = StreamLayer{pw + a.O.w0 * wsz, nullptr, Hd, E};
+    a.tab.L[1] = StreamLayer{a.S.r_sum, pw + a.O.w_hh * wsz, 4 * E, E};    // last iteration (t = 0): W_hh only
+  }
+  if (lp) MT_HEAD_LAUNCH(head_bwd_kernel, bf16); else MT_HEAD_LAUNCH(head_bwd_kernel, float);
   MT_LAUNCH_CHECK();
   float* G = grads;
   const HStash& S = a.S;

@@ -152,6 +152,7 @@ struct KArgs {
   long long sb, st;        // row(b,t) = b*sb + t*st
   int training;
   DropCfg drop_g1, drop_g2, drop_out;
+  StreamTable tab;         // in-loop weight blocks in consumption order
 };
 
 struct SmemFwd {
@@ -165,20 +166,29 @@ __device__ __forceinline__ int mod_of(const Dims& D, int j) {
   return m;
 }
 
-template <typename WT>
-__global__ void __launch_bounds__(NTHREADS, 1) mfn_fwd_kernel(const __grid_constant__ KArgs a) {
-  extern __shared__ __align__(16) float smem[];
+template <bool STREAM, typename WT>
+__global__ void __launch_bounds__(NTHREADS + 32, 1) mfn_fwd_kernel(const __grid_constant__ KArgs a) {
+  extern __shared__ __align__(128) float smem[];
   const Dims& D = a.D;
   const int Hs = D.Hs, H2 = 2 * D.Hs, MEM = D.MEM, A1 = D.A1, A2 = D.A2, G = D.G, O = D.O;
   SmemFwd s;
   {
-    float* p = smem;
+    float* p = smem + (STREAM ? RING_BYTES / sizeof(float) : 0);
     s.h = p; p += Hs * BT; s.c = p; p += Hs * BT; s.mem = p; p += MEM * BT; s.z = p; p += 4 * Hs * BT;
     s.cstar = p; p += H2 * BT; s.a1 = p; p += A1 * BT; s.att = p; p += H2 * BT; s.both = p; p += (H2 + MEM) * BT;
     s.a2 = p; p += A2 * BT; s.chat = p; p += MEM * BT; s.gh = p; p += 2 * G * BT; s.gm = p; p += 2 * MEM * BT;
     s.last = p; p += (Hs + MEM) * BT; s.oh = p; p += O * BT; s.part = p;
   }
   __shared__ long long rows[BT];
+  // weight ring (STREAM): barriers + slots live at the start of the dynamic shared memory block
+  WRing ring = ring_setup(reinterpret_cast<uint8_t*>(smem), STREAM && threadIdx.x == 0);
+  if (STREAM) {
+    __syncthreads();                              // the only CTA-wide barrier that includes the producer warp
+    if (threadIdx.x >= NTHREADS) {
+      if (threadIdx.x == NTHREADS) stream_producer<WT>(a.tab, a.T, 0, ring);
+      return;
+    }
+  }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b0 = blockIdx.x * BT;
   const int nb = min(BT, a.B - b0);
@@ -187,27 +197,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) mfn_fwd_kernel(const __grid_const
 
   for (int e = tid; e < Hs * BT; e += NTHREADS) { s.h[e] = 0.f; s.c[e] = 0.f; }
   for (int e = tid; e < MEM * BT; e += NTHREADS) s.mem[e] = 0.f;
-  __syncthreads();
+  cta_sync();
 
   for (int t = 0; t < a.T; ++t) {
     if (tid < BT) rows[tid] = (long long)(b0 + min(tid, nb - 1)) * a.sb + (long long)t * a.st;
-    __syncthreads();
+    cta_sync();
     // ---- z = zx (hoisted x-projection + both biases) + W_hh h_{t-1} -------------------------------
     load_rows(s.z, 4 * Hs, a.S.gates, rows, nb);
     stash_rows(a.S.hprev, Hs, s.h, rows, nb);
     for (int e = tid; e < Hs * BT; e += NTHREADS) s.cstar[e] = s.c[e];          // c_{t-1} half
-    __syncthreads();
+    cta_sync();
     for (int m = 0; m < D.n_mods; ++m) {
       const int H = D.H[m];
       float* zm = s.z + 4 * D.hoff[m] * BT;
       const float* bhh = P + D.b_hh[m];
-      dense<WT>(TP + D.t_hh[m], 4 * H, H, 4 * H, s.h + D.hoff[m] * BT, s.part, [&](int n, float* acc) {
+      dense<STREAM, WT>(ring, TP + D.t_hh[m], H, 4 * H, s.h + D.hoff[m] * BT, s.part, [&](int n, float* acc) {
         const float bias = bhh[n];
 #pragma unroll
         for (int b = 0; b < BT; ++b) zm[n * BT + b] += acc[b] + bias;
       });
     }
-    __syncthreads();
+    cta_sync();
     // ---- LSTM gates: c_t = s(f) c + s(i) tanh(g); h_t = s(o) tanh(c_t) ----------------------------
     for (int e = tid; e < Hs * BT; e += NTHREADS) {
       const int j = e / BT, b = e % BT;
@@ -226,21 +236,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) mfn_fwd_kernel(const __grid_const
       s.cstar[(Hs + j) * BT + b] = cn;
       s.last[e] = hn;
     }
-    __syncthreads();
+    cta_sync();
     if (a.training) { stash_rows(a.S.gates, 4 * Hs, s.z, rows, nb); stash_rows(a.S.cstar, H2, s.cstar, rows, nb); }
     // ---- delta-memory attention over cStar --------------------------------------------------------
-    dense<WT>(TP + D.t_att1_fc1, A1, H2, A1, s.cstar, s.part, [&](int n, float* acc) {
+    dense<STREAM, WT>(ring, TP + D.t_att1_fc1, H2, A1, s.cstar, s.part, [&](int n, float* acc) {
       const float bias = P[D.att1_fc1.b + n];
 #pragma unroll
       for (int b = 0; b < BT; ++b) s.a1[n * BT + b] = fmaxf(acc[b] + bias, 0.f);
     });
-    __syncthreads();
-    dense<WT>(TP + D.t_att1_fc2, H2, A1, H2, s.a1, s.part, [&](int n, float* acc) {
+    cta_sync();
+    dense<STREAM, WT>(ring, TP + D.t_att1_fc2, A1, H2, s.a1, s.part, [&](int n, float* acc) {
       const float bias = P[D.att1_fc2.b + n];
 #pragma unroll
       for (int b = 0; b < BT; ++b) s.att[n * BT + b] = acc[b] + bias;
     });
-    __syncthreads();
+    cta_sync();
     // softmax over the 2Hs FEATURES of each narrative: warp b handles narrative b
     if (warp < BT) {
       float mx = -INFINITY;
@@ -257,18 +267,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) mfn_fwd_kernel(const __grid_const
       }
     }
     for (int e = tid; e < MEM * BT; e += NTHREADS) s.both[H2 * BT + e] = s.mem[e];   // || mem_{t-1}
-    __syncthreads();
+    cta_sync();
     if (a.training) {
       stash_rows(a.S.a1, A1, s.a1, rows, nb); stash_rows(a.S.att, H2, s.att, rows, nb);
       stash_rows(a.S.both, H2 + MEM, s.both, rows, nb);
     }
     // ---- cHat = tanh(att2(attended)) ; gamma hidden = relu(gamma_fc1(both)) -----------------------
-    dense<WT>(TP + D.t_att2_fc1, A2, H2, A2, s.both, s.part, [&](int n, float* acc) {
+    dense<STREAM, WT>(ring, TP + D.t_att2_fc1, H2, A2, s.both, s.part, [&](int n, float* acc) {
       const float bias = P[D.att2_fc1.b + n];
 #pragma unroll
       for (int b = 0; b < BT; ++b) s.a2[n * BT + b] = fmaxf(acc[b] + bias, 0.f);
     });
-    dense<WT>(TP + D.t_g_fc1, 2 * G, H2 + MEM, 2 * G, s.both, s.part, [&](int n, float* acc) {
+    dense<STREAM, WT>(ring, TP + D.t_g_fc1, H2 + MEM, 2 * G, s.both, s.part, [&](int n, float* acc) {
       const bool second = n >= G;
       const float bias = second ? P[D.g2_fc1.b + n - G] : P[D.g1_fc1.b + n];
       const DropCfg& dc = second ? a.drop_g2 : a.drop_g1;
@@ -281,37 +291,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) mfn_fwd_kernel(const __grid_const
         s.gh[n * BT + b] = v;
       }
     });
-    __syncthreads();
-    dense<WT>(TP + D.t_att2_fc2, MEM, A2, MEM, s.a2, s.part, [&](int n, float* acc) {
+    cta_sync();
+    dense<STREAM, WT>(ring, TP + D.t_att2_fc2, A2, MEM, s.a2, s.part, [&](int n, float* acc) {
       const float bias = P[D.att2_fc2.b + n];
 #pragma unroll
       for (int b = 0; b < BT; ++b) s.chat[n * BT + b] = tanhf(acc[b] + bias);
     });
-    dense<WT>(TP + D.t_g1_fc2, MEM, G, MEM, s.gh, s.part, [&](int n, float* acc) {
+    dense<STREAM, WT>(ring, TP + D.t_g1_fc2, G, MEM, s.gh, s.part, [&](int n, float* acc) {
       const float bias = P[D.g1_fc2.b + n];
 #pragma unroll
       for (int b = 0; b < BT; ++b) s.gm[n * BT + b] = sigmoidf_(acc[b] + bias);
     });
-    dense<WT>(TP + D.t_g2_fc2, MEM, G, MEM, s.gh + G * BT, s.part, [&](int n, float* acc) {
+    dense<STREAM, WT>(ring, TP + D.t_g2_fc2, G, MEM, s.gh + G * BT, s.part, [&](int n, float* acc) {
       const float bias = P[D.g2_fc2.b + n];
 #pragma unroll
       for (int b = 0; b < BT; ++b) s.gm[(MEM + n) * BT + b] = sigmoidf_(acc[b] + bias);
     });
-    __syncthreads();
+    cta_sync();
     // ---- mem_t = gamma1 * mem_{t-1} + gamma2 * cHat -----------------------------------------------
     for (int e = tid; e < MEM * BT; e += NTHREADS) {
       float mn = s.gm[e] * s.mem[e] + s.gm[MEM * BT + e] * s.chat[e];
       s.mem[e] = mn;
       s.last[Hs * BT + e] = mn;
     }
-    __syncthreads();
+    cta_sync();
     if (a.training) {
       stash_rows(a.S.a2, A2, s.a2, rows, nb); stash_rows(a.S.chat, MEM, s.chat, rows, nb);
       stash_rows(a.S.gh, 2 * G, s.gh, rows, nb); stash_rows(a.S.gm, 2 * MEM, s.gm, rows, nb);
       stash_rows(a.S.last, Hs + MEM, s.last, rows, nb);
     }
     // ---- output head: y_t = out_fc2(drop(relu(out_fc1([h_t || mem_t])))) * mask ------------------------
-    dense<WT>(TP + D.t_out_fc1, O, Hs + MEM, O, s.last, s.part, [&](int n, float* acc) {
+    dense<STREAM, WT>(ring, TP + D.t_out_fc1, Hs + MEM, O, s.last, s.part, [&](int n, float* acc) {
       const float bias = P[D.out_fc1.b + n];
 #pragma unroll
       for (int b = 0; b < BT; ++b) {
@@ -320,7 +330,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mfn_fwd_kernel(const __grid_const
         s.oh[n * BT + b] = v;
       }
     });
-    __syncthreads();
+    cta_sync();
     if (a.training) stash_rows(a.S.oh, O, s.oh, rows, nb);
     if (warp < BT) {
       float acc = 0.f;
@@ -333,7 +343,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mfn_fwd_kernel(const __grid_const
         a.out[(size_t)b * a.T + t] = y;
       }
     }
-    __syncthreads();
+    cta_sync();
   }
   // final state (MFN.h / MFN.c / MFN.mem attributes of the reference module)
   for (int e = tid; e < nb * Hs; e += NTHREADS) {
@@ -348,12 +358,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) mfn_fwd_kernel(const __grid_const
 // ------------------------------------------------------------------------------------------------------
 // reverse-time kernel.  Weights are the row-major originals W[out][in] viewed as Wt with K = out, N = in.
 // ------------------------------------------------------------------------------------------------------
-template <typename WT>
-__global__ void __launch_bounds__(NTHREADS, 1) mfn_bwd_kernel(const __grid_constant__ KArgs a) {
-  extern __shared__ __align__(16) float smem[];
+template <bool STREAM, typename WT>
+__global__ void __launch_bounds__(NTHREADS + 32, 1) mfn_bwd_kernel(const __grid_constant__ KArgs a) {
+  extern __shared__ __align__(128) float smem[];
   const Dims& D = a.D;
   const int Hs = D.Hs, H2 = 2 * D.Hs, MEM = D.MEM, A1 = D.A1, A2 = D.A2, G = D.G, O = D.O;
-  float* p = smem;
+  float* p = smem + (STREAM ? RING_BYTES / sizeof(float) : 0);
   float* dh = p; p += Hs * BT;            // carries (gradient wrt h_t, c_t, mem_t arriving from step t+1)
   float* dc = p; p += Hs * BT;
   float* dmem = p; p += MEM * BT;
@@ -381,6 +391,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) mfn_bwd_kernel(const __grid_const
   float* part = p;
   __shared__ long long rows[BT];
   __shared__ float dyv[BT];
+  // weight ring (STREAM): barriers + slots live at the start of the dynamic shared memory block
+  WRing ring = ring_setup(reinterpret_cast<uint8_t*>(smem), STREAM && threadIdx.x == 0);
+  if (STREAM) {
+    __syncthreads();                              // the only CTA-wide barrier that includes the producer warp
+    if (threadIdx.x >= NTHREADS) {
+      if (threadIdx.x == NTHREADS) stream_producer<WT>(a.tab, a.T, a.T - 1, ring);
+      return;
+    }
+  }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b0 = blockIdx.x * BT;
   const int nb = min(BT, a.B - b0);
@@ -390,7 +409,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mfn_bwd_kernel(const __grid_const
 
   for (int e = tid; e < Hs * BT; e += NTHREADS) { dh[e] = 0.f; dc[e] = 0.f; }
   for (int e = tid; e < MEM * BT; e += NTHREADS) dmem[e] = 0.f;
-  __syncthreads();
+  cta_sync();
 
   for (int t = a.T - 1; t >= 0; --t) {
     if (tid < BT) {
@@ -401,7 +420,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mfn_bwd_kernel(const __grid_const
       dyv[tid] = g;
       if (tid < nb) a.S.dyv[rows[tid]] = g;
     }
-    __syncthreads();
+    cta_sync();
     load_rows(oh, O, a.S.oh, rows, nb);
     load_rows(gm, 2 * MEM, a.S.gm, rows, nb);
     load_rows(gh, 2 * G, a.S.gh, rows, nb);
@@ -412,20 +431,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) mfn_bwd_kernel(const __grid_const
     load_rows(cstar, H2, a.S.cstar, rows, nb);
     load_rows(a1, A1, a.S.a1, rows, nb);
     load_rows(gates, 4 * Hs, a.S.gates, rows, nb);
-    __syncthreads();
+    cta_sync();
     // ---- head: d_oh = dy * w_o2 gated by (oh > 0) -------------------------------------------------
     for (int e = tid; e < O * BT; e += NTHREADS) {
       int j = e / BT, b = e % BT;
       dzoh[e] = oh[e] > 0.f ? dyv[b] * P[D.out_fc2.w + j] * sc_o : 0.f;
     }
-    __syncthreads();
+    cta_sync();
     stash_rows(a.S.dzoh, O, dzoh, rows, nb);
-    dense<WT>(W + D.out_fc1.w, Hs + MEM, O, Hs + MEM, dzoh, part, [&](int n, float* acc) {
+    dense<STREAM, WT>(ring, W + D.out_fc1.w, O, Hs + MEM, dzoh, part, [&](int n, float* acc) {
       float* dst = n < Hs ? dh + n * BT : dmem + (n - Hs) * BT;
 #pragma unroll
       for (int b = 0; b < BT; ++b) dst[b] += acc[b];
     });
-    __syncthreads();
+    cta_sync();
     // ---- mem_t = gm1*mem_prev + gm2*chat ----------------------------------------------------------
     for (int e = tid; e < MEM * BT; e += NTHREADS) {
       const float g = dmem[e], g1 = gm[e], g2 = gm[MEM * BT + e];
@@ -435,40 +454,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) mfn_bwd_kernel(const __grid_const
       dzchat[e] = g * g2 * (1.f - ch * ch);
       dmem[e] = g * g1;                                            // direct path to mem_{t-1}
     }
-    __syncthreads();
+    cta_sync();
     stash_rows(a.S.dzg, 2 * MEM, dzg, rows, nb);
     stash_rows(a.S.dzchat, MEM, dzchat, rows, nb);
-    dense<WT>(W + D.g1_fc2.w, G, MEM, G, dzg, part, [&](int n, float* acc) {
+    dense<STREAM, WT>(ring, W + D.g1_fc2.w, MEM, G, dzg, part, [&](int n, float* acc) {
 #pragma unroll
       for (int b = 0; b < BT; ++b) dgh[n * BT + b] = gh[n * BT + b] > 0.f ? acc[b] * sc_g : 0.f;
     });
-    dense<WT>(W + D.g2_fc2.w, G, MEM, G, dzg + MEM * BT, part, [&](int n, float* acc) {
+    dense<STREAM, WT>(ring, W + D.g2_fc2.w, MEM, G, dzg + MEM * BT, part, [&](int n, float* acc) {
 #pragma unroll
       for (int b = 0; b < BT; ++b) dgh[(G + n) * BT + b] = gh[(G + n) * BT + b] > 0.f ? acc[b] * sc_g : 0.f;
     });
-    dense<WT>(W + D.att2_fc2.w, A2, MEM, A2, dzchat, part, [&](int n, float* acc) {
+    dense<STREAM, WT>(ring, W + D.att2_fc2.w, MEM, A2, dzchat, part, [&](int n, float* acc) {
 #pragma unroll
       for (int b = 0; b < BT; ++b) da2[n * BT + b] = a2[n * BT + b] > 0.f ? acc[b] : 0.f;
     });
-    __syncthreads();
+    cta_sync();
     stash_rows(a.S.dgh, 2 * G, dgh, rows, nb);
     stash_rows(a.S.da2, A2, da2, rows, nb);
     // ---- d both = gamma1_fc1^T dgh1 + gamma2_fc1^T dgh2 ; d attended += att2_fc1^T da2 ------------------
-    dense<WT>(W + D.g1_fc1.w, H2 + MEM, G, H2 + MEM, dgh, part, [&](int n, float* acc) {
+    dense<STREAM, WT>(ring, W + D.g1_fc1.w, G, H2 + MEM, dgh, part, [&](int n, float* acc) {
 #pragma unroll
       for (int b = 0; b < BT; ++b) dboth[n * BT + b] = acc[b];
     });
-    __syncthreads();
-    dense<WT>(W + D.g2_fc1.w, H2 + MEM, G, H2 + MEM, dgh + G * BT, part, [&](int n, float* acc) {
+    cta_sync();
+    dense<STREAM, WT>(ring, W + D.g2_fc1.w, G, H2 + MEM, dgh + G * BT, part, [&](int n, float* acc) {
 #pragma unroll
       for (int b = 0; b < BT; ++b) dboth[n * BT + b] += acc[b];
     });
-    __syncthreads();
-    dense<WT>(W + D.att2_fc1.w, H2, A2, H2, da2, part, [&](int n, float* acc) {
+    cta_sync();
+    dense<STREAM, WT>(ring, W + D.att2_fc1.w, A2, H2, da2, part, [&](int n, float* acc) {
 #pragma unroll
       for (int b = 0; b < BT; ++b) dboth[n * BT + b] += acc[b];
     });
-    __syncthreads();
+    cta_sync();
     for (int e = tid; e < MEM * BT; e += NTHREADS) dmem[e] += dboth[H2 * BT + e];     // both = attended || mem_{t-1}
     // ---- attended = att * cstar ; att = softmax(logits) -------------------------------------------
     if (warp < BT) {
@@ -481,19 +500,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) mfn_bwd_kernel(const __grid_const
         dcstar[f * BT + warp] = da * pa;
       }
     }
-    __syncthreads();
+    cta_sync();
     stash_rows(a.S.dlogit, H2, dlogit, rows, nb);
-    dense<WT>(W + D.att1_fc2.w, A1, H2, A1, dlogit, part, [&](int n, float* acc) {
+    dense<STREAM, WT>(ring, W + D.att1_fc2.w, H2, A1, dlogit, part, [&](int n, float* acc) {
 #pragma unroll
       for (int b = 0; b < BT; ++b) da1[n * BT + b] = a1[n * BT + b] > 0.f ? acc[b] : 0.f;
     });
-    __syncthreads();
+    cta_sync();
     stash_rows(a.S.da1, A1, da1, rows, nb);
-    dense<WT>(W + D.att1_fc1.w, H2, A1, H2, da1, part, [&](int n, float* acc) {
+    dense<STREAM, WT>(ring, W + D.att1_fc1.w, A1, H2, da1, part, [&](int n, float* acc) {
 #pragma unroll
       for (int b = 0; b < BT; ++b) dcstar[n * BT + b] += acc[b];
     });
-    __syncthreads();
+    cta_sync();
     // ---- LSTM cell backward -----------------------------------------------------------------------
     for (int e = tid; e < Hs * BT; e += NTHREADS) {
       const int j = e / BT, b = e % BT;
@@ -513,31 +532,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) mfn_bwd_kernel(const __grid_const
       dzm[(3 * H + jj) * BT + b] = dhv * tc * go * (1.f - go);
       dc[e] = dcstar[j * BT + b] + dcv * gf;                       // gradient wrt c_{t-1}
     }
-    __syncthreads();
+    cta_sync();
     stash_rows(a.S.dz_lstm, 4 * Hs, dz, rows, nb);
     for (int m = 0; m < D.n_mods; ++m) {
       const int H = D.H[m];
       float* dst = dhp + D.hoff[m] * BT;
-      dense<WT>(W + D.w_hh[m], H, 4 * H, H, dz + 4 * D.hoff[m] * BT, part, [&](int n, float* acc) {
+      dense<STREAM, WT>(ring, W + D.w_hh[m], 4 * H, H, dz + 4 * D.hoff[m] * BT, part, [&](int n, float* acc) {
 #pragma unroll
         for (int b = 0; b < BT; ++b) dst[n * BT + b] = acc[b];
       });
     }
-    __syncthreads();
+    cta_sync();
     for (int e = tid; e < Hs * BT; e += NTHREADS) dh[e] = dhp[e];
-    __syncthreads();
+    cta_sync();
   }
 }
 
 size_t fwd_smem_floats(const Dims& D) {
   const int Hs = D.Hs, H2 = 2 * D.Hs;
   size_t f = (size_t)Hs * 2 + D.MEM + 4 * Hs + H2 + D.A1 + H2 + (H2 + D.MEM) + D.A2 + D.MEM + 2 * D.G + 2 * D.MEM + (Hs + D.MEM) + D.O;
-  return f * BT + (size_t)PART_FLOATS;
+  return f * BT + (size_t)PART_FLOATS + RING_BYTES / sizeof(float);
 }
 size_t bwd_smem_floats(const Dims& D) {
   const int Hs = D.Hs, H2 = 2 * D.Hs;
   size_t f = (size_t)Hs * 3 + D.MEM + D.O + 4 * D.MEM + 4 * D.G + 2 * (H2 + D.MEM) + 2 * D.MEM + 2 * D.A2 + 4 * H2 + 2 * D.A1 + 8 * Hs + D.O;
-  return f * BT + (size_t)PART_FLOATS;
+  return f * BT + (size_t)PART_FLOATS + RING_BYTES / sizeof(float);
 }
 
 int layout_strides(const MtMfnCfg& c, const Dims& D, const int64_t* stride_b, const int64_t* stride_t, long long& sb, long long& st) {
@@ -636,13 +655,27 @@ int mt_mfn_fwd(const MtMfnCfg* cfg, const float* params, const void* params_lp, 
   const size_t smem = fwd_smem_floats(D) * sizeof(float);
   mt_prof_work(2.0 * (double)D.t_total * c.B * c.T, 0.0);
   const int grid = (c.B + BT - 1) / BT;
-  if (lp) {
-    MT_TRY(set_smem(mfn_fwd_kernel<bf16>, smem));
-    mfn_fwd_kernel<bf16><<<grid, NTHREADS, smem, st>>>(a);
-  } else {
-    MT_TRY(set_smem(mfn_fwd_kernel<float>, smem));
-    mfn_fwd_kernel<float><<<grid, NTHREADS, smem, st>>>(a);
-  }
+  // weight blocks in the order the kernel consumes them each step
+  a.tab.n = 0;
+  auto add = [&](size_t off, int K, int N) {
+    StreamLayer& Lr = a.tab.L[a.tab.n++];
+    Lr.ptr = lp ? (const void*)((const bf16*)S.tpack + off) : (const void*)((const float*)S.tpack + off);
+    Lr.ptr_special = nullptr; Lr.K = K; Lr.N = N;
+  };
+  for (int m = 0; m < D.n_mods; ++m) add(D.t_hh[m], D.H[m], 4 * D.H[m]);
+  add(D.t_att1_fc1, H2, D.A1); add(D.t_att1_fc2, D.A1, H2); add(D.t_att2_fc1, H2, D.A2); add(D.t_g_fc1, H2 + D.MEM, 2 * D.G);
+  add(D.t_att2_fc2, D.A2, D.MEM); add(D.t_g1_fc2, D.G, D.MEM); add(D.t_g2_fc2, D.G, D.MEM); add(D.t_out_fc1, D.Hs + D.MEM, D.O);
+#define MT_MFN_LAUNCH(KERNEL, WT_)                                                        \
+  do {                                                                                     \
+    if (stream_table_ok<WT_>(a.tab)) {                                                     \
+      MT_TRY(set_smem(KERNEL<true, WT_>, smem));                                           \
+      KERNEL<true, WT_><<<grid, NTHREADS + 32, smem, st>>>(a);                             \
+    } else {                                                                               \
+      MT_TRY(set_smem(KERNEL<false, WT_>, smem));                                          \
+      KERNEL<false, WT_><<<grid, NTHREADS, smem, st>>>(a);                                 \
+    }                                                                                      \
+  } while (0)
+  if (lp) MT_MFN_LAUNCH(mfn_fwd_kernel, bf16); else MT_MFN_LAUNCH(mfn_fwd_kernel, float);
   MT_LAUNCH_CHECK();
   return MT_OK;
 }
@@ -677,13 +710,18 @@ int mt_mfn_bwd(const MtMfnCfg* cfg, const float* params, const void* params_lp, 
   const size_t smem = bwd_smem_floats(D) * sizeof(float);
   mt_prof_work(2.0 * (double)D.t_total * c.B * c.T, 0.0);
   const int grid = (c.B + BT - 1) / BT;
-  if (lp) {
-    MT_TRY(set_smem(mfn_bwd_kernel<bf16>, smem));
-    mfn_bwd_kernel<bf16><<<grid, NTHREADS, smem, st>>>(a);
-  } else {
-    MT_TRY(set_smem(mfn_bwd_kernel<float>, smem));
-    mfn_bwd_kernel<float><<<grid, NTHREADS, smem, st>>>(a);
-  }
+  a.tab.n = 0;
+  auto add = [&](size_t off, int K, int N) {
+    StreamLayer& Lr = a.tab.L[a.tab.n++];
+    Lr.ptr = lp ? (const void*)((const bf16*)params_lp + off) : (const void*)(params + off);
+    Lr.ptr_special = nullptr; Lr.K = K; Lr.N = N;
+  };
+  // row-major originals W[out][in] consumed as K = out, N = in, in the order of the reverse-time kernel
+  add(D.out_fc1.w, D.O, Hs + MEM); add(D.g1_fc2.w, MEM, D.G); add(D.g2_fc2.w, MEM, D.G); add(D.att2_fc2.w, MEM, D.A2);
+  add(D.g1_fc1.w, D.G, H2 + MEM); add(D.g2_fc1.w, D.G, H2 + MEM); add(D.att2_fc1.w, D.A2, H2); add(D.att1_fc2.w, H2, D.A1);
+  add(D.att1_fc1.w, D.A1, H2);
+  for (int m = 0; m < D.n_mods; ++m) add(D.w_hh[m], 4 * D.H[m], D.H[m]);
+  if (lp) MT_MFN_LAUNCH(mfn_bwd_kernel, bf16); else MT_MFN_LAUNCH(mfn_bwd_kernel, float);
   MT_LAUNCH_CHECK();
 
   // ---- batched weight gradients over all T*B rows ----------------------------------------------------

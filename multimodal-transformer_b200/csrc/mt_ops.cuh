@@ -36,6 +36,12 @@ int mt_act_bwd_run(int M, int N, const void* dy, bool dy_bf16, const void* y, bo
 struct TransposeJob { const float* src; void* dst; int R, C, ldd; };
 int mt_transpose_pack_run(const TransposeJob* jobs, int n_jobs, bool dst_bf16, cudaStream_t st);
 
+// ---- tensor-core attention engine for bf16 (mt_attention_mma.cu) --------------------------------------------
+bool mt_attn_mma_supported(int B, int T, int d, int h);
+int mt_attn_mma_fwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop, cudaStream_t st);
+int mt_attn_mma_bwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse, const void* dout,
+                        void* dqkv, DropCfg drop, cudaStream_t st);
+
 // ---- attention (mt_attention.cu) ---------------------------------------------------------------------
 int mt_attn_fwd_run(int dtype, int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop,
                     cudaStream_t st);

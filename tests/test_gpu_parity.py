@@ -182,6 +182,37 @@ def test_attention_fwd_bwd(B, T, d, h, p):
         assert torch.allclose(probs[-1, :, T // 2:, :], torch.full_like(probs[-1, :, T // 2:, :], 1.0 / T), rtol=1e-6)   # trap A.1
 
 
+@pytest.mark.parametrize('B,T,d,h,p', [(2, 128, 256, 8, 0.0), (3, 37, 256, 8, 0.1), (2, 200, 128, 8, 0.0), (2, 70, 512, 8, 0.1),
+                                       (1, 64, 256, 8, 0.1), (2, 130, 256, 8, 0.0)])
+def test_attention_tensor_core_engine_bf16(B, T, d, h, p):
+    """bf16 mode: the mma.sync engine against the fp64 oracle on the same bf16-rounded inputs and the same dropout
+    masks, and against the FFMA engine."""
+    mtb.set_compute_dtype('bf16')
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    qkv = (torch.randn(B, T, 3 * d, generator=g) * 0.7).bfloat16()
+    mask = torch.ones(B, T); mask[-1, T // 2:] = 0
+    dout = torch.randn(B, T, d, generator=g).bfloat16()
+    seed = 4711
+    qr = qkv.double().requires_grad_(True)
+    outr, _ = _attn_ref(qr, mask.double(), h, Dropper(seed) if p > 0 else None, p, 0)
+    outr.backward(dout.double())
+    res = {}
+    for force in (1, 0):
+        old = _lib.lib().mt_attention_force_ffma(force)
+        mtb.fix_seed(seed)
+        qd = qkv.to(DEV).requires_grad_(True)
+        out = K.attention_packed(qd, mask.to(DEV), h, p)
+        out.backward(dout.to(DEV))
+        _lib.lib().mt_attention_force_ffma(old)
+        res[force] = (out.detach().float().cpu(), qd.grad.float().cpu())
+        assert_close(res[force][0], outr, 1.5e-2, f'out force_ffma={force}')
+        assert_close(res[force][1], qr.grad, 2.5e-2, f'dqkv force_ffma={force}')
+    # padded query rows: uniform attention over ALL keys (trap A.1), through the tensor-core engine too
+    if p == 0:
+        v = qkv[-1, :, 2 * d:].float()
+        assert_close(res[0][0][-1, T - 1], v.mean(0), 2e-2, 'masked row = mean(V)')
+
+
 def test_mha_golden_and_attn_attribute():
     gold = util.gold('mha')
     shapes = {f'linears.{i}.{p}': s for i in range(4) for p, s in (('weight', (256, 256)), ('bias', (256,)))}
