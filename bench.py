@@ -156,7 +156,7 @@ def run_ours(args, rank, local_rank, world):
     import torch.distributed as dist
     import multimodal_transformer_b200 as mtb
     from multimodal_transformer_b200 import _lib
-    from multimodal_transformer_b200.training import FlatAdam, train_step_loss
+    from multimodal_transformer_b200.training import FlatAdam, GraphedForward, GraphedTrainStep, train_step_loss
     from multimodal_transformer_b200 import synthetic as fill      # deterministic synthetic inputs (torch-free)
 
     torch.cuda.set_device(local_rank)
@@ -182,35 +182,45 @@ def run_ours(args, rank, local_rank, world):
     loss_host = torch.zeros(1).pin_memory()
     pred_host = torch.zeros(B, T, 1).pin_memory()
 
+    # eager path (one launch at a time; used for the per-kernel breakdown and reported as `eager`)
     def train_step(e2e):
-        if e2e:
-            x = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-            m, tg = host_mask.to(dev, non_blocking=True), host_target.to(dev, non_blocking=True)
-        else:
-            x, m, tg = res, res_mask, res_target
+        x, m, tg = res, res_mask, res_target
         model.train()
         pred = model(x, m, lengths)
         loss = train_step_loss(pred, tg, norm)
         opt.step()
         opt.zero_grad()
+        return loss
+
+    # the product path: the whole step captured once into a CUDA graph (multimodal_transformer_b200.training)
+    gstep = GraphedTrainStep(model, opt, B, T, DIMS, dev, norm_fn=lambda _l: norm)
+    for _ in range(2):
+        train_step(False)
+    gstep.load(res, res_mask, res_target, lengths)
+    l0 = L.mt_launch_count()
+    gstep.capture()
+    launches_per_step = (L.mt_launch_count() - l0) // (gstep.warmup + 1)
+    gfwd = GraphedForward(model, B, T, DIMS, dev)
+    gfwd.load(res, res_mask)
+    gfwd.capture()
+
+    def g_train(e2e):
+        if e2e:
+            gstep.load(host, host_mask, host_target, lengths)          # pinned host -> static device buffers
+        loss = gstep.replay()
         if e2e:
             loss_host.copy_(loss, non_blocking=True)
             torch.cuda.current_stream().synchronize()
         return loss
 
-    def infer_step(e2e):
-        model.eval()
-        with torch.no_grad():
-            if e2e:
-                x = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-                m = host_mask.to(dev, non_blocking=True)
-            else:
-                x, m = res, res_mask
-            pred = model(x, m, lengths)
-            if e2e:
-                pred_host.copy_(pred, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-        return pred
+    def g_infer(e2e):
+        if e2e:
+            gfwd.load(host, host_mask)
+        gfwd.graph.replay()
+        if e2e:
+            pred_host.copy_(gfwd.pred, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return gfwd.pred
 
     def timed(fn, e2e, warm, steps):
         for _ in range(warm):
@@ -219,7 +229,6 @@ def run_ours(args, rank, local_rank, world):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        l0 = L.mt_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
@@ -232,23 +241,29 @@ def run_ours(args, rank, local_rank, world):
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item() / steps, L.mt_launch_count() - l0
+        return ms.item() / steps
 
     W, K = max(3, args.warmup), args.steps
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms_train, launches = timed(train_step, False, W, K)
+    ms_train = timed(g_train, False, W, K)
     clocks = sampler.stop() if sampler else None
-    ms_inf, _ = timed(infer_step, False, W, K)
-    ms_train_e2e, _ = timed(train_step, True, W, K)
-    ms_inf_e2e, _ = timed(infer_step, True, W, K)
+    launches = launches_per_step * K
+    ms_inf = timed(g_infer, False, W, K)
+    ms_train_e2e = timed(g_train, True, W, K)
+    ms_inf_e2e = timed(g_infer, True, W, K)
+    ms_eager = timed(train_step, False, 2, max(2, min(K, 5)))
 
     # ---- per-kernel breakdown of the train step (after the timed regions; events after every launch) ---------
     roofline, kernels = None, None
     if rank == 0 and not args.no_profile:
         P = peaks()
-        nprof = 2
+        nprof = 1
+        # the host needs ~30 us per launch; a busy-wait kernel in front lets it run ahead so that consecutive event
+        # records bracket a kernel's true duration instead of the host's enqueue gap
+        torch.cuda.synchronize()
+        _lib.check(L.mt_spin(60.0, _lib.stream()))
         _lib.check(L.mt_prof_start(20000, _lib.stream()))
         for _ in range(nprof):
             train_step(False)
@@ -265,7 +280,7 @@ def run_ours(args, rank, local_rank, world):
         tot = sum(a[0] for a in agg.values())
         kernels = []
         for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0]):
-            ent = dict(site=k, launches_per_step=a[3] / nprof, ms_per_step=a[0] / nprof, share=a[0] / tot)
+            ent = dict(site=k, launches_per_step=a[3] / nprof, ms_per_step=a[0] / nprof, share=a[0] / nprof / ms_train)
             if a[1] > 0:
                 ent['tflops'] = a[1] / (a[0] * 1e-3) / 1e12
             if a[2] > 0:
@@ -314,6 +329,9 @@ def run_ours(args, rank, local_rank, world):
             'e2e': {'value': gb / (ms_train_e2e * 1e-3), 'unit': 'narratives/s', 'ms_per_step': ms_train_e2e, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': 4},
             'gpu_launches': int(launches),
+            'launch_mode': f'one CUDA graph per step ({int(launches_per_step)} kernel nodes from libmt_b200.so, captured once); '
+                           f'eager launch of the same step: {ms_eager:.2f} ms',
+            'eager': {'ms_per_step': ms_eager, 'value': gb / (ms_eager * 1e-3)},
             'clocks': clocks,
             'model_flops_utilisation': {'train_tflops_per_gpu': 3 * FLOP_PER_TOKEN_FWD * B * T / (ms_train * 1e-3) / 1e12 if T == 128 and N == 6 else None},
             'roofline': roofline, 'kernels': kernels, 'cpu_baseline': cpu,

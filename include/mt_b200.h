@@ -206,6 +206,19 @@ int mt_mse_loss_fwd_bwd(const float* pred, const float* target, size_t n, float 
 int mt_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
                  float weight_decay, int step, void* stream);
 
+/* Captured-graph variants: the per-step scalars live in DEVICE memory so one CUDA graph of the whole train step can be
+ * replayed with a different loss normaliser / learning rate / step count each time.  step_dev holds the 1-based step
+ * count of THIS update; p_lp (optional) receives the bf16 shadow of the updated parameters in the same launch. */
+int mt_mse_loss_fwd_bwd_dev(const float* pred, const float* target, size_t n, const float* inv_norm_dev, float* loss, float* dpred,
+                            void* stream);
+int mt_adam_step_dev(float* p, const float* g, float* m, float* v, size_t n, const float* lr_dev, float lr, float beta1, float beta2,
+                     float eps, float weight_decay, const int64_t* step_dev, void* p_lp, void* stream);
+/* Every dropout site adds *dev_ptr (a device uint64, may be NULL = 0) to its seed: bump it between replays of a captured
+ * graph to draw fresh masks.  Process-wide. */
+int mt_set_seed_offset_ptr(const uint64_t* dev_ptr);
+/* Busy-wait kernel (ms <= 2000): lets the host run ahead of the device so per-launch event timings are back to back. */
+int mt_spin(float ms, void* stream);
+
 /* Generic GEMM (exposed for tests and profiling):  C[M,N] = A·B^T-style contraction, see csrc/mt_gemm.cuh.
  * a_kmajor: A element (m,k) at A[m*lda+k] (else A[k*lda+m]); b_kmajor: B element (n,k) at B[n*ldb+k] (else B[k*ldb+n]). */
 int mt_gemm(int dtype, int M, int N, int K, const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor,

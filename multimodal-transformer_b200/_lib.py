@@ -75,6 +75,10 @@ _PROTOS = {
     'mt_cast_bf16_to_f32': (c_int, [P, P, c_size_t, P]),
     'mt_mse_loss_fwd_bwd': (c_int, [P, P, c_size_t, c_float, P, P, P]),
     'mt_adam_step': (c_int, [P, P, P, P, c_size_t, c_float, c_float, c_float, c_float, c_float, c_int, P]),
+    'mt_mse_loss_fwd_bwd_dev': (c_int, [P, P, c_size_t, P, P, P, P]),
+    'mt_adam_step_dev': (c_int, [P, P, P, P, c_size_t, P, c_float, c_float, c_float, c_float, c_float, P, P, P]),
+    'mt_set_seed_offset_ptr': (c_int, [P]),
+    'mt_spin': (c_int, [c_float, P]),
     'mt_gemm': (c_int, [c_int, c_int, c_int, c_int, P, c_int, c_int, P, c_int, c_int, P, c_int, c_int, P, c_int, c_int, P]),
     'mt_gemm_engine': (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
     'mt_gemm_force_simt': (c_int, [c_int]),

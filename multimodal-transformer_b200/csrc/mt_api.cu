@@ -5,6 +5,15 @@
 
 char g_mt_cuda_err[512] = "";
 unsigned long long g_mt_launches = 0ull;
+const unsigned long long* g_mt_seed_offset_ptr = nullptr;
+
+namespace {
+__global__ void spin_kernel(long long ns) {
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+  do { asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1)); } while ((long long)(t1 - t0) < ns);
+}
+}  // namespace
 
 int mt_set_cuda_error(cudaError_t e, const char* file, int line) {
   snprintf(g_mt_cuda_err, sizeof(g_mt_cuda_err), "%s (%s) at %s:%d", cudaGetErrorName(e), cudaGetErrorString(e), file, line);
@@ -72,6 +81,19 @@ int mt_prof_get(int i, char* name, int name_cap, float* ms, double* flops, doubl
   snprintf(name, (size_t)name_cap, "%s", g_recs[i].name);
   if (flops) *flops = g_recs[i].flops;
   if (bytes) *bytes = g_recs[i].bytes;
+  return MT_OK;
+}
+
+int mt_set_seed_offset_ptr(const uint64_t* dev_ptr) {
+  g_mt_seed_offset_ptr = reinterpret_cast<const unsigned long long*>(dev_ptr);
+  return MT_OK;
+}
+
+int mt_spin(float ms, void* stream) {
+  if (ms < 0.f || ms > 2000.f) return MT_ERR_ARG;
+  spin_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long)(ms * 1e6f));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return mt_set_cuda_error(e, __FILE__, __LINE__);
   return MT_OK;
 }
 

@@ -40,7 +40,8 @@ __device__ __forceinline__ void stage_tile(float* s, const T* base /* (b, row 0,
 template <typename T, int DK>
 __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(int B, int T_, int d, int h, const T* __restrict__ qkv,
                                                               const float* __restrict__ mask, T* __restrict__ out,
-                                                              float* __restrict__ lse, DropCfg drop, float scale) {
+                                                              float* __restrict__ lse, DropCfg drop_in, float scale) {
+  const DropCfg drop = mt_drop_resolve(drop_in);
   constexpr int KT = AT_TILE_ELEMS / DK;
   __shared__ __align__(16) float Ks[KT * DK];
   __shared__ __align__(16) float Vs[KT * DK];
@@ -109,8 +110,9 @@ template <typename T, int DK>
 __global__ void __launch_bounds__(AT_THREADS) attn_bwd_dq_kernel(int B, int T_, int d, int h, const T* __restrict__ qkv,
                                                                  const float* __restrict__ mask, const T* __restrict__ out,
                                                                  const float* __restrict__ lse, const T* __restrict__ dout,
-                                                                 T* __restrict__ dqkv, float* __restrict__ Dws, DropCfg drop,
+                                                                 T* __restrict__ dqkv, float* __restrict__ Dws, DropCfg drop_in,
                                                                  float scale) {
+  const DropCfg drop = mt_drop_resolve(drop_in);
   constexpr int KT = AT_TILE_ELEMS / DK;
   __shared__ __align__(16) float Ks[KT * DK];
   __shared__ __align__(16) float Vs[KT * DK];
@@ -177,7 +179,8 @@ template <typename T, int DK>
 __global__ void __launch_bounds__(AT_THREADS) attn_bwd_dkv_kernel(int B, int T_, int d, int h, const T* __restrict__ qkv,
                                                                   const float* __restrict__ mask, const float* __restrict__ lse,
                                                                   const T* __restrict__ dout, T* __restrict__ dqkv,
-                                                                  const float* __restrict__ Dws, DropCfg drop, float scale) {
+                                                                  const float* __restrict__ Dws, DropCfg drop_in, float scale) {
+  const DropCfg drop = mt_drop_resolve(drop_in);
   constexpr int QT = AT_TILE_ELEMS / DK;
   __shared__ __align__(16) float Qs[QT * DK];
   __shared__ __align__(16) float Gs[QT * DK];

@@ -102,7 +102,8 @@ __device__ __forceinline__ void mma_p_s(float (*o)[4], const uint32_t (*pa)[4], 
 template <int DK>
 __global__ void __launch_bounds__(THREADS) attn_mma_fwd_kernel(int B, int T, int d, int h, const bf16* __restrict__ qkv,
                                                                const float* __restrict__ mask, bf16* __restrict__ out,
-                                                               float* __restrict__ lse, DropCfg drop, float scale) {
+                                                               float* __restrict__ lse, DropCfg drop_in, float scale) {
+  const DropCfg drop = mt_drop_resolve(drop_in);
   constexpr int LD = DK + 8;
   __shared__ __align__(16) bf16 Ks[TILE * LD];
   __shared__ __align__(16) bf16 Vs[TILE * LD];
@@ -189,7 +190,8 @@ template <int DK>
 __global__ void __launch_bounds__(THREADS) attn_mma_bwd_kernel(int B, int T, int d, int h, const bf16* __restrict__ qkv,
                                                                const float* __restrict__ mask, const bf16* __restrict__ out,
                                                                const float* __restrict__ lse, const bf16* __restrict__ dout,
-                                                               bf16* __restrict__ dqkv, DropCfg drop, float scale) {
+                                                               bf16* __restrict__ dqkv, DropCfg drop_in, float scale) {
+  const DropCfg drop = mt_drop_resolve(drop_in);
   constexpr int LD = DK + 8;
   __shared__ __align__(16) bf16 S0[TILE * LD];
   __shared__ __align__(16) bf16 S1[TILE * LD];

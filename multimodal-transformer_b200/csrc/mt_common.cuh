@@ -105,13 +105,22 @@ struct DropCfg {
   float scale;       // 1/(1-p)
   uint64_t seed;
   uint32_t site;
+  const unsigned long long* seed_off;   // optional device word added to `seed` (lets a captured CUDA graph draw fresh masks per replay)
 };
+extern const unsigned long long* g_mt_seed_offset_ptr;   // set by mt_set_seed_offset_ptr (mt_api.cu)
 static inline DropCfg mt_make_drop(float p, uint64_t seed, uint32_t site) {
   DropCfg d;
   d.thresh = (p > 0.f) ? mt_drop_threshold(p) : 0u;
   d.scale = (p > 0.f) ? 1.0f / (1.0f - p) : 1.0f;
   d.seed = seed;
   d.site = site;
+  d.seed_off = (p > 0.f) ? g_mt_seed_offset_ptr : nullptr;
+  return d;
+}
+// fold the optional device-side seed offset into the seed ONCE per thread, at kernel entry
+__device__ __forceinline__ DropCfg mt_drop_resolve(DropCfg d) {
+  if (d.thresh != 0u && d.seed_off) d.seed += (uint64_t)__ldg(d.seed_off);
+  d.seed_off = nullptr;
   return d;
 }
 __device__ __forceinline__ float mt_drop_factor(const DropCfg& d, uint64_t idx) {

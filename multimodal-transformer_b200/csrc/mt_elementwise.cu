@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(int M, const floa
 }
 
 template <typename TO>
-__global__ void drop_grad_kernel(size_t n4, const float* __restrict__ g, TO* __restrict__ out, DropCfg drop) {
+__global__ void drop_grad_kernel(size_t n4, const float* __restrict__ g, TO* __restrict__ out, DropCfg drop_in) {
+  const DropCfg drop = mt_drop_resolve(drop_in);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 v = ld4(g + i * 4);
     v.x *= mt_drop_factor(drop, i * 4 + 0);
@@ -152,13 +153,15 @@ __global__ void drop_grad_kernel(size_t n4, const float* __restrict__ g, TO* __r
 
 // out = x + y * dropout_factor   (SublayerConnection residual, stand-alone path)
 __global__ void residual_dropout_kernel(size_t n, const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out,
-                                        DropCfg drop) {
+                                        DropCfg drop_in) {
+  const DropCfg drop = mt_drop_resolve(drop_in);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     out[i] = (x ? x[i] : 0.f) + y[i] * mt_drop_factor(drop, i);
 }
 
 template <typename TS, typename TD>
-__global__ void cast2d_kernel(const TS* __restrict__ src, int lds, TD* __restrict__ dst, int ldd, int rows, int cols, DropCfg drop) {
+__global__ void cast2d_kernel(const TS* __restrict__ src, int lds, TD* __restrict__ dst, int ldd, int rows, int cols, DropCfg drop_in) {
+  const DropCfg drop = mt_drop_resolve(drop_in);
   size_t n = (size_t)rows * ldd;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     int r = (int)(i / ldd), c = (int)(i % ldd);
@@ -204,7 +207,8 @@ __global__ void cast_b2f_kernel(const bf16* __restrict__ s, float* __restrict__ 
 }
 
 __global__ void mse_kernel(const float* __restrict__ pred, const float* __restrict__ target, size_t n, float inv_norm,
-                           float* __restrict__ loss, float* __restrict__ dpred) {
+                           const float* __restrict__ inv_norm_dev, float* __restrict__ loss, float* __restrict__ dpred) {
+  if (inv_norm_dev) inv_norm = __ldg(inv_norm_dev);
   float acc = 0.f;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float e = pred[i] - target[i];
@@ -225,7 +229,14 @@ __global__ void mse_kernel(const float* __restrict__ pred, const float* __restri
 
 // torch.optim.Adam (L2 weight decay added to the gradient, bias-corrected), MFT/train.py:557
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
-                            float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+                            float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
+                            const float* __restrict__ lr_dev, const long long* __restrict__ step_dev, bf16* __restrict__ p_lp) {
+  if (step_dev) {                        // captured-graph mode: the step count (and lr) live in device memory
+    const float t = (float)__ldg(step_dev);
+    bc1 = 1.0f - powf(b1, t);
+    bc2_sqrt = sqrtf(1.0f - powf(b2, t));
+  }
+  if (lr_dev) lr = __ldg(lr_dev);
   const float step = lr / bc1;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float pi = p[i];
@@ -234,7 +245,9 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
     m[i] = mi; v[i] = vi;
     float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = pi - step * (mi / denom);
+    pi -= step * (mi / denom);
+    p[i] = pi;
+    if (p_lp) p_lp[i] = __float2bfloat16(pi);
   }
 }
 
@@ -398,7 +411,17 @@ int mt_mse_loss_fwd_bwd(const float* pred, const float* target, size_t n, float 
   if (!pred || !target || !loss || n == 0) return MT_ERR_ARG;
   int grid = ew_grid(n, 256);
   if (grid > 148) grid = 148;
-  mse_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pred, target, n, inv_norm, loss, dpred);
+  mse_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pred, target, n, inv_norm, nullptr, loss, dpred);
+  MT_LAUNCH_CHECK_S((cudaStream_t)stream);
+  return MT_OK;
+}
+
+int mt_mse_loss_fwd_bwd_dev(const float* pred, const float* target, size_t n, const float* inv_norm_dev, float* loss, float* dpred,
+                            void* stream) {
+  if (!pred || !target || !loss || !inv_norm_dev || n == 0) return MT_ERR_ARG;
+  int grid = ew_grid(n, 256);
+  if (grid > 148) grid = 148;
+  mse_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pred, target, n, 0.f, inv_norm_dev, loss, dpred);
   MT_LAUNCH_CHECK_S((cudaStream_t)stream);
   return MT_OK;
 }
@@ -409,7 +432,18 @@ int mt_adam_step(float* p, const float* g, float* m, float* v, size_t n, float l
   if (n == 0) return MT_OK;
   float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
   float bc2 = (float)(1.0 - pow((double)beta2, (double)step));
-  adam_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2));
+  adam_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), nullptr,
+                                                                   nullptr, nullptr);
+  MT_LAUNCH_CHECK_S((cudaStream_t)stream);
+  return MT_OK;
+}
+
+int mt_adam_step_dev(float* p, const float* g, float* m, float* v, size_t n, const float* lr_dev, float lr, float beta1, float beta2,
+                     float eps, float weight_decay, const int64_t* step_dev, void* p_lp, void* stream) {
+  if (!p || !g || !m || !v || !step_dev) return MT_ERR_ARG;
+  if (n == 0) return MT_OK;
+  adam_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, 1.f, 1.f, lr_dev,
+                                                                   reinterpret_cast<const long long*>(step_dev), reinterpret_cast<bf16*>(p_lp));
   MT_LAUNCH_CHECK_S((cudaStream_t)stream);
   return MT_OK;
 }

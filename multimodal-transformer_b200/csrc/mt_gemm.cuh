@@ -11,7 +11,7 @@
 struct GemmEpi {
   const float* bias = nullptr;     // [N]
   int act = MT_ACT_NONE;
-  DropCfg drop = {0u, 1.0f, 0ull, 0u};   // output dropout, element index m*N + n
+  DropCfg drop = {0u, 1.0f, 0ull, 0u, nullptr};   // output dropout, element index m*N + n
   const void* gate = nullptr;      // operand-dtype [M, ldg]: out *= (gate > 0 ? gate_scale : 0)   (relu/dropout backward)
   int ldg = 0;
   float gate_scale = 1.0f;

@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(SimtArgs g) {
   }
 
   const GemmEpi& e = g.epi;
+  const DropCfg edrop = mt_drop_resolve(e.drop);
   TC* C = reinterpret_cast<TC*>(g.C);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(SimtArgs g) {
       if (e.bias) v += e.bias[n];
       if (e.act == MT_ACT_RELU) v = fmaxf(v, 0.f);
       else if (e.act == MT_ACT_TANH) v = tanhf(v);
-      v *= mt_drop_factor(e.drop, (uint64_t)m * (uint64_t)g.N + (uint64_t)n);
+      v *= mt_drop_factor(edrop, (uint64_t)m * (uint64_t)g.N + (uint64_t)n);
       if (e.gate) {
         float gt = to_f(reinterpret_cast<const TI*>(e.gate)[(size_t)m * e.ldg + n]);
         v = gt > 0.f ? v * e.gate_scale : 0.f;

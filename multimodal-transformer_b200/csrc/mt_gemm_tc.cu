@@ -23,7 +23,9 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;                 // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int STAGES = 4;
-constexpr int TC_THREADS = 320;            // TMA warp, MMA warp, 8 epilogue warps
+// epilogue warps per CTA: 4 per TMEM lane quarter for the 128-wide tile (the epilogue is issue-bound; more warps hide its
+// latencies), 2 per quarter for the 64-wide one; plus the TMA warp and the MMA warp
+template <int BN> struct EpiWarps { static constexpr int value = BN >= 128 ? 16 : 8; };
 constexpr uint32_t SPIN_LIMIT = 1u << 27;
 
 struct TcArgs {
@@ -111,13 +113,15 @@ struct Smem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EPI_BYTES = 8 * 32 * (BN / 2 + 4) * 4;      // 8 epilogue warps x 32 rows x (BN/2 + 4) floats
+  static constexpr int EW = EpiWarps<BN>::value;
+  static constexpr int THREADS = 64 + 32 * EW;
+  static constexpr int EPI_BYTES = EW * 32 * (BN / (EW / 4) + 4) * 4;      // per epilogue warp: 32 rows x (its columns + 4) floats
   static constexpr int BAR_BYTES = 256;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024 /* alignment slack */;
 };
 
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(Smem<BN>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ TcArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -139,7 +143,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], S::EW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -214,8 +218,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ===== epilogue warps: warp w owns TMEM lane quarter (w % 4) and column half (w - 2) / 4 of every tile =====
-    constexpr int HN = BN / 2;                 // columns per epilogue warp
+    // ===== epilogue warps: warp w owns TMEM lane quarter (w % 4) and column slice (w - 2) / 4 of every tile =====
+    constexpr int HN = BN / (S::EW / 4);       // columns per epilogue warp
     constexpr int LDS = HN + 4;                // staged row stride in floats (16-byte aligned, conflict-free both ways)
     constexpr int LPR = HN / 4;                // lanes per output row (16-byte column quads)
     constexpr int RPI = 32 / LPR;              // rows covered by one warp-wide access
@@ -224,6 +228,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int q = warp & 3, half = (warp - 2) >> 2;
     float* stg = epi_stage + (warp - 2) * 32 * LDS;
     const GemmEpi& e = g.epi;
+    const DropCfg edrop = mt_drop_resolve(e.drop);
     const int lr = lane / LPR, lc = (lane % LPR) * 4;
     int it = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
@@ -290,10 +295,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int k = 0; k < 4; ++k) o[k] = tanhf(o[k]);
           }
-          if (e.drop.thresh != 0u) {
+          if (edrop.thresh != 0u) {
             const uint64_t idx = (uint64_t)m * (uint64_t)g.N + (uint64_t)n;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) o[k] *= mt_drop_factor(e.drop, idx + k);
+            for (int k = 0; k < 4; ++k) o[k] *= mt_drop_factor(edrop, idx + k);
           }
           if (e.gate) {
             o[0] = gt[u].x > 0.f ? o[0] * e.gate_scale : 0.f; o[1] = gt[u].y > 0.f ? o[1] * e.gate_scale : 0.f;
@@ -395,7 +400,7 @@ int launch_tc(const GemmDesc& d, cudaStream_t st) {
   }
   const int n_work = g.tiles_m * g.tiles_n * g.splits;
   const int grid = n_work < num_sms() ? n_work : num_sms();
-  gemm_tc_kernel<BN><<<grid, TC_THREADS, Smem<BN>::TOTAL, st>>>(ma, mb, g);
+  gemm_tc_kernel<BN><<<grid, Smem<BN>::THREADS, Smem<BN>::TOTAL, st>>>(ma, mb, g);
   MT_LAUNCH_CHECK();
   return MT_OK;
 }

@@ -501,6 +501,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mfn_mem_fwd_kernel(const __grid_c
     if (i < a.T) prefetch_rows(tab, stages + (size_t)i * stage_bytes, b0, nb, a.sb, a.st, i);
     cp_commit();
   }
+  const DropCfg drop_g1 = mt_drop_resolve(a.drop_g1), drop_g2 = mt_drop_resolve(a.drop_g2);
   ST* gh_op = reinterpret_cast<ST*>(a.gh_op);
   ST* memprev_op = reinterpret_cast<ST*>(a.memprev_op);
   ST* last_op = reinterpret_cast<ST*>(a.last_op);
@@ -519,7 +520,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mfn_mem_fwd_kernel(const __grid_c
     // ---- gamma hidden = drop(relu(gpre_t + W_gm mem_{t-1})) ----
     dense_s<WT>(Wm, MEM, G2, [&](int) { return mem; }, part, [&](int n, float* acc) {
       const bool second = n >= G;
-      const DropCfg& dc = second ? a.drop_g2 : a.drop_g1;
+      const DropCfg& dc = second ? drop_g2 : drop_g1;
       const int j = second ? n - G : n;
 #pragma unroll
       for (int b = 0; b < BT; ++b) {
@@ -711,8 +712,9 @@ __global__ void __launch_bounds__(256) mfn_softmax_attend_bwd_kernel(int M, int 
 template <typename ST>
 __global__ void __launch_bounds__(256) mfn_head_fwd_kernel(int B, int T, long long sb, long long st, int O, const float* __restrict__ pre,
                                                             const float* __restrict__ w2, const float* __restrict__ b2,
-                                                            const float* __restrict__ mask, DropCfg drop, ST* __restrict__ oh,
+                                                            const float* __restrict__ mask, DropCfg drop_in, ST* __restrict__ oh,
                                                             float* __restrict__ out) {
+  const DropCfg drop = mt_drop_resolve(drop_in);
   const int lane = threadIdx.x & 31;
   const long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // i = b*T + t
   if (i >= (long long)B * T) return;

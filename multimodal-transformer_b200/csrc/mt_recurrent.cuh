@@ -249,10 +249,24 @@ __device__ __forceinline__ void load_rows(float* __restrict__ s, int w, const fl
   }
 }
 
+// raise a kernel's dynamic shared-memory limit (only when it has to grow; keyed by the kernel's address)
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
   if (bytes > 227 * 1024) return MT_ERR_UNSUPPORTED;
-  MT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  static const void* fn[64];
+  static size_t granted[64];
+  static int n = 0;
+  const void* key = reinterpret_cast<const void*>(kernel);
+  int i = 0;
+  while (i < n && fn[i] != key) ++i;
+  if (i == n) {
+    if (n == 64) { MT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)); return MT_OK; }
+    fn[n] = key; granted[n] = 0; ++n;
+  }
+  if (bytes > granted[i]) {
+    MT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    granted[i] = bytes;
+  }
   return MT_OK;
 }
 

@@ -448,6 +448,27 @@ def mse_loss_sum_normalised(pred, target, norm):
     return loss, dp
 
 
+def mse_loss_sum_normalised_dev(pred, target, inv_norm_t):
+    """Same as mse_loss_sum_normalised with 1/norm read from a device scalar (captured-graph train step)."""
+    p = require(pred if pred.is_contiguous() else pred.contiguous(), torch.float32, 'pred')
+    t = require(target if target.is_contiguous() else target.contiguous(), torch.float32, 'target')
+    require(inv_norm_t, torch.float32, 'inv_norm')
+    loss = torch.zeros(1, dtype=torch.float32, device=p.device)
+    dp = torch.empty_like(p)
+    check(lib().mt_mse_loss_fwd_bwd_dev(ptr(p), ptr(t), p.numel(), ptr(inv_norm_t), ptr(loss), ptr(dp), stream()))
+    return loss, dp
+
+
+def adam_step_flat_dev(p, g, m, v, step_t, lr_t, lr=0.0, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, p_lp=None):
+    """Adam with the step count (int64 device scalar) and optionally lr (fp32 device scalar) read on the device; writes the
+    bf16 shadow `p_lp` in the same launch when given."""
+    for t_, nm in ((p, 'p'), (g, 'g'), (m, 'm'), (v, 'v')):
+        require(t_, torch.float32, nm)
+    require(step_t, torch.int64, 'step')
+    check(lib().mt_adam_step_dev(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), ptr(lr_t), lr, betas[0], betas[1], eps, weight_decay,
+                                 ptr(step_t), ptr(p_lp), stream()))
+
+
 def adam_step_flat(p, g, m, v, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
     for t_, nm in ((p, 'p'), (g, 'g'), (m, 'm'), (v, 'v')):
         require(t_, torch.float32, nm)

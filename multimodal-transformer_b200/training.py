@@ -98,6 +98,167 @@ class FlatAdam:
             K.adam_step_flat(flat, g, st[0], st[1], self.step_count, lr, self.betas, self.eps, self.weight_decay)
             a._lp_key = None             # the kernel wrote the arena behind autograd's back: refresh the bf16 shadow
 
+    @torch.no_grad()
+    def step_dev(self, step_t, lr_t=None):
+        """step() with the step count (and optionally lr) in device memory -- the form a captured CUDA graph replays.
+        The bf16 shadow of each arena is refreshed by the same launch."""
+        self.all_reduce_grads()
+        lr = self.param_groups[0]['lr']
+        for a in self._all_arenas():
+            g = self._flat_grad(a)
+            if g is None:
+                continue
+            flat = a.bind()
+            st = self.state.get(id(a))
+            if st is None:
+                st = (torch.zeros_like(flat), torch.zeros_like(flat))
+                self.state[id(a)] = st
+            lp = a.lp if (a.lp is not None and a._lp_key is not None) else None
+            K.adam_step_flat_dev(flat, g, st[0], st[1], step_t, lr_t, lr, self.betas, self.eps, self.weight_decay, lp)
+            if lp is None:
+                a._lp_key = None
+
     def zero_grad(self):
         for p in self.model.parameters():
             p.grad = None
+
+
+class GraphedTrainStep:
+    """The whole train step -- forward, fused loss, backward, gradient all-reduce (when torch.distributed is up) and
+    Adam -- captured ONCE into a CUDA graph for a fixed (B, T) and replayed per batch: the ~530 kernel launches of a
+    step cost ~16 ms of host time when issued one by one, more than the kernels themselves take.  Per-step scalars
+    (1/sum(lengths), Adam step count, lr, dropout seed offset) live in device memory so a replay sees fresh values.
+
+        step = GraphedTrainStep(model, opt, B, T, {mod: in_dim}, device)
+        loss = step(inputs, mask, target, lengths)          # tensors on host (pinned) or device; returns loss [1] on device
+
+    Re-create it after load_state_dict() or a change of model.train()/dtype (the graph bakes addresses and modes)."""
+
+    def __init__(self, model, opt, B, T, in_dims, device, norm_fn=None, warmup=3):
+        from . import _lib
+        self.model, self.opt, self.B, self.T, self.device = model, opt, B, T, device
+        self.mods = list(in_dims)
+        self.x = {m: torch.zeros(B, T, d, device=device) for m, d in in_dims.items()}
+        self.mask = torch.zeros(B, T, 1, device=device)
+        self.target = torch.zeros(B, T, 1, device=device)
+        self.inv_norm = torch.ones(1, device=device)
+        self.lr = torch.full((1,), float(opt.param_groups[0]['lr']), device=device)
+        self.step_t = torch.full((1,), int(opt.step_count), dtype=torch.int64, device=device)
+        self.seed_off = torch.zeros(1, dtype=torch.int64, device=device)
+        self.lengths = [T] * B
+        self.norm_fn = norm_fn or (lambda lengths: float(sum(lengths)))
+        self.warmup = warmup
+        self.graph = None
+        self.loss = None
+        self._lib = _lib
+
+    def load(self, inputs, mask, target, lengths):
+        for m in self.mods:
+            self.x[m].copy_(inputs[m], non_blocking=True)
+        self.mask.copy_(mask.reshape(self.B, self.T, 1), non_blocking=True)
+        self.target.copy_(target.reshape(self.B, self.T, 1), non_blocking=True)
+        self.inv_norm.fill_(1.0 / self.norm_fn(lengths))
+        lr = float(self.opt.param_groups[0]['lr'])
+        if lr != getattr(self, '_lr_seen', None):
+            self.lr.fill_(lr); self._lr_seen = lr
+
+    def _step(self):
+        self.seed_off.add_(1)
+        self.step_t.add_(1)
+        self.model.train()
+        pred = self.model(self.x, self.mask, self.lengths)
+        loss, dpred = K.mse_loss_sum_normalised_dev(pred.detach(), self.target, self.inv_norm)
+        pred.backward(dpred.view_as(pred))
+        self.opt.step_dev(self.step_t, self.lr)
+        self.opt.zero_grad()
+        return loss
+
+    def capture(self):
+        """Warm up eagerly on a side stream (lazy initialisation: arena binding, Adam state, kernel attributes), undo
+        the warm-up's parameter / optimizer updates, then capture one step.  Capturing executes nothing."""
+        L = self._lib.lib()
+        opt = self.opt
+        warm = max(1, int(self.warmup))
+        snap = {k: v.detach().clone() for k, v in self.model.state_dict().items()}
+        had_state = {k: (m.clone(), v.clone()) for k, (m, v) in opt.state.items()}
+        step0, count0 = self.step_t.clone(), opt.step_count
+        self._lib.check(L.mt_set_seed_offset_ptr(self._lib.ptr(self.seed_off)))
+        try:
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(warm):
+                    self._step()
+                with torch.no_grad():
+                    for k, v in self.model.state_dict().items():
+                        v.copy_(snap[k])
+                    for k, (m, v) in opt.state.items():
+                        if k in had_state:
+                            m.copy_(had_state[k][0]); v.copy_(had_state[k][1])
+                        else:
+                            m.zero_(); v.zero_()
+                    self.step_t.copy_(step0)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            opt.step_count = count0
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.loss = self._step()
+        finally:
+            self._lib.check(L.mt_set_seed_offset_ptr(None))      # eager calls keep their value seeds
+        return self
+
+    def replay(self):
+        self.graph.replay()
+        self.opt.step_count += 1
+        return self.loss
+
+    def __call__(self, inputs, mask, target, lengths):
+        self.load(inputs, mask, target, lengths)
+        if self.graph is None:
+            self.capture()
+        return self.replay()
+
+
+class GraphedForward:
+    """eval() forward captured into a CUDA graph for a fixed (B, T); returns the static prediction buffer [B,T,1]."""
+
+    def __init__(self, model, B, T, in_dims, device, warmup=2):
+        self.model, self.B, self.T, self.device = model, B, T, device
+        self.mods = list(in_dims)
+        self.x = {m: torch.zeros(B, T, d, device=device) for m, d in in_dims.items()}
+        self.mask = torch.zeros(B, T, 1, device=device)
+        self.lengths = [T] * B
+        self.warmup = warmup
+        self.graph = None
+        self.pred = None
+
+    def load(self, inputs, mask):
+        for m in self.mods:
+            self.x[m].copy_(inputs[m], non_blocking=True)
+        self.mask.copy_(mask.reshape(self.B, self.T, 1), non_blocking=True)
+
+    def _fwd(self):
+        self.model.eval()
+        with torch.no_grad():
+            return self.model(self.x, self.mask, self.lengths)
+
+    def capture(self):
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup):
+                self._fwd()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.pred = self._fwd()
+        return self
+
+    def __call__(self, inputs, mask):
+        self.load(inputs, mask)
+        if self.graph is None:
+            self.capture()
+        self.graph.replay()
+        return self.pred

@@ -495,3 +495,64 @@ def test_launch_counter_counts_our_kernels():
     ln = mtb.LayerNorm(256).to(DEV)
     ln(torch.randn(8, 256, device=DEV))
     assert L.mt_launch_count() == before + 1
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_graphed_train_step_equals_eager_steps(mode):
+    """The CUDA-graph train step (device-side step count / loss normaliser / lr) replays to the same parameters as the
+    eager module path: dropout off so both are deterministic; atomics in the wgrad split-K leave round-off only."""
+    from multimodal_transformer_b200.training import FlatAdam, GraphedTrainStep, train_step_loss
+    N, B, T = 2, 6, 12
+    dims = {'acoustic': 88, 'image': 256, 'linguistic': 300}
+    sd = util.filled_sd(util.mods_shapes('MFT.MultiTransformer', N), 61)
+    batches = [fill.make_batch(B, T, dims, 70 + i) for i in range(3)]
+    mtb.set_compute_dtype(mode)
+
+    def fresh():
+        model = mtb.MultiTransformer(MODS, dims, N=N, dropout=0.0).to(DEV); model.load_state_dict(sd)
+        for mod in model.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        return model, FlatAdam(model, lr=1e-3, weight_decay=1e-4)
+
+    model_e, opt_e = fresh()
+    losses_e = []
+    for inputs, mask, target, lengths in batches:
+        model_e.train()
+        pred = model_e({k: t(v).to(DEV) for k, v in inputs.items()}, t(mask).to(DEV), lengths)
+        losses_e.append(train_step_loss(pred, t(target).to(DEV), float(sum(lengths))).item())
+        opt_e.step(); opt_e.zero_grad()
+
+    model_g, opt_g = fresh()
+    gstep = GraphedTrainStep(model_g, opt_g, B, T, dims, torch.device(DEV), warmup=2)
+    losses_g = []
+    for inputs, mask, target, lengths in batches:
+        loss = gstep({k: t(v) for k, v in inputs.items()}, t(mask), t(target), lengths)
+        losses_g.append(loss.item())
+    assert opt_g.step_count == 3          # the warm-up steps inside capture() leave no trace
+    for a, b in zip(losses_e, losses_g):
+        assert abs(a - b) <= (1e-4 if mode == 'fp32' else 3e-2) * abs(a), (losses_e, losses_g)
+    model_e2 = model_e
+    tol = 2e-4 if mode == 'fp32' else 3e-2
+    pe = dict(model_e2.named_parameters())
+    for k, p in model_g.named_parameters():
+        if k.startswith(('attn', 'ff')):
+            continue
+        assert_close(p, pe[k], tol, k, 1e-6)
+
+
+def test_graph_replay_draws_fresh_dropout_masks():
+    """Two replays of the captured step on the same batch give different losses in train mode (the dropout seed offset
+    lives in device memory and is bumped inside the graph), and eager calls afterwards are unaffected."""
+    from multimodal_transformer_b200.training import FlatAdam, GraphedTrainStep
+    N, B, T = 2, 4, 8
+    dims = {'acoustic': 88, 'image': 256, 'linguistic': 300}
+    sd = util.filled_sd(util.mods_shapes('MFT.MultiTransformer', N), 62)
+    inputs, mask, target, lengths = fill.make_batch(B, T, dims, 62)
+    model = mtb.MultiTransformer(MODS, dims, N=N).to(DEV); model.load_state_dict(sd)
+    opt = FlatAdam(model, lr=0.0)             # lr 0: parameters stay put, only the masks change between replays
+    gstep = GraphedTrainStep(model, opt, B, T, dims, torch.device(DEV), warmup=1)
+    a = gstep({k: t(v) for k, v in inputs.items()}, t(mask), t(target), lengths).item()
+    b = gstep({k: t(v) for k, v in inputs.items()}, t(mask), t(target), lengths).item()
+    assert a != b
+    assert _lib.lib().mt_launch_count() > 0
