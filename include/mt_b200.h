@@ -101,6 +101,8 @@ int mt_attention_bwd(int dtype, int B, int T, int d, int h, const void* qkv, con
 size_t mt_attention_bwd_ws_bytes(int B, int T, int h);
 /* test hook: route bf16 attention through the FFMA engine (A/B the tensor-core engine); returns the previous setting. */
 int mt_attention_force_ffma(int on);
+/* test hook: route bf16 attention with T <= 128 through the tiled any-T tensor-core kernel instead of the whole-head one. */
+int mt_attention_force_tiled(int on);
 /* materialise p_attn [B,h,T,T] fp32 (the reference keeps it as MultiHeadedAttention.attn, :59); debug/inspection. */
 int mt_attention_probs(int dtype, int B, int T, int d, int h, const void* qkv, const float* mask, float* probs,
                        void* stream);

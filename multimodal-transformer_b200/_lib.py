@@ -55,6 +55,7 @@ _PROTOS = {
     'mt_attention_bwd': (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, c_float, c_uint64, c_uint32, P, c_size_t, P]),
     'mt_attention_bwd_ws_bytes': (c_size_t, [c_int, c_int, c_int]),
     'mt_attention_force_ffma': (c_int, [c_int]),
+    'mt_attention_force_tiled': (c_int, [c_int]),
     'mt_attention_probs': (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
     'mt_encoder_param_count': (c_size_t, [c_int, c_int, c_int]),
     'mt_encoder_ws_bytes': (c_size_t, [POINTER(MtEncoderCfg)]),

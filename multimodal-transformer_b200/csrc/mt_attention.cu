@@ -59,7 +59,8 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(int B, int T_, int
 #pragma unroll
   for (int c = 0; c < DK; ++c) o[c] = 0.f;
   float m = -INFINITY, l = 0.f;
-  const uint64_t drop_row = ((uint64_t)((size_t)b * h + hd) * T_ + (uint64_t)(active ? i : 0)) * (uint64_t)T_;
+  const uint64_t drop_row = (uint64_t)((size_t)b * h + hd) * T_ + (uint64_t)(active ? i : 0);      // flat (b, head, query) row
+  const uint32_t P2 = (uint32_t)(T_ + 1) >> 1;
   for (int j0 = 0; j0 < T_; j0 += KT) {
     __syncthreads();
     stage_tile<T, DK>(Ks, qb + d, ld, j0, KT, T_);
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(int B, int T_, int
       }
       float p = expf(s - m);
       l += p;
-      p *= mt_drop_factor(drop, drop_row + (uint64_t)(j0 + j));
+      p *= mt_attn_drop_factor(drop, drop_row, P2, (uint32_t)(j0 + j));
       const float4* vr = reinterpret_cast<const float4*>(Vs + j * DK);
 #pragma unroll
       for (int c = 0; c < DK / 4; ++c) {
@@ -137,7 +138,8 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_dq_kernel(int B, int T_, 
   }
 #pragma unroll
   for (int c = 0; c < DK; ++c) dq[c] = 0.f;
-  const uint64_t drop_row = ((uint64_t)((size_t)b * h + hd) * T_ + (uint64_t)(active ? i : 0)) * (uint64_t)T_;
+  const uint64_t drop_row = (uint64_t)((size_t)b * h + hd) * T_ + (uint64_t)(active ? i : 0);      // flat (b, head, query) row
+  const uint32_t P2 = (uint32_t)(T_ + 1) >> 1;
   for (int j0 = 0; j0 < T_; j0 += KT) {
     __syncthreads();
     stage_tile<T, DK>(Ks, qb + d, ld, j0, KT, T_);
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_dq_kernel(int B, int T_, 
         dp = fmaf(go[4 * c + 2], vv.z, dp); dp = fmaf(go[4 * c + 3], vv.w, dp);
       }
       float p = expf(s * scale - L);
-      dp *= mt_drop_factor(drop, drop_row + (uint64_t)(j0 + j));
+      dp *= mt_attn_drop_factor(drop, drop_row, P2, (uint32_t)(j0 + j));
       float ds = p * (dp - D) * scale;
 #pragma unroll
       for (int c = 0; c < DK / 4; ++c) {
@@ -227,7 +229,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_dkv_kernel(int B, int T_,
       const float valid = Ms[e];
       // masked query rows: scores are a constant row -> p = 1/T (lse holds log T), and no score gradient
       float p = expf((valid != 0.f ? s * scale : 0.f) - Ls[e]);
-      float f = mt_drop_factor(drop, (uint64_t)(bh * T_ + (size_t)(i0 + e)) * (uint64_t)T_ + (uint64_t)j);
+      float f = mt_attn_drop_factor(drop, (uint64_t)(bh * T_ + (size_t)(i0 + e)), (uint32_t)(T_ + 1) >> 1, (uint32_t)j);
       float pd = p * f;
       float ds = valid * p * (dp * f - Ds[e]) * scale;
 #pragma unroll

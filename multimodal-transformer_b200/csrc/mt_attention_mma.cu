@@ -8,45 +8,15 @@
 // fetched with ldmatrix (transposed where the contraction runs over the row index).  Softmax statistics, the
 // probabilities and all accumulators stay in registers; P / dS are re-packed from accumulator layout to A-operand
 // layout without touching shared memory.
-#include "mt_ops.cuh"
+#include "mt_mma.cuh"
 
 namespace {
+
+using namespace mtmma;
 
 constexpr int TILE = 64;          // rows of the streamed operand per shared-memory tile
 constexpr int WARPS = 4;          // 16 owned rows each -> 64 owned rows per CTA
 constexpr int THREADS = WARPS * 32;
-
-__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void ldsm4(uint32_t* r, const bf16* p) {
-  uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
-}
-__device__ __forceinline__ void ldsm4t(uint32_t* r, const bf16* p) {
-  uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
-}
-__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-
-// A-operand fragments of a [16 x DK] row-major global operand (rows r0 = row0 + lane/4 and r0 + 8), zero beyond `rows`
-template <int DK>
-__device__ __forceinline__ void load_a_frags(uint32_t (*a)[4], const bf16* base, int ld, int row0, int rows, int lane) {
-  const int r0 = row0 + (lane >> 2), r1 = r0 + 8, c = 2 * (lane & 3);
-#pragma unroll
-  for (int ks = 0; ks < DK / 16; ++ks) {
-    a[ks][0] = r0 < rows ? *reinterpret_cast<const uint32_t*>(base + (size_t)r0 * ld + ks * 16 + c) : 0u;
-    a[ks][1] = r1 < rows ? *reinterpret_cast<const uint32_t*>(base + (size_t)r1 * ld + ks * 16 + c) : 0u;
-    a[ks][2] = r0 < rows ? *reinterpret_cast<const uint32_t*>(base + (size_t)r0 * ld + ks * 16 + 8 + c) : 0u;
-    a[ks][3] = r1 < rows ? *reinterpret_cast<const uint32_t*>(base + (size_t)r1 * ld + ks * 16 + 8 + c) : 0u;
-  }
-}
 
 // stage TILE rows [row0, row0 + TILE) of a [rows x DK] global operand into smem[TILE][DK + 8] (zero beyond `rows`)
 template <int DK>
@@ -122,7 +92,8 @@ __global__ void __launch_bounds__(THREADS) attn_mma_fwd_kernel(int B, int T, int
 #pragma unroll
   for (int i = 0; i < DK / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   const uint64_t bh = (uint64_t)b * h + hd;
-  const uint64_t drow0 = (bh * T + (uint64_t)min(r0, T - 1)) * (uint64_t)T, drow1 = (bh * T + (uint64_t)min(r1, T - 1)) * (uint64_t)T;
+  const uint64_t drow0 = bh * T + (uint64_t)min(r0, T - 1), drow1 = bh * T + (uint64_t)min(r1, T - 1);
+  const uint32_t P2 = (uint32_t)(T + 1) >> 1;
 
   for (int j0 = 0; j0 < T; j0 += TILE) {
     __syncthreads();
@@ -155,14 +126,15 @@ __global__ void __launch_bounds__(THREADS) attn_mma_fwd_kernel(int B, int T, int
     uint32_t pa[TILE / 16][4];
 #pragma unroll
     for (int nt = 0; nt < TILE / 8; ++nt) {
-      float p[4];
+      float p[4], f[4];
+      mt_attn_drop_pair(drop, drow0, P2, (uint32_t)(j0 + nt * 8 + 2 * (lane & 3)), f[0], f[1]);
+      mt_attn_drop_pair(drop, drow1, P2, (uint32_t)(j0 + nt * 8 + 2 * (lane & 3)), f[2], f[3]);
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int j = j0 + nt * 8 + 2 * (lane & 3) + e;
         const float p0 = __expf(s[nt][e] - m0), p1 = __expf(s[nt][2 + e] - m1);
         l0 += p0; l1 += p1;
-        p[e] = p0 * mt_drop_factor(drop, drow0 + (uint64_t)j);
-        p[2 + e] = p1 * mt_drop_factor(drop, drow1 + (uint64_t)j);
+        p[e] = p0 * f[e];
+        p[2 + e] = p1 * f[2 + e];
       }
       pa[nt >> 1][(nt & 1) * 2 + 0] = pack2(p[0], p[1]);
       pa[nt >> 1][(nt & 1) * 2 + 1] = pack2(p[2], p[3]);
@@ -233,7 +205,8 @@ __global__ void __launch_bounds__(THREADS) attn_mma_bwd_kernel(int B, int T, int
     const bool v0 = r0 < T && !(mask != nullptr && mask[(size_t)b * T + r0] == 0.f);
     const bool v1 = r1 < T && !(mask != nullptr && mask[(size_t)b * T + r1] == 0.f);
     const float L0 = r0 < T ? lse[bh * T + r0] : 0.f, L1 = r1 < T ? lse[bh * T + r1] : 0.f;
-    const uint64_t drow0 = (bh * T + (uint64_t)min(r0, T - 1)) * (uint64_t)T, drow1 = (bh * T + (uint64_t)min(r1, T - 1)) * (uint64_t)T;
+    const uint64_t drow0 = bh * T + (uint64_t)min(r0, T - 1), drow1 = bh * T + (uint64_t)min(r1, T - 1);
+    const uint32_t P2 = (uint32_t)(T + 1) >> 1;
     float dq[DK / 8][4];
 #pragma unroll
     for (int i = 0; i < DK / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
@@ -248,13 +221,15 @@ __global__ void __launch_bounds__(THREADS) attn_mma_bwd_kernel(int B, int T, int
       uint32_t da[TILE / 16][4];
 #pragma unroll
       for (int nt = 0; nt < TILE / 8; ++nt) {
-        float ds[4];
+        float ds[4], fa[2], fb[2];
+        mt_attn_drop_pair(drop, drow0, P2, (uint32_t)(j0 + nt * 8 + c), fa[0], fa[1]);
+        mt_attn_drop_pair(drop, drow1, P2, (uint32_t)(j0 + nt * 8 + c), fb[0], fb[1]);
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int j = j0 + nt * 8 + c + e;
           const bool in = j < T;
           const float p0 = __expf(s[nt][e] * scale - L0), p1 = __expf(s[nt][2 + e] * scale - L1);
-          const float f0 = mt_drop_factor(drop, drow0 + (uint64_t)j), f1 = mt_drop_factor(drop, drow1 + (uint64_t)j);
+          const float f0 = fa[e], f1 = fb[e];
           ds[e] = (v0 && in) ? p0 * (dp[nt][e] * f0 - D0) * scale : 0.f;
           ds[2 + e] = (v1 && in) ? p1 * (dp[nt][2 + e] * f1 - D1) * scale : 0.f;
         }
@@ -311,12 +286,12 @@ __global__ void __launch_bounds__(THREADS) attn_mma_bwd_kernel(int B, int T, int
           const int ci = nt * 8 + c + e;           // query column inside the tile
           const int i = i0 + ci;
           const float vd = Vd[ci], Lq = Ls[ci], Dq = Ds[ci];
-          const uint64_t dbase = (bh * T + (uint64_t)min(i, T - 1)) * (uint64_t)T;
+          const uint64_t drow = bh * T + (uint64_t)min(i, T - 1);
           // masked query rows are constant rows: p = exp(0 - log T) = 1/T, and they carry no score gradient
           const float p0 = vd == 0.f ? 0.f : __expf((vd > 0.f ? s[nt][e] * scale : 0.f) - Lq);
           const float p1 = vd == 0.f ? 0.f : __expf((vd > 0.f ? s[nt][2 + e] * scale : 0.f) - Lq);
-          const float f0 = mt_drop_factor(drop, dbase + (uint64_t)min(r0, T - 1));
-          const float f1 = mt_drop_factor(drop, dbase + (uint64_t)min(r1, T - 1));
+          const float f0 = mt_attn_drop_factor(drop, drow, (uint32_t)(T + 1) >> 1, (uint32_t)min(r0, T - 1));
+          const float f1 = mt_attn_drop_factor(drop, drow, (uint32_t)(T + 1) >> 1, (uint32_t)min(r1, T - 1));
           pd[e] = p0 * f0; pd[2 + e] = p1 * f1;
           ds[e] = vd > 0.f ? p0 * (dp[nt][e] * f0 - Dq) * scale : 0.f;
           ds[2 + e] = vd > 0.f ? p1 * (dp[nt][2 + e] * f1 - Dq) * scale : 0.f;
@@ -349,7 +324,11 @@ bool mt_attn_mma_supported(int B, int T, int d, int h) {
   return (dk == 16 || dk == 32 || dk == 64) && d % 8 == 0 && B <= 65535 && h <= 65535;
 }
 
+static int g_force_tiled = 0;
+extern "C" int mt_attention_force_tiled(int on) { const int old = g_force_tiled; g_force_tiled = on; return old; }
+
 int mt_attn_mma_fwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop, cudaStream_t st) {
+  if (!g_force_tiled && mt_attn128_supported(B, T, d, h)) return mt_attn128_fwd_run(B, T, d, h, qkv, mask, out, lse, drop, st);
   const int dk = d / h;
   const float scale = 1.0f / sqrtf((float)dk);
   dim3 grid((T + WARPS * 16 - 1) / (WARPS * 16), h, B);
@@ -366,6 +345,7 @@ int mt_attn_mma_fwd_run(int B, int T, int d, int h, const void* qkv, const float
 
 int mt_attn_mma_bwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse, const void* dout,
                         void* dqkv, DropCfg drop, cudaStream_t st) {
+  if (!g_force_tiled && mt_attn128_supported(B, T, d, h)) return mt_attn128_bwd_run(B, T, d, h, qkv, mask, out, lse, dout, dqkv, drop, st);
   const int dk = d / h;
   const float scale = 1.0f / sqrtf((float)dk);
   dim3 grid((T + WARPS * 16 - 1) / (WARPS * 16), h, B);

@@ -128,6 +128,27 @@ __device__ __forceinline__ float mt_drop_factor(const DropCfg& d, uint64_t idx) 
   return mt_rand_u32(d.seed, d.site, idx) >= d.thresh ? d.scale : 0.0f;
 }
 
+// Attention-probability dropout (site MT_SITE_ATTN_P): one 32-bit draw decides TWO adjacent keys of a query row, 16 bits
+// each (threshold = thresh >> 16), because the per-element hash dominated the attention kernels' instruction count.
+// row = flat (batch, head, query) index, P2 = ceil(T / 2), j = key index.   Mirrored by oracle/dropout_rng.py:attn_keep_mask.
+__device__ __forceinline__ uint32_t mt_attn_drop_bits(const DropCfg& d, uint64_t row, uint32_t P2, uint32_t j) {
+  return mt_rand_u32(d.seed, d.site, row * (uint64_t)P2 + (uint64_t)(j >> 1));
+}
+__device__ __forceinline__ float mt_attn_drop_factor(const DropCfg& d, uint64_t row, uint32_t P2, uint32_t j) {
+  if (d.thresh == 0u) return 1.0f;
+  const uint32_t bits = mt_attn_drop_bits(d, row, P2, j);
+  const uint32_t v = (j & 1u) ? (bits >> 16) : (bits & 0xFFFFu);
+  return v >= (d.thresh >> 16) ? d.scale : 0.0f;
+}
+// both keys of the pair (j even): f[0] for key j, f[1] for key j + 1
+__device__ __forceinline__ void mt_attn_drop_pair(const DropCfg& d, uint64_t row, uint32_t P2, uint32_t j, float& f0, float& f1) {
+  if (d.thresh == 0u) { f0 = f1 = 1.0f; return; }
+  const uint32_t bits = mt_attn_drop_bits(d, row, P2, j);
+  const uint32_t t16 = d.thresh >> 16;
+  f0 = (bits & 0xFFFFu) >= t16 ? d.scale : 0.0f;
+  f1 = (bits >> 16) >= t16 ? d.scale : 0.0f;
+}
+
 // dropout site ids (oracle/dropout_rng.py)
 #define MT_SITE_ATTN_P 0
 #define MT_SITE_SUB0 1

@@ -42,6 +42,12 @@ int mt_attn_mma_fwd_run(int B, int T, int d, int h, const void* qkv, const float
 int mt_attn_mma_bwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse, const void* dout,
                         void* dqkv, DropCfg drop, cudaStream_t st);
 
+// ---- whole-head-per-CTA attention for T <= 128 (mt_attention_t128.cu), bf16 -----------------------------------
+bool mt_attn128_supported(int B, int T, int d, int h);
+int mt_attn128_fwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop, cudaStream_t st);
+int mt_attn128_bwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse, const void* dout,
+                       void* dqkv, DropCfg drop, cudaStream_t st);
+
 // ---- attention (mt_attention.cu) ---------------------------------------------------------------------
 int mt_attn_fwd_run(int dtype, int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop,
                     cudaStream_t st);

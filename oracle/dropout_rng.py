@@ -52,6 +52,23 @@ def keep_mask(seed, site, shape, p):
     return (rand_u32(seed, site, idx) >= threshold(p)).reshape(tuple(shape))
 
 
+def attn_keep_mask(seed, site, shape, p):
+    """Keep-mask of attention probabilities [B,h,T,T] (csrc/mt_common.cuh: mt_attn_drop_factor): one 32-bit draw per PAIR of
+    adjacent keys of a query row -- index row * ceil(T/2) + (j >> 1), even key = low 16 bits, odd key = high 16 bits,
+    threshold = threshold(p) >> 16."""
+    *lead, T, Tk = [int(s) for s in shape]
+    rows = 1
+    for s in lead:
+        rows *= s
+    rows *= T
+    P2 = (Tk + 1) // 2
+    idx = torch.arange(rows * P2, dtype=torch.int64)
+    bits = rand_u32(seed, site, idx).reshape(rows, P2)
+    lo, hi = bits & 0xFFFF, (bits >> 16) & 0xFFFF
+    both = torch.stack([lo, hi], dim=-1).reshape(rows, 2 * P2)[:, :Tk]
+    return (both >= (threshold(p) >> 16)).reshape(tuple(shape))
+
+
 class Dropper:
     """Applies dropout exactly as the CUDA kernels do.
 
@@ -66,6 +83,13 @@ class Dropper:
             return x
         keep = keep_mask(self.seed, site, x.shape, p).to(x.device)
         return x * keep.to(x.dtype) * (1.0 / (1.0 - p))
+
+    def attn(self, p_attn, p, site):
+        """Dropout on attention probabilities [B,h,T,T] (pair generator, see attn_keep_mask)."""
+        if self.seed is None or p <= 0.0:
+            return p_attn
+        keep = attn_keep_mask(self.seed, site, p_attn.shape, p).to(p_attn.device)
+        return p_attn * keep.to(p_attn.dtype) * (1.0 / (1.0 - p))
 
 
 # ---- site ids (shared with csrc/mt_common.cuh) -------------------------------------------

@@ -183,7 +183,8 @@ def test_attention_fwd_bwd(B, T, d, h, p):
 
 
 @pytest.mark.parametrize('B,T,d,h,p', [(2, 128, 256, 8, 0.0), (3, 37, 256, 8, 0.1), (2, 200, 128, 8, 0.0), (2, 70, 512, 8, 0.1),
-                                       (1, 64, 256, 8, 0.1), (2, 130, 256, 8, 0.0)])
+                                       (1, 64, 256, 8, 0.1), (2, 130, 256, 8, 0.0), (3, 128, 256, 8, 0.1), (2, 1, 128, 8, 0.0),
+                                       (2, 125, 128, 8, 0.1), (2, 9, 512, 8, 0.1)])
 def test_attention_tensor_core_engine_bf16(B, T, d, h, p):
     """bf16 mode: the mma.sync engine against the fp64 oracle on the same bf16-rounded inputs and the same dropout
     masks, and against the FFMA engine."""
@@ -197,16 +198,19 @@ def test_attention_tensor_core_engine_bf16(B, T, d, h, p):
     outr, _ = _attn_ref(qr, mask.double(), h, Dropper(seed) if p > 0 else None, p, 0)
     outr.backward(dout.double())
     res = {}
-    for force in (1, 0):
-        old = _lib.lib().mt_attention_force_ffma(force)
+    L = _lib.lib()
+    for eng in ('ffma', 'tiled', 'whole-head'):          # FFMA engine, tiled any-T mma.sync kernel, T <= 128 whole-head kernel
+        old = L.mt_attention_force_ffma(int(eng == 'ffma'))
+        old_t = L.mt_attention_force_tiled(int(eng == 'tiled'))
         mtb.fix_seed(seed)
         qd = qkv.to(DEV).requires_grad_(True)
         out = K.attention_packed(qd, mask.to(DEV), h, p)
         out.backward(dout.to(DEV))
-        _lib.lib().mt_attention_force_ffma(old)
-        res[force] = (out.detach().float().cpu(), qd.grad.float().cpu())
-        assert_close(res[force][0], outr, 1.5e-2, f'out force_ffma={force}')
-        assert_close(res[force][1], qr.grad, 2.5e-2, f'dqkv force_ffma={force}')
+        L.mt_attention_force_ffma(old); L.mt_attention_force_tiled(old_t)
+        res[eng] = (out.detach().float().cpu(), qd.grad.float().cpu())
+        assert_close(res[eng][0], outr, 1.5e-2, f'out {eng}')
+        assert_close(res[eng][1], qr.grad, 2.5e-2, f'dqkv {eng}')
+    res[0] = res['whole-head']
     # padded query rows: uniform attention over ALL keys (trap A.1), through the tensor-core engine too
     if p == 0:
         v = qkv[-1, :, 2 * d:].float()
