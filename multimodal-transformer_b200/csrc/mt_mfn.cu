@@ -24,6 +24,7 @@
 // (1,B) for the reference's permuted [T,B,D] views.  ST is the GEMM operand type (float / bf16): tensors that only
 // feed GEMMs are kept in ST, recurrent state and everything entering a transcendental stays fp32.
 #include "mt_recurrent.cuh"
+#include "mt_mfn.cuh"
 
 GemmDesc mt_wgrad_desc(int M, int Nout, int Kin, const void* dy, int ldy, const void* x, int ldx, float* dW, int ldw);
 
@@ -235,25 +236,6 @@ __device__ __forceinline__ void st_op(ST* p, float v) { *p = from_f<ST>(v); }
 // ======================================================================================================
 // F2 / B4: LSTM recurrences (one CTA per narrative tile and modality)
 // ======================================================================================================
-struct LstmArgs {
-  int B, T, n_mods;
-  long long sb, st;
-  int H[MT_MAX_MODS], hoff[MT_MAX_MODS];
-  int Hs, MEM;
-  const void* w_hh[MT_MAX_MODS];     // WT [4H][H]
-  const float* b_hh[MT_MAX_MODS];
-  float* gates;                      // [M,4Hs]
-  float* cstar;                      // [M,2Hs]
-  void* cstar_op;                    // ST [M,2Hs] (null when it aliases cstar)
-  void* last_op;                     // ST [M,Hs+MEM]
-  void* hprev_op;                    // ST [M,Hs] (training)
-  float* h_last; float* c_last;
-  int training;
-  const float* dlast;                // backward: [M,Hs+MEM]
-  const float* dcstar;               //           [M,2Hs]
-  void* dz_op;                       //           ST [M,4Hs]
-};
-
 template <typename WT, typename ST>
 __global__ void __launch_bounds__(NTHREADS, 1) mfn_lstm_fwd_kernel(const __grid_constant__ LstmArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -435,28 +417,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) mfn_lstm_bwd_kernel(const __grid_
 // ======================================================================================================
 // F4 / B2: memory recurrences (one CTA per narrative tile)
 // ======================================================================================================
-struct MemArgs {
-  int B, T;
-  long long sb, st;
-  int Hs, MEM, G;
-  const void* g1_fc1_w; const void* g2_fc1_w;      // WT [G][2Hs+MEM]
-  const void* g1_fc2_w; const void* g2_fc2_w;      // WT [MEM][G]
-  const float* g1_fc2_b; const float* g2_fc2_b;
-  const float* gpre;       // [M,2G]
-  const float* chat;       // [M,MEM]
-  void* gh_op;             // ST [M,2G]
-  float* gm;               // [M,2MEM]
-  void* memprev_op;        // ST [M,MEM]
-  void* last_op;           // ST [M,Hs+MEM]
-  float* mem_last;
-  DropCfg drop_g1, drop_g2;
-  int training;
-  const float* dlast;      // backward: [M,Hs+MEM]
-  void* dzg_op;            //           ST [M,2MEM]
-  void* dzchat_op;         //           ST [M,MEM]
-  void* dgh_op;            //           ST [M,2G]
-};
-
 template <typename WT, typename ST>
 __global__ void __launch_bounds__(NTHREADS, 1) mfn_mem_fwd_kernel(const __grid_constant__ MemArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
