@@ -27,6 +27,28 @@ def _arenas_of(model):
     return out
 
 
+def shard_batch(inputs, mask, target, lengths, rank, world):
+    """Data-parallel partition of one global batch: narratives sorted by length (descending, stable --
+    what generateTrainBatch does, MFT/train.py:62-63) are dealt round-robin to the ranks, so every rank sees a balanced
+    sum of lengths; each shard keeps the GLOBAL padded length T, which keeps kernels shape-identical across ranks.
+    Works on numpy arrays or torch tensors.  Returns (inputs, mask, target, lengths, global_norm) for `rank`;
+    global_norm = sum of ALL lengths is the loss normaliser every rank must use (gradients are then SUMMED)."""
+    order = sorted(range(len(lengths)), key=lambda i: -lengths[i])
+    mine = order[rank::world]
+    take = (lambda a: a[mine])
+    return ({m: take(v) for m, v in inputs.items()}, take(mask), take(target), [lengths[i] for i in mine], float(sum(lengths)))
+
+
+def all_reduce_flat_(bufs, group=None):
+    """SUM-all-reduce every flat gradient buffer in place (one collective per arena; NCCL on GPUs, gloo in the CPU tests).
+    No-op without an initialised process group or with a single rank."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return bufs
+    for g in bufs:
+        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+    return bufs
+
+
 def train_step_loss(pred, target, norm):
     """loss = sum((pred - target)^2) / norm (MFT/train.py:135-139) computed and differentiated by one kernel, then
     pred.backward(dloss/dpred).  `norm` is the GLOBAL sum of lengths under data parallelism.  Returns loss [1]."""
@@ -76,7 +98,7 @@ class FlatAdam:
             g = self._flat_grad(a)
             if g is None:
                 continue
-            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+            all_reduce_flat_([g], self.group)
             if a.flat_grad() is None:          # gathered copy: scatter back
                 for p, v in zip(a.params, a.grad_views(g)):
                     p.grad.copy_(v)
