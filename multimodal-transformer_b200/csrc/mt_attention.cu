@@ -342,13 +342,16 @@ int mt_attn_fwd_run(int dtype, int B, int T_, int d, int h, const void* qkv, con
 }
 
 int mt_attn_bwd_run(int dtype, int B, int T_, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse,
-                    const void* dout, void* dqkv, DropCfg drop, float* Dws, cudaStream_t st) {
+                    const void* dout, void* dqkv, DropCfg drop, float* Dws, cudaStream_t st, float* dbias) {
   MT_TRY(check_shape(B, T_, d, h));
   if (!qkv || !out || !lse || !dout || !dqkv || !Dws) return MT_ERR_ARG;
+  bool done = false;
   if (dtype == MT_BF16 && !g_attn_force_ffma && mt_attn_mma_supported(B, T_, d, h))
-    return mt_attn_mma_bwd_run(B, T_, d, h, qkv, mask, out, lse, dout, dqkv, drop, st);
-  if (dtype == MT_BF16) return bwd_dispatch<bf16>(B, T_, d, h, qkv, mask, out, lse, dout, dqkv, drop, Dws, st);
-  return bwd_dispatch<float>(B, T_, d, h, qkv, mask, out, lse, dout, dqkv, drop, Dws, st);
+    MT_TRY(mt_attn_mma_bwd_run(B, T_, d, h, qkv, mask, out, lse, dout, dqkv, drop, st, dbias, &done));
+  else if (dtype == MT_BF16) MT_TRY(bwd_dispatch<bf16>(B, T_, d, h, qkv, mask, out, lse, dout, dqkv, drop, Dws, st));
+  else MT_TRY(bwd_dispatch<float>(B, T_, d, h, qkv, mask, out, lse, dout, dqkv, drop, Dws, st));
+  if (dbias && !done) MT_TRY(mt_colsum_run(dtype == MT_BF16, B * T_, 3 * d, dqkv, 3 * d, dbias, 1, st));
+  return MT_OK;
 }
 
 extern "C" {

@@ -344,8 +344,12 @@ int mt_attn_mma_fwd_run(int B, int T, int d, int h, const void* qkv, const float
 }
 
 int mt_attn_mma_bwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse, const void* dout,
-                        void* dqkv, DropCfg drop, cudaStream_t st) {
-  if (!g_force_tiled && mt_attn128_supported(B, T, d, h)) return mt_attn128_bwd_run(B, T, d, h, qkv, mask, out, lse, dout, dqkv, drop, st);
+                        void* dqkv, DropCfg drop, cudaStream_t st, float* dbias, bool* dbias_done) {
+  if (dbias_done) *dbias_done = false;
+  if (!g_force_tiled && mt_attn128_supported(B, T, d, h)) {
+    if (dbias_done) *dbias_done = dbias != nullptr;
+    return mt_attn128_bwd_run(B, T, d, h, qkv, mask, out, lse, dout, dqkv, drop, st, dbias);
+  }
   const int dk = d / h;
   const float scale = 1.0f / sqrtf((float)dk);
   dim3 grid((T + WARPS * 16 - 1) / (WARPS * 16), h, B);

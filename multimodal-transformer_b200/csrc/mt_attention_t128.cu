@@ -131,6 +131,19 @@ __global__ void __launch_bounds__(NT, 2) attn128_fwd_kernel(int B, int T, int d,
   }
 }
 
+// column sums over the 16 rows of an accumulator fragment set acc[DK/8][4] (rows lane/4 and lane/4 + 8, columns
+// i*8 + 2*(lane%4) + {0,1}) added into s[DK]; rows beyond T hold exact zeros
+template <int DK>
+__device__ __forceinline__ void colsum_frag(float* s, const float (*acc)[4], int lane) {
+#pragma unroll
+  for (int i = 0; i < DK / 8; ++i) {
+    float a = acc[i][0] + acc[i][2], b = acc[i][1] + acc[i][3];
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    if (lane < 4) { atomicAdd(s + i * 8 + 2 * lane, a); atomicAdd(s + i * 8 + 2 * lane + 1, b); }
+  }
+}
+
 template <int DK>
 struct BwdSmem {
   static constexpr int LD = DK + 8, LP = TMAX + 8;
@@ -141,10 +154,13 @@ template <int DK>
 __global__ void __launch_bounds__(NT, DK <= 32 ? 2 : 1) attn128_bwd_kernel(int B, int T, int d, int h, const bf16* __restrict__ qkv,
                                                                            const float* __restrict__ mask, const bf16* __restrict__ out,
                                                                            const float* __restrict__ lse, const bf16* __restrict__ dout,
-                                                                           bf16* __restrict__ dqkv, DropCfg drop_in, float scale) {
+                                                                           bf16* __restrict__ dqkv, DropCfg drop_in, float scale,
+                                                                           float* __restrict__ dbias) {
   const DropCfg drop = mt_drop_resolve(drop_in);
   constexpr int LD = BwdSmem<DK>::LD, LP = BwdSmem<DK>::LP;
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ float s_cs[3 * DK];          // column sums of this head's dQ | dK | dV slabs (bias gradient of the QKV projection)
+  if (dbias) for (int i = threadIdx.x; i < 3 * DK; i += NT) s_cs[i] = 0.f;
   bf16* Qs = reinterpret_cast<bf16*>(smem_raw);
   bf16* Ks = Qs + TMAX * LD;
   bf16* Vs = Ks + TMAX * LD;
@@ -255,6 +271,7 @@ __global__ void __launch_bounds__(NT, DK <= 32 ? 2 : 1) attn128_bwd_kernel(int B
       if (in0) *reinterpret_cast<uint32_t*>(dqkv + ((size_t)b * T + r0) * ld + hd * DK + i * 8 + c) = pack2(dq[i][0], dq[i][1]);
       if (in1) *reinterpret_cast<uint32_t*>(dqkv + ((size_t)b * T + r1) * ld + hd * DK + i * 8 + c) = pack2(dq[i][2], dq[i][3]);
     }
+    if (dbias) colsum_frag<DK>(s_cs, dq, lane);
   }
   __syncthreads();
 
@@ -287,19 +304,24 @@ __global__ void __launch_bounds__(NT, DK <= 32 ? 2 : 1) attn128_bwd_kernel(int B
         *reinterpret_cast<uint32_t*>(dqkv + ((size_t)b * T + r1) * ld + 2 * d + hd * DK + i * 8 + c) = pack2(dv[i][2], dv[i][3]);
       }
     }
+    if (dbias) { colsum_frag<DK>(s_cs + DK, dk, lane); colsum_frag<DK>(s_cs + 2 * DK, dv, lane); }
+  }
+  if (dbias) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * DK; i += NT) atomicAdd(dbias + (i / DK) * d + hd * DK + (i % DK), s_cs[i]);
   }
 }
 
 template <int DK>
 int launch_bwd(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse, const void* dout, void* dqkv,
-               DropCfg drop, float scale, cudaStream_t st) {
+               DropCfg drop, float scale, float* dbias, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
     MT_CUDA(cudaFuncSetAttribute(attn128_bwd_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdSmem<DK>::BYTES));
     attr = true;
   }
   attn128_bwd_kernel<DK><<<B * h, NT, BwdSmem<DK>::BYTES, st>>>(B, T, d, h, (const bf16*)qkv, mask, (const bf16*)out, lse, (const bf16*)dout,
-                                                                 (bf16*)dqkv, drop, scale);
+                                                                 (bf16*)dqkv, drop, scale, dbias);
   MT_LAUNCH_CHECK();
   return MT_OK;
 }
@@ -327,14 +349,14 @@ int mt_attn128_fwd_run(int B, int T, int d, int h, const void* qkv, const float*
 }
 
 int mt_attn128_bwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse, const void* dout,
-                       void* dqkv, DropCfg drop, cudaStream_t st) {
+                       void* dqkv, DropCfg drop, cudaStream_t st, float* dbias) {
   const int dk = d / h;
   const float scale = 1.0f / sqrtf((float)dk);
   mt_prof_work(10.0 * B * (double)T * T * d, (double)B * T * d * 9.0 * 2.0);
   switch (dk) {
-    case 16: return launch_bwd<16>(B, T, d, h, qkv, mask, out, lse, dout, dqkv, drop, scale, st);
-    case 32: return launch_bwd<32>(B, T, d, h, qkv, mask, out, lse, dout, dqkv, drop, scale, st);
-    case 64: return launch_bwd<64>(B, T, d, h, qkv, mask, out, lse, dout, dqkv, drop, scale, st);
+    case 16: return launch_bwd<16>(B, T, d, h, qkv, mask, out, lse, dout, dqkv, drop, scale, dbias, st);
+    case 32: return launch_bwd<32>(B, T, d, h, qkv, mask, out, lse, dout, dqkv, drop, scale, dbias, st);
+    case 64: return launch_bwd<64>(B, T, d, h, qkv, mask, out, lse, dout, dqkv, drop, scale, dbias, st);
     default: return MT_ERR_UNSUPPORTED;
   }
 }

@@ -58,6 +58,17 @@ __device__ __forceinline__ float4 ld4(const bf16* p) {
   float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
   return make_float4(fa.x, fa.y, fb.x, fb.y);
 }
+// raw (unconverted) 4-element loads: keep prefetched registers free of dependent convert instructions
+template <typename T> struct Raw4;
+template <> struct Raw4<float> { typedef float4 type; };
+template <> struct Raw4<bf16> { typedef uint2 type; };
+__device__ __forceinline__ float4 ld4raw(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ uint2 ld4raw(const bf16* p) { return *reinterpret_cast<const uint2*>(p); }
+__device__ __forceinline__ float4 cvt4(float4 v) { return v; }
+__device__ __forceinline__ float4 cvt4(uint2 u) {
+  float2 fa = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.x)), fb = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.y));
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ void st4(bf16* p, float4 v) {
   __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
@@ -80,6 +91,11 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ---- counter-based dropout generator (mirrored by oracle/dropout_rng.py) -----------------------------
+// One 32-bit draw decides TWO adjacent elements (16 bits each, threshold = (p * 2^32) >> 16): the per-element hash was the
+// largest single instruction cost of every epilogue that applies dropout.
+//   key            = mix32(seed_lo ^ 0x9E3779B9 * (site + 1)) + seed_hi * 0x85EBCA6B          (once per thread)
+//   draw32(pair)   = mix32(pair_lo ^ key ^ pair_hi * 0xC2B2AE35)
+//   element e      -> pair e >> 1, low half when e is even;   keep = half >= t16
 __host__ __device__ __forceinline__ uint32_t mt_mix32(uint32_t x) {
   x ^= x >> 16;
   x *= 0x7FEB352Du;
@@ -88,12 +104,6 @@ __host__ __device__ __forceinline__ uint32_t mt_mix32(uint32_t x) {
   x ^= x >> 16;
   return x;
 }
-__host__ __device__ __forceinline__ uint32_t mt_rand_u32(uint64_t seed, uint32_t site, uint64_t idx) {
-  uint32_t lo = (uint32_t)idx, hi = (uint32_t)(idx >> 32);
-  uint32_t h = mt_mix32(lo ^ (uint32_t)seed);
-  uint32_t add = 0x9E3779B9u * (site + 1u) + (uint32_t)(seed >> 32);
-  return mt_mix32(h + add + hi * 0x85EBCA6Bu);
-}
 static inline uint32_t mt_drop_threshold(float p) {
   double t = (double)p * 4294967296.0;
   if (t <= 0) return 0u;
@@ -101,11 +111,12 @@ static inline uint32_t mt_drop_threshold(float p) {
   return (uint32_t)t;
 }
 struct DropCfg {
-  uint32_t thresh;   // 0 => dropout disabled
+  uint32_t thresh;   // 0 => dropout disabled; the kernels compare 16-bit halves against thresh >> 16
   float scale;       // 1/(1-p)
   uint64_t seed;
   uint32_t site;
   const unsigned long long* seed_off;   // optional device word added to `seed` (lets a captured CUDA graph draw fresh masks per replay)
+  uint32_t key;      // filled by mt_drop_resolve
 };
 extern const unsigned long long* g_mt_seed_offset_ptr;   // set by mt_set_seed_offset_ptr (mt_api.cu)
 static inline DropCfg mt_make_drop(float p, uint64_t seed, uint32_t site) {
@@ -115,24 +126,45 @@ static inline DropCfg mt_make_drop(float p, uint64_t seed, uint32_t site) {
   d.seed = seed;
   d.site = site;
   d.seed_off = (p > 0.f) ? g_mt_seed_offset_ptr : nullptr;
+  d.key = 0u;
   return d;
 }
-// fold the optional device-side seed offset into the seed ONCE per thread, at kernel entry
+// fold the optional device-side seed offset into the seed and derive the site key ONCE per thread, at kernel entry
 __device__ __forceinline__ DropCfg mt_drop_resolve(DropCfg d) {
-  if (d.thresh != 0u && d.seed_off) d.seed += (uint64_t)__ldg(d.seed_off);
+  if (d.thresh != 0u) {
+    if (d.seed_off) d.seed += (uint64_t)__ldg(d.seed_off);
+    d.key = mt_mix32((uint32_t)d.seed ^ (0x9E3779B9u * (d.site + 1u))) + (uint32_t)(d.seed >> 32) * 0x85EBCA6Bu;
+  }
   d.seed_off = nullptr;
   return d;
 }
+__device__ __forceinline__ uint32_t mt_draw32(const DropCfg& d, uint64_t pair) {
+  return mt_mix32((uint32_t)pair ^ d.key ^ ((uint32_t)(pair >> 32) * 0xC2B2AE35u));
+}
 __device__ __forceinline__ float mt_drop_factor(const DropCfg& d, uint64_t idx) {
   if (d.thresh == 0u) return 1.0f;
-  return mt_rand_u32(d.seed, d.site, idx) >= d.thresh ? d.scale : 0.0f;
+  const uint32_t bits = mt_draw32(d, idx >> 1);
+  const uint32_t v = (idx & 1ull) ? (bits >> 16) : (bits & 0xFFFFu);
+  return v >= (d.thresh >> 16) ? d.scale : 0.0f;
+}
+// elements idx (even) and idx + 1
+__device__ __forceinline__ void mt_drop_pair(const DropCfg& d, uint64_t idx, float& f0, float& f1) {
+  if (d.thresh == 0u) { f0 = f1 = 1.0f; return; }
+  const uint32_t bits = mt_draw32(d, idx >> 1);
+  const uint32_t t16 = d.thresh >> 16;
+  f0 = (bits & 0xFFFFu) >= t16 ? d.scale : 0.0f;
+  f1 = (bits >> 16) >= t16 ? d.scale : 0.0f;
+}
+// elements idx .. idx + 3 (idx a multiple of 2)
+__device__ __forceinline__ void mt_drop_quad(const DropCfg& d, uint64_t idx, float* f) {
+  mt_drop_pair(d, idx, f[0], f[1]);
+  mt_drop_pair(d, idx + 2, f[2], f[3]);
 }
 
-// Attention-probability dropout (site MT_SITE_ATTN_P): one 32-bit draw decides TWO adjacent keys of a query row, 16 bits
-// each (threshold = thresh >> 16), because the per-element hash dominated the attention kernels' instruction count.
-// row = flat (batch, head, query) index, P2 = ceil(T / 2), j = key index.   Mirrored by oracle/dropout_rng.py:attn_keep_mask.
+// Attention-probability dropout (site MT_SITE_ATTN_P): pair index = row * ceil(T/2) + (j >> 1) so a pair never straddles
+// two query rows.  row = flat (batch, head, query) index, j = key index.   Mirrored by oracle/dropout_rng.py:attn_keep_mask.
 __device__ __forceinline__ uint32_t mt_attn_drop_bits(const DropCfg& d, uint64_t row, uint32_t P2, uint32_t j) {
-  return mt_rand_u32(d.seed, d.site, row * (uint64_t)P2 + (uint64_t)(j >> 1));
+  return mt_draw32(d, row * (uint64_t)P2 + (uint64_t)(j >> 1));
 }
 __device__ __forceinline__ float mt_attn_drop_factor(const DropCfg& d, uint64_t row, uint32_t P2, uint32_t j) {
   if (d.thresh == 0u) return 1.0f;

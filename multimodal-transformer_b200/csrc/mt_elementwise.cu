@@ -58,33 +58,58 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(int M, const floa
 //   g = dy*a;  dx = (g - mean(g) - xc * sum(g*xc) / ((d-1) * s * (s+eps))) / (s+eps)  [+ dres]
 //   da += sum_rows dy * xhat ; db += sum_rows dy        (register partials -> smem -> one atomic per column per CTA)
 // ------------------------------------------------------------------------------------------------------
-template <typename TY, int NCH>
+//   NEXT: the same pass also emits what the layer below consumes first -- nx_out = dx * dropout_factor(site, row*d + col)
+//   in the operand dtype (the gradient through that sublayer's output dropout) and nx_db += colsum(nx_out) (the bias
+//   gradient of the Linear that produced the dropped tensor) -- instead of a drop_grad pass + a colsum pass over dx.
+template <typename TY, int NCH, bool NEXT>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(int M, const float* __restrict__ x, const float* __restrict__ a, float eps,
                                                                const TY* __restrict__ dy, const float* __restrict__ dres,
-                                                               float* __restrict__ dx, float* __restrict__ da, float* __restrict__ db) {
+                                                               float* __restrict__ dx, float* __restrict__ da, float* __restrict__ db,
+                                                               TY* __restrict__ nx_out, float* __restrict__ nx_db, DropCfg nx_drop_in) {
   constexpr int d = NCH * 128;
-  __shared__ float s_da[d], s_db[d];
+  __shared__ float s_da[d], s_db[d], s_dn[NEXT ? d : 1];
+  const DropCfg nx_drop = mt_drop_resolve(nx_drop_in);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < d; i += blockDim.x) { s_da[i] = 0.f; s_db[i] = 0.f; }
+  for (int i = threadIdx.x; i < d; i += blockDim.x) { s_da[i] = 0.f; s_db[i] = 0.f; if (NEXT) s_dn[i] = 0.f; }
   __syncthreads();
-  float4 av[NCH], pa[NCH], pb[NCH];
+  float4 av[NCH], pa[NCH], pb[NCH], pn[NEXT ? NCH : 1];
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     av[c] = ld4(a + c * 128 + lane * 4);
     pa[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     pb[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (NEXT) pn[c] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  for (int row = blockIdx.x * LN_WARPS + warp; row < M; row += gridDim.x * LN_WARPS) {
-    const float* xr = x + (size_t)row * d;
-    const TY* gr = dy + (size_t)row * d;
-    float4 v[NCH], g[NCH];
-    float s = 0.f;
+  // software pipeline: the next row's x / dy / dres are in flight while this row goes through its three dependent
+  // warp reductions (one row per warp leaves too few bytes in flight otherwise)
+  const int stride = gridDim.x * LN_WARPS;
+  int row = blockIdx.x * LN_WARPS + warp;
+  float4 nv[NCH], nr[NCH];
+  typename Raw4<TY>::type ng[NCH];
+  if (row < M) {
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-      v[c] = ld4(xr + c * 128 + lane * 4);
-      g[c] = ld4(gr + c * 128 + lane * 4);
-      s += (v[c].x + v[c].y) + (v[c].z + v[c].w);
+      nv[c] = ld4(x + (size_t)row * d + c * 128 + lane * 4);
+      ng[c] = ld4raw(dy + (size_t)row * d + c * 128 + lane * 4);
+      nr[c] = dres ? ld4(dres + (size_t)row * d + c * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  }
+  for (; row < M; row += stride) {
+    float4 v[NCH], g[NCH], r[NCH];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) { v[c] = nv[c]; g[c] = cvt4(ng[c]); r[c] = nr[c]; }
+    const int nrow = row + stride;
+    if (nrow < M) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        nv[c] = ld4(x + (size_t)nrow * d + c * 128 + lane * 4);
+        ng[c] = ld4raw(dy + (size_t)nrow * d + c * 128 + lane * 4);
+        if (dres) nr[c] = ld4(dres + (size_t)nrow * d + c * 128 + lane * 4);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) s += (v[c].x + v[c].y) + (v[c].z + v[c].w);
     const float mean = warp_sum(s) * (1.0f / d);
     float q = 0.f;
 #pragma unroll
@@ -116,11 +141,24 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(int M, const floa
       o.y = (g[c].y - gm - v[c].y * k) * inv;
       o.z = (g[c].z - gm - v[c].z * k) * inv;
       o.w = (g[c].w - gm - v[c].w * k) * inv;
-      if (dres) {
-        float4 r = ld4(dres + (size_t)row * d + c * 128 + lane * 4);
-        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-      }
+      o.x += r[c].x; o.y += r[c].y; o.z += r[c].z; o.w += r[c].w;
       st4(dxr + c * 128 + lane * 4, o);
+      if (NEXT) {
+        const uint64_t idx = (uint64_t)row * d + c * 128 + lane * 4;
+        float f[4];
+        mt_drop_quad(nx_drop, idx, f);
+        o.x *= f[0]; o.y *= f[1]; o.z *= f[2]; o.w *= f[3];
+        st4(nx_out + (size_t)row * d + c * 128 + lane * 4, o);
+        pn[c].x += o.x; pn[c].y += o.y; pn[c].z += o.z; pn[c].w += o.w;
+      }
+    }
+  }
+  if (NEXT) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      int col = c * 128 + lane * 4;
+      atomicAdd(&s_dn[col + 0], pn[c].x); atomicAdd(&s_dn[col + 1], pn[c].y);
+      atomicAdd(&s_dn[col + 2], pn[c].z); atomicAdd(&s_dn[col + 3], pn[c].w);
     }
   }
 #pragma unroll
@@ -135,6 +173,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(int M, const floa
   for (int i = threadIdx.x; i < d; i += blockDim.x) {
     atomicAdd(da + i, s_da[i]);
     atomicAdd(db + i, s_db[i]);
+    if (NEXT) atomicAdd(nx_db + i, s_dn[i]);
   }
 }
 
@@ -143,10 +182,9 @@ __global__ void drop_grad_kernel(size_t n4, const float* __restrict__ g, TO* __r
   const DropCfg drop = mt_drop_resolve(drop_in);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 v = ld4(g + i * 4);
-    v.x *= mt_drop_factor(drop, i * 4 + 0);
-    v.y *= mt_drop_factor(drop, i * 4 + 1);
-    v.z *= mt_drop_factor(drop, i * 4 + 2);
-    v.w *= mt_drop_factor(drop, i * 4 + 3);
+    float f[4];
+    mt_drop_quad(drop, (uint64_t)i * 4, f);
+    v.x *= f[0]; v.y *= f[1]; v.z *= f[2]; v.w *= f[3];
     st4(out + i * 4, v);
   }
 }
@@ -275,21 +313,23 @@ int ln_fwd_dispatch(int M, int d, const float* x, const float* a, const float* b
   return MT_OK;
 }
 
-template <typename TY>
+template <typename TY, bool NEXT>
 int ln_bwd_dispatch(int M, int d, const float* x, const float* a, float eps, const TY* dy, const float* dres, float* dx, float* da,
-                    float* db, cudaStream_t st) {
+                    float* db, TY* nx_out, float* nx_db, DropCfg nx_drop, cudaStream_t st) {
   int grid = (M + LN_WARPS - 1) / LN_WARPS;
   if (grid > 148 * 4) grid = 148 * 4;
-  mt_prof_work(0.0, (double)M * d * (8.0 + sizeof(TY) + (dres ? 4.0 : 0.0)));
+  mt_prof_work(0.0, (double)M * d * (8.0 + sizeof(TY) + (dres ? 4.0 : 0.0) + (NEXT ? sizeof(TY) : 0.0)));
+#define MT_LNB(NCH) ln_bwd_kernel<TY, NCH, NEXT><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, eps, dy, dres, dx, da, db, nx_out, nx_db, nx_drop)
   switch (d / 128) {
-    case 1: ln_bwd_kernel<TY, 1><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, eps, dy, dres, dx, da, db); break;
-    case 2: ln_bwd_kernel<TY, 2><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, eps, dy, dres, dx, da, db); break;
-    case 3: ln_bwd_kernel<TY, 3><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, eps, dy, dres, dx, da, db); break;
-    case 4: ln_bwd_kernel<TY, 4><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, eps, dy, dres, dx, da, db); break;
-    case 6: ln_bwd_kernel<TY, 6><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, eps, dy, dres, dx, da, db); break;
-    case 8: ln_bwd_kernel<TY, 8><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, eps, dy, dres, dx, da, db); break;
+    case 1: MT_LNB(1); break;
+    case 2: MT_LNB(2); break;
+    case 3: MT_LNB(3); break;
+    case 4: MT_LNB(4); break;
+    case 6: MT_LNB(6); break;
+    case 8: MT_LNB(8); break;
     default: return MT_ERR_UNSUPPORTED;
   }
+#undef MT_LNB
   MT_LAUNCH_CHECK();
   return MT_OK;
 }
@@ -303,10 +343,16 @@ int mt_ln_fwd_run(int M, int d, const float* x, const float* a, const float* b, 
 }
 
 int mt_ln_bwd_run(int M, int d, const float* x, const float* a, float eps, const void* dy, bool dy_bf16, const float* dres, float* dx,
-                  float* da, float* db, cudaStream_t st) {
+                  float* da, float* db, cudaStream_t st, const LnBwdNext* nx) {
   if (M <= 0 || d <= 0 || d % 128 != 0 || d > 1024 || !x || !a || !dy || !dx || !da || !db) return MT_ERR_ARG;
-  if (dy_bf16) return ln_bwd_dispatch<bf16>(M, d, x, a, eps, (const bf16*)dy, dres, dx, da, db, st);
-  return ln_bwd_dispatch<float>(M, d, x, a, eps, (const float*)dy, dres, dx, da, db, st);
+  const DropCfg nodrop = mt_make_drop(0.f, 0, 0);
+  if (nx && nx->out) {
+    if (!nx->dbias || nx->out == dy) return MT_ERR_ARG;
+    if (dy_bf16) return ln_bwd_dispatch<bf16, true>(M, d, x, a, eps, (const bf16*)dy, dres, dx, da, db, (bf16*)nx->out, nx->dbias, nx->drop, st);
+    return ln_bwd_dispatch<float, true>(M, d, x, a, eps, (const float*)dy, dres, dx, da, db, (float*)nx->out, nx->dbias, nx->drop, st);
+  }
+  if (dy_bf16) return ln_bwd_dispatch<bf16, false>(M, d, x, a, eps, (const bf16*)dy, dres, dx, da, db, nullptr, nullptr, nodrop, st);
+  return ln_bwd_dispatch<float, false>(M, d, x, a, eps, (const float*)dy, dres, dx, da, db, nullptr, nullptr, nodrop, st);
 }
 
 int mt_drop_grad_run(int M, int N, const float* g, void* out, bool out_bf16, DropCfg drop, cudaStream_t st) {

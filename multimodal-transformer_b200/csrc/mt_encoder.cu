@@ -222,7 +222,21 @@ int mt_encoder_bwd(const MtEncoderCfg* cfg, const float* params, const void* par
   float* g_cur = w.g0;
   float* g_nxt = w.g1;
   const float* x_last = w.L[c.n_layers - 1].x_out;
-  MT_TRY(mt_ln_bwd_run(M, d, x_last, params + P.lnf_a, 1e-6f, dy, lp && !c.y_f32, nullptr, g_cur, grads + P.lnf_a, grads + P.lnf_b, st));
+  // every LayerNorm backward also emits the dropped operand-dtype gradient the sublayer below starts from, and that
+  // sublayer's output-bias gradient (LnBwdNext), so no separate dropout-gradient / column-sum passes run over [M,d]
+  {
+    const size_t bl = P.layer_stride * (c.n_layers - 1);
+    const DropCfg dr = mt_make_drop(p, c.seed, mt_enc_site(c.stack_id, c.n_layers - 1, MT_SITE_SUB1));
+    LnBwdNext nx{w.dact, grads + bl + P.b_2, dr};
+    const bool dy_lp = lp && !c.y_f32;
+    if (dy_lp == lp) {
+      MT_TRY(mt_ln_bwd_run(M, d, x_last, params + P.lnf_a, 1e-6f, dy, dy_lp, nullptr, g_cur, grads + P.lnf_a, grads + P.lnf_b, st, &nx));
+    } else {      // fp32 dy in bf16 mode: the fused second output has dy's dtype, so take the two-pass route once
+      MT_TRY(mt_ln_bwd_run(M, d, x_last, params + P.lnf_a, 1e-6f, dy, dy_lp, nullptr, g_cur, grads + P.lnf_a, grads + P.lnf_b, st));
+      MT_TRY(mt_drop_grad_run(M, d, g_cur, w.dact, lp, dr, st));
+      MT_TRY(mt_colsum_run(lp, M, d, w.dact, d, grads + bl + P.b_2, 1, st));
+    }
+  }
 
   for (int l = c.n_layers - 1; l >= 0; --l) {
     const size_t base = P.layer_stride * l;
@@ -230,29 +244,29 @@ int mt_encoder_bwd(const MtEncoderCfg* cfg, const float* params, const void* par
     float* gf = grads + base;
     LayerBufs& b = w.L[l];
     const float* x_l = l == 0 ? x : w.L[l - 1].x_out;
-    // ---- FFN sublayer: x_out = xp + drop(w_2 hid + b_2) -------------------------------------------
-    MT_TRY(mt_drop_grad_run(M, d, g_cur, w.dact, lp, mt_make_drop(p, c.seed, mt_enc_site(c.stack_id, l, MT_SITE_SUB1)), st));
+    // ---- FFN sublayer: x_out = xp + drop(w_2 hid + b_2); w.dact = drop' . g_cur and db_2 are already there ----------
     MT_TRY(mt_gemm_run(c.dtype, wgrad_gemm(M, d, dff, w.dact, d, b.hid, dff, gf + P.w_2, dff), st));
-    MT_TRY(mt_colsum_run(lp, M, d, w.dact, d, gf + P.b_2, 1, st));
     GemmDesc g = dgrad_gemm(M, d, dff, w.dact, wptr(c, params, params_lp, base + P.w_2), w.dhid, !lp);
     g.epi.gate = b.hid; g.epi.ldg = dff; g.epi.gate_scale = keep_scale;   // relu' and the hidden dropout mask in one test
+    g.epi.colsum = gf + P.b_1;                                            // db_1 = colsum(dhid), from the epilogue
     MT_TRY(mt_gemm_run(c.dtype, g, st));
     MT_TRY(mt_gemm_run(c.dtype, wgrad_gemm(M, dff, d, w.dhid, dff, b.v, d, gf + P.w_1, d), st));
-    MT_TRY(mt_colsum_run(lp, M, dff, w.dhid, dff, gf + P.b_1, 1, st));
     MT_TRY(mt_gemm_run(c.dtype, dgrad_gemm(M, dff, d, w.dhid, wptr(c, params, params_lp, base + P.w_1), w.dact2, !lp), st));
-    MT_TRY(mt_ln_bwd_run(M, d, b.xp, pf + P.ln2_a, 1e-6f, w.dact2, lp, g_cur, g_nxt, gf + P.ln2_a, gf + P.ln2_b, st));
-    // ---- attention sublayer: xp = x + drop(att w_o + b_o) -----------------------------------------
-    MT_TRY(mt_drop_grad_run(M, d, g_nxt, w.dact, lp, mt_make_drop(p, c.seed, mt_enc_site(c.stack_id, l, MT_SITE_SUB0)), st));
+    {
+      LnBwdNext nx{w.dact, gf + P.b_o, mt_make_drop(p, c.seed, mt_enc_site(c.stack_id, l, MT_SITE_SUB0))};
+      MT_TRY(mt_ln_bwd_run(M, d, b.xp, pf + P.ln2_a, 1e-6f, w.dact2, lp, g_cur, g_nxt, gf + P.ln2_a, gf + P.ln2_b, st, &nx));
+    }
+    // ---- attention sublayer: xp = x + drop(att w_o + b_o); w.dact = drop' . g_nxt and db_o are already there ---------
     MT_TRY(mt_gemm_run(c.dtype, wgrad_gemm(M, d, d, w.dact, d, b.att, d, gf + P.w_o, d), st));
-    MT_TRY(mt_colsum_run(lp, M, d, w.dact, d, gf + P.b_o, 1, st));
     MT_TRY(mt_gemm_run(c.dtype, dgrad_gemm(M, d, d, w.dact, wptr(c, params, params_lp, base + P.w_o), w.dact2, !lp), st));
     MT_TRY(mt_attn_bwd_run(c.dtype, c.B, c.T, d, c.h, b.qkv, mask, b.att, b.lse, w.dact2, w.dqkv,
-                           mt_make_drop(p, c.seed, mt_enc_site(c.stack_id, l, MT_SITE_ATTN_P)), w.Dws, st));
+                           mt_make_drop(p, c.seed, mt_enc_site(c.stack_id, l, MT_SITE_ATTN_P)), w.Dws, st, gf + P.b_qkv));
     MT_TRY(mt_gemm_run(c.dtype, wgrad_gemm(M, 3 * d, d, w.dqkv, 3 * d, b.u, d, gf + P.w_qkv, d), st));
-    MT_TRY(mt_colsum_run(lp, M, 3 * d, w.dqkv, 3 * d, gf + P.b_qkv, 1, st));
-    MT_TRY(mt_gemm_run(c.dtype, dgrad_gemm(M, 3 * d, d, w.dqkv, wptr(c, params, params_lp, base + P.w_qkv), w.dact, !lp), st));
+    MT_TRY(mt_gemm_run(c.dtype, dgrad_gemm(M, 3 * d, d, w.dqkv, wptr(c, params, params_lp, base + P.w_qkv), w.dact2, !lp), st));
     float* out = l == 0 ? dx : g_cur;
-    MT_TRY(mt_ln_bwd_run(M, d, x_l, pf + P.ln1_a, 1e-6f, w.dact, lp, g_nxt, out, gf + P.ln1_a, gf + P.ln1_b, st));
+    LnBwdNext nx{nullptr, nullptr, mt_make_drop(0.f, 0, 0)};
+    if (l > 0) nx = LnBwdNext{w.dact, gf - P.layer_stride + P.b_2, mt_make_drop(p, c.seed, mt_enc_site(c.stack_id, l - 1, MT_SITE_SUB1))};
+    MT_TRY(mt_ln_bwd_run(M, d, x_l, pf + P.ln1_a, 1e-6f, w.dact2, lp, g_nxt, out, gf + P.ln1_a, gf + P.ln1_b, st, &nx));
     // g_cur now holds dL/dx_l (g_nxt is free again)
   }
   return MT_OK;

@@ -21,6 +21,13 @@ int mt_gemm_run(int dtype, const GemmDesc& g, cudaStream_t st) {
 #if MT_HAVE_TC
   if (dtype == MT_BF16 && !g_force_simt && mt_gemm_tc_supported(g)) return mt_gemm_tc_run(g, st);
 #endif
+  if (g.epi.colsum) {        // the FFMA engine has no fused column sum: run it, then one column-sum pass over C
+    if (g.split_k > 1) return MT_ERR_ARG;
+    GemmDesc g2 = g;
+    g2.epi.colsum = nullptr;
+    MT_TRY(mt_gemm_simt_run(dtype, g2, st));
+    return mt_colsum_run(dtype == MT_BF16 && !g.c_f32, g.M, g.N, g.C, g.ldc, g.epi.colsum, 1, st);
+  }
   return mt_gemm_simt_run(dtype, g, st);
 }
 

@@ -20,6 +20,8 @@ struct GemmEpi {
   const float* rowmask = nullptr;  // fp32 [M], multiplies the final value
   float alpha = 1.0f;
   int accumulate = 0;              // C += result (non-atomic)
+  float* colsum = nullptr;         // fp32 [N], ACCUMULATED: column sums of the final output (bias gradient of the layer whose
+                                   // pre-activation gradient this GEMM produces); not with split_k
 };
 
 struct GemmDesc {

@@ -117,7 +117,8 @@ struct Smem {
   static constexpr int THREADS = 64 + 32 * EW;
   static constexpr int EPI_BYTES = EW * 32 * (BN / (EW / 4) + 4) * 4;      // per epilogue warp: 32 rows x (its columns + 4) floats
   static constexpr int BAR_BYTES = 256;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024 /* alignment slack */;
+  static constexpr int CS_COLS = 1024;                                      // epi.colsum: per-CTA column accumulators (N <= CS_COLS)
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + CS_COLS * 4 + 1024 /* alignment slack */;
 };
 
 template <int BN>
@@ -134,6 +135,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* acc_full = bars + 2 * STAGES; // [2]       MMA -> epilogue
   uint64_t* acc_empty = acc_full + 2;     // [2]       epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* cs_smem = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + S::EPI_BYTES + S::BAR_BYTES);
+  if (g.epi.colsum) for (int i = threadIdx.x; i < g.N; i += blockDim.x) cs_smem[i] = 0.f;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_work = g.tiles_m * g.tiles_n * g.splits;
@@ -268,6 +271,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (e.bias) bias4 = *reinterpret_cast<const float4*>(e.bias + n);
+      float cs[4] = {0.f, 0.f, 0.f, 0.f};       // this lane's column partial sums (epi.colsum)
 #pragma unroll 1
       for (int i0 = 0; i0 < ITERS; i0 += U) {
         float4 res[U], gt[U];
@@ -296,9 +300,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int k = 0; k < 4; ++k) o[k] = tanhf(o[k]);
           }
           if (edrop.thresh != 0u) {
-            const uint64_t idx = (uint64_t)m * (uint64_t)g.N + (uint64_t)n;
+            float f[4];        // N % 4 == 0 and n % 4 == 0: idx is a multiple of 4
+            mt_drop_quad(edrop, (uint64_t)m * (uint64_t)g.N + (uint64_t)n, f);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) o[k] *= mt_drop_factor(edrop, idx + k);
+            for (int k = 0; k < 4; ++k) o[k] *= f[k];
           }
           if (e.gate) {
             o[0] = gt[u].x > 0.f ? o[0] * e.gate_scale : 0.f; o[1] = gt[u].y > 0.f ? o[1] * e.gate_scale : 0.f;
@@ -308,12 +313,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           o[2] = (o[2] + res[u].z) * rm[u]; o[3] = (o[3] + res[u].w) * rm[u];
           if (g.c_f32) st4(reinterpret_cast<float*>(g.C) + (size_t)m * g.ldc + n, make_float4(o[0], o[1], o[2], o[3]));
           else st4(reinterpret_cast<bf16*>(g.C) + (size_t)m * g.ldc + n, make_float4(o[0], o[1], o[2], o[3]));
+          cs[0] += o[0]; cs[1] += o[1]; cs[2] += o[2]; cs[3] += o[3];
+        }
+      }
+      if (e.colsum) {        // lanes lc, lc + LPR, ... hold the same columns (and took the same `continue` decisions above)
+        const unsigned am = __activemask();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+          for (int o = LPR; o < 32; o <<= 1) cs[k] += __shfl_xor_sync(am, cs[k], o);
+        }
+        if (lr == 0) {       // shared-memory accumulation across this CTA's tiles and warps; one global atomic per column at exit
+#pragma unroll
+          for (int k = 0; k < 4; ++k) atomicAdd(cs_smem + n + k, cs[k]);
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (g.epi.colsum) for (int i = threadIdx.x; i < g.N; i += blockDim.x) atomicAdd(g.epi.colsum + i, cs_smem[i]);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
@@ -414,6 +433,7 @@ bool mt_gemm_tc_supported(const GemmDesc& d) {
   if (((uintptr_t)d.A & 15) || ((uintptr_t)d.B & 15) || ((uintptr_t)d.C & 15)) return false;
   if (d.epi.accumulate) return false;
   if (d.split_k > 1 && !d.c_f32) return false;
+  if (d.epi.colsum && (d.split_k > 1 || d.N > 1024)) return false;
   if (d.epi.bias && ((uintptr_t)d.epi.bias & 15)) return false;
   if (d.epi.residual && (((uintptr_t)d.epi.residual & 15) || d.epi.ldr % 4 != 0)) return false;
   if (d.epi.gate && (((uintptr_t)d.epi.gate & 7) || d.epi.ldg % 4 != 0)) return false;

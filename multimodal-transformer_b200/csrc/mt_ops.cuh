@@ -22,8 +22,11 @@ static inline size_t mt_esize(int dtype) { return dtype == MT_BF16 ? 2 : 4; }
 
 // ---- element-wise / row-wise kernels (mt_elementwise.cu) ---------------------------------------------
 int mt_ln_fwd_run(int M, int d, const float* x, const float* a, const float* b, float eps, void* y, bool y_bf16, cudaStream_t st);
+// optional second output of the LayerNorm backward: out = dx * dropout_factor(drop, row*d + col) in the operand dtype
+// (same dtype as dy) and dbias[d] += colsum(out) -- what the sublayer below needs first (see ln_bwd_kernel)
+struct LnBwdNext { void* out; float* dbias; DropCfg drop; };
 int mt_ln_bwd_run(int M, int d, const float* x, const float* a, float eps, const void* dy, bool dy_bf16, const float* dres,
-                  float* dx, float* da, float* db, cudaStream_t st);
+                  float* dx, float* da, float* db, cudaStream_t st, const LnBwdNext* nx = nullptr);
 // out[M,N] (bf16 or f32) = g[M,N] (f32) * dropout_factor(site, m*N+n)      (gradient through an output dropout)
 int mt_drop_grad_run(int M, int N, const float* g, void* out, bool out_bf16, DropCfg drop, cudaStream_t st);
 // 2-D cast with zero padding / optional input dropout: dst[r, c] = c < cols ? src[r*lds + c] * drop(r*cols + c) : 0
@@ -39,17 +42,19 @@ int mt_transpose_pack_run(const TransposeJob* jobs, int n_jobs, bool dst_bf16, c
 // ---- tensor-core attention engine for bf16 (mt_attention_mma.cu) --------------------------------------------
 bool mt_attn_mma_supported(int B, int T, int d, int h);
 int mt_attn_mma_fwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop, cudaStream_t st);
+// dbias (optional, fp32 [3d], ACCUMULATED): column sums of dqkv = the QKV projection's bias gradient; *dbias_done tells
+// whether the kernel that ran produced it (otherwise the caller runs a column-sum pass)
 int mt_attn_mma_bwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse, const void* dout,
-                        void* dqkv, DropCfg drop, cudaStream_t st);
+                        void* dqkv, DropCfg drop, cudaStream_t st, float* dbias = nullptr, bool* dbias_done = nullptr);
 
 // ---- whole-head-per-CTA attention for T <= 128 (mt_attention_t128.cu), bf16 -----------------------------------
 bool mt_attn128_supported(int B, int T, int d, int h);
 int mt_attn128_fwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop, cudaStream_t st);
 int mt_attn128_bwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse, const void* dout,
-                       void* dqkv, DropCfg drop, cudaStream_t st);
+                       void* dqkv, DropCfg drop, cudaStream_t st, float* dbias = nullptr);
 
 // ---- attention (mt_attention.cu) ---------------------------------------------------------------------
 int mt_attn_fwd_run(int dtype, int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop,
                     cudaStream_t st);
 int mt_attn_bwd_run(int dtype, int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse,
-                    const void* dout, void* dqkv, DropCfg drop, float* Dws, cudaStream_t st);
+                    const void* dout, void* dqkv, DropCfg drop, float* Dws, cudaStream_t st, float* dbias = nullptr);

@@ -5,9 +5,10 @@ TEST INFRASTRUCTURE (see oracle/__init__.py).
 The reference draws dropout masks from PyTorch's Philox stream
 (``nn.Dropout`` at MFT/multiTransformer.py:17,45,101,158-174), which a fused
 kernel cannot reproduce bit-for-bit.  The CUDA path therefore defines its own
-stateless generator -- ``keep = hash(seed, site, element_index) >= p * 2**32`` --
+stateless generator -- one 32-bit ``hash(seed, site, element_index >> 1)`` per PAIR of elements, 16 bits each,
+``keep = half >= (p * 2**32) >> 16`` --
 and train-mode parity is "same result given the same masks": this file
-restates that generator (csrc/mt_common.cuh: mt_rand_u32) with torch int64
+restates that generator (csrc/mt_common.cuh: mt_draw32) with torch int64
 arithmetic so the oracle can apply *identical* masks.
 """
 import torch
@@ -25,16 +26,16 @@ def _mix32(x):
     return x
 
 
-def rand_u32(seed, site, idx):
-    """idx: int64 tensor of element indices (>= 0).  Returns int64 tensor in [0, 2**32)."""
+def draw32(seed, site, pair):
+    """csrc/mt_common.cuh: mt_drop_resolve (key) + mt_draw32.  pair: int64 tensor of PAIR indices (>= 0).
+    Returns int64 tensor in [0, 2**32): low 16 bits decide the even element of the pair, high 16 bits the odd one."""
     seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     seed_lo, seed_hi = seed & _M32, (seed >> 32) & _M32
-    lo = idx & _M32
-    hi = (idx >> 32) & _M32
-    h = _mix32(lo ^ seed_lo)
-    add = (0x9E3779B9 * (int(site) + 1) + seed_hi) & _M32
-    h = _mix32((h + add + ((hi * 0x85EBCA6B) & _M32)) & _M32)
-    return h
+    key0 = seed_lo ^ ((0x9E3779B9 * (int(site) + 1)) & _M32)
+    key = (int(_mix32(torch.tensor(key0, dtype=torch.int64))) + seed_hi * 0x85EBCA6B) & _M32
+    lo = pair & _M32
+    hi = (pair >> 32) & _M32
+    return _mix32(lo ^ key ^ ((hi * 0xC2B2AE35) & _M32))
 
 
 def threshold(p):
@@ -44,17 +45,19 @@ def threshold(p):
 
 
 def keep_mask(seed, site, shape, p):
-    """Boolean keep-mask of `shape` (row-major element index)."""
+    """Boolean keep-mask of `shape` (row-major element index e: pair e >> 1, low half for even e)."""
     n = 1
     for s in shape:
         n *= int(s)
     idx = torch.arange(n, dtype=torch.int64)
-    return (rand_u32(seed, site, idx) >= threshold(p)).reshape(tuple(shape))
+    bits = draw32(seed, site, idx >> 1)
+    v = torch.where((idx & 1) == 1, (bits >> 16) & 0xFFFF, bits & 0xFFFF)
+    return (v >= (threshold(p) >> 16)).reshape(tuple(shape))
 
 
 def attn_keep_mask(seed, site, shape, p):
     """Keep-mask of attention probabilities [B,h,T,T] (csrc/mt_common.cuh: mt_attn_drop_factor): one 32-bit draw per PAIR of
-    adjacent keys of a query row -- index row * ceil(T/2) + (j >> 1), even key = low 16 bits, odd key = high 16 bits,
+    adjacent keys of a query row -- pair index row * ceil(T/2) + (j >> 1), even key = low 16 bits, odd key = high 16 bits,
     threshold = threshold(p) >> 16."""
     *lead, T, Tk = [int(s) for s in shape]
     rows = 1
@@ -63,7 +66,7 @@ def attn_keep_mask(seed, site, shape, p):
     rows *= T
     P2 = (Tk + 1) // 2
     idx = torch.arange(rows * P2, dtype=torch.int64)
-    bits = rand_u32(seed, site, idx).reshape(rows, P2)
+    bits = draw32(seed, site, idx).reshape(rows, P2)
     lo, hi = bits & 0xFFFF, (bits >> 16) & 0xFFFF
     both = torch.stack([lo, hi], dim=-1).reshape(rows, 2 * P2)[:, :Tk]
     return (both >= (threshold(p) >> 16)).reshape(tuple(shape))
