@@ -70,6 +70,10 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ uint32_t pack_bf2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -121,7 +125,20 @@ struct Smem {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + CS_COLS * 4 + 1024 /* alignment slack */;
 };
 
-template <int BN>
+// Epilogue feature bits.  The hot shapes of the encoder / MFN path get their own instantiation (every test below folds at
+// compile time); F_GENERIC keeps all features behind run-time tests of the argument block.
+enum : uint32_t {
+  F_BIAS = 1u, F_RELU = 2u, F_TANH = 4u, F_DROP = 8u, F_GATE = 16u, F_RES = 32u, F_ROWMASK = 64u, F_CF32 = 128u, F_ATOMIC = 256u,
+  F_COLSUM = 512u, F_ALPHA = 1024u, F_EDGE = 2048u, F_RUNTIME = 4096u
+};
+constexpr uint32_t F_GENERIC = 0x1FFFu;
+#define HAS(bit, rt) (((F) & (bit)) != 0u && ((((F) & F_RUNTIME) == 0u) || (rt)))
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int BN, uint32_t F>
 __global__ void __launch_bounds__(Smem<BN>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ TcArgs g) {
   extern __shared__ uint8_t smem_raw[];
@@ -224,15 +241,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===== epilogue warps: warp w owns TMEM lane quarter (w % 4) and column slice (w - 2) / 4 of every tile =====
     constexpr int HN = BN / (S::EW / 4);       // columns per epilogue warp
     constexpr int LDS = HN + 4;                // staged row stride in floats (16-byte aligned, conflict-free both ways)
-    constexpr int LPR = HN / 4;                // lanes per output row (16-byte column quads)
+    constexpr int LPR = HN / 8;                // lanes per output row: each lane owns 8 consecutive columns
     constexpr int RPI = 32 / LPR;              // rows covered by one warp-wide access
     constexpr int ITERS = 32 / RPI;
-    constexpr int U = 4;                       // row-iterations whose global loads are issued back to back
     const int q = warp & 3, half = (warp - 2) >> 2;
     float* stg = epi_stage + (warp - 2) * 32 * LDS;
     const GemmEpi& e = g.epi;
-    const DropCfg edrop = mt_drop_resolve(e.drop);
-    const int lr = lane / LPR, lc = (lane % LPR) * 4;
+    const bool f_atomic = HAS(F_ATOMIC, g.atomic), f_cf32 = HAS(F_CF32, g.c_f32), f_bias = HAS(F_BIAS, e.bias != nullptr);
+    const bool f_res = HAS(F_RES, e.residual != nullptr), f_gate = HAS(F_GATE, e.gate != nullptr), f_rm = HAS(F_ROWMASK, e.rowmask != nullptr);
+    const bool f_colsum = HAS(F_COLSUM, e.colsum != nullptr), f_relu = HAS(F_RELU, e.act == MT_ACT_RELU), f_tanh = HAS(F_TANH, e.act == MT_ACT_TANH);
+    const bool f_alpha = HAS(F_ALPHA, e.alpha != 1.0f);
+    DropCfg edrop = mt_drop_resolve(e.drop);
+    const bool f_drop = HAS(F_DROP, edrop.thresh != 0u);
+    const int lr = lane / LPR, lc = (lane % LPR) * 8;
     int it = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
       const int tile = w % tiles;
@@ -257,75 +278,141 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
       const int n = n0 + lc;
-      if (n >= g.N || row_base >= g.M) continue;
-      if (g.atomic) {
-#pragma unroll 4
+      bool hi_ok = true;                        // columns n + 4 .. n + 7 exist (N % 4 == 0, so a quad is all-or-nothing)
+      if (F & F_EDGE) {
+        if (n >= g.N || row_base >= g.M) continue;
+        hi_ok = n + 4 < g.N;
+      }
+      if (f_atomic) {                           // split-K partial sums: vector reductions into the zero-initialised fp32 C
+#pragma unroll
         for (int i = 0; i < ITERS; ++i) {
           const int r = i * RPI + lr, m = row_base + r;
-          if (m >= g.M) continue;
-          const float4 a4 = *reinterpret_cast<const float4*>(stg + r * LDS + lc);
+          if ((F & F_EDGE) && m >= g.M) continue;
+          float4 a0 = *reinterpret_cast<const float4*>(stg + r * LDS + lc), a1 = *reinterpret_cast<const float4*>(stg + r * LDS + lc + 4);
+          if (f_alpha) { a0.x *= e.alpha; a0.y *= e.alpha; a0.z *= e.alpha; a0.w *= e.alpha; a1.x *= e.alpha; a1.y *= e.alpha; a1.z *= e.alpha; a1.w *= e.alpha; }
           float* cp = reinterpret_cast<float*>(g.C) + (size_t)m * g.ldc + n;
-          atomicAdd(cp, a4.x * e.alpha); atomicAdd(cp + 1, a4.y * e.alpha); atomicAdd(cp + 2, a4.z * e.alpha); atomicAdd(cp + 3, a4.w * e.alpha);
+          red_add_v4(cp, a0.x, a0.y, a0.z, a0.w);
+          if (hi_ok) red_add_v4(cp + 4, a1.x, a1.y, a1.z, a1.w);
         }
         continue;
       }
-      float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (e.bias) bias4 = *reinterpret_cast<const float4*>(e.bias + n);
-      float cs[4] = {0.f, 0.f, 0.f, 0.f};       // this lane's column partial sums (epi.colsum)
-#pragma unroll 1
-      for (int i0 = 0; i0 < ITERS; i0 += U) {
-        float4 res[U], gt[U];
-        float rm[U];
+      float bias8[8];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {            // issue every global load of this batch first
-          const int m = row_base + (i0 + u) * RPI + lr;
-          res[u] = make_float4(0.f, 0.f, 0.f, 0.f); gt[u] = make_float4(1.f, 1.f, 1.f, 1.f); rm[u] = 1.f;
-          if (m < g.M) {
-            if (e.residual) res[u] = *reinterpret_cast<const float4*>(e.residual + (size_t)m * e.ldr + n);
-            if (e.gate) gt[u] = ld4(reinterpret_cast<const bf16*>(e.gate) + (size_t)m * e.ldg + n);
-            if (e.rowmask) rm[u] = e.rowmask[m];
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int r = (i0 + u) * RPI + lr, m = row_base + r;
-          if (m >= g.M) continue;
-          const float4 a4 = *reinterpret_cast<const float4*>(stg + r * LDS + lc);
-          float o[4] = {a4.x * e.alpha + bias4.x, a4.y * e.alpha + bias4.y, a4.z * e.alpha + bias4.z, a4.w * e.alpha + bias4.w};
-          if (e.act == MT_ACT_RELU) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) o[k] = fmaxf(o[k], 0.f);
-          } else if (e.act == MT_ACT_TANH) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) o[k] = tanhf(o[k]);
-          }
-          if (edrop.thresh != 0u) {
-            float f[4];        // N % 4 == 0 and n % 4 == 0: idx is a multiple of 4
-            mt_drop_quad(edrop, (uint64_t)m * (uint64_t)g.N + (uint64_t)n, f);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) o[k] *= f[k];
-          }
-          if (e.gate) {
-            o[0] = gt[u].x > 0.f ? o[0] * e.gate_scale : 0.f; o[1] = gt[u].y > 0.f ? o[1] * e.gate_scale : 0.f;
-            o[2] = gt[u].z > 0.f ? o[2] * e.gate_scale : 0.f; o[3] = gt[u].w > 0.f ? o[3] * e.gate_scale : 0.f;
-          }
-          o[0] = (o[0] + res[u].x) * rm[u]; o[1] = (o[1] + res[u].y) * rm[u];
-          o[2] = (o[2] + res[u].z) * rm[u]; o[3] = (o[3] + res[u].w) * rm[u];
-          if (g.c_f32) st4(reinterpret_cast<float*>(g.C) + (size_t)m * g.ldc + n, make_float4(o[0], o[1], o[2], o[3]));
-          else st4(reinterpret_cast<bf16*>(g.C) + (size_t)m * g.ldc + n, make_float4(o[0], o[1], o[2], o[3]));
-          cs[0] += o[0]; cs[1] += o[1]; cs[2] += o[2]; cs[3] += o[3];
+      for (int k = 0; k < 8; ++k) bias8[k] = 0.f;
+      if (f_bias) {
+        const float4 b0 = *reinterpret_cast<const float4*>(e.bias + n);
+        bias8[0] = b0.x; bias8[1] = b0.y; bias8[2] = b0.z; bias8[3] = b0.w;
+        if (hi_ok) {
+          const float4 b1 = *reinterpret_cast<const float4*>(e.bias + n + 4);
+          bias8[4] = b1.x; bias8[5] = b1.y; bias8[6] = b1.z; bias8[7] = b1.w;
         }
       }
-      if (e.colsum) {        // lanes lc, lc + LPR, ... hold the same columns (and took the same `continue` decisions above)
+      // issue every global load of this tile first (residual / gate / row mask of the lane's ITERS rows) ...
+      float4 res[ITERS][2];
+      uint4 gt[ITERS];
+      float rm[ITERS];
+#pragma unroll
+      for (int i = 0; i < ITERS; ++i) {
+        const int m = row_base + i * RPI + lr;
+        res[i][0] = res[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        gt[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);      // bf16 ones: gate open
+        rm[i] = 1.f;
+        if (!(F & F_EDGE) || m < g.M) {
+          if (f_res) {
+            res[i][0] = *reinterpret_cast<const float4*>(e.residual + (size_t)m * e.ldr + n);
+            if (hi_ok) res[i][1] = *reinterpret_cast<const float4*>(e.residual + (size_t)m * e.ldr + n + 4);
+          }
+          if (f_gate) {
+            const bf16* gp = reinterpret_cast<const bf16*>(e.gate) + (size_t)m * e.ldg + n;
+            if (hi_ok && (e.ldg & 7) == 0) gt[i] = *reinterpret_cast<const uint4*>(gp);
+            else {
+              const uint2 g0 = *reinterpret_cast<const uint2*>(gp);
+              gt[i].x = g0.x; gt[i].y = g0.y;
+              if (hi_ok) { const uint2 g1 = *reinterpret_cast<const uint2*>(gp + 4); gt[i].z = g1.x; gt[i].w = g1.y; }
+            }
+          }
+          if (f_rm) rm[i] = e.rowmask[m];
+        }
+      }
+      float cs[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cs[k] = 0.f;
+      // ... then stream the rows: 8 columns per lane, 16-byte (bf16) / 2 x 16-byte (fp32) stores
+#pragma unroll
+      for (int i = 0; i < ITERS; ++i) {
+        const int r = i * RPI + lr, m = row_base + r;
+        if ((F & F_EDGE) && m >= g.M) continue;
+        const float4 a0 = *reinterpret_cast<const float4*>(stg + r * LDS + lc), a1 = *reinterpret_cast<const float4*>(stg + r * LDS + lc + 4);
+        float o[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        if (f_alpha) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] *= e.alpha;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] += bias8[k];
+        if (f_relu) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = fmaxf(o[k], 0.f);
+        } else if (f_tanh) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = tanhf(o[k]);
+        }
+        if (f_drop) {            // N % 4 == 0 and n % 4 == 0: the element index is a multiple of 4
+          float f[8];
+          const uint64_t idx = (uint64_t)m * (uint64_t)g.N + (uint64_t)n;
+          mt_drop_quad(edrop, idx, f);
+          mt_drop_quad(edrop, idx + 4, f + 4);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] *= f[k];
+        }
+        if (f_gate) {
+          const uint32_t gw[4] = {gt[i].x, gt[i].y, gt[i].z, gt[i].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 g2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[k]));
+            o[2 * k] = g2.x > 0.f ? o[2 * k] * e.gate_scale : 0.f;
+            o[2 * k + 1] = g2.y > 0.f ? o[2 * k + 1] * e.gate_scale : 0.f;
+          }
+        }
+        if (f_res) {
+          o[0] += res[i][0].x; o[1] += res[i][0].y; o[2] += res[i][0].z; o[3] += res[i][0].w;
+          o[4] += res[i][1].x; o[5] += res[i][1].y; o[6] += res[i][1].z; o[7] += res[i][1].w;
+        }
+        if (f_rm) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] *= rm[i];
+        }
+        if (f_cf32) {
+          float* cp = reinterpret_cast<float*>(g.C) + (size_t)m * g.ldc + n;
+          st4(cp, make_float4(o[0], o[1], o[2], o[3]));
+          if (hi_ok) st4(cp + 4, make_float4(o[4], o[5], o[6], o[7]));
+        } else {
+          bf16* cp = reinterpret_cast<bf16*>(g.C) + (size_t)m * g.ldc + n;
+          if (hi_ok && (g.ldc & 7) == 0) {
+            uint4 pk;
+            pk.x = pack_bf2(o[0], o[1]); pk.y = pack_bf2(o[2], o[3]); pk.z = pack_bf2(o[4], o[5]); pk.w = pack_bf2(o[6], o[7]);
+            *reinterpret_cast<uint4*>(cp) = pk;
+          } else {
+            st4(cp, make_float4(o[0], o[1], o[2], o[3]));
+            if (hi_ok) st4(cp + 4, make_float4(o[4], o[5], o[6], o[7]));
+          }
+        }
+        if (f_colsum) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) cs[k] += o[k];
+        }
+      }
+      if (f_colsum) {        // lanes lc, lc + LPR, ... hold the same columns (and took the same `continue` decisions above)
         const unsigned am = __activemask();
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < 8; ++k) {
 #pragma unroll
           for (int o = LPR; o < 32; o <<= 1) cs[k] += __shfl_xor_sync(am, cs[k], o);
         }
         if (lr == 0) {       // shared-memory accumulation across this CTA's tiles and warps; one global atomic per column at exit
 #pragma unroll
-          for (int k = 0; k < 4; ++k) atomicAdd(cs_smem + n + k, cs[k]);
+          for (int k = 0; k < 8; ++k)
+            if (k < 4 || hi_ok) atomicAdd(cs_smem + n + k, cs[k]);
         }
       }
     }
@@ -388,6 +475,37 @@ int num_sms() {
   return n;
 }
 
+template <int BN, uint32_t F>
+int launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& g, int grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    MT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL));
+    attr_set = true;
+  }
+  gemm_tc_kernel<BN, F><<<grid, Smem<BN>::THREADS, Smem<BN>::TOTAL, st>>>(ma, mb, g);
+  MT_LAUNCH_CHECK();
+  return MT_OK;
+}
+
+// the feature set a descriptor needs
+template <int BN>
+uint32_t needed_features(const GemmDesc& d, const TcArgs& g) {
+  uint32_t f = 0;
+  if (g.atomic) f |= F_ATOMIC;
+  if (d.epi.bias) f |= F_BIAS;
+  if (d.epi.act == MT_ACT_RELU) f |= F_RELU;
+  if (d.epi.act == MT_ACT_TANH) f |= F_TANH;
+  if (d.epi.drop.thresh != 0u) f |= F_DROP;
+  if (d.epi.gate) f |= F_GATE;
+  if (d.epi.residual) f |= F_RES;
+  if (d.epi.rowmask) f |= F_ROWMASK;
+  if (d.c_f32) f |= F_CF32;
+  if (d.epi.colsum) f |= F_COLSUM;
+  if (d.epi.alpha != 1.0f) f |= F_ALPHA;
+  if (d.M % BM != 0 || d.N % BN != 0 || d.ldc % 8 != 0 || (d.epi.gate && d.epi.ldg % 8 != 0)) f |= F_EDGE;
+  return f;
+}
+
 template <int BN>
 int launch_tc(const GemmDesc& d, cudaStream_t st) {
   TcArgs g;
@@ -412,16 +530,25 @@ int launch_tc(const GemmDesc& d, cudaStream_t st) {
   CUtensorMap ma, mb;
   MT_TRY(make_map(&ma, d.A, d.M, d.K, d.lda, d.a_kmajor, BM));
   MT_TRY(make_map(&mb, d.B, d.N, d.K, d.ldb, d.b_kmajor, BN));
-  static bool attr_set = false;
-  if (!attr_set) {
-    MT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL));
-    attr_set = true;
-  }
   const int n_work = g.tiles_m * g.tiles_n * g.splits;
   const int grid = n_work < num_sms() ? n_work : num_sms();
-  gemm_tc_kernel<BN><<<grid, Smem<BN>::THREADS, Smem<BN>::TOTAL, st>>>(ma, mb, g);
-  MT_LAUNCH_CHECK();
-  return MT_OK;
+  const uint32_t f = needed_features<BN>(d, g);
+  if (BN == 128) {
+    // instantiations of the encoder / MFN hot path (see mt_encoder.cu): exact feature-set matches only
+    switch (f) {
+      case F_BIAS: return launch_inst<128, F_BIAS>(ma, mb, g, grid, st);                                        // QKV projection
+      case F_BIAS | F_DROP | F_RES | F_CF32: return launch_inst<128, F_BIAS | F_DROP | F_RES | F_CF32>(ma, mb, g, grid, st);   // out-proj / FFN2, train
+      case F_BIAS | F_RES | F_CF32: return launch_inst<128, F_BIAS | F_RES | F_CF32>(ma, mb, g, grid, st);      // out-proj / FFN2, eval
+      case F_BIAS | F_RELU | F_DROP: return launch_inst<128, F_BIAS | F_RELU | F_DROP>(ma, mb, g, grid, st);    // FFN1, train
+      case F_BIAS | F_RELU: return launch_inst<128, F_BIAS | F_RELU>(ma, mb, g, grid, st);                      // FFN1, eval
+      case 0u: return launch_inst<128, 0u>(ma, mb, g, grid, st);                                                // dgrads
+      case F_GATE | F_COLSUM: return launch_inst<128, F_GATE | F_COLSUM>(ma, mb, g, grid, st);                  // dgrad through relu + dropout
+      case F_ATOMIC | F_CF32: return launch_inst<128, F_ATOMIC | F_CF32>(ma, mb, g, grid, st);                  // wgrads (full tiles)
+      case F_ATOMIC | F_CF32 | F_EDGE: return launch_inst<128, F_ATOMIC | F_CF32 | F_EDGE>(ma, mb, g, grid, st);   // wgrads (ragged tiles)
+      default: break;
+    }
+  }
+  return launch_inst<BN, F_GENERIC>(ma, mb, g, grid, st);
 }
 
 }  // namespace
