@@ -3,16 +3,21 @@
 //   C[m,n] = epilogue( sum_k A(m,k) B(n,k) )      A, B each K-major or MN-major (see mt_gemm.cuh)
 //
 // Persistent, warp-specialised kernel, one CTA per SM:
-//   warp 0  : TMA producer   -- cp.async.bulk.tensor 2-D boxes (128-byte swizzle) into a 4-stage shared-memory ring
+//   warp 0  : TMA producer   -- cp.async.bulk.tensor 2-D boxes (128-byte swizzle) into a shared-memory ring
 //   warp 1  : MMA issuer     -- one elected lane issues tcgen05.mma (M=128, N=BN, K=16) from shared-memory
 //                               descriptors; tcgen05.commit releases ring slots and publishes accumulators
 //   warps 2-9: epilogue      -- each owns a TMEM lane quarter x a column half: tcgen05.ld the fp32 accumulator
 //                               (double-buffered in TMEM so the next tile's MMAs overlap this tile's epilogue),
-//                               release it, transpose through shared memory, then stream rows: the residual /
-//                               gate loads of four row groups are issued back to back before any is consumed, and
-//                               bias / activation / dropout / gate / residual / row-mask are applied on fully
-//                               coalesced 128-256-byte row segments (fp32 atomics for split-K wgrad work items).
-// Work items are (tile_m, tile_n, k_split) triples enumerated identically by all three roles.
+//                               release it, transpose 32-column passes through shared memory, then stream rows: the
+//                               residual / gate loads of a pass are issued before any is consumed, and bias /
+//                               activation / dropout / gate / residual / row-mask are applied on fully coalesced
+//                               row segments, 8 columns per lane (vector fp32 reductions for split-K wgrad work items).
+// Two ring modes:
+//   streaming      : every k-block brings an A box and a B box (5 stages of 32 KB) -- long K, split-K wgrads.
+//   weight-resident: K <= 256 (every projection of the encoder forward and most dgrads): the CTA is pinned to ONE column
+//                    slice of the output, loads that slice of the weight matrix (<= 64 KB) once, keeps it in shared memory
+//                    for all its row tiles, and the ring (6 stages of 16 KB) carries activations only.  This halves
+//                    the L2 -> SM traffic of these HBM-bound GEMMs and doubles the look-ahead of the ring.
 // Out-of-bounds rows / columns / k are zero-filled by TMA and predicated in the epilogue.
 #include <cuda.h>
 
@@ -22,10 +27,9 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;                 // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int STAGES = 4;
-// epilogue warps per CTA: 4 per TMEM lane quarter for the 128-wide tile (the epilogue is issue-bound; more warps hide its
-// latencies), 2 per quarter for the 64-wide one; plus the TMA warp and the MMA warp
-template <int BN> struct EpiWarps { static constexpr int value = BN >= 128 ? 16 : 8; };
+constexpr int EW = 8;                  // epilogue warps: 4 TMEM lane quarters x 2 column halves
+constexpr int KB_RES = 4;              // weight-resident mode: at most this many k-blocks (K <= 256)
+constexpr int MAX_STAGES = 8;
 constexpr uint32_t SPIN_LIMIT = 1u << 27;
 
 struct TcArgs {
@@ -35,6 +39,7 @@ struct TcArgs {
   void* C; int ldc; int c_f32; int atomic;
   GemmEpi epi;
   int gate_bf16;
+  unsigned long long* trace;           // debug: per-tile clock64 stamps of CTA 0 (mt_gemm_debug_trace), else null
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------
@@ -116,13 +121,15 @@ template <int BN>
 struct Smem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EW = EpiWarps<BN>::value;
+  static constexpr int RING_BYTES = (BN > 128 ? 176 : 160) * 1024;                      // resident weights + ring, or ring only
+  static constexpr int NS_STREAM = RING_BYTES / (A_BYTES + B_BYTES);                    // 6 (BN = 64) / 5 (128) / 3 (256)
+  static constexpr int NS_RES = (RING_BYTES - KB_RES * B_BYTES) / A_BYTES;              // 8 / 6 / 3
   static constexpr int THREADS = 64 + 32 * EW;
-  static constexpr int EPI_BYTES = EW * 32 * (BN / (EW / 4) + 4) * 4;      // per epilogue warp: 32 rows x (its columns + 4) floats
+  static constexpr int EPI_BYTES = EW * 32 * (32 + 4) * 4;                              // per epilogue warp: 32 rows x (32 + 4) floats
   static constexpr int BAR_BYTES = 256;
-  static constexpr int CS_COLS = 1024;                                      // epi.colsum: per-CTA column accumulators (N <= CS_COLS)
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + CS_COLS * 4 + 1024 /* alignment slack */;
+  static constexpr int CS_COLS = 1024;                                                  // epi.colsum: per-CTA column accumulators (N <= CS_COLS)
+  static constexpr int TOTAL = RING_BYTES + EPI_BYTES + BAR_BYTES + CS_COLS * 4 + 1024 /* alignment slack */;
+  static_assert(NS_STREAM <= MAX_STAGES && NS_RES <= MAX_STAGES, "barrier arrays");
 };
 
 // Epilogue feature bits.  The hot shapes of the encoder / MFN path get their own instantiation (every test below folds at
@@ -138,32 +145,54 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int BN, uint32_t F>
+// work item i of this CTA -> (m tile, n tile, split); false when the CTA is done.  Enumerated identically by all roles.
+template <bool RES>
+__device__ __forceinline__ bool get_work(const TcArgs& g, int i, int& tm, int& tn, int& split) {
+  if (RES) {                     // pinned to column slice blockIdx.x % tiles_n; row tiles dealt among the CTAs of that slice
+    tn = (int)blockIdx.x % g.tiles_n;
+    const int rank = (int)blockIdx.x / g.tiles_n, cnt = ((int)gridDim.x - tn + g.tiles_n - 1) / g.tiles_n;
+    tm = rank + i * cnt;
+    split = 0;
+    return tm < g.tiles_m;
+  }
+  const int tiles = g.tiles_m * g.tiles_n;
+  const int w = (int)blockIdx.x + i * (int)gridDim.x;
+  if (w >= tiles * g.splits) return false;
+  const int tile = w % tiles;
+  split = w / tiles;
+  tm = tile / g.tiles_n; tn = tile % g.tiles_n;
+  return true;
+}
+
+template <int BN, uint32_t F, bool RES>
 __global__ void __launch_bounds__(Smem<BN>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ TcArgs g) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // 1 KB aligned, still a shared-space pointer
   using S = Smem<BN>;
-  uint8_t* stage_base = smem;
-  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES + S::EPI_BYTES);
-  uint64_t* full = bars;                  // [STAGES]  TMA -> MMA
-  uint64_t* empty = bars + STAGES;        // [STAGES]  MMA -> TMA
-  uint64_t* acc_full = bars + 2 * STAGES; // [2]       MMA -> epilogue
-  uint64_t* acc_empty = acc_full + 2;     // [2]       epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* cs_smem = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + S::EPI_BYTES + S::BAR_BYTES);
-  if (g.epi.colsum) for (int i = threadIdx.x; i < g.N; i += blockDim.x) cs_smem[i] = 0.f;
+  constexpr int NS = RES ? S::NS_RES : S::NS_STREAM;
+  constexpr int SLOT = RES ? S::A_BYTES : S::A_BYTES + S::B_BYTES;
+  uint8_t* res_b = smem;                                            // RES: resident weight slice, KB_RES boxes
+  uint8_t* ring = RES ? smem + KB_RES * S::B_BYTES : smem;
+  float* epi_stage = reinterpret_cast<float*>(smem + S::RING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::RING_BYTES + S::EPI_BYTES);
+  uint64_t* full = bars;                         // [MAX_STAGES]  TMA -> MMA
+  uint64_t* empty = bars + MAX_STAGES;           // [MAX_STAGES]  MMA -> TMA
+  uint64_t* acc_full = bars + 2 * MAX_STAGES;    // [2]           MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;            // [2]           epilogue -> MMA
+  uint64_t* b_full = acc_empty + 2;              // [1]           resident weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+  float* cs_smem = reinterpret_cast<float*>(smem + S::RING_BYTES + S::EPI_BYTES + S::BAR_BYTES);
+  if (HAS(F_COLSUM, g.epi.colsum != nullptr)) for (int i = threadIdx.x; i < g.N; i += blockDim.x) cs_smem[i] = 0.f;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_work = g.tiles_m * g.tiles_n * g.splits;
-  const int tiles = g.tiles_m * g.tiles_n;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], S::EW); }
+    for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EW); }
+    mbar_init(b_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -178,70 +207,106 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
+      const int a_mn = g.a_mn, b_mn = g.b_mn, kb_per = g.kb_per, kb_total = g.kb_total;
+      const bool tracing = g.trace != nullptr && blockIdx.x == 0;
+      int tm, tn, split;
+      if (RES && get_work<RES>(g, 0, tm, tn, split)) {          // the weight slice of this CTA's column tile, once
+        mbar_expect_tx(b_full, (uint32_t)(kb_total * S::B_BYTES));
+        for (int kb = 0; kb < kb_total; ++kb) {
+          uint8_t* sb = res_b + kb * S::B_BYTES;
+          if (b_mn) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), &map_b, tn * BN + 64 * j, kb * BK, b_full);
+          } else {
+            tma_load_2d(sb, &map_b, kb * BK, tn * BN, b_full);
+          }
+        }
+      }
       int stage = 0; uint32_t phase = 0;
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const int tile = w % tiles, split = w / tiles;
-        const int m0 = (tile / g.tiles_n) * BM, n0 = (tile % g.tiles_n) * BN;
-        const int kb0 = split * g.kb_per, kb1 = min(g.kb_total, kb0 + g.kb_per);
+      for (int i = 0; get_work<RES>(g, i, tm, tn, split); ++i) {
+        const int m0 = tm * BM, n0 = tn * BN;
+        const int kb0 = split * kb_per, kb1 = min(kb_total, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* sa = stage_base + stage * S::STAGE_BYTES;
-          uint8_t* sb = sa + S::A_BYTES;
-          mbar_expect_tx(&full[stage], S::STAGE_BYTES);
+          if (tracing && kb == kb0 && i < 64) g.trace[i * 8 + 0] = clock64();
+          if (tracing && i < 16 && kb - kb0 < 4) g.trace[512 + (i * 4 + kb - kb0) * 2] = clock64();
+          uint8_t* sa = ring + stage * SLOT;
+          mbar_expect_tx(&full[stage], SLOT);
           const int k0 = kb * BK;
-          if (g.a_mn) {
+          if (a_mn) {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &map_a, m0 + 64 * j, k0, &full[stage]);
           } else {
             tma_load_2d(sa, &map_a, k0, m0, &full[stage]);
           }
-          if (g.b_mn) {
+          if (!RES) {
+            uint8_t* sb = sa + S::A_BYTES;
+            if (b_mn) {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), &map_b, n0 + 64 * j, k0, &full[stage]);
-          } else {
-            tma_load_2d(sb, &map_b, k0, n0, &full[stage]);
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), &map_b, n0 + 64 * j, k0, &full[stage]);
+            } else {
+              tma_load_2d(sb, &map_b, k0, n0, &full[stage]);
+            }
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NS) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
+    // ONE thread issues everything, so every instruction here is exposed latency: all loop-invariant descriptor fields are
+    // built once (a shared-memory descriptor only differs in its 14-bit start-address field), the per-k advance is one add
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)g.a_mn << 15) | ((uint32_t)g.b_mn << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t a_mn = (uint32_t)g.a_mn, b_mn = (uint32_t)g.b_mn;
+      const int kb_per = g.kb_per, kb_total = g.kb_total;
+      const bool tracing = g.trace != nullptr && blockIdx.x == 0;
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (a_mn << 15) | (b_mn << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      // descriptor = [start addr >> 4 : 14][LBO >> 4 : 14 @16] | hi: [SBO >> 4 : 14][version 1 @14][SWIZZLE_128B = 2 @29]
+      const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t a_lbo = (a_mn ? (uint32_t)((BK * 128) >> 4) : 1u) << 16, b_lbo = (b_mn ? (uint32_t)((BK * 128) >> 4) : 1u) << 16;
+      const uint32_t a_kstep = a_mn ? (uint32_t)((16 * 128) >> 4) : 2u, b_kstep = b_mn ? (uint32_t)((16 * 128) >> 4) : 2u;   // 16 k-elements, in 16-byte units
+      const uint32_t ring_u32 = smem_u32(ring), resb_u32 = smem_u32(res_b);
       int stage = 0; uint32_t phase = 0;
-      int it = 0;
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-        const int split = w / tiles;
-        const int kb0 = split * g.kb_per, kb1 = min(g.kb_total, kb0 + g.kb_per);
+      int tm, tn, split;
+      if (RES && get_work<RES>(g, 0, tm, tn, split)) { mbar_wait(b_full, 0); tc_fence_after(); }
+      for (int it = 0; get_work<RES>(g, it, tm, tn, split); ++it) {
+        const int kb0 = split * kb_per, kb1 = min(kb_total, kb0 + kb_per);
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1;
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        if (tracing && it < 64) g.trace[it * 8 + 1] = clock64();
+        uint32_t accum = 0u;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(stage_base + stage * S::STAGE_BYTES);
-          const uint32_t sb = sa + S::A_BYTES;
+          if (tracing && it < 64 && kb == kb0) g.trace[it * 8 + 2] = clock64();
+          if (tracing && it < 64 && kb == kb1 - 1) g.trace[it * 8 + 3] = clock64();
+          if (tracing && it < 16 && kb - kb0 < 4) g.trace[512 + (it * 4 + kb - kb0) * 2 + 1] = clock64();
+          const uint32_t sa = ring_u32 + (uint32_t)(stage * SLOT);
+          const uint32_t sb = RES ? resb_u32 + (uint32_t)(kb * S::B_BYTES) : sa + (uint32_t)S::A_BYTES;
+          const uint32_t a_lo = a_lbo | ((sa >> 4) & 0x3FFFu), b_lo = b_lbo | ((sb >> 4) & 0x3FFFu);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t ad = g.a_mn ? make_desc(sa + k * 16 * 128, BK * 128, 1024) : make_desc(sa + k * 32, 16, 1024);
-            const uint64_t bd = g.b_mn ? make_desc(sb + k * 16 * 128, BK * 128, 1024) : make_desc(sb + k * 32, 16, 1024);
-            tc_mma(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + (uint32_t)k * a_kstep);
+            const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + (uint32_t)k * b_kstep);
+            tc_mma(tmem_d, ad, bd, idesc, accum);
+            accum = 1u;
           }
           tc_commit(&empty[stage]);                 // ring slot is free once these MMAs have read it
           if (kb == kb1 - 1) tc_commit(&acc_full[acc]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (tracing && it < 16 && kb - kb0 < 4) g.trace[640 + it * 4 + kb - kb0] = clock64();
+          if (++stage == NS) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else {
-    // ===== epilogue warps: warp w owns TMEM lane quarter (w % 4) and column slice (w - 2) / 4 of every tile =====
-    constexpr int HN = BN / (S::EW / 4);       // columns per epilogue warp
-    constexpr int LDS = HN + 4;                // staged row stride in floats (16-byte aligned, conflict-free both ways)
-    constexpr int LPR = HN / 8;                // lanes per output row: each lane owns 8 consecutive columns
+    // ===== epilogue warps: warp w owns TMEM lane quarter (w % 4) and column half (w - 2) / 4 of every tile =====
+    constexpr int HN = BN / 2;                 // columns per epilogue warp
+    constexpr int NP = HN / 32;                // 32-column passes through the staging buffer
+    constexpr int LDS = 32 + 4;                // staged row stride in floats (16-byte aligned, conflict-free both ways)
+    constexpr int LPR = 4;                     // lanes per output row: each lane owns 8 consecutive columns
     constexpr int RPI = 32 / LPR;              // rows covered by one warp-wide access
     constexpr int ITERS = 32 / RPI;
     const int q = warp & 3, half = (warp - 2) >> 2;
@@ -254,172 +319,176 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     DropCfg edrop = mt_drop_resolve(e.drop);
     const bool f_drop = HAS(F_DROP, edrop.thresh != 0u);
     const int lr = lane / LPR, lc = (lane % LPR) * 8;
-    int it = 0;
-    for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-      const int tile = w % tiles;
-      const int m0 = (tile / g.tiles_n) * BM, n0 = (tile % g.tiles_n) * BN + half * HN;
+    int tm, tn, split;
+    for (int it = 0; get_work<RES>(g, it, tm, tn, split); ++it) {
+      const int m0 = tm * BM;
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1;
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
+      const bool tr = g.trace && blockIdx.x == 0 && it < 64 && warp == 2 && lane == 0;
+      if (tr) g.trace[it * 8 + 4] = clock64();
       const int row_base = m0 + q * 32;
-      __syncwarp();                             // previous tile's reads of `stg` are complete
-#pragma unroll
-      for (int c0 = 0; c0 < HN; c0 += 32) {
+#pragma unroll 1
+      for (int p = 0; p < NP; ++p) {
         uint32_t v[32];
-        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * HN + c0), v);
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * HN + p * 32), v);
+        if (p == NP - 1) {      // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[acc]);
+          if (tr) g.trace[it * 8 + 5] = clock64();
+        }
+        __syncwarp();                             // previous pass's reads of `stg` are complete
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(stg + lane * LDS + c0 + j * 4) =
-              make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-      }
-      // all TMEM reads of this accumulator are done: hand it back to the MMA warp before touching global memory
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);
-      const int n = n0 + lc;
-      bool hi_ok = true;                        // columns n + 4 .. n + 7 exist (N % 4 == 0, so a quad is all-or-nothing)
-      if (F & F_EDGE) {
-        if (n >= g.N || row_base >= g.M) continue;
-        hi_ok = n + 4 < g.N;
-      }
-      if (f_atomic) {                           // split-K partial sums: vector reductions into the zero-initialised fp32 C
+          *reinterpret_cast<float4*>(stg + lane * LDS + j * 4) = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                             __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        __syncwarp();
+        const int n = tn * BN + half * HN + p * 32 + lc;
+        bool hi_ok = true;                        // columns n + 4 .. n + 7 exist (N % 4 == 0, so a quad is all-or-nothing)
+        if (F & F_EDGE) {
+          if (n >= g.N || row_base >= g.M) continue;
+          hi_ok = n + 4 < g.N;
+        }
+        if (f_atomic) {                           // split-K partial sums: vector reductions into the zero-initialised fp32 C
+#pragma unroll
+          for (int i = 0; i < ITERS; ++i) {
+            const int r = i * RPI + lr, m = row_base + r;
+            if ((F & F_EDGE) && m >= g.M) continue;
+            float4 a0 = *reinterpret_cast<const float4*>(stg + r * LDS + lc), a1 = *reinterpret_cast<const float4*>(stg + r * LDS + lc + 4);
+            if (f_alpha) { a0.x *= e.alpha; a0.y *= e.alpha; a0.z *= e.alpha; a0.w *= e.alpha; a1.x *= e.alpha; a1.y *= e.alpha; a1.z *= e.alpha; a1.w *= e.alpha; }
+            float* cp = reinterpret_cast<float*>(g.C) + (size_t)m * g.ldc + n;
+            red_add_v4(cp, a0.x, a0.y, a0.z, a0.w);
+            if (hi_ok) red_add_v4(cp + 4, a1.x, a1.y, a1.z, a1.w);
+          }
+          continue;
+        }
+        float bias8[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bias8[k] = 0.f;
+        if (f_bias) {
+          const float4 b0 = *reinterpret_cast<const float4*>(e.bias + n);
+          bias8[0] = b0.x; bias8[1] = b0.y; bias8[2] = b0.z; bias8[3] = b0.w;
+          if (hi_ok) {
+            const float4 b1 = *reinterpret_cast<const float4*>(e.bias + n + 4);
+            bias8[4] = b1.x; bias8[5] = b1.y; bias8[6] = b1.z; bias8[7] = b1.w;
+          }
+        }
+        // issue every global load of this pass first (residual / gate / row mask of the lane's ITERS rows) ...
+        float4 res[ITERS][2];
+        uint4 gt[ITERS];
+        float rm[ITERS];
+#pragma unroll
+        for (int i = 0; i < ITERS; ++i) {
+          const int m = row_base + i * RPI + lr;
+          res[i][0] = res[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          gt[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);      // bf16 ones: gate open
+          rm[i] = 1.f;
+          if (!(F & F_EDGE) || m < g.M) {
+            if (f_res) {
+              res[i][0] = *reinterpret_cast<const float4*>(e.residual + (size_t)m * e.ldr + n);
+              if (hi_ok) res[i][1] = *reinterpret_cast<const float4*>(e.residual + (size_t)m * e.ldr + n + 4);
+            }
+            if (f_gate) {
+              const bf16* gp = reinterpret_cast<const bf16*>(e.gate) + (size_t)m * e.ldg + n;
+              if (hi_ok && (e.ldg & 7) == 0) gt[i] = *reinterpret_cast<const uint4*>(gp);
+              else {
+                const uint2 g0 = *reinterpret_cast<const uint2*>(gp);
+                gt[i].x = g0.x; gt[i].y = g0.y;
+                if (hi_ok) { const uint2 g1 = *reinterpret_cast<const uint2*>(gp + 4); gt[i].z = g1.x; gt[i].w = g1.y; }
+              }
+            }
+            if (f_rm) rm[i] = e.rowmask[m];
+          }
+        }
+        float cs[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cs[k] = 0.f;
+        // ... then stream the rows: 8 columns per lane, 16-byte (bf16) / 2 x 16-byte (fp32) stores
 #pragma unroll
         for (int i = 0; i < ITERS; ++i) {
           const int r = i * RPI + lr, m = row_base + r;
           if ((F & F_EDGE) && m >= g.M) continue;
-          float4 a0 = *reinterpret_cast<const float4*>(stg + r * LDS + lc), a1 = *reinterpret_cast<const float4*>(stg + r * LDS + lc + 4);
-          if (f_alpha) { a0.x *= e.alpha; a0.y *= e.alpha; a0.z *= e.alpha; a0.w *= e.alpha; a1.x *= e.alpha; a1.y *= e.alpha; a1.z *= e.alpha; a1.w *= e.alpha; }
-          float* cp = reinterpret_cast<float*>(g.C) + (size_t)m * g.ldc + n;
-          red_add_v4(cp, a0.x, a0.y, a0.z, a0.w);
-          if (hi_ok) red_add_v4(cp + 4, a1.x, a1.y, a1.z, a1.w);
-        }
-        continue;
-      }
-      float bias8[8];
+          const float4 a0 = *reinterpret_cast<const float4*>(stg + r * LDS + lc), a1 = *reinterpret_cast<const float4*>(stg + r * LDS + lc + 4);
+          float o[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+          if (f_alpha) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) bias8[k] = 0.f;
-      if (f_bias) {
-        const float4 b0 = *reinterpret_cast<const float4*>(e.bias + n);
-        bias8[0] = b0.x; bias8[1] = b0.y; bias8[2] = b0.z; bias8[3] = b0.w;
-        if (hi_ok) {
-          const float4 b1 = *reinterpret_cast<const float4*>(e.bias + n + 4);
-          bias8[4] = b1.x; bias8[5] = b1.y; bias8[6] = b1.z; bias8[7] = b1.w;
-        }
-      }
-      // issue every global load of this tile first (residual / gate / row mask of the lane's ITERS rows) ...
-      float4 res[ITERS][2];
-      uint4 gt[ITERS];
-      float rm[ITERS];
+            for (int k = 0; k < 8; ++k) o[k] *= e.alpha;
+          }
 #pragma unroll
-      for (int i = 0; i < ITERS; ++i) {
-        const int m = row_base + i * RPI + lr;
-        res[i][0] = res[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        gt[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);      // bf16 ones: gate open
-        rm[i] = 1.f;
-        if (!(F & F_EDGE) || m < g.M) {
-          if (f_res) {
-            res[i][0] = *reinterpret_cast<const float4*>(e.residual + (size_t)m * e.ldr + n);
-            if (hi_ok) res[i][1] = *reinterpret_cast<const float4*>(e.residual + (size_t)m * e.ldr + n + 4);
+          for (int k = 0; k < 8; ++k) o[k] += bias8[k];
+          if (f_relu) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = fmaxf(o[k], 0.f);
+          } else if (f_tanh) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = tanhf(o[k]);
+          }
+          if (f_drop) {            // N % 4 == 0 and n % 4 == 0: the element index is a multiple of 4
+            float f[8];
+            const uint64_t idx = (uint64_t)m * (uint64_t)g.N + (uint64_t)n;
+            mt_drop_quad(edrop, idx, f);
+            mt_drop_quad(edrop, idx + 4, f + 4);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] *= f[k];
           }
           if (f_gate) {
-            const bf16* gp = reinterpret_cast<const bf16*>(e.gate) + (size_t)m * e.ldg + n;
-            if (hi_ok && (e.ldg & 7) == 0) gt[i] = *reinterpret_cast<const uint4*>(gp);
-            else {
-              const uint2 g0 = *reinterpret_cast<const uint2*>(gp);
-              gt[i].x = g0.x; gt[i].y = g0.y;
-              if (hi_ok) { const uint2 g1 = *reinterpret_cast<const uint2*>(gp + 4); gt[i].z = g1.x; gt[i].w = g1.y; }
+            const uint32_t gw[4] = {gt[i].x, gt[i].y, gt[i].z, gt[i].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 g2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[k]));
+              o[2 * k] = g2.x > 0.f ? o[2 * k] * e.gate_scale : 0.f;
+              o[2 * k + 1] = g2.y > 0.f ? o[2 * k + 1] * e.gate_scale : 0.f;
             }
           }
-          if (f_rm) rm[i] = e.rowmask[m];
-        }
-      }
-      float cs[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) cs[k] = 0.f;
-      // ... then stream the rows: 8 columns per lane, 16-byte (bf16) / 2 x 16-byte (fp32) stores
-#pragma unroll
-      for (int i = 0; i < ITERS; ++i) {
-        const int r = i * RPI + lr, m = row_base + r;
-        if ((F & F_EDGE) && m >= g.M) continue;
-        const float4 a0 = *reinterpret_cast<const float4*>(stg + r * LDS + lc), a1 = *reinterpret_cast<const float4*>(stg + r * LDS + lc + 4);
-        float o[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        if (f_alpha) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) o[k] *= e.alpha;
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] += bias8[k];
-        if (f_relu) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) o[k] = fmaxf(o[k], 0.f);
-        } else if (f_tanh) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) o[k] = tanhf(o[k]);
-        }
-        if (f_drop) {            // N % 4 == 0 and n % 4 == 0: the element index is a multiple of 4
-          float f[8];
-          const uint64_t idx = (uint64_t)m * (uint64_t)g.N + (uint64_t)n;
-          mt_drop_quad(edrop, idx, f);
-          mt_drop_quad(edrop, idx + 4, f + 4);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) o[k] *= f[k];
-        }
-        if (f_gate) {
-          const uint32_t gw[4] = {gt[i].x, gt[i].y, gt[i].z, gt[i].w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 g2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[k]));
-            o[2 * k] = g2.x > 0.f ? o[2 * k] * e.gate_scale : 0.f;
-            o[2 * k + 1] = g2.y > 0.f ? o[2 * k + 1] * e.gate_scale : 0.f;
+          if (f_res) {
+            o[0] += res[i][0].x; o[1] += res[i][0].y; o[2] += res[i][0].z; o[3] += res[i][0].w;
+            o[4] += res[i][1].x; o[5] += res[i][1].y; o[6] += res[i][1].z; o[7] += res[i][1].w;
           }
-        }
-        if (f_res) {
-          o[0] += res[i][0].x; o[1] += res[i][0].y; o[2] += res[i][0].z; o[3] += res[i][0].w;
-          o[4] += res[i][1].x; o[5] += res[i][1].y; o[6] += res[i][1].z; o[7] += res[i][1].w;
-        }
-        if (f_rm) {
+          if (f_rm) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) o[k] *= rm[i];
-        }
-        if (f_cf32) {
-          float* cp = reinterpret_cast<float*>(g.C) + (size_t)m * g.ldc + n;
-          st4(cp, make_float4(o[0], o[1], o[2], o[3]));
-          if (hi_ok) st4(cp + 4, make_float4(o[4], o[5], o[6], o[7]));
-        } else {
-          bf16* cp = reinterpret_cast<bf16*>(g.C) + (size_t)m * g.ldc + n;
-          if (hi_ok && (g.ldc & 7) == 0) {
-            uint4 pk;
-            pk.x = pack_bf2(o[0], o[1]); pk.y = pack_bf2(o[2], o[3]); pk.z = pack_bf2(o[4], o[5]); pk.w = pack_bf2(o[6], o[7]);
-            *reinterpret_cast<uint4*>(cp) = pk;
-          } else {
+            for (int k = 0; k < 8; ++k) o[k] *= rm[i];
+          }
+          if (f_cf32) {
+            float* cp = reinterpret_cast<float*>(g.C) + (size_t)m * g.ldc + n;
             st4(cp, make_float4(o[0], o[1], o[2], o[3]));
             if (hi_ok) st4(cp + 4, make_float4(o[4], o[5], o[6], o[7]));
+          } else {
+            bf16* cp = reinterpret_cast<bf16*>(g.C) + (size_t)m * g.ldc + n;
+            if (hi_ok && (g.ldc & 7) == 0) {
+              uint4 pk;
+              pk.x = pack_bf2(o[0], o[1]); pk.y = pack_bf2(o[2], o[3]); pk.z = pack_bf2(o[4], o[5]); pk.w = pack_bf2(o[6], o[7]);
+              *reinterpret_cast<uint4*>(cp) = pk;
+            } else {
+              st4(cp, make_float4(o[0], o[1], o[2], o[3]));
+              if (hi_ok) st4(cp + 4, make_float4(o[4], o[5], o[6], o[7]));
+            }
+          }
+          if (f_colsum) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cs[k] += o[k];
           }
         }
-        if (f_colsum) {
+        if (f_colsum) {        // lanes lc, lc + LPR, ... hold the same columns (and took the same `continue` decisions above)
+          const unsigned am = __activemask();
 #pragma unroll
-          for (int k = 0; k < 8; ++k) cs[k] += o[k];
-        }
-      }
-      if (f_colsum) {        // lanes lc, lc + LPR, ... hold the same columns (and took the same `continue` decisions above)
-        const unsigned am = __activemask();
+          for (int k = 0; k < 8; ++k) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+            for (int o = LPR; o < 32; o <<= 1) cs[k] += __shfl_xor_sync(am, cs[k], o);
+          }
+          if (lr == 0) {       // shared-memory accumulation across this CTA's tiles and warps; one global atomic per column at exit
 #pragma unroll
-          for (int o = LPR; o < 32; o <<= 1) cs[k] += __shfl_xor_sync(am, cs[k], o);
-        }
-        if (lr == 0) {       // shared-memory accumulation across this CTA's tiles and warps; one global atomic per column at exit
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            if (k < 4 || hi_ok) atomicAdd(cs_smem + n + k, cs[k]);
+            for (int k = 0; k < 8; ++k)
+              if (k < 4 || hi_ok) atomicAdd(cs_smem + n + k, cs[k]);
+          }
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (g.epi.colsum) for (int i = threadIdx.x; i < g.N; i += blockDim.x) atomicAdd(g.epi.colsum + i, cs_smem[i]);
+  if (HAS(F_COLSUM, g.epi.colsum != nullptr)) for (int i = threadIdx.x; i < g.N; i += blockDim.x) atomicAdd(g.epi.colsum + i, cs_smem[i]);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
@@ -475,14 +544,16 @@ int num_sms() {
   return n;
 }
 
-template <int BN, uint32_t F>
+unsigned long long* g_trace = nullptr;
+
+template <int BN, uint32_t F, bool RES>
 int launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& g, int grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    MT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL));
+    MT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, F, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL));
     attr_set = true;
   }
-  gemm_tc_kernel<BN, F><<<grid, Smem<BN>::THREADS, Smem<BN>::TOTAL, st>>>(ma, mb, g);
+  gemm_tc_kernel<BN, F, RES><<<grid, Smem<BN>::THREADS, Smem<BN>::TOTAL, st>>>(ma, mb, g);
   MT_LAUNCH_CHECK();
   return MT_OK;
 }
@@ -527,28 +598,35 @@ int launch_tc(const GemmDesc& d, cudaStream_t st) {
   g.atomic = d.split_k > 1 ? 1 : 0;
   g.epi = d.epi;
   g.gate_bf16 = 1;
+  g.trace = g_trace;
   CUtensorMap ma, mb;
   MT_TRY(make_map(&ma, d.A, d.M, d.K, d.lda, d.a_kmajor, BM));
   MT_TRY(make_map(&mb, d.B, d.N, d.K, d.ldb, d.b_kmajor, BN));
   const int n_work = g.tiles_m * g.tiles_n * g.splits;
   const int grid = n_work < num_sms() ? n_work : num_sms();
   const uint32_t f = needed_features<BN>(d, g);
-  if (BN == 128) {
+  // weight-resident mode: short K, no split, and at least one CTA per column slice
+  const bool res = g.splits == 1 && g.kb_total <= KB_RES && grid >= g.tiles_n;
+  if constexpr (BN >= 128) {
     // instantiations of the encoder / MFN hot path (see mt_encoder.cu): exact feature-set matches only
+#define MT_INST(FEAT)                                                       \
+  case (FEAT):                                                              \
+    return res ? launch_inst<BN, (FEAT), true>(ma, mb, g, grid, st) : launch_inst<BN, (FEAT), false>(ma, mb, g, grid, st)
     switch (f) {
-      case F_BIAS: return launch_inst<128, F_BIAS>(ma, mb, g, grid, st);                                        // QKV projection
-      case F_BIAS | F_DROP | F_RES | F_CF32: return launch_inst<128, F_BIAS | F_DROP | F_RES | F_CF32>(ma, mb, g, grid, st);   // out-proj / FFN2, train
-      case F_BIAS | F_RES | F_CF32: return launch_inst<128, F_BIAS | F_RES | F_CF32>(ma, mb, g, grid, st);      // out-proj / FFN2, eval
-      case F_BIAS | F_RELU | F_DROP: return launch_inst<128, F_BIAS | F_RELU | F_DROP>(ma, mb, g, grid, st);    // FFN1, train
-      case F_BIAS | F_RELU: return launch_inst<128, F_BIAS | F_RELU>(ma, mb, g, grid, st);                      // FFN1, eval
-      case 0u: return launch_inst<128, 0u>(ma, mb, g, grid, st);                                                // dgrads
-      case F_GATE | F_COLSUM: return launch_inst<128, F_GATE | F_COLSUM>(ma, mb, g, grid, st);                  // dgrad through relu + dropout
-      case F_ATOMIC | F_CF32: return launch_inst<128, F_ATOMIC | F_CF32>(ma, mb, g, grid, st);                  // wgrads (full tiles)
-      case F_ATOMIC | F_CF32 | F_EDGE: return launch_inst<128, F_ATOMIC | F_CF32 | F_EDGE>(ma, mb, g, grid, st);   // wgrads (ragged tiles)
+      MT_INST(F_BIAS);                                   // QKV projection
+      MT_INST(F_BIAS | F_DROP | F_RES | F_CF32);         // out-proj / FFN2, train
+      MT_INST(F_BIAS | F_RES | F_CF32);                  // out-proj / FFN2, eval
+      MT_INST(F_BIAS | F_RELU | F_DROP);                 // FFN1, train
+      MT_INST(F_BIAS | F_RELU);                          // FFN1, eval
+      MT_INST(0u);                                       // dgrads
+      MT_INST(F_GATE | F_COLSUM);                        // dgrad through relu + dropout
+      case F_ATOMIC | F_CF32: return launch_inst<BN, F_ATOMIC | F_CF32, false>(ma, mb, g, grid, st);                    // wgrads (full tiles)
+      case F_ATOMIC | F_CF32 | F_EDGE: return launch_inst<BN, F_ATOMIC | F_CF32 | F_EDGE, false>(ma, mb, g, grid, st);  // wgrads (ragged tiles)
       default: break;
     }
+#undef MT_INST
   }
-  return launch_inst<BN, F_GENERIC>(ma, mb, g, grid, st);
+  return res ? launch_inst<BN, F_GENERIC, true>(ma, mb, g, grid, st) : launch_inst<BN, F_GENERIC, false>(ma, mb, g, grid, st);
 }
 
 }  // namespace
@@ -569,8 +647,14 @@ bool mt_gemm_tc_supported(const GemmDesc& d) {
   return true;
 }
 
+void mt_gemm_tc_set_trace(unsigned long long* p) { g_trace = p; }
+
 int mt_gemm_tc_run(const GemmDesc& d, cudaStream_t st) {
   if (!mt_gemm_tc_supported(d)) return MT_ERR_UNSUPPORTED;
+  // 256-wide tiles (tcgen05.mma N = 256: half as many MMA / TMA issues per output, the single issuing threads are the
+  // bottleneck of short-K GEMMs) whenever the weight-resident mode applies
+  const int kb_total = (d.K + BK - 1) / BK;
+  if (d.N >= 256 && d.split_k <= 1 && kb_total <= KB_RES) return launch_tc<256>(d, st);
   if (d.N > 64) return launch_tc<128>(d, st);
   return launch_tc<64>(d, st);
 }
