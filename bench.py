@@ -41,6 +41,8 @@ def parse():
     ap.add_argument('--cpu-sample', type=int, default=8, help='narratives per CPU-baseline step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-profile', action='store_true')
+    ap.add_argument('--gemm-mode', type=int, default=0, help='tcgen05 GEMM CTAs per SM (tuning; 0 = library default)')
+    ap.add_argument('--serial-stacks', action='store_true', help='run the modality stacks on one stream')
     return ap.parse_args()
 
 
@@ -165,6 +167,10 @@ def run_ours(args, rank, local_rank, world):
         dist.init_process_group('nccl', device_id=dev)
     L = _lib.lib()
     mtb.set_compute_dtype(args.dtype)
+    if args.gemm_mode:
+        L.mt_gemm_tc_mode(args.gemm_mode)
+    if args.serial_stacks:
+        mtb.set_parallel_stacks(False)
     B, T, N = args.batch, args.seq, args.layers
 
     torch.manual_seed(1)                                            # MFT/train.py:524; default (random) init
@@ -263,6 +269,7 @@ def run_ours(args, rank, local_rank, world):
         # the host needs ~30 us per launch; a busy-wait kernel in front lets it run ahead so that consecutive event
         # records bracket a kernel's true duration instead of the host's enqueue gap
         torch.cuda.synchronize()
+        mtb.set_parallel_stacks(False)              # the per-launch profiler times consecutive launches of ONE stream
         _lib.check(L.mt_spin(60.0, _lib.stream()))
         _lib.check(L.mt_prof_start(20000, _lib.stream()))
         for _ in range(nprof):

@@ -229,6 +229,9 @@ int mt_gemm(int dtype, int M, int N, int K, const void* A, int lda, int a_kmajor
 int mt_gemm_engine(int dtype, int M, int N, int K, int a_kmajor, int b_kmajor);
 /* test hook: route every GEMM through the FFMA engine (A/B the tensor-core engine); returns the previous setting. */
 int mt_gemm_force_simt(int on);
+/* tuning hook: 1 = one CTA per SM (weight-resident ring, 256-wide tiles), 2 = two CTAs per SM with a streaming ring (default);
+ * returns the previous mode. */
+int mt_gemm_tc_mode(int mode);
 /* debug hook: CTA 0 of every tcgen05 GEMM writes per-tile clock64 stamps (8 x uint64 per tile, first 64 tiles: TMA issue, MMA
  * tile start, first operands landed, last k-block landed, epilogue sees the accumulator, accumulator released, last pass
  * starts; then per-k-block issue / landing stamps of the first 16 tiles) into dev_buf (>= 8 KB); NULL switches it off. */

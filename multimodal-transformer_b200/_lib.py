@@ -84,6 +84,7 @@ _PROTOS = {
     'mt_gemm_engine': (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
     'mt_gemm_force_simt': (c_int, [c_int]),
     'mt_gemm_debug_trace': (c_int, [P]),
+    'mt_gemm_tc_mode': (c_int, [c_int]),
 }
 
 EXPORTS = tuple(_PROTOS)      # every symbol include/mt_b200.h declares

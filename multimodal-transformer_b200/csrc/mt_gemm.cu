@@ -9,6 +9,7 @@
 
 static int g_force_simt = 0;
 void mt_gemm_tc_set_trace(unsigned long long* p);      // mt_gemm_tc.cu
+int mt_gemm_tc_set_mode(int mode);
 
 int mt_gemm_run(int dtype, const GemmDesc& g, cudaStream_t st) {
   if (g_mt_prof_on) {
@@ -60,6 +61,7 @@ int mt_gemm_engine(int dtype, int M, int N, int K, int a_kmajor, int b_kmajor) {
 }
 
 /* debug hook: CTA 0 of every tcgen05 GEMM writes per-tile clock64 stamps (8 words per tile, 64 tiles) into `dev_buf`; NULL = off */
+int mt_gemm_tc_mode(int mode) { return mt_gemm_tc_set_mode(mode); }
 int mt_gemm_debug_trace(void* dev_buf) { mt_gemm_tc_set_trace((unsigned long long*)dev_buf); return MT_OK; }
 
 /* test hook: route every GEMM through the FFMA engine (used to A/B the tensor-core engine) */

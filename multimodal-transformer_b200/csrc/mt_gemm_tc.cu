@@ -117,13 +117,15 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
-template <int BN>
+// OCC = CTAs per SM.  OCC = 2 (two independent pipelines per SM, streaming ring of 2 stages each): the single TMA / MMA issuing
+// threads and the epilogue warps are all latency-bound, so a second resident CTA fills their bubbles.
+template <int BN, int OCC>
 struct Smem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int RING_BYTES = (BN > 128 ? 176 : 160) * 1024;                      // resident weights + ring, or ring only
+  static constexpr int RING_BYTES = OCC == 2 ? 2 * (A_BYTES + B_BYTES) : (BN > 128 ? 176 : 160) * 1024;   // resident weights + ring, or ring only
   static constexpr int NS_STREAM = RING_BYTES / (A_BYTES + B_BYTES);                    // 6 (BN = 64) / 5 (128) / 3 (256)
-  static constexpr int NS_RES = (RING_BYTES - KB_RES * B_BYTES) / A_BYTES;              // 8 / 6 / 3
+  static constexpr int NS_RES = OCC == 2 ? 1 : (RING_BYTES - KB_RES * B_BYTES) / A_BYTES;   // 8 / 6 / 3 (unused with OCC = 2)
   static constexpr int THREADS = 64 + 32 * EW;
   static constexpr int EPI_BYTES = EW * 32 * (32 + 4) * 4;                              // per epilogue warp: 32 rows x (32 + 4) floats
   static constexpr int BAR_BYTES = 256;
@@ -164,12 +166,13 @@ __device__ __forceinline__ bool get_work(const TcArgs& g, int i, int& tm, int& t
   return true;
 }
 
-template <int BN, uint32_t F, bool RES>
-__global__ void __launch_bounds__(Smem<BN>::THREADS, 1)
+template <int BN, uint32_t F, bool RES, int OCC>
+__global__ void __launch_bounds__(Smem<BN, OCC>::THREADS, OCC)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ TcArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // 1 KB aligned, still a shared-space pointer
-  using S = Smem<BN>;
+  using S = Smem<BN, OCC>;
+  static_assert(!(RES && OCC == 2), "weight-resident mode needs the whole SM");
   constexpr int NS = RES ? S::NS_RES : S::NS_STREAM;
   constexpr int SLOT = RES ? S::A_BYTES : S::A_BYTES + S::B_BYTES;
   uint8_t* res_b = smem;                                            // RES: resident weight slice, KB_RES boxes
@@ -545,15 +548,16 @@ int num_sms() {
 }
 
 unsigned long long* g_trace = nullptr;
+int g_tc_mode = 2;       // CTAs per SM of the 128-wide-tile kernel (mt_gemm_tc_set_mode)
 
-template <int BN, uint32_t F, bool RES>
+template <int BN, uint32_t F, bool RES, int OCC = 1>
 int launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& g, int grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    MT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, F, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL));
+    MT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, F, RES, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN, OCC>::TOTAL));
     attr_set = true;
   }
-  gemm_tc_kernel<BN, F, RES><<<grid, Smem<BN>::THREADS, Smem<BN>::TOTAL, st>>>(ma, mb, g);
+  gemm_tc_kernel<BN, F, RES, OCC><<<grid, Smem<BN, OCC>::THREADS, Smem<BN, OCC>::TOTAL, st>>>(ma, mb, g);
   MT_LAUNCH_CHECK();
   return MT_OK;
 }
@@ -577,7 +581,7 @@ uint32_t needed_features(const GemmDesc& d, const TcArgs& g) {
   return f;
 }
 
-template <int BN>
+template <int BN, int OCC>
 int launch_tc(const GemmDesc& d, cudaStream_t st) {
   TcArgs g;
   g.M = d.M; g.N = d.N; g.K = d.K;
@@ -586,7 +590,7 @@ int launch_tc(const GemmDesc& d, cudaStream_t st) {
   g.kb_total = (d.K + BK - 1) / BK;
   int splits = 1;
   if (d.split_k > 1) {                       // wgrad-style: few output tiles, long K -> one work item per SM
-    splits = num_sms() / (g.tiles_m * g.tiles_n);
+    splits = OCC * num_sms() / (g.tiles_m * g.tiles_n);
     if (splits < 1) splits = 1;
   }
   if (splits > g.kb_total) splits = g.kb_total;
@@ -603,15 +607,16 @@ int launch_tc(const GemmDesc& d, cudaStream_t st) {
   MT_TRY(make_map(&ma, d.A, d.M, d.K, d.lda, d.a_kmajor, BM));
   MT_TRY(make_map(&mb, d.B, d.N, d.K, d.ldb, d.b_kmajor, BN));
   const int n_work = g.tiles_m * g.tiles_n * g.splits;
-  const int grid = n_work < num_sms() ? n_work : num_sms();
+  const int grid = n_work < OCC * num_sms() ? n_work : OCC * num_sms();
   const uint32_t f = needed_features<BN>(d, g);
   // weight-resident mode: short K, no split, and at least one CTA per column slice
-  const bool res = g.splits == 1 && g.kb_total <= KB_RES && grid >= g.tiles_n;
+  const bool res = OCC == 1 && g.splits == 1 && g.kb_total <= KB_RES && grid >= g.tiles_n;
   if constexpr (BN >= 128) {
     // instantiations of the encoder / MFN hot path (see mt_encoder.cu): exact feature-set matches only
-#define MT_INST(FEAT)                                                       \
-  case (FEAT):                                                              \
-    return res ? launch_inst<BN, (FEAT), true>(ma, mb, g, grid, st) : launch_inst<BN, (FEAT), false>(ma, mb, g, grid, st)
+#define MT_INST(FEAT)                                                                       \
+  case (FEAT):                                                                              \
+    if constexpr (OCC == 2) return launch_inst<BN, (FEAT), false, 2>(ma, mb, g, grid, st);  \
+    else return res ? launch_inst<BN, (FEAT), true>(ma, mb, g, grid, st) : launch_inst<BN, (FEAT), false>(ma, mb, g, grid, st)
     switch (f) {
       MT_INST(F_BIAS);                                   // QKV projection
       MT_INST(F_BIAS | F_DROP | F_RES | F_CF32);         // out-proj / FFN2, train
@@ -620,13 +625,14 @@ int launch_tc(const GemmDesc& d, cudaStream_t st) {
       MT_INST(F_BIAS | F_RELU);                          // FFN1, eval
       MT_INST(0u);                                       // dgrads
       MT_INST(F_GATE | F_COLSUM);                        // dgrad through relu + dropout
-      case F_ATOMIC | F_CF32: return launch_inst<BN, F_ATOMIC | F_CF32, false>(ma, mb, g, grid, st);                    // wgrads (full tiles)
-      case F_ATOMIC | F_CF32 | F_EDGE: return launch_inst<BN, F_ATOMIC | F_CF32 | F_EDGE, false>(ma, mb, g, grid, st);  // wgrads (ragged tiles)
+      case F_ATOMIC | F_CF32: return launch_inst<BN, F_ATOMIC | F_CF32, false, OCC>(ma, mb, g, grid, st);                    // wgrads (full tiles)
+      case F_ATOMIC | F_CF32 | F_EDGE: return launch_inst<BN, F_ATOMIC | F_CF32 | F_EDGE, false, OCC>(ma, mb, g, grid, st);  // wgrads (ragged tiles)
       default: break;
     }
 #undef MT_INST
   }
-  return res ? launch_inst<BN, F_GENERIC, true>(ma, mb, g, grid, st) : launch_inst<BN, F_GENERIC, false>(ma, mb, g, grid, st);
+  if constexpr (OCC == 2) return launch_inst<BN, F_GENERIC, false, 2>(ma, mb, g, grid, st);
+  else return res ? launch_inst<BN, F_GENERIC, true>(ma, mb, g, grid, st) : launch_inst<BN, F_GENERIC, false>(ma, mb, g, grid, st);
 }
 
 }  // namespace
@@ -654,7 +660,14 @@ int mt_gemm_tc_run(const GemmDesc& d, cudaStream_t st) {
   // 256-wide tiles (tcgen05.mma N = 256: half as many MMA / TMA issues per output, the single issuing threads are the
   // bottleneck of short-K GEMMs) whenever the weight-resident mode applies
   const int kb_total = (d.K + BK - 1) / BK;
-  if (d.N >= 256 && d.split_k <= 1 && kb_total <= KB_RES) return launch_tc<256>(d, st);
-  if (d.N > 64) return launch_tc<128>(d, st);
-  return launch_tc<64>(d, st);
+  (void)kb_total;
+  if (g_tc_mode == 1) {                                 // one CTA per SM: weight-resident 256-wide tiles where they apply
+    if (d.N >= 256 && d.split_k <= 1 && kb_total <= KB_RES) return launch_tc<256, 1>(d, st);
+    if (d.N > 64) return launch_tc<128, 1>(d, st);
+    return launch_tc<64, 1>(d, st);
+  }
+  if (d.N > 64) return launch_tc<128, 2>(d, st);        // two CTAs per SM, streaming ring
+  return launch_tc<64, 1>(d, st);
 }
+
+int mt_gemm_tc_set_mode(int mode) { int old = g_tc_mode; g_tc_mode = mode; return old; }

@@ -12,7 +12,7 @@ import torch
 from . import _lib
 from ._lib import ACT_NONE, ACT_RELU, ACT_TANH, MT_BF16, MT_F32, check, lib, ptr, require, stream
 
-_state = {'dtype': MT_F32, 'seed': 0x5EED0000, 'counter': 0, 'fixed_seed': None}
+_state = {'dtype': MT_F32, 'seed': 0x5EED0000, 'counter': 0, 'fixed_seed': None, 'parallel_stacks': True}
 
 
 def set_compute_dtype(name):
@@ -24,6 +24,18 @@ def set_compute_dtype(name):
 
 def get_compute_dtype():
     return 'fp32' if _state['dtype'] == MT_F32 else 'bf16'
+
+
+def set_parallel_stacks(on):
+    """Run the per-modality encoder stacks of MultiTransformer on side CUDA streams (default on).  Returns the previous
+    setting.  The per-launch profiler (mt_prof_*) assumes one stream: switch this off while profiling."""
+    old = _state['parallel_stacks']
+    _state['parallel_stacks'] = bool(on)
+    return old
+
+
+def parallel_stacks():
+    return _state['parallel_stacks']
 
 
 def manual_seed(seed):

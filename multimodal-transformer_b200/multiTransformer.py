@@ -293,14 +293,34 @@ class MultiTransformer(nn.Module):
         self.device = _pick_device(device)
         self.to(self.device)
 
+    def _stack(self, mod, inputs, mask):
+        e = self.embed[mod]
+        x = K.linear(inputs[mod], e.weight, e.bias, out_f32=self.use_encoder)
+        if self.use_encoder:
+            x = self.transformer[mod](x, mask)
+        return x
+
     def forward(self, inputs, mask, lengths, tgt_init=0.5, target=None):
-        xs = []
-        for mod in self.mods:
-            e = self.embed[mod]
-            x = K.linear(inputs[mod], e.weight, e.bias, out_f32=self.use_encoder)
-            if self.use_encoder:
-                x = self.transformer[mod](x, mask)
-            xs.append(x)
+        if K.parallel_stacks() and self.use_encoder and len(self.mods) > 1 and inputs[self.mods[0]].is_cuda:
+            # the modality stacks are independent until the MFN: run them on side streams so the prologue / tail of one
+            # stack's kernels overlaps the others' (autograd replays each stack's backward on the same stream); under CUDA
+            # graph capture this becomes a fork / join in the graph
+            cur = torch.cuda.current_stream()
+            dev = inputs[self.mods[0]].device
+            if getattr(self, '_side', None) is None or self._side[0].device != dev:
+                self._side = [torch.cuda.Stream(device=dev) for _ in self.mods[1:]]
+            xs = [None] * len(self.mods)
+            for i, mod in enumerate(self.mods[1:], 1):
+                s = self._side[i - 1]
+                s.wait_stream(cur)
+                with torch.cuda.stream(s):
+                    xs[i] = self._stack(mod, inputs, mask)
+            xs[0] = self._stack(self.mods[0], inputs, mask)
+            for i, s in enumerate(self._side, 1):
+                cur.wait_stream(s)
+                xs[i].record_stream(cur)
+        else:
+            xs = [self._stack(mod, inputs, mask) for mod in self.mods]
         # [B,T,D] row order goes straight into the recurrence (the reference permutes to [T,B,D] first, :300);
         # the output mask (:310) is applied by the kernel.
         return self.mfn._run(xs, mask, t_major=False)
