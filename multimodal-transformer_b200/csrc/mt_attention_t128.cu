@@ -33,25 +33,75 @@ __device__ __forceinline__ void stage_all(bf16* s, const bf16* base, int ld, int
   }
 }
 
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  const int n = valid ? 16 : 0;                  // src-size 0: the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// asynchronous version of stage_all: rows [0, T) of a [T x DK] global operand -> smem[TMAX][DK + 8], rows >= T zero-filled
+template <int DK>
+__device__ __forceinline__ void stage_all_async(bf16* s, const bf16* base, int ld, int T) {
+  constexpr int LD = DK + 8, V = DK / 8;
+  for (int e = threadIdx.x; e < TMAX * V; e += NT) {
+    const int r = e / V, c = (e % V) * 8;
+    cp_async16(s + r * LD + c, base + (size_t)min(r, T - 1) * ld + c, r < T);
+  }
+}
+
+template <int DK>
+struct FwdSmem {
+  static constexpr int LD = DK + 8;
+  static constexpr size_t BYTES = (size_t)(2 * 3 * TMAX * LD) * sizeof(bf16);      // double-buffered Q | K | V
+};
+
+// Persistent forward: a CTA walks (narrative, head) items; the next item's Q / K / V tiles are in flight (cp.async) while the
+// current one is computed, so no global-load latency is exposed after the first item.
 template <int DK>
 __global__ void __launch_bounds__(NT, 2) attn128_fwd_kernel(int B, int T, int d, int h, const bf16* __restrict__ qkv,
                                                             const float* __restrict__ mask, bf16* __restrict__ out,
                                                             float* __restrict__ lse, DropCfg drop_in, float scale) {
   const DropCfg drop = mt_drop_resolve(drop_in);
   constexpr int LD = DK + 8;
-  __shared__ __align__(16) bf16 Ks[TMAX * LD];
-  __shared__ __align__(16) bf16 Vs[TMAX * LD];
-  const int b = blockIdx.x / h, hd = blockIdx.x % h;
+  extern __shared__ __align__(16) unsigned char fwd_smem[];
+  bf16* bufs = reinterpret_cast<bf16*>(fwd_smem);                 // [2][Q | K | V][TMAX * LD]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ld = 3 * d;
-  const bf16* qb = qkv + (size_t)b * T * ld + hd * DK;
-  stage_all<DK>(Ks, qb + d, ld, T);
-  stage_all<DK>(Vs, qb + 2 * d, ld, T);
+  const int n_items = B * h;
   const int i0 = warp * 16;
-  uint32_t qa[DK / 16][4];
-  load_a_frags<DK>(qa, qb, ld, i0, T, lane);
+  {
+    const bf16* qb = qkv + (size_t)(blockIdx.x / h) * T * ld + (blockIdx.x % h) * DK;
+    stage_all_async<DK>(bufs, qb, ld, T);
+    stage_all_async<DK>(bufs + TMAX * LD, qb + d, ld, T);
+    stage_all_async<DK>(bufs + 2 * TMAX * LD, qb + 2 * d, ld, T);
+    cp_async_commit();
+  }
+  int cur = 0;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, cur ^= 1) {
+  const int b = item / h, hd = item % h;
+  {
+    const int nxt = item + gridDim.x;
+    if (nxt < n_items) {
+      const bf16* qn = qkv + (size_t)(nxt / h) * T * ld + (nxt % h) * DK;
+      bf16* nb = bufs + (cur ^ 1) * 3 * TMAX * LD;
+      stage_all_async<DK>(nb, qn, ld, T);
+      stage_all_async<DK>(nb + TMAX * LD, qn + d, ld, T);
+      stage_all_async<DK>(nb + 2 * TMAX * LD, qn + 2 * d, ld, T);
+    }
+    cp_async_commit();
+  }
+  cp_async_wait<1>();
   __syncthreads();
-  if (i0 >= T) return;
+  const bf16* Qs = bufs + cur * 3 * TMAX * LD;
+  const bf16* Ks = Qs + TMAX * LD;
+  const bf16* Vs = Ks + TMAX * LD;
+  if (i0 < T) {
+  uint32_t qa[DK / 16][4];
+#pragma unroll
+  for (int ks = 0; ks < DK / 16; ++ks) ldsm_a(qa[ks], Qs + i0 * LD + ks * 16, LD, lane);
   const int r0 = i0 + (lane >> 2), r1 = r0 + 8, c = 2 * (lane & 3);
   // masked query rows: every score becomes the same constant, i.e. scale 0 (reference: masked_fill(-1e9) over the row)
   const float rs0 = (mask != nullptr && r0 < T && mask[(size_t)b * T + r0] == 0.f) ? 0.f : scale * LOG2E;
@@ -129,6 +179,10 @@ __global__ void __launch_bounds__(NT, 2) attn128_fwd_kernel(int B, int T, int d,
     if (r0 < T) lse[bh * T + r0] = (mx0 + log2f(l0)) * LN2;
     if (r1 < T) lse[bh * T + r1] = (mx1 + log2f(l1)) * LN2;
   }
+  }                                  // i0 < T
+  __syncthreads();                   // every warp is done with this buffer before the stage after next overwrites it
+  }                                  // items
+  cp_async_wait<0>();
 }
 
 // column sums over the 16 rows of an accumulator fragment set acc[DK/8][4] (rows lane/4 and lane/4 + 8, columns
@@ -167,24 +221,37 @@ __global__ void __launch_bounds__(NT, DK <= 32 ? 2 : 1) attn128_bwd_kernel(int B
   bf16* Gs = Vs + TMAX * LD;            // dO
   bf16* Ps = Gs + TMAX * LD;            // P . dropout      [query][key]
   bf16* Ds = Ps + TMAX * LP;            // dS               [query][key]
-  const int b = blockIdx.x / h, hd = blockIdx.x % h;
+  // Persistent: CTA c owns head c % h and walks the narratives c / h, c / h + gridDim.x / h, ... (gridDim.x % h == 0), so the
+  // bias-gradient column sums accumulate in shared memory and leave with ONE atomic per column per CTA.  Loads are
+  // staggered half a phase ahead, all on single buffers: K / V of the next item land during phase 2 (phase 1 is their only
+  // reader), Q / dO of this item land during phase 1 (phase 2 is their only shared-memory reader; phase 1 takes its own 16
+  // query rows of Q / dO / O straight from global memory as register fragments).
+  const int hd = blockIdx.x % h;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ld = 3 * d;
+  const int bstep = gridDim.x / h;
+  const int w0 = warp * 16;
+  const int r0 = w0 + (lane >> 2), r1 = r0 + 8, c = 2 * (lane & 3);
+  const int nchunk = (T + 15) >> 4;            // 16-row chunks holding at least one valid row
+  {
+    const bf16* qb = qkv + (size_t)(blockIdx.x / h) * T * ld + hd * DK;
+    if ((int)blockIdx.x / h < B) { stage_all_async<DK>(Ks, qb + d, ld, T); stage_all_async<DK>(Vs, qb + 2 * d, ld, T); }
+    cp_async_commit();
+  }
+  for (int b = blockIdx.x / h; b < B; b += bstep) {
   const bf16* qb = qkv + (size_t)b * T * ld + hd * DK;
   const bf16* gob = dout + (size_t)b * T * d + hd * DK;
   const bf16* ob = out + (size_t)b * T * d + hd * DK;
   const uint64_t bh = (uint64_t)b * h + hd;
-  stage_all<DK>(Qs, qb, ld, T);
-  stage_all<DK>(Ks, qb + d, ld, T);
-  stage_all<DK>(Vs, qb + 2 * d, ld, T);
-  stage_all<DK>(Gs, gob, d, T);
-  const int w0 = warp * 16;
-  const int r0 = w0 + (lane >> 2), r1 = r0 + 8, c = 2 * (lane & 3);
-  const int nchunk = (T + 15) >> 4;            // 16-row chunks holding at least one valid row
-  // D = rowsum(dO * O) of the two owned query rows (from global, overlaps the staging above)
+  stage_all_async<DK>(Qs, qb, ld, T);
+  stage_all_async<DK>(Gs, gob, d, T);
+  cp_async_commit();
+  // own rows of Q / dO as A fragments, and D = rowsum(dO * O) of the two owned query rows
+  uint32_t qa[DK / 16][4], ga[DK / 16][4];
   float D0 = 0.f, D1 = 0.f;
   if (w0 < T) {
-    uint32_t ga[DK / 16][4], oa[DK / 16][4];
+    uint32_t oa[DK / 16][4];
+    load_a_frags<DK>(qa, qb, ld, w0, T, lane);
     load_a_frags<DK>(ga, gob, d, w0, T, lane);
     load_a_frags<DK>(oa, ob, d, w0, T, lane);
 #pragma unroll
@@ -200,16 +267,11 @@ __global__ void __launch_bounds__(NT, DK <= 32 ? 2 : 1) attn128_bwd_kernel(int B
     D0 += __shfl_xor_sync(0xffffffffu, D0, 1); D0 += __shfl_xor_sync(0xffffffffu, D0, 2);
     D1 += __shfl_xor_sync(0xffffffffu, D1, 1); D1 += __shfl_xor_sync(0xffffffffu, D1, 2);
   }
+  cp_async_wait<1>();                          // K / V of this item have landed (Q / dO may still be in flight)
   __syncthreads();
 
   // ---------------- phase 1: this warp's 16 query rows -> P, dS (shared memory) and dQ --------------------
   if (w0 < T) {
-    uint32_t qa[DK / 16][4], ga[DK / 16][4];
-#pragma unroll
-    for (int ks = 0; ks < DK / 16; ++ks) {
-      ldsm_a(qa[ks], Qs + w0 * LD + ks * 16, LD, lane);
-      ldsm_a(ga[ks], Gs + w0 * LD + ks * 16, LD, lane);
-    }
     const bool in0 = r0 < T, in1 = r1 < T;
     const bool mk0 = mask != nullptr && in0 && mask[(size_t)b * T + r0] == 0.f;
     const bool mk1 = mask != nullptr && in1 && mask[(size_t)b * T + r1] == 0.f;
@@ -273,7 +335,14 @@ __global__ void __launch_bounds__(NT, DK <= 32 ? 2 : 1) attn128_bwd_kernel(int B
     }
     if (dbias) colsum_frag<DK>(s_cs, dq, lane);
   }
+  cp_async_wait<0>();                          // Q / dO tiles of this item
   __syncthreads();
+  if (b + bstep < B) {                         // K / V are dead until the next item's phase 1: fetch them now
+    const bf16* qn = qkv + (size_t)(b + bstep) * T * ld + hd * DK;
+    stage_all_async<DK>(Ks, qn + d, ld, T);
+    stage_all_async<DK>(Vs, qn + 2 * d, ld, T);
+  }
+  cp_async_commit();
 
   // ---------------- phase 2: this warp's 16 keys -> dV = (P.drop)^T dO, dK = dS^T Q -------------------------
   if (w0 < T) {
@@ -306,10 +375,10 @@ __global__ void __launch_bounds__(NT, DK <= 32 ? 2 : 1) attn128_bwd_kernel(int B
     }
     if (dbias) { colsum_frag<DK>(s_cs + DK, dk, lane); colsum_frag<DK>(s_cs + 2 * DK, dv, lane); }
   }
-  if (dbias) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < 3 * DK; i += NT) atomicAdd(dbias + (i / DK) * d + hd * DK + (i % DK), s_cs[i]);
-  }
+  __syncthreads();                             // Q / dO / P / dS tiles are free for the next item
+  }                                            // items
+  cp_async_wait<0>();
+  if (dbias) for (int i = threadIdx.x; i < 3 * DK; i += NT) atomicAdd(dbias + (i / DK) * d + hd * DK + (i % DK), s_cs[i]);
 }
 
 template <int DK>
@@ -320,7 +389,11 @@ int launch_bwd(int B, int T, int d, int h, const void* qkv, const float* mask, c
     MT_CUDA(cudaFuncSetAttribute(attn128_bwd_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdSmem<DK>::BYTES));
     attr = true;
   }
-  attn128_bwd_kernel<DK><<<B * h, NT, BwdSmem<DK>::BYTES, st>>>(B, T, d, h, (const bf16*)qkv, mask, (const bf16*)out, lse, (const bf16*)dout,
+  const int per_sm = DK <= 32 ? 2 : 1;
+  int grid = (per_sm * 148 / h) * h;           // a multiple of h: every CTA keeps one head
+  if (grid < h) grid = h;
+  if (grid > B * h) grid = B * h;
+  attn128_bwd_kernel<DK><<<grid, NT, BwdSmem<DK>::BYTES, st>>>(B, T, d, h, (const bf16*)qkv, mask, (const bf16*)out, lse, (const bf16*)dout,
                                                                  (bf16*)dqkv, drop, scale, dbias);
   MT_LAUNCH_CHECK();
   return MT_OK;
@@ -338,12 +411,23 @@ int mt_attn128_fwd_run(int B, int T, int d, int h, const void* qkv, const float*
   const int dk = d / h;
   const float scale = 1.0f / sqrtf((float)dk);
   mt_prof_work(4.0 * B * (double)T * T * d, (double)B * T * d * 4.0 * 2.0);
+  const int grid = B * h < 2 * 148 ? B * h : 2 * 148;
+#define MT_FWD(DK)                                                                                                                     \
+  {                                                                                                                                    \
+    static bool attr = false;                                                                                                          \
+    if (!attr) {                                                                                                                       \
+      MT_CUDA(cudaFuncSetAttribute(attn128_fwd_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdSmem<DK>::BYTES));     \
+      attr = true;                                                                                                                     \
+    }                                                                                                                                  \
+    attn128_fwd_kernel<DK><<<grid, NT, FwdSmem<DK>::BYTES, st>>>(B, T, d, h, (const bf16*)qkv, mask, (bf16*)out, lse, drop, scale);    \
+  }
   switch (dk) {
-    case 16: attn128_fwd_kernel<16><<<B * h, NT, 0, st>>>(B, T, d, h, (const bf16*)qkv, mask, (bf16*)out, lse, drop, scale); break;
-    case 32: attn128_fwd_kernel<32><<<B * h, NT, 0, st>>>(B, T, d, h, (const bf16*)qkv, mask, (bf16*)out, lse, drop, scale); break;
-    case 64: attn128_fwd_kernel<64><<<B * h, NT, 0, st>>>(B, T, d, h, (const bf16*)qkv, mask, (bf16*)out, lse, drop, scale); break;
+    case 16: MT_FWD(16) break;
+    case 32: MT_FWD(32) break;
+    case 64: MT_FWD(64) break;
     default: return MT_ERR_UNSUPPORTED;
   }
+#undef MT_FWD
   MT_LAUNCH_CHECK();
   return MT_OK;
 }
