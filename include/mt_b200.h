@@ -164,6 +164,8 @@ size_t mt_mfn_ws_bytes(const MtMfnCfg* cfg);
 int mt_mfn_fwd(const MtMfnCfg* cfg, const float* params, const void* params_lp, const void* const* x,
                const int64_t* stride_b, const int64_t* stride_t, const float* mask, float* out, float* h_last,
                float* c_last, float* mem_last, void* ws, size_t ws_bytes, void* stream);
+/* test hook: run the bf16 recurrences on the FFMA kernels instead of the tensor-core ones; returns the previous setting. */
+int mt_mfn_force_ffma(int on);
 /* dout fp32 [B,T] -> dx[m] [B,T,D_m] (dtype, contiguous), grads fp32 flat (OVERWRITTEN). */
 int mt_mfn_bwd(const MtMfnCfg* cfg, const float* params, const void* params_lp, const void* const* x,
                const int64_t* stride_b, const int64_t* stride_t, const float* mask, const float* dout, void* const* dx,

@@ -83,6 +83,7 @@ _PROTOS = {
     'mt_gemm': (c_int, [c_int, c_int, c_int, c_int, P, c_int, c_int, P, c_int, c_int, P, c_int, c_int, P, c_int, c_int, P]),
     'mt_gemm_engine': (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
     'mt_gemm_force_simt': (c_int, [c_int]),
+    'mt_mfn_force_ffma': (c_int, [c_int]),
     'mt_gemm_debug_trace': (c_int, [P]),
     'mt_gemm_tc_mode': (c_int, [c_int]),
 }

@@ -795,7 +795,12 @@ GemmDesc lin_dgrad(int M, int Nout, int Kin, const void* dy, int lda, const void
 
 }  // namespace
 
+static int g_mfn_force_ffma = 0;
+
 extern "C" {
+
+/* test hook: run the bf16 recurrences on the FFMA kernels instead of the tensor-core ones; returns the previous setting */
+int mt_mfn_force_ffma(int on) { int old = g_mfn_force_ffma; g_mfn_force_ffma = on; return old; }
 
 size_t mt_mfn_param_count(const MtMfnCfg* cfg) {
   Dims D;
@@ -892,7 +897,8 @@ int mt_mfn_fwd(const MtMfnCfg* cfg, const float* params, const void* params_lp, 
     int Hq = 0;
     for (int m = 0; m < D.n_mods; ++m) { smem = smax(smem, lstm_fwd_smem(D.H[m], wsz)); Hq += D.H[m] * D.H[m]; }
     mt_prof_work(2.0 * 4.0 * Hq * (double)M, 4.0 * M * (double)(4 * Hs * 2 + 2 * H2 + Hs));
-    MT_REC_LAUNCH(mfn_lstm_fwd_kernel, dim3(tiles, D.n_mods), smem, a);
+    if (lp && !g_mfn_force_ffma && mt_mfn_mma_lstm_supported(a)) MT_TRY(mt_mfn_mma_lstm_fwd(a, st));
+    else MT_REC_LAUNCH(mfn_lstm_fwd_kernel, dim3(tiles, D.n_mods), smem, a);
   }
   // F3: delta-memory attention block, batched over all rows
   MT_TRY(mt_gemm_run(c.dtype, lin_fwd(M, D.A1, H2, S.cstar_op, H2, W(D.att1_fc1.w), H2, S.a1_op, D.A1, !lp, params + D.att1_fc1.b, MT_ACT_RELU), st));
@@ -915,7 +921,8 @@ int mt_mfn_fwd(const MtMfnCfg* cfg, const float* params, const void* params_lp, 
     a.mem_last = mem_last;
     const size_t smem = mem_fwd_smem(D, wsz);
     mt_prof_work(2.0 * (2.0 * G * MEM + 2.0 * G * MEM) * (double)M, 4.0 * M * (double)(2 * G + MEM + 2 * MEM + MEM));
-    MT_REC_LAUNCH(mfn_mem_fwd_kernel, dim3(tiles), smem, a);
+    if (lp && !g_mfn_force_ffma && mt_mfn_mma_mem_supported(a)) MT_TRY(mt_mfn_mma_mem_fwd(a, st));
+    else MT_REC_LAUNCH(mfn_mem_fwd_kernel, dim3(tiles), smem, a);
   }
   // F5: head
   MT_TRY(mt_gemm_run(c.dtype, lin_fwd(M, D.O, Hs + MEM, S.last_op, Hs + MEM, W(D.out_fc1.w), Hs + MEM, S.pre, D.O, true, params + D.out_fc1.b, MT_ACT_RELU), st));
@@ -972,7 +979,8 @@ int mt_mfn_bwd(const MtMfnCfg* cfg, const float* params, const void* params_lp, 
     fill_mem_args(a, c, D, S, params, params_lp, sb, stt);
     const size_t smem = mem_bwd_smem(D, wsz, wsz);
     mt_prof_work(2.0 * (2.0 * G * MEM + 2.0 * G * MEM) * (double)M, 4.0 * M * (double)(6 * MEM + 2 * G) + wsz * M * (double)(4 * MEM + 4 * G));
-    MT_REC_LAUNCH(mfn_mem_bwd_kernel, dim3(tiles), smem, a);
+    if (lp && !g_mfn_force_ffma && mt_mfn_mma_mem_supported(a)) MT_TRY(mt_mfn_mma_mem_bwd(a, st));
+    else MT_REC_LAUNCH(mfn_mem_bwd_kernel, dim3(tiles), smem, a);
   }
   // B3: batched dgrads through the attention block
   {
@@ -1006,7 +1014,8 @@ int mt_mfn_bwd(const MtMfnCfg* cfg, const float* params, const void* params_lp, 
     int Hq = 0;
     for (int m = 0; m < D.n_mods; ++m) { smem = smax(smem, lstm_bwd_smem(D.H[m], wsz)); Hq += D.H[m] * D.H[m]; }
     mt_prof_work(2.0 * 4.0 * Hq * (double)M, 4.0 * M * (double)(4 * Hs + 2 * H2 + H2 + Hs) + wsz * M * 4.0 * Hs);
-    MT_REC_LAUNCH(mfn_lstm_bwd_kernel, dim3(tiles, D.n_mods), smem, a);
+    if (lp && !g_mfn_force_ffma && mt_mfn_mma_lstm_supported(a)) MT_TRY(mt_mfn_mma_lstm_bwd(a, st));
+    else MT_REC_LAUNCH(mfn_lstm_bwd_kernel, dim3(tiles, D.n_mods), smem, a);
   }
   // B5: batched weight gradients over all T*B rows, input gradients
   auto wg = [&](const void* dz, int ldz, int Nout, const void* xin, int ldx, int Kin, size_t w_off, int ldw) -> int {

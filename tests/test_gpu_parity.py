@@ -310,6 +310,52 @@ def test_mfn_fwd_bwd_vs_oracle(train, B, T):
         np.testing.assert_allclose(y.detach().cpu().numpy(), util.gold('mfn')['y'], rtol=2e-5, atol=2e-6)
 
 
+@pytest.mark.parametrize('train,B,T', [(False, 3, 6), (True, 11, 9), (True, 16, 5), (False, 8, 130)])
+def test_mfn_tensor_core_recurrences_bf16(train, B, T):
+    """bf16 mode: the tensor-core recurrence kernels (mt_mfn_mma.cu: weights in registers, 8 narratives per CTA, ragged last
+    tile when B % 8 != 0) against the FFMA recurrences on the same stash layouts, and against the fp64 oracle."""
+    shapes = util.strip_prefix(util.mods_shapes('MFT.MultiTransformer'), 'mfn.')
+    sd = util.filled_sd(shapes, 6)
+    inputs, _, _, _ = fill.make_batch(B, T, {m: 256 for m in MODS}, 8)
+    w = t(fill.fill_array('mfn_w', (B, T, 1), 8))
+    seed = 91
+    sdr = {'mfn.' + k: v.double().requires_grad_(True) for k, v in sd.items()}
+    xr = {m: t(inputs[m]).double().permute(1, 0, 2).contiguous().requires_grad_(True) for m in MODS}
+    yr, hr, cr, memr = O.mfn(sdr, 'mfn', xr, MODS, Dropper(seed if train else None), return_states=True)
+    (yr * w.double()).sum().backward()
+    mtb.set_compute_dtype('bf16')
+    L = _lib.lib()
+    res = {}
+    for eng in ('mma', 'ffma'):
+        old = L.mt_mfn_force_ffma(int(eng == 'ffma'))
+        try:
+            mfn = mtb.MFN(MODS, {m: 256 for m in MODS}, 1).to(DEV); mfn.load_state_dict(sd); mfn.train(train)
+            mtb.fix_seed(seed)
+            xd = {m: t(inputs[m]).permute(1, 0, 2).contiguous().to(DEV).bfloat16().requires_grad_(True) for m in MODS}
+            y = mfn(xd)
+            (y * w.to(DEV)).sum().backward()
+            res[eng] = (y.detach().float().cpu(), {k: p.grad.detach().cpu() for k, p in mfn.named_parameters()},
+                        {m: xd[m].grad.detach().float().cpu() for m in MODS}, mfn.mem.detach().float().cpu())
+        finally:
+            L.mt_mfn_force_ffma(old)
+    y, g, dx, mem = res['mma']
+    yf, gf, dxf, memf = res['ffma']
+    assert (y - yr.float()).abs().max().item() < 2e-2                     # bf16 budget on the prediction
+    assert (y - yf).abs().max().item() < 1e-2
+    assert_close(mem, memr, 3e-2, 'mem')
+    for k in g:
+        want = sdr['mfn.' + k].grad.float()
+        if want.norm() < 1e-6:
+            continue
+        cos = torch.nn.functional.cosine_similarity(g[k].flatten(), want.flatten(), dim=0).item()
+        cosf = torch.nn.functional.cosine_similarity(gf[k].flatten(), want.flatten(), dim=0).item()
+        assert cos > 0.99 or cos > cosf - 5e-3, (k, cos, cosf)
+    for m in MODS:
+        cos = torch.nn.functional.cosine_similarity(dx[m].flatten(), xr[m].grad.float().flatten(), dim=0).item()
+        cosf = torch.nn.functional.cosine_similarity(dxf[m].flatten(), xr[m].grad.float().flatten(), dim=0).item()
+        assert cos > 0.99 or cos > cosf - 5e-3, (m, cos, cosf)        # no worse than the FFMA recurrences on bf16 operands
+
+
 # ---- whole models against the golden outputs of the imported reference ---------------------------------------
 def _check_grads(model, gold, rtol):
     n = 0
