@@ -287,6 +287,247 @@ __global__ void __launch_bounds__(NTH, 1) mem_bwd_mma_kernel(const __grid_consta
   }
 }
 
+// ======================================================================================================
+// LSTM recurrence, forward (LSTHM cell, MFT/multiTransformer.py:208): z = zx_t + b_hh + W_hh h_{t-1}, gates (i, f, g, o).
+// One CTA per (8 narratives, modality).  The 4H gate rows are permuted so that one 16-row mma tile holds the four gates of
+// four hidden units (tile row r: gate r / 4, unit 4 * tile + r % 4): the thread pair (lane, lane ^ 16) then holds i, g and
+// f, o of the same unit, activates its own two gates, swaps them with one shuffle each, and each of the two finishes one
+// narrative of that unit -- c_t and h_t never leave registers (h_t also goes to shared memory as the next step's B operand).
+// H <= 96, H % 4 == 0 (the defaults are 48 / 88 / 88): tiles 4 * (warp + 8 i), i < 3; K padded to 96 with zero fragments.
+// ======================================================================================================
+constexpr int LMT = 3;            // 16-row tiles per warp
+constexpr int LKS = 6;            // k-steps (K = 96)
+constexpr int LDH = 96 + 8;       // h tile row stride: conflict-free fragment reads
+constexpr int LDEPTH = 3;
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(NTH, 1) lstm_fwd_mma_kernel(const __grid_constant__ LstmArgs a) {
+  __shared__ __align__(16) bf16 hS[2][NB * LDH];
+  const int m = blockIdx.y;
+  const int H = a.H[m], hoff = a.hoff[m], Hs = a.Hs;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, q = lane & 3;
+  const int b0 = blockIdx.x * NB;
+  const bool lower = gid < 4;                       // holds i (row gid) and g (row gid + 8); the upper half holds f and o
+  const int gate0 = lower ? 0 : 1, gate1 = gate0 + 2;
+  const bf16* W = reinterpret_cast<const bf16*>(a.w_hh[m]);
+  uint32_t A[LMT][LKS][4];
+  int unit[LMT];
+  float bz[LMT][2];                                 // b_hh of this thread's two gate rows
+#pragma unroll
+  for (int i = 0; i < LMT; ++i) {
+    const int mt = warp + NW * i;
+    unit[i] = 4 * mt + (gid & 3);
+    auto get = [&](int r, int c) {
+      const int u = 4 * mt + (r & 3);
+      return (u < H && c < H) ? bf(W + (size_t)((r >> 2) * H + u) * H + c) : 0.f;
+    };
+#pragma unroll
+    for (int ks = 0; ks < LKS; ++ks) frag_a(A[i][ks], 0, ks * 16, lane, get);
+    const bool on = unit[i] < H;
+    bz[i][0] = on ? a.b_hh[m][gate0 * H + unit[i]] : 0.f;
+    bz[i][1] = on ? a.b_hh[m][gate1 * H + unit[i]] : 0.f;
+  }
+  const int nn[2] = {2 * q, 2 * q + 1};
+  bool val[2]; long long rbase[2];
+#pragma unroll
+  for (int p = 0; p < 2; ++p) { val[p] = b0 + nn[p] < a.B; rbase[p] = (long long)min(b0 + nn[p], a.B - 1) * a.sb; }
+  const int mine = lower ? 0 : 1;                   // the narrative (of its two) this thread finishes
+  for (int e = threadIdx.x; e < 2 * NB * LDH; e += NTH) hS[0][e] = __float2bfloat16(0.f);
+  float c[LMT] = {0.f, 0.f, 0.f}, h[LMT] = {0.f, 0.f, 0.f};
+  float zx[LDEPTH][LMT][4];
+  auto fetch = [&](int t, float (*z)[4]) {
+#pragma unroll
+    for (int i = 0; i < LMT; ++i) {
+      if (unit[i] >= H) continue;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const long long row = rbase[v & 1] + (long long)t * a.st;
+        z[i][v] = a.gates[row * (4 * Hs) + 4 * hoff + ((v >> 1) ? gate1 : gate0) * H + unit[i]];
+      }
+    }
+  };
+#pragma unroll
+  for (int i = 0; i < LDEPTH; ++i) if (i < a.T) fetch(i, zx[i]);
+  bf16* cstar_op = reinterpret_cast<bf16*>(a.cstar_op);
+  bf16* last_op = reinterpret_cast<bf16*>(a.last_op);
+  bf16* hprev_op = reinterpret_cast<bf16*>(a.hprev_op);
+  const int LW = Hs + a.MEM;
+  __syncthreads();
+
+  for (int t0 = 0; t0 < a.T; t0 += LDEPTH) {
+#pragma unroll
+    for (int s = 0; s < LDEPTH; ++s) {
+      const int t = t0 + s;
+      if (t >= a.T) break;
+      const bf16* hin = hS[t & 1];
+      bf16* hout = hS[(t & 1) ^ 1];
+      float acc[LMT][4];
+#pragma unroll
+      for (int i = 0; i < LMT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < LKS; ++ks) {
+        if (ks * 16 >= H) continue;
+        uint32_t bb0, bb1;
+        frag_b(bb0, bb1, hin, LDH, ks * 16, lane);
+#pragma unroll
+        for (int i = 0; i < LMT; ++i) mma16816(acc[i], A[i][ks], bb0, bb1);
+      }
+#pragma unroll
+      for (int i = 0; i < LMT; ++i) {
+        if (4 * (warp + NW * i) >= H) continue;                  // warp-uniform: this tile does not exist for this modality
+        float g[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const float z = acc[i][v] + zx[s][i][v] + bz[i][v >> 1];
+          // lower half: row gid = i (sigmoid), row gid + 8 = g (tanh); upper half: f and o (both sigmoid)
+          g[v] = (lower && (v >> 1)) ? tanhf(z) : sigmoidf_(z);
+        }
+        if (TRAIN && unit[i] < H) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            if (val[v & 1])
+              a.gates[(rbase[v & 1] + (long long)t * a.st) * (4 * Hs) + 4 * hoff + ((v >> 1) ? gate1 : gate0) * H + unit[i]] = g[v];
+        }
+        // swap: the lower thread sends its narrative-n1 pair (i, g), the upper thread its narrative-n0 pair (f, o)
+        const float s0 = lower ? g[1] : g[0], s1 = lower ? g[3] : g[2];
+        const float r0 = __shfl_xor_sync(0xffffffffu, s0, 16), r1 = __shfl_xor_sync(0xffffffffu, s1, 16);
+        const float gi = lower ? g[0] : r0, gg = lower ? g[2] : r1, gf = lower ? r0 : g[1], go = lower ? r1 : g[3];
+        const float cp = c[i], hp = h[i];
+        const float cn = gf * cp + gi * gg;
+        const float hn = go * tanhf(cn);
+        c[i] = cn; h[i] = hn;
+        if (unit[i] < H) {
+          const int n = nn[mine];
+          hout[n * LDH + unit[i]] = __float2bfloat16(hn);
+          if (val[mine]) {
+            const long long row = rbase[mine] + (long long)t * a.st;
+            const int col = hoff + unit[i];
+            a.cstar[row * (2 * Hs) + col] = cp;
+            a.cstar[row * (2 * Hs) + Hs + col] = cn;
+            if (cstar_op) { cstar_op[row * (2 * Hs) + col] = __float2bfloat16(cp); cstar_op[row * (2 * Hs) + Hs + col] = __float2bfloat16(cn); }
+            last_op[row * LW + col] = __float2bfloat16(hn);
+            if (TRAIN) hprev_op[row * Hs + col] = __float2bfloat16(hp);
+          }
+        }
+      }
+      if (t + LDEPTH < a.T) fetch(t + LDEPTH, zx[s]);
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < LMT; ++i) {
+    if (unit[i] < H && val[mine]) {
+      if (a.h_last) a.h_last[(size_t)(b0 + nn[mine]) * Hs + hoff + unit[i]] = h[i];
+      if (a.c_last) a.c_last[(size_t)(b0 + nn[mine]) * Hs + hoff + unit[i]] = c[i];
+    }
+  }
+}
+
+// ======================================================================================================
+// LSTM recurrence, backward (reverse time).  Warp w < ceil(H / 16) owns hidden units 16 w .. 16 w + 15 in BOTH roles: the
+// element-wise cell backward of those units (dc in registers) and the rows of dh_{t-1} = W_hh^T dz (A = W_hh^T with
+// k = gate * 96 + unit, 24 k-steps, fragments in registers), so dh never leaves the accumulator registers either.
+// ======================================================================================================
+constexpr int BKS = 24;            // k-steps over k = gate * 96 + unit
+constexpr int LDZ = 4 * 96 + 8;    // dz tile row stride
+constexpr int LBDEPTH = 2;
+
+__global__ void __launch_bounds__(NTH, 1) lstm_bwd_mma_kernel(const __grid_constant__ LstmArgs a) {
+  __shared__ __align__(16) bf16 dzS[2][NB * LDZ];
+  const int m = blockIdx.y;
+  const int H = a.H[m], hoff = a.hoff[m], Hs = a.Hs;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, q = lane & 3;
+  const int b0 = blockIdx.x * NB;
+  const bool active = warp * 16 < H;                 // warp-uniform
+  const bf16* W = reinterpret_cast<const bf16*>(a.w_hh[m]);
+  uint32_t A[BKS][4];
+  if (active) {
+    auto get = [&](int r, int k) {                   // r = output unit, k = gate * 96 + unit
+      const int gate = k / 96, u = k - gate * 96;
+      return (r < H && u < H) ? bf(W + (size_t)(gate * H + u) * H + r) : 0.f;
+    };
+#pragma unroll
+    for (int ks = 0; ks < BKS; ++ks) frag_a(A[ks], warp * 16, ks * 16, lane, get);
+  }
+  const int uu[2] = {warp * 16 + gid, warp * 16 + gid + 8};
+  const int nn[2] = {2 * q, 2 * q + 1};
+  bool val[2]; long long rbase[2];
+#pragma unroll
+  for (int p = 0; p < 2; ++p) { val[p] = b0 + nn[p] < a.B; rbase[p] = (long long)min(b0 + nn[p], a.B - 1) * a.sb; }
+  for (int e = threadIdx.x; e < 2 * NB * LDZ; e += NTH) dzS[0][e] = __float2bfloat16(0.f);
+  const int LW = Hs + a.MEM;
+  bf16* dz_op = reinterpret_cast<bf16*>(a.dz_op);
+  float dh[4] = {0.f, 0.f, 0.f, 0.f}, dc[4] = {0.f, 0.f, 0.f, 0.f};
+  struct In { float gi[4], gf[4], gg[4], go[4], cp[4], cn[4], dcp[4], dcn[4], dhd[4]; };
+  In in[LBDEPTH];
+  auto fetch = [&](int t, In& x) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int u = uu[v >> 1];
+      if (!active || u >= H) continue;
+      const long long row = rbase[v & 1] + (long long)t * a.st;
+      const float* gt = a.gates + row * (4 * Hs) + 4 * hoff + u;
+      x.gi[v] = gt[0]; x.gf[v] = gt[H]; x.gg[v] = gt[2 * H]; x.go[v] = gt[3 * H];
+      x.cp[v] = a.cstar[row * (2 * Hs) + hoff + u];
+      x.cn[v] = a.cstar[row * (2 * Hs) + Hs + hoff + u];
+      x.dcp[v] = a.dcstar[row * (2 * Hs) + hoff + u];
+      x.dcn[v] = a.dcstar[row * (2 * Hs) + Hs + hoff + u];
+      x.dhd[v] = a.dlast[row * LW + hoff + u];
+    }
+  };
+#pragma unroll
+  for (int i = 0; i < LBDEPTH; ++i) if (i < a.T) fetch(a.T - 1 - i, in[i]);
+  __syncthreads();
+
+  for (int i0 = 0; i0 < a.T; i0 += LBDEPTH) {
+#pragma unroll
+    for (int s = 0; s < LBDEPTH; ++s) {
+      const int i = i0 + s;
+      if (i >= a.T) break;
+      const int t = a.T - 1 - i;
+      bf16* dzo = dzS[i & 1];
+      if (active) {
+        const In& x = in[s];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int u = uu[v >> 1];
+          if (u >= H) continue;
+          const float tc = tanhf(x.cn[v]);
+          const float dhv = dh[v] + x.dhd[v];
+          const float dcv = dc[v] + x.dcn[v] + dhv * x.go[v] * (1.f - tc * tc);
+          const float zi = dcv * x.gg[v] * x.gi[v] * (1.f - x.gi[v]);
+          const float zf = dcv * x.cp[v] * x.gf[v] * (1.f - x.gf[v]);
+          const float zg = dcv * x.gi[v] * (1.f - x.gg[v] * x.gg[v]);
+          const float zo = dhv * tc * x.go[v] * (1.f - x.go[v]);
+          dc[v] = x.dcp[v] + dcv * x.gf[v];                          // gradient wrt c_{t-1}
+          bf16* zr = dzo + nn[v & 1] * LDZ + u;
+          zr[0] = __float2bfloat16(zi); zr[96] = __float2bfloat16(zf); zr[192] = __float2bfloat16(zg); zr[288] = __float2bfloat16(zo);
+          if (val[v & 1]) {
+            bf16* zo_g = dz_op + (rbase[v & 1] + (long long)t * a.st) * (4 * Hs) + 4 * hoff + u;
+            zo_g[0] = __float2bfloat16(zi); zo_g[H] = __float2bfloat16(zf); zo_g[2 * H] = __float2bfloat16(zg); zo_g[3 * H] = __float2bfloat16(zo);
+          }
+        }
+        if (i + LBDEPTH < a.T) fetch(t - LBDEPTH, in[s]);
+      }
+      __syncthreads();
+      if (active) {                                  // dh_{t-1} = W_hh^T dz
+        float acc[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < BKS; ++ks) {
+          if ((ks % 6) * 16 >= H) continue;          // zero-padded unit columns of this gate block
+          uint32_t bb0, bb1;
+          frag_b(bb0, bb1, dzo, LDZ, ks * 16, lane);
+          mma16816(acc[ks & 3], A[ks], bb0, bb1);
+        }
+#pragma unroll
+        for (int v = 0; v < 4; ++v) dh[v] = (acc[0][v] + acc[1][v]) + (acc[2][v] + acc[3][v]);
+      }
+    }
+  }
+}
+
 }  // namespace
 
 bool mt_mfn_mma_mem_supported(const MemArgs& a) { return a.MEM == 128 && a.G == 64 && (a.Hs % 2) == 0; }
@@ -306,6 +547,23 @@ int mt_mfn_mma_mem_bwd(const MemArgs& a, cudaStream_t st) {
   return MT_OK;
 }
 
-bool mt_mfn_mma_lstm_supported(const LstmArgs&) { return false; }
-int mt_mfn_mma_lstm_fwd(const LstmArgs&, cudaStream_t) { return MT_ERR_UNSUPPORTED; }
-int mt_mfn_mma_lstm_bwd(const LstmArgs&, cudaStream_t) { return MT_ERR_UNSUPPORTED; }
+bool mt_mfn_mma_lstm_supported(const LstmArgs& a) {
+  for (int m = 0; m < a.n_mods; ++m)
+    if (a.H[m] > 96 || a.H[m] % 4 != 0) return false;
+  return true;
+}
+
+int mt_mfn_mma_lstm_fwd(const LstmArgs& a, cudaStream_t st) {
+  const dim3 grid((a.B + NB - 1) / NB, a.n_mods);
+  if (a.training) lstm_fwd_mma_kernel<true><<<grid, NTH, 0, st>>>(a);
+  else lstm_fwd_mma_kernel<false><<<grid, NTH, 0, st>>>(a);
+  MT_LAUNCH_CHECK();
+  return MT_OK;
+}
+
+int mt_mfn_mma_lstm_bwd(const LstmArgs& a, cudaStream_t st) {
+  const dim3 grid((a.B + NB - 1) / NB, a.n_mods);
+  lstm_bwd_mma_kernel<<<grid, NTH, 0, st>>>(a);
+  MT_LAUNCH_CHECK();
+  return MT_OK;
+}
