@@ -40,6 +40,13 @@ __device__ __forceinline__ void frag_b(uint32_t& b0, uint32_t& b1, const bf16* S
   b1 = *reinterpret_cast<const uint32_t*>(p + 8);
 }
 __device__ __forceinline__ float bf(const bf16* p) { return __bfloat162float(*p); }
+// bf16-mode transcendental functions: hardware approximations (ex2 / tanh units, ~1e-3 relative), far inside the bf16 budget
+__device__ __forceinline__ float fsig(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float ftanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // ======================================================================================================
 // memory recurrence, forward:  gh = drop(relu(gpre_t + Wm mem_{t-1}));  g{1,2} = sigmoid(W2{1,2} gh{1,2} + b);
@@ -137,8 +144,8 @@ __global__ void __launch_bounds__(NTH, 1) mem_fwd_mma_kernel(const __grid_consta
       float mp[4], g1[4], g2[4];
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
-        g1[v] = sigmoidf_(c1[v] + bias1[v >> 1]);
-        g2[v] = sigmoidf_(c2[v] + bias2[v >> 1]);
+        g1[v] = fsig(c1[v] + bias1[v >> 1]);
+        g2[v] = fsig(c2[v] + bias2[v >> 1]);
         mp[v] = mem[v];
         mem[v] = g1[v] * mp[v] + g2[v] * ch[s][v];
         memS[nn[v & 1] * LDK + ff[v >> 1]] = __float2bfloat16(mem[v]);
@@ -331,7 +338,10 @@ __global__ void __launch_bounds__(NTH, 1) lstm_fwd_mma_kernel(const __grid_const
   bool val[2]; long long rbase[2];
 #pragma unroll
   for (int p = 0; p < 2; ++p) { val[p] = b0 + nn[p] < a.B; rbase[p] = (long long)min(b0 + nn[p], a.B - 1) * a.sb; }
-  const int mine = lower ? 0 : 1;                   // the narrative (of its two) this thread finishes
+  // the narrative (of its two) this thread finishes: n0 for the lower half, n1 for the upper half
+  const int n_mine = lower ? nn[0] : nn[1];
+  const bool val_mine = lower ? val[0] : val[1];
+  const long long rb_mine = lower ? rbase[0] : rbase[1];
   for (int e = threadIdx.x; e < 2 * NB * LDH; e += NTH) hS[0][e] = __float2bfloat16(0.f);
   float c[LMT] = {0.f, 0.f, 0.f}, h[LMT] = {0.f, 0.f, 0.f};
   float zx[LDEPTH][LMT][4];
@@ -380,7 +390,7 @@ __global__ void __launch_bounds__(NTH, 1) lstm_fwd_mma_kernel(const __grid_const
         for (int v = 0; v < 4; ++v) {
           const float z = acc[i][v] + zx[s][i][v] + bz[i][v >> 1];
           // lower half: row gid = i (sigmoid), row gid + 8 = g (tanh); upper half: f and o (both sigmoid)
-          g[v] = (lower && (v >> 1)) ? tanhf(z) : sigmoidf_(z);
+          g[v] = (lower && (v >> 1)) ? ftanh(z) : fsig(z);
         }
         if (TRAIN && unit[i] < H) {
 #pragma unroll
@@ -394,13 +404,12 @@ __global__ void __launch_bounds__(NTH, 1) lstm_fwd_mma_kernel(const __grid_const
         const float gi = lower ? g[0] : r0, gg = lower ? g[2] : r1, gf = lower ? r0 : g[1], go = lower ? r1 : g[3];
         const float cp = c[i], hp = h[i];
         const float cn = gf * cp + gi * gg;
-        const float hn = go * tanhf(cn);
+        const float hn = go * ftanh(cn);
         c[i] = cn; h[i] = hn;
         if (unit[i] < H) {
-          const int n = nn[mine];
-          hout[n * LDH + unit[i]] = __float2bfloat16(hn);
-          if (val[mine]) {
-            const long long row = rbase[mine] + (long long)t * a.st;
+          hout[n_mine * LDH + unit[i]] = __float2bfloat16(hn);
+          if (val_mine) {
+            const long long row = rb_mine + (long long)t * a.st;
             const int col = hoff + unit[i];
             a.cstar[row * (2 * Hs) + col] = cp;
             a.cstar[row * (2 * Hs) + Hs + col] = cn;
@@ -416,9 +425,9 @@ __global__ void __launch_bounds__(NTH, 1) lstm_fwd_mma_kernel(const __grid_const
   }
 #pragma unroll
   for (int i = 0; i < LMT; ++i) {
-    if (unit[i] < H && val[mine]) {
-      if (a.h_last) a.h_last[(size_t)(b0 + nn[mine]) * Hs + hoff + unit[i]] = h[i];
-      if (a.c_last) a.c_last[(size_t)(b0 + nn[mine]) * Hs + hoff + unit[i]] = c[i];
+    if (unit[i] < H && val_mine) {
+      if (a.h_last) a.h_last[(size_t)(b0 + n_mine) * Hs + hoff + unit[i]] = h[i];
+      if (a.c_last) a.c_last[(size_t)(b0 + n_mine) * Hs + hoff + unit[i]] = c[i];
     }
   }
 }
@@ -492,7 +501,7 @@ __global__ void __launch_bounds__(NTH, 1) lstm_bwd_mma_kernel(const __grid_const
         for (int v = 0; v < 4; ++v) {
           const int u = uu[v >> 1];
           if (u >= H) continue;
-          const float tc = tanhf(x.cn[v]);
+          const float tc = ftanh(x.cn[v]);
           const float dhv = dh[v] + x.dhd[v];
           const float dcv = dc[v] + x.dcn[v] + dhv * x.go[v] * (1.f - tc * tc);
           const float zi = dcv * x.gg[v] * x.gi[v] * (1.f - x.gi[v]);
