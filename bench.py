@@ -18,6 +18,10 @@ import sys
 import threading
 import time
 
+# stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
+if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', ''):
+    os.environ['NCCL_DEBUG'] = 'WARN'
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -343,9 +347,20 @@ def run_ours(args, rank, local_rank, world):
             'model_flops_utilisation': {'train_tflops_per_gpu': 3 * FLOP_PER_TOKEN_FWD * B * T / (ms_train * 1e-3) / 1e12 if T == 128 and N == 6 else None},
             'roofline': roofline, 'kernels': kernels, 'cpu_baseline': cpu,
         }
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
+        # tear down in order: captured graphs hold NCCL kernels, so drop them before the communicator; and never let a stuck
+        # communicator teardown hang the job after the result line is out
+        torch.cuda.synchronize()
+        dist.barrier()
+        gstep.graph = None
+        gfwd.graph = None
+        torch.cuda.synchronize()
+        watchdog = threading.Timer(20.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
         dist.destroy_process_group()
+        watchdog.cancel()
 
 
 def main():

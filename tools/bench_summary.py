@@ -1,5 +1,5 @@
 import json, sys
-d = json.load(open(sys.argv[1]))
+d = json.loads([l for l in open(sys.argv[1]) if l.startswith("{")][-1])
 print("train ms", round(d["ms_per_step"], 2), "value", round(d["value"]), "inf ms", round(d["inference"]["ms_per_step"], 2), "e2e", round(d["e2e"]["value"]),
       "launches", d["gpu_launches"], "clocks", d["clocks"])
 for k in (d["kernels"] or [])[:int(sys.argv[2]) if len(sys.argv) > 2 else 30]:
