@@ -429,6 +429,89 @@ def test_sft_golden():
     util.assert_digest_close(util.grad_digest(fb.grad), gold['grad:fusionLayer.bias'], 3e-4, 'fusion.b')
 
 
+# ---- BASELINE configs 4 and 5 at oracle-sized batches, and size-independent properties at full size -------------------
+def _enc_shapes_d(N, d, dff):
+    out = {}
+    for l in range(N):
+        for i in range(4):
+            out[f'layers.{l}.self_attn.linears.{i}.weight'] = (d, d); out[f'layers.{l}.self_attn.linears.{i}.bias'] = (d,)
+        out[f'layers.{l}.feed_forward.w_1.weight'] = (dff, d); out[f'layers.{l}.feed_forward.w_1.bias'] = (dff,)
+        out[f'layers.{l}.feed_forward.w_2.weight'] = (d, dff); out[f'layers.{l}.feed_forward.w_2.bias'] = (d,)
+        for k in range(2):
+            out[f'layers.{l}.sublayer.{k}.norm.a_2'] = (d,); out[f'layers.{l}.sublayer.{k}.norm.b_2'] = (d,)
+    out['norm.a_2'] = (d,); out['norm.b_2'] = (d,)
+    return out
+
+
+@pytest.mark.parametrize('mode,T', [('fp32', 300), ('bf16', 1024)])
+def test_config5_scaled_encoder_d512_long_sequence(mode, T):
+    """BASELINE config 5 shape class (d_model 512, 8 heads of 64, d_ff 256, long T -> the tiled any-T attention engine) on one
+    narrative, forward + backward against the fp64 oracle; the last quarter of the windows is padding."""
+    from multimodal_transformer_b200.multiTransformer import _make_encoder as mk
+    d, dff, N, B = 512, 256, 1, 1
+    enc = mk(d, dff, 8, 0.1, N).to(DEV).eval()
+    sd = util.filled_sd(_enc_shapes_d(N, d, dff), 33)
+    enc.load_state_dict(sd)
+    x = t(fill.fill_array('c5_x', (B, T, d), 33)) * 3.0
+    mask = torch.ones(B, T, 1); mask[:, 3 * T // 4:] = 0
+    w = t(fill.fill_array('c5_w', (B, T, d), 34))
+    sdr = {'e.' + k: v.double().requires_grad_(True) for k, v in sd.items()}
+    xr = x.double().requires_grad_(True)
+    yr = O.encoder(sdr, 'e', xr, mask.double(), N, 8)
+    (yr * w.double()).sum().backward()
+    mtb.set_compute_dtype(mode)
+    xd = x.to(DEV).requires_grad_(True)
+    y = enc(xd, mask.to(DEV))
+    (y.float() * w.to(DEV)).sum().backward()
+    if mode == 'fp32':
+        assert_close(y, yr, 2e-5, 'y'); assert_close(xd.grad, xr.grad, 5e-5, 'dx')
+    else:
+        assert (y.float().cpu() - yr.float()).abs().max().item() < 6e-2 * max(1.0, yr.abs().max().item())
+        cos = torch.nn.functional.cosine_similarity(xd.grad.float().cpu().flatten(), xr.grad.float().flatten(), dim=0).item()
+        assert cos > 0.99, cos
+
+
+def test_config4_b3_mfn_long_recurrence():
+    """BASELINE config 4 shape class: B3-MFN (no encoder) over 1024-window sequences, bf16 tensor-core recurrences, B = 3 (ragged
+    tile): prediction within the bf16 budget of the fp64 oracle at every step (error must not grow along the recurrence)."""
+    dims = {'acoustic': 256, 'image': 256, 'linguistic': 300}
+    T, B = 1024, 3
+    sd = util.filled_sd(util.mods_shapes('B3.MultiTransformer'), 12)
+    inputs, mask, target, lengths = fill.make_batch(B, T, dims, 12)
+    with torch.no_grad():
+        predr = O.multi_transformer({k: v.double() for k, v in sd.items()}, '', {k: t(v).double() for k, v in inputs.items()},
+                                    t(mask).double(), MODS, use_encoder=False)
+    mtb.set_compute_dtype('bf16')
+    model = mtb.B3MultiTransformer(MODS, dims).eval(); model.load_state_dict(sd)
+    pred = model({k: t(v).to(DEV) for k, v in inputs.items()}, t(mask).to(DEV), lengths)
+    err = (pred.detach().float().cpu() - predr.float()).abs()
+    assert err.max().item() < 2e-2, err.max().item()
+    assert err[:, T // 2:].max().item() < 2e-2
+    # BPTT over 1024 steps runs and produces finite gradients for every MFN parameter
+    ((pred - t(target).to(DEV)) ** 2).sum().div(sum(lengths)).backward()
+    for k, p in model.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+
+
+def test_full_size_properties_batch256():
+    """BASELINE config 2 at full size (B = 256, T = 128, N = 6, bf16), properties that need no oracle: padded windows predict
+    exactly 0, narratives are independent (a sub-batch reproduces its rows of the full batch), eval() is deterministic."""
+    dims = {'acoustic': 88, 'image': 256, 'linguistic': 300}
+    B, T = 256, 128
+    mtb.set_compute_dtype('bf16')
+    torch.manual_seed(1)
+    model = mtb.MultiTransformer(MODS, dims, N=6).eval()
+    inputs, mask, target, lengths = fill.make_batch(B, T, dims, 2)
+    x = {k: t(v).to(DEV) for k, v in inputs.items()}; m = t(mask).to(DEV)
+    with torch.no_grad():
+        p1 = model(x, m, lengths); p2 = model(x, m, lengths)
+        sub = slice(40, 56)
+        ps = model({k: v[sub].contiguous() for k, v in x.items()}, m[sub].contiguous(), lengths[sub])
+    assert torch.equal(p1, p2)
+    assert torch.isfinite(p1).all() and (p1 * (1 - m)).abs().max().item() == 0.0
+    assert torch.equal(ps, p1[sub])
+
+
 # ---- train mode with injected masks, bf16 mode, DP-style invariants --------------------------------------------
 def test_mft_train_mode_matches_oracle_with_same_masks():
     N, B, T, seed = 2, 4, 12, 31337
