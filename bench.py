@@ -274,6 +274,8 @@ def run_ours(args, rank, local_rank, world):
         # records bracket a kernel's true duration instead of the host's enqueue gap
         torch.cuda.synchronize()
         mtb.set_parallel_stacks(False)              # the per-launch profiler times consecutive launches of ONE stream
+        train_step(False)                           # un-profiled: lets the caching allocator settle for the one-stream schedule
+        torch.cuda.synchronize()
         _lib.check(L.mt_spin(60.0, _lib.stream()))
         _lib.check(L.mt_prof_start(20000, _lib.stream()))
         for _ in range(nprof):

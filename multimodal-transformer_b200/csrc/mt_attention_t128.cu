@@ -33,6 +33,21 @@ __device__ __forceinline__ void stage_all(bf16* s, const bf16* base, int ld, int
   }
 }
 
+// 2^x on the SFU (ex2.approx: 2 ulp, flushes denormals; -inf -> 0): this kernel is the bf16 path
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// dropout factors of keys j, j + 1 (j even) of the query row whose pair-index base is row * ceil(T / 2) (hoisted by the caller)
+__device__ __forceinline__ void drop_pair_at(const DropCfg& d, uint64_t pair_base, uint32_t j, float& f0, float& f1) {
+  if (d.thresh == 0u) { f0 = f1 = 1.0f; return; }
+  const uint32_t bits = mt_draw32(d, pair_base + (uint64_t)(j >> 1));
+  const uint32_t t16 = d.thresh >> 16;
+  f0 = (bits & 0xFFFFu) >= t16 ? d.scale : 0.0f;
+  f1 = (bits >> 16) >= t16 ? d.scale : 0.0f;
+}
+
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
   const int n = valid ? 16 : 0;                  // src-size 0: the 16 destination bytes are zero-filled
@@ -60,7 +75,7 @@ struct FwdSmem {
 
 // Persistent forward: a CTA walks (narrative, head) items; the next item's Q / K / V tiles are in flight (cp.async) while the
 // current one is computed, so no global-load latency is exposed after the first item.
-template <int DK>
+template <int DK, bool FULL>      // FULL: T == 128, no bound tests
 __global__ void __launch_bounds__(NT, 2) attn128_fwd_kernel(int B, int T, int d, int h, const bf16* __restrict__ qkv,
                                                             const float* __restrict__ mask, bf16* __restrict__ out,
                                                             float* __restrict__ lse, DropCfg drop_in, float scale) {
@@ -98,7 +113,7 @@ __global__ void __launch_bounds__(NT, 2) attn128_fwd_kernel(int B, int T, int d,
   const bf16* Qs = bufs + cur * 3 * TMAX * LD;
   const bf16* Ks = Qs + TMAX * LD;
   const bf16* Vs = Ks + TMAX * LD;
-  if (i0 < T) {
+  if (FULL || i0 < T) {
   uint32_t qa[DK / 16][4];
 #pragma unroll
   for (int ks = 0; ks < DK / 16; ++ks) ldsm_a(qa[ks], Qs + i0 * LD + ks * 16, LD, lane);
@@ -106,7 +121,7 @@ __global__ void __launch_bounds__(NT, 2) attn128_fwd_kernel(int B, int T, int d,
   // masked query rows: every score becomes the same constant, i.e. scale 0 (reference: masked_fill(-1e9) over the row)
   const float rs0 = (mask != nullptr && r0 < T && mask[(size_t)b * T + r0] == 0.f) ? 0.f : scale * LOG2E;
   const float rs1 = (mask != nullptr && r1 < T && mask[(size_t)b * T + r1] == 0.f) ? 0.f : scale * LOG2E;
-  const int nkt = (T + 7) >> 3;                       // 8-key tiles that hold at least one valid key
+  const int nkt = FULL ? TMAX / 8 : (T + 7) >> 3;     // 8-key tiles that hold at least one valid key
   float s[TMAX / 8][4];
   float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
@@ -128,7 +143,7 @@ __global__ void __launch_bounds__(NT, 2) attn128_fwd_kernel(int B, int T, int d,
     }
 #pragma unroll
     for (int e = 0; e < 2; ++e) {          // keys beyond T never contribute (their probability is exactly 0)
-      const bool in = nt * 8 + c + e < T;
+      const bool in = FULL || nt * 8 + c + e < T;
       s[nt][e] = in ? s[nt][e] * rs0 : -INFINITY;
       s[nt][2 + e] = in ? s[nt][2 + e] * rs1 : -INFINITY;
       mx0 = fmaxf(mx0, s[nt][e]); mx1 = fmaxf(mx1, s[nt][2 + e]);
@@ -137,24 +152,24 @@ __global__ void __launch_bounds__(NT, 2) attn128_fwd_kernel(int B, int T, int d,
   mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
   mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
   const uint64_t bh = (uint64_t)b * h + hd;
-  const uint64_t drow0 = bh * T + (uint64_t)min(r0, T - 1), drow1 = bh * T + (uint64_t)min(r1, T - 1);
   const uint32_t P2 = (uint32_t)(T + 1) >> 1;
+  const uint64_t dbase0 = (bh * T + (uint64_t)min(r0, T - 1)) * P2, dbase1 = (bh * T + (uint64_t)min(r1, T - 1)) * P2;
   float l0 = 0.f, l1 = 0.f;
   float o[DK / 8][4];
 #pragma unroll
   for (int i = 0; i < DK / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
 #pragma unroll
   for (int kk = 0; kk < TMAX / 16; ++kk) {
-    if (kk * 16 < T) {
+    if (FULL || kk * 16 < T) {
       uint32_t pa[4];
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         const int nt = 2 * kk + hf;
-        const float p0 = exp2f(s[nt][0] - mx0), p1 = exp2f(s[nt][1] - mx0), p2 = exp2f(s[nt][2] - mx1), p3 = exp2f(s[nt][3] - mx1);
+        const float p0 = fast_exp2(s[nt][0] - mx0), p1 = fast_exp2(s[nt][1] - mx0), p2 = fast_exp2(s[nt][2] - mx1), p3 = fast_exp2(s[nt][3] - mx1);
         l0 += p0 + p1; l1 += p2 + p3;
         float f0, f1, f2, f3;
-        mt_attn_drop_pair(drop, drow0, P2, (uint32_t)(nt * 8 + c), f0, f1);
-        mt_attn_drop_pair(drop, drow1, P2, (uint32_t)(nt * 8 + c), f2, f3);
+        drop_pair_at(drop, dbase0, (uint32_t)(nt * 8 + c), f0, f1);
+        drop_pair_at(drop, dbase1, (uint32_t)(nt * 8 + c), f2, f3);
         pa[hf * 2 + 0] = pack2(p0 * f0, p1 * f1);
         pa[hf * 2 + 1] = pack2(p2 * f2, p3 * f3);
       }
@@ -204,7 +219,7 @@ struct BwdSmem {
   static constexpr size_t BYTES = (size_t)(4 * TMAX * LD + 2 * TMAX * LP) * sizeof(bf16);
 };
 
-template <int DK>
+template <int DK, bool FULL>
 __global__ void __launch_bounds__(NT, DK <= 32 ? 2 : 1) attn128_bwd_kernel(int B, int T, int d, int h, const bf16* __restrict__ qkv,
                                                                            const float* __restrict__ mask, const bf16* __restrict__ out,
                                                                            const float* __restrict__ lse, const bf16* __restrict__ dout,
@@ -232,7 +247,7 @@ __global__ void __launch_bounds__(NT, DK <= 32 ? 2 : 1) attn128_bwd_kernel(int B
   const int bstep = gridDim.x / h;
   const int w0 = warp * 16;
   const int r0 = w0 + (lane >> 2), r1 = r0 + 8, c = 2 * (lane & 3);
-  const int nchunk = (T + 15) >> 4;            // 16-row chunks holding at least one valid row
+  const int nchunk = FULL ? TMAX / 16 : (T + 15) >> 4;      // 16-row chunks holding at least one valid row
   {
     const bf16* qb = qkv + (size_t)(blockIdx.x / h) * T * ld + hd * DK;
     if ((int)blockIdx.x / h < B) { stage_all_async<DK>(Ks, qb + d, ld, T); stage_all_async<DK>(Vs, qb + 2 * d, ld, T); }
@@ -249,7 +264,7 @@ __global__ void __launch_bounds__(NT, DK <= 32 ? 2 : 1) attn128_bwd_kernel(int B
   // own rows of Q / dO as A fragments, and D = rowsum(dO * O) of the two owned query rows
   uint32_t qa[DK / 16][4], ga[DK / 16][4];
   float D0 = 0.f, D1 = 0.f;
-  if (w0 < T) {
+  if (FULL || w0 < T) {
     uint32_t oa[DK / 16][4];
     load_a_frags<DK>(qa, qb, ld, w0, T, lane);
     load_a_frags<DK>(ga, gob, d, w0, T, lane);
@@ -271,16 +286,16 @@ __global__ void __launch_bounds__(NT, DK <= 32 ? 2 : 1) attn128_bwd_kernel(int B
   __syncthreads();
 
   // ---------------- phase 1: this warp's 16 query rows -> P, dS (shared memory) and dQ --------------------
-  if (w0 < T) {
-    const bool in0 = r0 < T, in1 = r1 < T;
+  if (FULL || w0 < T) {
+    const bool in0 = FULL || r0 < T, in1 = FULL || r1 < T;
     const bool mk0 = mask != nullptr && in0 && mask[(size_t)b * T + r0] == 0.f;
     const bool mk1 = mask != nullptr && in1 && mask[(size_t)b * T + r1] == 0.f;
     const float rs0 = mk0 ? 0.f : scale * LOG2E, rs1 = mk1 ? 0.f : scale * LOG2E;
     // masked rows carry no score gradient (masked_fill blocks it) but still feed dV with P = 1/T
     const float gs0 = (in0 && !mk0) ? scale : 0.f, gs1 = (in1 && !mk1) ? scale : 0.f;
     const float L0 = in0 ? lse[bh * T + r0] * LOG2E : 0.f, L1 = in1 ? lse[bh * T + r1] * LOG2E : 0.f;
-    const uint64_t drow0 = bh * T + (uint64_t)min(r0, T - 1), drow1 = bh * T + (uint64_t)min(r1, T - 1);
     const uint32_t P2 = (uint32_t)(T + 1) >> 1;
+    const uint64_t dbase0 = (bh * T + (uint64_t)min(r0, T - 1)) * P2, dbase1 = (bh * T + (uint64_t)min(r1, T - 1)) * P2;
     float dq[DK / 8][4];
 #pragma unroll
     for (int i = 0; i < DK / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
@@ -306,11 +321,11 @@ __global__ void __launch_bounds__(NT, DK <= 32 ? 2 : 1) attn128_bwd_kernel(int B
           mma16816(dp, ga[DK / 32 * 2], bv[0], bv[1]);
         }
         float f0, f1, f2, f3;
-        mt_attn_drop_pair(drop, drow0, P2, (uint32_t)(j + c), f0, f1);
-        mt_attn_drop_pair(drop, drow1, P2, (uint32_t)(j + c), f2, f3);
-        const bool k0 = j + c < T, k1 = j + c + 1 < T;
-        const float p0 = (in0 && k0) ? exp2f(s[0] * rs0 - L0) : 0.f, p1 = (in0 && k1) ? exp2f(s[1] * rs0 - L0) : 0.f;
-        const float p2 = (in1 && k0) ? exp2f(s[2] * rs1 - L1) : 0.f, p3 = (in1 && k1) ? exp2f(s[3] * rs1 - L1) : 0.f;
+        drop_pair_at(drop, dbase0, (uint32_t)(j + c), f0, f1);
+        drop_pair_at(drop, dbase1, (uint32_t)(j + c), f2, f3);
+        const bool k0 = FULL || j + c < T, k1 = FULL || j + c + 1 < T;
+        const float p0 = (in0 && k0) ? fast_exp2(s[0] * rs0 - L0) : 0.f, p1 = (in0 && k1) ? fast_exp2(s[1] * rs0 - L0) : 0.f;
+        const float p2 = (in1 && k0) ? fast_exp2(s[2] * rs1 - L1) : 0.f, p3 = (in1 && k1) ? fast_exp2(s[3] * rs1 - L1) : 0.f;
         const uint32_t pd01 = pack2(p0 * f0, p1 * f1), pd23 = pack2(p2 * f2, p3 * f3);
         const uint32_t ds01 = pack2(p0 * (dp[0] * f0 - D0) * gs0, p1 * (dp[1] * f1 - D0) * gs0);
         const uint32_t ds23 = pack2(p2 * (dp[2] * f2 - D1) * gs1, p3 * (dp[3] * f3 - D1) * gs1);
@@ -345,7 +360,7 @@ __global__ void __launch_bounds__(NT, DK <= 32 ? 2 : 1) attn128_bwd_kernel(int B
   cp_async_commit();
 
   // ---------------- phase 2: this warp's 16 keys -> dV = (P.drop)^T dO, dK = dS^T Q -------------------------
-  if (w0 < T) {
+  if (FULL || w0 < T) {
     float dk[DK / 8][4], dv[DK / 8][4];
 #pragma unroll
     for (int i = 0; i < DK / 8; ++i) { dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f; dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f; }
@@ -386,15 +401,20 @@ int launch_bwd(int B, int T, int d, int h, const void* qkv, const float* mask, c
                DropCfg drop, float scale, float* dbias, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    MT_CUDA(cudaFuncSetAttribute(attn128_bwd_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdSmem<DK>::BYTES));
+    MT_CUDA(cudaFuncSetAttribute(attn128_bwd_kernel<DK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdSmem<DK>::BYTES));
+    MT_CUDA(cudaFuncSetAttribute(attn128_bwd_kernel<DK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdSmem<DK>::BYTES));
     attr = true;
   }
   const int per_sm = DK <= 32 ? 2 : 1;
   int grid = (per_sm * 148 / h) * h;           // a multiple of h: every CTA keeps one head
   if (grid < h) grid = h;
   if (grid > B * h) grid = B * h;
-  attn128_bwd_kernel<DK><<<grid, NT, BwdSmem<DK>::BYTES, st>>>(B, T, d, h, (const bf16*)qkv, mask, (const bf16*)out, lse, (const bf16*)dout,
-                                                                 (bf16*)dqkv, drop, scale, dbias);
+  if (T == TMAX)
+    attn128_bwd_kernel<DK, true><<<grid, NT, BwdSmem<DK>::BYTES, st>>>(B, T, d, h, (const bf16*)qkv, mask, (const bf16*)out, lse, (const bf16*)dout,
+                                                                         (bf16*)dqkv, drop, scale, dbias);
+  else
+    attn128_bwd_kernel<DK, false><<<grid, NT, BwdSmem<DK>::BYTES, st>>>(B, T, d, h, (const bf16*)qkv, mask, (const bf16*)out, lse, (const bf16*)dout,
+                                                                          (bf16*)dqkv, drop, scale, dbias);
   MT_LAUNCH_CHECK();
   return MT_OK;
 }
@@ -416,10 +436,12 @@ int mt_attn128_fwd_run(int B, int T, int d, int h, const void* qkv, const float*
   {                                                                                                                                    \
     static bool attr = false;                                                                                                          \
     if (!attr) {                                                                                                                       \
-      MT_CUDA(cudaFuncSetAttribute(attn128_fwd_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdSmem<DK>::BYTES));     \
+      MT_CUDA(cudaFuncSetAttribute(attn128_fwd_kernel<DK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdSmem<DK>::BYTES));  \
+      MT_CUDA(cudaFuncSetAttribute(attn128_fwd_kernel<DK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdSmem<DK>::BYTES)); \
       attr = true;                                                                                                                     \
     }                                                                                                                                  \
-    attn128_fwd_kernel<DK><<<grid, NT, FwdSmem<DK>::BYTES, st>>>(B, T, d, h, (const bf16*)qkv, mask, (bf16*)out, lse, drop, scale);    \
+    if (T == TMAX) attn128_fwd_kernel<DK, true><<<grid, NT, FwdSmem<DK>::BYTES, st>>>(B, T, d, h, (const bf16*)qkv, mask, (bf16*)out, lse, drop, scale);  \
+    else attn128_fwd_kernel<DK, false><<<grid, NT, FwdSmem<DK>::BYTES, st>>>(B, T, d, h, (const bf16*)qkv, mask, (bf16*)out, lse, drop, scale);          \
   }
   switch (dk) {
     case 16: MT_FWD(16) break;

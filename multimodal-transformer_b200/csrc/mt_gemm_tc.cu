@@ -666,6 +666,7 @@ int mt_gemm_tc_run(const GemmDesc& d, cudaStream_t st) {
     if (d.N > 64) return launch_tc<128, 1>(d, st);
     return launch_tc<64, 1>(d, st);
   }
+  if (d.split_k > 1 && d.N > 64) return launch_tc<128, 1>(d, st);   // split-K wgrads: fewer, longer splits (half the fp32 reductions)
   if (d.N > 64) return launch_tc<128, 2>(d, st);        // two CTAs per SM, streaming ring
   return launch_tc<64, 1>(d, st);
 }
