@@ -319,7 +319,7 @@ int mt_linear_fwd(int dtype, int M, int N, int K, const void* x, int x_f32, cons
 size_t mt_linear_bwd_ws_bytes(int dtype, int M, int N, int K, int x_f32, float in_drop_p) {
   WsCarver k(nullptr);
   k.take_bytes((size_t)M * N * mt_esize(dtype));
-  k.take_bytes((size_t)M * K * mt_esize(dtype));
+  k.take_bytes((size_t)M * lin_kp(dtype, K) * mt_esize(dtype));
   if (dtype == MT_BF16) k.take_bytes((size_t)N * K * 2);
   return k.total();
 }
@@ -335,8 +335,11 @@ int mt_linear_bwd(int dtype, int M, int N, int K, const void* x, int x_f32, cons
   const bool lp = dtype == MT_BF16;
   if (!ws || ws_bytes < mt_linear_bwd_ws_bytes(dtype, M, N, K, x_f32, in_drop_p)) return MT_ERR_WS;
   WsCarver k(ws);
+  // the staged input keeps 16-byte aligned rows (K padded to a multiple of 8 in bf16 mode, zero columns) so that the weight
+  // gradient stays on the tcgen05 engine for any K (the 300-wide word vectors): TMA clips the box at the logical width K
+  const int Kp = lin_kp(dtype, K);
   void* dz = k.take_bytes((size_t)M * N * mt_esize(dtype));
-  void* xs = k.take_bytes((size_t)M * K * mt_esize(dtype));
+  void* xs = k.take_bytes((size_t)M * Kp * mt_esize(dtype));
   void* wl = lp ? k.take_bytes((size_t)N * K * 2) : nullptr;
   const bool dy_lp = lp && !dy_f32;
   const void* dzp = dy;
@@ -345,12 +348,13 @@ int mt_linear_bwd(int dtype, int M, int N, int K, const void* x, int x_f32, cons
     dzp = dz;
   }
   const void* xa = x;
-  if (in_drop_p > 0.f || (lp && x_f32)) {
-    MT_TRY(mt_cast2d_run(x, lp && !x_f32, K, xs, lp, K, M, K, mt_make_drop(in_drop_p, seed, site), st));
-    xa = xs;
+  int ldx = K;
+  if (in_drop_p > 0.f || (lp && (x_f32 || Kp != K))) {
+    MT_TRY(mt_cast2d_run(x, lp && !x_f32, K, xs, lp, Kp, M, K, mt_make_drop(in_drop_p, seed, site), st));
+    xa = xs; ldx = Kp;
   }
   MT_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)N * K, st));
-  MT_TRY(mt_gemm_run(dtype, wgrad_gemm(M, N, K, dzp, N, xa, K, dW, K), st));
+  MT_TRY(mt_gemm_run(dtype, wgrad_gemm(M, N, K, dzp, N, xa, ldx, dW, K), st));
   if (db) MT_TRY(mt_colsum_run(lp, M, N, dzp, N, db, 0, st));
   if (dx) {
     const void* wa = W;
