@@ -241,6 +241,47 @@ class GraphedTrainStep:
             self.capture()
         return self.replay()
 
+    # ---- pipelined input path: the host->device copy of batch k + 1 runs on a copy stream while batch k computes ------
+    def prefetch(self, inputs, mask, target, lengths):
+        """Enqueue the host->device copy of the NEXT batch (pinned host tensors) on the copy stream into one of two staging
+        sets and return at once.  `step_prefetched()` then moves it into the graph's static inputs with device-to-device
+        copies (3 TB/s) and replays.  PCIe time (84 MB = 1.6 ms at B = 256) disappears behind the previous step."""
+        if not hasattr(self, '_stage'):
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            mk = lambda: dict(x={m: torch.empty_like(v) for m, v in self.x.items()}, mask=torch.empty_like(self.mask),
+                              target=torch.empty_like(self.target), ready=torch.cuda.Event(), free=torch.cuda.Event(), lengths=None)
+            self._stage = [mk(), mk()]
+            self._next_in, self._next_out = 0, 0
+            for s_ in self._stage:
+                s_['free'].record(torch.cuda.current_stream(self.device))
+        st = self._stage[self._next_in]
+        self._next_in ^= 1
+        cs = self._copy_stream
+        cs.wait_event(st['free'])                    # the device-to-device copies that last read this set are done
+        with torch.cuda.stream(cs):
+            for m in self.mods:
+                st['x'][m].copy_(inputs[m], non_blocking=True)
+            st['mask'].copy_(mask.reshape(self.B, self.T, 1), non_blocking=True)
+            st['target'].copy_(target.reshape(self.B, self.T, 1), non_blocking=True)
+            st['ready'].record(cs)
+        st['lengths'] = lengths
+
+    def step_prefetched(self):
+        """Run the train step on the oldest prefetched batch; returns the loss [1] on the device."""
+        st = self._stage[self._next_out]
+        self._next_out ^= 1
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(st['ready'])
+        for m in self.mods:
+            self.x[m].copy_(st['x'][m], non_blocking=True)
+        self.mask.copy_(st['mask'], non_blocking=True)
+        self.target.copy_(st['target'], non_blocking=True)
+        st['free'].record(cur)
+        self.inv_norm.fill_(1.0 / self.norm_fn(st['lengths']))
+        if self.graph is None:
+            self.capture()
+        return self.replay()
+
 
 class GraphedForward:
     """eval() forward captured into a CUDA graph for a fixed (B, T); returns the static prediction buffer [B,T,1]."""
@@ -280,6 +321,40 @@ class GraphedForward:
 
     def __call__(self, inputs, mask):
         self.load(inputs, mask)
+        if self.graph is None:
+            self.capture()
+        self.graph.replay()
+        return self.pred
+
+    def prefetch(self, inputs, mask):
+        """Host->device copy of the NEXT batch on a copy stream (see GraphedTrainStep.prefetch)."""
+        if not hasattr(self, '_stage'):
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            mk = lambda: dict(x={m: torch.empty_like(v) for m, v in self.x.items()}, mask=torch.empty_like(self.mask),
+                              ready=torch.cuda.Event(), free=torch.cuda.Event())
+            self._stage = [mk(), mk()]
+            self._next_in, self._next_out = 0, 0
+            for s_ in self._stage:
+                s_['free'].record(torch.cuda.current_stream(self.device))
+        st = self._stage[self._next_in]
+        self._next_in ^= 1
+        cs = self._copy_stream
+        cs.wait_event(st['free'])
+        with torch.cuda.stream(cs):
+            for m in self.mods:
+                st['x'][m].copy_(inputs[m], non_blocking=True)
+            st['mask'].copy_(mask.reshape(self.B, self.T, 1), non_blocking=True)
+            st['ready'].record(cs)
+
+    def forward_prefetched(self):
+        st = self._stage[self._next_out]
+        self._next_out ^= 1
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(st['ready'])
+        for m in self.mods:
+            self.x[m].copy_(st['x'][m], non_blocking=True)
+        self.mask.copy_(st['mask'], non_blocking=True)
+        st['free'].record(cur)
         if self.graph is None:
             self.capture()
         self.graph.replay()

@@ -674,6 +674,49 @@ def test_graphed_train_step_equals_eager_steps(mode):
         assert_close(p, pe[k], tol, k, 1e-6)
 
 
+def test_prefetched_input_pipeline_equals_direct_calls():
+    """GraphedTrainStep.prefetch / step_prefetched (host->device copy of batch k + 1 on a copy stream while batch k computes)
+    gives exactly the losses and parameters of the direct __call__ path; same for GraphedForward."""
+    from multimodal_transformer_b200.training import FlatAdam, GraphedForward, GraphedTrainStep
+    N, B, T = 1, 4, 8
+    dims = {'acoustic': 88, 'image': 256, 'linguistic': 300}
+    sd = util.filled_sd(util.mods_shapes('MFT.MultiTransformer', N), 5)
+    batches = [fill.make_batch(B, T, dims, 90 + i) for i in range(4)]
+    pin = lambda a: t(a).pin_memory()
+
+    def run(prefetched):
+        model = mtb.MultiTransformer(MODS, dims, N=N, dropout=0.0).to(DEV); model.load_state_dict(sd)
+        for mod in model.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        opt = FlatAdam(model, lr=1e-3)
+        g = GraphedTrainStep(model, opt, B, T, dims, torch.device(DEV), warmup=1)
+        hb = [({k: pin(v) for k, v in i.items()}, pin(m), pin(tg), l) for i, m, tg, l in batches]
+        losses = []
+        if prefetched:
+            g.prefetch(*hb[0])
+            for k in range(len(hb)):
+                if k + 1 < len(hb):
+                    g.prefetch(*hb[k + 1])
+                losses.append(g.step_prefetched().item())
+        else:
+            for b in hb:
+                losses.append(g(*b).item())
+        gf = GraphedForward(model, B, T, dims, torch.device(DEV), warmup=1)
+        if prefetched:
+            gf.prefetch(hb[0][0], hb[0][1]); pred = gf.forward_prefetched().clone()
+        else:
+            pred = gf(hb[0][0], hb[0][1]).clone()
+        return losses, pred, {k: p.detach().clone() for k, p in model.named_parameters()}
+
+    la, pa, wa = run(False)
+    lb, pb, wb = run(True)
+    assert la[0] == lb[0] and all(abs(a - b) <= 1e-5 * abs(a) for a, b in zip(la, lb)), (la, lb)
+    assert_close(pb, pa, 1e-5, 'pred', 1e-7)
+    for k in wa:
+        assert_close(wb[k], wa[k], 1e-5, k, 1e-7)          # split-K atomics reorder fp32 sums between runs
+
+
 def test_graph_replay_draws_fresh_dropout_masks():
     """Two replays of the captured step on the same batch give different losses in train mode (the dropout seed offset
     lives in device memory and is bumped inside the graph), and eager calls afterwards are unaffected."""

@@ -16,6 +16,6 @@ cap attn_bwd attn128_bwd 2 1
 cap attn_fwd attn128_fwd 2 1
 cap gemm 'gemm_tc_kernel' 7 8
 cap gemm_bwd 'gemm_tc_kernel' 130 12
-cap rowwise 'ln_bwd|ln_fwd|colsum_vec|drop_grad' 40 6
-cap mfn 'mfn_lstm|mfn_mem' 0 4
+cap rowwise 'ln_bwd|ln_fwd' 40 4
+cap mfn 'lstm_fwd_mma|lstm_bwd_mma|mem_fwd_mma|mem_bwd_mma' 0 4
 ls -la $OUT
