@@ -714,7 +714,9 @@ def test_prefetched_input_pipeline_equals_direct_calls():
     assert la[0] == lb[0] and all(abs(a - b) <= 1e-5 * abs(a) for a, b in zip(la, lb)), (la, lb)
     assert_close(pb, pa, 1e-5, 'pred', 1e-7)
     for k in wa:
-        assert_close(wb[k], wa[k], 1e-5, k, 1e-7)          # split-K atomics reorder fp32 sums between runs
+        # split-K atomics reorder fp32 sums between runs, and Adam turns the round-off of analytically-zero gradients (the
+        # key-projection bias) into +-lr steps: allow a few lr
+        assert_close(wb[k], wa[k], 1e-4, k, 1e-5)
 
 
 def test_graph_replay_draws_fresh_dropout_masks():
