@@ -231,8 +231,8 @@ int mt_gemm(int dtype, int M, int N, int K, const void* A, int lda, int a_kmajor
 int mt_gemm_engine(int dtype, int M, int N, int K, int a_kmajor, int b_kmajor);
 /* test hook: route every GEMM through the FFMA engine (A/B the tensor-core engine); returns the previous setting. */
 int mt_gemm_force_simt(int on);
-/* tuning hook: 1 = one CTA per SM (weight-resident ring, 256-wide tiles), 2 = two CTAs per SM with a streaming ring (default);
- * returns the previous mode. */
+/* tuning hook: 0 = 256-wide weight-resident tiles where they apply (two CTAs per SM with a streaming ring elsewhere), 1 = one CTA per
+ * SM everywhere, 2 = never use the 256-wide tile (default, measured fastest on the MFT step); returns the previous mode. */
 int mt_gemm_tc_mode(int mode);
 /* debug hook: CTA 0 of every tcgen05 GEMM writes per-tile clock64 stamps (8 x uint64 per tile, first 64 tiles: TMA issue, MMA
  * tile start, first operands landed, last k-block landed, epilogue sees the accumulator, accumulator released, last pass

@@ -27,7 +27,13 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;                 // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int EW = 8;                  // epilogue warps: 4 TMEM lane quarters x 2 column halves
+// epilogue warps = 4 TMEM lane quarters x (2 | 4) column slices, each slice drained in passes of PW columns through a staging
+// buffer.  The 256-wide tile uses 16 warps (the epilogue, not the MMA issue loop, bounded it with 8) and 16-column passes so
+// that the staging still fits next to the 128 KB resident weight slice.
+template <int BN> struct EpiCfg {
+  static constexpr int EW = BN > 128 ? 16 : 8;
+  static constexpr int PW = BN > 128 ? 16 : 32;
+};
 constexpr int KB_RES = 4;              // weight-resident mode: at most this many k-blocks (K <= 256)
 constexpr int MAX_STAGES = 8;
 constexpr uint32_t SPIN_LIMIT = 1u << 27;
@@ -106,6 +112,16 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor, version 1)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -126,8 +142,9 @@ struct Smem {
   static constexpr int RING_BYTES = OCC == 2 ? 2 * (A_BYTES + B_BYTES) : (BN > 128 ? 176 : 160) * 1024;   // resident weights + ring, or ring only
   static constexpr int NS_STREAM = RING_BYTES / (A_BYTES + B_BYTES);                    // 6 (BN = 64) / 5 (128) / 3 (256)
   static constexpr int NS_RES = OCC == 2 ? 1 : (RING_BYTES - KB_RES * B_BYTES) / A_BYTES;   // 8 / 6 / 3 (unused with OCC = 2)
+  static constexpr int EW = EpiCfg<BN>::EW, PW = EpiCfg<BN>::PW;
   static constexpr int THREADS = 64 + 32 * EW;
-  static constexpr int EPI_BYTES = EW * 32 * (32 + 4) * 4;                              // per epilogue warp: 32 rows x (32 + 4) floats
+  static constexpr int EPI_BYTES = EW * 32 * (PW + 4) * 4;                              // per epilogue warp: 32 rows x (PW + 4) floats
   static constexpr int BAR_BYTES = 256;
   static constexpr int CS_COLS = 1024;                                                  // epi.colsum: per-CTA column accumulators (N <= CS_COLS)
   static constexpr int TOTAL = RING_BYTES + EPI_BYTES + BAR_BYTES + CS_COLS * 4 + 1024 /* alignment slack */;
@@ -194,7 +211,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EW); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], S::EW); }
     mbar_init(b_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -305,11 +322,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ===== epilogue warps: warp w owns TMEM lane quarter (w % 4) and column half (w - 2) / 4 of every tile =====
-    constexpr int HN = BN / 2;                 // columns per epilogue warp
-    constexpr int NP = HN / 32;                // 32-column passes through the staging buffer
-    constexpr int LDS = 32 + 4;                // staged row stride in floats (16-byte aligned, conflict-free both ways)
-    constexpr int LPR = 4;                     // lanes per output row: each lane owns 8 consecutive columns
+    // ===== epilogue warps: warp w owns TMEM lane quarter (w % 4) and column slice (w - 2) / 4 of every tile =====
+    constexpr int PW = S::PW;                  // columns per pass through the staging buffer
+    constexpr int HN = BN / (S::EW / 4);       // columns per epilogue warp
+    constexpr int NP = HN / PW;
+    constexpr int LDS = PW + 4;                // staged row stride in floats (16-byte aligned)
+    constexpr int LPR = PW / 8;                // lanes per output row: each lane owns 8 consecutive columns
     constexpr int RPI = 32 / LPR;              // rows covered by one warp-wide access
     constexpr int ITERS = 32 / RPI;
     const int q = warp & 3, half = (warp - 2) >> 2;
@@ -334,8 +352,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int row_base = m0 + q * 32;
 #pragma unroll 1
       for (int p = 0; p < NP; ++p) {
-        uint32_t v[32];
-        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * HN + p * 32), v);
+        uint32_t v[PW];
+        if constexpr (PW == 32) tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * HN + p * PW), v);
+        else tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * HN + p * PW), v);
         if (p == NP - 1) {      // all TMEM reads of this accumulator are done: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -344,11 +363,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         __syncwarp();                             // previous pass's reads of `stg` are complete
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < PW / 4; ++j)
           *reinterpret_cast<float4*>(stg + lane * LDS + j * 4) = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                                                              __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
         __syncwarp();
-        const int n = tn * BN + half * HN + p * 32 + lc;
+        const int n = tn * BN + half * HN + p * PW + lc;
         bool hi_ok = true;                        // columns n + 4 .. n + 7 exist (N % 4 == 0, so a quad is all-or-nothing)
         if (F & F_EDGE) {
           if (n >= g.N || row_base >= g.M) continue;
@@ -548,7 +567,7 @@ int num_sms() {
 }
 
 unsigned long long* g_trace = nullptr;
-int g_tc_mode = 2;       // CTAs per SM of the 128-wide-tile kernel (mt_gemm_tc_set_mode)
+int g_tc_mode = 2;       // 0 = 256-wide tiles where they apply, 1 = one CTA per SM everywhere, 2 = never use the 256-wide tile (default: measured fastest)
 
 template <int BN, uint32_t F, bool RES, int OCC = 1>
 int launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& g, int grid, cudaStream_t st) {
@@ -661,13 +680,19 @@ int mt_gemm_tc_run(const GemmDesc& d, cudaStream_t st) {
   // bottleneck of short-K GEMMs) whenever the weight-resident mode applies
   const int kb_total = (d.K + BK - 1) / BK;
   (void)kb_total;
-  if (g_tc_mode == 1) {                                 // one CTA per SM: weight-resident 256-wide tiles where they apply
-    if (d.N >= 256 && d.split_k <= 1 && kb_total <= KB_RES) return launch_tc<256, 1>(d, st);
+  const bool wide_ok = d.N >= 256 && d.split_k <= 1 && kb_total <= KB_RES;
+  if (g_tc_mode == 1) {                                 // one CTA per SM everywhere
+    if (wide_ok) return launch_tc<256, 1>(d, st);
     if (d.N > 64) return launch_tc<128, 1>(d, st);
     return launch_tc<64, 1>(d, st);
   }
-  if (d.split_k > 1 && d.N > 64) return launch_tc<128, 1>(d, st);   // split-K wgrads: fewer, longer splits (half the fp32 reductions)
-  if (d.N > 64) return launch_tc<128, 2>(d, st);        // two CTAs per SM, streaming ring
+  // mode 0: 256-wide weight-resident tiles (one CTA per SM, 16 epilogue warps) where they apply -- measured 5 % SLOWER on the MFT
+  // step than mode 2 (8.84 vs 9.26 ms: 768 wide tiles quantise badly over 148 SMs and a lone CTA cannot hide its own fill
+  // latency), so the default is mode 2: split-K wgrads on fewer, longer splits, everything else two CTAs per SM with a
+  // streaming ring
+  if (g_tc_mode == 0 && wide_ok) return launch_tc<256, 1>(d, st);
+  if (d.split_k > 1 && d.N > 64) return launch_tc<128, 1>(d, st);
+  if (d.N > 64) return launch_tc<128, 2>(d, st);
   return launch_tc<64, 1>(d, st);
 }
 
