@@ -46,6 +46,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-profile', action='store_true')
     ap.add_argument('--gemm-mode', type=int, default=0, help='tcgen05 GEMM CTAs per SM (tuning; 0 = library default)')
+    ap.add_argument('--tune', default='', help='library tuning knobs, e.g. 0=2,1=2 (mt_tune key=value)')
     ap.add_argument('--serial-stacks', action='store_true', help='run the modality stacks on one stream')
     return ap.parse_args()
 
@@ -173,6 +174,9 @@ def run_ours(args, rank, local_rank, world):
     mtb.set_compute_dtype(args.dtype)
     if args.gemm_mode:
         L.mt_gemm_tc_mode(args.gemm_mode)
+    for kv in filter(None, args.tune.split(',')):
+        k_, v_ = kv.split('=')
+        L.mt_tune(int(k_), int(v_))
     if args.serial_stacks:
         mtb.set_parallel_stacks(False)
     B, T, N = args.batch, args.seq, args.layers

@@ -126,6 +126,8 @@ typedef struct {
   uint64_t seed;
   int stack_id;      /* selects the dropout sites: site = (stack_id*64 + layer)*8 + k */
   int y_f32;
+  int grid_share;    /* 0/1: this stack owns the GPU; s > 1: it runs concurrently with s - 1 other streams (the other modality stacks):
+                        its GEMM / LayerNorm kernels launch 1/s of the resident CTA slots so the stacks co-reside on the SMs */
 } MtEncoderCfg;
 
 size_t mt_encoder_param_count(int d, int dff, int n_layers);
@@ -234,6 +236,10 @@ int mt_gemm_force_simt(int on);
 /* tuning hook: 0 = 256-wide weight-resident tiles where they apply (two CTAs per SM with a streaming ring elsewhere), 1 = one CTA per
  * SM everywhere, 2 = never use the 256-wide tile (default, measured fastest on the MFT step); returns the previous mode. */
 int mt_gemm_tc_mode(int mode);
+/* tuning knobs; returns the previous value (-1: bad key).  key 0 / 1 / 2 = grid share of the tcgen05 GEMM / the T <= 128 attention /
+ * the LayerNorm kernels: a share s > 1 launches 1/s of the resident CTA slots, so kernels of concurrent streams (the modality stacks
+ * of MultiTransformer) co-reside on the SMs instead of queueing behind each other. */
+int mt_tune(int key, int value);
 /* debug hook: CTA 0 of every tcgen05 GEMM writes per-tile clock64 stamps (8 x uint64 per tile, first 64 tiles: TMA issue, MMA
  * tile start, first operands landed, last k-block landed, epilogue sees the accumulator, accumulator released, last pass
  * starts; then per-k-block issue / landing stamps of the first 16 tiles) into dev_buf (>= 8 KB); NULL switches it off. */

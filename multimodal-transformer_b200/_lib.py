@@ -20,7 +20,7 @@ MT_MAX_MODS = 4
 class MtEncoderCfg(Structure):
     _fields_ = [('B', c_int), ('T', c_int), ('d', c_int), ('h', c_int), ('dff', c_int), ('n_layers', c_int),
                 ('dtype', c_int), ('training', c_int), ('p_drop', c_float), ('seed', c_uint64), ('stack_id', c_int),
-                ('y_f32', c_int)]
+                ('y_f32', c_int), ('grid_share', c_int)]
 
 
 class MtMfnCfg(Structure):
@@ -86,6 +86,7 @@ _PROTOS = {
     'mt_mfn_force_ffma': (c_int, [c_int]),
     'mt_gemm_debug_trace': (c_int, [P]),
     'mt_gemm_tc_mode': (c_int, [c_int]),
+    'mt_tune': (c_int, [c_int, c_int]),
 }
 
 EXPORTS = tuple(_PROTOS)      # every symbol include/mt_b200.h declares

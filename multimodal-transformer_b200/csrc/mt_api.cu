@@ -113,6 +113,15 @@ const char* mt_last_cuda_error(void) { return g_mt_cuda_err; }
 
 int mt_version(void) { return 100; }
 
+/* tuning knobs (see include/mt_b200.h: mt_tune) */
+int g_mt_tune[8] = {1, 1, 1, 0, 0, 0, 0, 0};
+int mt_tune(int key, int value) {
+  if (key < 0 || key >= 8) return -1;
+  int old = g_mt_tune[key];
+  g_mt_tune[key] = value;
+  return old;
+}
+
 uint64_t mt_launch_count(void) { return (uint64_t)g_mt_launches; }
 
 int mt_check_device(int dev) {

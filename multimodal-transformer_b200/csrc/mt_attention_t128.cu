@@ -406,7 +406,7 @@ int launch_bwd(int B, int T, int d, int h, const void* qkv, const float* mask, c
     attr = true;
   }
   const int per_sm = DK <= 32 ? 2 : 1;
-  int grid = (per_sm * 148 / h) * h;           // a multiple of h: every CTA keeps one head
+  int grid = (per_sm * 148 / (g_mt_tune[MT_TUNE_ATTN_SHARE] > 1 ? g_mt_tune[MT_TUNE_ATTN_SHARE] : 1) / h) * h;      // a multiple of h: every CTA keeps one head
   if (grid < h) grid = h;
   if (grid > B * h) grid = B * h;
   if (T == TMAX)
@@ -431,7 +431,8 @@ int mt_attn128_fwd_run(int B, int T, int d, int h, const void* qkv, const float*
   const int dk = d / h;
   const float scale = 1.0f / sqrtf((float)dk);
   mt_prof_work(4.0 * B * (double)T * T * d, (double)B * T * d * 4.0 * 2.0);
-  const int grid = B * h < 2 * 148 ? B * h : 2 * 148;
+  const int slots = 2 * 148 / (g_mt_tune[MT_TUNE_ATTN_SHARE] > 1 ? g_mt_tune[MT_TUNE_ATTN_SHARE] : 1);
+  const int grid = B * h < slots ? B * h : slots;
 #define MT_FWD(DK)                                                                                                                     \
   {                                                                                                                                    \
     static bool attr = false;                                                                                                          \

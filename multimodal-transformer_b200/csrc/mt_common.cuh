@@ -37,6 +37,13 @@ void mt_prof_tag(const char* tag);                   // ... and with a shape tag
     if (_r != MT_OK) return _r; \
   } while (0)
 
+// tuning knobs (mt_tune): [0] GEMM grid share, [1] attention grid share, [2] LayerNorm grid share -- a share of s launches 1/s of the
+// resident CTA slots so that kernels of concurrent streams (the three modality stacks) co-reside instead of queueing
+extern int g_mt_tune[8];
+#define MT_TUNE_GEMM_SHARE 0
+#define MT_TUNE_ATTN_SHARE 1
+#define MT_TUNE_LN_SHARE 2
+
 static inline size_t mt_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---- typed loads / stores ----------------------------------------------------------------------------

@@ -91,6 +91,15 @@ int carve(const MtEncoderCfg& c, void* ws, EncWs& w) {
   return MT_OK;
 }
 
+// the stack's kernels share the SMs with `share - 1` concurrent streams for the duration of one C call (mt_tune knobs)
+struct GridShareScope {
+  int g0, g2;
+  explicit GridShareScope(int share) : g0(g_mt_tune[MT_TUNE_GEMM_SHARE]), g2(g_mt_tune[MT_TUNE_LN_SHARE]) {
+    if (share > 1) { g_mt_tune[MT_TUNE_GEMM_SHARE] = share; g_mt_tune[MT_TUNE_LN_SHARE] = share; }
+  }
+  ~GridShareScope() { g_mt_tune[MT_TUNE_GEMM_SHARE] = g0; g_mt_tune[MT_TUNE_LN_SHARE] = g2; }
+};
+
 int check_cfg(const MtEncoderCfg* c) {
   if (!c) return MT_ERR_ARG;
   if (c->B <= 0 || c->T <= 0 || c->d <= 0 || c->h <= 0 || c->dff <= 0 || c->n_layers <= 0) return MT_ERR_ARG;
@@ -169,6 +178,7 @@ int mt_encoder_fwd(const MtEncoderCfg* cfg, const float* params, const void* par
   const EncParams P = enc_params(d, dff, c.n_layers);
   const float p = c.p_drop;
   const float* xin = x;
+  GridShareScope share(c.grid_share);
   for (int l = 0; l < c.n_layers; ++l) {
     const size_t base = P.layer_stride * l;
     const float* pf = params + base;
@@ -217,6 +227,7 @@ int mt_encoder_bwd(const MtEncoderCfg* cfg, const float* params, const void* par
   const EncParams P = enc_params(d, dff, c.n_layers);
   const float p = c.p_drop;
   const float keep_scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+  GridShareScope share(c.grid_share);
   MT_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * P.total, st));
 
   float* g_cur = w.g0;

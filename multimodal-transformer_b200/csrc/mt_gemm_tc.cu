@@ -626,7 +626,11 @@ int launch_tc(const GemmDesc& d, cudaStream_t st) {
   MT_TRY(make_map(&ma, d.A, d.M, d.K, d.lda, d.a_kmajor, BM));
   MT_TRY(make_map(&mb, d.B, d.N, d.K, d.ldb, d.b_kmajor, BN));
   const int n_work = g.tiles_m * g.tiles_n * g.splits;
-  const int grid = n_work < OCC * num_sms() ? n_work : OCC * num_sms();
+  // g_tc_share > 1: launch only 1/share of the resident CTA slots so that GEMMs of concurrent streams (the three modality stacks)
+  // co-reside on every SM instead of queueing behind each other (mt_tune)
+  int slots = OCC * num_sms();
+  if (g_mt_tune[MT_TUNE_GEMM_SHARE] > 1 && d.split_k <= 1) slots = slots / g_mt_tune[MT_TUNE_GEMM_SHARE];
+  const int grid = n_work < slots ? n_work : slots;
   const uint32_t f = needed_features<BN>(d, g);
   // weight-resident mode: short K, no split, and at least one CTA per column slice
   const bool res = OCC == 1 && g.splits == 1 && g.kb_total <= KB_RES && grid >= g.tiles_n;

@@ -332,7 +332,8 @@ class EncoderFn(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad)
         p_drop = float(cfgd['p_drop'])
         cfg = _lib.MtEncoderCfg(B, T, d, cfgd['h'], cfgd['dff'], cfgd['n_layers'], dt, int(need_grad), p_drop,
-                                next_seed() if p_drop > 0 else 0, cfgd['stack_id'], int(cfgd.get('y_f32', dt == MT_F32)))
+                                next_seed() if p_drop > 0 else 0, cfgd['stack_id'], int(cfgd.get('y_f32', dt == MT_F32)),
+                                int(cfgd.get('grid_share', 0)))
         L = lib()
         nws = L.mt_encoder_ws_bytes(ctypes.byref(cfg))
         if nws == 0:

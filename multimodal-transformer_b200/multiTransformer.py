@@ -187,6 +187,8 @@ class Encoder(nn.Module):
                     p_drop=l0.sublayer[0].dropout.p if self.training else 0.0, stack_id=self.stack_id)
         if self.out_fp32 is not None:
             cfgd['y_f32'] = bool(self.out_fp32)
+        if getattr(self, 'grid_share', 0) > 1:      # set by MultiTransformer while its stacks run on concurrent streams
+            cfgd['grid_share'] = int(self.grid_share)
         if x.dtype != torch.float32:
             x = x.float()
         return K.encoder_stack(x, mask, self.arena(), cfgd)
@@ -310,6 +312,8 @@ class MultiTransformer(nn.Module):
             if getattr(self, '_side', None) is None or self._side[0].device != dev:
                 self._side = [torch.cuda.Stream(device=dev) for _ in self.mods[1:]]
             xs = [None] * len(self.mods)
+            for mod in self.mods:                     # concurrent stacks share the SMs: half-size grids co-reside (measured -2 %)
+                self.transformer[mod].grid_share = 2
             for i, mod in enumerate(self.mods[1:], 1):
                 s = self._side[i - 1]
                 s.wait_stream(cur)
@@ -320,6 +324,9 @@ class MultiTransformer(nn.Module):
                 cur.wait_stream(s)
                 xs[i].record_stream(cur)
         else:
+            if self.use_encoder:
+                for mod in self.mods:
+                    self.transformer[mod].grid_share = 0
             xs = [self._stack(mod, inputs, mask) for mod in self.mods]
         # [B,T,D] row order goes straight into the recurrence (the reference permutes to [T,B,D] first, :300);
         # the output mask (:310) is applied by the kernel.
