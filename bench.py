@@ -42,7 +42,7 @@ def parse():
     ap.add_argument('--seq', type=int, default=128)
     ap.add_argument('--layers', type=int, default=6)
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
-    ap.add_argument('--cpu-sample', type=int, default=8, help='narratives per CPU-baseline step')
+    ap.add_argument('--cpu-sample', type=int, default=32, help='narratives per CPU-baseline step (the reference trains with batch 25, MFT/train.py:74)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-profile', action='store_true')
     ap.add_argument('--gemm-mode', type=int, default=0, help='tcgen05 GEMM CTAs per SM (tuning; 0 = library default)')
