@@ -238,7 +238,8 @@ int mt_gemm_force_simt(int on);
 int mt_gemm_tc_mode(int mode);
 /* tuning knobs; returns the previous value (-1: bad key).  key 0 / 1 / 2 = grid share of the tcgen05 GEMM / the T <= 128 attention /
  * the LayerNorm kernels: a share s > 1 launches 1/s of the resident CTA slots, so kernels of concurrent streams (the modality stacks
- * of MultiTransformer) co-reside on the SMs instead of queueing behind each other. */
+ * of MultiTransformer) co-reside on the SMs instead of queueing behind each other.  key 3 = programmatic dependent launch of the tcgen05
+ * GEMM (its prologue may overlap the tail of the previous kernel of the stream; default 0: measured gain 0.4 % inside the captured step). */
 int mt_tune(int key, int value);
 /* debug hook: CTA 0 of every tcgen05 GEMM writes per-tile clock64 stamps (8 x uint64 per tile, first 64 tiles: TMA issue, MMA
  * tile start, first operands landed, last k-block landed, epilogue sees the accumulator, accumulator released, last pass

@@ -43,6 +43,7 @@ extern int g_mt_tune[8];
 #define MT_TUNE_GEMM_SHARE 0
 #define MT_TUNE_ATTN_SHARE 1
 #define MT_TUNE_LN_SHARE 2
+#define MT_TUNE_PDL 3          // [3] programmatic dependent launch of the tcgen05 GEMM (prologue overlaps the previous kernel's tail)
 
 static inline size_t mt_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -223,6 +223,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may run while the
+  // previous kernel of the stream is still draining; from here on global memory is touched, so wait for it to complete.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -576,7 +579,13 @@ int launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& g, i
     MT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, F, RES, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN, OCC>::TOTAL));
     attr_set = true;
   }
-  gemm_tc_kernel<BN, F, RES, OCC><<<grid, Smem<BN, OCC>::THREADS, Smem<BN, OCC>::TOTAL, st>>>(ma, mb, g);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Smem<BN, OCC>::THREADS); cfg.dynamicSmemBytes = Smem<BN, OCC>::TOTAL; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = g_mt_tune[MT_TUNE_PDL] ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  MT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, F, RES, OCC>, ma, mb, g));
   MT_LAUNCH_CHECK();
   return MT_OK;
 }
