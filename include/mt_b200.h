@@ -159,6 +159,9 @@ typedef struct {
   int training;           /* keep the stash backward needs */
   float p_gamma, p_out;   /* dropout probs applied in this call (0.2, 0.5 in train mode; pass 0 in eval) */
   uint64_t seed;
+  int bwd_phase;          /* mt_mfn_bwd only: 0 = whole backward; 1 = everything except the batched weight / bias gradients (dx and the
+                             reverse-time recurrences: what upstream layers wait for); 2 = only those weight / bias gradients, which
+                             nothing downstream depends on -- a caller may enqueue phase 2 on another stream once phase 1 is enqueued */
 } MtMfnCfg;
 
 size_t mt_mfn_param_count(const MtMfnCfg* cfg);

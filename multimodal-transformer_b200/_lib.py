@@ -26,7 +26,7 @@ class MtEncoderCfg(Structure):
 class MtMfnCfg(Structure):
     _fields_ = [('B', c_int), ('T', c_int), ('n_mods', c_int), ('in_dim', c_int * MT_MAX_MODS), ('hid', c_int * MT_MAX_MODS),
                 ('mem_dim', c_int), ('h_att1', c_int), ('h_att2', c_int), ('h_gamma', c_int), ('h_out', c_int),
-                ('dtype', c_int), ('training', c_int), ('p_gamma', c_float), ('p_out', c_float), ('seed', c_uint64)]
+                ('dtype', c_int), ('training', c_int), ('p_gamma', c_float), ('p_out', c_float), ('seed', c_uint64), ('bwd_phase', c_int)]
 
 
 class MtLstmHeadCfg(Structure):

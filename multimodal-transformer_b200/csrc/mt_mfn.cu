@@ -961,6 +961,11 @@ int mt_mfn_bwd(const MtMfnCfg* cfg, const float* params, const void* params_lp, 
   const int tiles = (c.B + BT - 1) / BT;
   auto W = [&](size_t off) { return wsel(lp, params, params_lp, off); };
 
+  // cfg->bwd_phase: 0 = everything; 1 = B1-B4 and the input gradients (what the encoder stacks wait for); 2 = only the batched
+  // weight / bias gradients B5 (independent of everything downstream: the caller may run it on another stream after phase 1)
+  const int phase = c.bwd_phase;
+  if (phase < 0 || phase > 2) return MT_ERR_ARG;
+  if (phase != 2) {
   MT_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * D.total, st));
   // B1: head
   {
@@ -1017,7 +1022,13 @@ int mt_mfn_bwd(const MtMfnCfg* cfg, const float* params, const void* params_lp, 
     if (lp && !g_mfn_force_ffma && mt_mfn_mma_lstm_supported(a)) MT_TRY(mt_mfn_mma_lstm_bwd(a, st));
     else MT_REC_LAUNCH(mfn_lstm_bwd_kernel, dim3(tiles, D.n_mods), smem, a);
   }
-  // B5: batched weight gradients over all T*B rows, input gradients
+  for (int m = 0; m < D.n_mods; ++m) {          // input gradients first: the encoder stacks' backward starts from them
+    const void* dzm = op_off(lp, (const void*)S.dz_op, 4 * D.hoff[m]);
+    if (dx && dx[m]) MT_TRY(mt_gemm_run(c.dtype, lin_dgrad(M, 4 * D.H[m], D.D[m], dzm, 4 * Hs, W(D.w_ih[m]), D.D[m], dx[m], D.D[m], !lp), st));
+  }
+  }                                             // phase != 2
+  if (phase == 1) return MT_OK;
+  // B5: batched weight gradients over all T*B rows
   auto wg = [&](const void* dz, int ldz, int Nout, const void* xin, int ldx, int Kin, size_t w_off, int ldw) -> int {
     return mt_gemm_run(c.dtype, mt_wgrad_desc(M, Nout, Kin, dz, ldz, xin, ldx, grads + w_off, ldw), st);
   };
@@ -1028,7 +1039,6 @@ int mt_mfn_bwd(const MtMfnCfg* cfg, const float* params, const void* params_lp, 
     MT_TRY(wg(dzm, 4 * Hs, 4 * D.H[m], op_off(lp, (const void*)S.hprev_op, D.hoff[m]), Hs, D.H[m], D.w_hh[m], D.H[m]));
     MT_TRY(bg(dzm, 4 * Hs, 4 * D.H[m], D.b_ih[m]));
     MT_CUDA(cudaMemcpyAsync(grads + D.b_hh[m], grads + D.b_ih[m], sizeof(float) * 4 * D.H[m], cudaMemcpyDeviceToDevice, st));
-    if (dx && dx[m]) MT_TRY(mt_gemm_run(c.dtype, lin_dgrad(M, 4 * D.H[m], D.D[m], dzm, 4 * Hs, W(D.w_ih[m]), D.D[m], dx[m], D.D[m], !lp), st));
   }
   MT_TRY(wg(S.da1_op, D.A1, D.A1, S.cstar_op, H2, H2, D.att1_fc1.w, H2));             MT_TRY(bg(S.da1_op, D.A1, D.A1, D.att1_fc1.b));
   MT_TRY(wg(S.dlogit_op, H2, H2, S.a1_op, D.A1, D.A1, D.att1_fc2.w, D.A1));           MT_TRY(bg(S.dlogit_op, H2, H2, D.att1_fc2.b));

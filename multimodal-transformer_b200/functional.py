@@ -12,7 +12,8 @@ import torch
 from . import _lib
 from ._lib import ACT_NONE, ACT_RELU, ACT_TANH, MT_BF16, MT_F32, check, lib, ptr, require, stream
 
-_state = {'dtype': MT_F32, 'seed': 0x5EED0000, 'counter': 0, 'fixed_seed': None, 'parallel_stacks': True}
+_state = {'dtype': MT_F32, 'seed': 0x5EED0000, 'counter': 0, 'fixed_seed': None, 'parallel_stacks': True, 'defer_wgrad': False,
+          'pending': [], 'wgrad_stream': {}}
 
 
 def set_compute_dtype(name):
@@ -36,6 +37,23 @@ def set_parallel_stacks(on):
 
 def parallel_stacks():
     return _state['parallel_stacks']
+
+
+def set_deferred_weight_grads(on):
+    """While on, MFN.backward enqueues its batched weight / bias gradients on a side stream and returns as soon as the input
+    gradients are enqueued, so the encoder stacks' backward overlaps them.  The caller MUST call `join_deferred()` on the
+    stream that consumes the parameter gradients (GraphedTrainStep / FlatAdam do) -- plain torch.optim users leave it off."""
+    old = _state['defer_wgrad']
+    _state['defer_wgrad'] = bool(on)
+    return old
+
+
+def join_deferred():
+    """Make the current stream wait for every deferred weight-gradient batch enqueued so far."""
+    cur = torch.cuda.current_stream()
+    for ev in _state['pending']:
+        cur.wait_event(ev)
+    _state['pending'].clear()
 
 
 def manual_seed(seed):
@@ -441,8 +459,31 @@ class MfnFn(torch.autograd.Function):
             sb = (ctypes.c_int64 * n_mods)(*[x.shape[2] * T for x in xs])
             st = (ctypes.c_int64 * n_mods)(*[x.shape[2] for x in xs])
         g = torch.empty(ctx.arena.total, dtype=torch.float32, device=dev)
-        check(lib().mt_mfn_bwd(ctypes.byref(cfg), ptr(flat), ptr(lp), xp, sb, st, ptr(m), ptr(dout), dxp, ptr(g), ptr(ws), ws.numel(),
-                               stream()))
+        if _state['defer_wgrad']:
+            # phase 1 (recurrences + input gradients) here; phase 2 (batched weight / bias gradients, which nothing downstream
+            # reads) on a side stream, joined by join_deferred() before the optimizer touches the gradients
+            cur = torch.cuda.current_stream(dev)
+            side = _state['wgrad_stream'].get(dev)
+            if side is None:
+                side = _state['wgrad_stream'][dev] = torch.cuda.Stream(device=dev)
+            cfg.bwd_phase = 1
+            check(lib().mt_mfn_bwd(ctypes.byref(cfg), ptr(flat), ptr(lp), xp, sb, st, ptr(m), ptr(dout), dxp, ptr(g), ptr(ws), ws.numel(),
+                                   stream()))
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                cfg.bwd_phase = 2
+                check(lib().mt_mfn_bwd(ctypes.byref(cfg), ptr(flat), ptr(lp), xp, sb, st, ptr(m), ptr(dout), dxp, ptr(g), ptr(ws), ws.numel(),
+                                       stream()))
+                ev = torch.cuda.Event()
+                ev.record(side)
+            cfg.bwd_phase = 0
+            for t_ in (g, ws, flat, m, dout, *xs) + ((lp,) if lp is not None else ()):
+                t_.record_stream(side)
+            _state['pending'].append(ev)
+        else:
+            cfg.bwd_phase = 0
+            check(lib().mt_mfn_bwd(ctypes.byref(cfg), ptr(flat), ptr(lp), xp, sb, st, ptr(m), ptr(dout), dxp, ptr(g), ptr(ws), ws.numel(),
+                                   stream()))
         return (None, None, None, None, None, *dxs, *ctx.arena.grad_views(g))
 
 

@@ -92,6 +92,7 @@ class FlatAdam:
 
     def all_reduce_grads(self):
         """SUM the gradients over ranks (the loss is already normalised by the global sum of lengths)."""
+        K.join_deferred()                             # weight gradients still in flight on a side stream (set_deferred_weight_grads)
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
             return
         for a in self._all_arenas():
@@ -190,8 +191,12 @@ class GraphedTrainStep:
         self.model.train()
         pred = self.model(self.x, self.mask, self.lengths)
         loss, dpred = K.mse_loss_sum_normalised_dev(pred.detach(), self.target, self.inv_norm)
-        pred.backward(dpred.view_as(pred))
-        self.opt.step_dev(self.step_t, self.lr)
+        old = K.set_deferred_weight_grads(True)        # MFN weight gradients overlap the encoder stacks' backward
+        try:
+            pred.backward(dpred.view_as(pred))
+        finally:
+            K.set_deferred_weight_grads(old)
+        self.opt.step_dev(self.step_t, self.lr)        # joins the deferred batches first (FlatAdam.all_reduce_grads)
         self.opt.zero_grad()
         return loss
 
