@@ -512,6 +512,39 @@ def test_full_size_properties_batch256():
     assert torch.equal(ps, p1[sub])
 
 
+@pytest.mark.parametrize('B,T,lengths', [(1, 1, [1]), (1, 5, [5]), (2, 3, [3, 1]), (9, 2, [2, 2, 2, 2, 1, 1, 1, 1, 1]), (3, 129, [129, 64, 1])])
+def test_edge_shapes_single_window_single_narrative_ragged(B, T, lengths):
+    """Degenerate and ragged shapes through the whole MFT path (fp32, forward + backward against the oracle): a single window, a single
+    narrative, narratives padded down to one valid window, T just above the whole-head attention limit (129 -> tiled engine in bf16,
+    FFMA here), batch sizes that do not fill a recurrence tile."""
+    N = 1
+    dims = {'acoustic': 88, 'image': 256, 'linguistic': 300}
+    sd = util.filled_sd(util.mods_shapes('MFT.MultiTransformer', N), 77)
+    inputs, _, target, _ = fill.make_batch(B, T, dims, 77)
+    mask = np.zeros((B, T, 1), np.float32)
+    for b, l in enumerate(lengths):
+        mask[b, :l] = 1.0
+    target = target * mask
+    model = mtb.MultiTransformer(MODS, dims, N=N).eval(); model.load_state_dict(sd)
+    sdr = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    predr = O.multi_transformer(sdr, '', {k: t(v).double() for k, v in inputs.items()}, t(mask).double(), MODS, N=N)
+    O.train_loss(predr, t(target).double(), lengths).backward()
+    for mode, tol in (('fp32', 2e-5), ('bf16', None)):
+        mtb.set_compute_dtype(mode)
+        model.zero_grad()
+        pred = model({k: t(v).to(DEV) for k, v in inputs.items()}, t(mask).to(DEV), lengths)
+        (((pred - t(target).to(DEV)) ** 2).sum() / sum(lengths)).backward()
+        assert pred.shape == (B, T, 1) and (pred.detach().cpu() * (1 - t(mask))).abs().max().item() == 0.0
+        if tol is not None:
+            assert_close(pred, predr, tol, 'pred')
+            fl = grad_floor([v.grad for v in sdr.values()])
+            for k, p in model.named_parameters():
+                if p.grad is not None:
+                    assert_close(p.grad, sdr[k].grad, 2e-4, k, 10 * fl)
+        else:
+            assert (pred.detach().float().cpu() - predr.float()).abs().max().item() < 2e-2
+
+
 # ---- train mode with injected masks, bf16 mode, DP-style invariants --------------------------------------------
 def test_mft_train_mode_matches_oracle_with_same_masks():
     N, B, T, seed = 2, 4, 12, 31337
