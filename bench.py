@@ -21,6 +21,7 @@ import time
 # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
 if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', ''):
     os.environ['NCCL_DEBUG'] = 'WARN'
+os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -266,35 +267,48 @@ def run_ours(args, rank, local_rank, world):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item() / steps
 
+    def note(msg):
+        if os.environ.get('MT_BENCH_VERBOSE'):
+            print(f'[bench rank {rank}] {msg}', file=sys.stderr, flush=True)
+
     W, K = max(3, args.warmup), args.steps
+    note('captured')
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
     ms_train = timed(g_train, False, W, K)
     clocks = sampler.stop() if sampler else None
     launches = launches_per_step * K
+    note('train timed')
     ms_inf = timed(g_infer, False, W, K)
+    note('inference timed')
     ms_train_e2e = timed(g_train, True, W, K)
+    note('train e2e timed')
     ms_inf_e2e = timed(g_infer, True, W, K)
+    note('inference e2e timed')
     ms_eager = timed(train_step, False, 2, max(2, min(K, 5)))
+    note('eager timed')
 
     # ---- per-kernel breakdown of the train step (after the timed regions; events after every launch) ---------
     roofline, kernels = None, None
-    if rank == 0 and not args.no_profile:
-        P = peaks()
-        nprof = 1
-        # the host needs ~30 us per launch; a busy-wait kernel in front lets it run ahead so that consecutive event
+    nprof = 1
+    if not args.no_profile:
+        # EVERY rank runs these eager steps (they all-reduce when N > 1); only rank 0 records.
+        # The host needs ~30 us per launch; a busy-wait kernel in front lets it run ahead so that consecutive event
         # records bracket a kernel's true duration instead of the host's enqueue gap
         torch.cuda.synchronize()
         mtb.set_parallel_stacks(False)              # the per-launch profiler times consecutive launches of ONE stream
         train_step(False)                           # un-profiled: lets the caching allocator settle for the one-stream schedule
         torch.cuda.synchronize()
-        _lib.check(L.mt_spin(60.0, _lib.stream()))
-        _lib.check(L.mt_prof_start(20000, _lib.stream()))
+        if rank == 0:
+            _lib.check(L.mt_spin(60.0, _lib.stream()))
+            _lib.check(L.mt_prof_start(20000, _lib.stream()))
         for _ in range(nprof):
             train_step(False)
         torch.cuda.synchronize()
-        n = L.mt_prof_stop()
+        n = L.mt_prof_stop() if rank == 0 else 0
+    if rank == 0 and not args.no_profile:
+        P = peaks()
         import ctypes
         agg = {}
         name = ctypes.create_string_buffer(128)
