@@ -22,15 +22,25 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(int M, const floa
     av[c] = ld4(a + c * 128 + lane * 4);
     bv[c] = ld4(b + c * 128 + lane * 4);
   }
-  for (int row = blockIdx.x * LN_WARPS + warp; row < M; row += gridDim.x * LN_WARPS) {
-    const float* xr = x + (size_t)row * d;
+  // software pipeline: the next row is in flight while this one goes through its two dependent warp reductions
+  const int stride = gridDim.x * LN_WARPS;
+  int row = blockIdx.x * LN_WARPS + warp;
+  float4 nv[NCH];
+  if (row < M) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) nv[c] = ld4(x + (size_t)row * d + c * 128 + lane * 4);
+  }
+  for (; row < M; row += stride) {
     float4 v[NCH];
     float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      v[c] = ld4(xr + c * 128 + lane * 4);
-      s += (v[c].x + v[c].y) + (v[c].z + v[c].w);
+    for (int c = 0; c < NCH; ++c) v[c] = nv[c];
+    if (row + stride < M) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) nv[c] = ld4(x + (size_t)(row + stride) * d + c * 128 + lane * 4);
     }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) s += (v[c].x + v[c].y) + (v[c].z + v[c].w);
     const float mean = warp_sum(s) * (1.0f / d);
     float q = 0.f;
 #pragma unroll

@@ -41,3 +41,8 @@ bool mt_gemm_tc_supported(const GemmDesc& g);
 
 // column sums: out[n] (+)= sum_m X[m*ldx + n] * (gate ? ...)   -- bias gradients
 int mt_colsum_run(int x_is_bf16, int M, int N, const void* X, int ldx, float* out, int accumulate, cudaStream_t st);
+
+// several column-sum jobs over tensors with the same number of rows in one launch (outputs are ACCUMULATED)
+#define MT_COLSUM_MAX_JOBS 16
+struct ColsumJob { const void* X; int ldx; int N; float* out; };
+int mt_colsum_multi_run(int x_is_bf16, int M, const ColsumJob* jobs, int n_jobs, cudaStream_t st);

@@ -208,7 +208,74 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(int M, int N, const T* 
   }
 }
 
+// several column-sum jobs of the same row count in ONE launch (blockIdx.z = job): the MFN backward has a dozen small bias
+// gradients whose individual launches cost more than their memory traffic
+struct ColsumJobs { ColsumJob j[MT_COLSUM_MAX_JOBS]; };
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_multi_kernel(int M, ColsumJobs jobs, int rows_per_block) {
+  __shared__ float4 red[8][32];
+  const ColsumJob jb = jobs.j[blockIdx.z];
+  const T* X = reinterpret_cast<const T*>(jb.X);
+  const int N = jb.N, ldx = jb.ldx;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 128 + tx * 4;
+  if (blockIdx.x * 128 >= N) return;                      // CTA-uniform
+  const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n < N) {
+    int m = m0 + ty;
+    for (; m + 24 < m1; m += 32) {
+      float4 a = ld4(X + (size_t)m * ldx + n), b = ld4(X + (size_t)(m + 8) * ldx + n);
+      float4 c = ld4(X + (size_t)(m + 16) * ldx + n), d = ld4(X + (size_t)(m + 24) * ldx + n);
+      s.x += (a.x + b.x) + (c.x + d.x); s.y += (a.y + b.y) + (c.y + d.y);
+      s.z += (a.z + b.z) + (c.z + d.z); s.w += (a.w + b.w) + (c.w + d.w);
+    }
+    for (; m < m1; m += 8) {
+      float4 a = ld4(X + (size_t)m * ldx + n);
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+    }
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+#pragma unroll
+    for (int q = 1; q < 8; ++q) { float4 o = red[q][tx]; s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w; }
+    atomicAdd(jb.out + n, s.x); atomicAdd(jb.out + n + 1, s.y); atomicAdd(jb.out + n + 2, s.z); atomicAdd(jb.out + n + 3, s.w);
+  }
+}
+
 }  // namespace
+
+// out_j[n] += sum_m X_j[m * ldx_j + n] for up to MT_COLSUM_MAX_JOBS tensors with M rows each (N_j % 4 == 0, 16-byte aligned rows)
+int mt_colsum_multi_run(int x_is_bf16, int M, const ColsumJob* jobs, int n_jobs, cudaStream_t st) {
+  if (n_jobs <= 0) return MT_OK;
+  if (n_jobs > MT_COLSUM_MAX_JOBS) return MT_ERR_ARG;
+  const size_t es = x_is_bf16 ? 2 : 4;
+  ColsumJobs J;
+  int maxN = 0;
+  double bytes = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    const ColsumJob& b = jobs[i];
+    if (b.N % 4 != 0 || b.ldx % 4 != 0 || ((uintptr_t)b.X % (4 * es)) != 0) {       // odd shape: one job at a time
+      for (int k = 0; k < n_jobs; ++k) MT_TRY(mt_colsum_run(x_is_bf16, M, jobs[k].N, jobs[k].X, jobs[k].ldx, jobs[k].out, 1, st));
+      return MT_OK;
+    }
+    J.j[i] = b;
+    maxN = b.N > maxN ? b.N : maxN;
+    bytes += (double)M * b.N * es;
+  }
+  const int gx = (maxN + 127) / 128;
+  int gy = (148 * 4 + gx * n_jobs - 1) / (gx * n_jobs);
+  if (gy < 1) gy = 1;
+  int rpb = ((M + gy - 1) / gy + 31) / 32 * 32;
+  if (rpb < 64) rpb = 64;
+  dim3 grid(gx, (M + rpb - 1) / rpb, n_jobs);
+  mt_prof_work(0.0, bytes);
+  if (x_is_bf16) colsum_multi_kernel<bf16><<<grid, 256, 0, st>>>(M, J, rpb);
+  else colsum_multi_kernel<float><<<grid, 256, 0, st>>>(M, J, rpb);
+  MT_LAUNCH_CHECK();
+  return MT_OK;
+}
 
 int mt_gemm_simt_run(int dtype, const GemmDesc& d, cudaStream_t st) {
   if (d.M <= 0 || d.N <= 0 || d.K <= 0 || !d.A || !d.B || !d.C) return MT_ERR_ARG;

@@ -1032,13 +1032,19 @@ int mt_mfn_bwd(const MtMfnCfg* cfg, const float* params, const void* params_lp, 
   auto wg = [&](const void* dz, int ldz, int Nout, const void* xin, int ldx, int Kin, size_t w_off, int ldw) -> int {
     return mt_gemm_run(c.dtype, mt_wgrad_desc(M, Nout, Kin, dz, ldz, xin, ldx, grads + w_off, ldw), st);
   };
-  auto bg = [&](const void* dz, int ldz, int Nout, size_t b_off) -> int { return mt_colsum_run(lp, M, Nout, dz, ldz, grads + b_off, 1, st); };
+  // bias gradients = column sums of the pre-activation gradients: collected and issued as ONE launch at the end
+  ColsumJob cjobs[MT_COLSUM_MAX_JOBS];
+  int n_cjobs = 0;
+  auto bg = [&](const void* dz, int ldz, int Nout, size_t b_off) -> int {
+    if (n_cjobs == MT_COLSUM_MAX_JOBS) return MT_ERR_ARG;
+    cjobs[n_cjobs++] = ColsumJob{dz, ldz, Nout, grads + b_off};
+    return MT_OK;
+  };
   for (int m = 0; m < D.n_mods; ++m) {
     const void* dzm = op_off(lp, (const void*)S.dz_op, 4 * D.hoff[m]);
     MT_TRY(wg(dzm, 4 * Hs, 4 * D.H[m], x[m], D.D[m], D.D[m], D.w_ih[m], D.D[m]));
     MT_TRY(wg(dzm, 4 * Hs, 4 * D.H[m], op_off(lp, (const void*)S.hprev_op, D.hoff[m]), Hs, D.H[m], D.w_hh[m], D.H[m]));
     MT_TRY(bg(dzm, 4 * Hs, 4 * D.H[m], D.b_ih[m]));
-    MT_CUDA(cudaMemcpyAsync(grads + D.b_hh[m], grads + D.b_ih[m], sizeof(float) * 4 * D.H[m], cudaMemcpyDeviceToDevice, st));
   }
   MT_TRY(wg(S.da1_op, D.A1, D.A1, S.cstar_op, H2, H2, D.att1_fc1.w, H2));             MT_TRY(bg(S.da1_op, D.A1, D.A1, D.att1_fc1.b));
   MT_TRY(wg(S.dlogit_op, H2, H2, S.a1_op, D.A1, D.A1, D.att1_fc2.w, D.A1));           MT_TRY(bg(S.dlogit_op, H2, H2, D.att1_fc2.b));
@@ -1054,6 +1060,9 @@ int mt_mfn_bwd(const MtMfnCfg* cfg, const float* params, const void* params_lp, 
   MT_TRY(wg(S.dzg_op, 2 * MEM, MEM, S.gh_op, 2 * G, G, D.g1_fc2.w, G));               MT_TRY(bg(S.dzg_op, 2 * MEM, MEM, D.g1_fc2.b));
   MT_TRY(wg(dzg2, 2 * MEM, MEM, gh2, 2 * G, G, D.g2_fc2.w, G));                       MT_TRY(bg(dzg2, 2 * MEM, MEM, D.g2_fc2.b));
   MT_TRY(wg(S.dzoh_op, D.O, D.O, S.last_op, Hs + MEM, Hs + MEM, D.out_fc1.w, Hs + MEM));   MT_TRY(bg(S.dzoh_op, D.O, D.O, D.out_fc1.b));
+  MT_TRY(mt_colsum_multi_run(lp, M, cjobs, n_cjobs, st));
+  for (int m = 0; m < D.n_mods; ++m)            // b_hh enters the gates exactly like b_ih: same gradient
+    MT_CUDA(cudaMemcpyAsync(grads + D.b_hh[m], grads + D.b_ih[m], sizeof(float) * 4 * D.H[m], cudaMemcpyDeviceToDevice, st));
   return MT_OK;
 }
 
