@@ -392,6 +392,7 @@ def run_ours(args, rank, local_rank, world):
         gstep.graph = None
         gfwd.graph = None
         torch.cuda.synchronize()
+        opt.close()                                  # the library's own NCCL communicator (mt_comm_*)
         watchdog = threading.Timer(20.0, lambda: os._exit(0))
         watchdog.daemon = True
         watchdog.start()

@@ -131,6 +131,7 @@ typedef struct {
 } MtEncoderCfg;
 
 size_t mt_encoder_param_count(int d, int dff, int n_layers);
+/* mt_encoder_stack_fwd / _bwd (the names proposed in SURVEY 8(b)) are aliases of mt_encoder_fwd / _bwd. */
 size_t mt_encoder_ws_bytes(const MtEncoderCfg* cfg);
 int mt_encoder_fwd(const MtEncoderCfg* cfg, const float* params, const void* params_lp, const float* x,
                    const float* mask, void* y, void* ws, size_t ws_bytes, void* stream);
@@ -138,6 +139,11 @@ int mt_encoder_fwd(const MtEncoderCfg* cfg, const float* params, const void* par
 int mt_encoder_bwd(const MtEncoderCfg* cfg, const float* params, const void* params_lp, const float* x,
                    const float* mask, const void* dy, float* dx, float* grads, void* ws, size_t ws_bytes,
                    void* stream);
+int mt_encoder_stack_fwd(const MtEncoderCfg* cfg, const float* params, const void* params_lp, const float* x,
+                         const float* mask, void* y, void* ws, size_t ws_bytes, void* stream);
+int mt_encoder_stack_bwd(const MtEncoderCfg* cfg, const float* params, const void* params_lp, const float* x,
+                         const float* mask, const void* dy, float* dx, float* grads, void* ws, size_t ws_bytes,
+                         void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Memory Fusion Network: MFN.forward MFT/multiTransformer.py:181-248 (LSTHM cells :208, delta-memory
@@ -227,6 +233,18 @@ int mt_adam_step_dev(float* p, const float* g, float* m, float* v, size_t n, con
 int mt_set_seed_offset_ptr(const uint64_t* dev_ptr);
 /* Busy-wait kernel (ms <= 2000): lets the host run ahead of the device so per-launch event timings are back to back. */
 int mt_spin(float ms, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange (the reference has no distributed code): one process per GPU, narratives sharded over
+ * ranks, ONE grouped NCCL all-reduce (SUM, fp32) over the flat gradient arenas per step, enqueued on the caller's stream (capturable).
+ * NCCL is resolved at run time from the libnccl.so.2 already loaded in the process; mt_comm_available() == 0 when there is none.
+ * Rank 0 calls mt_comm_unique_id, the host broadcasts the 128 bytes, every rank calls mt_comm_init (collective) on its own device.
+ * ------------------------------------------------------------------------------------------------- */
+int mt_comm_available(void);
+int mt_comm_unique_id(char* id128);
+int mt_comm_init(const char* id128, int rank, int world, void** comm);
+int mt_comm_destroy(void* comm);
+int mt_allreduce_grads(void* comm, float* const* bufs, const size_t* counts, int n_bufs, void* stream);
 
 /* Generic GEMM (exposed for tests and profiling):  C[M,N] = A·B^T-style contraction, see csrc/mt_gemm.cuh.
  * a_kmajor: A element (m,k) at A[m*lda+k] (else A[k*lda+m]); b_kmajor: B element (n,k) at B[n*ldb+k] (else B[k*ldb+n]). */

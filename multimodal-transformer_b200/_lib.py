@@ -61,6 +61,13 @@ _PROTOS = {
     'mt_encoder_ws_bytes': (c_size_t, [POINTER(MtEncoderCfg)]),
     'mt_encoder_fwd': (c_int, [POINTER(MtEncoderCfg), P, P, P, P, P, P, c_size_t, P]),
     'mt_encoder_bwd': (c_int, [POINTER(MtEncoderCfg), P, P, P, P, P, P, P, P, c_size_t, P]),
+    'mt_encoder_stack_fwd': (c_int, [POINTER(MtEncoderCfg), P, P, P, P, P, P, c_size_t, P]),
+    'mt_encoder_stack_bwd': (c_int, [POINTER(MtEncoderCfg), P, P, P, P, P, P, P, P, c_size_t, P]),
+    'mt_comm_available': (c_int, []),
+    'mt_comm_unique_id': (c_int, [c_char_p]),
+    'mt_comm_init': (c_int, [c_char_p, c_int, c_int, POINTER(c_void_p)]),
+    'mt_comm_destroy': (c_int, [P]),
+    'mt_allreduce_grads': (c_int, [P, POINTER(c_void_p), POINTER(c_size_t), c_int, P]),
     'mt_mfn_param_count': (c_size_t, [POINTER(MtMfnCfg)]),
     'mt_mfn_ws_bytes': (c_size_t, [POINTER(MtMfnCfg)]),
     'mt_mfn_fwd': (c_int, [POINTER(MtMfnCfg), P, P, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int64), P, P, P, P, P, P, c_size_t, P]),

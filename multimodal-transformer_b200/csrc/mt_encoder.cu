@@ -283,6 +283,15 @@ int mt_encoder_bwd(const MtEncoderCfg* cfg, const float* params, const void* par
   return MT_OK;
 }
 
+int mt_encoder_stack_fwd(const MtEncoderCfg* cfg, const float* params, const void* params_lp, const float* x, const float* mask, void* y,
+                         void* ws, size_t ws_bytes, void* stream) {
+  return mt_encoder_fwd(cfg, params, params_lp, x, mask, y, ws, ws_bytes, stream);
+}
+int mt_encoder_stack_bwd(const MtEncoderCfg* cfg, const float* params, const void* params_lp, const float* x, const float* mask,
+                         const void* dy, float* dx, float* grads, void* ws, size_t ws_bytes, void* stream) {
+  return mt_encoder_bwd(cfg, params, params_lp, x, mask, dy, dx, grads, ws, ws_bytes, stream);
+}
+
 // ------------------------------------------------------------------------------------------------------
 // Linear.  W is always the fp32 master weight [N,K]; in bf16 mode it is cast (and K-padded to a multiple of 8
 // so rows are 16-byte aligned for TMA) into the workspace on every call -- these matrices are tiny.

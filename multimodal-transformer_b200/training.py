@@ -70,6 +70,7 @@ class FlatAdam:
         self.step_count = 0
         self.state = {}          # id(arena) -> (m, v)
         self.misc = None
+        self._comm_tried, self._comm_handle = False, None
         self.param_groups = [dict(lr=lr)]      # ReduceLROnPlateau-style schedulers poke this
 
     def _all_arenas(self):
@@ -90,19 +91,62 @@ class FlatAdam:
             g = torch.cat([p.grad.reshape(-1) for p in arena.params])
         return g
 
+    def _comm(self, device):
+        """The library's own NCCL communicator (C ABI: mt_comm_init / mt_allreduce_grads), created on first use from a unique id
+        that rank 0 broadcasts through torch.distributed.  None when unavailable (no NCCL in the process, sub-groups, CPU)."""
+        if self._comm_tried:
+            return self._comm_handle
+        self._comm_tried = True
+        import ctypes
+        from . import _lib
+        L = _lib.lib()
+        if self.group is not None or device.type != 'cuda' or dist.get_backend() != 'nccl' or not L.mt_comm_available():
+            return None
+        idbuf = ctypes.create_string_buffer(128)
+        if dist.get_rank() == 0:
+            _lib.check(L.mt_comm_unique_id(idbuf))
+        t = torch.frombuffer(bytearray(idbuf.raw), dtype=torch.uint8).to(device)
+        dist.broadcast(t, 0)
+        idbuf = ctypes.create_string_buffer(bytes(t.cpu().numpy().tobytes()), 128)
+        handle = ctypes.c_void_p()
+        torch.cuda.synchronize(device)
+        _lib.check(L.mt_comm_init(idbuf, dist.get_rank(), dist.get_world_size(), ctypes.byref(handle)))
+        self._comm_handle = handle
+        return handle
+
+    def close(self):
+        """Destroy the library communicator (call before torch.distributed.destroy_process_group)."""
+        if getattr(self, '_comm_handle', None) is not None:
+            from . import _lib
+            _lib.lib().mt_comm_destroy(self._comm_handle)
+            self._comm_handle = None
+
     def all_reduce_grads(self):
-        """SUM the gradients over ranks (the loss is already normalised by the global sum of lengths)."""
+        """SUM the gradients over ranks (the loss is already normalised by the global sum of lengths): ONE grouped NCCL all-reduce
+        over every flat gradient arena through the C ABI (mt_allreduce_grads), torch.distributed otherwise."""
         K.join_deferred()                             # weight gradients still in flight on a side stream (set_deferred_weight_grads)
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
             return
+        flats, gathered = [], []
         for a in self._all_arenas():
             g = self._flat_grad(a)
             if g is None:
                 continue
+            (flats if a.flat_grad() is not None else gathered).append((a, g))
+        comm = self._comm(flats[0][1].device) if flats else None
+        if comm is not None:
+            import ctypes
+            from . import _lib
+            n = len(flats)
+            bufs = (ctypes.c_void_p * n)(*[g.data_ptr() for _, g in flats])
+            counts = (ctypes.c_size_t * n)(*[g.numel() for _, g in flats])
+            _lib.check(_lib.lib().mt_allreduce_grads(comm, bufs, counts, n, _lib.stream()))
+        else:
+            all_reduce_flat_([g for _, g in flats], self.group)
+        for a, g in gathered:                         # gradients that do not live in one flat buffer: reduce a packed copy, scatter back
             all_reduce_flat_([g], self.group)
-            if a.flat_grad() is None:          # gathered copy: scatter back
-                for p, v in zip(a.params, a.grad_views(g)):
-                    p.grad.copy_(v)
+            for p, v in zip(a.params, a.grad_views(g)):
+                p.grad.copy_(v)
 
     @torch.no_grad()
     def step(self):
