@@ -308,7 +308,7 @@ inline int ew_grid(size_t n, int threads) {
 template <typename TY>
 int ln_fwd_dispatch(int M, int d, const float* x, const float* a, const float* b, float eps, TY* y, cudaStream_t st) {
   int grid = (M + LN_WARPS - 1) / LN_WARPS;
-  if (grid > 148 * 8 / (g_mt_tune[MT_TUNE_LN_SHARE] > 1 ? g_mt_tune[MT_TUNE_LN_SHARE] : 1)) grid = 148 * 8 / (g_mt_tune[MT_TUNE_LN_SHARE] > 1 ? g_mt_tune[MT_TUNE_LN_SHARE] : 1);
+  if (grid > 148 * 4 / (g_mt_tune[MT_TUNE_LN_SHARE] > 1 ? g_mt_tune[MT_TUNE_LN_SHARE] : 1)) grid = 148 * 4 / (g_mt_tune[MT_TUNE_LN_SHARE] > 1 ? g_mt_tune[MT_TUNE_LN_SHARE] : 1);
   mt_prof_work(0.0, (double)M * d * (4.0 + sizeof(TY)));
   switch (d / 128) {
     case 1: ln_fwd_kernel<TY, 1><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, b, eps, y); break;
@@ -327,7 +327,7 @@ template <typename TY, bool NEXT>
 int ln_bwd_dispatch(int M, int d, const float* x, const float* a, float eps, const TY* dy, const float* dres, float* dx, float* da,
                     float* db, TY* nx_out, float* nx_db, DropCfg nx_drop, cudaStream_t st) {
   int grid = (M + LN_WARPS - 1) / LN_WARPS;
-  if (grid > 148 * 4 / (g_mt_tune[MT_TUNE_LN_SHARE] > 1 ? g_mt_tune[MT_TUNE_LN_SHARE] : 1)) grid = 148 * 4 / (g_mt_tune[MT_TUNE_LN_SHARE] > 1 ? g_mt_tune[MT_TUNE_LN_SHARE] : 1);
+  if (grid > 148 * 2 / (g_mt_tune[MT_TUNE_LN_SHARE] > 1 ? g_mt_tune[MT_TUNE_LN_SHARE] : 1)) grid = 148 * 2 / (g_mt_tune[MT_TUNE_LN_SHARE] > 1 ? g_mt_tune[MT_TUNE_LN_SHARE] : 1);
   mt_prof_work(0.0, (double)M * d * (8.0 + sizeof(TY) + (dres ? 4.0 : 0.0) + (NEXT ? sizeof(TY) : 0.0)));
 #define MT_LNB(NCH) ln_bwd_kernel<TY, NCH, NEXT><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, eps, dy, dres, dx, da, db, nx_out, nx_db, nx_drop)
   switch (d / 128) {
