@@ -219,6 +219,28 @@ __global__ void cast2d_kernel(const TS* __restrict__ src, int lds, TD* __restric
   }
 }
 
+// vectorised cast2d: 4 columns per thread (cols, lds, ldd multiples of 4; 16-byte aligned rows); pad columns [cols, ldd) are zeroed
+template <typename TS, typename TD>
+__global__ void cast2d_vec_kernel(const TS* __restrict__ src, int lds, TD* __restrict__ dst, int ldd, int rows, int cols, DropCfg drop_in) {
+  const DropCfg drop = mt_drop_resolve(drop_in);
+  const int qpr = ldd >> 2;                                   // quads per destination row
+  const size_t n = (size_t)rows * qpr;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / qpr), c = (int)(i - (size_t)r * qpr) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < cols) {
+      v = ld4(src + (size_t)r * lds + c);
+      if (drop.thresh != 0u) {
+        float f[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) f[k] = mt_drop_factor(drop, (uint64_t)r * cols + c + k);
+        v.x *= f[0]; v.y *= f[1]; v.z *= f[2]; v.w *= f[3];
+      }
+    }
+    st4(dst + (size_t)r * ldd + c, v);
+  }
+}
+
 template <typename TG, typename TY, typename TZ>
 __global__ void act_bwd_kernel(size_t n, int N, const TG* __restrict__ dy, const TY* __restrict__ y, int act,
                                const float* __restrict__ rowmask, TZ* __restrict__ dz) {
@@ -379,6 +401,17 @@ int mt_cast2d_run(const void* src, bool src_bf16, int lds, void* dst, bool dst_b
                   cudaStream_t st) {
   if (rows <= 0 || cols <= 0 || ldd < cols || lds < cols) return MT_ERR_ARG;
   size_t n = (size_t)rows * ldd;
+  const size_t ses = src_bf16 ? 2 : 4, des = dst_bf16 ? 2 : 4;
+  if (cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && ((uintptr_t)src % (4 * ses)) == 0 && ((uintptr_t)dst % (4 * des)) == 0) {
+    const int gridv = ew_grid(n / 4, 256);
+    mt_prof_work(0.0, (double)rows * cols * ses + (double)n * des);
+    if (!src_bf16 && dst_bf16) cast2d_vec_kernel<float, bf16><<<gridv, 256, 0, st>>>((const float*)src, lds, (bf16*)dst, ldd, rows, cols, drop);
+    else if (!src_bf16 && !dst_bf16) cast2d_vec_kernel<float, float><<<gridv, 256, 0, st>>>((const float*)src, lds, (float*)dst, ldd, rows, cols, drop);
+    else if (src_bf16 && dst_bf16) cast2d_vec_kernel<bf16, bf16><<<gridv, 256, 0, st>>>((const bf16*)src, lds, (bf16*)dst, ldd, rows, cols, drop);
+    else cast2d_vec_kernel<bf16, float><<<gridv, 256, 0, st>>>((const bf16*)src, lds, (float*)dst, ldd, rows, cols, drop);
+    MT_LAUNCH_CHECK();
+    return MT_OK;
+  }
   int grid = ew_grid(n, 256);
   if (!src_bf16 && dst_bf16) cast2d_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)src, lds, (bf16*)dst, ldd, rows, cols, drop);
   else if (!src_bf16 && !dst_bf16) cast2d_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, lds, (float*)dst, ldd, rows, cols, drop);
