@@ -199,7 +199,9 @@ class GraphedTrainStep:
         step = GraphedTrainStep(model, opt, B, T, {mod: in_dim}, device)
         loss = step(inputs, mask, target, lengths)          # tensors on host (pinned) or device; returns loss [1] on device
 
-    Re-create it after load_state_dict() or a change of model.train()/dtype (the graph bakes addresses and modes)."""
+    Re-create it after load_state_dict() or a change of model.train()/dtype (the graph bakes addresses and modes).
+    If the model was trained eagerly on the default stream before, drop every reference to those iterations' outputs / losses first
+    (they keep autograd AccumulateGrad nodes alive that are bound to the legacy stream, which a capturing stream may not touch)."""
 
     def __init__(self, model, opt, B, T, in_dims, device, norm_fn=None, warmup=3):
         from . import _lib
@@ -273,8 +275,16 @@ class GraphedTrainStep:
             torch.cuda.synchronize(self.device)
             opt.step_count = count0
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self.loss = self._step()
+            try:
+                with torch.cuda.graph(self.graph):
+                    self.loss = self._step()
+            except RuntimeError as e:
+                self.graph = None
+                if 'legacy stream' in str(e) or 'StreamCapture' in str(e):
+                    raise RuntimeError('CUDA-graph capture of the train step failed because an autograd graph of an earlier EAGER iteration '
+                                       'is still alive (its AccumulateGrad nodes are bound to the default stream): delete the references to '
+                                       'earlier outputs / losses (del out, loss) and call zero_grad(set_to_none=True) before capturing') from e
+                raise
         finally:
             self._lib.check(L.mt_set_seed_offset_ptr(None))      # eager calls keep their value seeds
         return self
