@@ -594,6 +594,27 @@ def test_bf16_mode_valence_within_2e2_and_ccc():
         assert abs(c_ref - c_16) < 1.5e-3, (b, c_ref, c_16)
 
 
+@pytest.mark.parametrize('name,cls,fin,inv', [('sft', 'NLPTransformer', 512, 'SFT.NLPTransformer'), ('unifull', 'UniFullTransformer', 556, 'MFT.UniFullTransformer'),
+                                              ('uni', 'UniTransformer', 300, 'MFT.UniTransformer')])
+def test_bf16_mode_other_models_within_2e2(name, cls, fin, inv):
+    """bf16 mode on the SFT / B2-Trans / Uni bodies (encoder stack + LSTM decoder with output feedback or MLP head): prediction within
+    2e-2 of the fp32 path (itself pinned to the reference's golden outputs in test_sft_golden / test_uni_golden), backward finite."""
+    N, B, T = 2, 4, 24
+    sd = util.filled_sd(util.mods_shapes(inv, N), 17)
+    inputs, mask, target, lengths = fill.make_batch(B, T, {'x': fin}, 17)
+    x = t(inputs['x']).to(DEV); m = t(mask).to(DEV)
+    preds = {}
+    for mode in ('fp32', 'bf16'):
+        mtb.set_compute_dtype(mode)
+        model = getattr(mtb, cls)(fin, N=N).eval(); model.load_state_dict(sd)
+        pred = model(x, m, lengths)
+        (((pred - t(target).to(DEV)) ** 2).sum() / sum(lengths)).backward()
+        preds[mode] = pred.detach().float().cpu()
+        for k, p in model.named_parameters():
+            assert p.grad is not None and torch.isfinite(p.grad).all(), (mode, k)
+    assert (preds['bf16'] - preds['fp32']).abs().max().item() < 2e-2
+
+
 def test_bf16_train_step_runs_and_grads_are_close():
     N, B, T = 2, 4, 16
     dims = {'acoustic': 88, 'image': 256, 'linguistic': 300}
