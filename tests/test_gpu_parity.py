@@ -184,7 +184,9 @@ def test_attention_fwd_bwd(B, T, d, h, p):
 
 @pytest.mark.parametrize('B,T,d,h,p', [(2, 128, 256, 8, 0.0), (3, 37, 256, 8, 0.1), (2, 200, 128, 8, 0.0), (2, 70, 512, 8, 0.1),
                                        (1, 64, 256, 8, 0.1), (2, 130, 256, 8, 0.0), (3, 128, 256, 8, 0.1), (2, 1, 128, 8, 0.0),
-                                       (2, 125, 128, 8, 0.1), (2, 9, 512, 8, 0.1)])
+                                       (2, 125, 128, 8, 0.1), (2, 9, 512, 8, 0.1),
+                                       # more (narrative, head) items than resident CTAs: the persistent loops and their prefetch pipelines
+                                       (48, 128, 256, 8, 0.1), (40, 100, 256, 8, 0.1)])
 def test_attention_tensor_core_engine_bf16(B, T, d, h, p):
     """bf16 mode: the mma.sync engine against the fp64 oracle on the same bf16-rounded inputs and the same dropout
     masks, and against the FFMA engine."""
