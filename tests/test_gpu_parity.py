@@ -103,6 +103,28 @@ def test_gemm_tcgen05_vs_fp64(M, N, K, akm, bkm, c_f32):
     assert_close(C, want, 1e-5 if c_f32 else 6e-3)
 
 
+@pytest.mark.parametrize('M,N,K,c_f32', [(65536, 256, 256, 1), (50000, 768, 256, 0), (65536, 128, 128, 0), (40000, 256, 768, 0)])
+@pytest.mark.parametrize('mode', [2, 1, 0])
+def test_gemm_tcgen05_many_tiles_per_cta(M, N, K, c_f32, mode):
+    """Persistent-loop coverage: several output tiles per CTA (TMEM accumulator hand-off, ring wrap-around, ragged last row tile) in
+    every kernel configuration (mode 2 = two streaming CTAs per SM, the default; 1 = weight-resident one CTA per SM; 0 = 256-wide
+    tiles), against a torch fp32 matmul of the same bf16 operands on the GPU."""
+    L = _lib.lib()
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g, device=DEV).bfloat16(); B = (torch.randn(N, K, generator=g, device=DEV) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, generator=g, device=DEV)
+    want = A.float() @ B.float().t() + bias
+    C = torch.full((M, N), float('nan'), device=DEV, dtype=torch.float32 if c_f32 else torch.bfloat16)
+    old = L.mt_gemm_tc_mode(mode)
+    try:
+        _lib.check(L.mt_gemm(1, M, N, K, _lib.ptr(A), K, 1, _lib.ptr(B), K, 1, _lib.ptr(C), N, c_f32, _lib.ptr(bias), 0, 1, None))
+        torch.cuda.synchronize()
+    finally:
+        L.mt_gemm_tc_mode(old)
+    err = (C.float() - want).abs().max().item()
+    assert err <= (2e-4 if c_f32 else 4e-2) * max(1.0, want.abs().max().item()), err
+
+
 def test_gemm_tcgen05_matches_ffma_engine_with_full_epilogue():
     """The encoder's fused epilogues (bias, relu, dropout, residual) through both engines: same bf16 inputs, same
     dropout masks -> results agree to fp32 accumulation-order noise."""
