@@ -166,6 +166,24 @@ def test_layernorm_fwd_bwd(d):
     assert_close(ln.a_2.grad, ar.grad, 1e-5, 'da'); assert_close(ln.b_2.grad, br.grad, 1e-5, 'db')
 
 
+def test_layernorm_many_rows_per_warp():
+    """The software-pipelined grid-stride loops of the LayerNorm kernels (dozens of rows per warp, ragged tail) against the oracle
+    formula evaluated with torch on the GPU in fp64."""
+    d, M = 256, 40003
+    g = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.randn(M, d, generator=g, device=DEV) * 2 + 0.3
+    a = torch.randn(d, generator=g, device=DEV); b = torch.randn(d, generator=g, device=DEV); dy = torch.randn(M, d, generator=g, device=DEV)
+    xr = x.double().requires_grad_(True); ar = a.double().requires_grad_(True); br = b.double().requires_grad_(True)
+    yr = O.layer_norm(xr, ar, br); yr.backward(dy.double())
+    ln = mtb.LayerNorm(d).to(DEV)
+    with torch.no_grad():
+        ln.a_2.copy_(a); ln.b_2.copy_(b)
+    xd = x.clone().requires_grad_(True)
+    y = ln(xd); y.backward(dy)
+    assert_close(y, yr, 1e-5, 'y'); assert_close(xd.grad, xr.grad, 1e-5, 'dx')
+    assert_close(ln.a_2.grad, ar.grad, 2e-5, 'da'); assert_close(ln.b_2.grad, br.grad, 2e-5, 'db')
+
+
 def test_layernorm_golden():
     gold = util.gold('ln')
     sd = util.filled_sd({'a_2': (256,), 'b_2': (256,)}, 3)
