@@ -613,6 +613,40 @@ def test_mft_train_mode_matches_oracle_with_same_masks():
         assert_close(p.grad, sdr[k].grad, 2e-4, k, fl)
 
 
+def test_mft_train_mode_medium_batch_both_dtypes_same_masks():
+    """Train mode (dropout on, the SAME counter-based masks in the oracle) at a size where every persistent kernel walks several
+    work items: 40 narratives x 128 windows = 320 (narrative, head) attention items, 40 GEMM row tiles, 5 recurrence tiles.
+    fp32 mode: 2e-5 / 3e-4 against the fp64 oracle; bf16 mode: valence within 2e-2, every gradient's cosine > 0.97."""
+    N, B, T, seed = 1, 40, 128, 4711
+    dims = {'acoustic': 88, 'image': 256, 'linguistic': 300}
+    sd = util.filled_sd(util.mods_shapes('MFT.MultiTransformer', N), 23)
+    inputs, mask, target, lengths = fill.make_batch(B, T, dims, 23)
+    sdr = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    predr = O.multi_transformer(sdr, '', {k: t(v).double() for k, v in inputs.items()}, t(mask).double(), MODS, N=N, drop=Dropper(seed))
+    O.train_loss(predr, t(target).double(), lengths).backward()
+    fl = grad_floor([v.grad for v in sdr.values()])
+    for mode in ('fp32', 'bf16'):
+        mtb.set_compute_dtype(mode)
+        model = mtb.MultiTransformer(MODS, dims, N=N).train(); model.load_state_dict(sd)
+        mtb.fix_seed(seed)
+        pred = model({k: t(v).to(DEV) for k, v in inputs.items()}, t(mask).to(DEV), lengths)
+        (((pred - t(target).to(DEV)) ** 2).sum() / sum(lengths)).backward()
+        if mode == 'fp32':
+            assert_close(pred, predr, 2e-5, 'pred')
+        else:
+            assert (pred.detach().float().cpu() - predr.float()).abs().max().item() < 2e-2
+        for k, p in model.named_parameters():
+            want = sdr[k].grad
+            if want is None:
+                assert p.grad is None
+                continue
+            if mode == 'fp32':
+                assert_close(p.grad, want, 3e-4, k, fl)
+            elif want.norm() > 100 * fl:
+                cos = torch.nn.functional.cosine_similarity(p.grad.double().cpu().flatten(), want.flatten(), dim=0).item()
+                assert cos > 0.97, (k, cos)
+
+
 def test_bf16_mode_valence_within_2e2_and_ccc():
     from oracle.ccc import eval_ccc
     N, B, T = 6, 6, 40
