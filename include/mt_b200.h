@@ -202,6 +202,44 @@ int mt_lstm_head_bwd(const MtLstmHeadCfg* cfg, const float* params, const void* 
                      void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Window front-end: what MultiCNNTransformer.forward does per modality BEFORE the hot path, for all windows of
+ * the batch in one call instead of one python iteration per narrative (MFT/models.py:117-132):
+ *   CNN      MFT/models.py:57-79   Conv1d(D -> E, kernel k, bias) over the K vectors of a window, then a global max over the
+ *                                  K - k + 1 positions                                                     (stage bit 1)
+ *   Highway  MFT/models.py:27-55   g = sigmoid(Wg c + bg); g * (Wp c + bp) + (1 - g) * c, then Dropout(0.3) :105,129   (stage bit 2)
+ * x fp32: stages & 1 -> [n_win, K, D] raw window vectors; stages == 2 -> [n_win, E] pooled features.  conv_w is nn.Conv1d's
+ * [E, D, k]; the Highway weights are nn.Linear's [E, E].  out fp32 [n_win, E].  The conv is ONE GEMM over overlapping rows of x
+ * (no im2col copy), tcgen05 in bf16 mode; the workspace carries what backward needs (same cfg, same ws).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int dtype;
+  int n_win;         /* B * T windows */
+  int K, D, E, k;    /* vectors per window, vector width, embedding width, conv kernel size (K, D, k unused when stages == 2) */
+  int stages;        /* 1 = CNN, 2 = Highway + dropout, 3 = both */
+  int training;      /* keep what backward needs */
+  float dropout_p;   /* dropout probability applied in this call (0.3 in the reference's train mode; pass 0 in eval mode) */
+  uint64_t seed;
+  uint32_t site;     /* dropout site id (one per modality) */
+} MtWindowCnnCfg;
+size_t mt_window_cnn_ws_bytes(const MtWindowCnnCfg* cfg);
+int mt_window_cnn_fwd(const MtWindowCnnCfg* cfg, const float* x, const float* conv_w, const float* conv_b, const float* wproj,
+                      const float* bproj, const float* wgate, const float* bgate, float* out, void* ws, size_t ws_bytes, void* stream);
+/* dout fp32 [n_win, E] -> parameter gradients (fp32, OVERWRITTEN); dx fp32 [n_win, E] only when stages == 2 (may be NULL): raw
+ * inputs are data and get no gradient. */
+int mt_window_cnn_bwd(const MtWindowCnnCfg* cfg, const float* x, const float* dout, float* dx, float* dconv_w, float* dconv_b,
+                      float* dwproj, float* dbproj, float* dwgate, float* dbgate, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Batched evaluation metrics: per-narrative concordance correlation coefficient and Pearson r of the first
+ * lengths[b] predictions of every narrative of a padded batch, in one launch -- eval_ccc MFT/train.py:42-50 and
+ * scipy.stats.pearsonr as called at MFT/train.py:236 (population moments, fp64 accumulation).  pred / target fp32 [B, T];
+ * ccc / pearson fp64 [B] (pearson may be NULL); sq_err fp64 [1] (may be NULL): sum over valid steps of (pred - target)^2,
+ * OVERWRITTEN (the MSELoss(sum) the evaluation loop accumulates, MFT/train.py:229).
+ * ------------------------------------------------------------------------------------------------- */
+int mt_ccc_batched(const float* pred, const float* target, const int* lengths, int B, int T, double* ccc, double* pearson,
+                   double* sq_err, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Utilities on flat buffers.
  * ------------------------------------------------------------------------------------------------- */
 /* out = x + dropout(y) (SublayerConnection.forward MFT/multiTransformer.py:103-104, stand-alone path; x may be NULL)

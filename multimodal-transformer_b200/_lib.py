@@ -33,6 +33,11 @@ class MtLstmHeadCfg(Structure):
     _fields_ = [('B', c_int), ('T', c_int), ('E', c_int), ('Hd', c_int), ('dtype', c_int), ('training', c_int)]
 
 
+class MtWindowCnnCfg(Structure):
+    _fields_ = [('dtype', c_int), ('n_win', c_int), ('K', c_int), ('D', c_int), ('E', c_int), ('k', c_int), ('stages', c_int),
+                ('training', c_int), ('dropout_p', c_float), ('seed', c_uint64), ('site', c_uint32)]
+
+
 P = c_void_p
 _PROTOS = {
     # name: (restype, argtypes)
@@ -77,6 +82,10 @@ _PROTOS = {
     'mt_lstm_head_ws_bytes': (c_size_t, [POINTER(MtLstmHeadCfg)]),
     'mt_lstm_head_fwd': (c_int, [POINTER(MtLstmHeadCfg), P, P, P, P, P, P, c_size_t, P]),
     'mt_lstm_head_bwd': (c_int, [POINTER(MtLstmHeadCfg), P, P, P, P, P, P, P, P, c_size_t, P]),
+    'mt_window_cnn_ws_bytes': (c_size_t, [POINTER(MtWindowCnnCfg)]),
+    'mt_window_cnn_fwd': (c_int, [POINTER(MtWindowCnnCfg), P, P, P, P, P, P, P, P, P, c_size_t, P]),
+    'mt_window_cnn_bwd': (c_int, [POINTER(MtWindowCnnCfg), P, P, P, P, P, P, P, P, P, P, c_size_t, P]),
+    'mt_ccc_batched': (c_int, [P, P, P, c_int, c_int, P, P, P, P]),
     'mt_residual_dropout_fwd': (c_int, [P, P, P, c_size_t, c_float, c_uint64, c_uint32, P]),
     'mt_dropout_bwd': (c_int, [P, P, c_size_t, c_float, c_uint64, c_uint32, P]),
     'mt_cast_f32_to_bf16': (c_int, [P, P, c_size_t, P]),

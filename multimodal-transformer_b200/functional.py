@@ -574,3 +574,103 @@ class LstmHeadFn(torch.autograd.Function):
 
 def lstm_head(enc, mask, arena, E, Hd):
     return LstmHeadFn.apply(enc, mask, arena, E, Hd, *arena.params)
+
+
+# ---------------------------------------------------------------------------------------------------------
+class WindowCnnFn(torch.autograd.Function):
+    """CNN (Conv1d over the K vectors of a window + global max-pool, MFT/models.py:57-79) and / or Highway + dropout
+    (MFT/models.py:27-55,129) for all windows of a batch: one mt_window_cnn_fwd / _bwd call each way.
+    stages: 1 = CNN only (x [..., K, D] -> [..., E]), 2 = Highway + dropout only (x [..., E]), 3 = both."""
+
+    @staticmethod
+    def forward(ctx, x, conv_w, conv_b, wproj, bproj, wgate, bgate, stages, p_drop, site):
+        dt = _state['dtype']
+        if x.dtype != torch.float32:
+            raise RuntimeError(f'window front-end input must be float32 (got {x.dtype})')
+        x = require(x if x.is_contiguous() else x.contiguous(), torch.float32, 'window input')
+        _lib.check_device(x.device.index)
+        for nm, w in (('conv1d.weight', conv_w), ('conv1d.bias', conv_b), ('linear_projection.weight', wproj),
+                      ('linear_projection.bias', bproj), ('linear_gate.weight', wgate), ('linear_gate.bias', bgate)):
+            if w is not None:
+                require(w, torch.float32, nm)
+        if stages & 1:
+            E, D, k = conv_w.shape
+            K = x.shape[-2]
+            if x.shape[-1] != D:
+                raise RuntimeError(f'window vectors are {x.shape[-1]} wide, conv1d expects {D}')
+            if K < k:
+                raise RuntimeError(f'a window of {K} vectors is shorter than the conv kernel ({k})')
+            lead = x.shape[:-2]
+        else:
+            E = wproj.shape[0]
+            K = D = k = 0
+            if x.shape[-1] != E:
+                raise RuntimeError(f'Highway input is {x.shape[-1]} wide, expected {E}')
+            lead = x.shape[:-1]
+        n_win = 1
+        for s in lead:
+            n_win *= int(s)
+        need_grad = any(ctx.needs_input_grad)
+        seed = next_seed() if p_drop > 0 else 0
+        cfg = _lib.MtWindowCnnCfg(dt, n_win, K, D, E, k, stages, int(need_grad), float(p_drop), seed, site)
+        L = lib()
+        nws = L.mt_window_cnn_ws_bytes(ctypes.byref(cfg))
+        if nws == 0:
+            raise RuntimeError('unsupported window front-end configuration')
+        ws = _ws(nws, x.device)
+        out = torch.empty((*lead, E), dtype=torch.float32, device=x.device)
+        check(L.mt_window_cnn_fwd(ctypes.byref(cfg), ptr(x), ptr(conv_w), ptr(conv_b), ptr(wproj), ptr(bproj), ptr(wgate), ptr(bgate),
+                                  ptr(out), ptr(ws), ws.numel(), stream()))
+        if need_grad:
+            ctx.save_for_backward(x, ws)
+            ctx.cfg = cfg
+            ctx.shapes = tuple(None if w is None else w.shape for w in (conv_w, conv_b, wproj, bproj, wgate, bgate))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, ws = ctx.saved_tensors
+        cfg = ctx.cfg
+        dout = dout if dout.is_contiguous() else dout.contiguous()
+        if dout.dtype != torch.float32:
+            dout = dout.float()
+        dev = x.device
+        grads = [None if s is None else torch.empty(s, dtype=torch.float32, device=dev) for s in ctx.shapes]
+        dx = torch.empty_like(x) if (cfg.stages == 2 and ctx.needs_input_grad[0]) else None
+        check(lib().mt_window_cnn_bwd(ctypes.byref(cfg), ptr(x), ptr(dout), ptr(dx), *[ptr(g) for g in grads], ptr(ws), ws.numel(),
+                                      stream()))
+        return (dx, *grads, None, None, None)
+
+
+def window_cnn(x, conv_w, conv_b, wproj, bproj, wgate, bgate, p_drop=0.0, site=0x6000):
+    """CNN + Highway + dropout of one modality: [..., K, D] -> [..., E]."""
+    return WindowCnnFn.apply(x, conv_w, conv_b, wproj, bproj, wgate, bgate, 3, float(p_drop), int(site))
+
+
+def conv_maxpool(x, conv_w, conv_b):
+    return WindowCnnFn.apply(x, conv_w, conv_b, None, None, None, None, 1, 0.0, 0)
+
+
+def highway(x, wproj, bproj, wgate, bgate, p_drop=0.0, site=0x6000):
+    return WindowCnnFn.apply(x, None, None, wproj, bproj, wgate, bgate, 2, float(p_drop), int(site))
+
+
+def ccc_batched(pred, target, lengths):
+    """Per-narrative CCC, Pearson r and the summed squared error of a padded batch in one launch (eval_ccc MFT/train.py:42-50;
+    the reference evaluates one narrative per forward).  pred / target [B,T] or [B,T,1] fp32 CUDA; lengths list or int tensor.
+    Returns (ccc [B] float64, pearson [B] float64, sq_err [] float64) on the device."""
+    B, T = pred.shape[0], pred.shape[1]
+    p = require(pred.reshape(B, T).contiguous(), torch.float32, 'pred')
+    t = require(target.reshape(B, T).contiguous(), torch.float32, 'target')
+    if torch.is_tensor(lengths):
+        ln = lengths.to(device=p.device, dtype=torch.int32).contiguous()
+    else:
+        ln = torch.tensor([int(v) for v in lengths], dtype=torch.int32).to(p.device)
+    if ln.numel() != B:
+        raise RuntimeError('lengths must have one entry per narrative')
+    _lib.check_device(p.device.index)
+    ccc = torch.empty(B, dtype=torch.float64, device=p.device)
+    pr = torch.empty(B, dtype=torch.float64, device=p.device)
+    se = torch.empty((), dtype=torch.float64, device=p.device)
+    check(lib().mt_ccc_batched(ptr(p), ptr(t), ptr(ln), B, T, ptr(ccc), ptr(pr), ptr(se), stream()))
+    return ccc, pr, se

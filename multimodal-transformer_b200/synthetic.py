@@ -49,3 +49,25 @@ def make_batch(B, T, dims, seed=1):
         mask[b, :l] = 1.0
     target = _rs(seed, 'target').uniform(0, 1, (B, T, 1)).astype(np.float32) * mask
     return inputs, mask, target, lengths
+
+
+RAW_SHAPES = {'linguistic': (33, 300), 'acoustic': (2, 88), 'image': (2, 1000), 'emotient': (2, 20)}   # (K vectors, D) per window
+
+
+def make_raw_batch(B, T, shapes, seed=1):
+    """Raw-level SEND-shaped batch in front of the window CNNs (MFT/train.py:571): shapes: mod -> (K, D).
+    inputs[mod] [B,T,K,D] f32, zero rows for padded windows; windows with K > 2 carry a random number (>= 2) of leading
+    non-zero vectors, the rest zero (short windows are zero-padded to the longest one).  Returns (inputs, mask, target, lengths)."""
+    lengths = make_lengths(B, T, seed)
+    mask = np.zeros((B, T, 1), np.float32)
+    for b, l in enumerate(lengths):
+        mask[b, :l] = 1.0
+    inputs = {}
+    for m, (K, D) in shapes.items():
+        x = _rs(seed, 'raw_' + m).standard_normal((B, T, K, D)).astype(np.float32)
+        if K > 2:
+            nvec = _rs(seed, 'nvec_' + m).randint(2, K + 1, size=(B, T))
+            x *= (np.arange(K)[None, None, :] < nvec[:, :, None]).astype(np.float32)[..., None]
+        inputs[m] = x * mask[..., None]
+    target = _rs(seed, 'target').uniform(0, 1, (B, T, 1)).astype(np.float32) * mask
+    return inputs, mask, target, lengths

@@ -111,3 +111,5 @@ SITE_SFT_EMBED = 0x5000
 
 def enc_site(stack, layer, k):
     return (stack * 64 + layer) * 8 + k
+# window front-end output dropout [B*T, E], one site per modality (index in the mods list)
+SITE_FRONT = 0x6000

@@ -1,0 +1,223 @@
+"""GPU (B200): the window front-end (CNN + max-pool + Highway + dropout: mt_window_cnn_fwd / _bwd), the MultiCNNTransformer mirrors
+built on it and the batched CCC kernel -- through the drop-in modules, i.e. through the C ABI -- against the CPU oracle on
+identical weights / inputs and against the golden outputs of the imported reference (tests/golden/front_*.npz).
+
+Tolerances: fp32 mode 1e-5 relative (forward) / 3e-4 (gradients); bf16 mode 2e-2 absolute on valence."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import multimodal_transformer_b200 as mtb
+from multimodal_transformer_b200 import _lib, functional as K, models as M
+from oracle import fill, frontend_oracle as FO, mt_oracle as O
+from oracle.ccc import eval_ccc
+from oracle.dropout_rng import SITE_FRONT, Dropper
+from tests import util
+from tests.test_gpu_parity import assert_close, grad_floor, t
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+@pytest.fixture(autouse=True)
+def _fp32_mode():
+    mtb.set_compute_dtype('fp32')
+    mtb.fix_seed(None)
+    yield
+    mtb.set_compute_dtype('fp32')
+    mtb.fix_seed(None)
+
+
+def front_meta():
+    with open(os.path.join(util.GOLD, 'front_meta.json')) as f:
+        return json.load(f)
+
+
+def front_inventory():
+    with open(os.path.join(util.GOLD, 'front_state_dict_keys.json')) as f:
+        return json.load(f)
+
+
+def _prim_sd(E, D, k):
+    sd = {'cnn.' + k_: v for k_, v in util.filled_sd({'conv1d.weight': (E, D, k), 'conv1d.bias': (E,)}, 20).items()}
+    sd.update({'hw.' + k_: v for k_, v in util.filled_sd({'linear_projection.weight': (E, E), 'linear_projection.bias': (E,),
+                                                         'linear_gate.weight': (E, E), 'linear_gate.bias': (E,)}, 21).items()})
+    return sd
+
+
+@pytest.mark.parametrize('tag', ['a', 'b', 'c', 'd'])
+def test_cnn_and_highway_modules_match_reference_golden(tag):
+    """CNN.forward / Highway.forward (stage 1 / stage 2 of the kernel) in fp32 mode against the imported reference's outputs
+    and gradients, incl. widths that are not multiples of 4 and a kernel size of 3."""
+    g = util.gold('front_prims'); m = front_meta()['prim_' + tag]
+    n, Kv, D, E, k = m['n'], m['K'], m['D'], m['E'], m['k']
+    sd = _prim_sd(E, D, k)
+    cnn = M.CNN(D, E, k).to(DEV); cnn.load_state_dict({k_[4:]: v for k_, v in sd.items() if k_.startswith('cnn.')})
+    hw = M.Highway(E).to(DEV); hw.load_state_dict({k_[3:]: v for k_, v in sd.items() if k_.startswith('hw.')})
+    x = t(fill.fill_array('front_x_' + tag, (n, Kv, D), 20) * 3.0).to(DEV)
+    w = t(fill.fill_array('front_w_' + tag, (n, E), 20)).to(DEV)
+    c = cnn(x.permute(0, 2, 1))                       # the reference hands the channel-major view to CNN.forward
+    assert_close(c, t(g[tag + '_c']), 1e-5, 'cnn out')
+    c2 = t(g[tag + '_c']).to(DEV).requires_grad_(True)
+    y = hw(c2)
+    assert_close(y, t(g[tag + '_y']), 1e-5, 'highway out')
+    (y * w).sum().backward()
+    (c * w).sum().backward()
+    assert_close(c2.grad, t(g[tag + '_dc']), 1e-4, 'dc')
+    for name, mod in (('cnn', cnn), ('hw', hw)):
+        for k_, p in mod.named_parameters():
+            assert_close(p.grad, t(g[f'{tag}_grad:{k_}']), 1e-4, k_, 1e-6)
+
+
+@pytest.mark.parametrize('n,Kv,D,E,k', [(300, 33, 300, 300, 2), (513, 2, 1000, 256, 2), (257, 2, 88, 88, 2), (64, 7, 36, 20, 3)])
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_window_cnn_fused_train_mode_same_masks(n, Kv, D, E, k, mode):
+    """All three stages in one call, train mode (dropout 0.3 with the oracle's masks), at the real modality shapes (linguistic 33 x 300,
+    image 2 x 1000, acoustic 2 x 88) and an odd one: fp32 mode against the fp64 oracle at 1e-5 / 3e-4; bf16 mode (tcgen05 GEMM over
+    overlapping rows) within bf16 operand rounding, gradients by cosine."""
+    seed = 99
+    sd = _prim_sd(E, D, k)
+    sd['cnn.conv1d.weight'] = sd['cnn.conv1d.weight'] * (1.0 / D) ** 0.5      # nn.Conv1d's default scale (fan_in = D * k), O(1) features
+    rs = np.random.RandomState(n)
+    x = rs.standard_normal((n, Kv, D)).astype(np.float32)
+    if Kv > 2:
+        nvec = rs.randint(k, Kv + 1, size=n)
+        x *= (np.arange(Kv)[None, :] < nvec[:, None]).astype(np.float32)[..., None]
+    w = rs.standard_normal((n, E)).astype(np.float32)
+    sdr = {k_: v.double().requires_grad_(True) for k_, v in sd.items()}
+    cr = FO.cnn(sdr, 'cnn', t(x).double())
+    yr = Dropper(seed)(FO.highway(sdr, 'hw', cr), 0.3, SITE_FRONT)
+    (yr * t(w).double()).sum().backward()
+    mtb.set_compute_dtype(mode)
+    mtb.fix_seed(seed)
+    ps = {k_: v.to(DEV).requires_grad_(True) for k_, v in sd.items()}
+    y = K.window_cnn(t(x).to(DEV), ps['cnn.conv1d.weight'], ps['cnn.conv1d.bias'], ps['hw.linear_projection.weight'],
+                     ps['hw.linear_projection.bias'], ps['hw.linear_gate.weight'], ps['hw.linear_gate.bias'], p_drop=0.3, site=SITE_FRONT)
+    (y * t(w).to(DEV)).sum().backward()
+    # identical dropout masks: the zero patterns agree exactly
+    assert torch.equal((y == 0).cpu(), (yr == 0)) or mode == 'bf16'
+    fl = grad_floor([v.grad for v in sdr.values()])
+    if mode == 'fp32':
+        assert_close(y, yr, 1e-5, 'out')
+        for k_, p in ps.items():
+            assert_close(p.grad, sdr[k_].grad, 3e-4, k_, fl)
+    else:
+        assert_close(y, yr, 2e-2, 'out')
+        for k_, p in ps.items():
+            cos = torch.nn.functional.cosine_similarity(p.grad.double().cpu().flatten(), sdr[k_].grad.flatten(), dim=0).item()
+            assert cos > 0.97, (k_, cos)           # bf16 near-ties may pick another arg-max position than the fp64 oracle
+
+
+def _load(model, name):
+    inv = front_inventory()[{'front_mft': 'MFT', 'front_sft': 'SFT', 'front_b2': 'B2', 'front_b3': 'B3'}[name] + '.MultiCNNTransformer']
+    m = front_meta()[name]
+    sd = util.filled_sd({k: tuple(s) for k, s in inv.items()}, m['seed'])
+    model.load_state_dict(sd)
+    shapes = {k: tuple(v) for k, v in m['shapes'].items()}
+    inputs, mask, target, lengths = fill.make_raw_batch(m['B'], m['T'], shapes, m['seed'])
+    return sd, inputs, mask, target, lengths
+
+
+@pytest.mark.parametrize('name,ctor', [
+    ('front_mft', lambda m: M.MultiCNNTransformer(m['mods'], {k: v[1] for k, v in m['shapes'].items()}, m['embed_dims'])),
+    ('front_b3', lambda m: M.B3MultiCNNTransformer(m['mods'], {k: v[1] for k, v in m['shapes'].items()})),
+    ('front_sft', lambda m: M.SFTMultiCNNTransformer(m['mods'], {k: v[1] for k, v in m['shapes'].items()})),
+    ('front_b2', lambda m: M.B2MultiCNNTransformer(m['mods'], {k: v[1] for k, v in m['shapes'].items()})),
+])
+def test_multicnn_models_match_reference_golden(name, ctor):
+    """The four MultiCNNTransformer variants end to end (raw windows -> prediction), eval mode, fp32: prediction, loss and every
+    parameter gradient against the imported reference; then bf16 mode within 2e-2 on valence."""
+    g = util.gold(name); m = front_meta()[name]
+    model = ctor(m).eval()
+    sd, inputs, mask, target, lengths = _load(model, name)
+    xin = {k: t(v).to(DEV) for k, v in inputs.items()}
+    pred = model(xin, lengths, t(mask).to(DEV))
+    assert_close(pred, t(g['pred']), 1e-5, 'pred', 1e-7)
+    loss = ((pred - t(target).to(DEV)) ** 2).sum() / sum(lengths)
+    assert abs(loss.item() - float(g['loss'])) <= 2e-5 * abs(float(g['loss']))
+    loss.backward()
+    checked = 0
+    for k, p in model.named_parameters():
+        if 'grad:' + k in g:
+            util.assert_digest_close(util.grad_digest(p.grad), g['grad:' + k], 3e-4, k); checked += 1
+        else:
+            assert p.grad is None and k.startswith(('Transformer.attn', 'Transformer.ff')), k
+    assert checked >= 12
+    mtb.set_compute_dtype('bf16')
+    with torch.no_grad():
+        p16 = model(xin, lengths, t(mask).to(DEV))
+    assert (p16.float().cpu() - t(g['pred'])).abs().max().item() < 2e-2
+
+
+def test_multicnn_mft_train_mode_same_masks_both_dtypes():
+    """Train mode through the front-end AND the hot path with the oracle's dropout masks (front-end sites 0x6000 + modality)."""
+    name, seed = 'front_mft', 1234
+    m = front_meta()[name]
+    dims = {k: v[1] for k, v in m['shapes'].items()}
+    model = M.MultiCNNTransformer(m['mods'], dims, m['embed_dims']).train()
+    sd, inputs, mask, target, lengths = _load(model, name)
+    sdr = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    predr = FO.mcnn_mft(sdr, {k: t(v).double() for k, v in inputs.items()}, t(mask).double(), m['mods'], drop=Dropper(seed))
+    O.train_loss(predr, t(target).double(), lengths).backward()
+    fl = grad_floor([v.grad for v in sdr.values()])
+    for mode in ('fp32', 'bf16'):
+        mtb.set_compute_dtype(mode)
+        model.zero_grad(set_to_none=True)
+        mtb.fix_seed(seed)
+        pred = model({k: t(v).to(DEV) for k, v in inputs.items()}, lengths, t(mask).to(DEV))
+        (((pred - t(target).to(DEV)) ** 2).sum() / sum(lengths)).backward()
+        if mode == 'fp32':
+            assert_close(pred, predr, 2e-5, 'pred')
+            for k, p in model.named_parameters():
+                if sdr[k].grad is not None:
+                    assert_close(p.grad, sdr[k].grad, 3e-4, k, fl)
+        else:
+            assert (pred.detach().float().cpu() - predr.float()).abs().max().item() < 2e-2
+
+
+def test_window_cnn_rejects_bad_arguments():
+    L = _lib.lib()
+    import ctypes
+    cfg = _lib.MtWindowCnnCfg(0, 4, 3, 8, 8, 4, 3, 0, 0.0, 0, 0)          # conv kernel longer than the window
+    assert L.mt_window_cnn_ws_bytes(ctypes.byref(cfg)) == 0
+    cfg = _lib.MtWindowCnnCfg(0, 4, 3, 8, 8, 2, 0, 0, 0.0, 0, 0)          # no stage selected
+    assert L.mt_window_cnn_ws_bytes(ctypes.byref(cfg)) == 0
+    x = torch.zeros(2, 1, 8, device=DEV)
+    cnn = M.CNN(8, 4, 2).to(DEV)
+    with pytest.raises(RuntimeError, match='shorter'):
+        cnn(x.permute(0, 2, 1))
+    with pytest.raises(RuntimeError, match='float32'):
+        K.highway(torch.zeros(2, 4, device=DEV, dtype=torch.bfloat16), *[torch.zeros(4, 4, device=DEV), torch.zeros(4, device=DEV)] * 2)
+
+
+# ---- batched evaluation metrics ----------------------------------------------------------------------------------------------------
+def test_ccc_batched_known_answers_and_oracle():
+    """The reference's published known-answers (PredSave -> PerfSave, tests/golden/ccc_kat.json) as ONE padded batch, plus random
+    ragged narratives against the eval_ccc restatement and scipy's pearsonr."""
+    from scipy.stats import pearsonr
+    with open(os.path.join(util.GOLD, 'ccc_kat.json')) as f:
+        kat = json.load(f)
+    T = max(len(k['pred']) for k in kat)
+    pred = np.zeros((len(kat), T), np.float32); act = np.zeros((len(kat), T), np.float32)
+    for i, k in enumerate(kat):
+        pred[i, :len(k['pred'])] = k['pred']; act[i, :len(k['actual'])] = k['actual']
+        pred[i, len(k['pred']):] = 7.0                      # padding must not leak into the statistics
+    lengths = [len(k['pred']) for k in kat]
+    ccc, pr, se = K.ccc_batched(t(pred).to(DEV), t(act).to(DEV).unsqueeze(-1), lengths)
+    for i, k in enumerate(kat):
+        assert abs(ccc[i].item() - k['ccc']) < 2e-7, (k['model'], k['vid'])
+    rs = np.random.RandomState(5)
+    B, T = 37, 300
+    lengths = [T] + [int(v) for v in rs.randint(2, T + 1, size=B - 1)]
+    a = rs.uniform(0, 1, (B, T)).astype(np.float32)
+    p = (0.7 * a + 0.3 * rs.uniform(0, 1, (B, T))).astype(np.float32)
+    ccc, pr, se = K.ccc_batched(t(p).to(DEV), t(a).to(DEV), torch.tensor(lengths))
+    want_se = 0.0
+    for b, l in enumerate(lengths):
+        assert abs(ccc[b].item() - eval_ccc(a[b, :l], p[b, :l])) < 1e-12
+        assert abs(pr[b].item() - pearsonr(p[b, :l].astype(np.float64), a[b, :l].astype(np.float64))[0]) < 1e-12
+        want_se += ((p[b, :l].astype(np.float64) - a[b, :l].astype(np.float64)) ** 2).sum()
+    assert abs(se.item() - want_se) < 1e-9 * want_se
