@@ -94,6 +94,10 @@ int mt_layernorm_bwd(int dtype, int M, int d, const float* x, const float* a_2, 
  * ------------------------------------------------------------------------------------------------- */
 int mt_attention_fwd(int dtype, int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse,
                      float p_drop, uint64_t seed, uint32_t site, void* stream);
+/* Ragged inference variant (no dropout, no lse): keys j >= key_len[b] (device int [B]) are excluded for narrative b; see
+ * MtEncoderCfg.key_len. */
+int mt_attention_ragged_fwd(int dtype, int B, int T, int d, int h, const void* qkv, const float* mask, const int* key_len, void* out,
+                            void* stream);
 /* dqkv [B,T,3d] overwritten.  ws: mt_attention_bwd_ws_bytes (B*h*T floats). */
 int mt_attention_bwd(int dtype, int B, int T, int d, int h, const void* qkv, const float* mask, const void* out,
                      const float* lse, const void* dout, void* dqkv, float p_drop, uint64_t seed, uint32_t site,
@@ -128,6 +132,10 @@ typedef struct {
   int y_f32;
   int grid_share;    /* 0/1: this stack owns the GPU; s > 1: it runs concurrently with s - 1 other streams (the other modality stacks):
                         its GEMM / LayerNorm kernels launch 1/s of the resident CTA slots so the stacks co-reside on the SMs */
+  const int* key_len; /* NULL, or device int [B] for RAGGED INFERENCE (mt_encoder_fwd with training == 0, p_drop == 0): narrative b only
+                        has its first key_len[b] windows, so attention keys beyond them are excluded and the first key_len[b] output
+                        rows equal a forward of that narrative alone (the reference evaluates with batch_size = 1, MFT/train.py:169,218,
+                        where no padded window exists; in a padded TRAINING batch padded windows are live keys, appendix A.12) */
 } MtEncoderCfg;
 
 size_t mt_encoder_param_count(int d, int dff, int n_layers);

@@ -20,7 +20,7 @@ MT_MAX_MODS = 4
 class MtEncoderCfg(Structure):
     _fields_ = [('B', c_int), ('T', c_int), ('d', c_int), ('h', c_int), ('dff', c_int), ('n_layers', c_int),
                 ('dtype', c_int), ('training', c_int), ('p_drop', c_float), ('seed', c_uint64), ('stack_id', c_int),
-                ('y_f32', c_int), ('grid_share', c_int)]
+                ('y_f32', c_int), ('grid_share', c_int), ('key_len', c_void_p)]
 
 
 class MtMfnCfg(Structure):
@@ -57,6 +57,7 @@ _PROTOS = {
     'mt_layernorm_fwd': (c_int, [c_int, c_int, c_int, P, P, P, c_float, P, c_int, P]),
     'mt_layernorm_bwd': (c_int, [c_int, c_int, c_int, P, P, c_float, P, c_int, P, P, P, P, P]),
     'mt_attention_fwd': (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, c_float, c_uint64, c_uint32, P]),
+    'mt_attention_ragged_fwd': (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]),
     'mt_attention_bwd': (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, c_float, c_uint64, c_uint32, P, c_size_t, P]),
     'mt_attention_bwd_ws_bytes': (c_size_t, [c_int, c_int, c_int]),
     'mt_attention_force_ffma': (c_int, [c_int]),

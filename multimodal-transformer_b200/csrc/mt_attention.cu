@@ -40,7 +40,8 @@ __device__ __forceinline__ void stage_tile(float* s, const T* base /* (b, row 0,
 template <typename T, int DK>
 __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(int B, int T_, int d, int h, const T* __restrict__ qkv,
                                                               const float* __restrict__ mask, T* __restrict__ out,
-                                                              float* __restrict__ lse, DropCfg drop_in, float scale) {
+                                                              float* __restrict__ lse, DropCfg drop_in, float scale,
+                                                              const int* __restrict__ klen) {
   const DropCfg drop = mt_drop_resolve(drop_in);
   constexpr int KT = AT_TILE_ELEMS / DK;
   __shared__ __align__(16) float Ks[KT * DK];
@@ -50,6 +51,8 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(int B, int T_, int
   const bool active = i < T_;
   const int ld = 3 * d;
   const T* qb = qkv + (size_t)b * T_ * ld + hd * DK;
+  // ragged inference: narrative b only HAS its first klen[b] windows -- keys beyond them do not exist (mt_b200.h: key_len)
+  const int Tk = klen ? max(1, min(klen[b], T_)) : T_;
   float q[DK], o[DK];
   bool masked = false;
   if (active) {
@@ -61,13 +64,13 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(int B, int T_, int
   float m = -INFINITY, l = 0.f;
   const uint64_t drop_row = (uint64_t)((size_t)b * h + hd) * T_ + (uint64_t)(active ? i : 0);      // flat (b, head, query) row
   const uint32_t P2 = (uint32_t)(T_ + 1) >> 1;
-  for (int j0 = 0; j0 < T_; j0 += KT) {
+  for (int j0 = 0; j0 < Tk; j0 += KT) {
     __syncthreads();
     stage_tile<T, DK>(Ks, qb + d, ld, j0, KT, T_);
     stage_tile<T, DK>(Vs, qb + 2 * d, ld, j0, KT, T_);
     __syncthreads();
     if (!active) continue;
-    const int jn = min(KT, T_ - j0);
+    const int jn = min(KT, Tk - j0);
     for (int j = 0; j < jn; ++j) {
       float s = 0.f;
       const float4* kr = reinterpret_cast<const float4*>(Ks + j * DK);
@@ -281,15 +284,16 @@ __global__ void attn_probs_kernel(int B, int T_, int d, int h, int dk, const T* 
 }
 
 template <typename T>
-int fwd_dispatch(int B, int T_, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop, cudaStream_t st) {
+int fwd_dispatch(int B, int T_, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop, cudaStream_t st,
+                 const int* klen) {
   const int dk = d / h;
   const float scale = 1.0f / sqrtf((float)dk);
   dim3 grid((T_ + AT_THREADS - 1) / AT_THREADS, h, B);
   mt_prof_work(4.0 * B * (double)T_ * T_ * d, (double)B * T_ * d * 4.0 * sizeof(T));
   switch (dk) {
-    case 16: attn_fwd_kernel<T, 16><<<grid, AT_THREADS, 0, st>>>(B, T_, d, h, (const T*)qkv, mask, (T*)out, lse, drop, scale); break;
-    case 32: attn_fwd_kernel<T, 32><<<grid, AT_THREADS, 0, st>>>(B, T_, d, h, (const T*)qkv, mask, (T*)out, lse, drop, scale); break;
-    case 64: attn_fwd_kernel<T, 64><<<grid, AT_THREADS, 0, st>>>(B, T_, d, h, (const T*)qkv, mask, (T*)out, lse, drop, scale); break;
+    case 16: attn_fwd_kernel<T, 16><<<grid, AT_THREADS, 0, st>>>(B, T_, d, h, (const T*)qkv, mask, (T*)out, lse, drop, scale, klen); break;
+    case 32: attn_fwd_kernel<T, 32><<<grid, AT_THREADS, 0, st>>>(B, T_, d, h, (const T*)qkv, mask, (T*)out, lse, drop, scale, klen); break;
+    case 64: attn_fwd_kernel<T, 64><<<grid, AT_THREADS, 0, st>>>(B, T_, d, h, (const T*)qkv, mask, (T*)out, lse, drop, scale, klen); break;
     default: return MT_ERR_UNSUPPORTED;
   }
   MT_LAUNCH_CHECK();
@@ -333,12 +337,12 @@ int check_shape(int B, int T_, int d, int h) {
 static int g_attn_force_ffma = 0;
 
 int mt_attn_fwd_run(int dtype, int B, int T_, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop,
-                    cudaStream_t st) {
+                    cudaStream_t st, const int* klen) {
   MT_TRY(check_shape(B, T_, d, h));
   if (!qkv || !out) return MT_ERR_ARG;
-  if (dtype == MT_BF16 && !g_attn_force_ffma && mt_attn_mma_supported(B, T_, d, h)) return mt_attn_mma_fwd_run(B, T_, d, h, qkv, mask, out, lse, drop, st);
-  if (dtype == MT_BF16) return fwd_dispatch<bf16>(B, T_, d, h, qkv, mask, out, lse, drop, st);
-  return fwd_dispatch<float>(B, T_, d, h, qkv, mask, out, lse, drop, st);
+  if (dtype == MT_BF16 && !g_attn_force_ffma && mt_attn_mma_supported(B, T_, d, h)) return mt_attn_mma_fwd_run(B, T_, d, h, qkv, mask, out, lse, drop, st, klen);
+  if (dtype == MT_BF16) return fwd_dispatch<bf16>(B, T_, d, h, qkv, mask, out, lse, drop, st, klen);
+  return fwd_dispatch<float>(B, T_, d, h, qkv, mask, out, lse, drop, st, klen);
 }
 
 int mt_attn_bwd_run(int dtype, int B, int T_, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse,
@@ -365,6 +369,12 @@ int mt_attention_fwd(int dtype, int B, int T, int d, int h, const void* qkv, con
 }
 
 size_t mt_attention_bwd_ws_bytes(int B, int T, int h) { return sizeof(float) * (size_t)B * (size_t)T * (size_t)h; }
+
+int mt_attention_ragged_fwd(int dtype, int B, int T, int d, int h, const void* qkv, const float* mask, const int* key_len, void* out,
+                            void* stream) {
+  if (!qkv || !out || !key_len || B <= 0 || T <= 0 || d <= 0 || h <= 0 || d % h != 0) return MT_ERR_ARG;
+  return mt_attn_fwd_run(dtype, B, T, d, h, qkv, mask, out, nullptr, mt_make_drop(0.f, 0, 0), (cudaStream_t)stream, key_len);
+}
 
 int mt_attention_bwd(int dtype, int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse,
                      const void* dout, void* dqkv, float p_drop, uint64_t seed, uint32_t site, void* ws, size_t ws_bytes,

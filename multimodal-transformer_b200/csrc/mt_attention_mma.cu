@@ -72,12 +72,14 @@ __device__ __forceinline__ void mma_p_s(float (*o)[4], const uint32_t (*pa)[4], 
 template <int DK>
 __global__ void __launch_bounds__(THREADS) attn_mma_fwd_kernel(int B, int T, int d, int h, const bf16* __restrict__ qkv,
                                                                const float* __restrict__ mask, bf16* __restrict__ out,
-                                                               float* __restrict__ lse, DropCfg drop_in, float scale) {
+                                                               float* __restrict__ lse, DropCfg drop_in, float scale,
+                                                               const int* __restrict__ klen) {
   const DropCfg drop = mt_drop_resolve(drop_in);
   constexpr int LD = DK + 8;
   __shared__ __align__(16) bf16 Ks[TILE * LD];
   __shared__ __align__(16) bf16 Vs[TILE * LD];
   const int b = blockIdx.z, hd = blockIdx.y;
+  const int Tk = klen ? max(1, min(klen[b], T)) : T;      // ragged inference: keys beyond the narrative's own length do not exist
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ld = 3 * d;
   const bf16* qb = qkv + (size_t)b * T * ld + hd * DK;
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(THREADS) attn_mma_fwd_kernel(int B, int T, int
   const uint64_t drow0 = bh * T + (uint64_t)min(r0, T - 1), drow1 = bh * T + (uint64_t)min(r1, T - 1);
   const uint32_t P2 = (uint32_t)(T + 1) >> 1;
 
-  for (int j0 = 0; j0 < T; j0 += TILE) {
+  for (int j0 = 0; j0 < Tk; j0 += TILE) {
     __syncthreads();
     stage<DK>(Ks, qb + d, ld, j0, T);
     stage<DK>(Vs, qb + 2 * d, ld, j0, T);
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(THREADS) attn_mma_fwd_kernel(int B, int T, int
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int j = j0 + nt * 8 + 2 * (lane & 3) + e;
-        const bool in = j < T;
+        const bool in = j < Tk;
         float v0 = mk0 ? -1e9f : s[nt][e] * scale, v1 = mk1 ? -1e9f : s[nt][2 + e] * scale;
         v0 = in ? v0 : -INFINITY; v1 = in ? v1 : -INFINITY;
         s[nt][e] = v0; s[nt][2 + e] = v1;
@@ -327,16 +329,17 @@ bool mt_attn_mma_supported(int B, int T, int d, int h) {
 static int g_force_tiled = 0;
 extern "C" int mt_attention_force_tiled(int on) { const int old = g_force_tiled; g_force_tiled = on; return old; }
 
-int mt_attn_mma_fwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop, cudaStream_t st) {
-  if (!g_force_tiled && mt_attn128_supported(B, T, d, h)) return mt_attn128_fwd_run(B, T, d, h, qkv, mask, out, lse, drop, st);
+int mt_attn_mma_fwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop, cudaStream_t st,
+                        const int* klen) {
+  if (!g_force_tiled && mt_attn128_supported(B, T, d, h)) return mt_attn128_fwd_run(B, T, d, h, qkv, mask, out, lse, drop, st, klen);
   const int dk = d / h;
   const float scale = 1.0f / sqrtf((float)dk);
   dim3 grid((T + WARPS * 16 - 1) / (WARPS * 16), h, B);
   mt_prof_work(4.0 * B * (double)T * T * d, (double)B * T * d * 4.0 * 2.0);
   switch (dk) {
-    case 16: attn_mma_fwd_kernel<16><<<grid, THREADS, 0, st>>>(B, T, d, h, (const bf16*)qkv, mask, (bf16*)out, lse, drop, scale); break;
-    case 32: attn_mma_fwd_kernel<32><<<grid, THREADS, 0, st>>>(B, T, d, h, (const bf16*)qkv, mask, (bf16*)out, lse, drop, scale); break;
-    case 64: attn_mma_fwd_kernel<64><<<grid, THREADS, 0, st>>>(B, T, d, h, (const bf16*)qkv, mask, (bf16*)out, lse, drop, scale); break;
+    case 16: attn_mma_fwd_kernel<16><<<grid, THREADS, 0, st>>>(B, T, d, h, (const bf16*)qkv, mask, (bf16*)out, lse, drop, scale, klen); break;
+    case 32: attn_mma_fwd_kernel<32><<<grid, THREADS, 0, st>>>(B, T, d, h, (const bf16*)qkv, mask, (bf16*)out, lse, drop, scale, klen); break;
+    case 64: attn_mma_fwd_kernel<64><<<grid, THREADS, 0, st>>>(B, T, d, h, (const bf16*)qkv, mask, (bf16*)out, lse, drop, scale, klen); break;
     default: return MT_ERR_UNSUPPORTED;
   }
   MT_LAUNCH_CHECK();

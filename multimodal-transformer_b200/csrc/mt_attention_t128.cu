@@ -78,7 +78,8 @@ struct FwdSmem {
 template <int DK, bool FULL>      // FULL: T == 128, no bound tests
 __global__ void __launch_bounds__(NT, 2) attn128_fwd_kernel(int B, int T, int d, int h, const bf16* __restrict__ qkv,
                                                             const float* __restrict__ mask, bf16* __restrict__ out,
-                                                            float* __restrict__ lse, DropCfg drop_in, float scale) {
+                                                            float* __restrict__ lse, DropCfg drop_in, float scale,
+                                                            const int* __restrict__ klen) {
   const DropCfg drop = mt_drop_resolve(drop_in);
   constexpr int LD = DK + 8;
   extern __shared__ __align__(16) unsigned char fwd_smem[];
@@ -121,7 +122,9 @@ __global__ void __launch_bounds__(NT, 2) attn128_fwd_kernel(int B, int T, int d,
   // masked query rows: every score becomes the same constant, i.e. scale 0 (reference: masked_fill(-1e9) over the row)
   const float rs0 = (mask != nullptr && r0 < T && mask[(size_t)b * T + r0] == 0.f) ? 0.f : scale * LOG2E;
   const float rs1 = (mask != nullptr && r1 < T && mask[(size_t)b * T + r1] == 0.f) ? 0.f : scale * LOG2E;
-  const int nkt = FULL ? TMAX / 8 : (T + 7) >> 3;     // 8-key tiles that hold at least one valid key
+  // ragged inference (klen, !FULL only): keys beyond the narrative's own length do not exist
+  const int Tk = (!FULL && klen != nullptr) ? max(1, min(klen[b], T)) : T;
+  const int nkt = FULL ? TMAX / 8 : (Tk + 7) >> 3;    // 8-key tiles that hold at least one valid key
   float s[TMAX / 8][4];
   float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(NT, 2) attn128_fwd_kernel(int B, int T, int d,
     }
 #pragma unroll
     for (int e = 0; e < 2; ++e) {          // keys beyond T never contribute (their probability is exactly 0)
-      const bool in = FULL || nt * 8 + c + e < T;
+      const bool in = FULL || nt * 8 + c + e < Tk;
       s[nt][e] = in ? s[nt][e] * rs0 : -INFINITY;
       s[nt][2 + e] = in ? s[nt][2 + e] * rs1 : -INFINITY;
       mx0 = fmaxf(mx0, s[nt][e]); mx1 = fmaxf(mx1, s[nt][2 + e]);
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(NT, 2) attn128_fwd_kernel(int B, int T, int d,
   for (int i = 0; i < DK / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
 #pragma unroll
   for (int kk = 0; kk < TMAX / 16; ++kk) {
-    if (FULL || kk * 16 < T) {
+    if (FULL || kk * 16 < Tk) {
       uint32_t pa[4];
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
@@ -427,7 +430,8 @@ bool mt_attn128_supported(int B, int T, int d, int h) {
   return (dk == 16 || dk == 32 || dk == 64) && d % 8 == 0 && (long long)B * h <= 0x7fffffffLL;
 }
 
-int mt_attn128_fwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop, cudaStream_t st) {
+int mt_attn128_fwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop, cudaStream_t st,
+                       const int* klen) {
   const int dk = d / h;
   const float scale = 1.0f / sqrtf((float)dk);
   mt_prof_work(4.0 * B * (double)T * T * d, (double)B * T * d * 4.0 * 2.0);
@@ -441,8 +445,8 @@ int mt_attn128_fwd_run(int B, int T, int d, int h, const void* qkv, const float*
       MT_CUDA(cudaFuncSetAttribute(attn128_fwd_kernel<DK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdSmem<DK>::BYTES)); \
       attr = true;                                                                                                                     \
     }                                                                                                                                  \
-    if (T == TMAX) attn128_fwd_kernel<DK, true><<<grid, NT, FwdSmem<DK>::BYTES, st>>>(B, T, d, h, (const bf16*)qkv, mask, (bf16*)out, lse, drop, scale);  \
-    else attn128_fwd_kernel<DK, false><<<grid, NT, FwdSmem<DK>::BYTES, st>>>(B, T, d, h, (const bf16*)qkv, mask, (bf16*)out, lse, drop, scale);          \
+    if (T == TMAX && !klen) attn128_fwd_kernel<DK, true><<<grid, NT, FwdSmem<DK>::BYTES, st>>>(B, T, d, h, (const bf16*)qkv, mask, (bf16*)out, lse, drop, scale, nullptr);  \
+    else attn128_fwd_kernel<DK, false><<<grid, NT, FwdSmem<DK>::BYTES, st>>>(B, T, d, h, (const bf16*)qkv, mask, (bf16*)out, lse, drop, scale, klen);          \
   }
   switch (dk) {
     case 16: MT_FWD(16) break;

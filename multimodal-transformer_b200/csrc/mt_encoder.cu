@@ -169,6 +169,7 @@ int mt_encoder_fwd(const MtEncoderCfg* cfg, const float* params, const void* par
   MT_TRY(check_cfg(cfg));
   const MtEncoderCfg& c = *cfg;
   if (!params || !x || !y || !ws || (c.dtype == MT_BF16 && !params_lp)) return MT_ERR_ARG;
+  if (c.key_len && (c.training || c.p_drop > 0.f)) return MT_ERR_UNSUPPORTED;      // ragged batches: inference only
   EncWs w;
   MT_TRY(carve(c, ws, w));
   if (ws_bytes < w.bytes) return MT_ERR_WS;
@@ -189,7 +190,7 @@ int mt_encoder_fwd(const MtEncoderCfg* cfg, const float* params, const void* par
     g.epi.bias = pf + P.b_qkv;
     MT_TRY(mt_gemm_run(c.dtype, g, st));
     MT_TRY(mt_attn_fwd_run(c.dtype, c.B, c.T, d, c.h, b.qkv, mask, b.att, b.lse,
-                           mt_make_drop(p, c.seed, mt_enc_site(c.stack_id, l, MT_SITE_ATTN_P)), st));
+                           mt_make_drop(p, c.seed, mt_enc_site(c.stack_id, l, MT_SITE_ATTN_P)), st, c.key_len));
     g = fwd_gemm(M, d, d, b.att, wptr(c, params, params_lp, base + P.w_o), b.xp, true);
     g.epi.bias = pf + P.b_o;
     g.epi.drop = mt_make_drop(p, c.seed, mt_enc_site(c.stack_id, l, MT_SITE_SUB0));

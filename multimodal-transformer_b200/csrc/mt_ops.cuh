@@ -41,7 +41,9 @@ int mt_transpose_pack_run(const TransposeJob* jobs, int n_jobs, bool dst_bf16, c
 
 // ---- tensor-core attention engine for bf16 (mt_attention_mma.cu) --------------------------------------------
 bool mt_attn_mma_supported(int B, int T, int d, int h);
-int mt_attn_mma_fwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop, cudaStream_t st);
+// klen (optional, int [B]): ragged INFERENCE -- narrative b only has its first klen[b] windows, keys beyond them are excluded
+int mt_attn_mma_fwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop, cudaStream_t st,
+                        const int* klen = nullptr);
 // dbias (optional, fp32 [3d], ACCUMULATED): column sums of dqkv = the QKV projection's bias gradient; *dbias_done tells
 // whether the kernel that ran produced it (otherwise the caller runs a column-sum pass)
 int mt_attn_mma_bwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse, const void* dout,
@@ -49,12 +51,13 @@ int mt_attn_mma_bwd_run(int B, int T, int d, int h, const void* qkv, const float
 
 // ---- whole-head-per-CTA attention for T <= 128 (mt_attention_t128.cu), bf16 -----------------------------------
 bool mt_attn128_supported(int B, int T, int d, int h);
-int mt_attn128_fwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop, cudaStream_t st);
+int mt_attn128_fwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop, cudaStream_t st,
+                       const int* klen = nullptr);
 int mt_attn128_bwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse, const void* dout,
                        void* dqkv, DropCfg drop, cudaStream_t st, float* dbias = nullptr);
 
 // ---- attention (mt_attention.cu) ---------------------------------------------------------------------
 int mt_attn_fwd_run(int dtype, int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop,
-                    cudaStream_t st);
+                    cudaStream_t st, const int* klen = nullptr);
 int mt_attn_bwd_run(int dtype, int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse,
                     const void* dout, void* dqkv, DropCfg drop, float* Dws, cudaStream_t st, float* dbias = nullptr);

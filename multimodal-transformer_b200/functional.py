@@ -13,7 +13,7 @@ from . import _lib
 from ._lib import ACT_NONE, ACT_RELU, ACT_TANH, MT_BF16, MT_F32, check, lib, ptr, require, stream
 
 _state = {'dtype': MT_F32, 'seed': 0x5EED0000, 'counter': 0, 'fixed_seed': None, 'parallel_stacks': True, 'defer_wgrad': False,
-          'pending': [], 'wgrad_stream': {}}
+          'pending': [], 'wgrad_stream': {}, 'key_len': None}
 
 
 def set_compute_dtype(name):
@@ -54,6 +54,47 @@ def join_deferred():
     for ev in _state['pending']:
         cur.wait_event(ev)
     _state['pending'].clear()
+
+
+class ragged_batch:
+    """Context manager for INFERENCE on a padded batch whose narratives have different lengths:
+
+        with mtb.ragged_batch(lengths):
+            pred = model(inputs, mask, lengths)
+
+    Inside it, narrative b only HAS its first lengths[b] windows: attention keys beyond them are excluded, so the valid part of
+    every prediction equals a forward of that narrative alone -- what the reference's evaluation computes with batch_size = 1
+    (MFT/train.py:169,218).  Without it a padded batch follows the reference's TRAINING semantics, where padded windows are
+    live attention keys.  No gradients, no dropout: a model in train() mode raises."""
+
+    def __init__(self, lengths):
+        self.lengths = lengths
+        self.old = None
+
+    def __enter__(self):
+        self.old = _state['key_len']
+        _state['key_len'] = self.lengths
+        return self
+
+    def __exit__(self, *exc):
+        _state['key_len'] = self.old
+        return False
+
+
+def _key_len(B, T, device, need_grad, p_drop):
+    """The active ragged_batch lengths as a device int32 [B] (None outside the context manager)."""
+    kl = _state['key_len']
+    if kl is None:
+        return None
+    if need_grad or p_drop > 0:
+        raise RuntimeError('ragged_batch is inference only: call model.eval() and run under torch.no_grad()')
+    if not torch.is_tensor(kl) or kl.device != device or kl.dtype != torch.int32:
+        kl = (kl.to(device=device, dtype=torch.int32) if torch.is_tensor(kl) else
+              torch.tensor([int(v) for v in kl], dtype=torch.int32).to(device))
+        _state['key_len'] = kl          # converted once per context, reused by every stack / layer call
+    if kl.numel() != B:
+        raise RuntimeError(f'ragged_batch: {kl.numel()} lengths for a batch of {B} narratives')
+    return kl.contiguous()
 
 
 def manual_seed(seed):
@@ -198,6 +239,10 @@ class AttentionFn(torch.autograd.Function):
         _lib.check_device(qkv.device.index)
         m = mask2d(mask, B, T, qkv.device)
         out = torch.empty((B, T, d), dtype=qkv.dtype, device=qkv.device)
+        kl = _key_len(B, T, qkv.device, any(ctx.needs_input_grad), p_drop)
+        if kl is not None:
+            check(lib().mt_attention_ragged_fwd(dt, B, T, d, h, ptr(qkv), ptr(m), ptr(kl), ptr(out), stream()))
+            return out
         lse = torch.empty((B, h, T), dtype=torch.float32, device=qkv.device)
         seed = next_seed() if p_drop > 0 else 0
         check(lib().mt_attention_fwd(dt, B, T, d, h, ptr(qkv), ptr(m), ptr(out), ptr(lse), p_drop, seed, 0, stream()))
@@ -351,7 +396,10 @@ class EncoderFn(torch.autograd.Function):
         p_drop = float(cfgd['p_drop'])
         cfg = _lib.MtEncoderCfg(B, T, d, cfgd['h'], cfgd['dff'], cfgd['n_layers'], dt, int(need_grad), p_drop,
                                 next_seed() if p_drop > 0 else 0, cfgd['stack_id'], int(cfgd.get('y_f32', dt == MT_F32)),
-                                int(cfgd.get('grid_share', 0)))
+                                int(cfgd.get('grid_share', 0)), None)
+        kl = _key_len(B, T, x.device, need_grad, p_drop)
+        if kl is not None:
+            cfg.key_len = kl.data_ptr()
         L = lib()
         nws = L.mt_encoder_ws_bytes(ctypes.byref(cfg))
         if nws == 0:

@@ -49,7 +49,7 @@ def test_struct_layouts_and_size_queries():
     mfn = sum(int(torch.tensor(s).prod()) for k, s in inv.items() if k.startswith('mfn.'))
     assert L.mt_mfn_param_count(ctypes.byref(cfg)) == mfn
     assert L.mt_mfn_ws_bytes(ctypes.byref(cfg)) > 0
-    ecfg = _lib.MtEncoderCfg(2, 16, 256, 8, 128, 6, 0, 1, 0.1, 0, 0, 1, 0)
+    ecfg = _lib.MtEncoderCfg(2, 16, 256, 8, 128, 6, 0, 1, 0.1, 0, 0, 1, 0, None)
     tr = L.mt_encoder_ws_bytes(ctypes.byref(ecfg))
     ecfg.training = 0
     assert 0 < L.mt_encoder_ws_bytes(ctypes.byref(ecfg)) < tr

@@ -221,3 +221,113 @@ def test_ccc_batched_known_answers_and_oracle():
         assert abs(pr[b].item() - pearsonr(p[b, :l].astype(np.float64), a[b, :l].astype(np.float64))[0]) < 1e-12
         want_se += ((p[b, :l].astype(np.float64) - a[b, :l].astype(np.float64)) ** 2).sum()
     assert abs(se.item() - want_se) < 1e-9 * want_se
+
+
+# ---- ragged inference: a padded batch that reproduces one-narrative-at-a-time evaluation -------------------------------------------
+@pytest.mark.parametrize('mode,force,T', [('fp32', None, 37), ('fp32', None, 150), ('bf16', None, 128), ('bf16', None, 100), ('bf16', 'tiled', 128),
+                                          ('bf16', None, 200), ('bf16', 'ffma', 90)])
+def test_ragged_attention_equals_per_narrative_attention(mode, force, T):
+    """Every attention engine (fp32 FFMA, bf16 FFMA, bf16 tiled tensor-core, bf16 whole-head T <= 128 incl. the T == 128 case):
+    with key_len, rows < len of narrative b equal the attention of that narrative alone (T = len, no mask)."""
+    B, d, h = 5, 256, 8
+    L = _lib.lib()
+    mtb.set_compute_dtype(mode)
+    dt = torch.float32 if mode == 'fp32' else torch.bfloat16
+    g = torch.Generator().manual_seed(T)
+    qkv = torch.randn(B, T, 3 * d, generator=g).to(DEV).to(dt)
+    lengths = [T, T - 1, max(1, T // 2), 9, 1]
+    mask = torch.zeros(B, T, 1, device=DEV)
+    for b, l in enumerate(lengths):
+        mask[b, :l] = 1
+    old = L.mt_attention_force_ffma(1) if force == 'ffma' else (L.mt_attention_force_tiled(1) if force == 'tiled' else None)
+    try:
+        with torch.no_grad():
+            with mtb.ragged_batch(lengths):
+                got = K.attention_packed(qkv, mask, h)
+            for b, l in enumerate(lengths):
+                alone = K.attention_packed(qkv[b:b + 1, :l].contiguous(), None, h)
+                assert_close(got[b, :l], alone[0], 1e-5 if mode == 'fp32' else 1e-2, f'narrative {b} (len {l})')
+                q, k, v = [x.float().view(l, h, d // h).transpose(0, 1) for x in qkv[b, :l].split(d, dim=-1)]
+                want = (torch.softmax(q @ k.transpose(1, 2) / (d // h) ** 0.5, -1) @ v).transpose(0, 1).reshape(l, d)
+                assert_close(got[b, :l], want, 2e-5 if mode == 'fp32' else 2e-2, f'narrative {b} vs torch')
+    finally:
+        if force == 'ffma':
+            L.mt_attention_force_ffma(old)
+        elif force == 'tiled':
+            L.mt_attention_force_tiled(old)
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_ragged_batch_equals_one_at_a_time_and_differs_from_padded(mode):
+    """MFT body, eval: inside ragged_batch the valid part of every prediction equals a forward of that narrative alone (the
+    reference's evaluation, batch_size = 1); the plain padded batch (training semantics: padded windows are live keys) does not."""
+    N, B, T = 2, 6, 40
+    dims = {'acoustic': 88, 'image': 256, 'linguistic': 300}
+    mods = ['acoustic', 'image', 'linguistic']
+    sd = util.filled_sd(util.mods_shapes('MFT.MultiTransformer', N), 41)
+    inputs, mask, _, lengths = fill.make_batch(B, T, dims, 41)
+    model = mtb.MultiTransformer(mods, dims, N=N).eval(); model.load_state_dict(sd)
+    mtb.set_compute_dtype(mode)
+    xin = {k: t(v).to(DEV) for k, v in inputs.items()}
+    tol = 1e-5 if mode == 'fp32' else 2e-2
+    with torch.no_grad():
+        padded = model(xin, t(mask).to(DEV), lengths)
+        with mtb.ragged_batch(lengths):
+            ragged = model(xin, t(mask).to(DEV), lengths)
+        worst_pad = 0.0
+        for b, l in enumerate(lengths):
+            alone = model({k: v[b:b + 1, :l].contiguous() for k, v in xin.items()}, torch.ones(1, l, 1, device=DEV), [l])
+            if mode == 'fp32':
+                want = O.multi_transformer(sd, '', {k: t(v[b:b + 1, :l]) for k, v in inputs.items()}, torch.ones(1, l, 1), mods, N=N)
+                assert_close(alone, want, 1e-5, f'alone vs oracle {b}', 1e-7)
+            err = (ragged[b, :l] - alone[0]).abs().max().item()
+            assert err <= tol * max(1.0, alone.abs().max().item()) * (1 if mode == 'bf16' else 1), (b, l, err)
+            assert not ragged[b, l:].any()                            # the output mask still zeroes the padding
+            if l < T:
+                worst_pad = max(worst_pad, (padded[b, :l] - alone[0]).abs().max().item())
+    if mode == 'fp32':
+        assert worst_pad > 1e-4                                       # padded keys DO change valid outputs without ragged_batch
+    model.train()
+    with pytest.raises(RuntimeError, match='inference only'):
+        with mtb.ragged_batch(lengths):
+            model(xin, t(mask).to(DEV), lengths)
+
+
+def test_batched_evaluation_equals_one_at_a_time():
+    """evaluate(): MultiCNNTransformer on raw windows, 9 narratives in batches of 4 with on-device CCC, against the reference's
+    procedure -- one narrative per forward, eval_ccc / pearsonr on the host (MFT/train.py:203-257)."""
+    from scipy.stats import pearsonr
+    m = front_meta()['front_mft']
+    shapes = {k: tuple(v) for k, v in m['shapes'].items()}
+    dims = {k: v[1] for k, v in shapes.items()}
+    model = M.MultiCNNTransformer(m['mods'], dims, m['embed_dims'])
+    inv = front_inventory()['MFT.MultiCNNTransformer']
+    model.load_state_dict(util.filled_sd({k: tuple(s) for k, s in inv.items()}, 5))
+    N, T = 9, 24
+    inputs, mask, target, lengths = fill.make_raw_batch(N, T, shapes, 77)
+    order = np.random.RandomState(1).permutation(N)                   # evaluation sets are not sorted by length
+    inputs = {k: v[order] for k, v in inputs.items()}; mask = mask[order]; lengths = [lengths[i] for i in order]
+    xin = {k: t(v).to(DEV) for k, v in inputs.items()}
+    model.eval()
+    ones, want_pred = [], []
+    with torch.no_grad():
+        for b, l in enumerate(lengths):
+            o = model({k: v[b:b + 1, :l].contiguous() for k, v in xin.items()}, [l], torch.ones(1, l, 1, device=DEV))
+            want_pred.append(o.reshape(-1).cpu().numpy())
+    rs = np.random.RandomState(2)
+    target = np.zeros((N, T, 1), np.float32)
+    for b, l in enumerate(lengths):                                   # targets correlated with the predictions: CCC needs signal
+        p = want_pred[b]
+        target[b, :l, 0] = 0.5 + 5.0 * (p - p.mean()) + 0.01 * rs.standard_normal(l)
+    preds, loss, stats, (bo, bt, bi) = mtb.evaluate(model, xin, t(target).to(DEV), t(mask).to(DEV), lengths, batch_size=4)
+    assert not model.training
+    cccs, corrs, se = [], [], 0.0
+    for b, l in enumerate(lengths):
+        np.testing.assert_allclose(preds[b], want_pred[b], rtol=1e-5, atol=1e-6)
+        cccs.append(eval_ccc(want_pred[b], target[b, :l, 0])); corrs.append(pearsonr(want_pred[b], target[b, :l, 0])[0])
+        se += ((want_pred[b].astype(np.float64) - target[b, :l, 0]) ** 2).sum()
+    assert abs(stats['ccc'] - np.mean(cccs)) < 1e-5 and abs(stats['ccc_std'] - np.std(cccs)) < 1e-5
+    assert abs(stats['corr'] - np.mean(corrs)) < 1e-5 and abs(stats['corr_std'] - np.std(corrs)) < 1e-5
+    assert abs(stats['max_ccc'] - max(cccs)) < 1e-5 and bi == int(np.argmax(cccs)) + 1
+    assert abs(loss - se / sum(lengths)) < 1e-5 * (se / sum(lengths))
+    np.testing.assert_allclose(bt, target[bi - 1, :lengths[bi - 1], 0])
