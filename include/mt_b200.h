@@ -248,6 +248,15 @@ int mt_ccc_batched(const float* pred, const float* target, const int* lengths, i
                    double* sq_err, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * GPU-side batcher: the padded corpus stays on the device; a batch is an index gather instead of the
+ * reference's torch.tensor(nested python lists) per batch (generateTrainBatch / generateInputChunkHelper MFT/train.py:59-108).
+ * mt_batch_gather: dst[b, 0:prefix] = src[idx[b] * row_stride + 0:prefix] for b < B (fp32; idx device int [B]; prefix <= row_stride:
+ * the first T_batch windows of a narrative are a contiguous prefix of its row).  mt_length_mask: mask[b,t] = t < lengths[b] (:103-106).
+ * ------------------------------------------------------------------------------------------------- */
+int mt_batch_gather(const float* src, size_t row_stride, const int* idx, int B, size_t prefix, float* dst, void* stream);
+int mt_length_mask(const int* lengths, int B, int T, float* mask, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Utilities on flat buffers.
  * ------------------------------------------------------------------------------------------------- */
 /* out = x + dropout(y) (SublayerConnection.forward MFT/multiTransformer.py:103-104, stand-alone path; x may be NULL)

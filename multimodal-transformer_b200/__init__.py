@@ -8,3 +8,4 @@ from .multiTransformer import *          # noqa: F401,F403  (the reference's cla
 from .multiTransformer import fusion_layer
 from .models import *                    # noqa: F401,F403  (models.py: CNN, Highway, MultiCNNTransformer variants)
 from .evaluation import evaluate          # noqa: F401
+from .batching import DeviceCorpus, generateTrainBatch          # noqa: F401

@@ -87,6 +87,8 @@ _PROTOS = {
     'mt_window_cnn_fwd': (c_int, [POINTER(MtWindowCnnCfg), P, P, P, P, P, P, P, P, P, c_size_t, P]),
     'mt_window_cnn_bwd': (c_int, [POINTER(MtWindowCnnCfg), P, P, P, P, P, P, P, P, P, P, c_size_t, P]),
     'mt_ccc_batched': (c_int, [P, P, P, c_int, c_int, P, P, P, P]),
+    'mt_batch_gather': (c_int, [P, c_size_t, P, c_int, c_size_t, P, P]),
+    'mt_length_mask': (c_int, [P, c_int, c_int, P, P]),
     'mt_residual_dropout_fwd': (c_int, [P, P, P, c_size_t, c_float, c_uint64, c_uint32, P]),
     'mt_dropout_bwd': (c_int, [P, P, c_size_t, c_float, c_uint64, c_uint32, P]),
     'mt_cast_f32_to_bf16': (c_int, [P, P, c_size_t, P]),

@@ -59,3 +59,59 @@ extern "C" int mt_ccc_batched(const float* pred, const float* target, const int*
   MT_LAUNCH_CHECK();
   return MT_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// GPU-side batcher: the reference assembles every batch with torch.tensor(nested python lists) and a sort by
+// length (generateTrainBatch / generateInputChunkHelper, MFT/train.py:59-108).  Here the padded corpus lives on the device once and
+// a batch is an index gather: dst[b, :prefix] = src[idx[b], :prefix] (the first T_batch windows of narrative idx[b]).
+// ---------------------------------------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void gather_prefix_kernel(const float* __restrict__ src, size_t row_stride, const int* __restrict__ idx, int B, size_t prefix,
+                                     float* __restrict__ dst, int vec) {
+  // grid.y = narrative of the batch; grid.x strides over its prefix
+  const int b = blockIdx.y;
+  const float* s = src + (size_t)idx[b] * row_stride;
+  float* d = dst + (size_t)b * prefix;
+  if (vec) {
+    const size_t n4 = prefix / 4;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+      reinterpret_cast<float4*>(d)[i] = __ldg(reinterpret_cast<const float4*>(s) + i);
+  } else {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < prefix; i += (size_t)gridDim.x * blockDim.x) d[i] = s[i];
+  }
+}
+
+// mask[b, t] = t < lengths[b]   (MFT/train.py:103-106)
+__global__ void length_mask_kernel(const int* __restrict__ lengths, int B, int T, float* __restrict__ mask) {
+  const size_t n = (size_t)B * T;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    mask[i] = (int)(i % T) < lengths[i / T] ? 1.f : 0.f;
+}
+
+}  // namespace
+
+extern "C" int mt_batch_gather(const float* src, size_t row_stride, const int* idx, int B, size_t prefix, float* dst, void* stream) {
+  if (!src || !idx || !dst || B <= 0 || prefix == 0 || prefix > row_stride) return MT_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int vec = (prefix % 4 == 0 && row_stride % 4 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0) ? 1 : 0;
+  const size_t work = vec ? prefix / 4 : prefix;
+  size_t gx = (work + 255) / 256;
+  const size_t cap = (size_t)(148 * 8 + B - 1) / B;          // ~8 CTAs per SM over the whole batch
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  mt_prof_work(0.0, 8.0 * (double)B * (double)prefix);
+  gather_prefix_kernel<<<dim3((unsigned)gx, (unsigned)B), 256, 0, st>>>(src, row_stride, idx, B, prefix, dst, vec);
+  MT_LAUNCH_CHECK();
+  return MT_OK;
+}
+
+extern "C" int mt_length_mask(const int* lengths, int B, int T, float* mask, void* stream) {
+  if (!lengths || !mask || B <= 0 || T <= 0) return MT_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t g = ((size_t)B * T + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  length_mask_kernel<<<(unsigned)g, 256, 0, st>>>(lengths, B, T, mask);
+  MT_LAUNCH_CHECK();
+  return MT_OK;
+}

@@ -114,6 +114,22 @@ def next_seed():
     return (_state['seed'] * 0x9E3779B97F4A7C15 + _state['counter']) & 0xFFFFFFFFFFFFFFFF
 
 
+def _apply(fn, *args):
+    """fn.apply(*args) with the caller's grad mode made visible to fn.forward: autograd runs every Function.forward with grad mode off
+    and reports `needs_input_grad` from `requires_grad` alone, so without this an inference call under torch.no_grad() would keep the
+    whole backward stash."""
+    old = _state.get('grad', True)
+    _state['grad'] = torch.is_grad_enabled()
+    try:
+        return fn.apply(*args)
+    finally:
+        _state['grad'] = old
+
+
+def _need_grad(ctx):
+    return _state.get('grad', True) and any(ctx.needs_input_grad)
+
+
 def _adt():
     return torch.float32 if _state['dtype'] == MT_F32 else torch.bfloat16
 
@@ -239,7 +255,7 @@ class AttentionFn(torch.autograd.Function):
         _lib.check_device(qkv.device.index)
         m = mask2d(mask, B, T, qkv.device)
         out = torch.empty((B, T, d), dtype=qkv.dtype, device=qkv.device)
-        kl = _key_len(B, T, qkv.device, any(ctx.needs_input_grad), p_drop)
+        kl = _key_len(B, T, qkv.device, _need_grad(ctx), p_drop)
         if kl is not None:
             check(lib().mt_attention_ragged_fwd(dt, B, T, d, h, ptr(qkv), ptr(m), ptr(kl), ptr(out), stream()))
             return out
@@ -264,7 +280,7 @@ class AttentionFn(torch.autograd.Function):
 
 
 def attention_packed(qkv, mask, h, p_drop=0.0):
-    return AttentionFn.apply(qkv, mask, h, float(p_drop))
+    return _apply(AttentionFn, qkv, mask, h, float(p_drop))
 
 
 def attention_probs(qkv, mask, h):
@@ -392,7 +408,7 @@ class EncoderFn(torch.autograd.Function):
         flat = arena.bind()
         lp = arena.shadow() if dt == MT_BF16 else None
         m = mask2d(mask, B, T, x.device)
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = _need_grad(ctx)
         p_drop = float(cfgd['p_drop'])
         cfg = _lib.MtEncoderCfg(B, T, d, cfgd['h'], cfgd['dff'], cfgd['n_layers'], dt, int(need_grad), p_drop,
                                 next_seed() if p_drop > 0 else 0, cfgd['stack_id'], int(cfgd.get('y_f32', dt == MT_F32)),
@@ -429,7 +445,7 @@ class EncoderFn(torch.autograd.Function):
 
 
 def encoder_stack(x, mask, arena, cfgd):
-    return EncoderFn.apply(x, mask, arena, cfgd, *arena.params)
+    return _apply(EncoderFn, x, mask, arena, cfgd, *arena.params)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -451,7 +467,7 @@ class MfnFn(torch.autograd.Function):
         flat = arena.bind()
         lp = arena.shadow() if dt == MT_BF16 else None
         m = mask2d(mask, B, T, dev)
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = _need_grad(ctx)
         cfg = _lib.MtMfnCfg()
         cfg.B, cfg.T, cfg.n_mods = B, T, n_mods
         for i in range(n_mods):
@@ -536,7 +552,7 @@ class MfnFn(torch.autograd.Function):
 
 
 def mfn_forward(xs, mask, arena, cfgd, t_major):
-    return MfnFn.apply(mask, arena, cfgd, bool(t_major), len(xs), *xs, *arena.params)
+    return _apply(MfnFn, mask, arena, cfgd, bool(t_major), len(xs), *xs, *arena.params)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -591,7 +607,7 @@ class LstmHeadFn(torch.autograd.Function):
         flat = arena.bind()
         lp = arena.shadow() if dt == MT_BF16 else None
         m = mask2d(mask, B, T, enc.device)
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = _need_grad(ctx)
         cfg = _lib.MtLstmHeadCfg(B, T, E, Hd, dt, int(need_grad))
         L = lib()
         nws = L.mt_lstm_head_ws_bytes(ctypes.byref(cfg))
@@ -621,7 +637,7 @@ class LstmHeadFn(torch.autograd.Function):
 
 
 def lstm_head(enc, mask, arena, E, Hd):
-    return LstmHeadFn.apply(enc, mask, arena, E, Hd, *arena.params)
+    return _apply(LstmHeadFn, enc, mask, arena, E, Hd, *arena.params)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -658,7 +674,7 @@ class WindowCnnFn(torch.autograd.Function):
         n_win = 1
         for s in lead:
             n_win *= int(s)
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = _need_grad(ctx)
         seed = next_seed() if p_drop > 0 else 0
         cfg = _lib.MtWindowCnnCfg(dt, n_win, K, D, E, k, stages, int(need_grad), float(p_drop), seed, site)
         L = lib()
@@ -692,15 +708,15 @@ class WindowCnnFn(torch.autograd.Function):
 
 def window_cnn(x, conv_w, conv_b, wproj, bproj, wgate, bgate, p_drop=0.0, site=0x6000):
     """CNN + Highway + dropout of one modality: [..., K, D] -> [..., E]."""
-    return WindowCnnFn.apply(x, conv_w, conv_b, wproj, bproj, wgate, bgate, 3, float(p_drop), int(site))
+    return _apply(WindowCnnFn, x, conv_w, conv_b, wproj, bproj, wgate, bgate, 3, float(p_drop), int(site))
 
 
 def conv_maxpool(x, conv_w, conv_b):
-    return WindowCnnFn.apply(x, conv_w, conv_b, None, None, None, None, 1, 0.0, 0)
+    return _apply(WindowCnnFn, x, conv_w, conv_b, None, None, None, None, 1, 0.0, 0)
 
 
 def highway(x, wproj, bproj, wgate, bgate, p_drop=0.0, site=0x6000):
-    return WindowCnnFn.apply(x, None, None, wproj, bproj, wgate, bgate, 2, float(p_drop), int(site))
+    return _apply(WindowCnnFn, x, None, None, wproj, bproj, wgate, bgate, 2, float(p_drop), int(site))
 
 
 def ccc_batched(pred, target, lengths):

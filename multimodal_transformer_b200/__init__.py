@@ -7,6 +7,7 @@ from .functional import (ccc_batched, fix_seed, get_compute_dtype, manual_seed, 
 from . import functional, multiTransformer                                                    # noqa: E402,F401
 from .multiTransformer import *                                                              # noqa: E402,F401,F403
 from .multiTransformer import fusion_layer                                                    # noqa: E402,F401
-from . import models, evaluation                                                              # noqa: E402,F401
+from . import models, evaluation, batching                                                              # noqa: E402,F401
 from .models import *                                                                        # noqa: E402,F401,F403
 from .evaluation import evaluate                                                              # noqa: E402,F401
+from .batching import DeviceCorpus, generateTrainBatch                                        # noqa: E402,F401

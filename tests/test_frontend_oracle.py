@@ -127,3 +127,40 @@ def test_raw_batch_generator_shapes_and_padding():
         assert not inputs['linguistic'][b, l:].any() and not inputs['image'][b, l:].any()
         assert inputs['linguistic'][b, :l, :2].all(axis=-1).all()        # at least two real vectors per valid window
     assert (target * (1 - mask) == 0).all()
+
+
+# ---- batcher -----------------------------------------------------------------------------------------------------------------------
+def _digest(a):
+    import hashlib
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+    return [list(a.shape), hashlib.sha256(a.tobytes()).hexdigest()]
+
+
+def batcher_gold():
+    with open(os.path.join(util.GOLD, 'batcher.json')) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize('tag,bs,on_eval', [('train_bs4', 4, False), ('eval_bs1', 1, True), ('eval_bs5', 5, True)])
+def test_batcher_oracle_matches_reference_batches(tag, bs, on_eval):
+    """The restated batcher yields bit-identical batches to the reference's own generateTrainBatch (same python RNG seed)."""
+    import random
+    from oracle.batcher_oracle import generate_train_batch
+    from oracle.make_golden_batcher import corpus
+    data, target, lengths = corpus()
+    random.seed(123)
+    got = list(generate_train_batch(data, target, lengths, batch_size=bs, on_eval=on_eval))
+    want = batcher_gold()[tag]
+    assert len(got) == len(want)
+    for (d, tg, mask, ln), w in zip(got, want):
+        assert ln == w['lengths']
+        assert _digest(tg) == w['target'] and _digest(mask) == w['mask']
+        for m_, v in d.items():
+            assert _digest(v) == w['data'][m_], m_
+
+
+def test_device_corpus_needs_a_gpu():
+    from oracle.make_golden_batcher import corpus
+    data, target, lengths = corpus()
+    with pytest.raises(RuntimeError, match='CUDA'):
+        mtb.DeviceCorpus(data, target, lengths, device='cpu')

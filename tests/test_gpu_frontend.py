@@ -331,3 +331,51 @@ def test_batched_evaluation_equals_one_at_a_time():
     assert abs(stats['max_ccc'] - max(cccs)) < 1e-5 and bi == int(np.argmax(cccs)) + 1
     assert abs(loss - se / sum(lengths)) < 1e-5 * (se / sum(lengths))
     np.testing.assert_allclose(bt, target[bi - 1, :lengths[bi - 1], 0])
+
+
+# ---- GPU-side batcher -----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('tag,bs,on_eval', [('train_bs4', 4, False), ('eval_bs1', 1, True), ('eval_bs5', 5, True)])
+def test_device_batcher_yields_the_reference_batches(tag, bs, on_eval):
+    """DeviceCorpus / generateTrainBatch (index gather on the device) against the golden digests of the reference's own
+    generateTrainBatch: bit-exact data, target, mask and lengths, same batch order under the same python RNG seed."""
+    import hashlib
+    import random
+    from oracle.make_golden_batcher import corpus
+    with open(os.path.join(util.GOLD, 'batcher.json')) as f:
+        want = json.load(f)[tag]
+
+    def dg(x):
+        a = np.ascontiguousarray(x.cpu().numpy().astype(np.float32))
+        return [list(a.shape), hashlib.sha256(a.tobytes()).hexdigest()]
+
+    data, target, lengths = corpus()
+    random.seed(123)
+    got = list(mtb.generateTrainBatch(data, target, lengths, None, batch_size=bs, onEval=on_eval))
+    assert len(got) == len(want)
+    for (d, tg, mask, ln), w in zip(got, want):
+        assert ln == w['lengths'] and dg(tg) == w['target'] and dg(mask) == w['mask']
+        assert all(v.is_cuda for v in d.values()) and tg.is_cuda and mask.is_cuda
+        for m_, v in d.items():
+            assert dg(v) == w['data'][m_], m_
+
+
+def test_device_batcher_large_rows_and_odd_sizes():
+    """Vector and scalar copy paths, many narratives, prefix shorter than the row: against the oracle batcher."""
+    import random
+    from oracle.batcher_oracle import generate_train_batch
+    rs = np.random.RandomState(8)
+    n, t_max = 70, 33
+    lengths = [int(v) for v in rs.randint(1, t_max + 1, size=n)]
+    data = {'a': rs.standard_normal((n, t_max, 3, 7)).astype(np.float32), 'b': rs.standard_normal((n, t_max, 2, 88)).astype(np.float32)}
+    target = rs.uniform(0, 1, (n, t_max)).astype(np.float32)
+    corpus = mtb.DeviceCorpus(data, target, lengths)
+    random.seed(5)
+    got = list(corpus.generateTrainBatch(batch_size=32))
+    random.seed(5)
+    want = list(generate_train_batch(data, target, lengths, batch_size=32))
+    assert len(got) == len(want) == 3
+    for (d, tg, mask, ln), (dw, tw, mw, lw) in zip(got, want):
+        assert ln == lw
+        assert np.array_equal(tg.cpu().numpy(), tw) and np.array_equal(mask.cpu().numpy(), mw)
+        for m_ in d:
+            assert np.array_equal(d[m_].cpu().numpy(), dw[m_]), m_
