@@ -37,12 +37,17 @@ class DeviceCorpus:
                 raise RuntimeError(f'{mod}: {a.shape[0]} narratives, {self.N} lengths')
             self.data[mod] = a.to(self.device, torch.float32).contiguous()
             self.row_shape[mod] = tuple(a.shape[1:])
+            if a.shape[1] < max(self.lengths):
+                raise RuntimeError(f'{mod}: padded to {a.shape[1]} windows but the longest narrative has {max(self.lengths)}')
         tg = input_target if torch.is_tensor(input_target) else torch.from_numpy(np.asarray(input_target, dtype=np.float32))
         self.target = tg.to(self.device, torch.float32).reshape(self.N, -1).contiguous()
         self.T_max = self.target.shape[1]
 
     def __len__(self):
         return self.N
+
+    def _alloc(self, B, per_win, T, t_cap):
+        return torch.empty(B * t_cap * per_win, dtype=torch.float32, device=self.device)[:B * T * per_win]
 
     def batch(self, chunk):
         """One batch from a list of corpus indices (the reference's `chunk`)."""
@@ -56,12 +61,15 @@ class DeviceCorpus:
         data = {}
         for mod, src in self.data.items():
             per_win = int(np.prod(self.row_shape[mod][1:])) if len(self.row_shape[mod]) > 1 else 1
-            out = torch.empty((B, T) + self.row_shape[mod][1:], dtype=torch.float32, device=self.device)
-            check(L.mt_batch_gather(ptr(src), src[0].numel(), ptr(idx), B, T * per_win, ptr(out), stream()))
+            # always allocate for T_max and hand out the contiguous prefix: constant block sizes hit the caching allocator every time
+            # (a fresh cudaMalloc of a few hundred MB per batch costs milliseconds, more than the gather itself)
+            t_mod = self.row_shape[mod][0]                      # this modality's padded window count (>= every length)
+            out = self._alloc(B, per_win, T, t_mod).view((B, T) + self.row_shape[mod][1:])
+            check(L.mt_batch_gather(ptr(src), t_mod * per_win, ptr(idx), B, T * per_win, ptr(out), stream()))
             data[mod] = out
-        target = torch.empty((B, T, 1), dtype=torch.float32, device=self.device)
+        target = self._alloc(B, 1, T, self.T_max).view(B, T, 1)
         check(L.mt_batch_gather(ptr(self.target), self.T_max, ptr(idx), B, T, ptr(target), stream()))
-        mask = torch.empty((B, T, 1), dtype=torch.float32, device=self.device)
+        mask = self._alloc(B, 1, T, self.T_max).view(B, T, 1)
         check(L.mt_length_mask(ptr(ln), B, T, ptr(mask), stream()))
         return data, target, mask, lengths
 
