@@ -207,7 +207,9 @@ class GraphedTrainStep:
         from . import _lib
         self.model, self.opt, self.B, self.T, self.device = model, opt, B, T, device
         self.mods = list(in_dims)
-        self.x = {m: torch.zeros(B, T, d, device=device) for m, d in in_dims.items()}
+        # in_dims: mod -> feature width (hot-path models, inputs [B,T,d]) or mod -> (K, D) (MultiCNNTransformer variants, raw windows
+        # [B,T,K,D]: the window front-end is then part of the captured step)
+        self.x = {m: torch.zeros((B, T) + (tuple(d) if isinstance(d, (tuple, list)) else (d,)), device=device) for m, d in in_dims.items()}
         self.mask = torch.zeros(B, T, 1, device=device)
         self.target = torch.zeros(B, T, 1, device=device)
         self.inv_norm = torch.ones(1, device=device)
@@ -235,7 +237,8 @@ class GraphedTrainStep:
         self.seed_off.add_(1)
         self.step_t.add_(1)
         self.model.train()
-        pred = self.model(self.x, self.mask, self.lengths)
+        from .evaluation import _call                  # models.py classes take (inputs, length, mask), multiTransformer.py's (inputs, mask, lengths)
+        pred = _call(self.model, self.x, self.mask, self.lengths)
         loss, dpred = K.mse_loss_sum_normalised_dev(pred.detach(), self.target, self.inv_norm)
         old = K.set_deferred_weight_grads(True)        # MFN weight gradients overlap the encoder stacks' backward
         try:
@@ -348,7 +351,9 @@ class GraphedForward:
     def __init__(self, model, B, T, in_dims, device, warmup=2):
         self.model, self.B, self.T, self.device = model, B, T, device
         self.mods = list(in_dims)
-        self.x = {m: torch.zeros(B, T, d, device=device) for m, d in in_dims.items()}
+        # in_dims: mod -> feature width (hot-path models, inputs [B,T,d]) or mod -> (K, D) (MultiCNNTransformer variants, raw windows
+        # [B,T,K,D]: the window front-end is then part of the captured step)
+        self.x = {m: torch.zeros((B, T) + (tuple(d) if isinstance(d, (tuple, list)) else (d,)), device=device) for m, d in in_dims.items()}
         self.mask = torch.zeros(B, T, 1, device=device)
         self.lengths = [T] * B
         self.warmup = warmup

@@ -379,3 +379,70 @@ def test_device_batcher_large_rows_and_odd_sizes():
         assert np.array_equal(tg.cpu().numpy(), tw) and np.array_equal(mask.cpu().numpy(), mw)
         for m_ in d:
             assert np.array_equal(d[m_].cpu().numpy(), dw[m_]), m_
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_graphed_train_step_with_window_front_end(mode):
+    """GraphedTrainStep over a MultiCNNTransformer (raw windows in, front-end + hot path + loss + backward + Adam in one CUDA graph)
+    replays to the same losses / parameters as eager steps with FlatAdam (dropout off: both deterministic)."""
+    from multimodal_transformer_b200.training import FlatAdam, GraphedTrainStep, train_step_loss
+    m = front_meta()['front_mft']
+    shapes = {k: tuple(v) for k, v in m['shapes'].items()}
+    dims = {k: v[1] for k, v in shapes.items()}
+    inv = front_inventory()['MFT.MultiCNNTransformer']
+    sd = util.filled_sd({k: tuple(s) for k, s in inv.items()}, 9)
+    B, T = 4, 10
+    batches = [fill.make_raw_batch(B, T, shapes, 80 + i) for i in range(3)]
+    mtb.set_compute_dtype(mode)
+
+    def fresh():
+        model = M.MultiCNNTransformer(m['mods'], dims, m['embed_dims']); model.load_state_dict(sd)
+        for mod in model.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+            if hasattr(mod, 'p_drop'):
+                mod.p_drop = 0.0
+        return model, FlatAdam(model, lr=1e-3, weight_decay=1e-4)
+
+    def no_dropout(model):                             # MFN / encoder dropout probabilities live in their cfg dicts
+        for mod in model.modules():
+            for attr in ('cfgd', '_cfgd'):
+                d = getattr(mod, attr, None)
+                if isinstance(d, dict):
+                    for k in list(d):
+                        if k.startswith('p_'):
+                            d[k] = 0.0
+
+    mtb.fix_seed(77)                                   # same dropout masks on both paths would need the graph's seed offsets: switch sites off instead
+    model_e, opt_e = fresh(); no_dropout(model_e)
+    losses_e = []
+    for inputs, mask, target, lengths in batches:
+        model_e.eval()                                  # eval(): every dropout off, gradients still flow -- deterministic reference for the graph
+        pred = model_e({k: t(v).to(DEV) for k, v in inputs.items()}, lengths, t(mask).to(DEV))
+        losses_e.append(train_step_loss(pred, t(target).to(DEV), float(sum(lengths))).item())
+        opt_e.step(); opt_e.zero_grad()
+    del pred
+
+    model_g, opt_g = fresh(); no_dropout(model_g)
+
+    class EvalStep(GraphedTrainStep):                   # the captured step calls model.train(); keep it in eval() for the comparison
+        def _step(self):
+            tr = self.model.train
+            self.model.train = lambda *a, **k: self.model
+            try:
+                return super()._step()
+            finally:
+                self.model.train = tr
+
+    model_g.eval()
+    gstep = EvalStep(model_g, opt_g, B, T, shapes, torch.device(DEV), warmup=2)
+    losses_g = [gstep({k: t(v) for k, v in inputs.items()}, t(mask), t(target), lengths).item() for inputs, mask, target, lengths in batches]
+    assert opt_g.step_count == 3
+    for a, b in zip(losses_e, losses_g):
+        assert abs(a - b) <= (1e-4 if mode == 'fp32' else 3e-2) * abs(a), (losses_e, losses_g)
+    if mode == 'fp32':          # bf16: three Adam steps at lr 1e-3 move a weight by at most 3e-3 whatever the gradient noise -- the losses are the check
+        pe = dict(model_e.named_parameters())
+        for k, p in model_g.named_parameters():
+            if k.startswith(('Transformer.attn', 'Transformer.ff')):
+                continue
+            assert_close(p, pe[k], 2e-4, k, 1e-6)
