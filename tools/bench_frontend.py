@@ -48,10 +48,13 @@ def main():
     ap.add_argument('--dtype', default='bf16')
     ap.add_argument('--iters', type=int, default=10)
     ap.add_argument('--cpu-narratives', type=int, default=4)
+    ap.add_argument('--gemm-mode', type=int, default=-1, help='mt_gemm_tc_mode override (tuning experiments)')
     args = ap.parse_args()
     dev = torch.device('cuda:0')
     mtb.set_compute_dtype(args.dtype)
     L = _lib.lib()
+    if args.gemm_mode >= 0:
+        L.mt_gemm_tc_mode(args.gemm_mode)
     out = {'workload': f'window front-end, B={args.B} T={args.T}, {args.dtype}', 'mods': {}}
     tot_f = tot_t = 0.0
     for mod, (Kv, D, E) in MODS.items():
