@@ -73,6 +73,29 @@ class DeviceCorpus:
         check(L.mt_length_mask(ptr(ln), B, T, ptr(mask), stream()))
         return data, target, mask, lengths
 
+    def batch_into(self, chunk, x, target, mask):
+        """Gather one batch straight into preallocated [B, T, ...] tensors (e.g. the static inputs of a captured train step,
+        GraphedTrainStep.x / .target / .mask) -- no intermediate batch tensors, no second copy.  Every narrative is taken up to the
+        buffers' T windows (the corpus is zero-padded beyond a narrative's length, so the tail arrives as zeros).  Returns lengths."""
+        order = sorted(range(len(chunk)), key=lambda i: -self.lengths[chunk[i]])
+        rows = [chunk[i] for i in order]
+        lengths = [self.lengths[r] for r in rows]
+        B, T = target.shape[0], target.shape[1]
+        if len(rows) != B or lengths[0] > T or T > self.T_max:
+            raise RuntimeError(f'batch_into: {len(rows)} narratives up to {lengths[0]} windows do not fit buffers of [{B}, {T}]')
+        meta = torch.tensor(rows + lengths, dtype=torch.int32).to(self.device, non_blocking=True)
+        idx, ln = meta[:B], meta[B:]
+        L = lib()
+        for mod, src in self.data.items():
+            per_win = int(np.prod(self.row_shape[mod][1:])) if len(self.row_shape[mod]) > 1 else 1
+            dst = x[mod]
+            if tuple(dst.shape) != (B, T) + self.row_shape[mod][1:] or not dst.is_contiguous() or dst.dtype != torch.float32:
+                raise RuntimeError(f'batch_into: buffer for {mod} must be contiguous float32 {(B, T) + self.row_shape[mod][1:]}')
+            check(L.mt_batch_gather(ptr(src), self.row_shape[mod][0] * per_win, ptr(idx), B, T * per_win, ptr(dst), stream()))
+        check(L.mt_batch_gather(ptr(self.target), self.T_max, ptr(idx), B, T, ptr(target), stream()))
+        check(L.mt_length_mask(ptr(ln), B, T, ptr(mask), stream()))
+        return lengths
+
     def generateTrainBatch(self, batch_size=25, onEval=False):
         index = list(range(self.N))
         if not onEval:

@@ -233,6 +233,18 @@ class GraphedTrainStep:
         if lr != getattr(self, '_lr_seen', None):
             self.lr.fill_(lr); self._lr_seen = lr
 
+    def step_from_corpus(self, corpus, chunk):
+        """One train step on the narratives `chunk` (corpus indices) of a batching.DeviceCorpus: the GPU batcher gathers them straight
+        into the graph's static inputs (no intermediate batch, no second copy), then the captured step replays."""
+        lengths = corpus.batch_into(chunk, self.x, self.target, self.mask)
+        self.inv_norm.fill_(1.0 / self.norm_fn(lengths))
+        lr = float(self.opt.param_groups[0]['lr'])
+        if lr != getattr(self, '_lr_seen', None):
+            self.lr.fill_(lr); self._lr_seen = lr
+        if self.graph is None:
+            self.capture()
+        return self.replay()
+
     def _step(self):
         self.seed_off.add_(1)
         self.step_t.add_(1)

@@ -446,3 +446,31 @@ def test_graphed_train_step_with_window_front_end(mode):
             if k.startswith(('Transformer.attn', 'Transformer.ff')):
                 continue
             assert_close(p, pe[k], 2e-4, k, 1e-6)
+
+
+def test_batch_into_static_buffers_equals_batch():
+    """DeviceCorpus.batch_into (gather straight into preallocated [B, T, ...] buffers, T >= the batch's longest narrative) gives the
+    same tensors as batch() zero-extended to T."""
+    rs = np.random.RandomState(3)
+    n, t_max, T = 20, 17, 15
+    lengths = [int(v) for v in rs.randint(1, T + 1, size=n)]
+    data = {'a': rs.standard_normal((n, t_max, 3, 8)).astype(np.float32), 'b': rs.standard_normal((n, t_max, 2, 5)).astype(np.float32)}
+    target = rs.uniform(0, 1, (n, t_max)).astype(np.float32)
+    for i, l in enumerate(lengths):
+        for v in data.values():
+            v[i, l:] = 0
+        target[i, l:] = 0
+    corpus = mtb.DeviceCorpus(data, target, lengths)
+    chunk = [int(v) for v in rs.permutation(n)[:8]]
+    d, tg, mask, ln = corpus.batch(chunk)
+    x = {m_: torch.full((8, T) + v.shape[2:], 7.0, device=DEV) for m_, v in data.items()}
+    tgt, msk = torch.full((8, T, 1), 7.0, device=DEV), torch.full((8, T, 1), 7.0, device=DEV)
+    ln2 = corpus.batch_into(chunk, x, tgt, msk)
+    Tb = ln[0]
+    assert ln2 == ln
+    for m_ in d:
+        assert torch.equal(x[m_][:, :Tb], d[m_]) and not x[m_][:, Tb:].any()
+    assert torch.equal(tgt[:, :Tb], tg) and not tgt[:, Tb:].any()
+    assert torch.equal(msk[:, :Tb], mask) and not msk[:, Tb:].any()
+    with pytest.raises(RuntimeError, match='do not fit'):
+        corpus.batch_into(chunk[:5], x, tgt, msk)
