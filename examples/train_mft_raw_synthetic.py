@@ -64,8 +64,6 @@ for epoch in range(1, args.epochs + 1):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     # evaluation: many narratives per forward (ragged_batch), CCC / Pearson on the device -- evaluate() MFT/train.py:203-257
-    _, vloss, stats, best = mtb.evaluate(model, valid.data, valid.target.unsqueeze(-1),
-                                         (torch.arange(T, device=device)[None, :] < torch.tensor(valid.lengths, device=device)[:, None])
-                                         .float().unsqueeze(-1), valid.lengths, batch_size=64)
+    _, vloss, stats, best = mtb.evaluate(model, valid, batch_size=64)
     print(f'epoch {epoch}: train loss {loss_sum / n_points:.5f} ({n_train / dt:.0f} narratives/s)  '
           f'valid loss {vloss:.5f} corr {stats["corr"]:.3f} ccc {stats["ccc"]:.4f} max ccc {stats["max_ccc"]:.4f}')

@@ -46,6 +46,13 @@ class DeviceCorpus:
     def __len__(self):
         return self.N
 
+    def length_mask(self):
+        """[N, T_max, 1] float mask of the whole corpus (1 for the valid windows of every narrative)."""
+        ln = torch.tensor(self.lengths, dtype=torch.int32).to(self.device)
+        mask = torch.empty((self.N, self.T_max, 1), dtype=torch.float32, device=self.device)
+        check(lib().mt_length_mask(ptr(ln), self.N, self.T_max, ptr(mask), stream()))
+        return mask
+
     def _alloc(self, B, per_win, T, t_cap):
         return torch.empty(B * t_cap * per_win, dtype=torch.float32, device=self.device)[:B * T * per_win]
 

@@ -21,8 +21,9 @@ def _call(model, inputs, mask, lengths):
     return model(inputs, mask, lengths)                   # multiTransformer.py signature: forward(inputs, mask, lengths)
 
 
-def evaluate(model, inputs, target, mask, lengths, batch_size=64):
-    """inputs: dict mod -> [N, T, ...] (or one tensor [N, T, F] for the single-input models), target / mask [N, T, 1], lengths: N ints
+def evaluate(model, inputs, target=None, mask=None, lengths=None, batch_size=64):
+    """`evaluate(model, corpus)` with a batching.DeviceCorpus, or explicit tensors --
+    inputs: dict mod -> [N, T, ...] (or one tensor [N, T, F] for the single-input models), target / mask [N, T, 1], lengths: N ints
     (any order; every narrative is padded to the common T).  All tensors on the model's GPU.
 
     Returns (predictions, loss, stats, (best_output, best_target, best_index)) like evaluate() MFT/train.py:203-257:
@@ -30,6 +31,12 @@ def evaluate(model, inputs, target, mask, lengths, batch_size=64):
       loss         sum of squared errors over valid time-points / number of valid time-points               (:229-231,249)
       stats        {'corr', 'corr_std', 'ccc', 'ccc_std', 'max_ccc'}                                       (:251-252)
       best_*       prediction / target of the narrative with the highest CCC and its 1-based position       (:240-245)"""
+    from .batching import DeviceCorpus
+    if isinstance(inputs, DeviceCorpus):
+        corpus = inputs
+        inputs, lengths = corpus.data, corpus.lengths
+        target = corpus.target.unsqueeze(-1)
+        mask = corpus.length_mask()
     lengths = [int(v) for v in lengths]
     N = len(lengths)
     was_training = model.training

@@ -331,6 +331,10 @@ def test_batched_evaluation_equals_one_at_a_time():
     assert abs(stats['max_ccc'] - max(cccs)) < 1e-5 and bi == int(np.argmax(cccs)) + 1
     assert abs(loss - se / sum(lengths)) < 1e-5 * (se / sum(lengths))
     np.testing.assert_allclose(bt, target[bi - 1, :lengths[bi - 1], 0])
+    # the same through a device-resident corpus: evaluate(model, corpus)
+    corpus = mtb.DeviceCorpus(inputs, target[..., 0], lengths)
+    preds2, loss2, stats2, _ = mtb.evaluate(model, corpus, batch_size=4)
+    assert abs(loss2 - loss) < 1e-12 and stats2 == stats and all(np.array_equal(a, b) for a, b in zip(preds, preds2))
 
 
 # ---- GPU-side batcher -----------------------------------------------------------------------------------------------------------------
