@@ -108,12 +108,15 @@ def main():
         return mtb.evaluate(model, feats, tgt, mask, lengths, batch_size=args.batch)
 
     def one_at_a_time():
-        from oracle.ccc import eval_ccc              # the checker's eval_ccc stands in for the reference's host-side statistics
+        def eval_ccc(y_true, y_pred):                # the reference's host-side statistic (MFT/train.py:42-50), numpy as there
+            tm, pm = y_true.mean(), y_pred.mean()
+            cov = ((y_true - tm) * (y_pred - pm)).mean()
+            return 2 * cov / (y_true.var() + y_pred.var() + (pm - tm) ** 2)
         cc = []
         with torch.no_grad():
             for b, l in enumerate(lengths):
                 o = model({m: v[b:b + 1, :l].contiguous() for m, v in feats.items()}, torch.ones(1, l, 1, device=dev), [l])
-                cc.append(eval_ccc(tgt[b, :l, 0].cpu().numpy(), o.reshape(-1).cpu().numpy()))
+                cc.append(eval_ccc(tgt[b, :l, 0].double().cpu().numpy(), o.reshape(-1).double().cpu().numpy()))
         return cc
 
     batched(); torch.cuda.synchronize()

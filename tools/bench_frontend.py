@@ -103,19 +103,20 @@ def main():
     out['train_ms_all_mods'] = round(tot_t, 4)
     out['narratives_per_s_train_front_end_only'] = round(args.B / (tot_t * 1e-3), 1)
 
-    # reference-style CPU loop on a bounded sample: one narrative per iteration, CNN -> Highway (oracle restatement, fp32 torch CPU)
-    from oracle import frontend_oracle as FO
+    # reference-style CPU loop on a bounded sample: one narrative per iteration, Conv1d -> max over positions -> Highway with the ATen
+    # operators the reference calls (MFT/models.py:68-79, 51-54), fp32 torch CPU
+    import torch.nn.functional as F
     nb = args.cpu_narratives
     t_cpu = 0.0
     for mod, (Kv, D, E) in MODS.items():
         x = torch.randn(nb, args.T, Kv, D)
-        ps = [p.detach().cpu() for p in params(D, E, 2, 'cpu')]
-        sd = {'cnn.conv1d.weight': ps[0], 'cnn.conv1d.bias': ps[1], 'hw.linear_projection.weight': ps[2], 'hw.linear_projection.bias': ps[3],
-              'hw.linear_gate.weight': ps[4], 'hw.linear_gate.bias': ps[5]}
+        cw, cb, pw, pb, gw, gb = [p.detach().cpu() for p in params(D, E, 2, 'cpu')]
         t0 = time.perf_counter()
         with torch.no_grad():
             for b in range(nb):
-                FO.highway(sd, 'hw', FO.cnn(sd, 'cnn', x[b]))
+                c = F.conv1d(x[b].permute(0, 2, 1), cw, cb).max(dim=2).values
+                g = torch.sigmoid(F.linear(c, gw, gb))
+                _ = g * F.linear(c, pw, pb) + (1 - g) * c
         t_cpu += time.perf_counter() - t0
     out['cpu_baseline'] = {'fwd_narratives_per_s': round(nb / t_cpu, 2), 'cores': torch.get_num_threads(), 'kind': 'port',
                            'sample': f'{nb} narratives x T={args.T}, forward only, per-narrative loop'}
