@@ -164,3 +164,58 @@ def test_device_corpus_needs_a_gpu():
     data, target, lengths = corpus()
     with pytest.raises(RuntimeError, match='CUDA'):
         mtb.DeviceCorpus(data, target, lengths, device='cpu')
+
+
+# ---- host logic of the inference helpers (no GPU) ------------------------------------------------------------------------------------
+def test_ragged_batch_context_nests_and_restores():
+    from multimodal_transformer_b200 import functional as K
+    assert K._state['key_len'] is None
+    with mtb.ragged_batch([3, 2]):
+        assert K._state['key_len'] == [3, 2]
+        with mtb.ragged_batch([5]):
+            assert K._state['key_len'] == [5]
+        assert K._state['key_len'] == [3, 2]
+    assert K._state['key_len'] is None
+    with pytest.raises(ValueError):
+        with mtb.ragged_batch([1]):
+            raise ValueError('propagates')
+    assert K._state['key_len'] is None
+
+
+def test_model_call_convention_dispatch():
+    """models.py classes take forward(inputs, length, mask); multiTransformer.py classes forward(inputs, mask, lengths)."""
+    from multimodal_transformer_b200.evaluation import _call
+    seen = {}
+
+    class Front(M._FrontEnd):
+        def forward(self, inputs, length, mask=None):
+            seen['front'] = (inputs, length, mask)
+
+    class Body(torch.nn.Module):
+        def forward(self, inputs, mask, lengths):
+            seen['body'] = (inputs, mask, lengths)
+
+    _call(Front(), 'x', 'm', [1]); _call(Body(), 'x', 'm', [1])
+    assert seen['front'] == ('x', [1], 'm') and seen['body'] == ('x', 'm', [1])
+
+
+def test_grad_mode_is_visible_to_function_forward():
+    """functional._apply hands the caller's grad mode to Function.forward (autograd always runs forward with grad mode off)."""
+    from multimodal_transformer_b200 import functional as K
+
+    class Probe(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x):
+            Probe.seen = K._need_grad(ctx)
+            return x.clone()
+
+        @staticmethod
+        def backward(ctx, g):
+            return g
+
+    x = torch.ones(2, requires_grad=True)
+    K._apply(Probe, x); assert Probe.seen is True
+    with torch.no_grad():
+        K._apply(Probe, x); assert Probe.seen is False
+    K._apply(Probe, torch.ones(2)); assert Probe.seen is False
+    assert K._state['grad'] is True
