@@ -62,3 +62,9 @@ def mcnn_b2(sd, inputs, mask, mods, N=6, drop=_NO_DROP):
     """B2-Trans/models.py:105-133."""
     emb = front(sd, inputs, mods, drop)
     return O.uni_full_transformer(sd, 'Transformer.', torch.cat([emb[m] for m in mods], 2), mask, N=N, drop=drop)
+
+
+def mcnn_uni(sd, inputs, mask, mods, N=6, drop=_NO_DROP):
+    """One modality: MFT/models.py:102-105,134-135 -- the front-end feeds UniTransformer."""
+    emb = front(sd, inputs, mods, drop)
+    return O.uni_transformer(sd, 'Transformer.', emb[mods[0]], mask, N=N, drop=drop)

@@ -49,6 +49,30 @@ def _run(model, inputs, mask, target, lengths):
     return res
 
 
+def single_modality():
+    """MFT MultiCNNTransformer with ONE modality (MFT/models.py:102-105: UniTransformer body) -> front_uni.npz + inventory entry."""
+    warnings.filterwarnings('ignore')
+    torch.set_num_threads(8)
+    with contextlib.redirect_stdout(io.StringIO()):
+        mft = _load_models('MFT', 'ref_models_mft1')
+        m = mft.MultiCNNTransformer(['linguistic'], {'linguistic': 300}, {'linguistic': 300}, device=torch.device('cpu'))
+    load_filled(m, 26)
+    shapes = {'linguistic': (4, 300)}
+    inputs, mask, target, lengths = fill.make_raw_batch(2, 6, shapes, 26)
+    np.savez(os.path.join(OUT, 'front_uni.npz'), **_run(m, inputs, mask, target, lengths))
+    with open(os.path.join(OUT, 'front_meta.json')) as f:
+        meta = json.load(f)
+    meta['front_uni'] = dict(B=2, T=6, mods=['linguistic'], shapes=shapes, embed_dims={'linguistic': 300}, lengths=lengths, seed=26)
+    with open(os.path.join(OUT, 'front_meta.json'), 'w') as f:
+        json.dump(meta, f, indent=1)
+    with open(os.path.join(OUT, 'front_state_dict_keys.json')) as f:
+        inv = json.load(f)
+    inv['MFT.MultiCNNTransformer.single'] = {k: list(v.shape) for k, v in m.state_dict().items()}
+    with open(os.path.join(OUT, 'front_state_dict_keys.json'), 'w') as f:
+        json.dump(inv, f)
+    print('single-modality golden written')
+
+
 def main():
     warnings.filterwarnings('ignore')
     torch.set_num_threads(8)
@@ -126,4 +150,8 @@ def main():
 
 
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'single':
+        single_modality()            # adds front_uni.npz without rewriting the other fixtures
+    else:
+        main()
+        single_modality()

@@ -112,7 +112,8 @@ def test_window_cnn_fused_train_mode_same_masks(n, Kv, D, E, k, mode):
 
 
 def _load(model, name):
-    inv = front_inventory()[{'front_mft': 'MFT', 'front_sft': 'SFT', 'front_b2': 'B2', 'front_b3': 'B3'}[name] + '.MultiCNNTransformer']
+    inv = front_inventory()[{'front_mft': 'MFT.MultiCNNTransformer', 'front_sft': 'SFT.MultiCNNTransformer', 'front_b2': 'B2.MultiCNNTransformer',
+                             'front_b3': 'B3.MultiCNNTransformer', 'front_uni': 'MFT.MultiCNNTransformer.single'}[name]]
     m = front_meta()[name]
     sd = util.filled_sd({k: tuple(s) for k, s in inv.items()}, m['seed'])
     model.load_state_dict(sd)
@@ -126,6 +127,7 @@ def _load(model, name):
     ('front_b3', lambda m: M.B3MultiCNNTransformer(m['mods'], {k: v[1] for k, v in m['shapes'].items()})),
     ('front_sft', lambda m: M.SFTMultiCNNTransformer(m['mods'], {k: v[1] for k, v in m['shapes'].items()})),
     ('front_b2', lambda m: M.B2MultiCNNTransformer(m['mods'], {k: v[1] for k, v in m['shapes'].items()})),
+    ('front_uni', lambda m: M.MultiCNNTransformer(m['mods'], {k: v[1] for k, v in m['shapes'].items()}, m['embed_dims'])),
 ])
 def test_multicnn_models_match_reference_golden(name, ctor):
     """The four MultiCNNTransformer variants end to end (raw windows -> prediction), eval mode, fp32: prediction, loss and every
@@ -145,7 +147,7 @@ def test_multicnn_models_match_reference_golden(name, ctor):
             util.assert_digest_close(util.grad_digest(p.grad), g['grad:' + k], 3e-4, k); checked += 1
         else:
             assert p.grad is None and k.startswith(('Transformer.attn', 'Transformer.ff')), k
-    assert checked >= 12
+    assert checked >= (12 if len(m['mods']) > 1 else 6)
     mtb.set_compute_dtype('bf16')
     with torch.no_grad():
         p16 = model(xin, lengths, t(mask).to(DEV))
