@@ -59,6 +59,19 @@ def test_shard_batch_deals_sorted_round_robin():
     assert abs(sum(l0) - sum(l1)) <= max(lengths)
 
 
+def test_shard_batch_takes_raw_window_batches():
+    """The same partition applies one level up (MultiCNNTransformer inputs [B,T,K,D]): shards keep the global T and the window axes."""
+    shapes = {'linguistic': (5, 30), 'image': (2, 10)}
+    inputs, mask, target, lengths = fill.make_raw_batch(6, 9, shapes, 4)
+    parts = [shard_batch(inputs, mask, target, lengths, r, 3) for r in range(3)]
+    assert sorted(l for p in parts for l in p[3]) == sorted(lengths)
+    for x, m, tg, ls, norm in parts:
+        assert x['linguistic'].shape == (2, 9, 5, 30) and x['image'].shape == (2, 9, 2, 10) and m.shape == (2, 9, 1)
+        assert norm == float(sum(lengths))
+        for b, l in enumerate(ls):
+            assert m[b, :l].all() and not m[b, l:].any() and not x['linguistic'][b, l:].any()
+
+
 def test_all_reduce_is_noop_without_process_group():
     g = torch.ones(5)
     assert all_reduce_flat_([g])[0] is g and torch.equal(g, torch.ones(5))
