@@ -193,3 +193,70 @@ def test_dropper_statistics_and_determinism():
     assert not torch.equal(m1, keep_mask(1235, 7, (512, 512), 0.1))
     assert not torch.equal(m1, keep_mask(1234, 8, (512, 512), 0.1))
     assert keep_mask(5, 1, (100,), 0.0).all()
+
+
+# ---- structural properties of the restated path (what the full-size GPU tests rely on) ------------------------------------------------
+def _small_mft(N=1, seed=51):
+    dims = {'acoustic': 88, 'image': 256, 'linguistic': 300}
+    sd = util.filled_sd(util.mods_shapes('MFT.MultiTransformer', N), seed)
+    return dims, sd
+
+
+def test_oracle_narratives_are_independent_units():
+    """No cross-sample operator on the path: permuting the batch permutes the predictions, and a narrative forwarded
+    alone at the same padded length gives the same prediction -- the basis of sharding narratives over GPUs without a collective."""
+    dims, sd = _small_mft()
+    inputs, mask, _, lengths = fill.make_batch(4, 9, dims, 52)
+    x = {k: t(v) for k, v in inputs.items()}
+    with torch.no_grad():
+        full = O.multi_transformer(sd, '', x, t(mask), MODS, N=1)
+        perm = torch.tensor([2, 0, 3, 1])
+        p = O.multi_transformer(sd, '', {k: v[perm] for k, v in x.items()}, t(mask)[perm], MODS, N=1)
+        one = O.multi_transformer(sd, '', {k: v[1:2] for k, v in x.items()}, t(mask)[1:2], MODS, N=1)
+    np.testing.assert_allclose(p.numpy(), full[perm].numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(one.numpy(), full[1:2].numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_oracle_padded_windows_are_live_keys_but_mfn_is_causal():
+    """Appendix A.12 and A.5: perturbing a PADDED window changes valid predictions (padded rows are attention keys), while the
+    B3 variant (no encoder: LSTHM + memory recurrence only) is causal -- a change at window t0 leaves predictions before t0 untouched."""
+    dims, sd = _small_mft()
+    inputs, mask, _, lengths = fill.make_batch(3, 10, dims, 53)
+    b = max(range(3), key=lambda i: -lengths[i] if lengths[i] < 10 else -99)       # a narrative with padding
+    assert lengths[b] < 10
+    x = {k: t(v).clone() for k, v in inputs.items()}
+    x2 = {k: v.clone() for k, v in x.items()}
+    x2['image'][b, lengths[b]:] += 1.0                                           # touch padded windows only
+    with torch.no_grad():
+        y, y2 = (O.multi_transformer(sd, '', xi, t(mask), MODS, N=1) for xi in (x, x2))
+    assert (y[b, :lengths[b]] - y2[b, :lengths[b]]).abs().max() > 1e-6
+    others = [i for i in range(3) if i != b]
+    np.testing.assert_allclose(y[others].numpy(), y2[others].numpy(), rtol=0, atol=0)
+    b3dims = {'acoustic': 256, 'image': 256, 'linguistic': 300}
+    sd3 = util.filled_sd(util.mods_shapes('B3.MultiTransformer'), 54)
+    inputs, mask, _, lengths = fill.make_batch(2, 8, b3dims, 54)
+    x = {k: t(v).clone() for k, v in inputs.items()}
+    x2 = {k: v.clone() for k, v in x.items()}
+    t0 = 5
+    x2['linguistic'][:, t0:] += 0.5
+    with torch.no_grad():
+        y, y2 = (O.multi_transformer(sd3, '', xi, torch.ones(2, 8, 1), MODS, use_encoder=False) for xi in (x, x2))
+    np.testing.assert_allclose(y[:, :t0].numpy(), y2[:, :t0].numpy(), rtol=0, atol=0)
+    assert (y[:, t0:] - y2[:, t0:]).abs().max() > 1e-6
+
+
+def test_oracle_loss_gradients_sum_over_shards():
+    """The reference loss is a SUM over narratives divided by the global sum of lengths (MFT/train.py:135-139): gradients of two shards
+    normalised by the GLOBAL norm add up to the full-batch gradient -- why data parallelism all-reduces with SUM, not mean."""
+    dims, sd0 = _small_mft()
+    inputs, mask, target, lengths = fill.make_batch(4, 7, dims, 55)
+
+    def grads(rows):
+        sd = {k: v.clone().requires_grad_(True) for k, v in sd0.items()}
+        pred = O.multi_transformer(sd, '', {k: t(v)[rows] for k, v in inputs.items()}, t(mask)[rows], MODS, N=1)
+        (((pred - t(target)[rows]) ** 2).sum() / float(sum(lengths))).backward()
+        return {k: v.grad for k, v in sd.items() if v.grad is not None}
+
+    full, a, b = grads([0, 1, 2, 3]), grads([0, 2]), grads([1, 3])
+    for k in full:
+        np.testing.assert_allclose((a[k] + b[k]).numpy(), full[k].numpy(), rtol=2e-4, atol=1e-7, err_msg=k)
