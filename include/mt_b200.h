@@ -107,6 +107,19 @@ size_t mt_attention_bwd_ws_bytes(int B, int T, int h);
 int mt_attention_force_ffma(int on);
 /* test hook: route bf16 attention with T <= 128 through the tiled any-T tensor-core kernel instead of the whole-head one. */
 int mt_attention_force_tiled(int on);
+/* tcgen05 / TMEM engine for T <= 128, 32-wide heads, an even number of heads (bf16 only; mt_attention_fwd / _bwd pick it
+ * automatically).  Direct entries for tests and probes: MT_ERR_UNSUPPORTED outside that envelope.  key_len may be NULL.
+ * mt_attention_tc_bwd: aux = workspace of mt_attention_tc_bwd_ws_bytes; dbias (optional, fp32 [3d], ACCUMULATED) receives the
+ * column sums of dqkv (the QKV projection's bias gradient). */
+int mt_attention_tc_fwd(int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, float p_drop,
+                        uint64_t seed, uint32_t site, const int* key_len, void* stream);
+int mt_attention_tc_bwd(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse,
+                        const void* dout, void* dqkv, float p_drop, uint64_t seed, uint32_t site, float* dbias, void* ws,
+                        size_t ws_bytes, void* stream);
+size_t mt_attention_tc_bwd_ws_bytes(int B, int T, int h);
+/* test hooks: variant bits of the tcgen05 attention kernels (0 = default); disable the engine (A/B against the mma.sync kernels). */
+int mt_attention_tc_variant(int v);
+int mt_attention_force_no_tc(int on);
 /* materialise p_attn [B,h,T,T] fp32 (the reference keeps it as MultiHeadedAttention.attn, :59); debug/inspection. */
 int mt_attention_probs(int dtype, int B, int T, int d, int h, const void* qkv, const float* mask, float* probs,
                        void* stream);

@@ -340,6 +340,9 @@ int mt_attn_fwd_run(int dtype, int B, int T_, int d, int h, const void* qkv, con
                     cudaStream_t st, const int* klen) {
   MT_TRY(check_shape(B, T_, d, h));
   if (!qkv || !out) return MT_ERR_ARG;
+  if (dtype == MT_BF16 && !g_attn_force_ffma && !g_mt_attn_no_tc && !mt_attn_force_tiled_on() && mt_attn_tc_supported(B, T_, d, h) &&
+      !(((uintptr_t)qkv | (uintptr_t)out) & 15))
+    return mt_attn_tc_fwd_run(B, T_, d, h, qkv, mask, out, lse, drop, st, klen);
   if (dtype == MT_BF16 && !g_attn_force_ffma && mt_attn_mma_supported(B, T_, d, h)) return mt_attn_mma_fwd_run(B, T_, d, h, qkv, mask, out, lse, drop, st, klen);
   if (dtype == MT_BF16) return fwd_dispatch<bf16>(B, T_, d, h, qkv, mask, out, lse, drop, st, klen);
   return fwd_dispatch<float>(B, T_, d, h, qkv, mask, out, lse, drop, st, klen);
@@ -350,7 +353,13 @@ int mt_attn_bwd_run(int dtype, int B, int T_, int d, int h, const void* qkv, con
   MT_TRY(check_shape(B, T_, d, h));
   if (!qkv || !out || !lse || !dout || !dqkv || !Dws) return MT_ERR_ARG;
   bool done = false;
-  if (dtype == MT_BF16 && !g_attn_force_ffma && mt_attn_mma_supported(B, T_, d, h))
+  // tcgen05 / TMEM engine: T <= 128 (even), 32-wide heads; it also produces the QKV bias gradient unless h > 8
+  if (dtype == MT_BF16 && !g_attn_force_ffma && !g_mt_attn_no_tc && !mt_attn_force_tiled_on() && mt_attn_tc_supported(B, T_, d, h) && !(T_ & 1) &&
+      !(((uintptr_t)qkv | (uintptr_t)out | (uintptr_t)dout | (uintptr_t)dqkv | (uintptr_t)Dws) & 15)) {
+    float* db = h <= 8 ? dbias : nullptr;
+    MT_TRY(mt_attn_tc_bwd_run(B, T_, d, h, qkv, mask, out, lse, dout, dqkv, drop, db, Dws, st));
+    done = db != nullptr;
+  } else if (dtype == MT_BF16 && !g_attn_force_ffma && mt_attn_mma_supported(B, T_, d, h))
     MT_TRY(mt_attn_mma_bwd_run(B, T_, d, h, qkv, mask, out, lse, dout, dqkv, drop, st, dbias, &done));
   else if (dtype == MT_BF16) MT_TRY(bwd_dispatch<bf16>(B, T_, d, h, qkv, mask, out, lse, dout, dqkv, drop, Dws, st));
   else MT_TRY(bwd_dispatch<float>(B, T_, d, h, qkv, mask, out, lse, dout, dqkv, drop, Dws, st));
@@ -368,7 +377,7 @@ int mt_attention_fwd(int dtype, int B, int T, int d, int h, const void* qkv, con
   return mt_attn_fwd_run(dtype, B, T, d, h, qkv, mask, out, lse, mt_make_drop(p_drop, seed, site), (cudaStream_t)stream);
 }
 
-size_t mt_attention_bwd_ws_bytes(int B, int T, int h) { return sizeof(float) * (size_t)B * (size_t)T * (size_t)h; }
+size_t mt_attention_bwd_ws_bytes(int B, int T, int h) { return mt_attn_bwd_ws_floats(B, T, h) * sizeof(float); }
 
 int mt_attention_ragged_fwd(int dtype, int B, int T, int d, int h, const void* qkv, const float* mask, const int* key_len, void* out,
                             void* stream) {

@@ -328,6 +328,7 @@ bool mt_attn_mma_supported(int B, int T, int d, int h) {
 
 static int g_force_tiled = 0;
 extern "C" int mt_attention_force_tiled(int on) { const int old = g_force_tiled; g_force_tiled = on; return old; }
+bool mt_attn_force_tiled_on() { return g_force_tiled != 0; }
 
 int mt_attn_mma_fwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop, cudaStream_t st,
                         const int* klen) {

@@ -85,7 +85,7 @@ int carve(const MtEncoderCfg& c, void* ws, EncWs& w) {
     w.dact2 = k.take_bytes(M * d * es);
     w.dhid = k.take_bytes(M * c.dff * es);
     w.dqkv = k.take_bytes(M * 3 * d * es);
-    w.Dws = k.take<float>((size_t)c.B * c.h * c.T);
+    w.Dws = k.take<float>(mt_attn_bwd_ws_floats(c.B, c.T, c.h));
   }
   w.bytes = k.total();
   return MT_OK;

@@ -56,6 +56,18 @@ int mt_attn128_fwd_run(int B, int T, int d, int h, const void* qkv, const float*
 int mt_attn128_bwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse, const void* dout,
                        void* dqkv, DropCfg drop, cudaStream_t st, float* dbias = nullptr);
 
+// ---- tcgen05 / TMEM attention for T <= 128, 32-wide heads, even head count (mt_attention_tc.cu), bf16 ---------------------
+extern int g_mt_attn_no_tc;
+bool mt_attn_force_tiled_on();
+bool mt_attn_tc_supported(int B, int T, int d, int h);
+int mt_attn_tc_fwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop, cudaStream_t st,
+                       const int* klen = nullptr);
+// aux: fp32 workspace of mt_attn_bwd_ws_floats(B, T, h) floats (per-query scalars); dbias as in mt_attn_mma_bwd_run (h <= 8)
+int mt_attn_tc_bwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse, const void* dout,
+                       void* dqkv, DropCfg drop, float* dbias, float* aux, cudaStream_t st);
+// workspace of any attention backward (Dws of mt_attn_bwd_run), in floats
+static inline size_t mt_attn_bwd_ws_floats(int B, int T, int h) { return 4 * (size_t)B * (size_t)T * (size_t)h + 64; }
+
 // ---- attention (mt_attention.cu) ---------------------------------------------------------------------
 int mt_attn_fwd_run(int dtype, int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop,
                     cudaStream_t st, const int* klen = nullptr);

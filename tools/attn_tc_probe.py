@@ -1,0 +1,175 @@
+"""A/B of the tcgen05 / TMEM attention kernels (csrc/mt_attention_tc.cu) against the mma.sync kernels of the same library on identical
+inputs, for every variant bit, plus CUDA-event timings at the benchmark size.  Run on a B200:  python tools/attn_tc_probe.py [fwd|bwd|all]"""
+import ctypes
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from multimodal_transformer_b200 import _lib  # noqa: E402
+
+L = _lib.lib()
+P = _lib.ptr
+BF16 = 1
+TIMING = False
+
+
+def make(B, T, d, h, seed=0, masked=True):
+    g = torch.Generator(device='cuda').manual_seed(seed)
+    qkv = (torch.randn(B, T, 3 * d, device='cuda', generator=g) * 1.5).to(torch.bfloat16)
+    mask = torch.ones(B, T, device='cuda')
+    if masked:
+        for b in range(B):
+            n = T - (b * 7) % (T // 2)
+            mask[b, n:] = 0
+    dout = (torch.randn(B, T, d, device='cuda', generator=g) * 0.5).to(torch.bfloat16)
+    return qkv, mask, dout
+
+
+_BUF = {}
+
+
+def buf(name, shape, dtype, zero=False):
+    """outputs are pre-allocated per shape so that timing loops measure the kernels, not the allocator"""
+    key = (name, tuple(shape), dtype)
+    if key not in _BUF:
+        _BUF[key] = torch.empty(*shape, device='cuda', dtype=dtype)
+    if zero:
+        _BUF[key].zero_()
+    return _BUF[key]
+
+
+def fwd_old(B, T, d, h, qkv, mask, p, seed, klen=None):
+    out = buf('o0', (B, T, d), torch.bfloat16)
+    lse = buf('l0', (B, h, T), torch.float32)
+    L.mt_attention_force_no_tc(1)
+    if klen is None:
+        _lib.check(L.mt_attention_fwd(BF16, B, T, d, h, P(qkv), P(mask), P(out), P(lse), p, seed, 5, _lib.stream()))
+    else:
+        _lib.check(L.mt_attention_ragged_fwd(BF16, B, T, d, h, P(qkv), P(mask), P(klen), P(out), _lib.stream()))
+    L.mt_attention_force_no_tc(0)
+    return out, lse
+
+
+def fwd_new(B, T, d, h, qkv, mask, p, seed, klen=None):
+    out = buf('o1', (B, T, d), torch.bfloat16, zero=not TIMING)
+    lse = buf('l1', (B, h, T), torch.float32, zero=not TIMING)
+    _lib.check(L.mt_attention_tc_fwd(B, T, d, h, P(qkv), P(mask), P(out), P(lse), p, seed, 5, P(klen), _lib.stream()))
+    return out, lse
+
+
+def bwd_old(B, T, d, h, qkv, mask, out, lse, dout, p, seed):
+    dqkv = buf('g0', (B, T, 3 * d), torch.bfloat16)
+    ws = buf('ws0', (L.mt_attention_bwd_ws_bytes(B, T, h),), torch.uint8)
+    L.mt_attention_force_no_tc(1)
+    _lib.check(L.mt_attention_bwd(BF16, B, T, d, h, P(qkv), P(mask), P(out), P(lse), P(dout), P(dqkv), p, seed, 5, P(ws), ws.numel(), _lib.stream()))
+    L.mt_attention_force_no_tc(0)
+    return dqkv
+
+
+def bwd_new(B, T, d, h, qkv, mask, out, lse, dout, p, seed, dbias=None):
+    dqkv = buf('g1', (B, T, 3 * d), torch.bfloat16, zero=not TIMING)
+    ws = buf('ws1', (L.mt_attention_tc_bwd_ws_bytes(B, T, h),), torch.uint8)
+    _lib.check(L.mt_attention_tc_bwd(B, T, d, h, P(qkv), P(mask), P(out), P(lse), P(dout), P(dqkv), p, seed, 5, P(dbias), P(ws), ws.numel(),
+                                     _lib.stream()))
+    return dqkv
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-20)).item()
+
+
+def timeit(fn, n=50):
+    global TIMING
+    TIMING = True
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    TIMING = False
+    return e0.elapsed_time(e1) / n * 1e3      # us
+
+
+def main():
+    what = sys.argv[1] if len(sys.argv) > 1 else 'all'
+    d, h = 256, 8
+    if what == 'prof':          # the workload ncu captures: two launches of each kernel at the benchmark size
+        B, T, p = 256, 128, 0.1
+        qkv, mask, dout = make(B, T, d, h, seed=1)
+        out, lse = fwd_old(B, T, d, h, qkv, mask, p, 99)
+        out, lse = out.clone(), lse.clone()
+        db = torch.zeros(3 * d, device='cuda')
+        for _ in range(2):
+            fwd_new(B, T, d, h, qkv, mask, p, 99)
+            bwd_new(B, T, d, h, qkv, mask, out, lse, dout, p, 99, db)
+        torch.cuda.synchronize()
+        print('prof ok')
+        return
+    res = {}
+    cases = [(4, 128, 0.0), (4, 128, 0.1), (5, 100, 0.0), (3, 40, 0.1), (2, 16, 0.0)]
+    for variant in (0, 1, 2, 3):
+        L.mt_attention_tc_variant(variant)
+        for (B, T, p) in cases:
+            key = f'v{variant}_B{B}_T{T}_p{p}'
+            qkv, mask, dout = make(B, T, d, h, seed=B * 1000 + T)
+            try:
+                o0, l0 = fwd_old(B, T, d, h, qkv, mask, p, 1234)
+                o0, l0 = o0.clone(), l0.clone()
+                if what in ('fwd', 'all'):
+                    o1, l1 = fwd_new(B, T, d, h, qkv, mask, p, 1234)
+                    torch.cuda.synchronize()
+                    res[key + '_fwd'] = {'out_rel': rel(o1, o0), 'lse_abs': (l1 - l0).abs().max().item()}
+                if what in ('bwd', 'all') and variant in (0, 2):
+                    g0 = bwd_old(B, T, d, h, qkv, mask, o0, l0, dout, p, 1234)
+                    db = torch.zeros(3 * d, device='cuda')
+                    g1 = bwd_new(B, T, d, h, qkv, mask, o0, l0, dout, p, 1234, db)
+                    torch.cuda.synchronize()
+                    dq0, dk0, dv0 = g0.split(d, dim=2)
+                    dq1, dk1, dv1 = g1.split(d, dim=2)
+                    res[key + '_bwd'] = {'dq': rel(dq1, dq0), 'dk': rel(dk1, dk0), 'dv': rel(dv1, dv0),
+                                         'dbias': rel(db, g0.float().sum((0, 1)))}
+            except RuntimeError as e:       # a faulting variant poisons the context: report and stop
+                res[key] = 'ERROR ' + str(e)
+                print(json.dumps(res, indent=1))
+                return
+    L.mt_attention_tc_variant(0)
+    if what in ('fwd', 'all'):      # ragged inference
+        B, T = 6, 128
+        qkv, mask, _ = make(B, T, d, h, seed=7, masked=False)
+        klen = torch.tensor([128, 100, 77, 64, 33, 5], device='cuda', dtype=torch.int32)
+        o0, _ = fwd_old(B, T, d, h, qkv, mask, 0.0, 0, klen)
+        o0 = o0.clone()
+        o1, _ = fwd_new(B, T, d, h, qkv, mask, 0.0, 0, klen)
+        for b in range(B):
+            res[f'ragged_b{b}'] = rel(o1[b, :klen[b]], o0[b, :klen[b]])
+    # timings at the benchmark size (one modality stack and three stacks' worth of narratives)
+    for B in (256, 768):
+        T, p = 128, 0.1
+        qkv, mask, dout = make(B, T, d, h, seed=1)
+        out, lse = fwd_old(B, T, d, h, qkv, mask, p, 99)
+        out, lse = out.clone(), lse.clone()
+        res[f'time_B{B}'] = {}
+        if what in ('fwd', 'all'):
+            res[f'time_B{B}']['fwd_old_us'] = timeit(lambda: fwd_old(B, T, d, h, qkv, mask, p, 99))
+            for v in (0, 1, 2):
+                L.mt_attention_tc_variant(v)
+                res[f'time_B{B}'][f'fwd_tc_v{v}_us'] = timeit(lambda: fwd_new(B, T, d, h, qkv, mask, p, 99))
+            L.mt_attention_tc_variant(0)
+        if what in ('bwd', 'all'):
+            res[f'time_B{B}']['bwd_old_us'] = timeit(lambda: bwd_old(B, T, d, h, qkv, mask, out, lse, dout, p, 99))
+            res[f'time_B{B}']['bwd_tc_us'] = timeit(lambda: bwd_new(B, T, d, h, qkv, mask, out, lse, dout, p, 99))
+    print(json.dumps(res, indent=1))
+    os.makedirs('gpurun_out', exist_ok=True)
+    json.dump(res, open(f'gpurun_out/attn_tc_probe_{what}.json', 'w'), indent=1)
+
+
+if __name__ == '__main__':
+    main()
