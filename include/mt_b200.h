@@ -117,8 +117,7 @@ int mt_attention_tc_bwd(int B, int T, int d, int h, const void* qkv, const float
                         const void* dout, void* dqkv, float p_drop, uint64_t seed, uint32_t site, float* dbias, void* ws,
                         size_t ws_bytes, void* stream);
 size_t mt_attention_tc_bwd_ws_bytes(int B, int T, int h);
-/* test hooks: variant bits of the tcgen05 attention kernels (0 = default); disable the engine (A/B against the mma.sync kernels). */
-int mt_attention_tc_variant(int v);
+/* test hook: disable the tcgen05 engine (A/B against the mma.sync kernels); returns the previous setting. */
 int mt_attention_force_no_tc(int on);
 /* materialise p_attn [B,h,T,T] fp32 (the reference keeps it as MultiHeadedAttention.attn, :59); debug/inspection. */
 int mt_attention_probs(int dtype, int B, int T, int d, int h, const void* qkv, const float* mask, float* probs,

@@ -65,7 +65,6 @@ _PROTOS = {
     'mt_attention_tc_fwd': (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, c_float, c_uint64, c_uint32, P, P]),
     'mt_attention_tc_bwd': (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, c_float, c_uint64, c_uint32, P, P, c_size_t, P]),
     'mt_attention_tc_bwd_ws_bytes': (c_size_t, [c_int, c_int, c_int]),
-    'mt_attention_tc_variant': (c_int, [c_int]),
     'mt_attention_force_no_tc': (c_int, [c_int]),
     'mt_attention_probs': (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
     'mt_encoder_param_count': (c_size_t, [c_int, c_int, c_int]),

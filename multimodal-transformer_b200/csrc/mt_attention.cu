@@ -353,8 +353,8 @@ int mt_attn_bwd_run(int dtype, int B, int T_, int d, int h, const void* qkv, con
   MT_TRY(check_shape(B, T_, d, h));
   if (!qkv || !out || !lse || !dout || !dqkv || !Dws) return MT_ERR_ARG;
   bool done = false;
-  // tcgen05 / TMEM engine: T <= 128 (even), 32-wide heads; it also produces the QKV bias gradient unless h > 8
-  if (dtype == MT_BF16 && !g_attn_force_ffma && !g_mt_attn_no_tc && !mt_attn_force_tiled_on() && mt_attn_tc_supported(B, T_, d, h) && !(T_ & 1) &&
+  // tcgen05 / TMEM engine: T <= 128, 32-wide heads; it also produces the QKV bias gradient unless h > 8
+  if (dtype == MT_BF16 && !g_attn_force_ffma && !g_mt_attn_no_tc && !mt_attn_force_tiled_on() && mt_attn_tc_supported(B, T_, d, h) &&
       !(((uintptr_t)qkv | (uintptr_t)out | (uintptr_t)dout | (uintptr_t)dqkv | (uintptr_t)Dws) & 15)) {
     float* db = h <= 8 ? dbias : nullptr;
     MT_TRY(mt_attn_tc_bwd_run(B, T_, d, h, qkv, mask, out, lse, dout, dqkv, drop, db, Dws, st));

@@ -4,17 +4,20 @@
 // fill value -1e9, live padded keys, softmax, dropout on the probabilities, P.V, heads merged in place.
 //
 // One narrative is exactly one UMMA M tile (128 rows), so a work item is (narrative, PAIR of heads): the pair's Q / K / V slabs are
-// three TMA boxes [128 rows x 64 columns] (128-byte swizzle) of the packed qkv activation, and one 4-warp group per head works
-// with one query row (forward) or one key row (backward) per thread -- no cross-lane reductions anywhere.
+// three TMA boxes [128 rows x 64 columns] (128-byte swizzle) of the packed qkv activation, and the compute warps work with one
+// query row (forward) or one key row (backward) per thread -- no cross-lane reductions in the main loops.
 //
 //   forward : S = Q K^T (tcgen05.mma M128 N128 K32, accumulator in TMEM) -> tcgen05.ld, softmax in the exp2 domain, pair-hash dropout
-//             -> P (bf16) written back over S in TMEM -> O = P V with P as the TMEM A operand (M128 N32 K128) -> tcgen05.ld, 1/l, store.
+//             -> P (bf16) written back over S in TMEM -> O = P V with P as the TMEM A operand (M128 N32 K128) -> tcgen05.ld, scale / l,
+//             store.  Two CTAs per SM (one warp group per head each) so that one CTA's softmax covers the other's MMA / TMA latency.
 //   backward: transposed formulation so that both big contractions over the queries take their A operand from TMEM:
 //             S^T = K Q^T and dP^T = V dO^T (lane = key) -> P^T, dS^T (bf16, TMEM) ; dV = P^T dO, dK = dS^T Q (TS form);
 //             dS also goes to shared memory once (the thread's row is an MN-major A operand) for dQ = dS K.
-//             The per-query scalars (log-sum-exp, D = rowsum(dO . O), mask) arrive as a small TMA bulk copy per item.
-// Roles per CTA (one per SM, persistent over items): warps 0-3 / 4-7 = head 0 / head 1 of the pair, warp 8 = TMA producer,
-// warp 9 = tcgen05.mma issuer (one elected lane) and TMEM owner.
+//             The per-query scalars (log-sum-exp, D = rowsum(dO . O), mask) arrive as a TMA bulk copy per item.  Two warp groups per
+//             head split the query columns (16 compute warps per SM); the QKV bias gradient (column sums of dQ | dK | dV) is reduced
+//             with a halving butterfly and leaves with one atomic per column per CTA.
+// The instruction stream of both kernels is dominated by the per-probability work (exp2, dropout hash, conversions), not by the MMAs:
+// packed fp32 pairs (FFMA2 / FADD2 / FMUL2), the dropout scale folded into the row normaliser, 32-bit pair indices.
 #include "mt_ops.cuh"
 #include "mt_tcgen05.cuh"
 
@@ -27,12 +30,12 @@ constexpr int HD = 32;                       // head width
 constexpr int TILE_BYTES = TM * 128;         // [128 rows x 64 bf16], 128-byte swizzle
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
-constexpr int NT = 320;
 
-int g_variant = 0;       // test hook (mt_attention_tc_variant): bit 0 = P through shared memory (SS form), bit 1 = 64-wide P.V tile
-
+// ------------------------------------------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------------------------------------------
 struct FwdArgs {
-  int B, T, d, h, n_items, variant;
+  int B, T, d, h, n_items;
   float scale_log2;
   const float* mask;
   bf16* out;
@@ -41,49 +44,39 @@ struct FwdArgs {
   DropCfg drop;
 };
 
-constexpr int FWD_STAGES = 3;
+constexpr int FWD_NT = 320;                  // warps 0-3 / 4-7: head 0 / 1 of the pair, warp 8: TMA, warp 9: MMA issue + TMEM
+constexpr int FWD_STAGES = 2;
 constexpr int FWD_STAGE_BYTES = 3 * TILE_BYTES;
-constexpr int FWD_P_BYTES = 2 * TM * TM * 2;                                   // variant bit 0 only: P of both heads, K-major A operand
-constexpr int FWD_SMEM = FWD_STAGES * FWD_STAGE_BYTES + FWD_P_BYTES + 256 + 1024;
-
-// dropout factors of keys j, j + 1 (j even) of the query row whose pair-index base is row * ceil(T / 2)
-__device__ __forceinline__ void drop_pair_at(const DropCfg& d, uint64_t pair_base, uint32_t j, float& f0, float& f1) {
-  if (d.thresh == 0u) { f0 = f1 = 1.0f; return; }
-  const uint32_t bits = mt_draw32(d, pair_base + (uint64_t)(j >> 1));
-  const uint32_t t16 = d.thresh >> 16;
-  f0 = (bits & 0xFFFFu) >= t16 ? d.scale : 0.0f;
-  f1 = (bits >> 16) >= t16 ? d.scale : 0.0f;
-}
+constexpr int FWD_SMEM = FWD_STAGES * FWD_STAGE_BYTES + 256 + 1024;     // 99.6 KB: two CTAs per SM
+constexpr int FWD_TMEM = 256;                // head w: S at w * 128 (P packed over its first 64 columns), O at w * 128 + 64
 
 template <bool FULL>
-__global__ void __launch_bounds__(NT, 1) attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ FwdArgs a) {
+__global__ void __launch_bounds__(FWD_NT, 2) attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ FwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stage_base = smem;
-  uint8_t* p_smem = smem + FWD_STAGES * FWD_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + FWD_P_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FWD_STAGES * FWD_STAGE_BYTES);
   uint64_t* full = bars;                    // [FWD_STAGES] TMA -> MMA
   uint64_t* empty = bars + FWD_STAGES;      // [FWD_STAGES] MMA -> TMA
   uint64_t* s_full = empty + FWD_STAGES;    // [2] S of head w is in TMEM
   uint64_t* p_ready = s_full + 2;           // [2] P of head w is in place (128 arrivals)
   uint64_t* o_full = p_ready + 2;           // [2] O of head w is in TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* o_read = o_full + 2;            // [2] ... and has been read out (128 arrivals): S of the next item may overwrite it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_read + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int hp_count = a.h >> 1;
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&map_qkv);
     for (int s = 0; s < FWD_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int w = 0; w < 2; ++w) { mbar_init(&s_full[w], 1); mbar_init(&p_ready[w], 128); mbar_init(&o_full[w], 1); }
+    for (int w = 0; w < 2; ++w) { mbar_init(&s_full[w], 1); mbar_init(&p_ready[w], 128); mbar_init(&o_full[w], 1); mbar_init(&o_read[w], 128); }
     mbar_init_fence();
   }
-  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  if (warp == 9) tmem_alloc<FWD_TMEM>(tmem_slot);
   fence_before();
   __syncthreads();
   fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: S of head w at w * 128 (P overlays its first 64 columns), O of head w at 256 + w * 64
-  const bool p_via_smem = (a.variant & 1) != 0, wide_pv = (a.variant & 2) != 0;
 
   if (warp == 8) {
     // ===== TMA producer: Q | K | V boxes of the item's head pair =====
@@ -103,7 +96,7 @@ __global__ void __launch_bounds__(NT, 1) attn_tc_fwd_kernel(const __grid_constan
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc(TM, TM, 0, 0);
-      const uint32_t idesc_o = wide_pv ? make_idesc(TM, 64, 0, 1) : make_idesc(TM, HD, 0, 1);
+      const uint32_t idesc_o = make_idesc(TM, HD, 0, 1);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++it) {
@@ -113,8 +106,8 @@ __global__ void __launch_bounds__(NT, 1) attn_tc_fwd_kernel(const __grid_constan
         fence_after();
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
-          // S_w overwrites P_w of the previous item: wait until that item's P.V MMAs have completed
-          if (it > 0) { mbar_wait(&o_full[w], par ^ 1); fence_after(); }
+          // S_w overwrites P_w and O_w of the previous item: its P.V MMAs are complete and O has been read once o_read flips
+          if (it > 0) { mbar_wait(&o_read[w], par ^ 1); fence_after(); }
 #pragma unroll
           for (int ks = 0; ks < HD / 16; ++ks)
             mma_ss(tmem_base + (uint32_t)(w * 128), make_desc(sq + 64 * w + 32 * ks, 16, 1024), make_desc(sk + 64 * w + 32 * ks, 16, 1024),
@@ -125,15 +118,10 @@ __global__ void __launch_bounds__(NT, 1) attn_tc_fwd_kernel(const __grid_constan
         for (int w = 0; w < 2; ++w) {
           mbar_wait(&p_ready[w], par);
           fence_after();
-          const uint32_t d_o = tmem_base + (uint32_t)(256 + w * 64);
 #pragma unroll
-          for (int ks = 0; ks < TM / 16; ++ks) {
-            const uint64_t bd = make_desc(sv + (wide_pv ? 0 : 64 * w) + 2048 * ks, 8192, 1024);
-            if (p_via_smem)
-              mma_ss(d_o, make_desc(smem_u32(p_smem) + w * (TM * TM * 2) + (ks >> 2) * TILE_BYTES + 32 * (ks & 3), 16, 1024), bd, idesc_o, ks > 0);
-            else
-              mma_ts(d_o, tmem_base + (uint32_t)(w * 128 + 8 * ks), bd, idesc_o, ks > 0);
-          }
+          for (int ks = 0; ks < TM / 16; ++ks)      // A = P in TMEM (8 columns per 16 keys), B = V as an MN-major operand (n = head column)
+            mma_ts(tmem_base + (uint32_t)(w * 128 + 64), tmem_base + (uint32_t)(w * 128 + 8 * ks), make_desc(sv + 64 * w + 2048 * ks, 8192, 1024),
+                   idesc_o, ks > 0);
           commit(&o_full[w]);
         }
         commit(&empty[stage]);
@@ -144,9 +132,10 @@ __global__ void __launch_bounds__(NT, 1) attn_tc_fwd_kernel(const __grid_constan
     // ===== softmax / epilogue: warp group w owns head 2 hp + w, thread = query row =====
     const DropCfg drop = mt_drop_resolve(a.drop);
     const int w = warp >> 2, r = threadIdx.x & 127;
-    const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t t_s = t_lane + (uint32_t)(w * 128), t_o = t_lane + (uint32_t)(256 + w * 64 + (wide_pv ? w * HD : 0));
+    const uint32_t t_s = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(w * 128);
     const uint32_t P2 = (uint32_t)(a.T + 1) >> 1;
+    const uint32_t thr_hi = (drop.thresh >> 16) << 16;
+    const bool dropping = drop.thresh != 0u;
     int it = 0;
     for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++it) {
       const uint32_t par = (uint32_t)it & 1u;
@@ -155,66 +144,75 @@ __global__ void __launch_bounds__(NT, 1) attn_tc_fwd_kernel(const __grid_constan
       const bool masked = a.mask != nullptr && row_ok && a.mask[(size_t)b * a.T + r] == 0.f;
       const float rs = masked ? 0.f : a.scale_log2;        // masked query rows: every score becomes the same constant
       const int Tk = (!FULL && a.klen != nullptr) ? max(1, min(a.klen[b], a.T)) : a.T;
-      const uint64_t bh = (uint64_t)b * a.h + hd;
-      const uint64_t dbase = (bh * a.T + (uint64_t)min(r, a.T - 1)) * P2;
+      const uint32_t bh = (uint32_t)(b * a.h + hd);
+      const uint32_t dbase = (bh * (uint32_t)a.T + (uint32_t)min(r, a.T - 1)) * P2;      // pair-index base of this row (fits: see host check)
       mbar_wait(&s_full[w], par);
       fence_after();
-      float mx = -INFINITY;
+      float mraw = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
         ld32(t_s + (uint32_t)(c * 32), v);
         ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = (FULL || c * 32 + i < Tk) ? __uint_as_float(v[i]) * rs : -INFINITY;
-          mx = fmaxf(mx, s);
+        for (int i = 0; i < 32; i += 2) {
+          const float s0 = (FULL || c * 32 + i < Tk) ? __uint_as_float(v[i]) : -INFINITY;
+          const float s1 = (FULL || c * 32 + i + 1 < Tk) ? __uint_as_float(v[i + 1]) : -INFINITY;
+          mraw = fmaxf(mraw, fmaxf(s0, s1));
         }
       }
-      float l = 0.f;
+      const float mx = masked ? 0.f : mraw * rs;           // rs > 0 for live rows: max(s * rs) = rs * max(s)
+      const uint64_t rs2 = pk2(rs, rs), nmx2 = pk2(-mx, -mx);
+      uint64_t l2 = pk2(0.f, 0.f);
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32], pk[16];
         ld32(t_s + (uint32_t)(c * 32), v);
         ld_wait();
+        const uint32_t pbase = dbase + (uint32_t)(c * 16);
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           const int j = c * 32 + i;
-          const float p0 = (FULL || j < Tk) ? ex2(__uint_as_float(v[i]) * rs - mx) : 0.f;
-          const float p1 = (FULL || j + 1 < Tk) ? ex2(__uint_as_float(v[i + 1]) * rs - mx) : 0.f;
-          l += p0 + p1;
-          float f0, f1;
-          drop_pair_at(drop, dbase, (uint32_t)j, f0, f1);
-          pk[i >> 1] = pack_bf2(p0 * f0, p1 * f1);
+          float p0, p1;
+          upk2(fma2(pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), rs2, nmx2), p0, p1);
+          p0 = (FULL || j < Tk) ? ex2(p0) : 0.f;
+          p1 = (FULL || j + 1 < Tk) ? ex2(p1) : 0.f;
+          l2 = add2(l2, pk2(p0, p1));
+          if (dropping) {        // one draw per pair of keys: low half -> key j, high half -> key j + 1; the keep scale is applied with 1 / l
+            const uint32_t bits = mt_mix32((pbase + (uint32_t)(i >> 1)) ^ drop.key);
+            p0 = (bits << 16) >= thr_hi ? p0 : 0.f;
+            p1 = bits >= thr_hi ? p1 : 0.f;
+          }
+          pk[i >> 1] = pack_bf2(p0, p1);
         }
-        if (p_via_smem) {         // K-major A operand: row r, keys c*32 .. c*32+31 = four 16-byte chunks of k-block c / 2
-          uint8_t* pb = p_smem + w * (TM * TM * 2) + (c >> 1) * TILE_BYTES;
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(pb + sw128_off(r, (c & 1) * 4 + q)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-        } else {
-          st16(t_s + (uint32_t)(c * 16), pk);
-        }
+        st16(t_s + (uint32_t)(c * 16), pk);
       }
-      if (p_via_smem) fence_proxy_async(); else st_wait();
+      st_wait();
       fence_before();
       mbar_arrive(&p_ready[w]);
-      const float inv = 1.0f / l;
-      if (a.lse != nullptr && row_ok) a.lse[bh * a.T + r] = (mx + log2f(l)) * LN2;      // natural-log LSE of the scaled scores
+      float l0, l1;
+      upk2(l2, l0, l1);
+      const float l = l0 + l1;
+      const float inv = drop.scale / l;
+      if (a.lse != nullptr && row_ok) a.lse[(size_t)bh * a.T + r] = (mx + log2f(l)) * LN2;      // natural-log LSE of the scaled scores
       mbar_wait(&o_full[w], par);
       fence_after();
       uint32_t o[32];
-      ld32(t_o, o);
+      ld32(t_s + 64, o);
       ld_wait();
+      fence_before();
+      mbar_arrive(&o_read[w]);
       if (row_ok) {
         bf16* op = a.out + ((size_t)b * a.T + r) * a.d + hd * HD;
+        const uint64_t inv2 = pk2(inv, inv);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
+          float f[8];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            upk2(mul2(pk2(__uint_as_float(o[8 * q + 2 * k]), __uint_as_float(o[8 * q + 2 * k + 1])), inv2), f[2 * k], f[2 * k + 1]);
           uint4 u;
-          u.x = pack_bf2(__uint_as_float(o[8 * q]) * inv, __uint_as_float(o[8 * q + 1]) * inv);
-          u.y = pack_bf2(__uint_as_float(o[8 * q + 2]) * inv, __uint_as_float(o[8 * q + 3]) * inv);
-          u.z = pack_bf2(__uint_as_float(o[8 * q + 4]) * inv, __uint_as_float(o[8 * q + 5]) * inv);
-          u.w = pack_bf2(__uint_as_float(o[8 * q + 6]) * inv, __uint_as_float(o[8 * q + 7]) * inv);
+          u.x = pack_bf2(f[0], f[1]); u.y = pack_bf2(f[2], f[3]); u.z = pack_bf2(f[4], f[5]); u.w = pack_bf2(f[6], f[7]);
           *reinterpret_cast<uint4*>(op + 8 * q) = u;
         }
       }
@@ -224,30 +222,29 @@ __global__ void __launch_bounds__(NT, 1) attn_tc_fwd_kernel(const __grid_constan
   __syncthreads();
   if (warp == 9) {
     fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc<FWD_TMEM>(tmem_base);
   }
 }
-
 
 // ------------------------------------------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------------------------------------------
 struct BwdArgs {
-  int B, T, d, h, n_items, variant;
-  const float* aux;       // [B][h][4][T]: lse * log2e | D = rowsum(dO . O) | score scale * log2e (0: masked row) | score-gradient scale (0: masked)
+  int B, T, d, h, n_items;
+  const float* aux;       // [B][h][4][128]: lse * log2e | D = rowsum(dO . O) | score scale * log2e (0: masked row) | score-gradient scale (0: masked)
   bf16* dqkv;
   float* dbias;           // optional fp32 [3d], accumulated
   DropCfg drop;
 };
 
+constexpr int BWD_NT = 576;                                             // warps 0-15 compute, 16 TMA, 17 MMA issue + TMEM
 constexpr int BWD_STAGES = 2;
 constexpr int BWD_AUX_BYTES = 2 * 4 * TM * 4;                           // two heads x four per-query vectors
 constexpr int BWD_STAGE_BYTES = 4 * TILE_BYTES + BWD_AUX_BYTES;         // Q | K | V | dO | aux
 constexpr int BWD_DS_BYTES = TM * TM * 2;                               // dS of one head as an MN-major A operand
-constexpr int BWD_CS_FLOATS = 4 * 2 * 96 * 2;                           // column sums: up to 8 head pairs are folded modulo 4 below -> sized for h <= 16
 constexpr int BWD_SMEM = BWD_STAGES * BWD_STAGE_BYTES + 2 * BWD_DS_BYTES + 256 + 1024;
 
-// aux[b][hd][k][q], see BwdArgs; one thread per (b, hd, q), q fastest
+// aux[b][hd][k][q] (row stride 128 whatever T is), see BwdArgs; one thread per (b, hd, q), q fastest
 __global__ void attn_tc_prep_kernel(int B, int T, int d, int h, const bf16* __restrict__ out, const bf16* __restrict__ dout,
                                     const float* __restrict__ lse, const float* __restrict__ mask, float* __restrict__ aux, float scale) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -271,30 +268,22 @@ __global__ void attn_tc_prep_kernel(int B, int T, int d, int h, const bf16* __re
     }
   }
   const bool masked = mask != nullptr && mask[row] == 0.f;
-  float* a = aux + (size_t)bh * 4 * T;
+  float* a = aux + (size_t)bh * 4 * TM;
   a[q] = lse[bh * T + q] * LOG2E;
-  a[T + q] = D;
-  a[2 * T + q] = masked ? 0.f : scale * LOG2E;      // masked query rows: constant scores (uniform P) ...
-  a[3 * T + q] = masked ? 0.f : scale;              // ... and no score gradient (masked_fill blocks it)
+  a[TM + q] = D;
+  a[2 * TM + q] = masked ? 0.f : scale * LOG2E;      // masked query rows: constant scores (uniform P) ...
+  a[3 * TM + q] = masked ? 0.f : scale;              // ... and no score gradient (masked_fill blocks it)
 }
 
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(done)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return done != 0;
-}
-
+// TMEM columns of head w (base w * 256).  Warp group hf of the head owns the queries [64 hf, 64 hf + 64):
+//   [0,128)   S^T  (fp32)  -> P^T  packed bf16 at [0,32) (hf 0) and [64,96) (hf 1): each group overwrites columns it has already read
+//   [128,256) dP^T (fp32)  -> dS^T packed bf16 at [128,160) and [192,224)
+//   accumulators of the second round in the gaps: dV [32,64), dK [96,128), dQ [160,192)
 template <bool FULL>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(BWD_NT, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do, const __grid_constant__ BwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ float s_cs[4 * 2 * 96];                  // [head pair % 4][w][dQ | dK | dV][32]: bias-gradient column sums of this CTA
+  __shared__ float s_cs[4 * 2 * 96];                  // [head pair][w][dQ | dK | dV][32]: bias-gradient column sums of this CTA
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stage_base = smem;
   uint8_t* ds_smem = smem + BWD_STAGES * BWD_STAGE_BYTES;
@@ -302,32 +291,30 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
   uint64_t* full = bars;                    // [2] TMA -> MMA / compute
   uint64_t* empty = bars + BWD_STAGES;      // [2] MMA -> TMA
   uint64_t* s_full = empty + BWD_STAGES;    // [2] S^T and dP^T of head w are in TMEM
-  uint64_t* p_ready = s_full + 2;           // [2] P^T / dS^T (TMEM) and dS (smem) of head w are in place (128 arrivals)
+  uint64_t* p_ready = s_full + 2;           // [2] P^T / dS^T (TMEM) and dS (smem) of head w are in place (256 arrivals)
   uint64_t* g_full = p_ready + 2;           // [2] dV, dK, dQ of head w are in TMEM
-  uint64_t* g_read = g_full + 2;            // [2] ... and have been read out (128 arrivals)
+  uint64_t* g_read = g_full + 2;            // [2] ... and have been read out (256 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_read + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int hp_count = a.h >> 1;
   const int T = a.T;
-  for (int i = threadIdx.x; i < 4 * 2 * 96; i += NT) s_cs[i] = 0.f;
-  if (warp == 8 && lane == 0) {
+  for (int i = threadIdx.x; i < 4 * 2 * 96; i += BWD_NT) s_cs[i] = 0.f;
+  if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&map_qkv);
     tma_prefetch_desc(&map_do);
     for (int s = 0; s < BWD_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int w = 0; w < 2; ++w) { mbar_init(&s_full[w], 1); mbar_init(&p_ready[w], 128); mbar_init(&g_full[w], 1); mbar_init(&g_read[w], 128); }
+    for (int w = 0; w < 2; ++w) { mbar_init(&s_full[w], 1); mbar_init(&p_ready[w], 256); mbar_init(&g_full[w], 1); mbar_init(&g_read[w], 256); }
     mbar_init_fence();
   }
-  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  if (warp == 17) tmem_alloc<512>(tmem_slot);
   fence_before();
   __syncthreads();
   fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int n_my = ((int)blockIdx.x < a.n_items) ? (a.n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  // TMEM columns of head w (base w * 256): [0,128) S^T -> P^T packed in [0,64), dV in [64,96), dK in [96,128);
-  //                                        [128,256) dP^T -> dS^T packed in [128,192), dQ in [192,224)
 
-  if (warp == 8) {
+  if (warp == 16) {
     // ===== TMA producer =====
     if (lane == 0) {
       for (int it = 0; it < n_my; ++it) {
@@ -336,14 +323,14 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         const int stage = it & 1;
         mbar_wait(&empty[stage], (((uint32_t)it >> 1) & 1u) ^ 1u);
         uint8_t* sb = stage_base + stage * BWD_STAGE_BYTES;
-        mbar_expect_tx(&full[stage], (uint32_t)(4 * TILE_BYTES + 32 * T));
+        mbar_expect_tx(&full[stage], (uint32_t)BWD_STAGE_BYTES);
 #pragma unroll
         for (int k = 0; k < 3; ++k) tma_load_2d(sb + k * TILE_BYTES, &map_qkv, k * a.d + hp * 64, b * T, &full[stage]);
         tma_load_2d(sb + 3 * TILE_BYTES, &map_do, hp * 64, b * T, &full[stage]);
-        bulk_load(sb + 4 * TILE_BYTES, a.aux + ((size_t)b * a.h + 2 * hp) * 4 * T, (uint32_t)(32 * T), &full[stage]);
+        bulk_load(sb + 4 * TILE_BYTES, a.aux + ((size_t)b * a.h + 2 * hp) * 4 * TM, (uint32_t)BWD_AUX_BYTES, &full[stage]);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 17) {
     // ===== MMA issuer: two independent per-head state machines, polled =====
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc(TM, TM, 0, 0);
@@ -387,14 +374,14 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
               const uint32_t sds = smem_u32(ds_smem + w * BWD_DS_BYTES);
               const uint32_t tw = tmem_base + (uint32_t)(w * 256);
 #pragma unroll
-              for (int ks = 0; ks < TM / 16; ++ks)
-                mma_ts(tw + 64, tw + 8 * ks, make_desc(sg + 64 * w + 2048 * ks, 8192, 1024), idesc_ts, ks > 0);
+              for (int ks = 0; ks < TM / 16; ++ks)      // packed A columns of 16 queries: [8 ks, 8 ks + 8) for ks < 4, 64 + ... beyond
+                mma_ts(tw + 32, tw + (ks < 4 ? 8 * ks : 32 + 8 * ks), make_desc(sg + 64 * w + 2048 * ks, 8192, 1024), idesc_ts, ks > 0);
 #pragma unroll
               for (int ks = 0; ks < TM / 16; ++ks)
-                mma_ts(tw + 96, tw + 128 + 8 * ks, make_desc(sq + 64 * w + 2048 * ks, 8192, 1024), idesc_ts, ks > 0);
+                mma_ts(tw + 96, tw + 128 + (ks < 4 ? 8 * ks : 32 + 8 * ks), make_desc(sq + 64 * w + 2048 * ks, 8192, 1024), idesc_ts, ks > 0);
 #pragma unroll
               for (int ks = 0; ks < TM / 16; ++ks)
-                mma_ss(tw + 192, make_desc(sds + 2048 * ks, TILE_BYTES, 1024), make_desc(sk + 64 * w + 2048 * ks, 8192, 1024), idesc_dq, ks > 0);
+                mma_ss(tw + 160, make_desc(sds + 2048 * ks, TILE_BYTES, 1024), make_desc(sk + 64 * w + 2048 * ks, 8192, 1024), idesc_dq, ks > 0);
               commit(&g_full[w]);
               ++g_it[w];
               if (g_it[w ^ 1] >= g_it[w]) commit(&empty[stage]);      // both heads of this item are done with the stage
@@ -407,100 +394,127 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
       }
     }
   } else {
-    // ===== compute: warp group w owns head 2 hp + w, thread = key row j =====
+    // ===== compute: warp group g = 2 w + hf: head 2 hp + w, queries [64 hf, 64 hf + 64), thread = key row j =====
     const DropCfg drop = mt_drop_resolve(a.drop);
-    const int w = warp >> 2, j = threadIdx.x & 127;
+    const int g = warp >> 2, w = g >> 1, hf = g & 1, j = threadIdx.x & 127;
     const uint32_t tw = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(w * 256);
     const uint32_t P2 = (uint32_t)(T + 1) >> 1;
-    const uint32_t t16 = drop.thresh >> 16;
+    const uint32_t thr_hi = (drop.thresh >> 16) << 16;
+    const bool dropping = drop.thresh != 0u;
     const bool key_ok = FULL || j < T;
     const uint32_t odd = (uint32_t)j & 1u;
-    uint8_t* dsb = ds_smem + w * BWD_DS_BYTES;
+    uint8_t* dsb = ds_smem + w * BWD_DS_BYTES + hf * TILE_BYTES;      // this group's 64-query block of the MN-major dS operand
+    const uint64_t ds2 = pk2(drop.scale, drop.scale);
     for (int it = 0; it < n_my; ++it) {
       const uint32_t par = (uint32_t)it & 1u;
       const int item = (int)blockIdx.x + it * (int)gridDim.x;
       const int b = item / hp_count, hp = item % hp_count, hd = 2 * hp + w;
       const int stage = it & 1;
-      const float* ax = reinterpret_cast<const float*>(stage_base + stage * BWD_STAGE_BYTES + 4 * TILE_BYTES) + w * 4 * T;
-      const uint64_t bh = (uint64_t)b * a.h + hd;
+      const float* ax = reinterpret_cast<const float*>(stage_base + stage * BWD_STAGE_BYTES + 4 * TILE_BYTES) + w * 4 * TM;
+      // pair index of (query q, key pair j >> 1) = (bh T + q) P2 + (j >> 1); this lane draws for the queries q + (j & 1)
+      const uint32_t bh = (uint32_t)(b * a.h + hd);
+      const uint32_t pidx0 = (bh * (uint32_t)T + (uint32_t)(hf * 64) + odd) * P2 + (uint32_t)(j >> 1);
       mbar_wait(&full[stage], ((uint32_t)it >> 1) & 1u);       // aux vectors (the MMA warp waits on the same phase for the tiles)
       mbar_wait(&s_full[w], par);
       fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t s[32], dp[32], pkp[16], pks[16];
-        ld32(tw + (uint32_t)(c * 32), s);
-        ld32(tw + (uint32_t)(128 + c * 32), dp);
+      for (int cc = 0; cc < 4; ++cc) {
+        const int q0 = hf * 64 + cc * 16;
+        uint32_t s[16], dp[16], pkp[8], pks[8];
+        ld16(tw + (uint32_t)q0, s);
+        ld16(tw + (uint32_t)(128 + q0), dp);
         ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const int q = c * 32 + i;
-          const float2 L = *reinterpret_cast<const float2*>(ax + q), D = *reinterpret_cast<const float2*>(ax + T + q);
-          const float2 rs = *reinterpret_cast<const float2*>(ax + 2 * T + q), gs = *reinterpret_cast<const float2*>(ax + 3 * T + q);
-          const bool ok0 = key_ok && (FULL || q < T), ok1 = key_ok && (FULL || q + 1 < T);
-          const float p0 = ok0 ? ex2(__uint_as_float(s[i]) * rs.x - L.x) : 0.f;
-          const float p1 = ok1 ? ex2(__uint_as_float(s[i + 1]) * rs.y - L.y) : 0.f;
-          float f0 = 1.f, f1 = 1.f;
-          if (drop.thresh != 0u) {
+        for (int i = 0; i < 16; i += 4) {
+          const int q = q0 + i;
+          const float4 L = *reinterpret_cast<const float4*>(ax + q), D = *reinterpret_cast<const float4*>(ax + TM + q);
+          const float4 rs = *reinterpret_cast<const float4*>(ax + 2 * TM + q), gs = *reinterpret_cast<const float4*>(ax + 3 * TM + q);
+          const float Dk[4] = {D.x, D.y, D.z, D.w};
+          float p[4], t[4];
+          upk2(fma2(pk2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), pk2(rs.x, rs.y), pk2(-L.x, -L.y)), p[0], p[1]);
+          upk2(fma2(pk2(__uint_as_float(s[i + 2]), __uint_as_float(s[i + 3])), pk2(rs.z, rs.w), pk2(-L.z, -L.w)), p[2], p[3]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) p[k] = (key_ok && (FULL || q + k < T)) ? ex2(p[k]) : 0.f;
+          // t = dP . keep-scale - D ; without a kept draw the probability's gradient is -D
+          upk2(fma2(pk2(__uint_as_float(dp[i]), __uint_as_float(dp[i + 1])), ds2, pk2(-D.x, -D.y)), t[0], t[1]);
+          upk2(fma2(pk2(__uint_as_float(dp[i + 2]), __uint_as_float(dp[i + 3])), ds2, pk2(-D.z, -D.w)), t[2], t[3]);
+          float pd[4] = {p[0], p[1], p[2], p[3]};
+          if (dropping) {
             // the 32-bit draw of (query, key pair j >> 1) serves keys j and j ^ 1: this lane draws for query q + (j & 1), its
             // neighbour for the other query of the pair, and they swap
-            const uint64_t qa = (uint64_t)min(q + (int)odd, T - 1);
-            const uint32_t mine = mt_draw32(drop, (bh * T + qa) * P2 + (uint64_t)(j >> 1));
-            const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
-            const uint32_t b0 = odd ? other : mine, b1 = odd ? mine : other;
-            f0 = ((odd ? (b0 >> 16) : (b0 & 0xFFFFu)) >= t16) ? drop.scale : 0.f;
-            f1 = ((odd ? (b1 >> 16) : (b1 & 0xFFFFu)) >= t16) ? drop.scale : 0.f;
-          }
-          pkp[i >> 1] = pack_bf2(p0 * f0, p1 * f1);
-          pks[i >> 1] = pack_bf2(p0 * (__uint_as_float(dp[i]) * f0 - D.x) * gs.x, p1 * (__uint_as_float(dp[i + 1]) * f1 - D.y) * gs.y);
-        }
-        st16(tw + (uint32_t)(c * 16), pkp);
-        st16(tw + (uint32_t)(128 + c * 16), pks);
-        // dS as the MN-major A operand of dQ = dS K: k row = key j, 64 queries per 128-byte row, two 64-query blocks
-        uint8_t* db = dsb + (c >> 1) * TILE_BYTES;
 #pragma unroll
-        for (int qd = 0; qd < 4; ++qd)
-          *reinterpret_cast<uint4*>(db + sw128_off(j, (c & 1) * 4 + qd)) = make_uint4(pks[4 * qd], pks[4 * qd + 1], pks[4 * qd + 2], pks[4 * qd + 3]);
+            for (int k = 0; k < 4; k += 2) {
+              const uint32_t mine = mt_mix32((pidx0 + (uint32_t)(cc * 16 + i + k) * P2) ^ drop.key);
+              const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+              const uint32_t b0 = odd ? other : mine, b1 = odd ? mine : other;
+              const bool k0 = odd ? (b0 >= thr_hi) : ((b0 << 16) >= thr_hi), k1 = odd ? (b1 >= thr_hi) : ((b1 << 16) >= thr_hi);
+              pd[k] = k0 ? p[k] : 0.f;
+              t[k] = k0 ? t[k] : -Dk[k];
+              pd[k + 1] = k1 ? p[k + 1] : 0.f;
+              t[k + 1] = k1 ? t[k + 1] : -Dk[k + 1];
+            }
+          }
+          float e[4];
+          upk2(mul2(mul2(pk2(p[0], p[1]), pk2(gs.x, gs.y)), pk2(t[0], t[1])), e[0], e[1]);
+          upk2(mul2(mul2(pk2(p[2], p[3]), pk2(gs.z, gs.w)), pk2(t[2], t[3])), e[2], e[3]);
+          pkp[i >> 1] = pack_bf2(pd[0], pd[1]);
+          pkp[(i >> 1) + 1] = pack_bf2(pd[2], pd[3]);
+          pks[i >> 1] = pack_bf2(e[0], e[1]);
+          pks[(i >> 1) + 1] = pack_bf2(e[2], e[3]);
+        }
+        st8(tw + (uint32_t)(hf * 64 + cc * 8), pkp);
+        st8(tw + (uint32_t)(128 + hf * 64 + cc * 8), pks);
+        // dS as the MN-major A operand of dQ = dS K: k row = key j, 64 queries per 128-byte row
+        *reinterpret_cast<uint4*>(dsb + sw128_off(j, cc * 2)) = make_uint4(pks[0], pks[1], pks[2], pks[3]);
+        *reinterpret_cast<uint4*>(dsb + sw128_off(j, cc * 2 + 1)) = make_uint4(pks[4], pks[5], pks[6], pks[7]);
       }
       st_wait();
       fence_proxy_async();
       fence_before();
       mbar_arrive(&p_ready[w]);
-      // ---- gradients: dV | dK rows = keys, dQ rows = queries; all rows beyond T are exact zeros ----
+      // ---- gradients: dV | dK rows = keys, dQ rows = queries; all rows beyond T are exact zeros.  Group 0 of the head takes
+      //      dQ and the first half of dK, group 1 dV (which still lacks the keep scale) and the second half of dK ----
       mbar_wait(&g_full[w], par);
       fence_after();
-      uint32_t gv[32], gk[32], gq[32];
-      ld32(tw + 64, gv);
-      ld32(tw + 96, gk);
-      ld32(tw + 192, gq);
+      uint32_t gm[32], gk[16];
+      ld32(tw + (hf ? 32u : 160u), gm);
+      ld16(tw + (uint32_t)(96 + hf * 16), gk);
       ld_wait();
       fence_before();
       mbar_arrive(&g_read[w]);
+      float v[48];
+      {
+        const uint64_t sc2 = hf ? ds2 : pk2(1.f, 1.f);
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) upk2(mul2(pk2(__uint_as_float(gm[i]), __uint_as_float(gm[i + 1])), sc2), v[i], v[i + 1]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[32 + i] = __uint_as_float(gk[i]);
+      }
       if (key_ok) {
         bf16* gp = a.dqkv + ((size_t)b * T + j) * (3 * a.d) + hd * HD;
+        bf16* gmain = gp + (hf ? 2 * a.d : 0);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const uint32_t* src = k == 0 ? gq : (k == 1 ? gk : gv);
+        for (int qd = 0; qd < 4; ++qd) {
+          uint4 u;
+          u.x = pack_bf2(v[8 * qd], v[8 * qd + 1]); u.y = pack_bf2(v[8 * qd + 2], v[8 * qd + 3]);
+          u.z = pack_bf2(v[8 * qd + 4], v[8 * qd + 5]); u.w = pack_bf2(v[8 * qd + 6], v[8 * qd + 7]);
+          *reinterpret_cast<uint4*>(gmain + 8 * qd) = u;
+        }
+        bf16* gkp = gp + a.d + hf * 16;
 #pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
-            uint4 u;
-            u.x = pack_bf2(__uint_as_float(src[8 * qd]), __uint_as_float(src[8 * qd + 1]));
-            u.y = pack_bf2(__uint_as_float(src[8 * qd + 2]), __uint_as_float(src[8 * qd + 3]));
-            u.z = pack_bf2(__uint_as_float(src[8 * qd + 4]), __uint_as_float(src[8 * qd + 5]));
-            u.w = pack_bf2(__uint_as_float(src[8 * qd + 6]), __uint_as_float(src[8 * qd + 7]));
-            *reinterpret_cast<uint4*>(gp + (size_t)k * a.d + 8 * qd) = u;
-          }
+        for (int qd = 0; qd < 2; ++qd) {
+          uint4 u;
+          u.x = pack_bf2(v[32 + 8 * qd], v[33 + 8 * qd]); u.y = pack_bf2(v[34 + 8 * qd], v[35 + 8 * qd]);
+          u.z = pack_bf2(v[36 + 8 * qd], v[37 + 8 * qd]); u.w = pack_bf2(v[38 + 8 * qd], v[39 + 8 * qd]);
+          *reinterpret_cast<uint4*>(gkp + 8 * qd) = u;
         }
       }
       if (a.dbias != nullptr) {
-        // column sums over the warp's 32 rows: butterfly that halves the number of live columns per lane at every step
-        float v[96];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { v[i] = __uint_as_float(gq[i]); v[32 + i] = __uint_as_float(gk[i]); v[64 + i] = __uint_as_float(gv[i]); }
+        // column sums over the warp's 32 rows: a butterfly that halves the number of live columns per lane at every step
         int col = 0;
 #pragma unroll
-        for (int step = 0; step < 5; ++step) {
-          const int n2 = 48 >> step;                // 48, 24, 12, 6, 3
+        for (int step = 0; step < 4; ++step) {
+          const int n2 = 24 >> step;                // 24, 12, 6, 3
           const int m = 16 >> step;
           const bool up = (lane & m) != 0;
 #pragma unroll
@@ -510,22 +524,28 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
           }
           col += up ? n2 : 0;
         }
-        float* cs = s_cs + ((hp & 3) * 2 + w) * 96;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) atomicAdd(cs + col + i, v[i]);
+        for (int i = 0; i < 3; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 1);
+        if ((lane & 1) == 0) {
+          float* cs = s_cs + ((hp & 3) * 2 + w) * 96;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int cidx = col + i;      // < 32: column of dQ (hf 0) / dV (hf 1); else column cidx - 32 + 16 hf of dK
+            atomicAdd(cs + (cidx < 32 ? (hf ? 64 : 0) + cidx : 32 + 16 * hf + (cidx - 32)), v[i]);
+          }
+        }
       }
     }
   }
   fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == 17) {
     fence_after();
     tmem_dealloc<512>(tmem_base);
   }
   if (a.dbias != nullptr) {
-    // s_cs[(hp % 4)][w][k][c] -> dbias[k * d + (2 hp + w) * 32 + c]; with more than 4 head pairs several pairs share a slot only if
-    // h > 8, which mt_attn_tc_bwd_run excludes when dbias is requested
-    for (int i = threadIdx.x; i < hp_count * 2 * 96; i += NT) {
+    // s_cs[hp][w][k][c] -> dbias[k * d + (2 hp + w) * 32 + c]   (h <= 8: at most 4 head pairs)
+    for (int i = threadIdx.x; i < hp_count * 2 * 96; i += BWD_NT) {
       const int hp = i / 192, w = (i / 96) & 1, k = (i % 96) / 32, c = i % 32;
       const float val = s_cs[i];
       if (val != 0.f) atomicAdd(a.dbias + (size_t)k * a.d + (2 * hp + w) * HD + c, val);
@@ -557,6 +577,7 @@ int num_sms() {
 bool mt_attn_tc_supported(int B, int T, int d, int h) {
   if (d % h != 0 || d / h != HD || (h & 1) || T < 1 || T > TM) return false;
   if ((long long)B * T > 0x7fffffffLL / (3LL * d)) return false;
+  if ((unsigned long long)B * h * T * ((T + 1) / 2) >= 0xffffffffULL) return false;      // 32-bit dropout pair indices
   return d % 64 == 0;
 }
 
@@ -567,29 +588,27 @@ int mt_attn_tc_fwd_run(int B, int T, int d, int h, const void* qkv, const float*
   CUtensorMap map;
   MT_TRY(make_map_2d(&map, qkv, (uint64_t)3 * d, (uint64_t)B * T, (uint64_t)3 * d, 64, TM));
   FwdArgs a;
-  a.B = B; a.T = T; a.d = d; a.h = h; a.n_items = B * (h / 2); a.variant = g_variant;
+  a.B = B; a.T = T; a.d = d; a.h = h; a.n_items = B * (h / 2);
   a.scale_log2 = LOG2E / sqrtf((float)HD);
   a.mask = mask; a.out = (bf16*)out; a.lse = lse; a.klen = klen; a.drop = drop;
   static bool attr_full[16] = {}, attr_part[16] = {};
-  const int sms = num_sms();
-  const int grid = a.n_items < sms ? a.n_items : sms;
+  const int slots = 2 * num_sms();
+  const int grid = a.n_items < slots ? a.n_items : slots;
   mt_prof_work(4.0 * B * (double)T * T * d, (double)B * T * d * 4.0 * 2.0);
   if (T == TM && !klen) {
     MT_TRY(set_smem_attr(attn_tc_fwd_kernel<true>, FWD_SMEM, attr_full));
-    attn_tc_fwd_kernel<true><<<grid, NT, FWD_SMEM, st>>>(map, a);
+    attn_tc_fwd_kernel<true><<<grid, FWD_NT, FWD_SMEM, st>>>(map, a);
   } else {
     MT_TRY(set_smem_attr(attn_tc_fwd_kernel<false>, FWD_SMEM, attr_part));
-    attn_tc_fwd_kernel<false><<<grid, NT, FWD_SMEM, st>>>(map, a);
+    attn_tc_fwd_kernel<false><<<grid, FWD_NT, FWD_SMEM, st>>>(map, a);
   }
   MT_LAUNCH_CHECK();
   return MT_OK;
 }
 
-
-
 int mt_attn_tc_bwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse, const void* dout,
                        void* dqkv, DropCfg drop, float* dbias, float* aux, cudaStream_t st) {
-  if (!mt_attn_tc_supported(B, T, d, h) || (T & 1)) return MT_ERR_UNSUPPORTED;      // T even: 16-byte granularity of the aux bulk copy
+  if (!mt_attn_tc_supported(B, T, d, h)) return MT_ERR_UNSUPPORTED;
   if (dbias != nullptr && h > 8) return MT_ERR_UNSUPPORTED;
   if (!aux || ((uintptr_t)aux & 15) || ((uintptr_t)qkv & 15) || ((uintptr_t)dout & 15) || ((uintptr_t)dqkv & 15) || ((uintptr_t)out & 15))
     return MT_ERR_ALIGN;
@@ -603,7 +622,7 @@ int mt_attn_tc_bwd_run(int B, int T, int d, int h, const void* qkv, const float*
   MT_TRY(make_map_2d(&map_qkv, qkv, (uint64_t)3 * d, (uint64_t)B * T, (uint64_t)3 * d, 64, TM));
   MT_TRY(make_map_2d(&map_do, dout, (uint64_t)d, (uint64_t)B * T, (uint64_t)d, 64, TM));
   BwdArgs a;
-  a.B = B; a.T = T; a.d = d; a.h = h; a.n_items = B * (h / 2); a.variant = g_variant;
+  a.B = B; a.T = T; a.d = d; a.h = h; a.n_items = B * (h / 2);
   a.aux = aux; a.dqkv = (bf16*)dqkv; a.dbias = dbias; a.drop = drop;
   static bool attr_full[16] = {}, attr_part[16] = {};
   const int sms = num_sms();
@@ -611,10 +630,10 @@ int mt_attn_tc_bwd_run(int B, int T, int d, int h, const void* qkv, const float*
   mt_prof_work(10.0 * B * (double)T * T * d, (double)B * T * d * 8.0 * 2.0);
   if (T == TM) {
     MT_TRY(set_smem_attr(attn_tc_bwd_kernel<true>, BWD_SMEM, attr_full));
-    attn_tc_bwd_kernel<true><<<grid, NT, BWD_SMEM, st>>>(map_qkv, map_do, a);
+    attn_tc_bwd_kernel<true><<<grid, BWD_NT, BWD_SMEM, st>>>(map_qkv, map_do, a);
   } else {
     MT_TRY(set_smem_attr(attn_tc_bwd_kernel<false>, BWD_SMEM, attr_part));
-    attn_tc_bwd_kernel<false><<<grid, NT, BWD_SMEM, st>>>(map_qkv, map_do, a);
+    attn_tc_bwd_kernel<false><<<grid, BWD_NT, BWD_SMEM, st>>>(map_qkv, map_do, a);
   }
   MT_LAUNCH_CHECK();
   return MT_OK;
@@ -632,8 +651,6 @@ int mt_attention_tc_bwd(int B, int T, int d, int h, const void* qkv, const float
   return mt_attn_tc_bwd_run(B, T, d, h, qkv, mask, out, lse, dout, dqkv, mt_make_drop(p_drop, seed, site), dbias, (float*)ws,
                             (cudaStream_t)stream);
 }
-/* test hook: variant bits of the tcgen05 attention kernels (see g_variant); returns the previous value */
-int mt_attention_tc_variant(int v) { int old = g_variant; g_variant = v; return old; }
 /* direct entry to the tcgen05 forward (tests / probes); MT_ERR_UNSUPPORTED outside its envelope */
 int mt_attention_tc_fwd(int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, float p_drop, uint64_t seed,
                         uint32_t site, const int* key_len, void* stream) {

@@ -66,7 +66,7 @@ int mt_attn_tc_fwd_run(int B, int T, int d, int h, const void* qkv, const float*
 int mt_attn_tc_bwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse, const void* dout,
                        void* dqkv, DropCfg drop, float* dbias, float* aux, cudaStream_t st);
 // workspace of any attention backward (Dws of mt_attn_bwd_run), in floats
-static inline size_t mt_attn_bwd_ws_floats(int B, int T, int h) { return 4 * (size_t)B * (size_t)T * (size_t)h + 64; }
+static inline size_t mt_attn_bwd_ws_floats(int B, int T, int h) { return 4 * (size_t)B * (size_t)(T < 128 ? 128 : T) * (size_t)h + 64; }
 
 // ---- attention (mt_attention.cu) ---------------------------------------------------------------------
 int mt_attn_fwd_run(int dtype, int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop,

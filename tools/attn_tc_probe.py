@@ -22,7 +22,7 @@ def make(B, T, d, h, seed=0, masked=True):
     mask = torch.ones(B, T, device='cuda')
     if masked:
         for b in range(B):
-            n = T - (b * 7) % (T // 2)
+            n = T - (b * 7) % max(T // 2, 1)
             mask[b, n:] = 0
     dout = (torch.randn(B, T, d, device='cuda', generator=g) * 0.5).to(torch.bfloat16)
     return qkv, mask, dout
@@ -114,9 +114,8 @@ def main():
         print('prof ok')
         return
     res = {}
-    cases = [(4, 128, 0.0), (4, 128, 0.1), (5, 100, 0.0), (3, 40, 0.1), (2, 16, 0.0)]
-    for variant in (0, 1, 2, 3):
-        L.mt_attention_tc_variant(variant)
+    cases = [(4, 128, 0.0), (4, 128, 0.1), (300, 128, 0.1), (5, 100, 0.0), (3, 40, 0.1), (2, 16, 0.0), (7, 37, 0.1), (3, 1, 0.0)]
+    for variant in (0,):
         for (B, T, p) in cases:
             key = f'v{variant}_B{B}_T{T}_p{p}'
             qkv, mask, dout = make(B, T, d, h, seed=B * 1000 + T)
@@ -140,7 +139,6 @@ def main():
                 res[key] = 'ERROR ' + str(e)
                 print(json.dumps(res, indent=1))
                 return
-    L.mt_attention_tc_variant(0)
     if what in ('fwd', 'all'):      # ragged inference
         B, T = 6, 128
         qkv, mask, _ = make(B, T, d, h, seed=7, masked=False)
@@ -159,13 +157,13 @@ def main():
         res[f'time_B{B}'] = {}
         if what in ('fwd', 'all'):
             res[f'time_B{B}']['fwd_old_us'] = timeit(lambda: fwd_old(B, T, d, h, qkv, mask, p, 99))
-            for v in (0, 1, 2):
-                L.mt_attention_tc_variant(v)
-                res[f'time_B{B}'][f'fwd_tc_v{v}_us'] = timeit(lambda: fwd_new(B, T, d, h, qkv, mask, p, 99))
-            L.mt_attention_tc_variant(0)
+            res[f'time_B{B}']['fwd_tc_us'] = timeit(lambda: fwd_new(B, T, d, h, qkv, mask, p, 99))
+            res[f'time_B{B}']['fwd_tc_nodrop_us'] = timeit(lambda: fwd_new(B, T, d, h, qkv, mask, 0.0, 99))
         if what in ('bwd', 'all'):
             res[f'time_B{B}']['bwd_old_us'] = timeit(lambda: bwd_old(B, T, d, h, qkv, mask, out, lse, dout, p, 99))
             res[f'time_B{B}']['bwd_tc_us'] = timeit(lambda: bwd_new(B, T, d, h, qkv, mask, out, lse, dout, p, 99))
+            db = torch.zeros(3 * d, device='cuda')
+            res[f'time_B{B}']['bwd_tc_dbias_us'] = timeit(lambda: bwd_new(B, T, d, h, qkv, mask, out, lse, dout, p, 99, db))
     print(json.dumps(res, indent=1))
     os.makedirs('gpurun_out', exist_ok=True)
     json.dump(res, open(f'gpurun_out/attn_tc_probe_{what}.json', 'w'), indent=1)
