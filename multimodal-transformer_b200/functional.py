@@ -12,6 +12,8 @@ import torch
 from . import _lib
 from ._lib import ACT_NONE, ACT_RELU, ACT_TANH, MT_BF16, MT_F32, check, lib, ptr, require, stream
 
+_SITE_RESIDUAL = 0x7000      # stand-alone SublayerConnection dropout: its own site range (0x6000.. belongs to the window front-end)
+
 _state = {'dtype': MT_F32, 'seed': 0x5EED0000, 'counter': 0, 'fixed_seed': None, 'parallel_stacks': True, 'defer_wgrad': False,
           'pending': [], 'wgrad_stream': {}, 'key_len': None}
 
@@ -110,8 +112,10 @@ def fix_seed(seed):
 def next_seed():
     if _state['fixed_seed'] is not None:
         return _state['fixed_seed']
+    # consecutive calls are a large odd stride apart: a captured graph adds +1 per replay to every seed (seed_off), so a unit stride
+    # would hand call k at replay r the seed of call k + 1 at replay r - 1 (identical masks on shared sites)
     _state['counter'] += 1
-    return (_state['seed'] * 0x9E3779B97F4A7C15 + _state['counter']) & 0xFFFFFFFFFFFFFFFF
+    return (_state['seed'] * 0x9E3779B97F4A7C15 + _state['counter'] * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
 
 
 def _apply(fn, *args):
@@ -302,7 +306,7 @@ class ResidualDropoutFn(torch.autograd.Function):
         y = require(y if y.is_contiguous() else y.contiguous(), torch.float32, 'y')
         out = torch.empty_like(x)
         seed = next_seed() if p > 0 else 0
-        check(lib().mt_residual_dropout_fwd(ptr(x), ptr(y), ptr(out), x.numel(), p, seed, 0x6000, stream()))
+        check(lib().mt_residual_dropout_fwd(ptr(x), ptr(y), ptr(out), x.numel(), p, seed, _SITE_RESIDUAL, stream()))
         ctx.meta = (p, seed)
         return out
 
@@ -313,7 +317,7 @@ class ResidualDropoutFn(torch.autograd.Function):
         if p <= 0:
             return g, g, None
         gy = torch.empty_like(g)
-        check(lib().mt_dropout_bwd(ptr(g), ptr(gy), g.numel(), p, seed, 0x6000, stream()))
+        check(lib().mt_dropout_bwd(ptr(g), ptr(gy), g.numel(), p, seed, _SITE_RESIDUAL, stream()))
         return g, gy, None
 
 

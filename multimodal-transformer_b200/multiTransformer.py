@@ -139,6 +139,18 @@ class EncoderLayer(nn.Module):
         return self.sublayer[1](x, self.feed_forward)
 
 
+def _check_encoder_shape(d_model, h, what):
+    """The sm_100a encoder kernels cover d_model % 128 == 0 (<= 1024) with head widths 16 / 32 / 64 -- every configuration the reference
+    instantiates except the 16-wide 'emotient' modality (EMBED 16, h = 8 -> d_k = 2, MFT/multiTransformer.py:260).  There is no CPU /
+    PyTorch fallback on this path, so an unsupported shape fails HERE, at construction, not at the first forward."""
+    dk = d_model // h if h and d_model % h == 0 else 0
+    if d_model % 128 != 0 or d_model > 1024 or dk not in (16, 32, 64):
+        raise NotImplementedError(
+            f'{what}: d_model={d_model}, h={h} (d_k={dk}) is outside the B200 encoder kernels (d_model % 128 == 0, d_model <= 1024, '
+            f'd_k in 16/32/64); the reference\'s "emotient" modality (d_model 16) is the one reference configuration not covered -- '
+            f'see INTEGRATION.md, "Unsupported reference configurations"')
+
+
 class Encoder(nn.Module):
     """MFT/multiTransformer.py:67-76: N cloned layers + final LayerNorm, executed by mt_encoder_fwd / mt_encoder_bwd
     on a flat parameter arena (the nn.Parameters below are views into it, so state_dict / optimizers see the
@@ -146,6 +158,8 @@ class Encoder(nn.Module):
 
     def __init__(self, layer, N):
         super().__init__()
+        if isinstance(layer, EncoderLayer) and isinstance(layer.self_attn, MultiHeadedAttention):
+            _check_encoder_shape(layer.size, layer.self_attn.h, 'Encoder')
         self.layers = clones(layer, N)
         self.norm = LayerNorm(layer.size)
         self.stack_id = 0          # selects the dropout streams of this stack

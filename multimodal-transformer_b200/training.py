@@ -229,6 +229,11 @@ class GraphedTrainStep:
         self.mask.copy_(mask.reshape(self.B, self.T, 1), non_blocking=True)
         self.target.copy_(target.reshape(self.B, self.T, 1), non_blocking=True)
         self.inv_norm.fill_(1.0 / self.norm_fn(lengths))
+        self._refresh_lr()
+
+    def _refresh_lr(self):
+        """The captured Adam reads lr from device memory: mirror opt.param_groups[0]['lr'] (ReduceLROnPlateau and friends change it
+        between steps) on EVERY path that feeds the graph -- load(), step_from_corpus() and step_prefetched()."""
         lr = float(self.opt.param_groups[0]['lr'])
         if lr != getattr(self, '_lr_seen', None):
             self.lr.fill_(lr); self._lr_seen = lr
@@ -238,9 +243,7 @@ class GraphedTrainStep:
         into the graph's static inputs (no intermediate batch, no second copy), then the captured step replays."""
         lengths = corpus.batch_into(chunk, self.x, self.target, self.mask)
         self.inv_norm.fill_(1.0 / self.norm_fn(lengths))
-        lr = float(self.opt.param_groups[0]['lr'])
-        if lr != getattr(self, '_lr_seen', None):
-            self.lr.fill_(lr); self._lr_seen = lr
+        self._refresh_lr()
         if self.graph is None:
             self.capture()
         return self.replay()
@@ -352,6 +355,7 @@ class GraphedTrainStep:
         self.target.copy_(st['target'], non_blocking=True)
         st['free'].record(cur)
         self.inv_norm.fill_(1.0 / self.norm_fn(st['lengths']))
+        self._refresh_lr()
         if self.graph is None:
             self.capture()
         return self.replay()
@@ -379,8 +383,9 @@ class GraphedForward:
 
     def _fwd(self):
         self.model.eval()
+        from .evaluation import _call                  # models.py classes take (inputs, length, mask), multiTransformer.py's (inputs, mask, lengths)
         with torch.no_grad():
-            return self.model(self.x, self.mask, self.lengths)
+            return _call(self.model, self.x, self.mask, self.lengths)
 
     def capture(self):
         side = torch.cuda.Stream(device=self.device)

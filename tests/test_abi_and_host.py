@@ -120,3 +120,13 @@ def test_no_product_import_of_oracle():
     out = subprocess.run(['grep', '-rlE', r'^\s*(from|import)\s+oracle', os.path.join(ROOT, 'multimodal-transformer_b200'),
                           os.path.join(ROOT, 'multimodal_transformer_b200')], capture_output=True, text=True).stdout
     assert out.strip() == ''
+
+
+def test_encoder_rejects_unsupported_shapes_at_construction():
+    """The reference's 'emotient' modality (d_model 16, h 8 -> d_k 2) is outside the sm_100a kernels: the constructor says so
+     instead of failing at the first forward."""
+    with pytest.raises(NotImplementedError, match='emotient'):
+        mtb.MultiTransformer(['emotient', 'linguistic'], {'emotient': 20, 'linguistic': 300})
+    with pytest.raises(NotImplementedError):
+        mtb.Encoder(mtb.EncoderLayer(16, mtb.MultiHeadedAttention(8, 16), mtb.PositionwiseFeedForward(16, 128), 0.1), 2)
+    mtb.MFN(['emotient', 'linguistic'], {'emotient': 16, 'linguistic': 256}, 1)      # the MFN alone takes it

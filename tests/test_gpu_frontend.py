@@ -480,3 +480,24 @@ def test_batch_into_static_buffers_equals_batch():
     assert torch.equal(msk[:, :Tb], mask) and not msk[:, Tb:].any()
     with pytest.raises(RuntimeError, match='do not fit'):
         corpus.batch_into(chunk[:5], x, tgt, msk)
+
+
+def test_graphed_forward_with_window_front_end():
+    """GraphedForward over a MultiCNNTransformer (forward(inputs, length, mask) argument order, raw windows in) equals the eager eval()
+    forward of the same model."""
+    from multimodal_transformer_b200.training import GraphedForward
+    m = front_meta()['front_mft']
+    shapes = {k: tuple(v) for k, v in m['shapes'].items()}
+    dims = {k: v[1] for k, v in shapes.items()}
+    inv = front_inventory()['MFT.MultiCNNTransformer']
+    sd = util.filled_sd({k: tuple(s) for k, s in inv.items()}, 9)
+    B, T = 3, 9
+    inputs, mask, target, lengths = fill.make_raw_batch(B, T, shapes, 41)
+    model = M.MultiCNNTransformer(m['mods'], dims, m['embed_dims']); model.load_state_dict(sd)
+    model.eval()
+    with torch.no_grad():
+        ref = model({k: t(v).to(DEV) for k, v in inputs.items()}, [T] * B, t(mask).to(DEV)).clone()
+    gf = GraphedForward(model, B, T, shapes, torch.device(DEV), warmup=1)
+    out = gf({k: t(v) for k, v in inputs.items()}, t(mask))
+    torch.cuda.synchronize()
+    assert_close(out, ref, 1e-5, 'pred', 1e-7)

@@ -864,3 +864,39 @@ def test_graph_replay_draws_fresh_dropout_masks():
     b = gstep({k: t(v) for k, v in inputs.items()}, t(mask), t(target), lengths).item()
     assert a != b
     assert _lib.lib().mt_launch_count() > 0
+
+
+def test_prefetch_path_follows_lr_changes():
+    """An LR scheduler (ReduceLROnPlateau pokes opt.param_groups[0]['lr'], MFT/train.py:558,588) must reach the captured Adam on the
+    prefetch path too: halving the lr mid-run gives the same parameters through step_prefetched() as through __call__()."""
+    from multimodal_transformer_b200.training import FlatAdam, GraphedTrainStep
+    N, B, T = 1, 4, 8
+    dims = {'acoustic': 88, 'image': 256, 'linguistic': 300}
+    sd = util.filled_sd(util.mods_shapes('MFT.MultiTransformer', N), 15)
+    batches = [fill.make_batch(B, T, dims, 30 + i) for i in range(4)]
+    pin = lambda a: t(a).pin_memory()
+
+    def run(prefetched, halve):
+        model = mtb.MultiTransformer(MODS, dims, N=N, dropout=0.0).to(DEV); model.load_state_dict(sd)
+        for mod in model.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        opt = FlatAdam(model, lr=1e-2)
+        g = GraphedTrainStep(model, opt, B, T, dims, torch.device(DEV), warmup=1)
+        hb = [({k: pin(v) for k, v in i.items()}, pin(m), pin(tg), l) for i, m, tg, l in batches]
+        for k, b in enumerate(hb):
+            if k == 2 and halve:
+                opt.param_groups[0]['lr'] *= 0.5
+            if prefetched:
+                g.prefetch(*b); g.step_prefetched()
+            else:
+                g(*b)
+        torch.cuda.synchronize()
+        return {k: p.detach().clone() for k, p in model.named_parameters() if not k.startswith(('attn', 'ff'))}
+
+    direct, pre, pre_const = run(False, True), run(True, True), run(True, False)
+    moved = 0.0
+    for k in direct:
+        assert_close(pre[k], direct[k], 1e-4, k, 1e-5)
+        moved = max(moved, (pre[k] - pre_const[k]).abs().max().item())
+    assert moved > 1e-4          # the halved lr really changed the trajectory
