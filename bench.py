@@ -32,6 +32,21 @@ DIMS = {'acoustic': 88, 'image': 256, 'linguistic': 300}
 METRIC = 'MFT narratives/sec (train step + inference)'
 FLOP_PER_TOKEN_FWD = 15836288          # SURVEY 8(d), T = 128
 
+# BASELINE.json configs (SURVEY 8(d) "configs restated").  c2 is the headline workload (and, sharded over ranks, config 3);
+# the others are driver-runnable lines of the same contract:  python bench.py --config c1|c4|c5
+CONFIGS = {
+    'c1': dict(label='SFT-VL (image 2x1000 + linguistic 33x300 raw windows -> window CNNs -> fusionLayer 556->512 -> NLPTransformer N=6), '
+                     'eval() forward, default train.py settings (SFT/train.py:533-535)', batch=25, seq=128, train=False,
+               flop_fwd_per_token=7188736),
+    'c2': dict(label='MFT-VAL', batch=256, seq=128, train=True, flop_fwd_per_token=FLOP_PER_TOKEN_FWD),
+    'c4': dict(label='B3-MFN (inputs 300/256/256 -> Linear embeds -> MFN, no encoder; B3-MFN/multiTransformer.py:250-307), LSTHM + '
+                     'delta-memory recurrence over 1024-window sequences, train step = fwd + loss + BPTT + Adam', batch=256, seq=1024,
+               train=True, flop_fwd_per_token=1766528),
+    'c5': dict(label='scaled MFT stress: three encoder stacks d_model 512, 8 heads (d_k 64), d_ff 256, N=6 + MFN on 512-wide inputs, '
+                     'T=4096; train step over the batch in micro-batches with gradient accumulation, then Adam', batch=512, seq=4096,
+               train=True, flop_fwd_per_token=200650000),
+}
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -39,17 +54,24 @@ def parse():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=256, help='narratives per GPU')
-    ap.add_argument('--seq', type=int, default=128)
+    ap.add_argument('--config', default='c2', choices=sorted(CONFIGS), help='BASELINE.json configuration (c2 = headline; c3 = c2 on N GPUs)')
+    ap.add_argument('--batch', type=int, default=0, help='narratives per GPU (0 = the configuration\'s own)')
+    ap.add_argument('--seq', type=int, default=0, help='windows per narrative (0 = the configuration\'s own)')
+    ap.add_argument('--micro', type=int, default=8, help='c5: narratives per micro-batch')
     ap.add_argument('--layers', type=int, default=6)
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
-    ap.add_argument('--cpu-sample', type=int, default=32, help='narratives per CPU-baseline step (the reference trains with batch 25, MFT/train.py:74)')
+    ap.add_argument('--cpu-sample', type=int, default=0, help='narratives per CPU-baseline step (0 = per configuration; the reference trains with batch 25, MFT/train.py:74)')
+    ap.add_argument('--port', action='store_true', help='--impl reference: time the oracle port even when baseline/_ref is present')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-profile', action='store_true')
     ap.add_argument('--gemm-mode', type=int, default=0, help='tcgen05 GEMM CTAs per SM (tuning; 0 = library default)')
     ap.add_argument('--tune', default='', help='library tuning knobs, e.g. 0=2,1=2 (mt_tune key=value)')
     ap.add_argument('--serial-stacks', action='store_true', help='run the modality stacks on one stream')
-    return ap.parse_args()
+    a = ap.parse_args()
+    c = CONFIGS[a.config]
+    a.batch = a.batch or c['batch']
+    a.seq = a.seq or c['seq']
+    return a
 
 
 def peaks():
@@ -108,8 +130,105 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------
+# Reference arm: the reference's OWN classes (baseline/_ref, copied verbatim by tools/install_ref.sh at build time) on the host cores,
+# in train mode with dropout and torch.optim.Adam exactly as MFT/train.py:110-155,557 drive them; the oracle port only if the
+# reference sources are absent (or --port).  Every configuration runs a BOUNDED sample of its workload and says which.
+C4_DIMS = {'acoustic': 256, 'image': 256, 'linguistic': 300}        # B3-MFN/models.py:90 window_embed_size
+C1_RAW = {'image': (2, 1000), 'linguistic': (33, 300)}              # SFT/train.py:533 mods, raw (K vectors, D) per window
+
+
+def _ref_train_step(model, xin, mk, tg, lengths, call):
+    """One iteration of the body of train() (MFT/train.py:119-143): forward, MSE(sum) / sum(lengths), backward, Adam, zero_grad."""
+    import torch
+    crit = torch.nn.MSELoss(reduction='sum')
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-4)
+
+    def step():
+        model.train()
+        out = call(model, xin, mk, lengths)
+        loss = crit(out, tg)
+        loss = loss / sum(lengths)
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        return float(loss)
+    return step
+
+
+def reference_step_factory(args):
+    """-> (step(), narratives per step, kind, description of the bounded sample)"""
+    import torch
+    from oracle import ref_loader as R
+    from multimodal_transformer_b200 import synthetic as fill
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(1)                                             # MFT/train.py:524
+    cfg, T = args.config, args.seq
+    t = torch.from_numpy
+    use_ref = R.available() and not args.port
+    if not use_ref:
+        if cfg != 'c2':
+            raise RuntimeError('baseline/_ref is missing (tools/install_ref.sh): only c2 has an oracle-port CPU arm')
+        B = args.cpu_sample or 25
+        return cpu_train_step_factory(args.layers, B, T), B, 'port', f'oracle port (no dropout), {B} narratives x T={T}'
+    hot = lambda m, x, mk, l: m(x, mk, l)                           # multiTransformer.py classes: (inputs, mask, lengths)
+    if cfg == 'c2':
+        B = args.cpu_sample or 25                                   # the reference's real batch size (generateTrainBatch default, MFT/train.py:74)
+        mt = R.load('MFT', 'multiTransformer')
+        model = R.cpu_instance(mt.MultiTransformer(MODS, DIMS, N=args.layers))
+        inputs, mask, target, lengths = fill.make_batch(B, T, DIMS, 1)
+        step = _ref_train_step(model, {k: t(v) for k, v in inputs.items()}, t(mask), t(target), lengths, hot)
+        return step, B, 'reference', (f'baseline/_ref MFT/multiTransformer.py::MultiTransformer N={args.layers}, train() body (dropout on, '
+                                      f'MSE(sum)/sum(lengths), Adam lr 1e-4 wd 1e-4), {B} narratives x T={T}, fp32')
+    if cfg == 'c1':
+        B = args.cpu_sample or 25
+        md = R.load('SFT', 'models')
+        mods = ['image', 'linguistic']
+        model = R.cpu_instance(md.MultiCNNTransformer(mods, {m: C1_RAW[m][1] for m in mods}))
+        inputs, mask, target, lengths = fill.make_raw_batch(B, T, C1_RAW, 1)
+        xin, mk = {k: t(v) for k, v in inputs.items()}, t(mask)
+
+        def step():
+            model.eval()
+            with torch.no_grad():
+                return float(model(xin, lengths, mk).sum())         # models.py classes: (inputs, length, mask)
+        return step, B, 'reference', f'baseline/_ref SFT/models.py::MultiCNNTransformer(image, linguistic), eval() forward, {B} narratives x T={T} raw windows, fp32'
+    if cfg == 'c4':
+        B = args.cpu_sample or 4
+        mt = R.load('B3-MFN', 'multiTransformer')
+        model = R.cpu_instance(mt.MultiTransformer(MODS, C4_DIMS))
+        inputs, mask, target, lengths = fill.make_batch(B, T, C4_DIMS, 1)
+        step = _ref_train_step(model, {k: t(v) for k, v in inputs.items()}, t(mask), t(target), lengths, hot)
+        return step, B, 'reference', f'baseline/_ref B3-MFN/multiTransformer.py::MultiTransformer, train() body, {B} narratives x T={T}, fp32'
+    if cfg == 'c5':
+        # the reference hard-codes d_model 256 inside MultiTransformer (MFT/multiTransformer.py:260): the scaled model is composed from
+        # its own primitives.  Bounded: 1 narrative, T capped at 1024 (the [B,h,T,T] scores it materialises need 0.5 GB per layer and
+        # stack at T = 4096) -- per token this UNDER-states the reference's cost at the full length.
+        B, Tc = 1, min(T, 1024)
+        mt = R.load('MFT', 'multiTransformer')
+        d, h, dff, N = 512, 8, 256, args.layers
+
+        class Scaled(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.embed = torch.nn.ModuleDict({m: torch.nn.Linear(d, d) for m in MODS})
+                self.enc = torch.nn.ModuleDict({m: mt.Encoder(mt.EncoderLayer(d, mt.MultiHeadedAttention(h, d), mt.PositionwiseFeedForward(d, dff, 0.1), 0.1), N)
+                                                for m in MODS})
+                self.mfn = mt.MFN(MODS, {m: d for m in MODS}, 1)
+
+            def forward(self, inputs, mask, lengths):
+                xs = {m: self.enc[m](self.embed[m](inputs[m]), mask).permute(1, 0, 2) for m in MODS}
+                return self.mfn(xs) * mask.float()
+        model = R.cpu_instance(Scaled())
+        dims = {m: d for m in MODS}
+        inputs, mask, target, lengths = fill.make_batch(B, Tc, dims, 1)
+        step = _ref_train_step(model, {k: t(v) for k, v in inputs.items()}, t(mask), t(target), lengths, hot)
+        return step, B * Tc / T, 'reference', (f'reference primitives (Encoder / MFN of baseline/_ref MFT/multiTransformer.py) at d=512 h=8 dff=256 N={N}, '
+                                               f'train() body, 1 narrative x T={Tc} = {Tc / T:.3f} narratives of T={T}, fp32')
+    raise ValueError(cfg)
+
+
 def cpu_train_step_factory(n_layers, B, T, seed=1):
-    """The oracle (CPU restatement of the reference path) doing one MFT train step: fwd + loss + backward + Adam."""
+    """The oracle (CPU restatement of the reference path) doing one MFT train step: fwd + loss + backward + Adam (no dropout)."""
     import torch
     from oracle import fill, mt_oracle as O
     from tests import util
@@ -132,29 +251,61 @@ def cpu_train_step_factory(n_layers, B, T, seed=1):
     return step
 
 
+def config_block(args, world, extra=None):
+    c = CONFIGS[args.config]
+    out = {'workload': f'{args.config}: {c["label"]}', 'batch_per_gpu': args.batch, 'global_batch': args.batch * world, 'seq_len': args.seq,
+           'parallelism': f'dp{world}'}
+    out.update(extra or {})
+    return out
+
+
+def metric_of(args):
+    if args.config == 'c2':
+        return METRIC
+    return {'c1': 'SFT narratives/sec (inference)', 'c4': 'B3-MFN narratives/sec (train step + inference)',
+            'c5': 'scaled-MFT narratives/sec (train step)'}[args.config]
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
+    import contextlib
     import torch
-    step = cpu_train_step_factory(args.layers, args.cpu_sample, args.seq)
-    for _ in range(max(1, min(args.warmup, 2))):
+    with contextlib.redirect_stdout(sys.stderr):                     # the reference's constructors print(): stdout carries ONE JSON line
+        step, per_step, kind, sample = reference_step_factory(args)
+    w = max(1, min(args.warmup, 2))
+    for _ in range(w):
         step()
-    k = max(1, min(args.steps, 5))
-    t0 = time.perf_counter()
-    for _ in range(k):
-        step()
+    # bounded: at most 5 timed steps, and stop early once ~40 s of CPU time are spent
+    k_max, k, t0 = max(1, min(args.steps, 5)), 0, time.perf_counter()
+    while k < k_max and (k == 0 or time.perf_counter() - t0 < 40.0):
+        step(); k += 1
     dt = (time.perf_counter() - t0) / k
-    val = args.cpu_sample / dt
+    val = per_step / dt
     cores = torch.get_num_threads()
-    sample = f'{args.cpu_sample} narratives x T={args.seq} per step, {k} timed steps (requested {args.steps}), fp32, torch CPU'
+    sample += f'; {w} warm-up + {k} timed steps (requested {args.steps}), {cores} threads of os.cpu_count()={os.cpu_count()}'
     print(json.dumps({
-        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'narratives/s', 'n_gpus': args.gpus, 'steps': k, 'warmup': min(args.warmup, 2),
+        'impl': 'reference', 'metric': metric_of(args), 'value': val, 'unit': 'narratives/s', 'n_gpus': args.gpus, 'steps': k, 'warmup': w,
         'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'MFT-VAL N={args.layers} train step (fwd+loss+bwd+Adam), T={args.seq}; CPU arm runs a bounded sample',
-                   'batch_per_step': args.cpu_sample, 'seq_len': args.seq},
-        'cpu_baseline': {'value': val, 'unit': 'narratives/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'config': config_block(args, 1, {'cpu_arm': 'bounded sample of the workload, see cpu_baseline.sample', 'narratives_per_cpu_step': per_step}),
+        'cpu_baseline': {'value': val, 'unit': 'narratives/s', 'cores': cores, 'kind': kind, 'sample': sample},
         'e2e': {'value': val, 'unit': 'narratives/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'gpu_launches': 0}))
+        'gpu_launches': 0}), flush=True)
+
+
+def cpu_baseline_subprocess(args):
+    """The reference arm in a child process that cannot see the GPU (the reference's constructors grab cuda:0 when they can)."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES='')
+    for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK'):
+        env.pop(k, None)
+    cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--config', args.config, '--steps', '3', '--warmup', '1',
+           '--layers', str(args.layers), '--seq', str(args.seq)] + (['--cpu-sample', str(args.cpu_sample)] if args.cpu_sample else [])
+    try:
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+        line = [l for l in r.stdout.splitlines() if l.startswith('{')][-1]
+        return json.loads(line)['cpu_baseline']
+    except Exception as e:                                           # noqa: BLE001 -- the GPU line must not die with the CPU leg
+        return {'value': None, 'unit': 'narratives/s', 'cores': os.cpu_count(), 'kind': 'unavailable', 'sample': f'reference arm failed: {e!r}'[:300]}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -181,43 +332,68 @@ def run_ours(args, rank, local_rank, world):
     if args.serial_stacks:
         mtb.set_parallel_stacks(False)
     B, T, N = args.batch, args.seq, args.layers
+    cfg = args.config
+    is_train = CONFIGS[cfg]['train']
 
     torch.manual_seed(1)                                            # MFT/train.py:524; default (random) init
-    model = mtb.MultiTransformer(MODS, DIMS, N=N, device=dev)
+    if cfg == 'c2':
+        dims = DIMS
+        model = mtb.MultiTransformer(MODS, DIMS, N=N, device=dev)
+        inputs, mask, target, lengths = fill.make_batch(B, T, dims, 1 + rank)
+    elif cfg == 'c4':
+        dims = C4_DIMS
+        model = mtb.B3MultiTransformer(MODS, C4_DIMS, device=dev)
+        inputs, mask, target, lengths = fill.make_batch(B, T, dims, 1 + rank)
+    elif cfg == 'c1':
+        from multimodal_transformer_b200 import models as M
+        dims = C1_RAW                                                # mod -> (K, D): the window front-end is part of the model
+        model = M.SFTMultiCNNTransformer(list(C1_RAW), {m: kd[1] for m, kd in C1_RAW.items()}, device=dev)
+        inputs, mask, target, lengths = fill.make_raw_batch(B, T, dims, 1 + rank)
+    else:
+        raise ValueError(cfg)
     model.to(dev)
     opt = FlatAdam(model, lr=1e-4, weight_decay=1e-4)
-
-    inputs, mask, target, lengths = fill.make_batch(B, T, DIMS, 1 + rank)
     norm = float(sum(sum(fill.make_lengths(B, T, 1 + r)) for r in range(world)))      # GLOBAL sum of lengths
     host = {k: torch.from_numpy(v).pin_memory() for k, v in inputs.items()}
     host_mask, host_target = torch.from_numpy(mask).pin_memory(), torch.from_numpy(target).pin_memory()
     res = {k: v.to(dev) for k, v in host.items()}
     res_mask, res_target = host_mask.to(dev), host_target.to(dev)
-    h2d = sum(v.numel() * 4 for v in host.values()) + host_mask.numel() * 4 + host_target.numel() * 4
+    h2d = sum(v.numel() * 4 for v in host.values()) + host_mask.numel() * 4 + (host_target.numel() * 4 if is_train else 0)
     loss_host = torch.zeros(1).pin_memory()
     pred_host = torch.zeros(B, T, 1).pin_memory()
 
     # eager path (one launch at a time; used for the per-kernel breakdown and reported as `eager`)
+    from multimodal_transformer_b200.evaluation import _call
+
     def train_step(e2e):
         x, m, tg = res, res_mask, res_target
+        if not is_train:
+            model.eval()
+            with torch.no_grad():
+                return _call(model, x, m, lengths)
         model.train()
-        pred = model(x, m, lengths)
+        pred = _call(model, x, m, lengths)
         loss = train_step_loss(pred, tg, norm)
         opt.step()
         opt.zero_grad()
         return loss
 
     # the product path: the whole step captured once into a CUDA graph (multimodal_transformer_b200.training)
-    gstep = GraphedTrainStep(model, opt, B, T, DIMS, dev, norm_fn=lambda _l: norm)
     for _ in range(2):
         train_step(False)
-    gstep.load(res, res_mask, res_target, lengths)
-    l0 = L.mt_launch_count()
-    gstep.capture()
-    launches_per_step = (L.mt_launch_count() - l0) // (gstep.warmup + 1)
-    gfwd = GraphedForward(model, B, T, DIMS, dev)
+    gstep = None
+    if is_train:
+        gstep = GraphedTrainStep(model, opt, B, T, dims, dev, norm_fn=lambda _l: norm)
+        gstep.load(res, res_mask, res_target, lengths)
+        l0 = L.mt_launch_count()
+        gstep.capture()
+        launches_per_step = (L.mt_launch_count() - l0) // (gstep.warmup + 1)
+    gfwd = GraphedForward(model, B, T, dims, dev)
     gfwd.load(res, res_mask)
+    l0 = L.mt_launch_count()
     gfwd.capture()
+    if not is_train:
+        launches_per_step = (L.mt_launch_count() - l0) // (gfwd.warmup + 1)
 
     # e2e: every step copies its inputs from pinned host memory and reads its result back.  The public API pipelines the
     # input copy: batch k + 1 crosses PCIe on a copy stream while batch k computes (GraphedTrainStep.prefetch).
@@ -276,15 +452,22 @@ def run_ours(args, rank, local_rank, world):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms_train = timed(g_train, False, W, K)
-    clocks = sampler.stop() if sampler else None
+    if is_train:
+        ms_train = timed(g_train, False, W, K)
+        clocks = sampler.stop() if sampler else None
+        note('train timed')
+        ms_inf = timed(g_infer, False, W, K)
+    else:
+        ms_inf = timed(g_infer, False, W, K)
+        clocks = sampler.stop() if sampler else None
+        ms_train = ms_inf                                           # inference-only configuration: `value` is the eval() forward
     launches = launches_per_step * K
-    note('train timed')
-    ms_inf = timed(g_infer, False, W, K)
     note('inference timed')
-    ms_train_e2e = timed(g_train, True, W, K)
+    ms_train_e2e = timed(g_train, True, W, K) if is_train else None
     note('train e2e timed')
     ms_inf_e2e = timed(g_infer, True, W, K)
+    if not is_train:
+        ms_train_e2e = ms_inf_e2e
     note('inference e2e timed')
     ms_eager = timed(train_step, False, 2, max(2, min(K, 5)))
     note('eager timed')
@@ -348,39 +531,38 @@ def run_ours(args, rank, local_rank, world):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        step = cpu_train_step_factory(N, args.cpu_sample, T)
-        step()
-        t0 = time.perf_counter()
-        reps = 3
-        for _ in range(reps):
-            step()
-        dt = (time.perf_counter() - t0) / reps
-        cpu = dict(value=args.cpu_sample / dt, unit='narratives/s', cores=torch.get_num_threads(), kind='port',
-                   sample=f'oracle MFT train step on {args.cpu_sample} narratives x T={T}, 1 warm-up + {reps} timed, fp32 torch CPU, '
-                          f'os.cpu_count()={os.cpu_count()}')
+        cpu = cpu_baseline_subprocess(args)
 
     if rank == 0:
         gb = world * B
         stash_gb = 3 * N * B * T * (256 * (4 + 2 + 6 + 2 + 4 + 2) + 128 * 2) / 1e9
+        fpt = CONFIGS[cfg]['flop_fwd_per_token'] if (cfg != 'c2' or (T == 128 and N == 6)) else None
+        if cfg == 'c2':
+            wl = {'workload': f'c2: MFT-VAL (acoustic 88 / image 256 / linguistic 300), N={N} d=256 h=8 dff=128, train step = fwd + '
+                              f'MSE/sum(lengths) + bwd + {"NCCL all-reduce + " if world > 1 else ""}Adam(lr 1e-4, wd 1e-4), dropout on',
+                  'l2': f'no explicit flush: each step streams ~{stash_gb:.1f} GB of activations per GPU, far above the 126 MB L2',
+                  'value_is': 'train step, inputs resident in HBM'}
+        else:
+            in_mb = h2d / 1e6
+            wl = {'l2': f'no explicit flush: every step reads {in_mb:.0f} MB of inputs plus its activation stash per GPU, above the 126 MB L2'
+                        if in_mb > 130 or is_train else f'inputs ({in_mb:.0f} MB) exceed L2 only together with the activations; no explicit flush',
+                  'value_is': ('train step' if is_train else 'eval() forward') + ', inputs resident in HBM'}
         out = {
-            'metric': METRIC, 'value': gb / (ms_train * 1e-3), 'unit': 'narratives/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+            'metric': metric_of(args), 'value': gb / (ms_train * 1e-3), 'unit': 'narratives/s', 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': ms_train, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype,
             'data': 'synthetic',
-            'config': {'workload': f'MFT-VAL (acoustic 88 / image 256 / linguistic 300), N={N} d=256 h=8 dff=128, train step = fwd + '
-                                   f'MSE/sum(lengths) + bwd + {"NCCL all-reduce + " if world > 1 else ""}Adam(lr 1e-4, wd 1e-4), dropout on',
-                       'batch_per_gpu': B, 'global_batch': gb, 'seq_len': T, 'parallelism': f'dp{world}',
-                       'l2': f'no explicit flush: each step streams ~{stash_gb:.1f} GB of activations per GPU, far above the 126 MB L2',
-                       'value_is': 'train step, inputs resident in HBM'},
+            'config': config_block(args, world, wl),
             'inference': {'value': gb / (ms_inf * 1e-3), 'unit': 'narratives/s', 'ms_per_step': ms_inf,
                           'e2e_value': gb / (ms_inf_e2e * 1e-3), 'd2h_bytes_per_step': B * T * 4},
             'e2e': {'value': gb / (ms_train_e2e * 1e-3), 'unit': 'narratives/s', 'ms_per_step': ms_train_e2e, 'h2d_bytes_per_step': h2d,
-                    'd2h_bytes_per_step': 4},
+                    'd2h_bytes_per_step': 4 if is_train else B * T * 4},
             'gpu_launches': int(launches),
             'launch_mode': f'one CUDA graph per step ({int(launches_per_step)} kernel nodes from libmt_b200.so, captured once); '
                            f'eager launch of the same step: {ms_eager:.2f} ms',
             'eager': {'ms_per_step': ms_eager, 'value': gb / (ms_eager * 1e-3)},
             'clocks': clocks,
-            'model_flops_utilisation': {'train_tflops_per_gpu': 3 * FLOP_PER_TOKEN_FWD * B * T / (ms_train * 1e-3) / 1e12 if T == 128 and N == 6 else None},
+            'model_flops_utilisation': {('train_tflops_per_gpu' if is_train else 'inference_tflops_per_gpu'):
+                                        (3 if is_train else 1) * fpt * B * T / (ms_train * 1e-3) / 1e12 if fpt else None},
             'roofline': roofline, 'kernels': kernels, 'cpu_baseline': cpu,
         }
         print(json.dumps(out), flush=True)
@@ -389,7 +571,8 @@ def run_ours(args, rank, local_rank, world):
         # communicator teardown hang the job after the result line is out
         torch.cuda.synchronize()
         dist.barrier()
-        gstep.graph = None
+        if gstep is not None:
+            gstep.graph = None
         gfwd.graph = None
         torch.cuda.synchronize()
         opt.close()                                  # the library's own NCCL communicator (mt_comm_*)
@@ -398,6 +581,161 @@ def run_ours(args, rank, local_rank, world):
         watchdog.start()
         dist.destroy_process_group()
         watchdog.cancel()
+
+# ---------------------------------------------------------------------------------------------------------
+def run_c5(args, rank, local_rank, world):
+    """BASELINE.json configs[4]: scaled MFT (d_model 512, 8 heads, T = 4096, batch 512).  The training stash of one narrative is ~0.8 GB
+    at this size, so the batch is walked in micro-batches of --micro narratives with gradient accumulation (the loss normaliser is the
+    sum of lengths of the WHOLE batch), followed by one Adam step: the same update as one 512-narrative step."""
+    import torch
+    import torch.distributed as dist
+    import multimodal_transformer_b200 as mtb
+    from multimodal_transformer_b200 import _lib
+    from multimodal_transformer_b200.training import FlatAdam, train_step_loss
+    from multimodal_transformer_b200 import synthetic as fill
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    L = _lib.lib()
+    mtb.set_compute_dtype(args.dtype)
+    B, T, N, mb, d = args.batch, args.seq, args.layers, args.micro, 512
+    assert B % mb == 0, '--batch must be a multiple of --micro'
+    n_mb = B // mb
+
+    class ScaledMFT(mtb.MultiTransformer):
+        EMBED = {'linguistic': d, 'emotient': 16, 'acoustic': d, 'image': d}
+
+    torch.manual_seed(1)
+    dims = {m: d for m in MODS}
+    model = ScaledMFT(MODS, dims, N=N, d_ff=256, h=8, device=dev).to(dev)
+    opt = FlatAdam(model, lr=1e-4, weight_decay=1e-4)
+    # synthetic inputs: one pinned-host micro-batch (the e2e path re-sends it for every micro-batch, like the c2 line re-sends its batch
+    # every step) and per-micro-batch device-resident inputs drawn on the device
+    inputs, mask, target, lengths = fill.make_batch(mb, T, dims, 1 + rank)
+    host = {k: torch.from_numpy(v).pin_memory() for k, v in inputs.items()}
+    host_mask, host_target = torch.from_numpy(mask).pin_memory(), torch.from_numpy(target).pin_memory()
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    res = [{m: torch.randn(mb, T, d, device=dev, generator=g) for m in MODS} for _ in range(min(n_mb, 4))]      # rotated: 4 x 201 MB > L2
+    res_mask, res_target = host_mask.to(dev), host_target.to(dev)
+    norm = float(sum(lengths)) * n_mb * world
+    stage = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+    loss_host = torch.zeros(1).pin_memory()
+    h2d = n_mb * (sum(v.numel() * 4 for v in host.values()) + host_mask.numel() * 4 + host_target.numel() * 4)
+
+    def step(e2e):
+        model.train()
+        total = None
+        for i in range(n_mb):
+            if e2e:
+                for k in stage:
+                    stage[k].copy_(host[k], non_blocking=True)
+                x, m_, tg = stage, host_mask.to(dev, non_blocking=True), host_target.to(dev, non_blocking=True)
+            else:
+                x, m_, tg = res[i % len(res)], res_mask, res_target
+            pred = model(x, m_, lengths)
+            l_ = train_step_loss(pred, tg, norm)
+            total = l_ if total is None else total + l_
+        opt.step()
+        opt.zero_grad()
+        if e2e:
+            loss_host.copy_(total, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return total
+
+    def infer(e2e):
+        model.eval()
+        with torch.no_grad():
+            for i in range(n_mb):
+                model(res[i % len(res)], res_mask, lengths)
+
+    def timed(fn, e2e, warm, steps):
+        for _ in range(warm):
+            fn(e2e)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn(e2e)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item() / steps
+
+    # a c5 step is tens of seconds: 1 warm-up + at most 2 timed steps keep the default run within minutes (the step itself is
+    # n_mb identical micro-steps, i.e. already an average over n_mb repetitions)
+    W, K = 1, max(1, min(args.steps, 2))
+    l0 = L.mt_launch_count()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_train = timed(step, False, W, K)
+    clocks = sampler.stop() if sampler else None
+    launches = (L.mt_launch_count() - l0) * K // (W + K)
+    ms_e2e = timed(step, True, 0, 1)
+    ms_inf = timed(infer, False, 0, 1)
+
+    roofline, kernels = None, None
+    if rank == 0 and not args.no_profile:
+        import ctypes
+        P = peaks()
+        n_mb_saved, n_mb = n_mb, 1                                    # profile ONE micro-batch step
+        mtb.set_parallel_stacks(False)
+        torch.cuda.synchronize()
+        _lib.check(L.mt_spin(60.0, _lib.stream()))
+        _lib.check(L.mt_prof_start(20000, _lib.stream()))
+        step(False)
+        torch.cuda.synchronize()
+        n = L.mt_prof_stop()
+        n_mb = n_mb_saved
+        agg, name = {}, ctypes.create_string_buffer(128)
+        ms, fl, by = ctypes.c_float(), ctypes.c_double(), ctypes.c_double()
+        for i in range(n):
+            _lib.check(L.mt_prof_get(i, name, 128, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(by)))
+            a = agg.setdefault(name.value.decode(), [0.0, 0.0, 0.0, 0])
+            a[0] += ms.value; a[1] += fl.value; a[2] += by.value; a[3] += 1
+        tot = sum(a[0] for a in agg.values())
+        kernels = []
+        for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:20]:
+            ent = dict(site=k, launches_per_micro_step=a[3], ms_per_micro_step=a[0], share=a[0] / tot)
+            if a[1] > 0:
+                ent['tflops'] = a[1] / (a[0] * 1e-3) / 1e12
+            if a[2] > 0:
+                ent['gbs'] = a[2] / (a[0] * 1e-3) / 1e9
+            kernels.append(ent)
+        top = kernels[0]
+        f_t, f_h = top.get('tflops', 0.0) / P['tf_sustained'], top.get('gbs', 0.0) / P['hbm']
+        roofline = (dict(bound='tensor', achieved=top.get('tflops', 0.0), peak=P['tf_sustained'], unit='TFLOP/s', frac=f_t) if f_t >= f_h else
+                    dict(bound='hbm', achieved=top.get('gbs', 0.0), peak=P['hbm'], unit='GB/s', frac=f_h))
+        roofline.update(kernel=top['site'], share_of_step=top['share'], peak_source=P['src'], traffic=None,
+                        how='algorithmic work annotated at the launch site / CUDA-event duration, one micro-batch step profiled')
+    cpu = cpu_baseline_subprocess(args) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    if rank == 0:
+        gb = world * B
+        fpt = CONFIGS['c5']['flop_fwd_per_token'] if (T == 4096 and N == 6) else None
+        print(json.dumps({
+            'metric': metric_of(args), 'value': gb / (ms_train * 1e-3), 'unit': 'narratives/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+            'ms_per_step': ms_train, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
+            'config': config_block(args, world, {'micro_batch': mb, 'micro_steps_per_step': n_mb,
+                                                 'l2': 'inputs rotate over 4 micro-batches (805 MB) and every micro-step streams GBs of activations: above the 126 MB L2',
+                                                 'value_is': 'train step (gradient accumulation over micro-batches + Adam), inputs resident in HBM'}),
+            'inference': {'value': gb / (ms_inf * 1e-3), 'unit': 'narratives/s', 'ms_per_step': ms_inf},
+            'e2e': {'value': gb / (ms_e2e * 1e-3), 'unit': 'narratives/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4},
+            'gpu_launches': int(launches), 'launch_mode': 'eager launches (a micro-step is ~0.3 s of kernels; launch overhead is noise)',
+            'clocks': clocks,
+            'model_flops_utilisation': {'train_tflops_per_gpu': 3 * fpt * B * T / (ms_train * 1e-3) / 1e12 if fpt else None},
+            'roofline': roofline, 'kernels': kernels, 'cpu_baseline': cpu}), flush=True)
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        opt.close()
+        dist.destroy_process_group()
 
 
 def main():
@@ -411,7 +749,10 @@ def main():
                '--master-port', '29533', os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
     if args.impl == 'reference':
+        os.environ['CUDA_VISIBLE_DEVICES'] = ''       # the reference's constructors grab cuda:0 whenever torch can see one: this arm is the CPU path
         run_reference(args, rank)
+    elif args.config == 'c5':
+        run_c5(args, rank, local_rank, world)
     else:
         run_ours(args, rank, local_rank, world)
 

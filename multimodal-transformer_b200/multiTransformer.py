@@ -287,7 +287,7 @@ class MultiTransformer(nn.Module):
         super().__init__()
         self.mods = mods
         self.window_embed_size = window_embed_size
-        self.embed_dim = dict(MultiTransformer.EMBED)
+        self.embed_dim = dict(type(self).EMBED)      # subclasses may scale d_model (bench.py --config c5)
         self.use_encoder = use_encoder
         self.embed, self.transformer, self.lstm, self.attn, self.ff = dict(), dict(), dict(), dict(), dict()
         for i, mod in enumerate(mods):
