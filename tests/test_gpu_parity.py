@@ -416,7 +416,7 @@ def test_mft_golden(name, N):
     model.load_state_dict(util.filled_sd(util.mods_shapes('MFT.MultiTransformer', N), m['seed']))
     inputs, mask, target, lengths = fill.make_batch(m['B'], m['T'], m['dims'], m['seed'])
     pred = model({k: t(v).to(DEV) for k, v in inputs.items()}, t(mask).to(DEV), lengths)
-    np.testing.assert_allclose(pred.detach().cpu().numpy(), gold['pred'], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(pred.detach().cpu().numpy(), gold['pred'], rtol=1e-5, atol=1e-7)      # north star: 1e-5 relative in fp32 mode
     assert pred.shape == (m['B'], m['T'], 1)
     assert (pred.detach().cpu()[t(mask) == 0] == 0).all()
     if 'loss' in gold:
@@ -485,10 +485,11 @@ def _enc_shapes_d(N, d, dff):
     return out
 
 
-@pytest.mark.parametrize('mode,T', [('fp32', 300), ('bf16', 1024)])
+@pytest.mark.parametrize('mode,T', [('fp32', 300), ('bf16', 1024), ('bf16', 4096)])
 def test_config5_scaled_encoder_d512_long_sequence(mode, T):
-    """BASELINE config 5 shape class (d_model 512, 8 heads of 64, d_ff 256, long T -> the tiled any-T attention engine) on one
-    narrative, forward + backward against the fp64 oracle; the last quarter of the windows is padding."""
+    """BASELINE config 5 (d_model 512, 8 heads of 64, d_ff 256, T up to the configuration's 4096 -> the tiled any-T attention engine) on
+    one narrative, forward + backward against the fp64 oracle; the last quarter of the windows is padding.  bf16: output within 2e-2
+    of max |y|, every parameter gradient within 8e-2 of its tensor's largest entry (measured at T = 4096: 4.2e-3 / 4.1e-2)."""
     from multimodal_transformer_b200.multiTransformer import _make_encoder as mk
     d, dff, N, B = 512, 256, 1, 1
     enc = mk(d, dff, 8, 0.1, N).to(DEV).eval()
@@ -508,31 +509,42 @@ def test_config5_scaled_encoder_d512_long_sequence(mode, T):
     if mode == 'fp32':
         assert_close(y, yr, 2e-5, 'y'); assert_close(xd.grad, xr.grad, 5e-5, 'dx')
     else:
-        assert (y.float().cpu() - yr.float()).abs().max().item() < 6e-2 * max(1.0, yr.abs().max().item())
+        assert_close(y, yr, 2e-2, 'y')
+        gmax = max(v.grad.abs().max().item() for v in sdr.values() if v.grad is not None)
+        for k, p in enc.named_parameters():
+            assert_close(p.grad, sdr['e.' + k].grad, 8e-2, k, 1e-4 * gmax)      # floor: the key bias gradient is analytically zero
+        # the input gradient sums 4096 bf16-rounded probabilities per element: bounded in the max norm AND in direction
+        assert_close(xd.grad, xr.grad, 0.2, 'dx')
         cos = torch.nn.functional.cosine_similarity(xd.grad.float().cpu().flatten(), xr.grad.float().flatten(), dim=0).item()
-        assert cos > 0.99, cos
+        assert cos > 0.995, cos
 
 
-def test_config4_b3_mfn_long_recurrence():
-    """BASELINE config 4 shape class: B3-MFN (no encoder) over 1024-window sequences, bf16 tensor-core recurrences, B = 3 (ragged
-    tile): prediction within the bf16 budget of the fp64 oracle at every step (error must not grow along the recurrence)."""
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_config4_b3_mfn_long_recurrence(mode):
+    """BASELINE config 4 shape class: B3-MFN (no encoder) over 1024-window sequences, B = 3 (ragged recurrence tile), forward AND
+    BPTT against the fp64 oracle: fp32 mode 2e-5 / 1e-4, bf16 (tensor-core recurrences) valence within 2e-2 at every step (the error
+    must not grow along the recurrence) and every gradient within 3e-2 of its tensor's largest entry (measured 6e-3)."""
     dims = {'acoustic': 256, 'image': 256, 'linguistic': 300}
     T, B = 1024, 3
     sd = util.filled_sd(util.mods_shapes('B3.MultiTransformer'), 12)
     inputs, mask, target, lengths = fill.make_batch(B, T, dims, 12)
-    with torch.no_grad():
-        predr = O.multi_transformer({k: v.double() for k, v in sd.items()}, '', {k: t(v).double() for k, v in inputs.items()},
-                                    t(mask).double(), MODS, use_encoder=False)
-    mtb.set_compute_dtype('bf16')
+    sdr = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    predr = O.multi_transformer(sdr, '', {k: t(v).double() for k, v in inputs.items()}, t(mask).double(), MODS, use_encoder=False)
+    O.train_loss(predr, t(target).double(), lengths).backward()
+    gmax = max(v.grad.abs().max().item() for v in sdr.values() if v.grad is not None)
+    mtb.set_compute_dtype(mode)
     model = mtb.B3MultiTransformer(MODS, dims).eval(); model.load_state_dict(sd)
     pred = model({k: t(v).to(DEV) for k, v in inputs.items()}, t(mask).to(DEV), lengths)
-    err = (pred.detach().float().cpu() - predr.float()).abs()
-    assert err.max().item() < 2e-2, err.max().item()
-    assert err[:, T // 2:].max().item() < 2e-2
-    # BPTT over 1024 steps runs and produces finite gradients for every MFN parameter
+    err = (pred.detach().double().cpu() - predr.detach()).abs()
+    if mode == 'fp32':
+        assert_close(pred, predr, 2e-5, 'pred')
+    else:
+        assert err.max().item() < 2e-2, err.max().item()
+        assert err[:, T // 2:].max().item() < 2e-2
     ((pred - t(target).to(DEV)) ** 2).sum().div(sum(lengths)).backward()
     for k, p in model.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        assert_close(p.grad, sdr[k].grad, 1e-4 if mode == 'fp32' else 3e-2, k, (1e-6 if mode == 'fp32' else 1e-4) * gmax)
 
 
 def test_full_size_properties_batch256():
@@ -552,6 +564,33 @@ def test_full_size_properties_batch256():
     assert torch.equal(p1, p2)
     assert torch.isfinite(p1).all() and (p1 * (1 - m)).abs().max().item() == 0.0
     assert torch.equal(ps, p1[sub])
+
+
+def test_config2_full_size_sampled_narratives_vs_fp64_oracle():
+    """The BENCHMARKED configuration (B = 256 narratives, T = 128, N = 6, bf16) against the oracle: narratives are independent units
+    (no cross-sample op on the path), so the fp64 oracle run on 8 sampled narratives ALONE must reproduce their rows of the full-batch
+    bf16 prediction within the north star's 2e-2 on valence, and the per-narrative CCC to 3 decimals."""
+    from oracle.ccc import eval_ccc
+    dims = {'acoustic': 88, 'image': 256, 'linguistic': 300}
+    B, T, N = 256, 128, 6
+    sd = util.filled_sd(util.mods_shapes('MFT.MultiTransformer', N), 77)
+    inputs, mask, target, lengths = fill.make_batch(B, T, dims, 78)
+    mtb.set_compute_dtype('bf16')
+    model = mtb.MultiTransformer(MODS, dims, N=N).eval(); model.load_state_dict(sd)
+    with torch.no_grad():
+        pred = model({k: t(v).to(DEV) for k, v in inputs.items()}, t(mask).to(DEV), lengths).float().cpu()
+    pick = [0, 1, 37, 100, 128, 199, 254, 255]          # first / last rows of GEMM tiles, both ends of the length-sorted batch
+    with torch.no_grad():
+        predr = O.multi_transformer({k: v.double() for k, v in sd.items()}, '', {k: t(v[pick]).double() for k, v in inputs.items()},
+                                    t(mask[pick]).double(), MODS, N=N).float()
+    err = (pred[pick] - predr).abs().max().item()
+    assert err < 2e-2, err
+    rs = np.random.RandomState(1)
+    for i, b in enumerate(pick):
+        l = lengths[b]
+        ref = predr[i, :l, 0].numpy()
+        tgt = 0.5 + 8.0 * (ref - ref.mean()) + 0.02 * rs.standard_normal(l)
+        assert abs(eval_ccc(tgt, ref) - eval_ccc(tgt, pred[b, :l, 0].numpy())) < 5e-4, b
 
 
 @pytest.mark.parametrize('B,T,lengths', [(1, 1, [1]), (1, 5, [5]), (2, 3, [3, 1]), (9, 2, [2, 2, 2, 2, 1, 1, 1, 1, 1]), (3, 129, [129, 64, 1])])
@@ -616,7 +655,8 @@ def test_mft_train_mode_matches_oracle_with_same_masks():
 def test_mft_train_mode_medium_batch_both_dtypes_same_masks():
     """Train mode (dropout on, the SAME counter-based masks in the oracle) at a size where every persistent kernel walks several
     work items: 40 narratives x 128 windows = 320 (narrative, head) attention items, 40 GEMM row tiles, 5 recurrence tiles.
-    fp32 mode: 2e-5 / 3e-4 against the fp64 oracle; bf16 mode: valence within 2e-2, every gradient's cosine > 0.97."""
+    fp32 mode: 2e-5 / 3e-4 against the fp64 oracle; bf16 mode: valence within 2e-2 and, per gradient tensor,
+    max |error| <= 4e-2 of the tensor's largest gradient (measured: 1.2e-2 worst)."""
     N, B, T, seed = 1, 40, 128, 4711
     dims = {'acoustic': 88, 'image': 256, 'linguistic': 300}
     sd = util.filled_sd(util.mods_shapes('MFT.MultiTransformer', N), 23)
@@ -642,9 +682,9 @@ def test_mft_train_mode_medium_batch_both_dtypes_same_masks():
                 continue
             if mode == 'fp32':
                 assert_close(p.grad, want, 3e-4, k, fl)
-            elif want.norm() > 100 * fl:
-                cos = torch.nn.functional.cosine_similarity(p.grad.double().cpu().flatten(), want.flatten(), dim=0).item()
-                assert cos > 0.97, (k, cos)
+            else:       # per-tensor relative bound; tensors whose gradient is (analytically) tiny are judged on the global scale
+                gmax = max(v.grad.abs().max().item() for v in sdr.values() if v.grad is not None)
+                assert_close(p.grad, want, 4e-2, k, 4e-5 * gmax)
 
 
 def test_bf16_mode_valence_within_2e2_and_ccc():
@@ -667,28 +707,37 @@ def test_bf16_mode_valence_within_2e2_and_ccc():
         ref = predr[b, :l, 0].numpy()
         target = 0.5 + 8.0 * (ref - ref.mean()) + 0.02 * rs.standard_normal(l)
         c_ref, c_16 = eval_ccc(target, ref), eval_ccc(target, p16[b, :l, 0].numpy())
-        assert abs(c_ref - c_16) < 1.5e-3, (b, c_ref, c_16)
+        assert abs(c_ref - c_16) < 5e-4, (b, c_ref, c_16)            # 'CCC unchanged to 3 decimals'
 
 
 @pytest.mark.parametrize('name,cls,fin,inv', [('sft', 'NLPTransformer', 512, 'SFT.NLPTransformer'), ('unifull', 'UniFullTransformer', 556, 'MFT.UniFullTransformer'),
                                               ('uni', 'UniTransformer', 300, 'MFT.UniTransformer')])
 def test_bf16_mode_other_models_within_2e2(name, cls, fin, inv):
     """bf16 mode on the SFT / B2-Trans / Uni bodies (encoder stack + LSTM decoder with output feedback or MLP head): prediction within
-    2e-2 of the fp32 path (itself pinned to the reference's golden outputs in test_sft_golden / test_uni_golden), backward finite."""
+    2e-2 of the fp64 ORACLE (not of this repository's own fp32 path), every parameter gradient within 6e-2 of its tensor's largest
+    entry + 4e-3 of the largest gradient of the model (tensors with tiny gradients carry absolute bf16 noise: measured 8.8e-4 /
+    2.9e-3 of the global scale); fp32 mode at 1e-5 / 3e-4 against the same oracle."""
     N, B, T = 2, 4, 24
     sd = util.filled_sd(util.mods_shapes(inv, N), 17)
     inputs, mask, target, lengths = fill.make_batch(B, T, {'x': fin}, 17)
     x = t(inputs['x']).to(DEV); m = t(mask).to(DEV)
-    preds = {}
+    ofn = {'NLPTransformer': O.nlp_transformer, 'UniFullTransformer': O.uni_full_transformer, 'UniTransformer': O.uni_transformer}[cls]
+    sdr = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    predr = ofn(sdr, '', t(inputs['x']).double(), t(mask).double(), N=N)
+    O.train_loss(predr, t(target).double(), lengths).backward()
+    gmax = max(v.grad.abs().max().item() for v in sdr.values() if v.grad is not None)
     for mode in ('fp32', 'bf16'):
         mtb.set_compute_dtype(mode)
         model = getattr(mtb, cls)(fin, N=N).eval(); model.load_state_dict(sd)
         pred = model(x, m, lengths)
         (((pred - t(target).to(DEV)) ** 2).sum() / sum(lengths)).backward()
-        preds[mode] = pred.detach().float().cpu()
+        if mode == 'fp32':
+            assert_close(pred, predr, 1e-5, 'pred', 1e-7)
+        else:
+            assert (pred.detach().double().cpu() - predr.detach()).abs().max().item() < 2e-2
         for k, p in model.named_parameters():
             assert p.grad is not None and torch.isfinite(p.grad).all(), (mode, k)
-    assert (preds['bf16'] - preds['fp32']).abs().max().item() < 2e-2
+            assert_close(p.grad, sdr[k].grad, 3e-4 if mode == 'fp32' else 6e-2, f'{mode}:{k}', (1e-6 if mode == 'fp32' else 4e-3) * gmax)
 
 
 def test_bf16_train_step_runs_and_grads_are_close():
@@ -897,6 +946,6 @@ def test_prefetch_path_follows_lr_changes():
     direct, pre, pre_const = run(False, True), run(True, True), run(True, False)
     moved = 0.0
     for k in direct:
-        assert_close(pre[k], direct[k], 1e-4, k, 1e-5)
+        assert_close(pre[k], direct[k], 1e-4, k, 2e-4)      # Adam turns round-off of analytically-zero gradients (key bias) into +-lr steps
         moved = max(moved, (pre[k] - pre_const[k]).abs().max().item())
     assert moved > 1e-4          # the halved lr really changed the trajectory
