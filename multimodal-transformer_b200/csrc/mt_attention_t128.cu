@@ -402,11 +402,10 @@ __global__ void __launch_bounds__(NT, DK <= 32 ? 2 : 1) attn128_bwd_kernel(int B
 template <int DK>
 int launch_bwd(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse, const void* dout, void* dqkv,
                DropCfg drop, float scale, float* dbias, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
+  static MtPerDeviceOnce once;
+  if (once.first()) {
     MT_CUDA(cudaFuncSetAttribute(attn128_bwd_kernel<DK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdSmem<DK>::BYTES));
     MT_CUDA(cudaFuncSetAttribute(attn128_bwd_kernel<DK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdSmem<DK>::BYTES));
-    attr = true;
   }
   const int per_sm = DK <= 32 ? 2 : 1;
   int grid = (per_sm * 148 / (g_mt_tune[MT_TUNE_ATTN_SHARE] > 1 ? g_mt_tune[MT_TUNE_ATTN_SHARE] : 1) / h) * h;      // a multiple of h: every CTA keeps one head
@@ -439,11 +438,10 @@ int mt_attn128_fwd_run(int B, int T, int d, int h, const void* qkv, const float*
   const int grid = B * h < slots ? B * h : slots;
 #define MT_FWD(DK)                                                                                                                     \
   {                                                                                                                                    \
-    static bool attr = false;                                                                                                          \
-    if (!attr) {                                                                                                                       \
+    static MtPerDeviceOnce once;                                                                                                       \
+    if (once.first()) {                                                                                                                \
       MT_CUDA(cudaFuncSetAttribute(attn128_fwd_kernel<DK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdSmem<DK>::BYTES));  \
       MT_CUDA(cudaFuncSetAttribute(attn128_fwd_kernel<DK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdSmem<DK>::BYTES)); \
-      attr = true;                                                                                                                     \
     }                                                                                                                                  \
     if (T == TMAX && !klen) attn128_fwd_kernel<DK, true><<<grid, NT, FwdSmem<DK>::BYTES, st>>>(B, T, d, h, (const bf16*)qkv, mask, (bf16*)out, lse, drop, scale, nullptr);  \
     else attn128_fwd_kernel<DK, false><<<grid, NT, FwdSmem<DK>::BYTES, st>>>(B, T, d, h, (const bf16*)qkv, mask, (bf16*)out, lse, drop, scale, klen);          \

@@ -555,13 +555,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
 
 // one-time (per device) opt-in to the large dynamic shared-memory carve-out
 template <typename K>
-int set_smem_attr(K kernel, int bytes, bool (&done)[16]) {
-  int dev = 0;
-  MT_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 16 || !done[dev]) {
-    MT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    if (dev >= 0 && dev < 16) done[dev] = true;
-  }
+int set_smem_attr(K kernel, int bytes, MtPerDeviceOnce& once) {
+  if (once.first()) MT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   return MT_OK;
 }
 
@@ -591,7 +586,7 @@ int mt_attn_tc_fwd_run(int B, int T, int d, int h, const void* qkv, const float*
   a.B = B; a.T = T; a.d = d; a.h = h; a.n_items = B * (h / 2);
   a.scale_log2 = LOG2E / sqrtf((float)HD);
   a.mask = mask; a.out = (bf16*)out; a.lse = lse; a.klen = klen; a.drop = drop;
-  static bool attr_full[16] = {}, attr_part[16] = {};
+  static MtPerDeviceOnce attr_full, attr_part;
   const int slots = 2 * num_sms();
   const int grid = a.n_items < slots ? a.n_items : slots;
   mt_prof_work(4.0 * B * (double)T * T * d, (double)B * T * d * 4.0 * 2.0);
@@ -624,7 +619,7 @@ int mt_attn_tc_bwd_run(int B, int T, int d, int h, const void* qkv, const float*
   BwdArgs a;
   a.B = B; a.T = T; a.d = d; a.h = h; a.n_items = B * (h / 2);
   a.aux = aux; a.dqkv = (bf16*)dqkv; a.dbias = dbias; a.drop = drop;
-  static bool attr_full[16] = {}, attr_part[16] = {};
+  static MtPerDeviceOnce attr_full, attr_part;
   const int sms = num_sms();
   const int grid = a.n_items < sms ? a.n_items : sms;
   mt_prof_work(10.0 * B * (double)T * T * d, (double)B * T * d * 8.0 * 2.0);

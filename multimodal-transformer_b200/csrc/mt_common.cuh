@@ -45,6 +45,19 @@ extern int g_mt_tune[8];
 #define MT_TUNE_LN_SHARE 2
 #define MT_TUNE_PDL 3          // [3] programmatic dependent launch of the tcgen05 GEMM (prologue overlaps the previous kernel's tail)
 
+// one-time-per-DEVICE guard for cudaFuncSetAttribute-style opt-ins (a process may drive several GPUs): true the first time the
+// current device asks
+struct MtPerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
 static inline size_t mt_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---- typed loads / stores ----------------------------------------------------------------------------

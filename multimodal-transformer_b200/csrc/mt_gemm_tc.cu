@@ -559,14 +559,10 @@ int make_map(CUtensorMap* map, const void* ptr, int rows, int K, int ld, bool km
 }
 
 int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
+  int dev = 0, n = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n > 0 ? n : 148;
 }
 
 unsigned long long* g_trace = nullptr;
@@ -574,11 +570,8 @@ int g_tc_mode = 2;       // 0 = 256-wide tiles where they apply, 1 = one CTA per
 
 template <int BN, uint32_t F, bool RES, int OCC = 1>
 int launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& g, int grid, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    MT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, F, RES, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN, OCC>::TOTAL));
-    attr_set = true;
-  }
+  static MtPerDeviceOnce once;
+  if (once.first()) MT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, F, RES, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN, OCC>::TOTAL));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Smem<BN, OCC>::THREADS); cfg.dynamicSmemBytes = Smem<BN, OCC>::TOTAL; cfg.stream = st;
   cudaLaunchAttribute at[1];
