@@ -317,6 +317,16 @@ int mt_allreduce_grads(void* comm, float* const* bufs, const size_t* counts, int
  * a_kmajor: A element (m,k) at A[m*lda+k] (else A[k*lda+m]); b_kmajor: B element (n,k) at B[n*ldb+k] (else B[k*ldb+n]). */
 int mt_gemm(int dtype, int M, int N, int K, const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor,
             void* C, int ldc, int c_f32, const float* bias, int act, int split_k_atomic, void* stream);
+/* Row-stream GEMM engine of the encoder projections (csrc/mt_gemm_rs.cu; exposed for tests and profiling): weight-resident, grouped
+ * over G modality stacks (nn.Linear call sites MFT/multiTransformer.py:19-20,47-65 and their input gradients).
+ *   C[g*Mg + m, n] = epi( sum_k A[g*Mg + m, k] B_g(n, k) ),  A bf16 [G*Mg, K];  B = G weight matrices back to back, each [N,K] (b_kmajor)
+ * or [K,N];  C bf16 or fp32 [G*Mg, N];  bias / colsum / ln_a / ln_b: G x N fp32 back to back or NULL;  drop_p > 0: output dropout with
+ * site `site + 512 g` on the group-local element index;  gate bf16 [G*Mg, N]: out = gate > 0 ? out * gate_scale : 0;  residual fp32
+ * [G*Mg, N];  colsum is ACCUMULATED;  ln_out (bf16 [G*Mg, N], needs N == 256 and c_f32): LayerNorm(C) with unbiased std, eps 1e-6 on std.
+ * MT_ERR_UNSUPPORTED outside the encoder's (N, K, feature) combinations. */
+int mt_gemm_rs(int G, int Mg, int N, int K, const void* A, const void* B, int b_kmajor, void* C, int c_f32, const float* bias, int act,
+               float drop_p, uint64_t seed, uint32_t site, const void* gate, float gate_scale, const float* residual, float* colsum,
+               void* ln_out, const float* ln_a, const float* ln_b, void* stream);
 /* which engine a (dtype, shape) GEMM would use: 0 = FFMA SIMT, 1 = tcgen05 */
 int mt_gemm_engine(int dtype, int M, int N, int K, int a_kmajor, int b_kmajor);
 /* test hook: route every GEMM through the FFMA engine (A/B the tensor-core engine); returns the previous setting. */

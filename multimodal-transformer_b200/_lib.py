@@ -104,6 +104,7 @@ _PROTOS = {
     'mt_set_seed_offset_ptr': (c_int, [P]),
     'mt_spin': (c_int, [c_float, P]),
     'mt_gemm': (c_int, [c_int, c_int, c_int, c_int, P, c_int, c_int, P, c_int, c_int, P, c_int, c_int, P, c_int, c_int, P]),
+    'mt_gemm_rs': (c_int, [c_int, c_int, c_int, c_int, P, P, c_int, P, c_int, P, c_int, c_float, c_uint64, c_uint32, P, c_float, P, P, P, P, P, P]),
     'mt_gemm_engine': (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
     'mt_gemm_force_simt': (c_int, [c_int]),
     'mt_mfn_force_ffma': (c_int, [c_int]),
