@@ -159,6 +159,19 @@ int mt_encoder_fwd(const MtEncoderCfg* cfg, const float* params, const void* par
 int mt_encoder_bwd(const MtEncoderCfg* cfg, const float* params, const void* params_lp, const float* x,
                    const float* mask, const void* dy, float* dx, float* grads, void* ws, size_t ws_bytes,
                    void* stream);
+/* Grouped form: n_stacks (<= 4) modality stacks of IDENTICAL shape in one call (the three per-modality encoders of MultiTransformer,
+ * MFT/multiTransformer.py:278-299, which the reference runs one after the other).  x / y / dy / dx are [n_stacks, B, T, d] (stack g at
+ * rows g*B*T), the parameter block of stack g starts at params + g*param_stride floats (params_lp + g*param_stride bf16 elements; gradients
+ * likewise), param_stride % 8 == 0.  seeds[g] / stack_ids[g] select stack g's dropout streams exactly as cfg->seed / cfg->stack_id do for
+ * a single stack (NULL: cfg->seed for all, cfg->stack_id + g), so the result equals n_stacks single-stack calls bit for bit in fp32 mode and
+ * up to the GEMM engine's summation order in bf16 mode.  One launch per projection / LayerNorm / weight gradient serves all stacks. */
+size_t mt_encoder_group_ws_bytes(const MtEncoderCfg* cfg, int n_stacks);
+int mt_encoder_group_fwd(const MtEncoderCfg* cfg, int n_stacks, const uint64_t* seeds, const int* stack_ids, const float* params,
+                         const void* params_lp, size_t param_stride, const float* x, const float* mask, void* y, void* ws, size_t ws_bytes,
+                         void* stream);
+int mt_encoder_group_bwd(const MtEncoderCfg* cfg, int n_stacks, const uint64_t* seeds, const int* stack_ids, const float* params,
+                         const void* params_lp, size_t param_stride, const float* x, const float* mask, const void* dy, float* dx, float* grads,
+                         void* ws, size_t ws_bytes, void* stream);
 int mt_encoder_stack_fwd(const MtEncoderCfg* cfg, const float* params, const void* params_lp, const float* x,
                          const float* mask, void* y, void* ws, size_t ws_bytes, void* stream);
 int mt_encoder_stack_bwd(const MtEncoderCfg* cfg, const float* params, const void* params_lp, const float* x,
@@ -327,6 +340,9 @@ int mt_gemm(int dtype, int M, int N, int K, const void* A, int lda, int a_kmajor
 int mt_gemm_rs(int G, int Mg, int N, int K, const void* A, const void* B, int b_kmajor, void* C, int c_f32, const float* bias, int act,
                float drop_p, uint64_t seed, uint32_t site, const void* gate, float gate_scale, const float* residual, float* colsum,
                void* ln_out, const float* ln_a, const float* ln_b, void* stream);
+/* debug hook of the row-stream engine: CTA 0 writes clock64 stamps (16 x uint64 per tile, first 32 tiles: TMA issue of k-blocks 0-3, their
+ * arrival as seen by the MMA thread, accumulator free, epilogue start / end of the two warp groups) into dev_buf (>= 4 KB); NULL = off. */
+int mt_gemm_rs_trace(void* dev_buf);
 /* which engine a (dtype, shape) GEMM would use: 0 = FFMA SIMT, 1 = tcgen05 */
 int mt_gemm_engine(int dtype, int M, int N, int K, int a_kmajor, int b_kmajor);
 /* test hook: route every GEMM through the FFMA engine (A/B the tensor-core engine); returns the previous setting. */
@@ -337,7 +353,9 @@ int mt_gemm_tc_mode(int mode);
 /* tuning knobs; returns the previous value (-1: bad key).  key 0 / 1 / 2 = grid share of the tcgen05 GEMM / the T <= 128 attention /
  * the LayerNorm kernels: a share s > 1 launches 1/s of the resident CTA slots, so kernels of concurrent streams (the modality stacks
  * of MultiTransformer) co-reside on the SMs instead of queueing behind each other.  key 3 = programmatic dependent launch of the tcgen05
- * GEMM (its prologue may overlap the tail of the previous kernel of the stream; default 0: measured gain 0.4 % inside the captured step). */
+ * GEMM (its prologue may overlap the tail of the previous kernel of the stream; default 0: measured gain 0.4 % inside the captured step).
+ * key 5 != 0: the encoder's projections skip the weight-resident row-stream engine (A/B against the streaming engine); key 6 != 0: no
+ * LayerNorm fused into the FFN output projection's epilogue. */
 int mt_tune(int key, int value);
 /* debug hook: CTA 0 of every tcgen05 GEMM writes per-tile clock64 stamps (8 x uint64 per tile, first 64 tiles: TMA issue, MMA
  * tile start, first operands landed, last k-block landed, epilogue sees the accumulator, accumulator released, last pass

@@ -71,6 +71,9 @@ _PROTOS = {
     'mt_encoder_ws_bytes': (c_size_t, [POINTER(MtEncoderCfg)]),
     'mt_encoder_fwd': (c_int, [POINTER(MtEncoderCfg), P, P, P, P, P, P, c_size_t, P]),
     'mt_encoder_bwd': (c_int, [POINTER(MtEncoderCfg), P, P, P, P, P, P, P, P, c_size_t, P]),
+    'mt_encoder_group_ws_bytes': (c_size_t, [POINTER(MtEncoderCfg), c_int]),
+    'mt_encoder_group_fwd': (c_int, [POINTER(MtEncoderCfg), c_int, POINTER(c_uint64), POINTER(c_int), P, P, c_size_t, P, P, P, P, c_size_t, P]),
+    'mt_encoder_group_bwd': (c_int, [POINTER(MtEncoderCfg), c_int, POINTER(c_uint64), POINTER(c_int), P, P, c_size_t, P, P, P, P, P, P, c_size_t, P]),
     'mt_encoder_stack_fwd': (c_int, [POINTER(MtEncoderCfg), P, P, P, P, P, P, c_size_t, P]),
     'mt_encoder_stack_bwd': (c_int, [POINTER(MtEncoderCfg), P, P, P, P, P, P, P, P, c_size_t, P]),
     'mt_comm_available': (c_int, []),
@@ -105,6 +108,7 @@ _PROTOS = {
     'mt_spin': (c_int, [c_float, P]),
     'mt_gemm': (c_int, [c_int, c_int, c_int, c_int, P, c_int, c_int, P, c_int, c_int, P, c_int, c_int, P, c_int, c_int, P]),
     'mt_gemm_rs': (c_int, [c_int, c_int, c_int, c_int, P, P, c_int, P, c_int, P, c_int, c_float, c_uint64, c_uint32, P, c_float, P, P, P, P, P, P]),
+    'mt_gemm_rs_trace': (c_int, [P]),
     'mt_gemm_engine': (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
     'mt_gemm_force_simt': (c_int, [c_int]),
     'mt_mfn_force_ffma': (c_int, [c_int]),

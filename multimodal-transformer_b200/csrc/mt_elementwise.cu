@@ -13,9 +13,11 @@ constexpr int LN_WARPS = 8;
 // ------------------------------------------------------------------------------------------------------
 template <typename TY, int NCH>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(int M, const float* __restrict__ x, const float* __restrict__ a,
-                                                               const float* __restrict__ b, float eps, TY* __restrict__ y) {
+                                                               const float* __restrict__ b, float eps, TY* __restrict__ y, size_t pstride) {
   constexpr int d = NCH * 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // grouped launch (gridDim.y = modality stacks): group g owns rows [g*M, (g+1)*M) and the parameters at a + g*pstride
+  x += (size_t)blockIdx.y * M * d; y += (size_t)blockIdx.y * M * d; a += blockIdx.y * pstride; b += blockIdx.y * pstride;
   float4 av[NCH], bv[NCH];
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
@@ -75,10 +77,17 @@ template <typename TY, int NCH, bool NEXT>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(int M, const float* __restrict__ x, const float* __restrict__ a, float eps,
                                                                const TY* __restrict__ dy, const float* __restrict__ dres,
                                                                float* __restrict__ dx, float* __restrict__ da, float* __restrict__ db,
-                                                               TY* __restrict__ nx_out, float* __restrict__ nx_db, DropCfg nx_drop_in) {
+                                                               TY* __restrict__ nx_out, float* __restrict__ nx_db, DropGroups nx_drops,
+                                                               size_t pstride) {
   constexpr int d = NCH * 128;
   __shared__ float s_da[d], s_db[d], s_dn[NEXT ? d : 1];
-  const DropCfg nx_drop = mt_drop_resolve(nx_drop_in);
+  const DropCfg nx_drop = mt_drop_resolve(nx_drops.d[blockIdx.y]);
+  {   // grouped launch: see ln_fwd_kernel; gradients of parameters are laid out like the parameters
+    const size_t ro = (size_t)blockIdx.y * M * d, po = blockIdx.y * pstride;
+    x += ro; dy += ro; dx += ro; a += po; da += po; db += po;
+    if (dres) dres += ro;
+    if (NEXT) { nx_out += ro; nx_db += po; }
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < d; i += blockDim.x) { s_da[i] = 0.f; s_db[i] = 0.f; if (NEXT) s_dn[i] = 0.f; }
   __syncthreads();
@@ -328,17 +337,19 @@ inline int ew_grid(size_t n, int threads) {
 }
 
 template <typename TY>
-int ln_fwd_dispatch(int M, int d, const float* x, const float* a, const float* b, float eps, TY* y, cudaStream_t st) {
-  int grid = (M + LN_WARPS - 1) / LN_WARPS;
-  if (grid > 148 * 4 / (g_mt_tune[MT_TUNE_LN_SHARE] > 1 ? g_mt_tune[MT_TUNE_LN_SHARE] : 1)) grid = 148 * 4 / (g_mt_tune[MT_TUNE_LN_SHARE] > 1 ? g_mt_tune[MT_TUNE_LN_SHARE] : 1);
-  mt_prof_work(0.0, (double)M * d * (4.0 + sizeof(TY)));
+int ln_fwd_dispatch(int M, int d, const float* x, const float* a, const float* b, float eps, TY* y, cudaStream_t st, int G, size_t pstride) {
+  int gx = (M + LN_WARPS - 1) / LN_WARPS;
+  const int cap4 = 148 * 4 / (g_mt_tune[MT_TUNE_LN_SHARE] > 1 ? g_mt_tune[MT_TUNE_LN_SHARE] : 1) / G;
+  if (gx > cap4) gx = cap4 > 0 ? cap4 : 1;
+  const dim3 grid((unsigned)gx, (unsigned)G);
+  mt_prof_work(0.0, (double)G * M * d * (4.0 + sizeof(TY)));
   switch (d / 128) {
-    case 1: ln_fwd_kernel<TY, 1><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, b, eps, y); break;
-    case 2: ln_fwd_kernel<TY, 2><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, b, eps, y); break;
-    case 3: ln_fwd_kernel<TY, 3><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, b, eps, y); break;
-    case 4: ln_fwd_kernel<TY, 4><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, b, eps, y); break;
-    case 6: ln_fwd_kernel<TY, 6><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, b, eps, y); break;
-    case 8: ln_fwd_kernel<TY, 8><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, b, eps, y); break;
+    case 1: ln_fwd_kernel<TY, 1><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, b, eps, y, pstride); break;
+    case 2: ln_fwd_kernel<TY, 2><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, b, eps, y, pstride); break;
+    case 3: ln_fwd_kernel<TY, 3><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, b, eps, y, pstride); break;
+    case 4: ln_fwd_kernel<TY, 4><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, b, eps, y, pstride); break;
+    case 6: ln_fwd_kernel<TY, 6><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, b, eps, y, pstride); break;
+    case 8: ln_fwd_kernel<TY, 8><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, b, eps, y, pstride); break;
     default: return MT_ERR_UNSUPPORTED;
   }
   MT_LAUNCH_CHECK();
@@ -347,11 +358,13 @@ int ln_fwd_dispatch(int M, int d, const float* x, const float* a, const float* b
 
 template <typename TY, bool NEXT>
 int ln_bwd_dispatch(int M, int d, const float* x, const float* a, float eps, const TY* dy, const float* dres, float* dx, float* da,
-                    float* db, TY* nx_out, float* nx_db, DropCfg nx_drop, cudaStream_t st) {
-  int grid = (M + LN_WARPS - 1) / LN_WARPS;
-  if (grid > 148 * 2 / (g_mt_tune[MT_TUNE_LN_SHARE] > 1 ? g_mt_tune[MT_TUNE_LN_SHARE] : 1)) grid = 148 * 2 / (g_mt_tune[MT_TUNE_LN_SHARE] > 1 ? g_mt_tune[MT_TUNE_LN_SHARE] : 1);
-  mt_prof_work(0.0, (double)M * d * (8.0 + sizeof(TY) + (dres ? 4.0 : 0.0) + (NEXT ? sizeof(TY) : 0.0)));
-#define MT_LNB(NCH) ln_bwd_kernel<TY, NCH, NEXT><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, eps, dy, dres, dx, da, db, nx_out, nx_db, nx_drop)
+                    float* db, TY* nx_out, float* nx_db, const DropGroups& nx_drop, cudaStream_t st, int G, size_t pstride) {
+  int gx = (M + LN_WARPS - 1) / LN_WARPS;
+  const int cap2 = 148 * 2 / (g_mt_tune[MT_TUNE_LN_SHARE] > 1 ? g_mt_tune[MT_TUNE_LN_SHARE] : 1) / G;
+  if (gx > cap2) gx = cap2 > 0 ? cap2 : 1;
+  const dim3 grid((unsigned)gx, (unsigned)G);
+  mt_prof_work(0.0, (double)G * M * d * (8.0 + sizeof(TY) + (dres ? 4.0 : 0.0) + (NEXT ? sizeof(TY) : 0.0)));
+#define MT_LNB(NCH) ln_bwd_kernel<TY, NCH, NEXT><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, eps, dy, dres, dx, da, db, nx_out, nx_db, nx_drop, pstride)
   switch (d / 128) {
     case 1: MT_LNB(1); break;
     case 2: MT_LNB(2); break;
@@ -368,23 +381,26 @@ int ln_bwd_dispatch(int M, int d, const float* x, const float* a, float eps, con
 
 }  // namespace
 
-int mt_ln_fwd_run(int M, int d, const float* x, const float* a, const float* b, float eps, void* y, bool y_bf16, cudaStream_t st) {
-  if (M <= 0 || d <= 0 || d % 128 != 0 || d > 1024 || !x || !a || !b || !y) return MT_ERR_ARG;
-  if (y_bf16) return ln_fwd_dispatch<bf16>(M, d, x, a, b, eps, (bf16*)y, st);
-  return ln_fwd_dispatch<float>(M, d, x, a, b, eps, (float*)y, st);
+int mt_ln_fwd_run(int M, int d, const float* x, const float* a, const float* b, float eps, void* y, bool y_bf16, cudaStream_t st, int G,
+                  size_t pstride) {
+  if (M <= 0 || d <= 0 || d % 128 != 0 || d > 1024 || !x || !a || !b || !y || G < 1 || G > MT_LN_MAX_GROUPS) return MT_ERR_ARG;
+  if (y_bf16) return ln_fwd_dispatch<bf16>(M, d, x, a, b, eps, (bf16*)y, st, G, pstride);
+  return ln_fwd_dispatch<float>(M, d, x, a, b, eps, (float*)y, st, G, pstride);
 }
 
 int mt_ln_bwd_run(int M, int d, const float* x, const float* a, float eps, const void* dy, bool dy_bf16, const float* dres, float* dx,
-                  float* da, float* db, cudaStream_t st, const LnBwdNext* nx) {
-  if (M <= 0 || d <= 0 || d % 128 != 0 || d > 1024 || !x || !a || !dy || !dx || !da || !db) return MT_ERR_ARG;
-  const DropCfg nodrop = mt_make_drop(0.f, 0, 0);
+                  float* da, float* db, cudaStream_t st, const LnBwdNext* nx, int G, size_t pstride, const DropCfg* nx_drops) {
+  if (M <= 0 || d <= 0 || d % 128 != 0 || d > 1024 || !x || !a || !dy || !dx || !da || !db || G < 1 || G > MT_LN_MAX_GROUPS) return MT_ERR_ARG;
+  DropGroups dg;
+  for (int i = 0; i < MT_LN_MAX_GROUPS; ++i) dg.d[i] = mt_make_drop(0.f, 0, 0);
   if (nx && nx->out) {
     if (!nx->dbias || nx->out == dy) return MT_ERR_ARG;
-    if (dy_bf16) return ln_bwd_dispatch<bf16, true>(M, d, x, a, eps, (const bf16*)dy, dres, dx, da, db, (bf16*)nx->out, nx->dbias, nx->drop, st);
-    return ln_bwd_dispatch<float, true>(M, d, x, a, eps, (const float*)dy, dres, dx, da, db, (float*)nx->out, nx->dbias, nx->drop, st);
+    for (int i = 0; i < G; ++i) dg.d[i] = nx_drops ? nx_drops[i] : nx->drop;
+    if (dy_bf16) return ln_bwd_dispatch<bf16, true>(M, d, x, a, eps, (const bf16*)dy, dres, dx, da, db, (bf16*)nx->out, nx->dbias, dg, st, G, pstride);
+    return ln_bwd_dispatch<float, true>(M, d, x, a, eps, (const float*)dy, dres, dx, da, db, (float*)nx->out, nx->dbias, dg, st, G, pstride);
   }
-  if (dy_bf16) return ln_bwd_dispatch<bf16, false>(M, d, x, a, eps, (const bf16*)dy, dres, dx, da, db, nullptr, nullptr, nodrop, st);
-  return ln_bwd_dispatch<float, false>(M, d, x, a, eps, (const float*)dy, dres, dx, da, db, nullptr, nullptr, nodrop, st);
+  if (dy_bf16) return ln_bwd_dispatch<bf16, false>(M, d, x, a, eps, (const bf16*)dy, dres, dx, da, db, nullptr, nullptr, dg, st, G, pstride);
+  return ln_bwd_dispatch<float, false>(M, d, x, a, eps, (const float*)dy, dres, dx, da, db, nullptr, nullptr, dg, st, G, pstride);
 }
 
 int mt_drop_grad_run(int M, int N, const float* g, void* out, bool out_bf16, DropCfg drop, cudaStream_t st) {

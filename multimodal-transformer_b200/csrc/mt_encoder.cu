@@ -2,6 +2,7 @@
 // Linear (embed / fusion layers), forward and backward, as sequences of GEMMs with fused epilogues, fused
 // attention and row-wise LayerNorm kernels.  The residual stream stays fp32; GEMM operands are `dtype`.
 #include "mt_ops.cuh"
+#include "mt_gemm_rs.cuh"
 
 namespace {
 
@@ -57,9 +58,18 @@ struct EncWs {
   size_t bytes;
 };
 
-int carve(const MtEncoderCfg& c, void* ws, EncWs& w) {
+// A call serves G modality stacks of identical shape (G = 1: the plain single-stack entry points).  Every activation buffer holds the
+// stacks back to back ([G*M, .], stack g at rows g*M), the parameter / gradient blocks of consecutive stacks are `pstride` floats apart.
+struct Groups {
+  int G = 1;
+  size_t pstride = 0;
+  uint64_t seed[MT_RS_MAX_GROUPS] = {};
+  int stack_id[MT_RS_MAX_GROUPS] = {};
+};
+
+int carve(const MtEncoderCfg& c, int G, void* ws, EncWs& w) {
   if (c.n_layers < 1 || c.n_layers > 64) return MT_ERR_ARG;
-  const size_t M = (size_t)c.B * c.T, d = c.d, es = mt_esize(c.dtype);
+  const size_t M = (size_t)G * c.B * c.T, d = c.d, es = mt_esize(c.dtype);
   WsCarver k(ws);
   const int sets = c.training ? c.n_layers : 1;
   for (int s = 0; s < sets; ++s) {
@@ -67,7 +77,7 @@ int carve(const MtEncoderCfg& c, void* ws, EncWs& w) {
     b.x_out = k.take<float>(M * d);
     b.u = k.take_bytes(M * d * es);
     b.qkv = k.take_bytes(M * 3 * d * es);
-    b.lse = k.take<float>((size_t)c.B * c.h * c.T);
+    b.lse = k.take<float>((size_t)G * c.B * c.h * c.T);
     b.att = k.take_bytes(M * d * es);
     b.xp = k.take<float>(M * d);
     b.v = k.take_bytes(M * d * es);
@@ -85,7 +95,7 @@ int carve(const MtEncoderCfg& c, void* ws, EncWs& w) {
     w.dact2 = k.take_bytes(M * d * es);
     w.dhid = k.take_bytes(M * c.dff * es);
     w.dqkv = k.take_bytes(M * 3 * d * es);
-    w.Dws = k.take<float>(mt_attn_bwd_ws_floats(c.B, c.T, c.h));
+    w.Dws = k.take<float>((size_t)G * mt_attn_bwd_ws_floats(c.B, c.T, c.h));
   }
   w.bytes = k.total();
   return MT_OK;
@@ -132,18 +142,243 @@ GemmDesc dgrad_gemm(int M, int Nout, int Kin, const void* dy, const void* W, voi
   return g;
 }
 // dW[Nout,Kin] = dy^T x : contraction over the M tokens, both operands mn-major, split-K with fp32 atomics
-GemmDesc wgrad_gemm(int M, int Nout, int Kin, const void* dy, int ldy, const void* x, int ldx, float* dW, int ldw) {
+GemmDesc wgrad_gemm(int M, int Nout, int Kin, const void* dy, int ldy, const void* x, int ldx, float* dW, int ldw, int groups = 1) {
   GemmDesc g;
   g.M = Nout; g.N = Kin; g.K = M;
   g.A = dy; g.lda = ldy; g.a_kmajor = false;
   g.B = x; g.ldb = ldx; g.b_kmajor = false;
   g.C = dW; g.ldc = ldw; g.c_f32 = true;
-  size_t tiles = (size_t)((Nout + 63) / 64) * ((Kin + 63) / 64);
+  size_t tiles = (size_t)((Nout + 63) / 64) * ((Kin + 63) / 64) * groups;
   int split = (int)((148 * 4 + tiles - 1) / tiles);
   int max_split = (M + 255) / 256;
   if (split > max_split) split = max_split;
   g.split_k = split < 2 ? 2 : split;          // always the atomic epilogue: dW is zero-initialised by the caller
   return g;
+}
+
+// One projection of the stack(s):  C[g] = epi(A[g] . W_g) for every group -- through the weight-resident row-stream engine
+// (mt_gemm_rs.cu, ONE launch for all groups) when the shape is one of its instantiations, else one streaming GEMM per group.
+struct Proj {
+  const MtEncoderCfg& c;
+  const Groups& gr;
+  const float* params; const void* params_lp;
+  float* grads;
+  cudaStream_t st;
+  int M;                                      // rows per group
+
+  // w_off / b_off: offsets inside a group's parameter block.  fwd: W [N,K]; dgrad: W [K(out),N(in)] read transposed.
+  // drop_k >= 0: output dropout site k of `layer`; colsum_off: bias-gradient block (grads) receiving the column sums;
+  // ln_* (fwd only): fused LayerNorm of the fp32 output with the gains at ln_a_off / ln_b_off -> ln_out (bf16)
+  int run(bool dgrad, int N, int K, const void* A, size_t w_off, void* C, bool c_f32, long long b_off, int act, int layer, int drop_k,
+          const void* gate, float gate_scale, const float* residual, long long colsum_off, void* ln_out = nullptr, size_t ln_a_off = 0,
+          size_t ln_b_off = 0) const {
+    const bool lp = c.dtype == MT_BF16;
+    const float p = drop_k >= 0 ? c.p_drop : 0.f;
+    if (lp) {
+      RsDesc r;
+      r.G = gr.G; r.Mg = M; r.N = N; r.K = K;
+      r.A = A; r.lda = K;
+      r.ldb = dgrad ? N : K; r.b_kmajor = !dgrad;
+      r.C = C; r.ldc = N; r.c_f32 = c_f32;
+      r.act = act;
+      r.gate = gate; r.ldg = N; r.gate_scale = gate_scale;
+      r.residual = residual; r.ldr = N;
+      r.ln_out = ln_out; r.ld_ln = N; r.ln_eps = 1e-6f;
+      for (int g = 0; g < gr.G; ++g) {
+        r.B[g] = (const bf16*)params_lp + g * gr.pstride + w_off;
+        r.bias[g] = b_off >= 0 ? params + g * gr.pstride + b_off : nullptr;
+        r.drop[g] = mt_make_drop(p, gr.seed[g], mt_enc_site(gr.stack_id[g], layer, drop_k < 0 ? 0 : drop_k));
+        r.colsum[g] = colsum_off >= 0 ? grads + g * gr.pstride + colsum_off : nullptr;
+        r.ln_a[g] = params + g * gr.pstride + ln_a_off;
+        r.ln_b[g] = params + g * gr.pstride + ln_b_off;
+      }
+      if (!g_mt_tune[MT_TUNE_NO_RS] && mt_gemm_rs_supported(r)) return mt_gemm_rs_run(r, st);
+    }
+    const size_t es = mt_esize(c.dtype);
+    for (int g = 0; g < gr.G; ++g) {
+      const size_t ro = (size_t)g * M;
+      const void* Ag = (const char*)A + ro * K * es;
+      void* Cg = (char*)C + ro * N * (c_f32 ? 4 : es);
+      const void* W = wptr(c, params + g * gr.pstride, lp ? (const void*)((const bf16*)params_lp + g * gr.pstride) : nullptr, w_off);
+      GemmDesc d = dgrad ? dgrad_gemm(M, K, N, Ag, W, Cg, c_f32 || !lp) : fwd_gemm(M, N, K, Ag, W, Cg, c_f32 || !lp);
+      if (b_off >= 0) d.epi.bias = params + g * gr.pstride + b_off;
+      d.epi.act = act;
+      d.epi.drop = mt_make_drop(p, gr.seed[g], mt_enc_site(gr.stack_id[g], layer, drop_k < 0 ? 0 : drop_k));
+      if (gate) { d.epi.gate = (const char*)gate + ro * N * es; d.epi.ldg = N; d.epi.gate_scale = gate_scale; }
+      if (residual) { d.epi.residual = residual + ro * N; d.epi.ldr = N; }
+      if (colsum_off >= 0) d.epi.colsum = grads + g * gr.pstride + colsum_off;
+      MT_TRY(mt_gemm_run(c.dtype, d, st));
+    }
+    if (ln_out)
+      MT_TRY(mt_ln_fwd_run(M, N, (const float*)C, params + ln_a_off, params + ln_b_off, 1e-6f, ln_out, lp, st, gr.G, gr.pstride));
+    return MT_OK;
+  }
+
+  // dW[g] = dy[g]^T x[g] for every group, one launch on the tcgen05 engine when the grouped split-K form applies
+  int wgrad(int Nout, int Kin, const void* dy, const void* x, size_t w_off) const {
+    const size_t es = mt_esize(c.dtype);
+    if (gr.G > 1 && c.dtype == MT_BF16 && M % 64 == 0) {
+      GemmDesc d = wgrad_gemm(M, Nout, Kin, dy, Nout, x, Kin, grads + w_off, Kin, gr.G);
+      d.groups = gr.G; d.c_gstride = (long long)gr.pstride;
+      const int rc = mt_gemm_run(c.dtype, d, st);
+      if (rc != MT_ERR_UNSUPPORTED) return rc;
+    }
+    for (int g = 0; g < gr.G; ++g) {
+      const size_t ro = (size_t)g * M;
+      MT_TRY(mt_gemm_run(c.dtype, wgrad_gemm(M, Nout, Kin, (const char*)dy + ro * Nout * es, Nout, (const char*)x + ro * Kin * es, Kin,
+                                              grads + g * gr.pstride + w_off, Kin), st));
+    }
+    return MT_OK;
+  }
+};
+
+int encoder_fwd_impl(const MtEncoderCfg& c, const Groups& gr, const float* params, const void* params_lp, const float* x, const float* mask,
+                     void* y, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!params || !x || !y || !ws || (c.dtype == MT_BF16 && !params_lp)) return MT_ERR_ARG;
+  if (c.key_len && (c.training || c.p_drop > 0.f)) return MT_ERR_UNSUPPORTED;      // ragged batches: inference only
+  EncWs w;
+  MT_TRY(carve(c, gr.G, ws, w));
+  if (ws_bytes < w.bytes) return MT_ERR_WS;
+  const int M = c.B * c.T, d = c.d, dff = c.dff, G = gr.G;
+  const bool lp = c.dtype == MT_BF16;
+  const size_t es = mt_esize(c.dtype);
+  const EncParams P = enc_params(d, dff, c.n_layers);
+  const float* xin = x;
+  GridShareScope share(c.grid_share);
+  const Proj pj{c, gr, params, params_lp, nullptr, st, M};
+  // the LayerNorm that follows a layer (the next layer's first norm, or the final norm) rides in the epilogue of that layer's last
+  // GEMM whenever its output has the operand dtype and the row-stream engine takes the shape
+  const bool y_lp = lp && !c.y_f32;
+  bool u_ready = false;
+  for (int l = 0; l < c.n_layers; ++l) {
+    const size_t base = P.layer_stride * l;
+    LayerBufs& b = w.L[l];
+    const bool last = l == c.n_layers - 1;
+    // sublayer 0: x + dropout(self_attn(LN(x)))
+    if (!u_ready) MT_TRY(mt_ln_fwd_run(M, d, xin, params + base + P.ln1_a, params + base + P.ln1_b, 1e-6f, b.u, lp, st, G, gr.pstride));
+    MT_TRY(pj.run(false, 3 * d, d, b.u, base + P.w_qkv, b.qkv, !lp, (long long)(base + P.b_qkv), MT_ACT_NONE, l, -1, nullptr, 1.f, nullptr, -1));
+    for (int g = 0; g < G; ++g) {
+      const size_t ro = (size_t)g * M;
+      MT_TRY(mt_attn_fwd_run(c.dtype, c.B, c.T, d, c.h, (const char*)b.qkv + ro * 3 * d * es, mask, (char*)b.att + ro * d * es,
+                             b.lse + (size_t)g * c.B * c.h * c.T,
+                             mt_make_drop(c.p_drop, gr.seed[g], mt_enc_site(gr.stack_id[g], l, MT_SITE_ATTN_P)), st, c.key_len));
+    }
+    MT_TRY(pj.run(false, d, d, b.att, base + P.w_o, b.xp, true, (long long)(base + P.b_o), MT_ACT_NONE, l, MT_SITE_SUB0, nullptr, 1.f, xin, -1));
+    // sublayer 1: x + dropout(w_2(dropout(relu(w_1(LN(x))))))
+    MT_TRY(mt_ln_fwd_run(M, d, b.xp, params + base + P.ln2_a, params + base + P.ln2_b, 1e-6f, b.v, lp, st, G, gr.pstride));
+    MT_TRY(pj.run(false, dff, d, b.v, base + P.w_1, b.hid, !lp, (long long)(base + P.b_1), MT_ACT_RELU, l, MT_SITE_FFN_H, nullptr, 1.f, nullptr, -1));
+    void* ln_out = nullptr;
+    size_t la = 0, lb = 0;
+    if (lp && !g_mt_tune[MT_TUNE_NO_LNFUSE] && (!last || y_lp)) {
+      ln_out = last ? y : w.L[l + 1].u;
+      la = last ? P.lnf_a : base + P.layer_stride + P.ln1_a;
+      lb = last ? P.lnf_b : base + P.layer_stride + P.ln1_b;
+    }
+    MT_TRY(pj.run(false, d, dff, b.hid, base + P.w_2, b.x_out, true, (long long)(base + P.b_2), MT_ACT_NONE, l, MT_SITE_SUB1, nullptr, 1.f, b.xp, -1,
+                  ln_out, la, lb));
+    u_ready = ln_out != nullptr;
+    xin = b.x_out;
+  }
+  if (u_ready) return MT_OK;      // the final norm left with the last FFN GEMM
+  return mt_ln_fwd_run(M, d, xin, params + P.lnf_a, params + P.lnf_b, 1e-6f, y, y_lp, st, G, gr.pstride);
+}
+
+int encoder_bwd_impl(const MtEncoderCfg& c, const Groups& gr, const float* params, const void* params_lp, const float* x, const float* mask,
+                     const void* dy, float* dx, float* grads, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!c.training) return MT_ERR_ARG;
+  if (!params || !x || !dy || !dx || !grads || !ws || (c.dtype == MT_BF16 && !params_lp)) return MT_ERR_ARG;
+  EncWs w;
+  MT_TRY(carve(c, gr.G, ws, w));
+  if (ws_bytes < w.bytes) return MT_ERR_WS;
+  const int M = c.B * c.T, d = c.d, dff = c.dff, G = gr.G;
+  const bool lp = c.dtype == MT_BF16;
+  const size_t es = mt_esize(c.dtype);
+  const EncParams P = enc_params(d, dff, c.n_layers);
+  const float p = c.p_drop;
+  const float keep_scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+  GridShareScope share(c.grid_share);
+  const Proj pj{c, gr, params, params_lp, grads, st, M};
+  for (int g = 0; g < G; ++g) MT_CUDA(cudaMemsetAsync(grads + g * gr.pstride, 0, sizeof(float) * P.total, st));
+
+  float* g_cur = w.g0;
+  float* g_nxt = w.g1;
+  const float* x_last = w.L[c.n_layers - 1].x_out;
+  DropCfg drops[MT_RS_MAX_GROUPS];
+  auto site_drops = [&](int layer, int k) {
+    for (int g = 0; g < G; ++g) drops[g] = mt_make_drop(p, gr.seed[g], mt_enc_site(gr.stack_id[g], layer, k));
+    return drops[0];
+  };
+  // every LayerNorm backward also emits the dropped operand-dtype gradient the sublayer below starts from, and that
+  // sublayer's output-bias gradient (LnBwdNext), so no separate dropout-gradient / column-sum passes run over [M,d]
+  {
+    const size_t bl = P.layer_stride * (c.n_layers - 1);
+    const DropCfg dr = site_drops(c.n_layers - 1, MT_SITE_SUB1);
+    LnBwdNext nx{w.dact, grads + bl + P.b_2, dr};
+    const bool dy_lp = lp && !c.y_f32;
+    if (dy_lp == lp) {
+      MT_TRY(mt_ln_bwd_run(M, d, x_last, params + P.lnf_a, 1e-6f, dy, dy_lp, nullptr, g_cur, grads + P.lnf_a, grads + P.lnf_b, st, &nx, G,
+                           gr.pstride, drops));
+    } else {      // fp32 dy in bf16 mode: the fused second output has dy's dtype, so take the two-pass route once
+      MT_TRY(mt_ln_bwd_run(M, d, x_last, params + P.lnf_a, 1e-6f, dy, dy_lp, nullptr, g_cur, grads + P.lnf_a, grads + P.lnf_b, st, nullptr, G,
+                           gr.pstride));
+      for (int g = 0; g < G; ++g) {
+        const size_t ro = (size_t)g * M * d;
+        MT_TRY(mt_drop_grad_run(M, d, g_cur + ro, (char*)w.dact + ro * es, lp, drops[g], st));
+        MT_TRY(mt_colsum_run(lp, M, d, (char*)w.dact + ro * es, d, grads + g * gr.pstride + bl + P.b_2, 1, st));
+      }
+    }
+  }
+
+  for (int l = c.n_layers - 1; l >= 0; --l) {
+    const size_t base = P.layer_stride * l;
+    LayerBufs& b = w.L[l];
+    const float* x_l = l == 0 ? x : w.L[l - 1].x_out;
+    // ---- FFN sublayer: x_out = xp + drop(w_2 hid + b_2); w.dact = drop' . g_cur and db_2 are already there ----------
+    MT_TRY(pj.wgrad(d, dff, w.dact, b.hid, base + P.w_2));
+    // relu' and the hidden dropout mask in one test (gate), db_1 = colsum(dhid) from the epilogue
+    MT_TRY(pj.run(true, dff, d, w.dact, base + P.w_2, w.dhid, !lp, -1, MT_ACT_NONE, l, -1, b.hid, keep_scale, nullptr, (long long)(base + P.b_1)));
+    MT_TRY(pj.wgrad(dff, d, w.dhid, b.v, base + P.w_1));
+    MT_TRY(pj.run(true, d, dff, w.dhid, base + P.w_1, w.dact2, !lp, -1, MT_ACT_NONE, l, -1, nullptr, 1.f, nullptr, -1));
+    {
+      LnBwdNext nx{w.dact, grads + base + P.b_o, site_drops(l, MT_SITE_SUB0)};
+      MT_TRY(mt_ln_bwd_run(M, d, b.xp, params + base + P.ln2_a, 1e-6f, w.dact2, lp, g_cur, g_nxt, grads + base + P.ln2_a, grads + base + P.ln2_b, st,
+                           &nx, G, gr.pstride, drops));
+    }
+    // ---- attention sublayer: xp = x + drop(att w_o + b_o); w.dact = drop' . g_nxt and db_o are already there ---------
+    MT_TRY(pj.wgrad(d, d, w.dact, b.att, base + P.w_o));
+    MT_TRY(pj.run(true, d, d, w.dact, base + P.w_o, w.dact2, !lp, -1, MT_ACT_NONE, l, -1, nullptr, 1.f, nullptr, -1));
+    for (int g = 0; g < G; ++g) {
+      const size_t ro = (size_t)g * M;
+      MT_TRY(mt_attn_bwd_run(c.dtype, c.B, c.T, d, c.h, (const char*)b.qkv + ro * 3 * d * es, mask, (const char*)b.att + ro * d * es,
+                             b.lse + (size_t)g * c.B * c.h * c.T, (const char*)w.dact2 + ro * d * es, (char*)w.dqkv + ro * 3 * d * es,
+                             mt_make_drop(p, gr.seed[g], mt_enc_site(gr.stack_id[g], l, MT_SITE_ATTN_P)),
+                             w.Dws + (size_t)g * mt_attn_bwd_ws_floats(c.B, c.T, c.h), st, grads + g * gr.pstride + base + P.b_qkv));
+    }
+    MT_TRY(pj.wgrad(3 * d, d, w.dqkv, b.u, base + P.w_qkv));
+    MT_TRY(pj.run(true, d, 3 * d, w.dqkv, base + P.w_qkv, w.dact2, !lp, -1, MT_ACT_NONE, l, -1, nullptr, 1.f, nullptr, -1));
+    float* out = l == 0 ? dx : g_cur;
+    LnBwdNext nx{nullptr, nullptr, mt_make_drop(0.f, 0, 0)};
+    if (l > 0) nx = LnBwdNext{w.dact, grads + base - P.layer_stride + P.b_2, site_drops(l - 1, MT_SITE_SUB1)};
+    MT_TRY(mt_ln_bwd_run(M, d, x_l, params + base + P.ln1_a, 1e-6f, w.dact2, lp, g_nxt, out, grads + base + P.ln1_a, grads + base + P.ln1_b, st, &nx,
+                         G, gr.pstride, drops));
+    // g_cur now holds dL/dx_l (g_nxt is free again)
+  }
+  return MT_OK;
+}
+
+Groups single_group(const MtEncoderCfg& c) {
+  Groups g;
+  g.G = 1; g.pstride = 0; g.seed[0] = c.seed; g.stack_id[0] = c.stack_id;
+  return g;
+}
+
+int make_groups(const MtEncoderCfg& c, int G, const uint64_t* seeds, const int* stack_ids, size_t pstride, Groups& g) {
+  if (G < 1 || G > MT_RS_MAX_GROUPS) return MT_ERR_ARG;
+  if (G > 1 && pstride < enc_params(c.d, c.dff, c.n_layers).total) return MT_ERR_ARG;
+  if (G > 1 && pstride % 8 != 0) return MT_ERR_ALIGN;      // bf16 weight blocks of every group stay 16-byte aligned (TMA)
+  g.G = G; g.pstride = G > 1 ? pstride : 0;
+  for (int i = 0; i < G; ++i) { g.seed[i] = seeds ? seeds[i] : c.seed; g.stack_id[i] = stack_ids ? stack_ids[i] : c.stack_id + i; }
+  return MT_OK;
 }
 
 }  // namespace
@@ -160,128 +395,48 @@ size_t mt_encoder_param_count(int d, int dff, int n_layers) { return enc_params(
 size_t mt_encoder_ws_bytes(const MtEncoderCfg* cfg) {
   if (check_cfg(cfg) != MT_OK) return 0;
   EncWs w;
-  if (carve(*cfg, nullptr, w) != MT_OK) return 0;
+  if (carve(*cfg, 1, nullptr, w) != MT_OK) return 0;
+  return w.bytes;
+}
+
+size_t mt_encoder_group_ws_bytes(const MtEncoderCfg* cfg, int n_stacks) {
+  if (check_cfg(cfg) != MT_OK || n_stacks < 1 || n_stacks > MT_RS_MAX_GROUPS) return 0;
+  if ((size_t)n_stacks * cfg->B * cfg->T > 0x7fffffffull / (3 * (size_t)cfg->d)) return 0;
+  EncWs w;
+  if (carve(*cfg, n_stacks, nullptr, w) != MT_OK) return 0;
   return w.bytes;
 }
 
 int mt_encoder_fwd(const MtEncoderCfg* cfg, const float* params, const void* params_lp, const float* x, const float* mask, void* y,
                    void* ws, size_t ws_bytes, void* stream) {
   MT_TRY(check_cfg(cfg));
-  const MtEncoderCfg& c = *cfg;
-  if (!params || !x || !y || !ws || (c.dtype == MT_BF16 && !params_lp)) return MT_ERR_ARG;
-  if (c.key_len && (c.training || c.p_drop > 0.f)) return MT_ERR_UNSUPPORTED;      // ragged batches: inference only
-  EncWs w;
-  MT_TRY(carve(c, ws, w));
-  if (ws_bytes < w.bytes) return MT_ERR_WS;
-  cudaStream_t st = (cudaStream_t)stream;
-  const int M = c.B * c.T, d = c.d, dff = c.dff;
-  const bool lp = c.dtype == MT_BF16;
-  const EncParams P = enc_params(d, dff, c.n_layers);
-  const float p = c.p_drop;
-  const float* xin = x;
-  GridShareScope share(c.grid_share);
-  for (int l = 0; l < c.n_layers; ++l) {
-    const size_t base = P.layer_stride * l;
-    const float* pf = params + base;
-    LayerBufs& b = w.L[l];
-    // sublayer 0: x + dropout(self_attn(LN(x)))
-    MT_TRY(mt_ln_fwd_run(M, d, xin, pf + P.ln1_a, pf + P.ln1_b, 1e-6f, b.u, lp, st));
-    GemmDesc g = fwd_gemm(M, 3 * d, d, b.u, wptr(c, params, params_lp, base + P.w_qkv), b.qkv, !lp);
-    g.epi.bias = pf + P.b_qkv;
-    MT_TRY(mt_gemm_run(c.dtype, g, st));
-    MT_TRY(mt_attn_fwd_run(c.dtype, c.B, c.T, d, c.h, b.qkv, mask, b.att, b.lse,
-                           mt_make_drop(p, c.seed, mt_enc_site(c.stack_id, l, MT_SITE_ATTN_P)), st, c.key_len));
-    g = fwd_gemm(M, d, d, b.att, wptr(c, params, params_lp, base + P.w_o), b.xp, true);
-    g.epi.bias = pf + P.b_o;
-    g.epi.drop = mt_make_drop(p, c.seed, mt_enc_site(c.stack_id, l, MT_SITE_SUB0));
-    g.epi.residual = xin; g.epi.ldr = d;
-    MT_TRY(mt_gemm_run(c.dtype, g, st));
-    // sublayer 1: x + dropout(w_2(dropout(relu(w_1(LN(x))))))
-    MT_TRY(mt_ln_fwd_run(M, d, b.xp, pf + P.ln2_a, pf + P.ln2_b, 1e-6f, b.v, lp, st));
-    g = fwd_gemm(M, dff, d, b.v, wptr(c, params, params_lp, base + P.w_1), b.hid, !lp);
-    g.epi.bias = pf + P.b_1;
-    g.epi.act = MT_ACT_RELU;
-    g.epi.drop = mt_make_drop(p, c.seed, mt_enc_site(c.stack_id, l, MT_SITE_FFN_H));
-    MT_TRY(mt_gemm_run(c.dtype, g, st));
-    g = fwd_gemm(M, d, dff, b.hid, wptr(c, params, params_lp, base + P.w_2), b.x_out, true);
-    g.epi.bias = pf + P.b_2;
-    g.epi.drop = mt_make_drop(p, c.seed, mt_enc_site(c.stack_id, l, MT_SITE_SUB1));
-    g.epi.residual = b.xp; g.epi.ldr = d;
-    MT_TRY(mt_gemm_run(c.dtype, g, st));
-    xin = b.x_out;
-  }
-  return mt_ln_fwd_run(M, d, xin, params + P.lnf_a, params + P.lnf_b, 1e-6f, y, lp && !c.y_f32, st);
+  return encoder_fwd_impl(*cfg, single_group(*cfg), params, params_lp, x, mask, y, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int mt_encoder_bwd(const MtEncoderCfg* cfg, const float* params, const void* params_lp, const float* x, const float* mask,
                    const void* dy, float* dx, float* grads, void* ws, size_t ws_bytes, void* stream) {
   MT_TRY(check_cfg(cfg));
-  const MtEncoderCfg& c = *cfg;
-  if (!c.training) return MT_ERR_ARG;
-  if (!params || !x || !dy || !dx || !grads || !ws || (c.dtype == MT_BF16 && !params_lp)) return MT_ERR_ARG;
-  EncWs w;
-  MT_TRY(carve(c, ws, w));
-  if (ws_bytes < w.bytes) return MT_ERR_WS;
-  cudaStream_t st = (cudaStream_t)stream;
-  const int M = c.B * c.T, d = c.d, dff = c.dff;
-  const bool lp = c.dtype == MT_BF16;
-  const EncParams P = enc_params(d, dff, c.n_layers);
-  const float p = c.p_drop;
-  const float keep_scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
-  GridShareScope share(c.grid_share);
-  MT_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * P.total, st));
+  return encoder_bwd_impl(*cfg, single_group(*cfg), params, params_lp, x, mask, dy, dx, grads, ws, ws_bytes, (cudaStream_t)stream);
+}
 
-  float* g_cur = w.g0;
-  float* g_nxt = w.g1;
-  const float* x_last = w.L[c.n_layers - 1].x_out;
-  // every LayerNorm backward also emits the dropped operand-dtype gradient the sublayer below starts from, and that
-  // sublayer's output-bias gradient (LnBwdNext), so no separate dropout-gradient / column-sum passes run over [M,d]
-  {
-    const size_t bl = P.layer_stride * (c.n_layers - 1);
-    const DropCfg dr = mt_make_drop(p, c.seed, mt_enc_site(c.stack_id, c.n_layers - 1, MT_SITE_SUB1));
-    LnBwdNext nx{w.dact, grads + bl + P.b_2, dr};
-    const bool dy_lp = lp && !c.y_f32;
-    if (dy_lp == lp) {
-      MT_TRY(mt_ln_bwd_run(M, d, x_last, params + P.lnf_a, 1e-6f, dy, dy_lp, nullptr, g_cur, grads + P.lnf_a, grads + P.lnf_b, st, &nx));
-    } else {      // fp32 dy in bf16 mode: the fused second output has dy's dtype, so take the two-pass route once
-      MT_TRY(mt_ln_bwd_run(M, d, x_last, params + P.lnf_a, 1e-6f, dy, dy_lp, nullptr, g_cur, grads + P.lnf_a, grads + P.lnf_b, st));
-      MT_TRY(mt_drop_grad_run(M, d, g_cur, w.dact, lp, dr, st));
-      MT_TRY(mt_colsum_run(lp, M, d, w.dact, d, grads + bl + P.b_2, 1, st));
-    }
-  }
+int mt_encoder_group_fwd(const MtEncoderCfg* cfg, int n_stacks, const uint64_t* seeds, const int* stack_ids, const float* params,
+                         const void* params_lp, size_t param_stride, const float* x, const float* mask, void* y, void* ws, size_t ws_bytes,
+                         void* stream) {
+  MT_TRY(check_cfg(cfg));
+  if (mt_encoder_group_ws_bytes(cfg, n_stacks) == 0) return MT_ERR_ARG;
+  Groups g;
+  MT_TRY(make_groups(*cfg, n_stacks, seeds, stack_ids, param_stride, g));
+  return encoder_fwd_impl(*cfg, g, params, params_lp, x, mask, y, ws, ws_bytes, (cudaStream_t)stream);
+}
 
-  for (int l = c.n_layers - 1; l >= 0; --l) {
-    const size_t base = P.layer_stride * l;
-    const float* pf = params + base;
-    float* gf = grads + base;
-    LayerBufs& b = w.L[l];
-    const float* x_l = l == 0 ? x : w.L[l - 1].x_out;
-    // ---- FFN sublayer: x_out = xp + drop(w_2 hid + b_2); w.dact = drop' . g_cur and db_2 are already there ----------
-    MT_TRY(mt_gemm_run(c.dtype, wgrad_gemm(M, d, dff, w.dact, d, b.hid, dff, gf + P.w_2, dff), st));
-    GemmDesc g = dgrad_gemm(M, d, dff, w.dact, wptr(c, params, params_lp, base + P.w_2), w.dhid, !lp);
-    g.epi.gate = b.hid; g.epi.ldg = dff; g.epi.gate_scale = keep_scale;   // relu' and the hidden dropout mask in one test
-    g.epi.colsum = gf + P.b_1;                                            // db_1 = colsum(dhid), from the epilogue
-    MT_TRY(mt_gemm_run(c.dtype, g, st));
-    MT_TRY(mt_gemm_run(c.dtype, wgrad_gemm(M, dff, d, w.dhid, dff, b.v, d, gf + P.w_1, d), st));
-    MT_TRY(mt_gemm_run(c.dtype, dgrad_gemm(M, dff, d, w.dhid, wptr(c, params, params_lp, base + P.w_1), w.dact2, !lp), st));
-    {
-      LnBwdNext nx{w.dact, gf + P.b_o, mt_make_drop(p, c.seed, mt_enc_site(c.stack_id, l, MT_SITE_SUB0))};
-      MT_TRY(mt_ln_bwd_run(M, d, b.xp, pf + P.ln2_a, 1e-6f, w.dact2, lp, g_cur, g_nxt, gf + P.ln2_a, gf + P.ln2_b, st, &nx));
-    }
-    // ---- attention sublayer: xp = x + drop(att w_o + b_o); w.dact = drop' . g_nxt and db_o are already there ---------
-    MT_TRY(mt_gemm_run(c.dtype, wgrad_gemm(M, d, d, w.dact, d, b.att, d, gf + P.w_o, d), st));
-    MT_TRY(mt_gemm_run(c.dtype, dgrad_gemm(M, d, d, w.dact, wptr(c, params, params_lp, base + P.w_o), w.dact2, !lp), st));
-    MT_TRY(mt_attn_bwd_run(c.dtype, c.B, c.T, d, c.h, b.qkv, mask, b.att, b.lse, w.dact2, w.dqkv,
-                           mt_make_drop(p, c.seed, mt_enc_site(c.stack_id, l, MT_SITE_ATTN_P)), w.Dws, st, gf + P.b_qkv));
-    MT_TRY(mt_gemm_run(c.dtype, wgrad_gemm(M, 3 * d, d, w.dqkv, 3 * d, b.u, d, gf + P.w_qkv, d), st));
-    MT_TRY(mt_gemm_run(c.dtype, dgrad_gemm(M, 3 * d, d, w.dqkv, wptr(c, params, params_lp, base + P.w_qkv), w.dact2, !lp), st));
-    float* out = l == 0 ? dx : g_cur;
-    LnBwdNext nx{nullptr, nullptr, mt_make_drop(0.f, 0, 0)};
-    if (l > 0) nx = LnBwdNext{w.dact, gf - P.layer_stride + P.b_2, mt_make_drop(p, c.seed, mt_enc_site(c.stack_id, l - 1, MT_SITE_SUB1))};
-    MT_TRY(mt_ln_bwd_run(M, d, x_l, pf + P.ln1_a, 1e-6f, w.dact2, lp, g_nxt, out, gf + P.ln1_a, gf + P.ln1_b, st, &nx));
-    // g_cur now holds dL/dx_l (g_nxt is free again)
-  }
-  return MT_OK;
+int mt_encoder_group_bwd(const MtEncoderCfg* cfg, int n_stacks, const uint64_t* seeds, const int* stack_ids, const float* params,
+                         const void* params_lp, size_t param_stride, const float* x, const float* mask, const void* dy, float* dx, float* grads,
+                         void* ws, size_t ws_bytes, void* stream) {
+  MT_TRY(check_cfg(cfg));
+  if (mt_encoder_group_ws_bytes(cfg, n_stacks) == 0) return MT_ERR_ARG;
+  Groups g;
+  MT_TRY(make_groups(*cfg, n_stacks, seeds, stack_ids, param_stride, g));
+  return encoder_bwd_impl(*cfg, g, params, params_lp, x, mask, dy, dx, grads, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int mt_encoder_stack_fwd(const MtEncoderCfg* cfg, const float* params, const void* params_lp, const float* x, const float* mask, void* y,

@@ -30,6 +30,8 @@ struct GemmDesc {
   const void* B = nullptr; int ldb = 0; bool b_kmajor = true;
   void* C = nullptr; int ldc = 0; bool c_f32 = false;
   int split_k = 1;                 // >1: partial sums are atomically added into fp32 C (caller zeroes C)
+  int groups = 1;                  // >1 (tcgen05 split-K wgrad form only, both operands mn-major): group g contracts rows [g*K, (g+1)*K) of
+  long long c_gstride = 0;         //     A / B into C + g * c_gstride -- the weight gradients of several modality stacks in one launch
   GemmEpi epi;
 };
 

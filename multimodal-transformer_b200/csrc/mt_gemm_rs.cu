@@ -8,7 +8,8 @@
 //   * the weight slice [BN x K] of that pair is loaded ONCE into shared memory (<= 128 KB) and stays;
 //   * the CTA streams 128-row activation tiles of its stack through a TMA ring of 16 KB k-blocks (one elected thread issues
 //     tcgen05.mma M128 x BN x 16 into a double-buffered TMEM accumulator, so tile i+1's MMAs overlap tile i's epilogue);
-//   * the epilogue works ROW-PER-THREAD straight out of TMEM (tcgen05.ld 32 columns at a time: lane = row): bias / ReLU / pair-hash
+//   * the epilogue (two warp groups, alternating 64-column pairs of chunks of the same tile) works ROW-PER-THREAD straight out of TMEM
+//     (tcgen05.ld 32 columns at a time: lane = row): bias / ReLU / pair-hash
 //     dropout / ReLU-dropout gate / fp32 residual are applied in registers, the result is written into a 128-byte-swizzled
 //     staging box and leaves with ONE TMA store per box; residual and gate tiles arrive the same way (TMA boxes, own producer warp,
 //     own ring) -- no thread ever issues a global load or store, so HBM sees only full 128-byte lines;
@@ -28,8 +29,8 @@ using namespace tc5;
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int BOX = BM * 128;            // every staged box is [128 rows x 128 bytes] = 16 KB
-constexpr int NT = 256;                  // warp 0: A / weight TMA, warp 1: MMA issue + TMEM, warp 2: residual / gate TMA, warps 4-7: epilogue
-constexpr int EPI_THREADS = 128;
+constexpr int NT = 384;                  // warp 0: A / weight TMA, warp 1: MMA issue + TMEM, warp 2: residual / gate TMA, warps 4-7 / 8-11: epilogue
+constexpr int EPI_THREADS = 128;         // per epilogue warp group
 constexpr int MAXG = MT_RS_MAX_GROUPS;
 constexpr int SMEM_LIMIT = 227 * 1024;
 
@@ -48,21 +49,23 @@ struct RsArgs {
   const float* ln_a[MAXG];
   const float* ln_b[MAXG];
   DropCfg drop[MAXG];
+  unsigned long long* trace;      // debug (mt_gemm_rs_trace): clock64 stamps of CTA 0, 16 words per tile, first 32 tiles
 };
 
 template <int BN, int KB, uint32_t F>
 struct Cfg {
   static constexpr int W_BYTES = KB * BN * 128;
-  static constexpr int AUX_BYTES = 1024 + 4 * BN * 4;             // barriers | bias | column sums | LayerNorm a_2, b_2
+  static constexpr int AUX_BYTES = 1024 + 4 * BN * 4 + 4096;      // barriers | bias | column sums | LayerNorm a_2, b_2 | row moments
   static constexpr int BOXES = (SMEM_LIMIT - 1024 - AUX_BYTES - W_BYTES) / BOX;      // 16 KB boxes left beside the resident weights
-  static constexpr bool TIGHT = BOXES < 7;                        // the 128 KB weight slice with a residual stream: shallow staging
-  static constexpr int NSO = TIGHT && (F & R_RES) ? 1 : 2;        // output staging boxes
-  static constexpr int NSR = (F & R_RES) ? (TIGHT ? 2 : 3) : 0;   // residual ring (fp32 [128 x 32] boxes)
+  static constexpr bool TIGHT = BOXES < 7;                        // the 128 KB weight slices
+  static constexpr int NSO = (TIGHT || (F & (R_RES | R_GATE))) ? 1 : 2;   // output staging boxes PER epilogue warp group
+  static constexpr int NSR = (F & R_RES) ? 4 : 0;                 // residual ring (fp32 [128 x 32] boxes)
   static constexpr int NSG = (F & R_GATE) ? 2 : 0;                // gate ring (bf16 [128 x 64] boxes)
-  static constexpr int FREE = SMEM_LIMIT - 1024 - AUX_BYTES - W_BYTES - (NSO + NSR + NSG) * BOX;
-  static constexpr int NSA = FREE / BOX > 8 ? 8 : FREE / BOX;     // activation ring
-  static constexpr int TOTAL = 1024 + W_BYTES + (NSA + NSO + NSR + NSG) * BOX + AUX_BYTES;
+  static constexpr int FREE = BOXES - 2 * NSO - NSR - NSG;
+  static constexpr int NSA = FREE > 8 ? 8 : FREE;                 // activation ring
+  static constexpr int TOTAL = 1024 + W_BYTES + (NSA + 2 * NSO + NSR + NSG) * BOX + AUX_BYTES;
   static constexpr int CHUNKS = BN / 32;
+  static constexpr int PAIRS = BN / 64;
   static_assert(NSA >= 2, "no room for the activation ring");
   static_assert(2 * BN <= 512, "two accumulators must fit in TMEM");
 };
@@ -75,7 +78,7 @@ __global__ void __launch_bounds__(NT, 1) gemm_rs_kernel(const __grid_constant__ 
   uint8_t* w_s = smem;
   uint8_t* a_ring = w_s + C::W_BYTES;
   uint8_t* o_stage = a_ring + C::NSA * BOX;
-  uint8_t* r_ring = o_stage + C::NSO * BOX;
+  uint8_t* r_ring = o_stage + 2 * C::NSO * BOX;
   uint8_t* g_ring = r_ring + C::NSR * BOX;
   uint8_t* aux = g_ring + C::NSG * BOX;
   uint64_t* bars = reinterpret_cast<uint64_t*>(aux);
@@ -93,6 +96,7 @@ __global__ void __launch_bounds__(NT, 1) gemm_rs_kernel(const __grid_constant__ 
   float* cs_s = bias_s + BN;
   float* lna_s = cs_s + BN;
   float* lnb_s = lna_s + BN;
+  float2* mom_s = reinterpret_cast<float2*>(lnb_s + BN);      // [tile parity][warp group][row] (mean, M2) of a row's column half
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // this CTA's (group, column slice) pair and its share of the group's row tiles
@@ -105,7 +109,7 @@ __global__ void __launch_bounds__(NT, 1) gemm_rs_kernel(const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.a); tma_prefetch_desc(&maps.b[grp]); tma_prefetch_desc(&maps.c);
     for (int s = 0; s < C::NSA; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
     mbar_init(w_full, 1);
     for (int s = 0; s < 4; ++s) { mbar_init(&full_r[s], 1); mbar_init(&empty_r[s], 4); mbar_init(&full_g[s], 1); mbar_init(&empty_g[s], 4); }
     mbar_init_fence();
@@ -141,6 +145,7 @@ __global__ void __launch_bounds__(NT, 1) gemm_rs_kernel(const __grid_constant__ 
         const int row0 = grp * g.rows_per_group + (rank + i * g.cnt) * BM;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&empty_a[stage], phase ^ 1);
+          if (g.trace && blockIdx.x == 0 && i < 32 && kb < 4) g.trace[i * 16 + kb] = clock64();
           mbar_expect_tx(&full_a[stage], BOX);
           tma_load_2d(a_ring + stage * BOX, &maps.a, kb * BK, row0, &full_a[stage]);
           if (++stage == C::NSA) { stage = 0; phase ^= 1; }
@@ -163,11 +168,13 @@ __global__ void __launch_bounds__(NT, 1) gemm_rs_kernel(const __grid_constant__ 
         const int acc = it & 1;
         mbar_wait(&acc_empty[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u);
         fence_after();
+        if (g.trace && blockIdx.x == 0 && it < 32) g.trace[it * 16 + 8] = clock64();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         uint32_t accum = 0u;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&full_a[stage], phase);
           fence_after();
+          if (g.trace && blockIdx.x == 0 && it < 32 && kb < 4) g.trace[it * 16 + 4 + kb] = clock64();
           const uint32_t sa = ring_u32 + (uint32_t)(stage * BOX), sb = w_u32 + (uint32_t)(kb * BN * 128);
           const uint32_t a_lo = a_lbo | ((sa >> 4) & 0x3FFFu), b_lo = b_lbo | ((sb >> 4) & 0x3FFFu);
 #pragma unroll
@@ -206,14 +213,18 @@ __global__ void __launch_bounds__(NT, 1) gemm_rs_kernel(const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: thread = one row of the tile (TMEM lane), 32 columns per pass =====
+    // ===== epilogue: two warp groups; thread = one row of the tile (TMEM lane), 32 columns per pass.  Warp group w owns the chunk
+    // pairs (64 columns) pr with pr % 2 == w of every tile, its own staging box(es), named barrier and TMA-store thread. =====
+    const int wg = (warp - 4) >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const bool storer = threadIdx.x == 4 * 32;
+    const bool storer = (threadIdx.x & (EPI_THREADS - 1)) == 0;
+    const int bar_id = 1 + wg;
+    uint8_t* my_stage = o_stage + wg * C::NSO * BOX;
     DropCfg drop = g.drop[grp];
     if (F & R_DROP) drop = mt_drop_resolve(drop);
     const uint32_t t16 = drop.thresh >> 16;
-    int ob = 0, rs = 0, gs = 0; uint32_t rph = 0, gph = 0;
+    int ob = 0;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     for (int it = 0; it < n_tiles; ++it) {
       const int tm = rank + it * g.cnt;
@@ -221,169 +232,178 @@ __global__ void __launch_bounds__(NT, 1) gemm_rs_kernel(const __grid_constant__ 
       const int acc = it & 1;
       mbar_wait(&acc_full[acc], (uint32_t)(it >> 1) & 1u);
       fence_after();
+      const bool tr = g.trace && blockIdx.x == 0 && it < 32 && storer;
+      if (tr) g.trace[it * 16 + 9 + 2 * wg] = clock64();
       const uint32_t tacc = lane_base + (uint32_t)(acc * BN);
       float s1 = 0.f, s2 = 0.f, x0 = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < C::CHUNKS; ++c) {
-        const bool box_start = (F & R_CF32) ? true : (c & 1) == 0;
-        const bool box_end = (F & R_CF32) ? true : (c & 1) == 1;
-        if (box_start) {          // the staging box about to be written must have been read out by its previous store
-          if (storer) bulk_wait_read<C::NSO - 1>();
-          bar_sync(1, EPI_THREADS);
-        }
-        uint32_t v[32];
-        ld32(tacc + (uint32_t)(c * 32), v);
-        ld_wait();
-        if (!(F & R_LN) && c == C::CHUNKS - 1) {      // accumulator drained: hand it back to the MMA warp
-          fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[acc]);
-        }
-        float o[32];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + 4 * j);
-          o[4 * j] = __uint_as_float(v[4 * j]) + b4.x; o[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
-          o[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z; o[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
-        }
-        if (F & R_RELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.f);
-        }
-        if (F & R_DROP) {
-          if (drop.thresh != 0u) {
-            // element index (m local to the group) * N + n: even, so a pair never straddles two rows
-            const uint64_t idx = (uint64_t)(tm * BM + row) * (uint64_t)g.N + (uint64_t)(n0 + c * 32);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const uint32_t bits = mt_draw32(drop, (idx >> 1) + (uint64_t)j);
-              o[2 * j] = (bits & 0xFFFFu) >= t16 ? o[2 * j] * drop.scale : 0.f;
-              o[2 * j + 1] = (bits >> 16) >= t16 ? o[2 * j + 1] * drop.scale : 0.f;
-            }
-          }
-        }
-        if (F & R_GATE) {
-          if ((c & 1) == 0) mbar_wait(&full_g[gs], gph);
-          const uint8_t* gb = g_ring + gs * BOX;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 gw = *reinterpret_cast<const uint4*>(gb + sw128_off(row, (c & 1) * 4 + j));
-            const uint32_t w4[4] = {gw.x, gw.y, gw.z, gw.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 g2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[k]));
-              o[8 * j + 2 * k] = g2.x > 0.f ? o[8 * j + 2 * k] * g.gate_scale : 0.f;
-              o[8 * j + 2 * k + 1] = g2.y > 0.f ? o[8 * j + 2 * k + 1] * g.gate_scale : 0.f;
-            }
-          }
-          if ((c & 1) == 1) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_g[gs]);
-            if (++gs == (C::NSG ? C::NSG : 1)) { gs = 0; gph ^= 1; }
-          }
-        }
-        if (F & R_RES) {
-          mbar_wait(&full_r[rs], rph);
-          const uint8_t* rb = r_ring + rs * BOX;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 r4 = *reinterpret_cast<const float4*>(rb + sw128_off(row, j));
-            o[4 * j] += r4.x; o[4 * j + 1] += r4.y; o[4 * j + 2] += r4.z; o[4 * j + 3] += r4.w;
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty_r[rs]);
-          if (++rs == (C::NSR ? C::NSR : 1)) { rs = 0; rph ^= 1; }
-        }
-        if (F & R_LN) {          // keep the finished fp32 row in TMEM for the normalising sweep; shifted single-pass moments
-          uint32_t w[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(o[j]);
-          st16(tacc + (uint32_t)(c * 32), w);
-          st16(tacc + (uint32_t)(c * 32 + 16), w + 16);
-          if (c == 0) x0 = o[0];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) { const float t = o[j] - x0; s1 += t; s2 = fmaf(t, t, s2); }
-        }
-        uint8_t* ob_s = o_stage + ob * BOX;
-        if (F & R_CF32) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(ob_s + sw128_off(row, j)) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 pk;
-            pk.x = pack_bf2(o[8 * j], o[8 * j + 1]); pk.y = pack_bf2(o[8 * j + 2], o[8 * j + 3]);
-            pk.z = pack_bf2(o[8 * j + 4], o[8 * j + 5]); pk.w = pack_bf2(o[8 * j + 6], o[8 * j + 7]);
-            *reinterpret_cast<uint4*>(ob_s + sw128_off(row, (c & 1) * 4 + j)) = pk;
-          }
-        }
-        if (F & R_COLSUM) {      // halving butterfly over the warp's 32 rows: lane l ends with the sum of column l
-#pragma unroll
-          for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
-            const bool up = (lane & off) != 0;
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-              const float send = up ? o[i] : o[i + n], keep = up ? o[i + n] : o[i];
-              o[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-            }
-          }
-          atomicAdd(cs_s + c * 32 + lane, o[0]);
-        }
-        if (box_end) {
-          fence_proxy_async();
-          bar_sync(1, EPI_THREADS);
-          if (storer) {
-            tma_store_2d(&maps.c, ob_s, (F & R_CF32) ? n0 + 32 * c : n0 + 32 * (c - 1), row0);
-            bulk_commit();
-          }
-          if (++ob == C::NSO) ob = 0;
-        }
-      }
-      if (F & R_LN) {
-        st_wait();
-        constexpr float inv_n = 1.0f / (float)BN;
-        const float mean = x0 + s1 * inv_n;
-        const float var = fmaxf(s2 - s1 * s1 * inv_n, 0.f) * (1.0f / (float)(BN - 1));
-        const float inv = 1.0f / (sqrtf(var) + g.ln_eps);
+      for (int pr = wg; pr < C::PAIRS; pr += 2) {
 #pragma unroll 1
-        for (int c = 0; c < C::CHUNKS; ++c) {
-          if ((c & 1) == 0) {
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = 2 * pr + cc;
+          const bool box_start = (F & R_CF32) ? true : cc == 0;
+          const bool box_end = (F & R_CF32) ? true : cc == 1;
+          if (box_start) {          // the staging box about to be written must have been read out by its previous store
             if (storer) bulk_wait_read<C::NSO - 1>();
-            bar_sync(1, EPI_THREADS);
+            bar_sync(bar_id, EPI_THREADS);
           }
           uint32_t v[32];
           ld32(tacc + (uint32_t)(c * 32), v);
           ld_wait();
-          if (c == C::CHUNKS - 1) {
-            fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+          float o[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + 4 * j);
+            o[4 * j] = __uint_as_float(v[4 * j]) + b4.x; o[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+            o[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z; o[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
           }
-          uint8_t* ob_s = o_stage + ob * BOX;
+          if (F & R_RELU) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float y[8];
+            for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.f);
+          }
+          if (F & R_DROP) {
+            if (drop.thresh != 0u) {
+              // element index (m local to the group) * N + n: even, so a pair never straddles two rows
+              const uint64_t idx = (uint64_t)(tm * BM + row) * (uint64_t)g.N + (uint64_t)(n0 + c * 32);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const int col = c * 32 + 8 * j + k;
-              y[k] = fmaf(lna_s[col] * inv, __uint_as_float(v[8 * j + k]) - mean, lnb_s[col]);
+              for (int j = 0; j < 16; ++j) {
+                const uint32_t bits = mt_draw32(drop, (idx >> 1) + (uint64_t)j);
+                o[2 * j] = (bits & 0xFFFFu) >= t16 ? o[2 * j] * drop.scale : 0.f;
+                o[2 * j + 1] = (bits >> 16) >= t16 ? o[2 * j + 1] * drop.scale : 0.f;
+              }
             }
-            uint4 pk;
-            pk.x = pack_bf2(y[0], y[1]); pk.y = pack_bf2(y[2], y[3]); pk.z = pack_bf2(y[4], y[5]); pk.w = pack_bf2(y[6], y[7]);
-            *reinterpret_cast<uint4*>(ob_s + sw128_off(row, (c & 1) * 4 + j)) = pk;
           }
-          if ((c & 1) == 1) {
+          if (F & R_GATE) {        // gate box use number: one per chunk pair, consumed by this warp group only
+            const int ug = it * C::PAIRS + pr, gs = ug % (C::NSG ? C::NSG : 1);
+            if (cc == 0) mbar_wait(&full_g[gs], (uint32_t)(ug / (C::NSG ? C::NSG : 1)) & 1u);
+            const uint8_t* gb = g_ring + gs * BOX;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 gw = *reinterpret_cast<const uint4*>(gb + sw128_off(row, cc * 4 + j));
+              const uint32_t w4[4] = {gw.x, gw.y, gw.z, gw.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 g2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[k]));
+                o[8 * j + 2 * k] = g2.x > 0.f ? o[8 * j + 2 * k] * g.gate_scale : 0.f;
+                o[8 * j + 2 * k + 1] = g2.y > 0.f ? o[8 * j + 2 * k + 1] * g.gate_scale : 0.f;
+              }
+            }
+            if (cc == 1) {
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&empty_g[gs]);
+            }
+          }
+          if (F & R_RES) {         // residual box use number: one per chunk
+            const int ur = it * C::CHUNKS + c, rs = ur % (C::NSR ? C::NSR : 1);
+            mbar_wait(&full_r[rs], (uint32_t)(ur / (C::NSR ? C::NSR : 1)) & 1u);
+            const uint8_t* rb = r_ring + rs * BOX;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 r4 = *reinterpret_cast<const float4*>(rb + sw128_off(row, j));
+              o[4 * j] += r4.x; o[4 * j + 1] += r4.y; o[4 * j + 2] += r4.z; o[4 * j + 3] += r4.w;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_r[rs]);
+          }
+          if (F & R_LN) {          // keep the finished fp32 row in TMEM for the normalising sweep; shifted single-pass moments
+            uint32_t w[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(o[j]);
+            st16(tacc + (uint32_t)(c * 32), w);
+            st16(tacc + (uint32_t)(c * 32 + 16), w + 16);
+            if (pr == wg && cc == 0) x0 = o[0];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { const float t = o[j] - x0; s1 += t; s2 = fmaf(t, t, s2); }
+          }
+          uint8_t* ob_s = my_stage + ob * BOX;
+          if (F & R_CF32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(ob_s + sw128_off(row, j)) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 pk;
+              pk.x = pack_bf2(o[8 * j], o[8 * j + 1]); pk.y = pack_bf2(o[8 * j + 2], o[8 * j + 3]);
+              pk.z = pack_bf2(o[8 * j + 4], o[8 * j + 5]); pk.w = pack_bf2(o[8 * j + 6], o[8 * j + 7]);
+              *reinterpret_cast<uint4*>(ob_s + sw128_off(row, cc * 4 + j)) = pk;
+            }
+          }
+          if (F & R_COLSUM) {      // halving butterfly over the warp's 32 rows: lane l ends with the sum of column l
+#pragma unroll
+            for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
+              const bool up = (lane & off) != 0;
+#pragma unroll
+              for (int i = 0; i < n; ++i) {
+                const float send = up ? o[i] : o[i + n], keep = up ? o[i + n] : o[i];
+                o[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+              }
+            }
+            atomicAdd(cs_s + c * 32 + lane, o[0]);
+          }
+          if (box_end) {
             fence_proxy_async();
-            bar_sync(1, EPI_THREADS);
+            bar_sync(bar_id, EPI_THREADS);
             if (storer) {
-              tma_store_2d(&maps.ln, ob_s, n0 + 32 * (c - 1), row0);
+              tma_store_2d(&maps.c, ob_s, (F & R_CF32) ? n0 + 32 * c : n0 + 64 * pr, row0);
               bulk_commit();
             }
             if (++ob == C::NSO) ob = 0;
           }
         }
       }
+      if (F & R_LN) {
+        // this warp group's half of the row -> (mean, M2); the two halves are merged through shared memory (Chan et al.)
+        constexpr float half_n = (float)(BN / 2);
+        const float m_w = x0 + s1 / half_n;
+        const float M2_w = fmaxf(s2 - s1 * s1 / half_n, 0.f);
+        float2* mom = mom_s + (it & 1) * 2 * BM;
+        mom[wg * BM + row] = make_float2(m_w, M2_w);
+        st_wait();
+        bar_sync(3, 2 * EPI_THREADS);
+        const float2 other = mom[(wg ^ 1) * BM + row];
+        const float dm = m_w - other.x;
+        const float mean = 0.5f * (m_w + other.x);
+        const float var = (M2_w + other.y + dm * dm * (half_n * 0.5f)) * (1.0f / (float)(BN - 1));
+        const float inv = 1.0f / (sqrtf(var) + g.ln_eps);
+#pragma unroll 1
+        for (int pr = wg; pr < C::PAIRS; pr += 2) {
+          if (storer) bulk_wait_read<C::NSO - 1>();
+          bar_sync(bar_id, EPI_THREADS);
+          uint8_t* ob_s = my_stage + ob * BOX;
+#pragma unroll 1
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c = 2 * pr + cc;
+            uint32_t v[32];
+            ld32(tacc + (uint32_t)(c * 32), v);
+            ld_wait();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float y[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int col = c * 32 + 8 * j + k;
+                y[k] = fmaf(lna_s[col] * inv, __uint_as_float(v[8 * j + k]) - mean, lnb_s[col]);
+              }
+              uint4 pk;
+              pk.x = pack_bf2(y[0], y[1]); pk.y = pack_bf2(y[2], y[3]); pk.z = pack_bf2(y[4], y[5]); pk.w = pack_bf2(y[6], y[7]);
+              *reinterpret_cast<uint4*>(ob_s + sw128_off(row, cc * 4 + j)) = pk;
+            }
+          }
+          fence_proxy_async();
+          bar_sync(bar_id, EPI_THREADS);
+          if (storer) {
+            tma_store_2d(&maps.ln, ob_s, n0 + 64 * pr, row0);
+            bulk_commit();
+          }
+          if (++ob == C::NSO) ob = 0;
+        }
+      }
+      if (tr) g.trace[it * 16 + 10 + 2 * wg] = clock64();
+      // every TMEM read of this tile by this warp is done: hand the accumulator back to the MMA warp
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
     }
     if (storer) bulk_wait_all<0>();
   }
@@ -397,6 +417,8 @@ __global__ void __launch_bounds__(NT, 1) gemm_rs_kernel(const __grid_constant__ 
     tmem_dealloc<2 * BN>(tmem_base);
   }
 }
+
+unsigned long long* g_rs_trace = nullptr;
 
 int num_sms() {
   int dev = 0, n = 0;
@@ -430,6 +452,7 @@ int launch(const RsDesc& d, cudaStream_t st) {
   g.rows_per_group = d.Mg;
   g.b_mn = d.b_kmajor ? 0 : 1;
   g.gate_scale = d.gate_scale; g.ln_eps = d.ln_eps;
+  g.trace = g_rs_trace;
   const int P = d.G * g.tiles_n;
   int cnt = num_sms() / P;
   if (cnt < 1) cnt = 1;
@@ -462,19 +485,15 @@ uint32_t features(const RsDesc& d) {
 }
 
 // the instantiations of the encoder path: (N, K, feature set) -> (BN, KB)
-#define RS_CASE(N_, K_, BN_, F_) \
-  if (d.N == (N_) && d.K == (K_) && f == (uint32_t)(F_)) return launch<BN_, (K_) / 64, (uint32_t)(F_)>(d, st)
-
 int dispatch(const RsDesc& d, cudaStream_t st, bool probe_only) {
   const uint32_t f = features(d);
 #define RS_PROBE(N_, K_, BN_, F_) \
   if (d.N == (N_) && d.K == (K_) && f == (uint32_t)(F_)) return probe_only ? MT_OK : launch<BN_, (K_) / 64, (uint32_t)(F_)>(d, st)
   // forward
+  if (g_mt_tune[4] == 1) { RS_PROBE(768, 256, 128, R_BIAS); }              // experiment: 6 narrow slices, deep ring
   RS_PROBE(768, 256, 256, R_BIAS);                                         // QKV projection
   RS_PROBE(256, 256, 128, R_BIAS | R_DROP | R_RES | R_CF32);               // output projection, train
   RS_PROBE(256, 256, 128, R_BIAS | R_RES | R_CF32);                        // output projection, eval
-  RS_PROBE(256, 256, 256, R_BIAS | R_DROP | R_RES | R_CF32 | R_LN);        // output projection + LayerNorm 2, train
-  RS_PROBE(256, 256, 256, R_BIAS | R_RES | R_CF32 | R_LN);                 // output projection + LayerNorm 2, eval
   RS_PROBE(128, 256, 128, R_BIAS | R_RELU | R_DROP);                       // FFN w_1, train
   RS_PROBE(128, 256, 128, R_BIAS | R_RELU);                                // FFN w_1, eval
   RS_PROBE(256, 128, 256, R_BIAS | R_DROP | R_RES | R_CF32);               // FFN w_2, train
@@ -485,7 +504,6 @@ int dispatch(const RsDesc& d, cudaStream_t st, bool probe_only) {
   RS_PROBE(128, 256, 128, R_GATE | R_COLSUM);                              // d hidden = (d out . w_2) gated by relu' / dropout, + d b_1
   RS_PROBE(256, 128, 256, 0u);                                             // d LN2-out = d hidden . w_1
   RS_PROBE(256, 256, 256, 0u);                                             // d att = d out . w_o
-  RS_PROBE(256, 768, 64, 0u);                                              // d LN1-out = d qkv . w_qkv
 #undef RS_PROBE
   return MT_ERR_UNSUPPORTED;
 }
@@ -525,6 +543,10 @@ int mt_gemm_rs_run(const RsDesc& d, cudaStream_t st) {
 }
 
 extern "C" {
+
+/* debug hook: CTA 0 of every row-stream GEMM writes clock64 stamps (16 x uint64 per tile, first 32 tiles: TMA issue of k-blocks 0-3,
+ * their arrival as seen by the MMA thread, accumulator free, epilogue start / end of the two warp groups) into dev_buf (>= 4 KB) */
+int mt_gemm_rs_trace(void* dev_buf) { g_rs_trace = (unsigned long long*)dev_buf; return MT_OK; }
 
 /* Probe / test entry of the row-stream engine: G groups of Mg rows; B = G weight matrices back to back ([N,K] K-major when b_kmajor,
  * else [K,N]); bias / colsum G x N back to back (may be NULL); drop_p > 0 applies output dropout with per-group sites site + 512 * g;

@@ -45,6 +45,8 @@ struct TcArgs {
   void* C; int ldc; int c_f32; int atomic;
   GemmEpi epi;
   int gate_bf16;
+  int groups, kb_group;                // grouped split-K (wgrads of several modality stacks): group g contracts k-blocks [g*kb_group, +kb_total)
+  long long c_gstride;                 // ... into C + g * c_gstride (fp32 elements)
   unsigned long long* trace;           // debug: per-tile clock64 stamps of CTA 0 (mt_gemm_debug_trace), else null
 };
 
@@ -166,7 +168,8 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 
 // work item i of this CTA -> (m tile, n tile, split); false when the CTA is done.  Enumerated identically by all roles.
 template <bool RES>
-__device__ __forceinline__ bool get_work(const TcArgs& g, int i, int& tm, int& tn, int& split) {
+__device__ __forceinline__ bool get_work(const TcArgs& g, int i, int& tm, int& tn, int& split, int& grp) {
+  grp = 0;
   if (RES) {                     // pinned to column slice blockIdx.x % tiles_n; row tiles dealt among the CTAs of that slice
     tn = (int)blockIdx.x % g.tiles_n;
     const int rank = (int)blockIdx.x / g.tiles_n, cnt = ((int)gridDim.x - tn + g.tiles_n - 1) / g.tiles_n;
@@ -174,9 +177,11 @@ __device__ __forceinline__ bool get_work(const TcArgs& g, int i, int& tm, int& t
     split = 0;
     return tm < g.tiles_m;
   }
-  const int tiles = g.tiles_m * g.tiles_n;
-  const int w = (int)blockIdx.x + i * (int)gridDim.x;
-  if (w >= tiles * g.splits) return false;
+  const int tiles = g.tiles_m * g.tiles_n, per = tiles * g.splits;
+  int w = (int)blockIdx.x + i * (int)gridDim.x;
+  if (w >= per * g.groups) return false;
+  grp = w / per;
+  w -= grp * per;
   const int tile = w % tiles;
   split = w / tiles;
   tm = tile / g.tiles_n; tn = tile % g.tiles_n;
@@ -232,8 +237,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) {
       const int a_mn = g.a_mn, b_mn = g.b_mn, kb_per = g.kb_per, kb_total = g.kb_total;
       const bool tracing = g.trace != nullptr && blockIdx.x == 0;
-      int tm, tn, split;
-      if (RES && get_work<RES>(g, 0, tm, tn, split)) {          // the weight slice of this CTA's column tile, once
+      int tm, tn, split, grp;
+      if (RES && get_work<RES>(g, 0, tm, tn, split, grp)) {          // the weight slice of this CTA's column tile, once
         mbar_expect_tx(b_full, (uint32_t)(kb_total * S::B_BYTES));
         for (int kb = 0; kb < kb_total; ++kb) {
           uint8_t* sb = res_b + kb * S::B_BYTES;
@@ -246,9 +251,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
       int stage = 0; uint32_t phase = 0;
-      for (int i = 0; get_work<RES>(g, i, tm, tn, split); ++i) {
+      for (int i = 0; get_work<RES>(g, i, tm, tn, split, grp); ++i) {
         const int m0 = tm * BM, n0 = tn * BN;
-        const int kb0 = split * kb_per, kb1 = min(kb_total, kb0 + kb_per);
+        const int kbase = grp * g.kb_group;
+        const int kb0 = kbase + split * kb_per, kb1 = min(kbase + kb_total, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           if (tracing && kb == kb0 && i < 64) g.trace[i * 8 + 0] = clock64();
@@ -290,10 +296,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t a_kstep = a_mn ? (uint32_t)((16 * 128) >> 4) : 2u, b_kstep = b_mn ? (uint32_t)((16 * 128) >> 4) : 2u;   // 16 k-elements, in 16-byte units
       const uint32_t ring_u32 = smem_u32(ring), resb_u32 = smem_u32(res_b);
       int stage = 0; uint32_t phase = 0;
-      int tm, tn, split;
-      if (RES && get_work<RES>(g, 0, tm, tn, split)) { mbar_wait(b_full, 0); tc_fence_after(); }
-      for (int it = 0; get_work<RES>(g, it, tm, tn, split); ++it) {
-        const int kb0 = split * kb_per, kb1 = min(kb_total, kb0 + kb_per);
+      int tm, tn, split, grp;
+      if (RES && get_work<RES>(g, 0, tm, tn, split, grp)) { mbar_wait(b_full, 0); tc_fence_after(); }
+      for (int it = 0; get_work<RES>(g, it, tm, tn, split, grp); ++it) {
+        const int kbase = grp * g.kb_group;
+        const int kb0 = kbase + split * kb_per, kb1 = min(kbase + kb_total, kb0 + kb_per);
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1;
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
@@ -308,7 +315,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (tracing && it < 64 && kb == kb1 - 1) g.trace[it * 8 + 3] = clock64();
           if (tracing && it < 16 && kb - kb0 < 4) g.trace[512 + (it * 4 + kb - kb0) * 2 + 1] = clock64();
           const uint32_t sa = ring_u32 + (uint32_t)(stage * SLOT);
-          const uint32_t sb = RES ? resb_u32 + (uint32_t)(kb * S::B_BYTES) : sa + (uint32_t)S::A_BYTES;
+          const uint32_t sb = RES ? resb_u32 + (uint32_t)((kb - kbase) * S::B_BYTES) : sa + (uint32_t)S::A_BYTES;
           const uint32_t a_lo = a_lbo | ((sa >> 4) & 0x3FFFu), b_lo = b_lbo | ((sb >> 4) & 0x3FFFu);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
@@ -343,8 +350,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     DropCfg edrop = mt_drop_resolve(e.drop);
     const bool f_drop = HAS(F_DROP, edrop.thresh != 0u);
     const int lr = lane / LPR, lc = (lane % LPR) * 8;
-    int tm, tn, split;
-    for (int it = 0; get_work<RES>(g, it, tm, tn, split); ++it) {
+    int tm, tn, split, grp;
+    for (int it = 0; get_work<RES>(g, it, tm, tn, split, grp); ++it) {
       const int m0 = tm * BM;
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1;
@@ -383,7 +390,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if ((F & F_EDGE) && m >= g.M) continue;
             float4 a0 = *reinterpret_cast<const float4*>(stg + r * LDS + lc), a1 = *reinterpret_cast<const float4*>(stg + r * LDS + lc + 4);
             if (f_alpha) { a0.x *= e.alpha; a0.y *= e.alpha; a0.z *= e.alpha; a0.w *= e.alpha; a1.x *= e.alpha; a1.y *= e.alpha; a1.z *= e.alpha; a1.w *= e.alpha; }
-            float* cp = reinterpret_cast<float*>(g.C) + (size_t)m * g.ldc + n;
+            float* cp = reinterpret_cast<float*>(g.C) + (size_t)grp * g.c_gstride + (size_t)m * g.ldc + n;
             red_add_v4(cp, a0.x, a0.y, a0.z, a0.w);
             if (hi_ok) red_add_v4(cp + 4, a1.x, a1.y, a1.z, a1.w);
           }
@@ -610,8 +617,9 @@ int launch_tc(const GemmDesc& d, cudaStream_t st) {
   g.tiles_n = (d.N + BN - 1) / BN;
   g.kb_total = (d.K + BK - 1) / BK;
   int splits = 1;
+  const int groups = d.groups > 1 ? d.groups : 1;
   if (d.split_k > 1) {                       // wgrad-style: few output tiles, long K -> one work item per SM
-    splits = OCC * num_sms() / (g.tiles_m * g.tiles_n);
+    splits = OCC * num_sms() / (g.tiles_m * g.tiles_n * groups);
     if (splits < 1) splits = 1;
   }
   if (splits > g.kb_total) splits = g.kb_total;
@@ -623,11 +631,12 @@ int launch_tc(const GemmDesc& d, cudaStream_t st) {
   g.atomic = d.split_k > 1 ? 1 : 0;
   g.epi = d.epi;
   g.gate_bf16 = 1;
+  g.groups = groups; g.kb_group = groups > 1 ? d.K / BK : 0; g.c_gstride = d.c_gstride;
   g.trace = g_trace;
   CUtensorMap ma, mb;
-  MT_TRY(make_map(&ma, d.A, d.M, d.K, d.lda, d.a_kmajor, BM));
-  MT_TRY(make_map(&mb, d.B, d.N, d.K, d.ldb, d.b_kmajor, BN));
-  const int n_work = g.tiles_m * g.tiles_n * g.splits;
+  MT_TRY(make_map(&ma, d.A, d.M, d.K * groups, d.lda, d.a_kmajor, BM));
+  MT_TRY(make_map(&mb, d.B, d.N, d.K * groups, d.ldb, d.b_kmajor, BN));
+  const int n_work = g.tiles_m * g.tiles_n * g.splits * groups;
   // g_tc_share > 1: launch only 1/share of the resident CTA slots so that GEMMs of concurrent streams (the three modality stacks)
   // co-reside on every SM instead of queueing behind each other (mt_tune)
   int slots = OCC * num_sms();
@@ -668,6 +677,7 @@ bool mt_gemm_tc_supported(const GemmDesc& d) {
   if (d.lda % 8 != 0 || d.ldb % 8 != 0) return false;
   if (((uintptr_t)d.A & 15) || ((uintptr_t)d.B & 15) || ((uintptr_t)d.C & 15)) return false;
   if (d.epi.accumulate) return false;
+  if (d.groups > 1 && (d.split_k <= 1 || d.a_kmajor || d.b_kmajor || d.K % BK != 0)) return false;      // grouping: split-K wgrad form only
   if (d.split_k > 1 && !d.c_f32) return false;
   if (d.epi.colsum && (d.split_k > 1 || d.N > 1024)) return false;
   if (d.epi.bias && ((uintptr_t)d.epi.bias & 15)) return false;

@@ -21,12 +21,19 @@ struct WsCarver {
 static inline size_t mt_esize(int dtype) { return dtype == MT_BF16 ? 2 : 4; }
 
 // ---- element-wise / row-wise kernels (mt_elementwise.cu) ---------------------------------------------
-int mt_ln_fwd_run(int M, int d, const float* x, const float* a, const float* b, float eps, void* y, bool y_bf16, cudaStream_t st);
+// G > 1: grouped launch over G modality stacks -- x / y are [G*M, d] (rows of group g at g*M), a / b of group g at a + g*pstride floats
+#define MT_LN_MAX_GROUPS 4
+struct DropGroups { DropCfg d[MT_LN_MAX_GROUPS]; };
+int mt_ln_fwd_run(int M, int d, const float* x, const float* a, const float* b, float eps, void* y, bool y_bf16, cudaStream_t st, int G = 1,
+                  size_t pstride = 0);
 // optional second output of the LayerNorm backward: out = dx * dropout_factor(drop, row*d + col) in the operand dtype
 // (same dtype as dy) and dbias[d] += colsum(out) -- what the sublayer below needs first (see ln_bwd_kernel)
 struct LnBwdNext { void* out; float* dbias; DropCfg drop; };
+// G > 1: grouped like mt_ln_fwd_run (dy / dres / dx / nx->out rows of group g at g*M; a / da / db / nx->dbias at + g*pstride;
+// nx_drops[g] = that group's dropout stream, element index local to the group)
 int mt_ln_bwd_run(int M, int d, const float* x, const float* a, float eps, const void* dy, bool dy_bf16, const float* dres,
-                  float* dx, float* da, float* db, cudaStream_t st, const LnBwdNext* nx = nullptr);
+                  float* dx, float* da, float* db, cudaStream_t st, const LnBwdNext* nx = nullptr, int G = 1, size_t pstride = 0,
+                  const DropCfg* nx_drops = nullptr);
 // out[M,N] (bf16 or f32) = g[M,N] (f32) * dropout_factor(site, m*N+n)      (gradient through an output dropout)
 int mt_drop_grad_run(int M, int N, const float* g, void* out, bool out_bf16, DropCfg drop, cudaStream_t st);
 // 2-D cast with zero padding / optional input dropout: dst[r, c] = c < cols ? src[r*lds + c] * drop(r*cols + c) : 0

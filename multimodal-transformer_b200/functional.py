@@ -14,8 +14,10 @@ from ._lib import ACT_NONE, ACT_RELU, ACT_TANH, MT_BF16, MT_F32, check, lib, ptr
 
 _SITE_RESIDUAL = 0x7000      # stand-alone SublayerConnection dropout: its own site range (0x6000.. belongs to the window front-end)
 
+import os as _os
+
 _state = {'dtype': MT_F32, 'seed': 0x5EED0000, 'counter': 0, 'fixed_seed': None, 'parallel_stacks': True, 'defer_wgrad': False,
-          'pending': [], 'wgrad_stream': {}, 'key_len': None}
+          'pending': [], 'wgrad_stream': {}, 'key_len': None, 'grouped_stacks': _os.environ.get('MT_GROUPED_STACKS', '1') != '0'}
 
 
 def set_compute_dtype(name):
@@ -39,6 +41,19 @@ def set_parallel_stacks(on):
 
 def parallel_stacks():
     return _state['parallel_stacks']
+
+
+def set_grouped_stacks(on):
+    """Run the per-modality encoder stacks of MultiTransformer as ONE grouped call (mt_encoder_group_fwd / _bwd: one launch per
+    projection / LayerNorm / weight gradient serves all stacks; default on) instead of one call per stack.  Returns the previous
+    setting."""
+    old = _state['grouped_stacks']
+    _state['grouped_stacks'] = bool(on)
+    return old
+
+
+def grouped_stacks():
+    return _state['grouped_stacks']
 
 
 def set_deferred_weight_grads(on):
@@ -396,6 +411,8 @@ class Arena:
         for p, o in zip(self.params, self.offsets):
             if p.grad is None or p.grad.data_ptr() != base + 4 * o:
                 return None
+        if (g0.storage_offset() + self.total) * 4 > g0.untyped_storage().nbytes():
+            return None          # adjacent by accident of the allocator, not one buffer
         return g0.as_strided((self.total,), (1,), g0.storage_offset())
 
 
@@ -450,6 +467,122 @@ class EncoderFn(torch.autograd.Function):
 
 def encoder_stack(x, mask, arena, cfgd):
     return _apply(EncoderFn, x, mask, arena, cfgd, *arena.params)
+
+
+class EncoderGroupFn(torch.autograd.Function):
+    """The per-modality embed Linears (MFT/multiTransformer.py:270,296) and encoder stacks (:278-299) of MultiTransformer as ONE grouped
+    call each way: every stack has the same shape, so their rows are laid out back to back and one launch per projection / LayerNorm /
+    weight gradient serves all of them (mt_encoder_group_fwd / _bwd).  Inputs: G raw inputs, then (weight, bias) of the G embeds, then
+    the parameters of the group arena.  Returns G views [B,T,d] of one output block."""
+
+    @staticmethod
+    def forward(ctx, mask, arena, cfgd, G, *tensors):
+        dt = _state['dtype']
+        xs, emb = list(tensors[:G]), tensors[G:3 * G]
+        B, T = xs[0].shape[0], xs[0].shape[1]
+        d = emb[0].shape[0]
+        M = B * T
+        dev = xs[0].device
+        _lib.check_device(dev.index)
+        L = lib()
+        flat = arena.bind()
+        lp = arena.shadow() if dt == MT_BF16 else None
+        pstride = arena.total // G
+        m = mask2d(mask, B, T, dev)
+        need_grad = _need_grad(ctx)
+        p_drop = float(cfgd['p_drop'])
+        seeds = [next_seed() if p_drop > 0 else 0 for _ in range(G)]
+        y_f32 = int(cfgd.get('y_f32', dt == MT_F32))
+        cfg = _lib.MtEncoderCfg(B, T, d, cfgd['h'], cfgd['dff'], cfgd['n_layers'], dt, int(need_grad), p_drop, seeds[0],
+                                cfgd['stack_ids'][0], y_f32, 0, None)
+        kl = _key_len(B, T, dev, need_grad, p_drop)
+        if kl is not None:
+            cfg.key_len = kl.data_ptr()
+        # embeds straight into the stacked residual-stream block
+        x0 = torch.empty((G, B, T, d), dtype=torch.float32, device=dev)
+        xin = []
+        for g in range(G):
+            x2 = xs[g].reshape(M, -1)
+            x2 = require(x2 if x2.is_contiguous() else x2.contiguous(), name='x')
+            if x2.dtype not in (torch.float32, torch.bfloat16) or (dt == MT_F32 and x2.dtype != torch.float32):
+                raise RuntimeError(f'embed input dtype {x2.dtype} does not match compute dtype {get_compute_dtype()}')
+            W, b = emb[2 * g], emb[2 * g + 1]
+            require(W, torch.float32, 'embed weight'); require(b, torch.float32, 'embed bias')
+            Kg = x2.shape[1]
+            x_f32 = int(x2.dtype == torch.float32)
+            ws = _ws(L.mt_linear_ws_bytes(dt, M, d, Kg, x_f32, 0.0), dev)
+            check(L.mt_linear_fwd(dt, M, d, Kg, ptr(x2), x_f32, ptr(W), ptr(b), ctypes.c_void_p(x0[g].data_ptr()), 1, ACT_NONE, None, 0.0, 0,
+                                  0x5000, ptr(ws), ws.numel(), stream()))
+            xin.append(x2)
+        nws = L.mt_encoder_group_ws_bytes(ctypes.byref(cfg), G)
+        if nws == 0:
+            raise RuntimeError(f'unsupported grouped encoder configuration {cfgd} for {G} x {(B, T, d)}')
+        ws = _ws(nws, dev)
+        y = torch.empty((G, B, T, d), dtype=torch.float32 if y_f32 else torch.bfloat16, device=dev)
+        c_seeds = (ctypes.c_uint64 * G)(*seeds)
+        c_ids = (ctypes.c_int * G)(*[int(i) for i in cfgd['stack_ids']])
+        check(L.mt_encoder_group_fwd(ctypes.byref(cfg), G, c_seeds, c_ids, ptr(flat), ptr(lp), pstride, ptr(x0), ptr(m), ptr(y), ptr(ws),
+                                     ws.numel(), stream()))
+        if need_grad:
+            ctx.save_for_backward(x0, m, ws, flat, lp, *xin, *emb)
+            ctx.cfg, ctx.arena, ctx.G, ctx.seeds, ctx.ids, ctx.pstride = cfg, arena, G, c_seeds, c_ids, pstride
+            ctx.x_need = ctx.needs_input_grad[4:4 + G]
+            ctx.x_shapes = [tuple(x.shape) for x in xs]
+        return tuple(y.unbind(0))
+
+    @staticmethod
+    def backward(ctx, *dys):
+        x0, m, ws, flat, lp, *rest = ctx.saved_tensors
+        G, cfg = ctx.G, ctx.cfg
+        xin, emb = rest[:G], rest[G:]
+        dt = cfg.dtype
+        M, d = cfg.B * cfg.T, cfg.d
+        dev = x0.device
+        want = torch.float32 if cfg.y_f32 else torch.bfloat16
+        # the G output gradients, back to back: in place when they already are one block (MfnFn.backward hands them out that way)
+        step = M * d * (4 if cfg.y_f32 else 2)
+        ok = all(t is not None and t.dtype == want and t.is_contiguous() for t in dys)
+        if ok and all(dys[g].data_ptr() == dys[0].data_ptr() + g * step for g in range(G)):
+            dy = dys[0]
+        else:
+            dy = torch.stack([torch.zeros((cfg.B, cfg.T, d), dtype=want, device=dev) if t is None else t.to(want).reshape(cfg.B, cfg.T, d)
+                              for t in dys])
+        dx = torch.empty_like(x0)
+        g_all = torch.empty(ctx.arena.total, dtype=torch.float32, device=dev)
+        L = lib()
+        check(L.mt_encoder_group_bwd(ctypes.byref(cfg), G, ctx.seeds, ctx.ids, ptr(flat), ptr(lp), ctx.pstride, ptr(x0), ptr(m), ptr(dy),
+                                     ptr(dx), ptr(g_all), ptr(ws), ws.numel(), stream()))
+        emb_grads, in_grads = [], []
+        # one block for the embed gradients, in parameter order: an optimizer arena over the embeds reads it in place
+        eg = torch.empty(sum(t_.numel() for t_ in emb), dtype=torch.float32, device=dev)
+        eo = 0
+        for g in range(G):
+            W = emb[2 * g]
+            Kg = W.shape[1]
+            x_f32 = int(xin[g].dtype == torch.float32)
+            dW = eg[eo:eo + W.numel()].view(W.shape)
+            db = eg[eo + W.numel():eo + W.numel() + d]
+            eo += W.numel() + d
+            dxin = torch.empty((M, Kg), dtype=torch.float32 if dt == MT_F32 else torch.bfloat16, device=dev) if ctx.x_need[g] else None
+            wsl = _ws(L.mt_linear_bwd_ws_bytes(dt, M, d, Kg, x_f32, 0.0), dev)
+            check(L.mt_linear_bwd(dt, M, d, Kg, ptr(xin[g]), x_f32, ptr(W), None, 1, ctypes.c_void_p(dx[g].data_ptr()), 1, ACT_NONE, None, 0.0,
+                                  0, 0x5000, ptr(dxin), ptr(dW), ptr(db), ptr(wsl), wsl.numel(), stream()))
+            emb_grads += [dW, db]
+            if dxin is not None:
+                dxin = dxin.view(ctx.x_shapes[g])
+                if x_f32 and dxin.dtype != torch.float32:
+                    dxin = dxin.float()
+            in_grads.append(dxin)
+        return (None, None, None, None, *in_grads, *emb_grads, *ctx.arena.grad_views(g_all))
+
+
+def encoder_stack_group(xs, mask, embeds, arena, cfgd):
+    """xs: G raw inputs [B,T,K_g]; embeds: G nn.Linear modules; arena: the group arena (stack-major).  Returns G tensors [B,T,d]."""
+    G = len(xs)
+    emb = []
+    for e in embeds:
+        emb += [e.weight, e.bias]
+    return _apply(EncoderGroupFn, mask, arena, cfgd, G, *xs, *emb, *arena.params)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -517,7 +650,11 @@ class MfnFn(torch.autograd.Function):
         dout = dout if dout.is_contiguous() else dout.contiguous()
         if dout.dtype != torch.float32:
             dout = dout.float()
-        dxs = [torch.empty_like(x) if need else None for x, need in zip(xs, ctx.x_need)]
+        if all(ctx.x_need) and all(x.shape == xs[0].shape and x.dtype == xs[0].dtype for x in xs):
+            # one block for all modalities: the grouped encoder backward reads it in place (no stacking copy)
+            dxs = list(torch.empty((n_mods,) + tuple(xs[0].shape), dtype=xs[0].dtype, device=dev).unbind(0))
+        else:
+            dxs = [torch.empty_like(x) if need else None for x, need in zip(xs, ctx.x_need)]
         dxp = (ctypes.c_void_p * n_mods)(*[None if d is None else d.data_ptr() for d in dxs])
         xp = (ctypes.c_void_p * n_mods)(*[x.data_ptr() for x in xs])
         if ctx.t_major:

@@ -309,6 +309,28 @@ class MultiTransformer(nn.Module):
         self.device = _pick_device(device)
         self.to(self.device)
 
+    def group_arena(self):
+        """One arena over the parameters of ALL modality stacks (stack-major), used by the grouped call; None when the stacks differ."""
+        if getattr(self, '_group_arena', None) is None:
+            encs = [self.transformer[m] for m in self.mods]
+            per = [e._canonical_params() for e in encs]
+            n = [sum(p.numel() for p in ps) for ps in per]
+            if len(set(n)) != 1 or n[0] % 8 != 0:
+                return None
+            self._group_arena = K.Arena([p for ps in per for p in ps])
+        return self._group_arena
+
+    def _groupable(self, inputs):
+        if not (K.grouped_stacks() and self.use_encoder and 2 <= len(self.mods) <= 4 and inputs[self.mods[0]].is_cuda):
+            return False
+        encs = [self.transformer[m] for m in self.mods]
+        if not all(e._fusable() for e in encs):
+            return False
+        sig = {(e.layers[0].size, e.layers[0].self_attn.h, e.layers[0].feed_forward.w_1.out_features, len(e.layers),
+                e.layers[0].sublayer[0].dropout.p, e.out_fp32, e.training) for e in encs}
+        shapes = {tuple(inputs[m].shape[:2]) for m in self.mods}
+        return len(sig) == 1 and len(shapes) == 1 and self.group_arena() is not None
+
     def _stack(self, mod, inputs, mask):
         e = self.embed[mod]
         x = K.linear(inputs[mod], e.weight, e.bias, out_f32=self.use_encoder)
@@ -317,6 +339,18 @@ class MultiTransformer(nn.Module):
         return x
 
     def forward(self, inputs, mask, lengths, tgt_init=0.5, target=None):
+        if self._groupable(inputs):
+            # the stacks have the same shape: ONE grouped call (embeds + encoders), one launch per projection / LayerNorm / weight
+            # gradient for all modalities, instead of one call per modality
+            e0 = self.transformer[self.mods[0]]
+            l0 = e0.layers[0]
+            cfgd = dict(h=l0.self_attn.h, dff=l0.feed_forward.w_1.out_features, n_layers=len(e0.layers),
+                        p_drop=l0.sublayer[0].dropout.p if e0.training else 0.0,
+                        stack_ids=[self.transformer[m].stack_id for m in self.mods])
+            if e0.out_fp32 is not None:
+                cfgd['y_f32'] = bool(e0.out_fp32)
+            xs = K.encoder_stack_group([inputs[m] for m in self.mods], mask, [self.embed[m] for m in self.mods], self.group_arena(), cfgd)
+            return self.mfn._run(list(xs), mask, t_major=False)
         if K.parallel_stacks() and self.use_encoder and len(self.mods) > 1 and inputs[self.mods[0]].is_cuda:
             # the modality stacks are independent until the MFN: run them on side streams so the prologue / tail of one
             # stack's kernels overlaps the others' (autograd replays each stack's backward on the same stream); under CUDA

@@ -16,15 +16,21 @@ from . import functional as K
 def _arenas_of(model):
     seen, out = set(), []
     for m in model.modules():
-        for getter in ('arena',):
+        for getter in ('arena', 'group_arena'):
             if hasattr(m, getter) and callable(getattr(m, getter)):
+                if getter == 'group_arena' and not getattr(m, 'use_encoder', True):
+                    continue
                 a = getattr(m, getter)()
-                if id(a) not in seen:
+                if a is not None and id(a) not in seen:
                     seen.add(id(a)); out.append(a)
         a = getattr(m, '_dec_arena', None)
         if a is not None and id(a) not in seen:
             seen.add(id(a)); out.append(a)
-    return out
+    # the same parameters can sit in a per-stack arena AND in the group arena of MultiTransformer; only the arena whose flat buffer the
+    # parameters currently live in (the one the last forward bound) owns them
+    bound = [a for a in out if a.bound()]
+    owned = {id(p) for a in bound for p in a.params}
+    return [a for a in out if a.bound() or not all(id(p) in owned for p in a.params)]
 
 
 def shard_batch(inputs, mask, target, lengths, rank, world):

@@ -10,20 +10,22 @@ L = _lib.lib()
 dev = 'cuda:0'
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 only = sys.argv[2].split(',') if len(sys.argv) > 2 else None
+for a in sys.argv[3:]:
+    if a.startswith('tune'):
+        k, v = a[4:].split('=')
+        L.mt_tune(int(k), int(v))
 G, Mg = 3, 32768
 rows = G * Mg
 HBM = 6549.4
 # name, N, K, b_kmajor, c_f32, bias, act, p, gate, res, colsum, ln
 cases = [('qkv', 768, 256, 1, 0, 1, 0, 0.0, 0, 0, 0, 0),
          ('oproj', 256, 256, 1, 1, 1, 0, 0.1, 0, 1, 0, 0),
-         ('oproj+ln', 256, 256, 1, 1, 1, 0, 0.1, 0, 1, 0, 1),
          ('ffn1', 128, 256, 1, 0, 1, 1, 0.1, 0, 0, 0, 0),
          ('ffn2', 256, 128, 1, 1, 1, 0, 0.1, 0, 1, 0, 0),
          ('ffn2+ln', 256, 128, 1, 1, 1, 0, 0.1, 0, 1, 0, 1),
          ('dgrad_w2', 128, 256, 0, 0, 0, 0, 0.0, 1, 0, 1, 0),
          ('dgrad_w1', 256, 128, 0, 0, 0, 0, 0.0, 0, 0, 0, 0),
-         ('dgrad_o', 256, 256, 0, 0, 0, 0, 0.0, 0, 0, 0, 0),
-         ('dgrad_qkv', 256, 768, 0, 0, 0, 0, 0.0, 0, 0, 0, 0)]
+         ('dgrad_o', 256, 256, 0, 0, 0, 0, 0.0, 0, 0, 0, 0)]
 out = {}
 nbuf = 3
 for (name, N, K, bkm, cf, bias, act, p, gate, res, colsum, ln) in cases:
@@ -72,3 +74,28 @@ for (name, N, K, bkm, cf, bias, act, p, gate, res, colsum, ln) in cases:
 os.makedirs('gpurun_out', exist_ok=True)
 if not only:
     json.dump(out, open('gpurun_out/gemm_rs_probe.json', 'w'), indent=1)
+
+# per-tile timeline of CTA 0 (clock64): where a tile's time goes
+if only and 'trace' in sys.argv[3:]:
+    for (name, N, K, bkm, cf, bias, act, p, gate, res, colsum, ln) in cases:
+        if name not in only:
+            continue
+        tb = torch.zeros(512, dtype=torch.int64, device=dev)
+        A = torch.randn(rows, K, device=dev).bfloat16(); W = (torch.randn(G, N, K, device=dev) / K ** 0.5).bfloat16()
+        C = torch.empty(rows, N, device=dev, dtype=torch.float32 if cf else torch.bfloat16)
+        b = torch.randn(G, N, device=dev) if bias else None
+        r = torch.randn(rows, N, device=dev) if res else None
+        gt = torch.randn(rows, N, device=dev).bfloat16() if gate else None
+        cs = torch.zeros(G, N, device=dev) if colsum else None
+        L.mt_gemm_rs_trace(_lib.ptr(tb))
+        _lib.check(L.mt_gemm_rs(G, Mg, N, K, _lib.ptr(A), _lib.ptr(W), bkm, _lib.ptr(C), cf, _lib.ptr(b), act, p, 5, 8, _lib.ptr(gt), 1.1, _lib.ptr(r),
+                                _lib.ptr(cs), None, None, None, _lib.stream()))
+        torch.cuda.synchronize()
+        L.mt_gemm_rs_trace(None)
+        t = tb.cpu().view(32, 16)
+        t0 = int(t[0, 0])
+        print('trace', name, '(cycles since first TMA issue): issue kb0-3 | landed kb0-3 | acc free | epi0 start end | epi1 start end')
+        for i in range(20):
+            if int(t[i, 0]) == 0:
+                break
+            print(i, [int(x) - t0 for x in t[i, :13]])
