@@ -336,6 +336,40 @@ int check_shape(int B, int T_, int d, int h) {
 
 static int g_attn_force_ffma = 0;
 
+// G stacks back to back in one call: one launch on the tcgen05 engine, one call per stack otherwise
+int mt_attn_group_fwd_run(int dtype, int G, int B, int T_, int d, int h, const void* qkv, const float* mask, void* out, float* lse,
+                          const DropCfg* drops, cudaStream_t st, const int* klen) {
+  MT_TRY(check_shape(B, T_, d, h));
+  if (!qkv || !out || G < 1 || G > 4) return MT_ERR_ARG;
+  if (G > 1 && dtype == MT_BF16 && !g_attn_force_ffma && !g_mt_attn_no_tc && !mt_attn_force_tiled_on() && mt_attn_tc_supported(B, T_, d, h) &&
+      !(((uintptr_t)qkv | (uintptr_t)out) & 15)) {
+    const int rc = mt_attn_tc_fwd_run(B, T_, d, h, qkv, mask, out, lse, drops[0], st, klen, G, drops);
+    if (rc != MT_ERR_UNSUPPORTED) return rc;
+  }
+  const size_t es = dtype == MT_BF16 ? 2 : 4, M = (size_t)B * T_;
+  for (int g = 0; g < G; ++g)
+    MT_TRY(mt_attn_fwd_run(dtype, B, T_, d, h, (const char*)qkv + g * M * 3 * d * es, mask, (char*)out + g * M * d * es,
+                           lse ? lse + (size_t)g * B * h * T_ : nullptr, drops[g], st, klen));
+  return MT_OK;
+}
+
+int mt_attn_group_bwd_run(int dtype, int G, int B, int T_, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse,
+                          const void* dout, void* dqkv, const DropCfg* drops, float* Dws, cudaStream_t st, float* dbias, size_t dbias_gstride) {
+  MT_TRY(check_shape(B, T_, d, h));
+  if (!qkv || !out || !lse || !dout || !dqkv || !Dws || G < 1 || G > 4) return MT_ERR_ARG;
+  if (G > 1 && dtype == MT_BF16 && dbias && h <= 8 && !g_attn_force_ffma && !g_mt_attn_no_tc && !mt_attn_force_tiled_on() &&
+      mt_attn_tc_supported(B, T_, d, h) && !(((uintptr_t)qkv | (uintptr_t)out | (uintptr_t)dout | (uintptr_t)dqkv | (uintptr_t)Dws) & 15)) {
+    const int rc = mt_attn_tc_bwd_run(B, T_, d, h, qkv, mask, out, lse, dout, dqkv, drops[0], dbias, Dws, st, G, drops, dbias_gstride);
+    if (rc != MT_ERR_UNSUPPORTED) return rc;
+  }
+  const size_t es = dtype == MT_BF16 ? 2 : 4, M = (size_t)B * T_;
+  for (int g = 0; g < G; ++g)
+    MT_TRY(mt_attn_bwd_run(dtype, B, T_, d, h, (const char*)qkv + g * M * 3 * d * es, mask, (const char*)out + g * M * d * es,
+                           lse + (size_t)g * B * h * T_, (const char*)dout + g * M * d * es, (char*)dqkv + g * M * 3 * d * es, drops[g],
+                           Dws + (size_t)g * mt_attn_bwd_ws_floats(B, T_, h), st, dbias ? dbias + g * dbias_gstride : nullptr));
+  return MT_OK;
+}
+
 int mt_attn_fwd_run(int dtype, int B, int T_, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop,
                     cudaStream_t st, const int* klen) {
   MT_TRY(check_shape(B, T_, d, h));

@@ -34,15 +34,31 @@ constexpr float LN2 = 0.6931471805599453f;
 // ------------------------------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------------------------------
+// Grouped launches (G modality stacks back to back, B narratives each): a CTA is pinned to ONE group -- blockIdx % G -- and walks that
+// group's (narrative, head pair) items, so the dropout key, the mask / key-length rows (shared by the groups) and the bias-gradient block
+// are fixed per CTA; global narrative index g * B + b addresses qkv / out / lse / aux, the LOCAL b the mask and the dropout stream.
+constexpr int MAXG = 4;
 struct FwdArgs {
-  int B, T, d, h, n_items;
+  int B, T, d, h, G;      // B = narratives per group
   float scale_log2;
   const float* mask;
   bf16* out;
   float* lse;
   const int* klen;
-  DropCfg drop;
+  DropCfg drop[MAXG];
 };
+struct ItemWalk {          // items of this CTA: global item = base + it * step, it < n
+  int grp, base, step, n;
+};
+__device__ __forceinline__ ItemWalk item_walk(int G, int B, int hp_count) {
+  ItemWalk w;
+  const int items_g = B * hp_count, cpg = (int)gridDim.x / G, rank = (int)blockIdx.x / G;
+  w.grp = (int)blockIdx.x % G;
+  w.base = w.grp * items_g + rank;
+  w.step = cpg;
+  w.n = rank < items_g ? (items_g - 1 - rank) / cpg + 1 : 0;
+  return w;
+}
 
 constexpr int FWD_NT = 320;                  // warps 0-3 / 4-7: head 0 / 1 of the pair, warp 8: TMA, warp 9: MMA issue + TMEM
 constexpr int FWD_STAGES = 2;
@@ -66,6 +82,7 @@ __global__ void __launch_bounds__(FWD_NT, 2) attn_tc_fwd_kernel(const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int hp_count = a.h >> 1;
+  const ItemWalk iw = item_walk(a.G, a.B, hp_count);
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&map_qkv);
     for (int s = 0; s < FWD_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -82,7 +99,8 @@ __global__ void __launch_bounds__(FWD_NT, 2) attn_tc_fwd_kernel(const __grid_con
     // ===== TMA producer: Q | K | V boxes of the item's head pair =====
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+      for (int it = 0; it < iw.n; ++it) {
+        const int item = iw.base + it * iw.step;
         const int b = item / hp_count, hp = item % hp_count;
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* sb = stage_base + stage * FWD_STAGE_BYTES;
@@ -98,8 +116,7 @@ __global__ void __launch_bounds__(FWD_NT, 2) attn_tc_fwd_kernel(const __grid_con
       const uint32_t idesc_s = make_idesc(TM, TM, 0, 0);
       const uint32_t idesc_o = make_idesc(TM, HD, 0, 1);
       int stage = 0; uint32_t phase = 0;
-      int it = 0;
-      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++it) {
+      for (int it = 0; it < iw.n; ++it) {
         const uint32_t par = (uint32_t)it & 1u;
         const uint32_t sq = smem_u32(stage_base + stage * FWD_STAGE_BYTES), sk = sq + TILE_BYTES, sv = sk + TILE_BYTES;
         mbar_wait(&full[stage], phase);
@@ -130,22 +147,23 @@ __global__ void __launch_bounds__(FWD_NT, 2) attn_tc_fwd_kernel(const __grid_con
     }
   } else {
     // ===== softmax / epilogue: warp group w owns head 2 hp + w, thread = query row =====
-    const DropCfg drop = mt_drop_resolve(a.drop);
+    const DropCfg drop = mt_drop_resolve(a.drop[iw.grp]);
     const int w = warp >> 2, r = threadIdx.x & 127;
     const uint32_t t_s = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(w * 128);
     const uint32_t P2 = (uint32_t)(a.T + 1) >> 1;
     const uint32_t thr_hi = (drop.thresh >> 16) << 16;
     const bool dropping = drop.thresh != 0u;
-    int it = 0;
-    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++it) {
+    for (int it = 0; it < iw.n; ++it) {
       const uint32_t par = (uint32_t)it & 1u;
-      const int b = item / hp_count, hd = 2 * (item % hp_count) + w;
+      const int item = iw.base + it * iw.step;
+      const int b = item / hp_count, hd = 2 * (item % hp_count) + w;      // b: global narrative (group * B + local)
+      const int bl = b - iw.grp * a.B;
       const bool row_ok = FULL || r < a.T;
-      const bool masked = a.mask != nullptr && row_ok && a.mask[(size_t)b * a.T + r] == 0.f;
+      const bool masked = a.mask != nullptr && row_ok && a.mask[(size_t)bl * a.T + r] == 0.f;
       const float rs = masked ? 0.f : a.scale_log2;        // masked query rows: every score becomes the same constant
-      const int Tk = (!FULL && a.klen != nullptr) ? max(1, min(a.klen[b], a.T)) : a.T;
+      const int Tk = (!FULL && a.klen != nullptr) ? max(1, min(a.klen[bl], a.T)) : a.T;
       const uint32_t bh = (uint32_t)(b * a.h + hd);
-      const uint32_t dbase = (bh * (uint32_t)a.T + (uint32_t)min(r, a.T - 1)) * P2;      // pair-index base of this row (fits: see host check)
+      const uint32_t dbase = ((uint32_t)(bl * a.h + hd) * (uint32_t)a.T + (uint32_t)min(r, a.T - 1)) * P2;      // pair-index base of this row, group-local (fits: see host check)
       mbar_wait(&s_full[w], par);
       fence_after();
       float mraw = -INFINITY;
@@ -230,11 +248,12 @@ __global__ void __launch_bounds__(FWD_NT, 2) attn_tc_fwd_kernel(const __grid_con
 // backward
 // ------------------------------------------------------------------------------------------------------------------------------------
 struct BwdArgs {
-  int B, T, d, h, n_items;
-  const float* aux;       // [B][h][4][128]: lse * log2e | D = rowsum(dO . O) | score scale * log2e (0: masked row) | score-gradient scale (0: masked)
+  int B, T, d, h, G;      // B = narratives per group
+  const float* aux;       // [G*B][h][4][128]: lse * log2e | D = rowsum(dO . O) | score scale * log2e (0: masked row) | score-gradient scale (0: masked)
   bf16* dqkv;
-  float* dbias;           // optional fp32 [3d], accumulated
-  DropCfg drop;
+  float* dbias;           // optional fp32 [3d] per group (dbias_gstride floats apart), accumulated
+  size_t dbias_gstride;
+  DropCfg drop[MAXG];
 };
 
 constexpr int BWD_NT = 576;                                             // warps 0-15 compute, 16 TMA, 17 MMA issue + TMEM
@@ -245,10 +264,10 @@ constexpr int BWD_DS_BYTES = TM * TM * 2;                               // dS of
 constexpr int BWD_SMEM = BWD_STAGES * BWD_STAGE_BYTES + 2 * BWD_DS_BYTES + 256 + 1024;
 
 // aux[b][hd][k][q] (row stride 128 whatever T is), see BwdArgs; one thread per (b, hd, q), q fastest
-__global__ void attn_tc_prep_kernel(int B, int T, int d, int h, const bf16* __restrict__ out, const bf16* __restrict__ dout,
+__global__ void attn_tc_prep_kernel(int B, int Bg, int T, int d, int h, const bf16* __restrict__ out, const bf16* __restrict__ dout,
                                     const float* __restrict__ lse, const float* __restrict__ mask, float* __restrict__ aux, float scale) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)B * h * T) return;
+  if (idx >= (long long)B * h * T) return;      // B = all narratives of the launch, Bg = per group (the mask is shared by the groups)
   const int q = (int)(idx % T);
   const long long bh = idx / T;
   const int b = (int)(bh / h), hd = (int)(bh % h);
@@ -267,7 +286,7 @@ __global__ void attn_tc_prep_kernel(int B, int T, int d, int h, const bf16* __re
       D += of.x * gf.x + of.y * gf.y;
     }
   }
-  const bool masked = mask != nullptr && mask[row] == 0.f;
+  const bool masked = mask != nullptr && mask[(size_t)(b % Bg) * T + q] == 0.f;
   float* a = aux + (size_t)bh * 4 * TM;
   a[q] = lse[bh * T + q] * LOG2E;
   a[TM + q] = D;
@@ -312,13 +331,14 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
   __syncthreads();
   fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int n_my = ((int)blockIdx.x < a.n_items) ? (a.n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const ItemWalk iw = item_walk(a.G, a.B, hp_count);
+  const int n_my = iw.n;
 
   if (warp == 16) {
     // ===== TMA producer =====
     if (lane == 0) {
       for (int it = 0; it < n_my; ++it) {
-        const int item = (int)blockIdx.x + it * (int)gridDim.x;
+        const int item = iw.base + it * iw.step;
         const int b = item / hp_count, hp = item % hp_count;
         const int stage = it & 1;
         mbar_wait(&empty[stage], (((uint32_t)it >> 1) & 1u) ^ 1u);
@@ -395,7 +415,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     }
   } else {
     // ===== compute: warp group g = 2 w + hf: head 2 hp + w, queries [64 hf, 64 hf + 64), thread = key row j =====
-    const DropCfg drop = mt_drop_resolve(a.drop);
+    const DropCfg drop = mt_drop_resolve(a.drop[iw.grp]);
     const int g = warp >> 2, w = g >> 1, hf = g & 1, j = threadIdx.x & 127;
     const uint32_t tw = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(w * 256);
     const uint32_t P2 = (uint32_t)(T + 1) >> 1;
@@ -407,12 +427,12 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     const uint64_t ds2 = pk2(drop.scale, drop.scale);
     for (int it = 0; it < n_my; ++it) {
       const uint32_t par = (uint32_t)it & 1u;
-      const int item = (int)blockIdx.x + it * (int)gridDim.x;
-      const int b = item / hp_count, hp = item % hp_count, hd = 2 * hp + w;
+      const int item = iw.base + it * iw.step;
+      const int b = item / hp_count, hp = item % hp_count, hd = 2 * hp + w;      // b: global narrative (group * B + local)
       const int stage = it & 1;
       const float* ax = reinterpret_cast<const float*>(stage_base + stage * BWD_STAGE_BYTES + 4 * TILE_BYTES) + w * 4 * TM;
       // pair index of (query q, key pair j >> 1) = (bh T + q) P2 + (j >> 1); this lane draws for the queries q + (j & 1)
-      const uint32_t bh = (uint32_t)(b * a.h + hd);
+      const uint32_t bh = (uint32_t)((b - iw.grp * a.B) * a.h + hd);      // group-local: the dropout stream of a stack does not depend on its group slot
       const uint32_t pidx0 = (bh * (uint32_t)T + (uint32_t)(hf * 64) + odd) * P2 + (uint32_t)(j >> 1);
       mbar_wait(&full[stage], ((uint32_t)it >> 1) & 1u);       // aux vectors (the MMA warp waits on the same phase for the tiles)
       mbar_wait(&s_full[w], par);
@@ -548,7 +568,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     for (int i = threadIdx.x; i < hp_count * 2 * 96; i += BWD_NT) {
       const int hp = i / 192, w = (i / 96) & 1, k = (i % 96) / 32, c = i % 32;
       const float val = s_cs[i];
-      if (val != 0.f) atomicAdd(a.dbias + (size_t)k * a.d + (2 * hp + w) * HD + c, val);
+      if (val != 0.f) atomicAdd(a.dbias + iw.grp * a.dbias_gstride + (size_t)k * a.d + (2 * hp + w) * HD + c, val);
     }
   }
 }
@@ -577,19 +597,21 @@ bool mt_attn_tc_supported(int B, int T, int d, int h) {
 }
 
 int mt_attn_tc_fwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop, cudaStream_t st,
-                       const int* klen) {
-  if (!mt_attn_tc_supported(B, T, d, h)) return MT_ERR_UNSUPPORTED;
+                       const int* klen, int G, const DropCfg* drops) {
+  if (!mt_attn_tc_supported(B, T, d, h) || G < 1 || G > MAXG || (long long)G * B * T > 0x7fffffffLL / (3LL * d)) return MT_ERR_UNSUPPORTED;
   if (((uintptr_t)qkv & 15) || ((uintptr_t)out & 15)) return MT_ERR_ALIGN;
   CUtensorMap map;
-  MT_TRY(make_map_2d(&map, qkv, (uint64_t)3 * d, (uint64_t)B * T, (uint64_t)3 * d, 64, TM));
+  MT_TRY(make_map_2d(&map, qkv, (uint64_t)3 * d, (uint64_t)G * B * T, (uint64_t)3 * d, 64, TM));
   FwdArgs a;
-  a.B = B; a.T = T; a.d = d; a.h = h; a.n_items = B * (h / 2);
+  a.B = B; a.T = T; a.d = d; a.h = h; a.G = G;
   a.scale_log2 = LOG2E / sqrtf((float)HD);
-  a.mask = mask; a.out = (bf16*)out; a.lse = lse; a.klen = klen; a.drop = drop;
+  a.mask = mask; a.out = (bf16*)out; a.lse = lse; a.klen = klen;
+  for (int i = 0; i < MAXG; ++i) a.drop[i] = drops && i < G ? drops[i] : drop;
   static MtPerDeviceOnce attr_full, attr_part;
-  const int slots = 2 * num_sms();
-  const int grid = a.n_items < slots ? a.n_items : slots;
-  mt_prof_work(4.0 * B * (double)T * T * d, (double)B * T * d * 4.0 * 2.0);
+  const int slots = 2 * num_sms(), n_items = B * (h / 2);
+  const int cpg = n_items < slots / G ? n_items : slots / G;      // CTAs per group
+  const int grid = cpg * G;
+  mt_prof_work(4.0 * G * B * (double)T * T * d, (double)G * B * T * d * 4.0 * 2.0);
   if (T == TM && !klen) {
     MT_TRY(set_smem_attr(attn_tc_fwd_kernel<true>, FWD_SMEM, attr_full));
     attn_tc_fwd_kernel<true><<<grid, FWD_NT, FWD_SMEM, st>>>(map, a);
@@ -602,27 +624,29 @@ int mt_attn_tc_fwd_run(int B, int T, int d, int h, const void* qkv, const float*
 }
 
 int mt_attn_tc_bwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse, const void* dout,
-                       void* dqkv, DropCfg drop, float* dbias, float* aux, cudaStream_t st) {
-  if (!mt_attn_tc_supported(B, T, d, h)) return MT_ERR_UNSUPPORTED;
+                       void* dqkv, DropCfg drop, float* dbias, float* aux, cudaStream_t st, int G, const DropCfg* drops, size_t dbias_gstride) {
+  if (!mt_attn_tc_supported(B, T, d, h) || G < 1 || G > MAXG || (long long)G * B * T > 0x7fffffffLL / (3LL * d)) return MT_ERR_UNSUPPORTED;
   if (dbias != nullptr && h > 8) return MT_ERR_UNSUPPORTED;
   if (!aux || ((uintptr_t)aux & 15) || ((uintptr_t)qkv & 15) || ((uintptr_t)dout & 15) || ((uintptr_t)dqkv & 15) || ((uintptr_t)out & 15))
     return MT_ERR_ALIGN;
   const float scale = 1.0f / sqrtf((float)HD);
   {
-    const long long n = (long long)B * h * T;
-    attn_tc_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(B, T, d, h, (const bf16*)out, (const bf16*)dout, lse, mask, aux, scale);
+    const long long n = (long long)G * B * h * T;
+    attn_tc_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(G * B, B, T, d, h, (const bf16*)out, (const bf16*)dout, lse, mask, aux, scale);
     MT_LAUNCH_CHECK();
   }
   CUtensorMap map_qkv, map_do;
-  MT_TRY(make_map_2d(&map_qkv, qkv, (uint64_t)3 * d, (uint64_t)B * T, (uint64_t)3 * d, 64, TM));
-  MT_TRY(make_map_2d(&map_do, dout, (uint64_t)d, (uint64_t)B * T, (uint64_t)d, 64, TM));
+  MT_TRY(make_map_2d(&map_qkv, qkv, (uint64_t)3 * d, (uint64_t)G * B * T, (uint64_t)3 * d, 64, TM));
+  MT_TRY(make_map_2d(&map_do, dout, (uint64_t)d, (uint64_t)G * B * T, (uint64_t)d, 64, TM));
   BwdArgs a;
-  a.B = B; a.T = T; a.d = d; a.h = h; a.n_items = B * (h / 2);
-  a.aux = aux; a.dqkv = (bf16*)dqkv; a.dbias = dbias; a.drop = drop;
+  a.B = B; a.T = T; a.d = d; a.h = h; a.G = G;
+  a.aux = aux; a.dqkv = (bf16*)dqkv; a.dbias = dbias; a.dbias_gstride = dbias_gstride;
+  for (int i = 0; i < MAXG; ++i) a.drop[i] = drops && i < G ? drops[i] : drop;
   static MtPerDeviceOnce attr_full, attr_part;
-  const int sms = num_sms();
-  const int grid = a.n_items < sms ? a.n_items : sms;
-  mt_prof_work(10.0 * B * (double)T * T * d, (double)B * T * d * 8.0 * 2.0);
+  const int sms = num_sms(), n_items = B * (h / 2);
+  const int cpg = n_items < sms / G ? n_items : sms / G;
+  const int grid = cpg * G;
+  mt_prof_work(10.0 * G * B * (double)T * T * d, (double)G * B * T * d * 8.0 * 2.0);
   if (T == TM) {
     MT_TRY(set_smem_attr(attn_tc_bwd_kernel<true>, BWD_SMEM, attr_full));
     attn_tc_bwd_kernel<true><<<grid, BWD_NT, BWD_SMEM, st>>>(map_qkv, map_do, a);

@@ -45,6 +45,7 @@ extern int g_mt_tune[8];
 #define MT_TUNE_LN_SHARE 2
 #define MT_TUNE_PDL 3          // [3] programmatic dependent launch of the tcgen05 GEMM (prologue overlaps the previous kernel's tail)
 #define MT_TUNE_NO_RS 5        // [5] != 0: the encoder's projections skip the row-stream engine (A/B against the streaming engine)
+#define MT_TUNE_NO_BIG_TILES 7 // [7] != 0: no 256-row / 256-wide tiles for the L2-bound GEMMs (split-K wgrads, long-K dgrad)
 #define MT_TUNE_NO_LNFUSE 6    // [6] != 0: no LayerNorm fused into the FFN output projection's epilogue
 
 // one-time-per-DEVICE guard for cudaFuncSetAttribute-style opt-ins (a process may drive several GPUs): true the first time the

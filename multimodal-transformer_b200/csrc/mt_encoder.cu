@@ -257,11 +257,10 @@ int encoder_fwd_impl(const MtEncoderCfg& c, const Groups& gr, const float* param
     // sublayer 0: x + dropout(self_attn(LN(x)))
     if (!u_ready) MT_TRY(mt_ln_fwd_run(M, d, xin, params + base + P.ln1_a, params + base + P.ln1_b, 1e-6f, b.u, lp, st, G, gr.pstride));
     MT_TRY(pj.run(false, 3 * d, d, b.u, base + P.w_qkv, b.qkv, !lp, (long long)(base + P.b_qkv), MT_ACT_NONE, l, -1, nullptr, 1.f, nullptr, -1));
-    for (int g = 0; g < G; ++g) {
-      const size_t ro = (size_t)g * M;
-      MT_TRY(mt_attn_fwd_run(c.dtype, c.B, c.T, d, c.h, (const char*)b.qkv + ro * 3 * d * es, mask, (char*)b.att + ro * d * es,
-                             b.lse + (size_t)g * c.B * c.h * c.T,
-                             mt_make_drop(c.p_drop, gr.seed[g], mt_enc_site(gr.stack_id[g], l, MT_SITE_ATTN_P)), st, c.key_len));
+    {
+      DropCfg ad[MT_RS_MAX_GROUPS];
+      for (int g = 0; g < G; ++g) ad[g] = mt_make_drop(c.p_drop, gr.seed[g], mt_enc_site(gr.stack_id[g], l, MT_SITE_ATTN_P));
+      MT_TRY(mt_attn_group_fwd_run(c.dtype, G, c.B, c.T, d, c.h, b.qkv, mask, b.att, b.lse, ad, st, c.key_len));
     }
     MT_TRY(pj.run(false, d, d, b.att, base + P.w_o, b.xp, true, (long long)(base + P.b_o), MT_ACT_NONE, l, MT_SITE_SUB0, nullptr, 1.f, xin, -1));
     // sublayer 1: x + dropout(w_2(dropout(relu(w_1(LN(x))))))
@@ -347,12 +346,11 @@ int encoder_bwd_impl(const MtEncoderCfg& c, const Groups& gr, const float* param
     // ---- attention sublayer: xp = x + drop(att w_o + b_o); w.dact = drop' . g_nxt and db_o are already there ---------
     MT_TRY(pj.wgrad(d, d, w.dact, b.att, base + P.w_o));
     MT_TRY(pj.run(true, d, d, w.dact, base + P.w_o, w.dact2, !lp, -1, MT_ACT_NONE, l, -1, nullptr, 1.f, nullptr, -1));
-    for (int g = 0; g < G; ++g) {
-      const size_t ro = (size_t)g * M;
-      MT_TRY(mt_attn_bwd_run(c.dtype, c.B, c.T, d, c.h, (const char*)b.qkv + ro * 3 * d * es, mask, (const char*)b.att + ro * d * es,
-                             b.lse + (size_t)g * c.B * c.h * c.T, (const char*)w.dact2 + ro * d * es, (char*)w.dqkv + ro * 3 * d * es,
-                             mt_make_drop(p, gr.seed[g], mt_enc_site(gr.stack_id[g], l, MT_SITE_ATTN_P)),
-                             w.Dws + (size_t)g * mt_attn_bwd_ws_floats(c.B, c.T, c.h), st, grads + g * gr.pstride + base + P.b_qkv));
+    {
+      DropCfg ad[MT_RS_MAX_GROUPS];
+      for (int g = 0; g < G; ++g) ad[g] = mt_make_drop(p, gr.seed[g], mt_enc_site(gr.stack_id[g], l, MT_SITE_ATTN_P));
+      MT_TRY(mt_attn_group_bwd_run(c.dtype, G, c.B, c.T, d, c.h, b.qkv, mask, b.att, b.lse, w.dact2, w.dqkv, ad, w.Dws, st,
+                                   grads + base + P.b_qkv, gr.pstride));
     }
     MT_TRY(pj.wgrad(3 * d, d, w.dqkv, b.u, base + P.w_qkv));
     MT_TRY(pj.run(true, d, 3 * d, w.dqkv, base + P.w_qkv, w.dact2, !lp, -1, MT_ACT_NONE, l, -1, nullptr, 1.f, nullptr, -1));

@@ -57,7 +57,7 @@ struct Cfg {
   static constexpr int W_BYTES = KB * BN * 128;
   static constexpr int AUX_BYTES = 1024 + 4 * BN * 4 + 4096;      // barriers | bias | column sums | LayerNorm a_2, b_2 | row moments
   static constexpr int BOXES = (SMEM_LIMIT - 1024 - AUX_BYTES - W_BYTES) / BOX;      // 16 KB boxes left beside the resident weights
-  static constexpr bool TIGHT = BOXES < 7;                        // the 128 KB weight slices
+  static constexpr bool TIGHT = BOXES < 8;                        // the 96 / 128 KB weight slices
   static constexpr int NSO = (TIGHT || (F & (R_RES | R_GATE))) ? 1 : 2;   // output staging boxes PER epilogue warp group
   static constexpr int NSR = (F & R_RES) ? 4 : 0;                 // residual ring (fp32 [128 x 32] boxes)
   static constexpr int NSG = (F & R_GATE) ? 2 : 0;                // gate ring (bf16 [128 x 64] boxes)
@@ -68,6 +68,7 @@ struct Cfg {
   static constexpr int PAIRS = BN / 64;
   static_assert(NSA >= 2, "no room for the activation ring");
   static_assert(2 * BN <= 512, "two accumulators must fit in TMEM");
+  static constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);      // allocation: a power of two
 };
 
 template <int BN, int KB, uint32_t F>
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(NT, 1) gemm_rs_kernel(const __grid_constant__ 
     for (int s = 0; s < 4; ++s) { mbar_init(&full_r[s], 1); mbar_init(&empty_r[s], 4); mbar_init(&full_g[s], 1); mbar_init(&empty_g[s], 4); }
     mbar_init_fence();
   }
-  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+  if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
   fence_before();
   __syncthreads();
   fence_after();
@@ -414,7 +415,7 @@ __global__ void __launch_bounds__(NT, 1) gemm_rs_kernel(const __grid_constant__ 
   }
   if (warp == 1) {
     fence_after();
-    tmem_dealloc<2 * BN>(tmem_base);
+    tmem_dealloc<C::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -491,6 +492,7 @@ int dispatch(const RsDesc& d, cudaStream_t st, bool probe_only) {
   if (d.N == (N_) && d.K == (K_) && f == (uint32_t)(F_)) return probe_only ? MT_OK : launch<BN_, (K_) / 64, (uint32_t)(F_)>(d, st)
   // forward
   if (g_mt_tune[4] == 1) { RS_PROBE(768, 256, 128, R_BIAS); }              // experiment: 6 narrow slices, deep ring
+  if (g_mt_tune[4] == 2) { RS_PROBE(768, 256, 192, R_BIAS); }              // experiment: 4 slices of 192 columns
   RS_PROBE(768, 256, 256, R_BIAS);                                         // QKV projection
   RS_PROBE(256, 256, 128, R_BIAS | R_DROP | R_RES | R_CF32);               // output projection, train
   RS_PROBE(256, 256, 128, R_BIAS | R_RES | R_CF32);                        // output projection, eval

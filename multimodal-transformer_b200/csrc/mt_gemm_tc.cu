@@ -30,9 +30,11 @@ constexpr int BK = 64;                 // bf16 elements per k-block = one 128-by
 // epilogue warps = 4 TMEM lane quarters x (2 | 4) column slices, each slice drained in passes of PW columns through a staging
 // buffer.  The 256-wide tile uses 16 warps (the epilogue, not the MMA issue loop, bounded it with 8) and 16-column passes so
 // that the staging still fits next to the 128 KB resident weight slice.
-template <int BN> struct EpiCfg {
-  static constexpr int EW = BN > 128 ? 16 : 8;
-  static constexpr int PW = BN > 128 ? 16 : 32;
+// MT = 128-row subtiles of a CTA tile (1 or 2).  MT = 2: a 256-row tile whose two tcgen05.mma per k-step share the B operand -- halves
+// the operand re-reads of the L2-bound shapes (split-K weight gradients, the long-K input gradient of the QKV projection).
+template <int BN, int MT = 1> struct EpiCfg {
+  static constexpr int EW = (BN > 128 && MT == 1) ? 16 : 8;
+  static constexpr int PW = (BN > 128 || MT == 2) ? 16 : 32;
 };
 constexpr int KB_RES = 4;              // weight-resident mode: at most this many k-blocks (K <= 256)
 constexpr int MAX_STAGES = 8;
@@ -137,14 +139,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 
 // OCC = CTAs per SM.  OCC = 2 (two independent pipelines per SM, streaming ring of 2 stages each): the single TMA / MMA issuing
 // threads and the epilogue warps are all latency-bound, so a second resident CTA fills their bubbles.
-template <int BN, int OCC>
+template <int BN, int OCC, int MT = 1>
 struct Smem {
-  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int A_BYTES = MT * BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int RING_BYTES = OCC == 2 ? 2 * (A_BYTES + B_BYTES) : (BN > 128 ? 176 : 160) * 1024;   // resident weights + ring, or ring only
+  static constexpr int RING_BYTES = OCC == 2 ? 2 * (A_BYTES + B_BYTES) : (MT == 2 ? (BN > 128 ? 192 : 144) : (BN > 128 ? 176 : 160)) * 1024;   // resident weights + ring, or ring only
   static constexpr int NS_STREAM = RING_BYTES / (A_BYTES + B_BYTES);                    // 6 (BN = 64) / 5 (128) / 3 (256)
   static constexpr int NS_RES = OCC == 2 ? 1 : (RING_BYTES - KB_RES * B_BYTES) / A_BYTES;   // 8 / 6 / 3 (unused with OCC = 2)
-  static constexpr int EW = EpiCfg<BN>::EW, PW = EpiCfg<BN>::PW;
+  static constexpr int EW = EpiCfg<BN, MT>::EW, PW = EpiCfg<BN, MT>::PW;
+  static constexpr int NACC = 2 * MT * BN <= 512 ? 2 : 1;                               // accumulator buffers in TMEM
+  static constexpr int TMEM_COLS = NACC * MT * BN <= 128 ? 128 : (NACC * MT * BN <= 256 ? 256 : 512);
   static constexpr int THREADS = 64 + 32 * EW;
   static constexpr int EPI_BYTES = EW * 32 * (PW + 4) * 4;                              // per epilogue warp: 32 rows x (PW + 4) floats
   static constexpr int BAR_BYTES = 256;
@@ -188,13 +192,15 @@ __device__ __forceinline__ bool get_work(const TcArgs& g, int i, int& tm, int& t
   return true;
 }
 
-template <int BN, uint32_t F, bool RES, int OCC>
-__global__ void __launch_bounds__(Smem<BN, OCC>::THREADS, OCC)
+template <int BN, uint32_t F, bool RES, int OCC, int MT>
+__global__ void __launch_bounds__(Smem<BN, OCC, MT>::THREADS, OCC)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ TcArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // 1 KB aligned, still a shared-space pointer
-  using S = Smem<BN, OCC>;
+  using S = Smem<BN, OCC, MT>;
   static_assert(!(RES && OCC == 2), "weight-resident mode needs the whole SM");
+  static_assert(!(RES && MT == 2), "weight-resident mode uses 128-row tiles");
+  constexpr int TM_ROWS = MT * BM;
   constexpr int NS = RES ? S::NS_RES : S::NS_STREAM;
   constexpr int SLOT = RES ? S::A_BYTES : S::A_BYTES + S::B_BYTES;
   uint8_t* res_b = smem;                                            // RES: resident weight slice, KB_RES boxes
@@ -221,7 +227,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(S::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -252,7 +258,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       int stage = 0; uint32_t phase = 0;
       for (int i = 0; get_work<RES>(g, i, tm, tn, split, grp); ++i) {
-        const int m0 = tm * BM, n0 = tn * BN;
+        const int m0 = tm * TM_ROWS, n0 = tn * BN;
         const int kbase = grp * g.kb_group;
         const int kb0 = kbase + split * kb_per, kb1 = min(kbase + kb_total, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -264,9 +270,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int k0 = kb * BK;
           if (a_mn) {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &map_a, m0 + 64 * j, k0, &full[stage]);
+            for (int j = 0; j < TM_ROWS / 64; ++j) tma_load_2d(sa + j * (BK * 128), &map_a, m0 + 64 * j, k0, &full[stage]);
           } else {
-            tma_load_2d(sa, &map_a, k0, m0, &full[stage]);
+#pragma unroll
+            for (int j = 0; j < MT; ++j) tma_load_2d(sa + j * (BM * BK * 2), &map_a, k0, m0 + BM * j, &full[stage]);
           }
           if (!RES) {
             uint8_t* sb = sa + S::A_BYTES;
@@ -301,11 +308,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int it = 0; get_work<RES>(g, it, tm, tn, split, grp); ++it) {
         const int kbase = grp * g.kb_group;
         const int kb0 = kbase + split * kb_per, kb1 = min(kbase + kb_total, kb0 + kb_per);
-        const int acc = it & 1;
-        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1;
+        const int acc = it % S::NACC;
+        const uint32_t acc_phase = (uint32_t)(it / S::NACC) & 1;
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * MT * BN);
         if (tracing && it < 64) g.trace[it * 8 + 1] = clock64();
         uint32_t accum = 0u;
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -319,9 +326,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint32_t a_lo = a_lbo | ((sa >> 4) & 0x3FFFu), b_lo = b_lbo | ((sb >> 4) & 0x3FFFu);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + (uint32_t)k * a_kstep);
             const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + (uint32_t)k * b_kstep);
-            tc_mma(tmem_d, ad, bd, idesc, accum);
+#pragma unroll
+            for (int j = 0; j < MT; ++j) {      // the subtiles' A blocks are (BM * BK * 2) bytes apart in either layout; they share B
+              const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + (uint32_t)(j * ((BM * BK * 2) >> 4)) + (uint32_t)k * a_kstep);
+              tc_mma(tmem_d + (uint32_t)(j * BN), ad, bd, idesc, accum);
+            }
             accum = 1u;
           }
           tc_commit(&empty[stage]);                 // ring slot is free once these MMAs have read it
@@ -352,20 +362,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int lr = lane / LPR, lc = (lane % LPR) * 8;
     int tm, tn, split, grp;
     for (int it = 0; get_work<RES>(g, it, tm, tn, split, grp); ++it) {
-      const int m0 = tm * BM;
-      const int acc = it & 1;
-      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1;
+      const int m0 = tm * TM_ROWS;
+      const int acc = it % S::NACC;
+      const uint32_t acc_phase = (uint32_t)(it / S::NACC) & 1;
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const bool tr = g.trace && blockIdx.x == 0 && it < 64 && warp == 2 && lane == 0;
       if (tr) g.trace[it * 8 + 4] = clock64();
-      const int row_base = m0 + q * 32;
 #pragma unroll 1
-      for (int p = 0; p < NP; ++p) {
+      for (int pp = 0; pp < MT * NP; ++pp) {
+        const int sub = pp / NP, p = pp - sub * NP;      // 128-row subtile, column pass
+        const int row_base = m0 + sub * BM + q * 32;
         uint32_t v[PW];
-        if constexpr (PW == 32) tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * HN + p * PW), v);
-        else tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * HN + p * PW), v);
-        if (p == NP - 1) {      // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+        if constexpr (PW == 32) tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + sub) * BN + half * HN + p * PW), v);
+        else tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + sub) * BN + half * HN + p * PW), v);
+        if (pp == MT * NP - 1) {      // all TMEM reads of this accumulator are done: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[acc]);
@@ -523,7 +534,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (HAS(F_COLSUM, g.epi.colsum != nullptr)) for (int i = threadIdx.x; i < g.N; i += blockDim.x) atomicAdd(g.epi.colsum + i, cs_smem[i]);
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(S::TMEM_COLS) : "memory");
   }
 }
 
@@ -575,23 +586,24 @@ int num_sms() {
 unsigned long long* g_trace = nullptr;
 int g_tc_mode = 2;       // 0 = 256-wide tiles where they apply, 1 = one CTA per SM everywhere, 2 = never use the 256-wide tile (default: measured fastest)
 
-template <int BN, uint32_t F, bool RES, int OCC = 1>
+template <int BN, uint32_t F, bool RES, int OCC = 1, int MT = 1>
 int launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& g, int grid, cudaStream_t st) {
   static MtPerDeviceOnce once;
-  if (once.first()) MT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, F, RES, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN, OCC>::TOTAL));
+  static_assert(Smem<BN, OCC, MT>::TOTAL <= 227 * 1024, "shared memory budget");
+  if (once.first()) MT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, F, RES, OCC, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN, OCC, MT>::TOTAL));
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Smem<BN, OCC>::THREADS); cfg.dynamicSmemBytes = Smem<BN, OCC>::TOTAL; cfg.stream = st;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Smem<BN, OCC, MT>::THREADS); cfg.dynamicSmemBytes = Smem<BN, OCC, MT>::TOTAL; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = g_mt_tune[MT_TUNE_PDL] ? 1 : 0;
   cfg.attrs = at; cfg.numAttrs = 1;
-  MT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, F, RES, OCC>, ma, mb, g));
+  MT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, F, RES, OCC, MT>, ma, mb, g));
   MT_LAUNCH_CHECK();
   return MT_OK;
 }
 
 // the feature set a descriptor needs
-template <int BN>
+template <int BN, int MT = 1>
 uint32_t needed_features(const GemmDesc& d, const TcArgs& g) {
   uint32_t f = 0;
   if (g.atomic) f |= F_ATOMIC;
@@ -605,15 +617,15 @@ uint32_t needed_features(const GemmDesc& d, const TcArgs& g) {
   if (d.c_f32) f |= F_CF32;
   if (d.epi.colsum) f |= F_COLSUM;
   if (d.epi.alpha != 1.0f) f |= F_ALPHA;
-  if (d.M % BM != 0 || d.N % BN != 0 || d.ldc % 8 != 0 || (d.epi.gate && d.epi.ldg % 8 != 0)) f |= F_EDGE;
+  if (d.M % (MT * BM) != 0 || d.N % BN != 0 || d.ldc % 8 != 0 || (d.epi.gate && d.epi.ldg % 8 != 0)) f |= F_EDGE;
   return f;
 }
 
-template <int BN, int OCC>
+template <int BN, int OCC, int MT = 1>
 int launch_tc(const GemmDesc& d, cudaStream_t st) {
   TcArgs g;
   g.M = d.M; g.N = d.N; g.K = d.K;
-  g.tiles_m = (d.M + BM - 1) / BM;
+  g.tiles_m = (d.M + MT * BM - 1) / (MT * BM);
   g.tiles_n = (d.N + BN - 1) / BN;
   g.kb_total = (d.K + BK - 1) / BK;
   int splits = 1;
@@ -642,10 +654,18 @@ int launch_tc(const GemmDesc& d, cudaStream_t st) {
   int slots = OCC * num_sms();
   if (g_mt_tune[MT_TUNE_GEMM_SHARE] > 1 && d.split_k <= 1) slots = slots / g_mt_tune[MT_TUNE_GEMM_SHARE];
   const int grid = n_work < slots ? n_work : slots;
-  const uint32_t f = needed_features<BN>(d, g);
+  const uint32_t f = needed_features<BN, MT>(d, g);
   // weight-resident mode: short K, no split, and at least one CTA per column slice
   const bool res = OCC == 1 && g.splits == 1 && g.kb_total <= KB_RES && grid >= g.tiles_n;
-  if constexpr (BN >= 128) {
+  if constexpr (MT == 2) {      // 256-row tiles: the L2-bound shapes only (see mt_gemm_tc_run)
+    switch (f) {
+      case F_ATOMIC | F_CF32: return launch_inst<BN, F_ATOMIC | F_CF32, false, 1, 2>(ma, mb, g, grid, st);
+      case F_ATOMIC | F_CF32 | F_EDGE: return launch_inst<BN, F_ATOMIC | F_CF32 | F_EDGE, false, 1, 2>(ma, mb, g, grid, st);
+      case 0u: return launch_inst<BN, 0u, false, 1, 2>(ma, mb, g, grid, st);
+      case F_EDGE: return launch_inst<BN, F_EDGE, false, 1, 2>(ma, mb, g, grid, st);
+      default: return MT_ERR_UNSUPPORTED;
+    }
+  } else if constexpr (BN >= 128) {
     // instantiations of the encoder / MFN hot path (see mt_encoder.cu): exact feature-set matches only
 #define MT_INST(FEAT)                                                                       \
   case (FEAT):                                                                              \
@@ -665,7 +685,8 @@ int launch_tc(const GemmDesc& d, cudaStream_t st) {
     }
 #undef MT_INST
   }
-  if constexpr (OCC == 2) return launch_inst<BN, F_GENERIC, false, 2>(ma, mb, g, grid, st);
+  if constexpr (MT == 2) return MT_ERR_UNSUPPORTED;
+  else if constexpr (OCC == 2) return launch_inst<BN, F_GENERIC, false, 2>(ma, mb, g, grid, st);
   else return res ? launch_inst<BN, F_GENERIC, true>(ma, mb, g, grid, st) : launch_inst<BN, F_GENERIC, false>(ma, mb, g, grid, st);
 }
 
@@ -707,6 +728,23 @@ int mt_gemm_tc_run(const GemmDesc& d, cudaStream_t st) {
   // latency), so the default is mode 2: split-K wgrads on fewer, longer splits, everything else two CTAs per SM with a
   // streaming ring
   if (g_tc_mode == 0 && wide_ok) return launch_tc<256, 1>(d, st);
+  // L2-bound shapes: every 128 x 128 tile re-reads both operand blocks, and the SM <-> L2 fabric (about 1.8 x HBM) is what these kernels
+  // saturate.  256-row tiles (two MMAs per k-step sharing B) and 256-wide tiles halve those re-reads: split-K weight gradients, and the
+  // long-K input gradient of the QKV projection (K = 768: the weight matrix cannot stay resident, mt_gemm_rs.cu does not take it)
+  if (!g_mt_tune[MT_TUNE_NO_BIG_TILES]) {
+    const bool plain = !d.epi.bias && d.epi.act == MT_ACT_NONE && d.epi.drop.thresh == 0u && !d.epi.gate && !d.epi.residual && !d.epi.rowmask &&
+                       !d.epi.colsum && d.epi.alpha == 1.0f && d.ldc % 8 == 0;
+    // (measured: the big tile pays off for the [768, 256] weight gradient of the QKV projection only -- 58 -> 55 us for three stacks; the
+    // smaller gradients are bound by the burst of fp32 atomics at the end of their few, long work items and lose with fewer, larger tiles)
+    if (d.split_k > 1 && plain && d.N % 256 == 0 && (long long)d.M * d.N >= 768LL * 256 && d.M % 256 == 0) {
+      const int rc = launch_tc<256, 1, 2>(d, st);
+      if (rc != MT_ERR_UNSUPPORTED) return rc;
+    }
+    if (d.split_k <= 1 && plain && !d.c_f32 && d.N == 256 && d.K >= 512 && d.M >= 256 * 64 && d.a_kmajor) {
+      const int rc = launch_tc<256, 1, 2>(d, st);
+      if (rc != MT_ERR_UNSUPPORTED) return rc;
+    }
+  }
   if (d.split_k > 1 && d.N > 64) return launch_tc<128, 1>(d, st);
   if (d.N > 64) return launch_tc<128, 2>(d, st);
   return launch_tc<64, 1>(d, st);

@@ -67,11 +67,15 @@ int mt_attn128_bwd_run(int B, int T, int d, int h, const void* qkv, const float*
 extern int g_mt_attn_no_tc;
 bool mt_attn_force_tiled_on();
 bool mt_attn_tc_supported(int B, int T, int d, int h);
+// G > 1: G modality stacks back to back (B narratives each; qkv / out / lse hold G*B narratives, mask / klen are shared), drops[g] = the
+// dropout stream of group g (pair indices local to the group)
 int mt_attn_tc_fwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop, cudaStream_t st,
-                       const int* klen = nullptr);
+                       const int* klen = nullptr, int G = 1, const DropCfg* drops = nullptr);
 // aux: fp32 workspace of mt_attn_bwd_ws_floats(B, T, h) floats (per-query scalars); dbias as in mt_attn_mma_bwd_run (h <= 8)
+// G > 1 as in mt_attn_tc_fwd_run; aux holds G * mt_attn_bwd_ws_floats(B, T, h) floats, dbias of group g at dbias + g * dbias_gstride
 int mt_attn_tc_bwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse, const void* dout,
-                       void* dqkv, DropCfg drop, float* dbias, float* aux, cudaStream_t st);
+                       void* dqkv, DropCfg drop, float* dbias, float* aux, cudaStream_t st, int G = 1, const DropCfg* drops = nullptr,
+                       size_t dbias_gstride = 0);
 // workspace of any attention backward (Dws of mt_attn_bwd_run), in floats
 static inline size_t mt_attn_bwd_ws_floats(int B, int T, int h) { return 4 * (size_t)B * (size_t)(T < 128 ? 128 : T) * (size_t)h + 64; }
 
@@ -80,3 +84,9 @@ int mt_attn_fwd_run(int dtype, int B, int T, int d, int h, const void* qkv, cons
                     cudaStream_t st, const int* klen = nullptr);
 int mt_attn_bwd_run(int dtype, int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse,
                     const void* dout, void* dqkv, DropCfg drop, float* Dws, cudaStream_t st, float* dbias = nullptr);
+// G modality stacks back to back (B narratives each; mask / klen shared; drops[g] = stack g's dropout stream; Dws: G * mt_attn_bwd_ws_floats;
+// dbias of stack g at dbias + g * dbias_gstride): one launch on the tcgen05 engine, one call per stack on the other engines
+int mt_attn_group_fwd_run(int dtype, int G, int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse,
+                          const DropCfg* drops, cudaStream_t st, const int* klen = nullptr);
+int mt_attn_group_bwd_run(int dtype, int G, int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse,
+                          const void* dout, void* dqkv, const DropCfg* drops, float* Dws, cudaStream_t st, float* dbias, size_t dbias_gstride);
