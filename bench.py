@@ -60,6 +60,7 @@ def parse():
     ap.add_argument('--micro', type=int, default=8, help='c5: narratives per micro-batch')
     ap.add_argument('--layers', type=int, default=6)
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--fp32-inputs', action='store_true', help='bf16 mode: send the window features to the device as fp32 (cast there) instead of bf16')
     ap.add_argument('--cpu-sample', type=int, default=0, help='narratives per CPU-baseline step (0 = per configuration; the reference trains with batch 25, MFT/train.py:74)')
     ap.add_argument('--port', action='store_true', help='--impl reference: time the oracle port even when baseline/_ref is present')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -354,11 +355,14 @@ def run_ours(args, rank, local_rank, world):
     model.to(dev)
     opt = FlatAdam(model, lr=1e-4, weight_decay=1e-4)
     norm = float(sum(sum(fill.make_lengths(B, T, 1 + r)) for r in range(world)))      # GLOBAL sum of lengths
-    host = {k: torch.from_numpy(v).pin_memory() for k, v in inputs.items()}
+    # window features cross PCIe in the compute dtype (bf16 mode: the embed GEMMs round them to bf16 anyway -- same values, half the bytes,
+    # no cast pass; raw-window configurations keep fp32: their front-end casts on the device)
+    in_dtype = torch.bfloat16 if (args.dtype == 'bf16' and cfg != 'c1' and not args.fp32_inputs) else torch.float32
+    host = {k: torch.from_numpy(v).to(in_dtype).pin_memory() for k, v in inputs.items()}
     host_mask, host_target = torch.from_numpy(mask).pin_memory(), torch.from_numpy(target).pin_memory()
     res = {k: v.to(dev) for k, v in host.items()}
     res_mask, res_target = host_mask.to(dev), host_target.to(dev)
-    h2d = sum(v.numel() * 4 for v in host.values()) + host_mask.numel() * 4 + (host_target.numel() * 4 if is_train else 0)
+    h2d = sum(v.numel() * v.element_size() for v in host.values()) + host_mask.numel() * 4 + (host_target.numel() * 4 if is_train else 0)
     loss_host = torch.zeros(1).pin_memory()
     pred_host = torch.zeros(B, T, 1).pin_memory()
 
@@ -383,12 +387,12 @@ def run_ours(args, rank, local_rank, world):
         train_step(False)
     gstep = None
     if is_train:
-        gstep = GraphedTrainStep(model, opt, B, T, dims, dev, norm_fn=lambda _l: norm)
+        gstep = GraphedTrainStep(model, opt, B, T, dims, dev, norm_fn=lambda _l: norm, input_dtype=in_dtype)
         gstep.load(res, res_mask, res_target, lengths)
         l0 = L.mt_launch_count()
         gstep.capture()
         launches_per_step = (L.mt_launch_count() - l0) // (gstep.warmup + 1)
-    gfwd = GraphedForward(model, B, T, dims, dev)
+    gfwd = GraphedForward(model, B, T, dims, dev, input_dtype=in_dtype)
     gfwd.load(res, res_mask)
     l0 = L.mt_launch_count()
     gfwd.capture()
@@ -551,7 +555,7 @@ def run_ours(args, rank, local_rank, world):
             'metric': metric_of(args), 'value': gb / (ms_train * 1e-3), 'unit': 'narratives/s', 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': ms_train, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype,
             'data': 'synthetic',
-            'config': config_block(args, world, wl),
+            'config': config_block(args, world, dict(wl, host_inputs=f'{str(in_dtype).replace("torch.", "")} window features in pinned host memory')),
             'inference': {'value': gb / (ms_inf * 1e-3), 'unit': 'narratives/s', 'ms_per_step': ms_inf,
                           'e2e_value': gb / (ms_inf_e2e * 1e-3), 'd2h_bytes_per_step': B * T * 4},
             'e2e': {'value': gb / (ms_train_e2e * 1e-3), 'unit': 'narratives/s', 'ms_per_step': ms_train_e2e, 'h2d_bytes_per_step': h2d,

@@ -263,35 +263,57 @@ constexpr int BWD_STAGE_BYTES = 4 * TILE_BYTES + BWD_AUX_BYTES;         // Q | K
 constexpr int BWD_DS_BYTES = TM * TM * 2;                               // dS of one head as an MN-major A operand
 constexpr int BWD_SMEM = BWD_STAGES * BWD_STAGE_BYTES + 2 * BWD_DS_BYTES + 256 + 1024;
 
-// aux[b][hd][k][q] (row stride 128 whatever T is), see BwdArgs; one thread per (b, hd, q), q fastest
-__global__ void attn_tc_prep_kernel(int B, int Bg, int T, int d, int h, const bf16* __restrict__ out, const bf16* __restrict__ dout,
-                                    const float* __restrict__ lse, const float* __restrict__ mask, float* __restrict__ aux, float scale) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)B * h * T) return;      // B = all narratives of the launch, Bg = per group (the mask is shared by the groups)
-  const int q = (int)(idx % T);
-  const long long bh = idx / T;
-  const int b = (int)(bh / h), hd = (int)(bh % h);
-  const size_t row = (size_t)b * T + q;
-  const uint4* o4 = reinterpret_cast<const uint4*>(out + row * d + hd * HD);
-  const uint4* g4 = reinterpret_cast<const uint4*>(dout + row * d + hd * HD);
-  float D = 0.f;
+// aux[b][hd][k][q] (row stride 128 whatever T is), see BwdArgs.  A block takes 32 consecutive token rows: each warp reads four rows'
+// 512 bytes of `out` and `dout` as 16-byte pieces (fully coalesced; lane l holds 8 columns of head l / (HD / 8)), the per-head dot
+// product closes with shuffles inside the head's lane group and lands in shared memory [head][row]; then the block writes the four
+// per-query vectors with q (the row) fastest, i.e. as full 128-byte segments.
+constexpr int PREP_ROWS = 32, PREP_MAXH = 32;
+__global__ void __launch_bounds__(256) attn_tc_prep_kernel(int B, int Bg, int T, int d, int h, const bf16* __restrict__ out,
+                                                           const bf16* __restrict__ dout, const float* __restrict__ lse,
+                                                           const float* __restrict__ mask, float* __restrict__ aux, float scale) {
+  constexpr int LPH = HD / 8;                       // lanes per head
+  __shared__ float sD[PREP_MAXH][PREP_ROWS + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long rows = (long long)B * T;           // B = all narratives of the launch, Bg = per group (the mask is shared by the groups)
+  for (long long r0 = (long long)blockIdx.x * PREP_ROWS; r0 < rows; r0 += (long long)gridDim.x * PREP_ROWS) {
+    for (int rr = warp; rr < PREP_ROWS; rr += 8) {
+      const long long row = r0 + rr;
+      if (row >= rows) continue;
+      for (int c0 = 0; c0 < d; c0 += 256) {         // 32 lanes x 8 columns per pass; d % 32 == 0, so a head's lane group is all-in or all-out
+        const int col = c0 + lane * 8;
+        const bool valid = col < d;
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        const uint4 o = valid ? *reinterpret_cast<const uint4*>(out + (size_t)row * d + col) : zero;
+        const uint4 g = valid ? *reinterpret_cast<const uint4*>(dout + (size_t)row * d + col) : zero;
+        const uint32_t ow[4] = {o.x, o.y, o.z, o.w}, gw[4] = {g.x, g.y, g.z, g.w};
+        float D = 0.f;
 #pragma unroll
-  for (int i = 0; i < HD / 8; ++i) {
-    const uint4 o = o4[i], g = g4[i];
-    const uint32_t ow[4] = {o.x, o.y, o.z, o.w}, gw[4] = {g.x, g.y, g.z, g.w};
+        for (int k = 0; k < 4; ++k) {
+          const float2 of = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ow[k]));
+          const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[k]));
+          D += of.x * gf.x + of.y * gf.y;
+        }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 of = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ow[k]));
-      const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[k]));
-      D += of.x * gf.x + of.y * gf.y;
+        for (int s = 1; s < LPH; s <<= 1) D += __shfl_xor_sync(0xffffffffu, D, s);
+        if (valid && (lane & (LPH - 1)) == 0) sD[col / HD][rr] = D;
+      }
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < h * PREP_ROWS; i += 256) {
+      const int hd = i / PREP_ROWS, rr = i % PREP_ROWS;
+      const long long row = r0 + rr;
+      if (row >= rows) continue;
+      const int b = (int)(row / T), q = (int)(row % T);
+      const bool masked = mask != nullptr && mask[(size_t)(b % Bg) * T + q] == 0.f;
+      const size_t bh = (size_t)b * h + hd;
+      float* a = aux + bh * 4 * TM;
+      a[q] = lse[bh * T + q] * LOG2E;
+      a[TM + q] = sD[hd][rr];
+      a[2 * TM + q] = masked ? 0.f : scale * LOG2E;      // masked query rows: constant scores (uniform P) ...
+      a[3 * TM + q] = masked ? 0.f : scale;              // ... and no score gradient (masked_fill blocks it)
+    }
+    __syncthreads();
   }
-  const bool masked = mask != nullptr && mask[(size_t)(b % Bg) * T + q] == 0.f;
-  float* a = aux + (size_t)bh * 4 * TM;
-  a[q] = lse[bh * T + q] * LOG2E;
-  a[TM + q] = D;
-  a[2 * TM + q] = masked ? 0.f : scale * LOG2E;      // masked query rows: constant scores (uniform P) ...
-  a[3 * TM + q] = masked ? 0.f : scale;              // ... and no score gradient (masked_fill blocks it)
 }
 
 // TMEM columns of head w (base w * 256).  Warp group hf of the head owns the queries [64 hf, 64 hf + 64):
@@ -631,8 +653,11 @@ int mt_attn_tc_bwd_run(int B, int T, int d, int h, const void* qkv, const float*
     return MT_ERR_ALIGN;
   const float scale = 1.0f / sqrtf((float)HD);
   {
-    const long long n = (long long)G * B * h * T;
-    attn_tc_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(G * B, B, T, d, h, (const bf16*)out, (const bf16*)dout, lse, mask, aux, scale);
+    const long long rows = (long long)G * B * T;
+    if (h > PREP_MAXH) return MT_ERR_UNSUPPORTED;
+    long long blocks = (rows + PREP_ROWS - 1) / PREP_ROWS;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    attn_tc_prep_kernel<<<(unsigned)blocks, 256, 0, st>>>(G * B, B, T, d, h, (const bf16*)out, (const bf16*)dout, lse, mask, aux, scale);
     MT_LAUNCH_CHECK();
   }
   CUtensorMap map_qkv, map_do;

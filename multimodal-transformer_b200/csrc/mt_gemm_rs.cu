@@ -121,12 +121,7 @@ __global__ void __launch_bounds__(NT, 1) gemm_rs_kernel(const __grid_constant__ 
   fence_after();
   const uint32_t tmem_base = *tmem_slot;
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  for (int i = threadIdx.x; i < BN; i += NT) {
-    bias_s[i] = (F & R_BIAS) ? g.bias[grp][n0 + i] : 0.f;
-    cs_s[i] = 0.f;
-    if (F & R_LN) { lna_s[i] = g.ln_a[grp][n0 + i]; lnb_s[i] = g.ln_b[grp][n0 + i]; }
-  }
-  __syncthreads();
+  // (the producer / MMA warps start at once; bias, column-sum and LayerNorm-gain staging is the epilogue warps' own business, below)
 
   if (warp == 0) {
     // ===== weight slice once, then the activation ring =====
@@ -224,9 +219,15 @@ __global__ void __launch_bounds__(NT, 1) gemm_rs_kernel(const __grid_constant__ 
     uint8_t* my_stage = o_stage + wg * C::NSO * BOX;
     DropCfg drop = g.drop[grp];
     if (F & R_DROP) drop = mt_drop_resolve(drop);
-    const uint32_t t16 = drop.thresh >> 16;
+    const uint32_t thr_hi = (drop.thresh >> 16) << 16;
     int ob = 0;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int i = (int)threadIdx.x - 4 * 32; i < BN; i += 2 * EPI_THREADS) {
+      bias_s[i] = (F & R_BIAS) ? g.bias[grp][n0 + i] : 0.f;
+      cs_s[i] = 0.f;
+      if (F & R_LN) { lna_s[i] = g.ln_a[grp][n0 + i]; lnb_s[i] = g.ln_b[grp][n0 + i]; }
+    }
+    bar_sync(3, 2 * EPI_THREADS);
     for (int it = 0; it < n_tiles; ++it) {
       const int tm = rank + it * g.cnt;
       const int row0 = grp * g.rows_per_group + tm * BM;
@@ -264,13 +265,14 @@ __global__ void __launch_bounds__(NT, 1) gemm_rs_kernel(const __grid_constant__ 
           }
           if (F & R_DROP) {
             if (drop.thresh != 0u) {
-              // element index (m local to the group) * N + n: even, so a pair never straddles two rows
-              const uint64_t idx = (uint64_t)(tm * BM + row) * (uint64_t)g.N + (uint64_t)(n0 + c * 32);
+              // element index (m local to the group) * N + n: even, so a pair never straddles two rows; the pair index fits 32 bits
+              // (rows per group <= 2^21, see mt_gemm_rs_supported), where mt_draw32 reduces to mix32(pair ^ key)
+              const uint32_t p0 = (uint32_t)(((uint64_t)(tm * BM + row) * (uint64_t)g.N + (uint64_t)(n0 + c * 32)) >> 1);
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                const uint32_t bits = mt_draw32(drop, (idx >> 1) + (uint64_t)j);
-                o[2 * j] = (bits & 0xFFFFu) >= t16 ? o[2 * j] * drop.scale : 0.f;
-                o[2 * j + 1] = (bits >> 16) >= t16 ? o[2 * j + 1] * drop.scale : 0.f;
+                const uint32_t bits = mt_mix32((p0 + (uint32_t)j) ^ drop.key);
+                o[2 * j] = (bits << 16) >= thr_hi ? o[2 * j] * drop.scale : 0.f;      // low half -> even element, high half -> odd
+                o[2 * j + 1] = bits >= thr_hi ? o[2 * j + 1] * drop.scale : 0.f;
               }
             }
           }

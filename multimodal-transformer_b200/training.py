@@ -209,13 +209,16 @@ class GraphedTrainStep:
     If the model was trained eagerly on the default stream before, drop every reference to those iterations' outputs / losses first
     (they keep autograd AccumulateGrad nodes alive that are bound to the legacy stream, which a capturing stream may not touch)."""
 
-    def __init__(self, model, opt, B, T, in_dims, device, norm_fn=None, warmup=3):
+    def __init__(self, model, opt, B, T, in_dims, device, norm_fn=None, warmup=3, input_dtype=torch.float32):
         from . import _lib
         self.model, self.opt, self.B, self.T, self.device = model, opt, B, T, device
         self.mods = list(in_dims)
         # in_dims: mod -> feature width (hot-path models, inputs [B,T,d]) or mod -> (K, D) (MultiCNNTransformer variants, raw windows
-        # [B,T,K,D]: the window front-end is then part of the captured step)
-        self.x = {m: torch.zeros((B, T) + (tuple(d) if isinstance(d, (tuple, list)) else (d,)), device=device) for m, d in in_dims.items()}
+        # [B,T,K,D]: the window front-end is then part of the captured step).  input_dtype = torch.bfloat16 (bf16 compute mode, hot-path
+        # models): the window features are held, copied from the host and fed to the embed GEMMs as bf16 -- the same values the embed
+        # would round them to anyway, half the PCIe bytes per step and no cast pass
+        self.x = {m: torch.zeros((B, T) + (tuple(d) if isinstance(d, (tuple, list)) else (d,)), device=device, dtype=input_dtype)
+                  for m, d in in_dims.items()}
         self.mask = torch.zeros(B, T, 1, device=device)
         self.target = torch.zeros(B, T, 1, device=device)
         self.inv_norm = torch.ones(1, device=device)
@@ -370,12 +373,14 @@ class GraphedTrainStep:
 class GraphedForward:
     """eval() forward captured into a CUDA graph for a fixed (B, T); returns the static prediction buffer [B,T,1]."""
 
-    def __init__(self, model, B, T, in_dims, device, warmup=2):
+    def __init__(self, model, B, T, in_dims, device, warmup=2, input_dtype=torch.float32):
         self.model, self.B, self.T, self.device = model, B, T, device
         self.mods = list(in_dims)
+        self._input_dtype = input_dtype
         # in_dims: mod -> feature width (hot-path models, inputs [B,T,d]) or mod -> (K, D) (MultiCNNTransformer variants, raw windows
         # [B,T,K,D]: the window front-end is then part of the captured step)
-        self.x = {m: torch.zeros((B, T) + (tuple(d) if isinstance(d, (tuple, list)) else (d,)), device=device) for m, d in in_dims.items()}
+        self.x = {m: torch.zeros((B, T) + (tuple(d) if isinstance(d, (tuple, list)) else (d,)), device=device, dtype=input_dtype)
+                  for m, d in in_dims.items()}
         self.mask = torch.zeros(B, T, 1, device=device)
         self.lengths = [T] * B
         self.warmup = warmup
