@@ -326,6 +326,10 @@ int mt_comm_init(const char* id128, int rank, int world, void** comm);
 int mt_comm_destroy(void* comm);
 int mt_allreduce_grads(void* comm, float* const* bufs, const size_t* counts, int n_bufs, void* stream);
 
+/* test hook: keep the bf16 LSTM-decoder forward (mt_lstm_head_fwd) on the FFMA kernel instead of the cluster / tensor-core kernel
+ * (csrc/mt_lstm_head_mma.cu: E == 256, bf16 mode); returns the previous setting. */
+int mt_lstm_head_force_ffma(int on);
+
 /* Generic GEMM (exposed for tests and profiling):  C[M,N] = A·B^T-style contraction, see csrc/mt_gemm.cuh.
  * a_kmajor: A element (m,k) at A[m*lda+k] (else A[k*lda+m]); b_kmajor: B element (n,k) at B[n*ldb+k] (else B[k*ldb+n]). */
 int mt_gemm(int dtype, int M, int N, int K, const void* A, int lda, int a_kmajor, const void* B, int ldb, int b_kmajor,

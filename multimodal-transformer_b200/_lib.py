@@ -90,6 +90,7 @@ _PROTOS = {
     'mt_lstm_head_ws_bytes': (c_size_t, [POINTER(MtLstmHeadCfg)]),
     'mt_lstm_head_fwd': (c_int, [POINTER(MtLstmHeadCfg), P, P, P, P, P, P, c_size_t, P]),
     'mt_lstm_head_bwd': (c_int, [POINTER(MtLstmHeadCfg), P, P, P, P, P, P, P, P, c_size_t, P]),
+    'mt_lstm_head_force_ffma': (c_int, [c_int]),
     'mt_window_cnn_ws_bytes': (c_size_t, [POINTER(MtWindowCnnCfg)]),
     'mt_window_cnn_fwd': (c_int, [POINTER(MtWindowCnnCfg), P, P, P, P, P, P, P, P, P, c_size_t, P]),
     'mt_window_cnn_bwd': (c_int, [POINTER(MtWindowCnnCfg), P, P, P, P, P, P, P, P, P, P, c_size_t, P]),

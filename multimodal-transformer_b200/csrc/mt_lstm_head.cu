@@ -9,6 +9,13 @@
 #include "mt_recurrent.cuh"
 
 GemmDesc mt_wgrad_desc(int M, int Nout, int Kin, const void* dy, int ldy, const void* x, int ldx, float* dW, int ldw);
+// tensor-core / cluster forward (mt_lstm_head_mma.cu), bf16 mode
+bool mt_lstm_head_mma_supported(int E, int Hd);
+int mt_lstm_head_mma_recurrence(int B, int T, bool training, const float* w_ih, const float* w_hh, const float* b_hh, const float* h0,
+                                const float* c0, float* gates, float* hprev, float* oprev, float* cprev, float* hcur, void* hall,
+                                cudaStream_t st);
+int mt_lstm_head_out_run(int M, int Hd, const float* oh, const float* w2, const float* b2, const float* mask, float* out, cudaStream_t st);
+static int g_head_force_ffma = 0;
 
 namespace {
 
@@ -48,6 +55,8 @@ struct HStash {
   float* dz;       // [M,4E]
   float* doh;      // [M,Hd]
   float* dyv;      // [M]
+  void* hall;      // [M,E] bf16 h_t: operand of the hoisted head (tensor-core forward)
+  float* oh_fwd;   // [M,Hd] relu(head layer 0): = oh when training, scratch otherwise
   size_t bytes;
 };
 
@@ -66,6 +75,8 @@ void carve(const MtLstmHeadCfg& c, void* ws, HStash& s) {
   } else {
     s.hprev = s.oprev = s.cprev = s.hcur = s.oh = s.dz = s.doh = s.dyv = nullptr;
   }
+  s.hall = k.take_bytes(M * E * 2);
+  s.oh_fwd = c.training ? s.oh : k.take<float>(M * Hd);
   s.bytes = k.total();
 }
 
@@ -302,6 +313,19 @@ int mt_lstm_head_fwd(const MtLstmHeadCfg* cfg, const float* params, const void* 
   g.C = a.S.gates; g.ldc = 4 * E; g.c_f32 = true;
   g.epi.bias = params + a.O.b_ih;
   MT_TRY(mt_gemm_run(c.dtype, g, st));
+  if (lp && !g_head_force_ffma && mt_lstm_head_mma_supported(E, c.Hd)) {
+    // bf16 mode: recurrence on the cluster / mma.sync kernel, MLP head hoisted into one GEMM + a row-wise dot product
+    MT_TRY(mt_lstm_head_mma_recurrence(c.B, c.T, c.training != 0, params + a.O.w_ih, params + a.O.w_hh, params + a.O.b_hh, params + a.O.h0,
+                                       params + a.O.c0, a.S.gates, a.S.hprev, a.S.oprev, a.S.cprev, a.S.hcur, a.S.hall, st));
+    GemmDesc h;
+    h.M = M; h.N = c.Hd; h.K = E;
+    h.A = a.S.hall; h.lda = E; h.a_kmajor = true;
+    h.B = (const bf16*)params_lp + a.O.w0; h.ldb = E; h.b_kmajor = true;
+    h.C = a.S.oh_fwd; h.ldc = c.Hd; h.c_f32 = true;
+    h.epi.bias = params + a.O.b0; h.epi.act = MT_ACT_RELU;
+    MT_TRY(mt_gemm_run(c.dtype, h, st));
+    return mt_lstm_head_out_run(M, c.Hd, a.S.oh_fwd, params + a.O.w2, params + a.O.b2, mask, out, st);
+  }
   const size_t smem = ((size_t)(E * 3 + 4 * E + c.Hd) * BT + (size_t)PART_FLOATS) * sizeof(float) + RING_BYTES;
   const int grid = (c.B + BT - 1) / BT;
   a.tab.n = 2;
@@ -383,5 +407,8 @@ int mt_lstm_head_bwd(const MtLstmHeadCfg* cfg, const float* params, const void* 
   }
   return MT_OK;
 }
+
+/* test hook: keep the bf16 decoder forward on the FFMA kernel (A/B against the cluster / tensor-core forward); returns the previous setting */
+int mt_lstm_head_force_ffma(int on) { int old = g_head_force_ffma; g_head_force_ffma = on; return old; }
 
 }  // extern "C"
