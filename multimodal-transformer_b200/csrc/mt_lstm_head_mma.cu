@@ -148,17 +148,20 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__((NWC + 1) * 32, 1) 
   for (int t = 0; t < a.T; ++t) {
     const bf16* hin = hS + (t & 1) * NB * LDH;
     const uint32_t out_off = (uint32_t)(((t & 1) ^ 1) * NB * LDH * (int)sizeof(bf16));
-    float acc[NTL][4];
+    // two independent accumulator chains per n-tile (even / odd k-steps): halves the dependent mma chain of the step
+    float acc[NTL][4], acb[NTL][4];
 #pragma unroll
-    for (int i = 0; i < NTL; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    for (int i = 0; i < NTL; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = acb[i][0] = acb[i][1] = acb[i][2] = acb[i][3] = 0.f;
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
       for (int i = 0; i < NTL; ++i) {
         const bf16* p = hin + (i * 8 + gid) * LDH + ks * 16 + 2 * q;
-        mma16816(acc[i], A[ks], *reinterpret_cast<const uint32_t*>(p), *reinterpret_cast<const uint32_t*>(p + 8));
+        mma16816((ks & 1) ? acb[i] : acc[i], A[ks], *reinterpret_cast<const uint32_t*>(p), *reinterpret_cast<const uint32_t*>(p + 8));
       }
     }
+#pragma unroll
+    for (int i = 0; i < NTL; ++i) { acc[i][0] += acb[i][0]; acc[i][1] += acb[i][1]; acc[i][2] += acb[i][2]; acc[i][3] += acb[i][3]; }
     mtrec::sbar_wait(&full[t % FDH], (uint32_t)(t / FDH) & 1u);
     const float* zs = zring + (size_t)(t % FDH) * STAGE_FLOATS;
 #pragma unroll
