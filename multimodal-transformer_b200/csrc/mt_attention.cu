@@ -353,15 +353,23 @@ int mt_attn_group_fwd_run(int dtype, int G, int B, int T_, int d, int h, const v
   return MT_OK;
 }
 
+bool mt_attn_group_bwd_uses_tc(int dtype, int G, int B, int T_, int d, int h, const void* qkv, const void* out, const void* dout,
+                               const void* dqkv, const float* Dws, const float* dbias) {
+  return G >= 1 && G <= 4 && dtype == MT_BF16 && dbias && h <= 8 && !g_attn_force_ffma && !g_mt_attn_no_tc && !mt_attn_force_tiled_on() &&
+         mt_attn_tc_supported(B, T_, d, h) && (long long)G * B * T_ <= 0x7fffffffLL / (3LL * d) &&
+         !(((uintptr_t)qkv | (uintptr_t)out | (uintptr_t)dout | (uintptr_t)dqkv | (uintptr_t)Dws) & 15);
+}
+
 int mt_attn_group_bwd_run(int dtype, int G, int B, int T_, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse,
-                          const void* dout, void* dqkv, const DropCfg* drops, float* Dws, cudaStream_t st, float* dbias, size_t dbias_gstride) {
+                          const void* dout, void* dqkv, const DropCfg* drops, float* Dws, cudaStream_t st, float* dbias, size_t dbias_gstride,
+                          bool d_ready) {
   MT_TRY(check_shape(B, T_, d, h));
   if (!qkv || !out || !lse || !dout || !dqkv || !Dws || G < 1 || G > 4) return MT_ERR_ARG;
-  if (G > 1 && dtype == MT_BF16 && dbias && h <= 8 && !g_attn_force_ffma && !g_mt_attn_no_tc && !mt_attn_force_tiled_on() &&
-      mt_attn_tc_supported(B, T_, d, h) && !(((uintptr_t)qkv | (uintptr_t)out | (uintptr_t)dout | (uintptr_t)dqkv | (uintptr_t)Dws) & 15)) {
-    const int rc = mt_attn_tc_bwd_run(B, T_, d, h, qkv, mask, out, lse, dout, dqkv, drops[0], dbias, Dws, st, G, drops, dbias_gstride);
-    if (rc != MT_ERR_UNSUPPORTED) return rc;
+  if ((G > 1 || d_ready) && mt_attn_group_bwd_uses_tc(dtype, G, B, T_, d, h, qkv, out, dout, dqkv, Dws, dbias)) {
+    const int rc = mt_attn_tc_bwd_run(B, T_, d, h, qkv, mask, out, lse, dout, dqkv, drops[0], dbias, Dws, st, G, drops, dbias_gstride, d_ready);
+    if (rc != MT_ERR_UNSUPPORTED || d_ready) return rc;
   }
+  if (d_ready) return MT_ERR_UNSUPPORTED;      // the caller skipped the full preparation: only the tcgen05 engine can continue
   const size_t es = dtype == MT_BF16 ? 2 : 4, M = (size_t)B * T_;
   for (int g = 0; g < G; ++g)
     MT_TRY(mt_attn_bwd_run(dtype, B, T_, d, h, (const char*)qkv + g * M * 3 * d * es, mask, (const char*)out + g * M * d * es,

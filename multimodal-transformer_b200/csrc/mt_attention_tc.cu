@@ -316,12 +316,28 @@ __global__ void __launch_bounds__(256) attn_tc_prep_kernel(int B, int Bg, int T,
   }
 }
 
+// the same without D (row 1 of aux already holds it: the output projection's input-gradient GEMM wrote it from its epilogue, see
+// mt_gemm_rs.cu R_ATTD): one thread per (b, hd, q), q fastest -- 4 bytes read, 12 written per query
+__global__ void attn_tc_prep_light_kernel(int B, int Bg, int T, int h, const float* __restrict__ lse, const float* __restrict__ mask,
+                                          float* __restrict__ aux, float scale) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * h * T) return;
+  const int q = (int)(idx % T);
+  const long long bh = idx / T;
+  const int b = (int)(bh / h);
+  const bool masked = mask != nullptr && mask[(size_t)(b % Bg) * T + q] == 0.f;
+  float* a = aux + (size_t)bh * 4 * TM;
+  a[q] = lse[bh * T + q] * LOG2E;
+  a[2 * TM + q] = masked ? 0.f : scale * LOG2E;
+  a[3 * TM + q] = masked ? 0.f : scale;
+}
+
 // TMEM columns of head w (base w * 256).  Warp group hf of the head owns the queries [64 hf, 64 hf + 64):
 //   [0,128)   S^T  (fp32)  -> P^T  packed bf16 at [0,32) (hf 0) and [64,96) (hf 1): each group overwrites columns it has already read
 //   [128,256) dP^T (fp32)  -> dS^T packed bf16 at [128,160) and [192,224)
 //   accumulators of the second round in the gaps: dV [32,64), dK [96,128), dQ [160,192)
 template <bool FULL>
-__global__ void __launch_bounds__(BWD_NT, 1)
+__global__ void __launch_bounds__(BWD_NT, 1)      // 18 warps are allocated as 20: 96 registers per thread is the ceiling
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do, const __grid_constant__ BwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ float s_cs[4 * 2 * 96];                  // [head pair][w][dQ | dK | dV][32]: bias-gradient column sums of this CTA
@@ -395,12 +411,13 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
               fence_after();
               const uint32_t sq = smem_u32(stage_base + stage * BWD_STAGE_BYTES), sk = sq + TILE_BYTES, sv = sk + TILE_BYTES, sg = sv + TILE_BYTES;
               const uint32_t tw = tmem_base + (uint32_t)(w * 256);
+              // one thread issues everything: build each operand's descriptor once, advance its 14-bit address field by a constant per k-step
+              const uint64_t dk0 = make_desc(sk + 64 * w, 16, 1024), dq0 = make_desc(sq + 64 * w, 16, 1024);
+              const uint64_t dv0 = make_desc(sv + 64 * w, 16, 1024), dg0 = make_desc(sg + 64 * w, 16, 1024);
 #pragma unroll
-              for (int ks = 0; ks < HD / 16; ++ks)
-                mma_ss(tw, make_desc(sk + 64 * w + 32 * ks, 16, 1024), make_desc(sq + 64 * w + 32 * ks, 16, 1024), idesc_s, ks > 0);
+              for (int ks = 0; ks < HD / 16; ++ks) mma_ss(tw, dk0 + (uint64_t)(2 * ks), dq0 + (uint64_t)(2 * ks), idesc_s, ks > 0);
 #pragma unroll
-              for (int ks = 0; ks < HD / 16; ++ks)
-                mma_ss(tw + 128, make_desc(sv + 64 * w + 32 * ks, 16, 1024), make_desc(sg + 64 * w + 32 * ks, 16, 1024), idesc_s, ks > 0);
+              for (int ks = 0; ks < HD / 16; ++ks) mma_ss(tw + 128, dv0 + (uint64_t)(2 * ks), dg0 + (uint64_t)(2 * ks), idesc_s, ks > 0);
               commit(&s_full[w]);
               ++s_it[w];
               progressed = true;
@@ -415,15 +432,16 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
               const uint32_t sq = smem_u32(stage_base + stage * BWD_STAGE_BYTES), sk = sq + TILE_BYTES, sg = sk + 2 * TILE_BYTES;
               const uint32_t sds = smem_u32(ds_smem + w * BWD_DS_BYTES);
               const uint32_t tw = tmem_base + (uint32_t)(w * 256);
+              const uint64_t dgm = make_desc(sg + 64 * w, 8192, 1024), dqm = make_desc(sq + 64 * w, 8192, 1024);
+              const uint64_t dsm = make_desc(sds, TILE_BYTES, 1024), dkm = make_desc(sk + 64 * w, 8192, 1024);
 #pragma unroll
               for (int ks = 0; ks < TM / 16; ++ks)      // packed A columns of 16 queries: [8 ks, 8 ks + 8) for ks < 4, 64 + ... beyond
-                mma_ts(tw + 32, tw + (ks < 4 ? 8 * ks : 32 + 8 * ks), make_desc(sg + 64 * w + 2048 * ks, 8192, 1024), idesc_ts, ks > 0);
+                mma_ts(tw + 32, tw + (ks < 4 ? 8 * ks : 32 + 8 * ks), dgm + (uint64_t)(128 * ks), idesc_ts, ks > 0);
 #pragma unroll
               for (int ks = 0; ks < TM / 16; ++ks)
-                mma_ts(tw + 96, tw + 128 + (ks < 4 ? 8 * ks : 32 + 8 * ks), make_desc(sq + 64 * w + 2048 * ks, 8192, 1024), idesc_ts, ks > 0);
+                mma_ts(tw + 96, tw + 128 + (ks < 4 ? 8 * ks : 32 + 8 * ks), dqm + (uint64_t)(128 * ks), idesc_ts, ks > 0);
 #pragma unroll
-              for (int ks = 0; ks < TM / 16; ++ks)
-                mma_ss(tw + 160, make_desc(sds + 2048 * ks, TILE_BYTES, 1024), make_desc(sk + 64 * w + 2048 * ks, 8192, 1024), idesc_dq, ks > 0);
+              for (int ks = 0; ks < TM / 16; ++ks) mma_ss(tw + 160, dsm + (uint64_t)(128 * ks), dkm + (uint64_t)(128 * ks), idesc_dq, ks > 0);
               commit(&g_full[w]);
               ++g_it[w];
               if (g_it[w ^ 1] >= g_it[w]) commit(&empty[stage]);      // both heads of this item are done with the stage
@@ -540,7 +558,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
           uint4 u;
           u.x = pack_bf2(v[8 * qd], v[8 * qd + 1]); u.y = pack_bf2(v[8 * qd + 2], v[8 * qd + 3]);
           u.z = pack_bf2(v[8 * qd + 4], v[8 * qd + 5]); u.w = pack_bf2(v[8 * qd + 6], v[8 * qd + 7]);
-          *reinterpret_cast<uint4*>(gmain + 8 * qd) = u;
+          __stcs(reinterpret_cast<uint4*>(gmain + 8 * qd), u);      // streaming store: leaves the few KB of L1 beside 200 KB of shared memory alone
         }
         bf16* gkp = gp + a.d + hf * 16;
 #pragma unroll
@@ -548,11 +566,14 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
           uint4 u;
           u.x = pack_bf2(v[32 + 8 * qd], v[33 + 8 * qd]); u.y = pack_bf2(v[34 + 8 * qd], v[35 + 8 * qd]);
           u.z = pack_bf2(v[36 + 8 * qd], v[37 + 8 * qd]); u.w = pack_bf2(v[38 + 8 * qd], v[39 + 8 * qd]);
-          *reinterpret_cast<uint4*>(gkp + 8 * qd) = u;
+          __stcs(reinterpret_cast<uint4*>(gkp + 8 * qd), u);
         }
       }
       if (a.dbias != nullptr) {
         // column sums over the warp's 32 rows: a butterfly that halves the number of live columns per lane at every step
+        // (the lane index is re-read here: keeping the kernel-wide `lane` alive across this 48-value block made ptxas spill it)
+        int lane;
+        asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
         int col = 0;
 #pragma unroll
         for (int step = 0; step < 4; ++step) {
@@ -646,13 +667,18 @@ int mt_attn_tc_fwd_run(int B, int T, int d, int h, const void* qkv, const float*
 }
 
 int mt_attn_tc_bwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse, const void* dout,
-                       void* dqkv, DropCfg drop, float* dbias, float* aux, cudaStream_t st, int G, const DropCfg* drops, size_t dbias_gstride) {
+                       void* dqkv, DropCfg drop, float* dbias, float* aux, cudaStream_t st, int G, const DropCfg* drops, size_t dbias_gstride,
+                       bool d_ready) {
   if (!mt_attn_tc_supported(B, T, d, h) || G < 1 || G > MAXG || (long long)G * B * T > 0x7fffffffLL / (3LL * d)) return MT_ERR_UNSUPPORTED;
   if (dbias != nullptr && h > 8) return MT_ERR_UNSUPPORTED;
   if (!aux || ((uintptr_t)aux & 15) || ((uintptr_t)qkv & 15) || ((uintptr_t)dout & 15) || ((uintptr_t)dqkv & 15) || ((uintptr_t)out & 15))
     return MT_ERR_ALIGN;
   const float scale = 1.0f / sqrtf((float)HD);
-  {
+  if (d_ready) {
+    const long long n = (long long)G * B * h * T;
+    attn_tc_prep_light_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(G * B, B, T, h, lse, mask, aux, scale);
+    MT_LAUNCH_CHECK();
+  } else {
     const long long rows = (long long)G * B * T;
     if (h > PREP_MAXH) return MT_ERR_UNSUPPORTED;
     long long blocks = (rows + PREP_ROWS - 1) / PREP_ROWS;

@@ -345,12 +345,25 @@ int encoder_bwd_impl(const MtEncoderCfg& c, const Groups& gr, const float* param
     }
     // ---- attention sublayer: xp = x + drop(att w_o + b_o); w.dact = drop' . g_nxt and db_o are already there ---------
     MT_TRY(pj.wgrad(d, d, w.dact, b.att, base + P.w_o));
-    MT_TRY(pj.run(true, d, d, w.dact, base + P.w_o, w.dact2, !lp, -1, MT_ACT_NONE, l, -1, nullptr, 1.f, nullptr, -1));
+    // d att = d out . w_o; when the tcgen05 attention backward follows, the same GEMM leaves D = rowsum(d att . att) per head in the
+    // attention kernel's per-query scalars (no separate pass over att and d att)
+    bool d_ready = false;
+    if (lp && !g_mt_tune[MT_TUNE_NO_RS] && d == 32 * c.h &&
+        mt_attn_group_bwd_uses_tc(c.dtype, G, c.B, c.T, d, c.h, b.qkv, b.att, w.dact2, w.dqkv, w.Dws, grads + base + P.b_qkv)) {
+      RsDesc r;
+      r.G = G; r.Mg = M; r.N = d; r.K = d;
+      r.A = w.dact; r.lda = d; r.ldb = d; r.b_kmajor = false;
+      r.C = w.dact2; r.ldc = d; r.c_f32 = false;
+      r.attd_src = b.att; r.attd_ld = d; r.attd_aux = w.Dws; r.attd_T = c.T;
+      for (int g = 0; g < G; ++g) { r.B[g] = (const bf16*)params_lp + g * gr.pstride + base + P.w_o; r.drop[g] = mt_make_drop(0.f, 0, 0); }
+      if (mt_gemm_rs_supported(r)) { MT_TRY(mt_gemm_rs_run(r, st)); d_ready = true; }
+    }
+    if (!d_ready) MT_TRY(pj.run(true, d, d, w.dact, base + P.w_o, w.dact2, !lp, -1, MT_ACT_NONE, l, -1, nullptr, 1.f, nullptr, -1));
     {
       DropCfg ad[MT_RS_MAX_GROUPS];
       for (int g = 0; g < G; ++g) ad[g] = mt_make_drop(p, gr.seed[g], mt_enc_site(gr.stack_id[g], l, MT_SITE_ATTN_P));
       MT_TRY(mt_attn_group_bwd_run(c.dtype, G, c.B, c.T, d, c.h, b.qkv, mask, b.att, b.lse, w.dact2, w.dqkv, ad, w.Dws, st,
-                                   grads + base + P.b_qkv, gr.pstride));
+                                   grads + base + P.b_qkv, gr.pstride, d_ready));
     }
     MT_TRY(pj.wgrad(3 * d, d, w.dqkv, b.u, base + P.w_qkv));
     MT_TRY(pj.run(true, d, 3 * d, w.dqkv, base + P.w_qkv, w.dact2, !lp, -1, MT_ACT_NONE, l, -1, nullptr, 1.f, nullptr, -1));

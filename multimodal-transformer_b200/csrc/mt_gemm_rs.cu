@@ -34,7 +34,7 @@ constexpr int EPI_THREADS = 128;         // per epilogue warp group
 constexpr int MAXG = MT_RS_MAX_GROUPS;
 constexpr int SMEM_LIMIT = 227 * 1024;
 
-enum : uint32_t { R_BIAS = 1u, R_RELU = 2u, R_DROP = 4u, R_GATE = 8u, R_RES = 16u, R_CF32 = 32u, R_COLSUM = 64u, R_LN = 128u };
+enum : uint32_t { R_BIAS = 1u, R_RELU = 2u, R_DROP = 4u, R_GATE = 8u, R_RES = 16u, R_CF32 = 32u, R_COLSUM = 64u, R_LN = 128u, R_ATTD = 256u };
 
 struct RsMaps {
   CUtensorMap a, c, r, g, ln;
@@ -49,6 +49,7 @@ struct RsArgs {
   const float* ln_a[MAXG];
   const float* ln_b[MAXG];
   DropCfg drop[MAXG];
+  float* attd_aux; int attd_T;      // R_ATTD: see RsDesc
   unsigned long long* trace;      // debug (mt_gemm_rs_trace): clock64 stamps of CTA 0, 16 words per tile, first 32 tiles
 };
 
@@ -58,9 +59,9 @@ struct Cfg {
   static constexpr int AUX_BYTES = 1024 + 4 * BN * 4 + 4096;      // barriers | bias | column sums | LayerNorm a_2, b_2 | row moments
   static constexpr int BOXES = (SMEM_LIMIT - 1024 - AUX_BYTES - W_BYTES) / BOX;      // 16 KB boxes left beside the resident weights
   static constexpr bool TIGHT = BOXES < 8;                        // the 96 / 128 KB weight slices
-  static constexpr int NSO = (TIGHT || (F & (R_RES | R_GATE))) ? 1 : 2;   // output staging boxes PER epilogue warp group
+  static constexpr int NSO = (TIGHT || (F & (R_RES | R_GATE | R_ATTD))) ? 1 : 2;   // output staging boxes PER epilogue warp group
   static constexpr int NSR = (F & R_RES) ? 4 : 0;                 // residual ring (fp32 [128 x 32] boxes)
-  static constexpr int NSG = (F & R_GATE) ? 2 : 0;                // gate ring (bf16 [128 x 64] boxes)
+  static constexpr int NSG = (F & (R_GATE | R_ATTD)) ? 2 : 0;     // gate / attention-output ring (bf16 [128 x 64] boxes)
   static constexpr int FREE = BOXES - 2 * NSO - NSR - NSG;
   static constexpr int NSA = FREE > 8 ? 8 : FREE;                 // activation ring
   static constexpr int TOTAL = 1024 + W_BYTES + (NSA + 2 * NSO + NSR + NSG) * BOX + AUX_BYTES;
@@ -188,12 +189,12 @@ __global__ void __launch_bounds__(NT, 1) gemm_rs_kernel(const __grid_constant__ 
     }
   } else if (warp == 2) {
     // ===== residual / gate boxes, in the order the epilogue consumes them =====
-    if ((F & (R_RES | R_GATE)) && lane == 0) {
+    if ((F & (R_RES | R_GATE | R_ATTD)) && lane == 0) {
       int rs = 0, gs = 0; uint32_t rph = 0, gph = 0;
       for (int i = 0; i < n_tiles; ++i) {
         const int row0 = grp * g.rows_per_group + (rank + i * g.cnt) * BM;
         for (int c = 0; c < C::CHUNKS; ++c) {
-          if ((F & R_GATE) && (c & 1) == 0) {
+          if ((F & (R_GATE | R_ATTD)) && (c & 1) == 0) {
             mbar_wait(&empty_g[gs], gph ^ 1);
             mbar_expect_tx(&full_g[gs], BOX);
             tma_load_2d(g_ring + gs * BOX, &maps.g, n0 + 32 * c, row0, &full_g[gs]);
@@ -294,6 +295,33 @@ __global__ void __launch_bounds__(NT, 1) gemm_rs_kernel(const __grid_constant__ 
             if (cc == 1) {
               __syncwarp();
               if (lane == 0) mbar_arrive(&empty_g[gs]);
+            }
+          }
+          if (F & R_ATTD) {        // D = rowsum over this head's 32 columns of dO . O (attention backward), O from the bf16 box ring
+            const int ug = it * C::PAIRS + pr, gs = ug % (C::NSG ? C::NSG : 1);
+            if (cc == 0) mbar_wait(&full_g[gs], (uint32_t)(ug / (C::NSG ? C::NSG : 1)) & 1u);
+            const uint8_t* gb = g_ring + gs * BOX;
+            float D = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 gw = *reinterpret_cast<const uint4*>(gb + sw128_off(row, cc * 4 + j));
+              const uint32_t w4[4] = {gw.x, gw.y, gw.z, gw.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 g2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[k]));
+                D = fmaf(o[8 * j + 2 * k], g2.x, D);
+                D = fmaf(o[8 * j + 2 * k + 1], g2.y, D);
+              }
+            }
+            if (cc == 1) {
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&empty_g[gs]);
+            }
+            const int m = tm * BM + row;                          // row inside the group
+            if (m < g.rows_per_group) {
+              const int bl = m / g.attd_T, q = m - bl * g.attd_T;
+              const size_t bh = ((size_t)grp * (g.rows_per_group / g.attd_T) + bl) * (size_t)(g.N >> 5) + (size_t)((n0 >> 5) + c);
+              g.attd_aux[(bh * 4 + 1) * 128 + q] = D;
             }
           }
           if (F & R_RES) {         // residual box use number: one per chunk
@@ -443,6 +471,7 @@ int launch(const RsDesc& d, cudaStream_t st) {
   maps.r = maps.c; maps.g = maps.c; maps.ln = maps.c;
   if (F & R_RES) MT_TRY(make_map_2d(&maps.r, d.residual, (uint64_t)d.N, rows, (uint64_t)d.ldr, 32, BM, 4));
   if (F & R_GATE) MT_TRY(make_map_2d(&maps.g, d.gate, (uint64_t)d.N, rows, (uint64_t)d.ldg, 64, BM));
+  if (F & R_ATTD) MT_TRY(make_map_2d(&maps.g, d.attd_src, (uint64_t)d.N, rows, (uint64_t)d.attd_ld, 64, BM));
   if (F & R_LN) MT_TRY(make_map_2d(&maps.ln, d.ln_out, (uint64_t)d.N, rows, (uint64_t)d.ld_ln, 64, BM));
   for (int i = 0; i < MAXG; ++i) {
     const int s = i < d.G ? i : 0;
@@ -455,6 +484,7 @@ int launch(const RsDesc& d, cudaStream_t st) {
   g.rows_per_group = d.Mg;
   g.b_mn = d.b_kmajor ? 0 : 1;
   g.gate_scale = d.gate_scale; g.ln_eps = d.ln_eps;
+  g.attd_aux = d.attd_aux; g.attd_T = d.attd_T > 0 ? d.attd_T : 1;
   g.trace = g_rs_trace;
   const int P = d.G * g.tiles_n;
   int cnt = num_sms() / P;
@@ -484,6 +514,7 @@ uint32_t features(const RsDesc& d) {
   if (d.c_f32) f |= R_CF32;
   if (d.colsum[0]) f |= R_COLSUM;
   if (d.ln_out) f |= R_LN;
+  if (d.attd_aux) f |= R_ATTD;
   return f;
 }
 
@@ -508,6 +539,7 @@ int dispatch(const RsDesc& d, cudaStream_t st, bool probe_only) {
   RS_PROBE(128, 256, 128, R_GATE | R_COLSUM);                              // d hidden = (d out . w_2) gated by relu' / dropout, + d b_1
   RS_PROBE(256, 128, 256, 0u);                                             // d LN2-out = d hidden . w_1
   RS_PROBE(256, 256, 256, 0u);                                             // d att = d out . w_o
+  RS_PROBE(256, 256, 128, R_ATTD);                                         // ... that also leaves D = rowsum(d att . att) per head for the attention backward
 #undef RS_PROBE
   return MT_ERR_UNSUPPORTED;
 }
@@ -529,6 +561,9 @@ bool mt_gemm_rs_supported(const RsDesc& d) {
   if (d.residual && (((uintptr_t)d.residual & 15) || d.ldr % 4 != 0)) return false;
   if (d.gate && (((uintptr_t)d.gate & 15) || d.ldg % 8 != 0)) return false;
   if (d.ln_out && (((uintptr_t)d.ln_out & 15) || d.ld_ln % 8 != 0 || !d.c_f32)) return false;
+  if (d.attd_aux && (!d.attd_src || ((uintptr_t)d.attd_src & 15) || d.attd_ld % 8 != 0 || d.attd_T <= 0 || d.attd_T > 128 || d.Mg % d.attd_T != 0 ||
+                     d.gate || d.c_f32))
+    return false;
   return dispatch(d, nullptr, true) == MT_OK;
 }
 

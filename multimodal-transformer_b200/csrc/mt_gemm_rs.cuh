@@ -26,6 +26,11 @@ struct RsDesc {
   const float* ln_a[MT_RS_MAX_GROUPS] = {};
   const float* ln_b[MT_RS_MAX_GROUPS] = {};
   float ln_eps = 1e-6f;
+  // attention-backward helper (input gradient of the output projection, N == d): D[b, head, q] = sum over the head's 32 columns of
+  // C (fp32, before rounding) * attd_src (the attention output, bf16 [G*Mg, N]) -> attd_aux[((b * h + head) * 4 + 1) * 128 + q]
+  // with b = row / attd_T (global narrative index), q = row % attd_T, h = N / 32: row 1 of mt_attention_tc.cu's per-query scalars
+  const void* attd_src = nullptr; int attd_ld = 0;
+  float* attd_aux = nullptr; int attd_T = 0;
 };
 
 bool mt_gemm_rs_supported(const RsDesc& d);

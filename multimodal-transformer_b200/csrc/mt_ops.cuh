@@ -75,7 +75,7 @@ int mt_attn_tc_fwd_run(int B, int T, int d, int h, const void* qkv, const float*
 // G > 1 as in mt_attn_tc_fwd_run; aux holds G * mt_attn_bwd_ws_floats(B, T, h) floats, dbias of group g at dbias + g * dbias_gstride
 int mt_attn_tc_bwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse, const void* dout,
                        void* dqkv, DropCfg drop, float* dbias, float* aux, cudaStream_t st, int G = 1, const DropCfg* drops = nullptr,
-                       size_t dbias_gstride = 0);
+                       size_t dbias_gstride = 0, bool d_ready = false);      // d_ready: aux row 1 (D) was written by the caller
 // workspace of any attention backward (Dws of mt_attn_bwd_run), in floats
 static inline size_t mt_attn_bwd_ws_floats(int B, int T, int h) { return 4 * (size_t)B * (size_t)(T < 128 ? 128 : T) * (size_t)h + 64; }
 
@@ -89,4 +89,9 @@ int mt_attn_bwd_run(int dtype, int B, int T, int d, int h, const void* qkv, cons
 int mt_attn_group_fwd_run(int dtype, int G, int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse,
                           const DropCfg* drops, cudaStream_t st, const int* klen = nullptr);
 int mt_attn_group_bwd_run(int dtype, int G, int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse,
-                          const void* dout, void* dqkv, const DropCfg* drops, float* Dws, cudaStream_t st, float* dbias, size_t dbias_gstride);
+                          const void* dout, void* dqkv, const DropCfg* drops, float* Dws, cudaStream_t st, float* dbias, size_t dbias_gstride,
+                          bool d_ready = false);
+// true when mt_attn_group_bwd_run will take the tcgen05 engine for these arguments (then the caller may pre-fill D = rowsum(dout . out)
+// into Dws[((b * h + head) * 4 + 1) * 128 + q] and pass d_ready)
+bool mt_attn_group_bwd_uses_tc(int dtype, int G, int B, int T, int d, int h, const void* qkv, const void* out, const void* dout,
+                               const void* dqkv, const float* Dws, const float* dbias);

@@ -150,7 +150,23 @@ def test_grouped_stacks_equal_per_stack_calls():
                     res.append((pred.detach().float().cpu(), {k: p.grad.detach().cpu() for k, p in model.named_parameters() if p.grad is not None}))
                 finally:
                     mtb.set_grouped_stacks(old)
-            (pg, gg), (pu, gu) = res
+            if mode == 'bf16':      # ... and against the streaming GEMM engine with the stand-alone attention-backward preparation pass
+                old = _lib.lib().mt_tune(5, 1)
+                try:
+                    model = mtb.MultiTransformer(MODS, dims, N=N).train(); model.load_state_dict(sd)
+                    mtb.fix_seed(1234)
+                    pred = model({k: t(v).to(DEV) for k, v in inputs.items()}, t(mask).to(DEV), lengths)
+                    (((pred - t(target).to(DEV)) ** 2).sum() / sum(lengths)).backward()
+                    res.append((pred.detach().float().cpu(), {k: p.grad.detach().cpu() for k, p in model.named_parameters() if p.grad is not None}))
+                finally:
+                    _lib.lib().mt_tune(5, old)
+                (ps, gs_) = res[2]
+                gmax_s = max(v.abs().max().item() for v in gs_.values())
+                assert (res[0][0] - ps).abs().max().item() <= tol * max(1.0, ps.abs().max().item())
+                for k in gs_:
+                    e = (res[0][1][k] - gs_[k]).abs().max().item()
+                    assert e <= gtol * max(gs_[k].abs().max().item(), 1e-3 * gmax_s), ('streaming engine', k, e)
+            (pg, gg), (pu, gu) = res[0], res[1]
             assert (pg - pu).abs().max().item() <= tol * max(1.0, pu.abs().max().item()), mode
             assert gg.keys() == gu.keys()
             gmax = max(v.abs().max().item() for v in gu.values())
