@@ -385,6 +385,9 @@ int mt_attn_fwd_run(int dtype, int B, int T_, int d, int h, const void* qkv, con
   if (dtype == MT_BF16 && !g_attn_force_ffma && !g_mt_attn_no_tc && !mt_attn_force_tiled_on() && mt_attn_tc_supported(B, T_, d, h) &&
       !(((uintptr_t)qkv | (uintptr_t)out) & 15))
     return mt_attn_tc_fwd_run(B, T_, d, h, qkv, mask, out, lse, drop, st, klen);
+  if (dtype == MT_BF16 && !g_attn_force_ffma && !g_mt_attn_no_tc && !mt_attn_force_tiled_on() && !klen && T_ > 128 && mt_attn_flash_supported(B, T_, d, h) &&
+      !(((uintptr_t)qkv | (uintptr_t)out) & 15))
+    return mt_attn_flash_fwd_run(B, T_, d, h, qkv, mask, out, lse, drop, st);
   if (dtype == MT_BF16 && !g_attn_force_ffma && mt_attn_mma_supported(B, T_, d, h)) return mt_attn_mma_fwd_run(B, T_, d, h, qkv, mask, out, lse, drop, st, klen);
   if (dtype == MT_BF16) return fwd_dispatch<bf16>(B, T_, d, h, qkv, mask, out, lse, drop, st, klen);
   return fwd_dispatch<float>(B, T_, d, h, qkv, mask, out, lse, drop, st, klen);

@@ -76,6 +76,9 @@ int mt_attn_tc_fwd_run(int B, int T, int d, int h, const void* qkv, const float*
 int mt_attn_tc_bwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse, const void* dout,
                        void* dqkv, DropCfg drop, float* dbias, float* aux, cudaStream_t st, int G = 1, const DropCfg* drops = nullptr,
                        size_t dbias_gstride = 0, bool d_ready = false);      // d_ready: aux row 1 (D) was written by the caller
+// ---- tcgen05 / TMEM flash attention for long sequences, 64-wide heads (mt_attention_flash.cu), bf16 ------------------------
+bool mt_attn_flash_supported(int B, int T, int d, int h);
+int mt_attn_flash_fwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop, cudaStream_t st);
 // workspace of any attention backward (Dws of mt_attn_bwd_run), in floats
 static inline size_t mt_attn_bwd_ws_floats(int B, int T, int h) { return 4 * (size_t)B * (size_t)(T < 128 ? 128 : T) * (size_t)h + 64; }
 
