@@ -404,6 +404,9 @@ int mt_attn_bwd_run(int dtype, int B, int T_, int d, int h, const void* qkv, con
     float* db = h <= 8 ? dbias : nullptr;
     MT_TRY(mt_attn_tc_bwd_run(B, T_, d, h, qkv, mask, out, lse, dout, dqkv, drop, db, Dws, st));
     done = db != nullptr;
+  } else if (dtype == MT_BF16 && !g_attn_force_ffma && !g_mt_attn_no_tc && !mt_attn_force_tiled_on() && T_ > 128 && mt_attn_flash_supported(B, T_, d, h) &&
+             !(((uintptr_t)qkv | (uintptr_t)out | (uintptr_t)dout | (uintptr_t)dqkv | (uintptr_t)Dws) & 15)) {
+    MT_TRY(mt_attn_flash_bwd_run(B, T_, d, h, qkv, mask, out, lse, dout, dqkv, drop, Dws, st));      // long sequences, 64-wide heads: tcgen05 flash
   } else if (dtype == MT_BF16 && !g_attn_force_ffma && mt_attn_mma_supported(B, T_, d, h))
     MT_TRY(mt_attn_mma_bwd_run(B, T_, d, h, qkv, mask, out, lse, dout, dqkv, drop, st, dbias, &done));
   else if (dtype == MT_BF16) MT_TRY(bwd_dispatch<bf16>(B, T_, d, h, qkv, mask, out, lse, dout, dqkv, drop, Dws, st));

@@ -288,6 +288,373 @@ __global__ void __launch_bounds__(FF_NT, 1) attn_flash_fwd_kernel(const __grid_c
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------------------------------------------
+// A work item is (narrative, head, key tile j): K_j / V_j stay in shared memory and dK_j / dV_j accumulate in TMEM while the query tiles
+// i = 0 .. T/128 - 1 stream through a TMA ring (Q_i, dO_i and the four per-query vectors lse*log2e | D | score scale | gradient scale).
+// Per block (i, j), in the transposed formulation of mt_attention_tc.cu (lane = key):
+//   S^T = K_j Q_i^T, dP^T = V_j dO_i^T (tcgen05.mma into TMEM)  ->  16 compute warps (warp group g: queries 32 g .. 32 g + 31, thread =
+//   key row) recompute P^T = exp2(S^T * scale - lse), apply the pair-hash dropout mask, form dS^T = P^T (dP^T * keep - D) * scale
+//   ->  P^T (bf16) goes to its OWN TMEM columns, dS^T to shared memory (double-buffered), so S^T / dP^T of block i + 1 are issued as soon
+//   as the compute warps have read block i, in front of the second round of block i:
+//   dV_j += P^T dO_i (A from TMEM), dK_j += dS^T Q_i, dQ_i = dS K_j (A from shared memory, K-major / MN-major views of the same tile).
+// dQ_i is a partial sum over the key tiles: it leaves with fp32 vector reductions into a [B*T, d] accumulation buffer (the classic
+// flash-attention backward); a last pass rounds it into dqkv.  dK_j / dV_j are stored once per item.
+constexpr int NSB = 3;                                   // Q / dO / aux ring stages
+constexpr int FB_NT = 576;                               // warps 0-15 compute, 16 TMA, 17 MMA issue + TMEM
+constexpr int FB_AUX = 4 * TQ * 4;                       // four per-query vectors
+constexpr int FB_STAGE = 2 * TILE_B + FB_AUX;
+constexpr int FB_DS = 2 * TILE_B;                        // dS^T of one block: [128 keys x 128 queries] bf16 as two 64-query tiles
+constexpr int FB_SMEM = 2 * TILE_B + NSB * FB_STAGE + 2 * FB_DS + 512 + 1024;
+
+struct FlashBwdArgs {
+  int B, T, d, h, n_t, n_items, t_stride;  // n_t = tiles of 128 (queries and keys), t_stride = row stride of aux
+  const float* aux;                        // [B][h][4][t_stride]
+  float* dq_acc;                           // fp32 [B*T, d], zero-initialised
+  bf16* dqkv;
+  DropCfg drop;
+};
+
+__global__ void __launch_bounds__(FB_NT, 1)
+attn_flash_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do, const __grid_constant__ FlashBwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* kv_s = smem;                                  // K_j | V_j
+  uint8_t* ring = smem + 2 * TILE_B;                     // stage: Q_i | dO_i | aux
+  uint8_t* ds_s = ring + NSB * FB_STAGE;                 // two dS^T buffers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ds_s + 2 * FB_DS);
+  uint64_t* full = bars;                    // [NSB]
+  uint64_t* empty = bars + NSB;             // [NSB]
+  uint64_t* kv_full = empty + NSB;          // [1]
+  uint64_t* kv_free = kv_full + 1;          // [1]
+  uint64_t* s_full = kv_free + 1;           // [1]  S^T, dP^T of the block are in TMEM
+  uint64_t* s_free = s_full + 1;            // [1]  ... and have been read (512 arrivals)
+  uint64_t* p_ready = s_free + 1;           // [1]  P^T (TMEM) and dS^T (shared) are in place (512 arrivals)
+  uint64_t* pt_free = p_ready + 1;          // [1]  dV MMAs of the block are complete: P^T may be overwritten
+  uint64_t* ds_free = pt_free + 1;          // [2]  dK / dQ MMAs that read this dS^T buffer are complete
+  uint64_t* g_full = ds_free + 2;           // [1]  dQ of the block is in TMEM
+  uint64_t* dq_free = g_full + 1;           // [1]  ... and has been drained (512 arrivals)
+  uint64_t* acc_full = dq_free + 1;         // [1]  dK, dV of the item are final
+  uint64_t* acc_read = acc_full + 1;        // [1]  ... and have been stored (512 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_read + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_t = a.n_t, T = a.T;
+  if (warp == 16 && lane == 0) {
+    tma_prefetch_desc(&map_qkv);
+    tma_prefetch_desc(&map_do);
+    for (int s = 0; s < NSB; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(kv_full, 1); mbar_init(kv_free, 1); mbar_init(s_full, 1); mbar_init(s_free, 512); mbar_init(p_ready, 512);
+    mbar_init(pt_free, 1); mbar_init(&ds_free[0], 1); mbar_init(&ds_free[1], 1); mbar_init(g_full, 1); mbar_init(dq_free, 512);
+    mbar_init(acc_full, 1); mbar_init(acc_read, 512);
+    mbar_init_fence();
+  }
+  if (warp == 17) tmem_alloc<512>(tmem_slot);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: S^T [0,128) | dP^T [128,256) | P^T packed bf16 [256,320) | dV [320,384) | dK [384,448) | dQ [448,512)
+  const int n_my = ((int)blockIdx.x < a.n_items) ? (a.n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp == 16) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t fill = 0;
+      for (int it = 0; it < n_my; ++it) {
+        const int item = (int)blockIdx.x + it * (int)gridDim.x;
+        const int jt = item % n_t, bh = item / n_t, hd = bh % a.h, b = bh / a.h;
+        const int row0 = b * T;
+        if (it > 0) mbar_wait(kv_free, (uint32_t)(it - 1) & 1u);
+        mbar_expect_tx(kv_full, 2 * TILE_B);
+        tma_load_2d(kv_s, &map_qkv, a.d + hd * HDF, row0 + jt * TQ, kv_full);
+        tma_load_2d(kv_s + TILE_B, &map_qkv, 2 * a.d + hd * HDF, row0 + jt * TQ, kv_full);
+        for (int i = 0; i < n_t; ++i, ++fill) {
+          const int stage = (int)(fill % NSB);
+          mbar_wait(&empty[stage], ((fill / NSB) & 1u) ^ 1u);
+          uint8_t* sb = ring + stage * FB_STAGE;
+          mbar_expect_tx(&full[stage], (uint32_t)FB_STAGE);
+          tma_load_2d(sb, &map_qkv, hd * HDF, row0 + i * TQ, &full[stage]);
+          tma_load_2d(sb + TILE_B, &map_do, hd * HDF, row0 + i * TQ, &full[stage]);
+          const float* ax = a.aux + (size_t)bh * 4 * a.t_stride + (size_t)i * TQ;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) bulk_load(sb + 2 * TILE_B + k * TQ * 4, ax + (size_t)k * a.t_stride, TQ * 4, &full[stage]);
+        }
+      }
+    }
+  } else if (warp == 17) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc(TQ, TQ, 0, 0);       // S^T / dP^T: both operands K-major
+      const uint32_t idesc_ts = make_idesc(TQ, HDF, 0, 1);     // dV (A in TMEM) and dK (A K-major in shared memory), B MN-major
+      const uint32_t idesc_dq = make_idesc(TQ, HDF, 1, 1);     // dQ: A = dS from shared memory, MN-major
+      const uint32_t kv_u32 = smem_u32(kv_s), ring_u32 = smem_u32(ring), ds_u32 = smem_u32(ds_s);
+      uint32_t use = 0, blk = 0;            // ring uses / blocks issued so far (S^T side)
+      uint32_t blk2 = 0, use2 = 0;          // blocks whose second round has been issued
+      auto round2 = [&](bool first_of_item) {
+        const int stage = (int)(use2 % NSB);
+        const uint32_t sq = ring_u32 + (uint32_t)(stage * FB_STAGE), sg = sq + TILE_B;
+        const uint32_t sds = ds_u32 + (uint32_t)((blk2 & 1u) * FB_DS);
+        mbar_wait(p_ready, blk2 & 1u);
+        fence_after();
+        const uint64_t dgm = make_desc(sg, 8192, 1024), dqm = make_desc(sq, 8192, 1024), dkm = make_desc(kv_u32, 8192, 1024);
+#pragma unroll
+        for (int ks = 0; ks < TQ / 16; ++ks)      // dV += P^T dO: A = P^T in TMEM (8 columns per 16 queries)
+          mma_ts(tmem_base + 320, tmem_base + (uint32_t)(256 + 8 * ks), dgm + (uint64_t)(128 * ks), idesc_ts, (!first_of_item || ks > 0) ? 1u : 0u);
+        commit(pt_free);
+#pragma unroll
+        for (int ks = 0; ks < TQ / 16; ++ks) {    // dK += dS^T Q: A K-major over the queries, two 64-query tiles
+          const uint64_t da = make_desc(sds + (uint32_t)((ks >> 2) * TILE_B + (ks & 3) * 32), 16, 1024);
+          mma_ss(tmem_base + 384, da, dqm + (uint64_t)(128 * ks), idesc_ts, (!first_of_item || ks > 0) ? 1u : 0u);
+        }
+        if (blk2 > 0) { mbar_wait(dq_free, (blk2 - 1) & 1u); fence_after(); }
+        {
+          const uint64_t dsm = make_desc(sds, TILE_B, 1024);
+#pragma unroll
+          for (int ks = 0; ks < TQ / 16; ++ks) mma_ss(tmem_base + 448, dsm + (uint64_t)(128 * ks), dkm + (uint64_t)(128 * ks), idesc_dq, ks > 0);
+        }
+        commit(g_full);
+        commit(&ds_free[blk2 & 1u]);
+        commit(&empty[stage]);
+        ++blk2; ++use2;
+      };
+      for (int it = 0; it < n_my; ++it) {
+        mbar_wait(kv_full, (uint32_t)it & 1u);
+        fence_after();
+        if (it > 0) { mbar_wait(acc_read, (uint32_t)(it - 1) & 1u); fence_after(); }
+        const uint64_t dk0 = make_desc(kv_u32, 16, 1024), dv0 = make_desc(kv_u32 + TILE_B, 16, 1024);
+        for (int i = 0; i < n_t; ++i, ++use, ++blk) {
+          const int stage = (int)(use % NSB);
+          mbar_wait(&full[stage], (use / NSB) & 1u);
+          fence_after();
+          if (blk > 0) { mbar_wait(s_free, (blk - 1) & 1u); fence_after(); }
+          const uint32_t sq = ring_u32 + (uint32_t)(stage * FB_STAGE), sg = sq + TILE_B;
+          const uint64_t dq0 = make_desc(sq, 16, 1024), dg0 = make_desc(sg, 16, 1024);
+#pragma unroll
+          for (int ks = 0; ks < HDF / 16; ++ks) mma_ss(tmem_base, dk0 + (uint64_t)(2 * ks), dq0 + (uint64_t)(2 * ks), idesc_s, ks > 0);
+#pragma unroll
+          for (int ks = 0; ks < HDF / 16; ++ks) mma_ss(tmem_base + 128, dv0 + (uint64_t)(2 * ks), dg0 + (uint64_t)(2 * ks), idesc_s, ks > 0);
+          commit(s_full);
+          if (i > 0) round2(i == 1);
+        }
+        round2(n_t == 1);
+        commit(kv_free);
+        commit(acc_full);
+      }
+    }
+  } else {
+    // ===== compute: warp group g owns the queries [32 g, 32 g + 32) of every block, thread = key row j =====
+    const DropCfg drop = mt_drop_resolve(a.drop);
+    const int g = warp >> 2, j = threadIdx.x & 127;
+    const uint32_t tl = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t P2 = (uint32_t)(T + 1) >> 1;
+    const uint32_t thr_hi = (drop.thresh >> 16) << 16;
+    const bool dropping = drop.thresh != 0u;
+    const uint32_t odd = (uint32_t)j & 1u;
+    const uint64_t ds2 = pk2(drop.scale, drop.scale);
+    uint32_t fillc = 0, blk = 0;
+    for (int it = 0; it < n_my; ++it) {
+      const int item = (int)blockIdx.x + it * (int)gridDim.x;
+      const int jt = item % n_t, bh = item / n_t, hd = bh % a.h, b = bh / a.h;
+      const int jg = jt * TQ + j;                      // key index inside the narrative
+      const bool key_ok = jg < T;
+      for (int i = 0; i < n_t; ++i, ++fillc, ++blk) {
+        const int stage = (int)(fillc % NSB);
+        const float* ax = reinterpret_cast<const float*>(ring + stage * FB_STAGE + 2 * TILE_B);
+        uint8_t* dsb = ds_s + (blk & 1u) * FB_DS + (g >> 1) * TILE_B;      // this group's 64-query tile of the dS^T operand
+        // pair index of (query q, key pair jg >> 1) = (bh T + q) P2 + (jg >> 1); this lane draws for the queries q + (j & 1)
+        const uint64_t p64 = ((uint64_t)bh * (uint64_t)T + (uint64_t)(i * TQ + g * 32) + odd) * (uint64_t)P2 + (uint64_t)(jg >> 1);
+        const uint32_t plo = (uint32_t)p64, phi = (uint32_t)(p64 >> 32) * 0xC2B2AE35u;
+        const bool wraps = plo > 0xFFFFFFFFu - 32u * P2;
+        mbar_wait(&full[stage], (fillc / NSB) & 1u);         // per-query vectors (the MMA warp waits on the same phase for the tiles)
+        mbar_wait(s_full, blk & 1u);
+        fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          const int q0 = g * 32 + cc * 16;
+          uint32_t s[16], dp[16], pkp[8], pks[8];
+          ld16(tl + (uint32_t)q0, s);
+          ld16(tl + (uint32_t)(128 + q0), dp);
+          ld_wait();
+          if (cc == 1) { fence_before(); mbar_arrive(s_free); }      // this thread's last read of S^T / dP^T
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) {
+            const int q = q0 + e;
+            const float4 L = *reinterpret_cast<const float4*>(ax + q), D = *reinterpret_cast<const float4*>(ax + TQ + q);
+            const float4 rs = *reinterpret_cast<const float4*>(ax + 2 * TQ + q), gs = *reinterpret_cast<const float4*>(ax + 3 * TQ + q);
+            const float Dk[4] = {D.x, D.y, D.z, D.w};
+            float p[4], t[4];
+            upk2(fma2(pk2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), pk2(rs.x, rs.y), pk2(-L.x, -L.y)), p[0], p[1]);
+            upk2(fma2(pk2(__uint_as_float(s[e + 2]), __uint_as_float(s[e + 3])), pk2(rs.z, rs.w), pk2(-L.z, -L.w)), p[2], p[3]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) p[k] = (key_ok && i * TQ + q + k < T) ? ex2(p[k]) : 0.f;
+            // t = dP . keep-scale - D ; without a kept draw the probability's gradient is -D
+            upk2(fma2(pk2(__uint_as_float(dp[e]), __uint_as_float(dp[e + 1])), ds2, pk2(-D.x, -D.y)), t[0], t[1]);
+            upk2(fma2(pk2(__uint_as_float(dp[e + 2]), __uint_as_float(dp[e + 3])), ds2, pk2(-D.z, -D.w)), t[2], t[3]);
+            float pd[4] = {p[0], p[1], p[2], p[3]};
+            if (dropping) {
+              // the 32-bit draw of (query, key pair jg >> 1) serves keys jg and jg ^ 1: this lane draws for query q + (j & 1), its
+              // neighbour for the other query of the pair, and they swap
+#pragma unroll
+              for (int k = 0; k < 4; k += 2) {
+                const uint32_t off = (uint32_t)(cc * 16 + e + k) * P2;
+                const uint32_t mine = wraps ? mt_draw32(drop, p64 + (uint64_t)off) : mt_mix32((plo + off) ^ drop.key ^ phi);
+                const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+                const uint32_t b0 = odd ? other : mine, b1 = odd ? mine : other;
+                const bool k0 = odd ? (b0 >= thr_hi) : ((b0 << 16) >= thr_hi), k1 = odd ? (b1 >= thr_hi) : ((b1 << 16) >= thr_hi);
+                pd[k] = k0 ? p[k] : 0.f;
+                t[k] = k0 ? t[k] : -Dk[k];
+                pd[k + 1] = k1 ? p[k + 1] : 0.f;
+                t[k + 1] = k1 ? t[k + 1] : -Dk[k + 1];
+              }
+            }
+            float ev[4];
+            upk2(mul2(mul2(pk2(p[0], p[1]), pk2(gs.x, gs.y)), pk2(t[0], t[1])), ev[0], ev[1]);
+            upk2(mul2(mul2(pk2(p[2], p[3]), pk2(gs.z, gs.w)), pk2(t[2], t[3])), ev[2], ev[3]);
+            pkp[e >> 1] = pack_bf2(pd[0], pd[1]);
+            pkp[(e >> 1) + 1] = pack_bf2(pd[2], pd[3]);
+            pks[e >> 1] = pack_bf2(ev[0], ev[1]);
+            pks[(e >> 1) + 1] = pack_bf2(ev[2], ev[3]);
+          }
+          if (cc == 0) {      // the block's first writes: the previous block's dV MMAs have read P^T, and the dK / dQ MMAs of block
+                              // blk - 2 have read this dS^T buffer
+            if (blk > 0) mbar_wait(pt_free, (blk - 1) & 1u);
+            if (blk > 1) mbar_wait(&ds_free[blk & 1u], ((blk >> 1) - 1) & 1u);
+            fence_after();
+          }
+          st8(tl + (uint32_t)(256 + g * 16 + cc * 8), pkp);
+          // dS^T row of this key: 16 queries = two 16-byte chunks of the 64-query tile (g >> 1), chunks (g & 1) * 4 + cc * 2 ..
+          *reinterpret_cast<uint4*>(dsb + sw128_off(j, (g & 1) * 4 + cc * 2)) = make_uint4(pks[0], pks[1], pks[2], pks[3]);
+          *reinterpret_cast<uint4*>(dsb + sw128_off(j, (g & 1) * 4 + cc * 2 + 1)) = make_uint4(pks[4], pks[5], pks[6], pks[7]);
+        }
+        st_wait();
+        fence_proxy_async();
+        fence_before();
+        mbar_arrive(p_ready);
+        // ---- drain dQ of the PREVIOUS block (its second round was issued behind this block's S^T): rows = queries, this group's
+        //      16 columns, fp32 vector reductions into the accumulation buffer ----
+        if (i > 0) {
+          mbar_wait(g_full, (blk - 1) & 1u);
+          fence_after();
+          uint32_t dq[16];
+          ld16(tl + (uint32_t)(448 + g * 16), dq);
+          ld_wait();
+          fence_before();
+          mbar_arrive(dq_free);
+          const int qg = (i - 1) * TQ + j;
+          if (qg < T) {
+            float* dst = a.dq_acc + ((size_t)b * T + qg) * a.d + hd * HDF + g * 16;
+#pragma unroll
+            for (int v4 = 0; v4 < 4; ++v4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * v4), "f"(__uint_as_float(dq[4 * v4])),
+                           "f"(__uint_as_float(dq[4 * v4 + 1])), "f"(__uint_as_float(dq[4 * v4 + 2])), "f"(__uint_as_float(dq[4 * v4 + 3]))
+                           : "memory");
+          }
+        }
+      }
+      // ---- item tail: dQ of the last block, then dK / dV of the key tile ----
+      {
+        mbar_wait(g_full, (blk - 1) & 1u);
+        fence_after();
+        uint32_t dq[16];
+        ld16(tl + (uint32_t)(448 + g * 16), dq);
+        ld_wait();
+        fence_before();
+        mbar_arrive(dq_free);
+        const int qg = (n_t - 1) * TQ + j;
+        if (qg < T) {
+          float* dst = a.dq_acc + ((size_t)b * T + qg) * a.d + hd * HDF + g * 16;
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * v4), "f"(__uint_as_float(dq[4 * v4])),
+                         "f"(__uint_as_float(dq[4 * v4 + 1])), "f"(__uint_as_float(dq[4 * v4 + 2])), "f"(__uint_as_float(dq[4 * v4 + 3]))
+                         : "memory");
+        }
+      }
+      mbar_wait(acc_full, (uint32_t)it & 1u);
+      fence_after();
+      uint32_t gv[16], gk[16];
+      ld16(tl + (uint32_t)(320 + g * 16), gv);
+      ld16(tl + (uint32_t)(384 + g * 16), gk);
+      ld_wait();
+      fence_before();
+      mbar_arrive(acc_read);
+      if (key_ok) {
+        bf16* gp = a.dqkv + ((size_t)b * T + jg) * (3 * a.d) + hd * HDF + g * 16;
+        float fv[16];
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) upk2(mul2(pk2(__uint_as_float(gv[e]), __uint_as_float(gv[e + 1])), ds2), fv[e], fv[e + 1]);      // dV still lacks the keep scale
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint4 u;
+          u.x = pack_bf2(__uint_as_float(gk[8 * hh]), __uint_as_float(gk[8 * hh + 1])); u.y = pack_bf2(__uint_as_float(gk[8 * hh + 2]), __uint_as_float(gk[8 * hh + 3]));
+          u.z = pack_bf2(__uint_as_float(gk[8 * hh + 4]), __uint_as_float(gk[8 * hh + 5])); u.w = pack_bf2(__uint_as_float(gk[8 * hh + 6]), __uint_as_float(gk[8 * hh + 7]));
+          *reinterpret_cast<uint4*>(gp + a.d + 8 * hh) = u;
+          uint4 w;
+          w.x = pack_bf2(fv[8 * hh], fv[8 * hh + 1]); w.y = pack_bf2(fv[8 * hh + 2], fv[8 * hh + 3]);
+          w.z = pack_bf2(fv[8 * hh + 4], fv[8 * hh + 5]); w.w = pack_bf2(fv[8 * hh + 6], fv[8 * hh + 7]);
+          *reinterpret_cast<uint4*>(gp + 2 * a.d + 8 * hh) = w;
+        }
+      }
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 17) {
+    fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// per-query scalars of the backward for any T: aux[b][hd][k][q] with row stride t_stride; one warp per token row (coalesced reads of
+// out / dout), D closes inside the head's 8-lane group
+__global__ void __launch_bounds__(256) flash_prep_kernel(int B, int T, int d, int h, int t_stride, const bf16* __restrict__ out,
+                                                         const bf16* __restrict__ dout, const float* __restrict__ lse,
+                                                         const float* __restrict__ mask, float* __restrict__ aux, float scale) {
+  const int lane = threadIdx.x & 31;
+  const long long rows = (long long)B * T;
+  for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * 8) {
+    const int b = (int)(row / T), q = (int)(row % T);
+    const bool masked = mask != nullptr && mask[row] == 0.f;
+    for (int c0 = 0; c0 < d; c0 += 256) {
+      const int col = c0 + lane * 8;
+      const bool valid = col < d;
+      const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+      const uint4 o = valid ? *reinterpret_cast<const uint4*>(out + (size_t)row * d + col) : zero;
+      const uint4 gq = valid ? *reinterpret_cast<const uint4*>(dout + (size_t)row * d + col) : zero;
+      const uint32_t ow[4] = {o.x, o.y, o.z, o.w}, gw[4] = {gq.x, gq.y, gq.z, gq.w};
+      float D = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 of = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ow[k]));
+        const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[k]));
+        D += of.x * gf.x + of.y * gf.y;
+      }
+#pragma unroll
+      for (int s = 1; s < HDF / 8; s <<= 1) D += __shfl_xor_sync(0xffffffffu, D, s);
+      if (valid && (lane & (HDF / 8 - 1)) == 0) {
+        const size_t bh = (size_t)b * h + col / HDF;
+        float* ap = aux + bh * 4 * t_stride;
+        ap[q] = lse[bh * T + q] * LOG2E_F;
+        ap[t_stride + q] = D;
+        ap[2 * t_stride + q] = masked ? 0.f : scale * LOG2E_F;
+        ap[3 * t_stride + q] = masked ? 0.f : scale;
+      }
+    }
+  }
+}
+
+// dqkv[:, 0:d] = bf16(dq_acc)
+__global__ void flash_dq_finish_kernel(long long rows, int d, const float* __restrict__ acc, bf16* __restrict__ dqkv) {
+  const long long n4 = rows * (d / 4);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (d / 4);
+    const int c = (int)(i % (d / 4)) * 4;
+    st4(dqkv + r * 3 * d + c, ld4(acc + r * d + c));
+  }
+}
+
 int num_sms_f() {
   int dev = 0, n = 0;
   cudaGetDevice(&dev);
@@ -322,5 +689,44 @@ int mt_attn_flash_fwd_run(int B, int T, int d, int h, const void* qkv, const flo
   mt_prof_work(4.0 * B * (double)T * T * d, (double)B * T * d * 4.0 * 2.0);
   attn_flash_fwd_kernel<<<grid, FF_NT, FF_SMEM, st>>>(map, a);
   MT_LAUNCH_CHECK();
+  return MT_OK;
+}
+
+// Dws layout: per-query scalars [B][h][4][Tpad] then the fp32 dQ accumulation buffer [B*T, d]
+int mt_attn_flash_bwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse, const void* dout,
+                          void* dqkv, DropCfg drop, float* ws, cudaStream_t st) {
+  if (!mt_attn_flash_supported(B, T, d, h)) return MT_ERR_UNSUPPORTED;
+  if (((uintptr_t)qkv & 15) || ((uintptr_t)out & 15) || ((uintptr_t)dout & 15) || ((uintptr_t)dqkv & 15) || ((uintptr_t)ws & 15)) return MT_ERR_ALIGN;
+  const int n_t = (T + TQ - 1) / TQ, tpad = n_t * TQ;
+  float* aux = ws;
+  float* dq_acc = ws + (size_t)B * h * 4 * tpad;
+  MT_CUDA(cudaMemsetAsync(dq_acc, 0, sizeof(float) * (size_t)B * T * d, st));
+  {
+    const long long rows = (long long)B * T;
+    long long blocks = (rows + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    flash_prep_kernel<<<(unsigned)blocks, 256, 0, st>>>(B, T, d, h, tpad, (const bf16*)out, (const bf16*)dout, lse, mask, aux, 1.0f / sqrtf((float)HDF));
+    MT_LAUNCH_CHECK();
+  }
+  CUtensorMap map_qkv, map_do;
+  MT_TRY(make_map_2d(&map_qkv, qkv, (uint64_t)3 * d, (uint64_t)B * T, (uint64_t)3 * d, 64, TQ));
+  MT_TRY(make_map_2d(&map_do, dout, (uint64_t)d, (uint64_t)B * T, (uint64_t)d, 64, TQ));
+  FlashBwdArgs a;
+  a.B = B; a.T = T; a.d = d; a.h = h; a.n_t = n_t; a.n_items = B * h * n_t; a.t_stride = tpad;
+  a.aux = aux; a.dq_acc = dq_acc; a.dqkv = (bf16*)dqkv; a.drop = drop;
+  static MtPerDeviceOnce once;
+  if (once.first()) MT_CUDA(cudaFuncSetAttribute(attn_flash_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM));
+  const int sms = num_sms_f();
+  const int grid = a.n_items < sms ? a.n_items : sms;
+  mt_prof_work(10.0 * B * (double)T * T * d, (double)B * T * d * 8.0 * 2.0);
+  attn_flash_bwd_kernel<<<grid, FB_NT, FB_SMEM, st>>>(map_qkv, map_do, a);
+  MT_LAUNCH_CHECK();
+  {
+    const long long n4 = (long long)B * T * (d / 4);
+    long long blocks = (n4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    flash_dq_finish_kernel<<<(unsigned)blocks, 256, 0, st>>>((long long)B * T, d, dq_acc, (bf16*)dqkv);
+    MT_LAUNCH_CHECK();
+  }
   return MT_OK;
 }

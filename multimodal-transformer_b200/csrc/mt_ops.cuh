@@ -79,8 +79,15 @@ int mt_attn_tc_bwd_run(int B, int T, int d, int h, const void* qkv, const float*
 // ---- tcgen05 / TMEM flash attention for long sequences, 64-wide heads (mt_attention_flash.cu), bf16 ------------------------
 bool mt_attn_flash_supported(int B, int T, int d, int h);
 int mt_attn_flash_fwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop, cudaStream_t st);
+// ws: mt_attn_bwd_ws_floats(B, T, h) floats; the QKV bias gradient is NOT produced (the caller column-sums dqkv)
+int mt_attn_flash_bwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse, const void* dout,
+                          void* dqkv, DropCfg drop, float* ws, cudaStream_t st);
 // workspace of any attention backward (Dws of mt_attn_bwd_run), in floats
-static inline size_t mt_attn_bwd_ws_floats(int B, int T, int h) { return 4 * (size_t)B * (size_t)(T < 128 ? 128 : T) * (size_t)h + 64; }
+// (per-query scalars [B][h][4][T rounded up to 128], plus -- long sequences -- the fp32 dQ accumulation buffer [B*T, 64 h] of the flash backward)
+static inline size_t mt_attn_bwd_ws_floats(int B, int T, int h) {
+  const size_t tpad = ((size_t)T + 127) / 128 * 128;
+  return 4 * (size_t)B * tpad * (size_t)h + 64 + (T > 128 ? (size_t)B * (size_t)T * 64 * (size_t)h : 0);
+}
 
 // ---- attention (mt_attention.cu) ---------------------------------------------------------------------
 int mt_attn_fwd_run(int dtype, int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop,
