@@ -57,7 +57,7 @@ def parse():
     ap.add_argument('--config', default='c2', choices=sorted(CONFIGS), help='BASELINE.json configuration (c2 = headline; c3 = c2 on N GPUs)')
     ap.add_argument('--batch', type=int, default=0, help='narratives per GPU (0 = the configuration\'s own)')
     ap.add_argument('--seq', type=int, default=0, help='windows per narrative (0 = the configuration\'s own)')
-    ap.add_argument('--micro', type=int, default=8, help='c5: narratives per micro-batch')
+    ap.add_argument('--micro', type=int, default=64, help='c5: narratives per micro-batch')
     ap.add_argument('--layers', type=int, default=6)
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--fp32-inputs', action='store_true', help='bf16 mode: send the window features to the device as fp32 (cast there) instead of bf16')

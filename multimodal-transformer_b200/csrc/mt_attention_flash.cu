@@ -3,16 +3,17 @@
 // row becomes uniform over all T keys), fill value -1e9, live padded keys, softmax, dropout on the probabilities, P.V, heads merged in
 // place; nothing [T, T] ever leaves the SM.
 //
-// Forward.  A work item is (narrative, head, PAIR of 128-query tiles); the two warp groups of the CTA own one query tile each and share
-// every K / V tile of the item (one TMA box [128 x 64] each per key tile, 3-stage ring).  Two passes over the keys instead of an online
+// Forward.  A work item is (narrative, head, PAIR of 128-query tiles); each query tile has two softmax warp groups (thread = query row,
+// the groups split the key columns) and both tiles share every K / V tile of the item (one TMA box [128 x 64] each per key tile,
+// 3-stage ring).  Two passes over the keys instead of an online
 // rescale of the TMEM accumulator:
 //   pass 1: S = Q K^T (tcgen05.mma M128 N128 K64 into TMEM) -> tcgen05.ld -> running row maximum (no exponentials);
-//   pass 2: S again -> p = exp2(s * scale - max) with the FINAL maximum, row sum, pair-hash dropout, P (bf16) written back over S as the
-//           TMEM A operand -> O += P V (M128 N64 K128, accumulating across key tiles, never rescaled).
+//   pass 2: S again -> p = exp2(s * scale - max) with the FINAL maximum, row sum, pair-hash dropout, P (bf16) into its own TMEM columns as the
+//           A operand -> O += P V (M128 N64 K128, accumulating across key tiles, never rescaled).
 // The extra Q K^T pass costs a third more MMA work on a tensor pipe that idles anyway -- the per-probability instruction stream (exp2,
 // dropout hash, conversions) is the bound -- and removes the correction warp / conditional-rescale machinery altogether.
-// One thread issues every MMA in program order; the tensor pipe executes them in that order, so S of key tile kt + 1 (issued after the
-// P.V product of kt) cannot overwrite P before it has been read.
+// S, P and O live in disjoint TMEM columns (2 x 128 + 2 x 64 + 2 x 64 = 512), so the only hazards are explicit: S may be overwritten
+// once both column halves have read it, P once the previous P.V product has completed (pv_done).
 #include "mt_ops.cuh"
 #include "mt_tcgen05.cuh"
 
@@ -36,8 +37,8 @@ struct FlashFwdArgs {
   DropCfg drop;
 };
 
-constexpr int FF_NT = 320;                  // warps 0-3 / 4-7: query tile 0 / 1, warp 8: TMA, warp 9: MMA issue + TMEM
-constexpr int FF_SMEM = 2 * TILE_B + NST * 2 * TILE_B + 512 + 1024;
+constexpr int FF_NT = 576;                  // warps 0-15 softmax (query tile w = warp / 8, key-column half hf = (warp / 4) % 2), 16: TMA, 17: MMA + TMEM
+constexpr int FF_SMEM = 2 * TILE_B + NST * 2 * TILE_B + 512 + 2 * 2 * 2 * TQ * 4 + 1024;
 
 __global__ void __launch_bounds__(FF_NT, 1) attn_flash_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ FlashFwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -50,31 +51,35 @@ __global__ void __launch_bounds__(FF_NT, 1) attn_flash_fwd_kernel(const __grid_c
   uint64_t* q_full = empty + NST;           // [1]
   uint64_t* q_free = q_full + 1;            // [1]   all S MMAs of the item are complete
   uint64_t* s_full = q_free + 1;            // [2]   S of query tile w is in TMEM
-  uint64_t* s_free = s_full + 2;            // [2]   pass 1: S has been read (128 arrivals)
-  uint64_t* p_ready = s_free + 2;           // [2]   pass 2: P is in place (128 arrivals)
-  uint64_t* o_full = p_ready + 2;           // [2]   all P.V products of the item are complete
-  uint64_t* o_read = o_full + 2;            // [2]   O has been read out (128 arrivals)
+  uint64_t* s_free = s_full + 2;            // [2]   pass 1: S has been read (256 arrivals)
+  uint64_t* p_ready = s_free + 2;           // [2]   pass 2: S has been read and P is in place (256 arrivals)
+  uint64_t* pv_done = p_ready + 2;          // [2]   the P.V product of the key tile is complete: P may be overwritten
+  uint64_t* o_full = pv_done + 2;           // [2]   all P.V products of the item are complete
+  uint64_t* o_read = o_full + 2;            // [2]   O has been read out (256 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_read + 2);
+  float* xmax = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);      // [tile][half][row] partial row maxima
+  float* xsum = xmax + 2 * 2 * TQ;                                                       // ... and partial row sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 8 && lane == 0) {
+  if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&map_qkv);
     for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(q_full, 1); mbar_init(q_free, 1);
     for (int w = 0; w < 2; ++w) {
-      mbar_init(&s_full[w], 1); mbar_init(&s_free[w], 128); mbar_init(&p_ready[w], 128); mbar_init(&o_full[w], 1); mbar_init(&o_read[w], 128);
+      mbar_init(&s_full[w], 1); mbar_init(&s_free[w], 256); mbar_init(&p_ready[w], 256); mbar_init(&pv_done[w], 1); mbar_init(&o_full[w], 1);
+      mbar_init(&o_read[w], 256);
     }
     mbar_init_fence();
   }
-  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  if (warp == 17) tmem_alloc<512>(tmem_slot);
   fence_before();
   __syncthreads();
   fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int n_kt = a.n_kt;
-  // TMEM: S of query tile w at w * 128 (P packed over its first 64 columns), O at 256 + w * 64
+  // TMEM columns: S of query tile w at w * 128 | O at 256 + w * 64 | P (bf16, packed two per column) at 384 + w * 64
 
-  if (warp == 8) {
+  if (warp == 16) {
     // ===== TMA producer =====
     if (lane == 0) {
       uint32_t fill = 0;                     // ring uses so far
@@ -98,7 +103,7 @@ __global__ void __launch_bounds__(FF_NT, 1) attn_flash_fwd_kernel(const __grid_c
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 17) {
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc(TQ, TQ, 0, 0);
@@ -116,7 +121,8 @@ __global__ void __launch_bounds__(FF_NT, 1) attn_flash_fwd_kernel(const __grid_c
       for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++it) {
         mbar_wait(q_full, (uint32_t)it & 1u);
         fence_after();
-        // ---- pass 1: S only; S_w of the next key tile waits until the softmax warps have read the previous one ----
+        // ---- pass 1: S only; S_w of the next key tile waits until the softmax warps have read the previous one.  (The first S of an
+        //      item needs no wait: the softmax warps delivered the last P of the previous item only after reading its S.) ----
         for (int kt = 0; kt < n_kt; ++kt, ++use) {
           const int stage = (int)(use % NST);
           mbar_wait(&full[stage], (use / NST) & 1u);
@@ -124,19 +130,15 @@ __global__ void __launch_bounds__(FF_NT, 1) attn_flash_fwd_kernel(const __grid_c
           const uint32_t sk = kv_u32 + (uint32_t)(stage * 2 * TILE_B);
 #pragma unroll
           for (int w = 0; w < 2; ++w) {
-            if (kt > 0 || it > 0) {
-              // first S of an item: the previous item's last P.V read P from this region -- in program order before this MMA; its O read
-              // is not needed here.  Within pass 1 wait for the read of the previous S.
-              if (kt > 0) { mbar_wait(&s_free[w], n_sfree[w] & 1u); ++n_sfree[w]; fence_after(); }
-            }
+            if (kt > 0) { mbar_wait(&s_free[w], n_sfree[w] & 1u); ++n_sfree[w]; fence_after(); }
             issue_s(w, sk);
           }
           commit(&empty[stage]);
         }
-        // ---- pass 2: S, then P.V once the softmax warps delivered P; S of kt + 1 is issued right behind P.V of kt ----
-        // the last pass-1 S must have been read before it is overwritten
+        // ---- pass 2: S, then P.V once the softmax warps delivered P (which also says that S has been read); S of kt + 1 is issued
+        //      right behind P.V of kt ----
 #pragma unroll
-        for (int w = 0; w < 2; ++w) { mbar_wait(&s_free[w], n_sfree[w] & 1u); ++n_sfree[w]; }
+        for (int w = 0; w < 2; ++w) { mbar_wait(&s_free[w], n_sfree[w] & 1u); ++n_sfree[w]; }      // the last pass-1 S has been read
         fence_after();
         {
           const int stage = (int)(use % NST);
@@ -165,8 +167,9 @@ __global__ void __launch_bounds__(FF_NT, 1) attn_flash_fwd_kernel(const __grid_c
             const uint64_t dv = make_desc(sv, 8192, 1024);
 #pragma unroll
             for (int ks = 0; ks < TQ / 16; ++ks)      // A = P in TMEM (8 columns per 16 keys), B = V as an MN-major operand (n = head column)
-              mma_ts(tmem_base + (uint32_t)(256 + w * HDF), tmem_base + (uint32_t)(w * 128 + 8 * ks), dv + (uint64_t)(128 * ks), idesc_o,
+              mma_ts(tmem_base + (uint32_t)(256 + w * HDF), tmem_base + (uint32_t)(384 + w * 64 + 8 * ks), dv + (uint64_t)(128 * ks), idesc_o,
                      (kt > 0 || ks > 0) ? 1u : 0u);
+            commit(&pv_done[w]);
             if (more) issue_s(w, sk_next);
             else commit(&o_full[w]);
           }
@@ -176,15 +179,21 @@ __global__ void __launch_bounds__(FF_NT, 1) attn_flash_fwd_kernel(const __grid_c
       }
     }
   } else {
-    // ===== softmax / epilogue: warp group w owns query tile w of the pair, thread = query row =====
+    // ===== softmax / epilogue: 16 warps.  Query tile w = warp / 8; the two warp groups of a tile split its key COLUMNS (half hf takes
+    //       keys 64 hf .. 64 hf + 63 of every key tile, and head columns 32 hf .. of O); thread = query row.  Row maxima (after pass
+    //       1) and row sums (at the end) of the two halves meet in shared memory. =====
     const DropCfg drop = mt_drop_resolve(a.drop);
-    const int w = warp >> 2, r = threadIdx.x & 127;
-    const uint32_t t_s = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(w * 128);
-    const uint32_t t_o = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(256 + w * HDF);
+    const int w = warp >> 3, hf = (warp >> 2) & 1, r = threadIdx.x & 127;
+    const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t t_s = t_lane + (uint32_t)(w * 128), t_o = t_lane + (uint32_t)(256 + w * HDF), t_p = t_lane + (uint32_t)(384 + w * 64);
     const uint32_t P2 = (uint32_t)(a.T + 1) >> 1;
     const uint32_t thr_hi = (drop.thresh >> 16) << 16;
     const bool dropping = drop.thresh != 0u;
-    uint32_t n_sfull = 0;
+    float* my_max = xmax + (w * 2 + hf) * TQ + r;
+    float* my_sum = xsum + (w * 2 + hf) * TQ + r;
+    const float* ot_max = xmax + (w * 2 + (hf ^ 1)) * TQ + r;
+    const float* ot_sum = xsum + (w * 2 + (hf ^ 1)) * TQ + r;
+    uint32_t n_sfull = 0, n_pv = 0;
     int it = 0;
     for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++it) {
       const int qp = item % a.n_qp, bh = item / a.n_qp, hd = bh % a.h, b = bh / a.h;
@@ -192,28 +201,36 @@ __global__ void __launch_bounds__(FF_NT, 1) attn_flash_fwd_kernel(const __grid_c
       const bool row_ok = q < a.T;
       const bool masked = a.mask != nullptr && row_ok && a.mask[(size_t)b * a.T + q] == 0.f;
       const float rs = masked ? 0.f : a.scale_log2;     // masked query rows: every score becomes the same constant
-      // ---- pass 1: row maximum of the raw scores ----
+      // ---- pass 1: row maximum of the raw scores over this half's key columns ----
       float mraw = -INFINITY;
       for (int kt = 0; kt < n_kt; ++kt) {
         mbar_wait(&s_full[w], n_sfull & 1u); ++n_sfull;
         fence_after();
         const int kleft = a.T - kt * TQ;                // keys of this tile that exist
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 2 * hf; c < 2 * hf + 2; ++c) {
           uint32_t v[32];
           ld32(t_s + (uint32_t)(c * 32), v);
           ld_wait();
+          if (kleft >= TQ) {                            // interior key tile (all but possibly the last): no per-key test
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mraw = fmaxf(mraw, (c * 32 + i < kleft) ? __uint_as_float(v[i]) : -INFINITY);
+            for (int i = 0; i < 32; i += 2) mraw = fmaxf(mraw, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mraw = fmaxf(mraw, (c * 32 + i < kleft) ? __uint_as_float(v[i]) : -INFINITY);
+          }
         }
         fence_before();
         mbar_arrive(&s_free[w]);
       }
+      *my_max = mraw;
+      bar_sync(1 + w, 256);
+      mraw = fmaxf(mraw, *ot_max);
       const float mx = masked ? 0.f : mraw * rs;         // rs > 0 for live rows: max(s * rs) = rs * max(s)
       const uint64_t rs2 = pk2(rs, rs), nmx2 = pk2(-mx, -mx);
       uint64_t l2 = pk2(0.f, 0.f);
       const uint64_t drow = ((uint64_t)bh * (uint64_t)a.T + (uint64_t)min(q, a.T - 1)) * (uint64_t)P2;      // pair-index base of this row
-      // ---- pass 2: probabilities with the final maximum, P -> TMEM, O accumulates in TMEM ----
+      // ---- pass 2: probabilities with the final maximum, P -> its own TMEM columns, O accumulates in TMEM ----
       for (int kt = 0; kt < n_kt; ++kt) {
         mbar_wait(&s_full[w], n_sfull & 1u); ++n_sfull;
         fence_after();
@@ -222,8 +239,9 @@ __global__ void __launch_bounds__(FF_NT, 1) attn_flash_fwd_kernel(const __grid_c
         const uint32_t plo = (uint32_t)pb64;
         const uint32_t phi = (uint32_t)(pb64 >> 32) * 0xC2B2AE35u;      // constant inside the tile unless the low word wraps (handled below)
         const bool wraps = plo > 0xFFFFFFFFu - 64u;
+        const bool full_tile = kleft >= TQ;             // warp-uniform: the compiler hoists it out of the unrolled pair loop
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 2 * hf; c < 2 * hf + 2; ++c) {
           uint32_t v[32], pk[16];
           ld32(t_s + (uint32_t)(c * 32), v);
           ld_wait();
@@ -232,8 +250,8 @@ __global__ void __launch_bounds__(FF_NT, 1) attn_flash_fwd_kernel(const __grid_c
             const int j = c * 32 + i;
             float p0, p1;
             upk2(fma2(pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), rs2, nmx2), p0, p1);
-            p0 = j < kleft ? ex2(p0) : 0.f;
-            p1 = j + 1 < kleft ? ex2(p1) : 0.f;
+            if (full_tile) { p0 = ex2(p0); p1 = ex2(p1); }
+            else { p0 = j < kleft ? ex2(p0) : 0.f; p1 = j + 1 < kleft ? ex2(p1) : 0.f; }
             l2 = add2(l2, pk2(p0, p1));
             if (dropping) {        // one draw per pair of keys: low half -> key j, high half -> key j + 1; the keep scale is applied with 1 / l
               const uint32_t off = (uint32_t)(c * 16 + (i >> 1));
@@ -245,30 +263,37 @@ __global__ void __launch_bounds__(FF_NT, 1) attn_flash_fwd_kernel(const __grid_c
             }
             pk[i >> 1] = pack_bf2(p0, p1);
           }
-          st16(t_s + (uint32_t)(c * 16), pk);
+          if (c == 2 * hf && (kt > 0 || it > 0)) {      // the previous P.V product has read P (completion number n_pv - 1 of pv_done)
+            mbar_wait(&pv_done[w], (n_pv - 1) & 1u);
+            fence_after();
+          }
+          st16(t_p + (uint32_t)(c * 16), pk);
         }
+        ++n_pv;
         st_wait();
         fence_before();
         mbar_arrive(&p_ready[w]);
       }
       float l0, l1;
       upk2(l2, l0, l1);
-      const float l = l0 + l1;
+      float l = l0 + l1;
+      *my_sum = l;
+      bar_sync(1 + w, 256);
+      l += *ot_sum;
       const float inv = drop.scale / l;
-      if (a.lse != nullptr && row_ok) a.lse[(size_t)bh * a.T + q] = (mx + log2f(l)) * LN2_F;      // natural-log LSE of the scaled scores
+      if (hf == 0 && a.lse != nullptr && row_ok) a.lse[(size_t)bh * a.T + q] = (mx + log2f(l)) * LN2_F;      // natural-log LSE of the scaled scores
       mbar_wait(&o_full[w], (uint32_t)it & 1u);
       fence_after();
-      uint32_t o[64];
-      ld32(t_o, o);
-      ld32(t_o + 32, o + 32);
+      uint32_t o[32];
+      ld32(t_o + (uint32_t)(hf * 32), o);
       ld_wait();
       fence_before();
       mbar_arrive(&o_read[w]);
       if (row_ok) {
-        bf16* op = a.out + ((size_t)b * a.T + q) * a.d + hd * HDF;
+        bf16* op = a.out + ((size_t)b * a.T + q) * a.d + hd * HDF + hf * 32;
         const uint64_t inv2 = pk2(inv, inv);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
+        for (int g = 0; g < 4; ++g) {
           float f[8];
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -282,7 +307,7 @@ __global__ void __launch_bounds__(FF_NT, 1) attn_flash_fwd_kernel(const __grid_c
   }
   fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == 17) {
     fence_after();
     tmem_dealloc<512>(tmem_base);
   }
@@ -467,6 +492,7 @@ attn_flash_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
         const uint64_t p64 = ((uint64_t)bh * (uint64_t)T + (uint64_t)(i * TQ + g * 32) + odd) * (uint64_t)P2 + (uint64_t)(jg >> 1);
         const uint32_t plo = (uint32_t)p64, phi = (uint32_t)(p64 >> 32) * 0xC2B2AE35u;
         const bool wraps = plo > 0xFFFFFFFFu - 32u * P2;
+        const bool interior = (jt + 1) * TQ <= T && (i + 1) * TQ <= T;      // every key and query of the block exists (CTA-uniform)
         mbar_wait(&full[stage], (fillc / NSB) & 1u);         // per-query vectors (the MMA warp waits on the same phase for the tiles)
         mbar_wait(s_full, blk & 1u);
         fence_after();
@@ -487,8 +513,13 @@ attn_flash_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_
             float p[4], t[4];
             upk2(fma2(pk2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), pk2(rs.x, rs.y), pk2(-L.x, -L.y)), p[0], p[1]);
             upk2(fma2(pk2(__uint_as_float(s[e + 2]), __uint_as_float(s[e + 3])), pk2(rs.z, rs.w), pk2(-L.z, -L.w)), p[2], p[3]);
+            if (interior) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) p[k] = (key_ok && i * TQ + q + k < T) ? ex2(p[k]) : 0.f;
+              for (int k = 0; k < 4; ++k) p[k] = ex2(p[k]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) p[k] = (key_ok && i * TQ + q + k < T) ? ex2(p[k]) : 0.f;
+            }
             // t = dP . keep-scale - D ; without a kept draw the probability's gradient is -D
             upk2(fma2(pk2(__uint_as_float(dp[e]), __uint_as_float(dp[e + 1])), ds2, pk2(-D.x, -D.y)), t[0], t[1]);
             upk2(fma2(pk2(__uint_as_float(dp[e + 2]), __uint_as_float(dp[e + 3])), ds2, pk2(-D.z, -D.w)), t[2], t[3]);
