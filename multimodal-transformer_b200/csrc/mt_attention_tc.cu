@@ -616,6 +616,280 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------------
+// backward, second formulation (default): the block pipeline of the long-sequence kernel (mt_attention_flash.cu) for T <= 128.
+// An item is still a (narrative, head pair) whose four TMA boxes share a ring stage, but its two heads are two BLOCKS of one pipeline:
+// all 16 compute warps work on the same head (warp group g: queries 32 g .. 32 g + 31, thread = key row), P^T goes to its own TMEM
+// columns and dS^T to a double-buffered shared-memory tile (K-major A operand of dK, MN-major A operand of dQ), so S^T / dP^T of the
+// next block are issued in front of the gradient MMAs of this one and the compute warps never wait for them; dQ / dK / dV of a block
+// are drained (8 columns per thread) while the next block's gradient MMAs run.
+// TMEM columns: S^T [0,128) | dP^T [128,256) | P^T packed bf16 [256,320) | dV [320,352) | dK [352,384) | dQ [384,416)
+template <bool FULL>
+__global__ void __launch_bounds__(BWD_NT, 1)
+attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do, const __grid_constant__ BwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ float s_cs[4 * 2 * 96];                  // [head pair][w][dQ | dK | dV][32]: bias-gradient column sums of this CTA
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* stage_base = smem;
+  uint8_t* ds_smem = smem + BWD_STAGES * BWD_STAGE_BYTES;      // two dS^T buffers (block parity)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ds_smem + 2 * BWD_DS_BYTES);
+  uint64_t* full = bars;                    // [2] TMA -> MMA / compute
+  uint64_t* empty = bars + BWD_STAGES;      // [2] MMA -> TMA
+  uint64_t* s_full = empty + BWD_STAGES;    // [1] S^T and dP^T of the block are in TMEM
+  uint64_t* s_free = s_full + 1;            // [1] ... and have been read (512 arrivals)
+  uint64_t* p_ready = s_free + 1;           // [1] P^T (TMEM) and dS^T (shared) of the block are in place (512 arrivals)
+  uint64_t* pt_free = p_ready + 1;          // [1] the dV MMAs of the block are complete: P^T may be overwritten
+  uint64_t* ds_free = pt_free + 1;          // [2] the dK / dQ MMAs that read this dS^T buffer are complete
+  uint64_t* g_full = ds_free + 2;           // [1] dV, dK, dQ of the block are in TMEM
+  uint64_t* g_read = g_full + 1;            // [1] ... and have been read out (512 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_read + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hp_count = a.h >> 1;
+  const int T = a.T;
+  for (int i = threadIdx.x; i < 4 * 2 * 96; i += BWD_NT) s_cs[i] = 0.f;
+  if (warp == 16 && lane == 0) {
+    tma_prefetch_desc(&map_qkv);
+    tma_prefetch_desc(&map_do);
+    for (int s = 0; s < BWD_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(s_full, 1); mbar_init(s_free, 512); mbar_init(p_ready, 512); mbar_init(pt_free, 1);
+    mbar_init(&ds_free[0], 1); mbar_init(&ds_free[1], 1); mbar_init(g_full, 1); mbar_init(g_read, 512);
+    mbar_init_fence();
+  }
+  if (warp == 17) tmem_alloc<512>(tmem_slot);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const ItemWalk iw = item_walk(a.G, a.B, hp_count);
+  const int n_my = iw.n;
+
+  if (warp == 16) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int it = 0; it < n_my; ++it) {
+        const int item = iw.base + it * iw.step;
+        const int b = item / hp_count, hp = item % hp_count;
+        const int stage = it & 1;
+        mbar_wait(&empty[stage], (((uint32_t)it >> 1) & 1u) ^ 1u);
+        uint8_t* sb = stage_base + stage * BWD_STAGE_BYTES;
+        mbar_expect_tx(&full[stage], (uint32_t)BWD_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) tma_load_2d(sb + k * TILE_BYTES, &map_qkv, k * a.d + hp * 64, b * T, &full[stage]);
+        tma_load_2d(sb + 3 * TILE_BYTES, &map_do, hp * 64, b * T, &full[stage]);
+        bulk_load(sb + 4 * TILE_BYTES, a.aux + ((size_t)b * a.h + 2 * hp) * 4 * TM, (uint32_t)BWD_AUX_BYTES, &full[stage]);
+      }
+    }
+  } else if (warp == 17) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc(TM, TM, 0, 0);
+      const uint32_t idesc_ts = make_idesc(TM, HD, 0, 1);      // dV: A in TMEM; dK: A K-major in shared memory; B MN-major
+      const uint32_t idesc_dq = make_idesc(TM, HD, 1, 1);      // dQ: A = dS from shared memory, MN-major
+      const uint32_t st_u32 = smem_u32(stage_base), ds_u32 = smem_u32(ds_smem);
+      const int n_blk = 2 * n_my;
+      auto round2 = [&](int pb) {           // gradient MMAs of block pb
+        const int stage = (pb >> 1) & 1, w = pb & 1;
+        const uint32_t sq = st_u32 + (uint32_t)(stage * BWD_STAGE_BYTES), sk = sq + TILE_BYTES, sg = sk + 2 * TILE_BYTES;
+        const uint32_t sds = ds_u32 + (uint32_t)((pb & 1) * BWD_DS_BYTES);
+        mbar_wait(p_ready, (uint32_t)pb & 1u);
+        if (pb > 0) mbar_wait(g_read, (uint32_t)(pb - 1) & 1u);      // dV / dK / dQ of the previous block have been read out
+        fence_after();
+        const uint64_t dgm = make_desc(sg + 64 * w, 8192, 1024), dqm = make_desc(sq + 64 * w, 8192, 1024), dkm = make_desc(sk + 64 * w, 8192, 1024);
+#pragma unroll
+        for (int ks = 0; ks < TM / 16; ++ks)      // dV = P^T dO: A = P^T in TMEM (8 columns per 16 queries)
+          mma_ts(tmem_base + 320, tmem_base + (uint32_t)(256 + 8 * ks), dgm + (uint64_t)(128 * ks), idesc_ts, ks > 0);
+        commit(pt_free);
+#pragma unroll
+        for (int ks = 0; ks < TM / 16; ++ks)      // dK = dS^T Q: A K-major over the queries, two 64-query tiles
+          mma_ss(tmem_base + 352, make_desc(sds + (uint32_t)((ks >> 2) * TILE_BYTES + (ks & 3) * 32), 16, 1024), dqm + (uint64_t)(128 * ks), idesc_ts, ks > 0);
+        {
+          const uint64_t dsm = make_desc(sds, TILE_BYTES, 1024);
+#pragma unroll
+          for (int ks = 0; ks < TM / 16; ++ks) mma_ss(tmem_base + 384, dsm + (uint64_t)(128 * ks), dkm + (uint64_t)(128 * ks), idesc_dq, ks > 0);
+        }
+        commit(g_full);
+        commit(&ds_free[pb & 1]);
+        if (w == 1) commit(&empty[stage]);      // both heads of the item are done with the stage
+      };
+      for (int blk = 0; blk < n_blk; ++blk) {
+        const int it = blk >> 1, w = blk & 1, stage = it & 1;
+        if (w == 0) { mbar_wait(&full[stage], ((uint32_t)it >> 1) & 1u); }
+        if (blk > 0) mbar_wait(s_free, (uint32_t)(blk - 1) & 1u);
+        fence_after();
+        const uint32_t sq = st_u32 + (uint32_t)(stage * BWD_STAGE_BYTES), sk = sq + TILE_BYTES, sv = sk + TILE_BYTES, sg = sv + TILE_BYTES;
+        const uint64_t dk0 = make_desc(sk + 64 * w, 16, 1024), dq0 = make_desc(sq + 64 * w, 16, 1024);
+        const uint64_t dv0 = make_desc(sv + 64 * w, 16, 1024), dg0 = make_desc(sg + 64 * w, 16, 1024);
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks) mma_ss(tmem_base, dk0 + (uint64_t)(2 * ks), dq0 + (uint64_t)(2 * ks), idesc_s, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks) mma_ss(tmem_base + 128, dv0 + (uint64_t)(2 * ks), dg0 + (uint64_t)(2 * ks), idesc_s, ks > 0);
+        commit(s_full);
+        if (blk > 0) round2(blk - 1);
+      }
+      if (n_blk > 0) round2(n_blk - 1);
+    }
+  } else {
+    // ===== compute: warp group g owns the queries [32 g, 32 g + 32) of every block, thread = key row j =====
+    const DropCfg drop = mt_drop_resolve(a.drop[iw.grp]);
+    const int g = warp >> 2, j = threadIdx.x & 127;
+    const uint32_t tl = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t P2 = (uint32_t)(T + 1) >> 1;
+    const uint32_t thr_hi = (drop.thresh >> 16) << 16;
+    const bool dropping = drop.thresh != 0u;
+    const bool key_ok = FULL || j < T;
+    const uint32_t odd = (uint32_t)j & 1u;
+    const uint64_t ds2 = pk2(drop.scale, drop.scale);
+    const int n_blk = 2 * n_my;
+    // read out dQ / dK / dV of block pb (8 columns of each per thread), store them, add their column sums to the bias gradient
+    auto drain = [&](int pb) {
+      const int it = pb >> 1, w = pb & 1;
+      const int item = iw.base + it * iw.step;
+      const int b = item / hp_count, hp = item % hp_count, hd = 2 * hp + w;
+      mbar_wait(g_full, (uint32_t)pb & 1u);
+      fence_after();
+      uint32_t rq[8], rk[8], rv[8];
+      ld8(tl + (uint32_t)(384 + g * 8), rq);
+      ld8(tl + (uint32_t)(352 + g * 8), rk);
+      ld8(tl + (uint32_t)(320 + g * 8), rv);
+      ld_wait();
+      fence_before();
+      mbar_arrive(g_read);
+      float v[24];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { v[i] = __uint_as_float(rq[i]); v[8 + i] = __uint_as_float(rk[i]); }
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) upk2(mul2(pk2(__uint_as_float(rv[i]), __uint_as_float(rv[i + 1])), ds2), v[16 + i], v[17 + i]);      // dV still lacks the keep scale
+      if (key_ok) {           // row j is query j of dQ and key j of dK / dV; rows beyond T are exact zeros
+        bf16* gp = a.dqkv + ((size_t)b * T + j) * (3 * a.d) + hd * HD + g * 8;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          uint4 u;
+          u.x = pack_bf2(v[8 * k], v[8 * k + 1]); u.y = pack_bf2(v[8 * k + 2], v[8 * k + 3]);
+          u.z = pack_bf2(v[8 * k + 4], v[8 * k + 5]); u.w = pack_bf2(v[8 * k + 6], v[8 * k + 7]);
+          __stcs(reinterpret_cast<uint4*>(gp + (size_t)k * a.d), u);
+        }
+      }
+      if (a.dbias != nullptr) {
+        // column sums over the warp's 32 rows: a butterfly that halves the number of live columns per lane at every step
+        int ln;
+        asm volatile("mov.u32 %0, %%laneid;" : "=r"(ln));
+        int col = 0;
+#pragma unroll
+        for (int step = 0; step < 3; ++step) {
+          const int n2 = 12 >> step;                // 12, 6, 3
+          const int m = 16 >> step;
+          const bool up = (ln & m) != 0;
+#pragma unroll
+          for (int i = 0; i < n2; ++i) {
+            const float send = up ? v[i] : v[i + n2], keep = up ? v[i + n2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+          }
+          col += up ? n2 : 0;
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          v[i] += __shfl_xor_sync(0xffffffffu, v[i], 2);
+          v[i] += __shfl_xor_sync(0xffffffffu, v[i], 1);
+        }
+        if ((ln & 3) == 0) {
+          float* cs = s_cs + ((hp & 3) * 2 + w) * 96;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int cidx = col + i;      // 0..23: [dQ | dK | dV] x 8 columns of this warp group
+            atomicAdd(cs + (cidx >> 3) * 32 + g * 8 + (cidx & 7), v[i]);
+          }
+        }
+      }
+    };
+    for (int blk = 0; blk < n_blk; ++blk) {
+      const int it = blk >> 1, w = blk & 1, stage = it & 1;
+      const int item = iw.base + it * iw.step;
+      const int b = item / hp_count, hp = item % hp_count, hd = 2 * hp + w;
+      const float* ax = reinterpret_cast<const float*>(stage_base + stage * BWD_STAGE_BYTES + 4 * TILE_BYTES) + w * 4 * TM;
+      uint8_t* dsb = ds_smem + (blk & 1) * BWD_DS_BYTES + (g >> 1) * TILE_BYTES;      // this group's 64-query tile of the dS^T operand
+      // pair index of (query q, key pair j >> 1) = (bh T + q) P2 + (j >> 1), group-local bh; this lane draws for the queries q + (j & 1)
+      const uint32_t bh = (uint32_t)((b - iw.grp * a.B) * a.h + hd);
+      const uint32_t pidx0 = (bh * (uint32_t)T + (uint32_t)(g * 32) + odd) * P2 + (uint32_t)(j >> 1);
+      if (w == 0) mbar_wait(&full[stage], ((uint32_t)it >> 1) & 1u);       // per-query vectors (the MMA warp waits on the same phase for the tiles)
+      mbar_wait(s_full, (uint32_t)blk & 1u);
+      fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int q0 = g * 32 + cc * 16;
+        uint32_t s[16], dp[16], pkp[8], pks[8];
+        ld16(tl + (uint32_t)q0, s);
+        ld16(tl + (uint32_t)(128 + q0), dp);
+        ld_wait();
+        if (cc == 1) { fence_before(); mbar_arrive(s_free); }      // this thread's last read of S^T / dP^T
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) {
+          const int q = q0 + e;
+          const float4 L = *reinterpret_cast<const float4*>(ax + q), D = *reinterpret_cast<const float4*>(ax + TM + q);
+          const float4 rs = *reinterpret_cast<const float4*>(ax + 2 * TM + q), gs = *reinterpret_cast<const float4*>(ax + 3 * TM + q);
+          const float Dk[4] = {D.x, D.y, D.z, D.w};
+          float p[4], t[4];
+          upk2(fma2(pk2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), pk2(rs.x, rs.y), pk2(-L.x, -L.y)), p[0], p[1]);
+          upk2(fma2(pk2(__uint_as_float(s[e + 2]), __uint_as_float(s[e + 3])), pk2(rs.z, rs.w), pk2(-L.z, -L.w)), p[2], p[3]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) p[k] = (key_ok && (FULL || q + k < T)) ? ex2(p[k]) : 0.f;
+          // t = dP . keep-scale - D ; without a kept draw the probability's gradient is -D
+          upk2(fma2(pk2(__uint_as_float(dp[e]), __uint_as_float(dp[e + 1])), ds2, pk2(-D.x, -D.y)), t[0], t[1]);
+          upk2(fma2(pk2(__uint_as_float(dp[e + 2]), __uint_as_float(dp[e + 3])), ds2, pk2(-D.z, -D.w)), t[2], t[3]);
+          float pd[4] = {p[0], p[1], p[2], p[3]};
+          if (dropping) {
+#pragma unroll
+            for (int k = 0; k < 4; k += 2) {
+              const uint32_t mine = mt_mix32((pidx0 + (uint32_t)(cc * 16 + e + k) * P2) ^ drop.key);
+              const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+              const uint32_t b0 = odd ? other : mine, b1 = odd ? mine : other;
+              const bool k0 = odd ? (b0 >= thr_hi) : ((b0 << 16) >= thr_hi), k1 = odd ? (b1 >= thr_hi) : ((b1 << 16) >= thr_hi);
+              pd[k] = k0 ? p[k] : 0.f;
+              t[k] = k0 ? t[k] : -Dk[k];
+              pd[k + 1] = k1 ? p[k + 1] : 0.f;
+              t[k + 1] = k1 ? t[k + 1] : -Dk[k + 1];
+            }
+          }
+          float ev[4];
+          upk2(mul2(mul2(pk2(p[0], p[1]), pk2(gs.x, gs.y)), pk2(t[0], t[1])), ev[0], ev[1]);
+          upk2(mul2(mul2(pk2(p[2], p[3]), pk2(gs.z, gs.w)), pk2(t[2], t[3])), ev[2], ev[3]);
+          pkp[e >> 1] = pack_bf2(pd[0], pd[1]);
+          pkp[(e >> 1) + 1] = pack_bf2(pd[2], pd[3]);
+          pks[e >> 1] = pack_bf2(ev[0], ev[1]);
+          pks[(e >> 1) + 1] = pack_bf2(ev[2], ev[3]);
+        }
+        if (cc == 0) {      // first writes of the block: the previous block's dV MMAs have read P^T, the dK / dQ MMAs of block blk - 2 this dS^T buffer
+          if (blk > 0) mbar_wait(pt_free, (uint32_t)(blk - 1) & 1u);
+          if (blk > 1) mbar_wait(&ds_free[blk & 1], (uint32_t)((blk >> 1) - 1) & 1u);
+          fence_after();
+        }
+        st8(tl + (uint32_t)(256 + g * 16 + cc * 8), pkp);
+        *reinterpret_cast<uint4*>(dsb + sw128_off(j, (g & 1) * 4 + cc * 2)) = make_uint4(pks[0], pks[1], pks[2], pks[3]);
+        *reinterpret_cast<uint4*>(dsb + sw128_off(j, (g & 1) * 4 + cc * 2 + 1)) = make_uint4(pks[4], pks[5], pks[6], pks[7]);
+      }
+      st_wait();
+      fence_proxy_async();
+      fence_before();
+      mbar_arrive(p_ready);
+      if (blk > 0) drain(blk - 1);      // its gradient MMAs were issued behind this block's S^T
+    }
+    if (n_blk > 0) drain(n_blk - 1);
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 17) {
+    fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+  if (a.dbias != nullptr) {
+    for (int i = threadIdx.x; i < hp_count * 2 * 96; i += BWD_NT) {
+      const int hp = i / 192, w = (i / 96) & 1, k = (i % 96) / 32, c = i % 32;
+      const float val = s_cs[i];
+      if (val != 0.f) atomicAdd(a.dbias + iw.grp * a.dbias_gstride + (size_t)k * a.d + (2 * hp + w) * HD + c, val);
+    }
+  }
+}
+
 // one-time (per device) opt-in to the large dynamic shared-memory carve-out
 template <typename K>
 int set_smem_attr(K kernel, int bytes, MtPerDeviceOnce& once) {
@@ -698,12 +972,21 @@ int mt_attn_tc_bwd_run(int B, int T, int d, int h, const void* qkv, const float*
   const int cpg = n_items < sms / G ? n_items : sms / G;
   const int grid = cpg * G;
   mt_prof_work(10.0 * G * B * (double)T * T * d, (double)G * B * T * d * 8.0 * 2.0);
-  if (T == TM) {
-    MT_TRY(set_smem_attr(attn_tc_bwd_kernel<true>, BWD_SMEM, attr_full));
-    attn_tc_bwd_kernel<true><<<grid, BWD_NT, BWD_SMEM, st>>>(map_qkv, map_do, a);
+  static MtPerDeviceOnce attr2_full, attr2_part;
+  if (g_mt_tune[4] == 3) {                    // A/B hook: the first formulation (two heads side by side, P^T / dS^T over S^T / dP^T)
+    if (T == TM) {
+      MT_TRY(set_smem_attr(attn_tc_bwd_kernel<true>, BWD_SMEM, attr_full));
+      attn_tc_bwd_kernel<true><<<grid, BWD_NT, BWD_SMEM, st>>>(map_qkv, map_do, a);
+    } else {
+      MT_TRY(set_smem_attr(attn_tc_bwd_kernel<false>, BWD_SMEM, attr_part));
+      attn_tc_bwd_kernel<false><<<grid, BWD_NT, BWD_SMEM, st>>>(map_qkv, map_do, a);
+    }
+  } else if (T == TM) {
+    MT_TRY(set_smem_attr(attn_tc_bwd2_kernel<true>, BWD_SMEM, attr2_full));
+    attn_tc_bwd2_kernel<true><<<grid, BWD_NT, BWD_SMEM, st>>>(map_qkv, map_do, a);
   } else {
-    MT_TRY(set_smem_attr(attn_tc_bwd_kernel<false>, BWD_SMEM, attr_part));
-    attn_tc_bwd_kernel<false><<<grid, BWD_NT, BWD_SMEM, st>>>(map_qkv, map_do, a);
+    MT_TRY(set_smem_attr(attn_tc_bwd2_kernel<false>, BWD_SMEM, attr2_part));
+    attn_tc_bwd2_kernel<false><<<grid, BWD_NT, BWD_SMEM, st>>>(map_qkv, map_do, a);
   }
   MT_LAUNCH_CHECK();
   return MT_OK;
