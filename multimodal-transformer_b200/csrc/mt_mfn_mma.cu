@@ -1096,16 +1096,340 @@ __global__ void __launch_bounds__(NTH, 1) lstm_bwd_mma2_kernel(const __grid_cons
   else lstm_bwd2_compute<24>(a, m, stages, dzS, STAGE, GB, HB, DZS, ncw, full, empty);
 }
 
+// ======================================================================================================
+// Memory recurrence, second cut (same ideas as the LSTM kernels above): 3-D TMA boxes feed the ring (2 per step forward, 6 per step
+// backward instead of 16 / 40 bulk copies), storer warps move the step's outputs out of shared-memory staging with 16-byte stores,
+// mem_t lives in a 3-deep bf16 ring that is both the next step's B operand and the source of the mem_{t-1} / mem_t stash rows,
+// sigmoids on the tanh unit, the dropout factors of a step are drawn before the step's first barrier.
+// ======================================================================================================
+struct MemMaps { CUtensorMap m[6]; };
+constexpr int MBOX = (128 + 4) * 4 * NB;             // bytes of an fp32 box {132, 1, 8}
+constexpr int MBOXH = (128 + 8) * 2 * NB;            // bytes of a bf16 box {136, 1, 8}
+constexpr int MROW = (128 + 4) * 4, MROWH = (128 + 8) * 2;
+constexpr int GMS = 256 * 4 + 16;                    // staging row of gamma1 | gamma2 (fp32)
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(NTH2, 1) mem_fwd_mma2_kernel(const __grid_constant__ MemArgs a, const __grid_constant__ MemMaps maps) {
+  __shared__ __align__(16) bf16 memS[HRING][NB * LDK];
+  __shared__ __align__(16) bf16 ghS[2][NB * LDK];
+  __shared__ __align__(16) unsigned char gmS[2][NB * GMS];
+  extern __shared__ __align__(128) unsigned char feed_smem[];
+  __shared__ __align__(8) uint64_t full[FD], empty[FD];
+  const int MEM = 128, G = 64, G2 = 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, q = lane & 3;
+  const int b0 = blockIdx.x * NB;
+  const int LW = a.Hs + MEM;
+  char* stages = reinterpret_cast<char*>(feed_smem);
+  constexpr int STAGE = 2 * MBOX;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < FD; ++i) { mtrec::sbar_init(&full[i], 1); mtrec::sbar_init(&empty[i], NW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int e = threadIdx.x; e < HRING * NB * LDK; e += NTH2) memS[0][e] = __float2bfloat16(0.f);
+  for (int e = threadIdx.x; e < 2 * NB * LDK; e += NTH2) ghS[0][e] = __float2bfloat16(0.f);
+  __syncthreads();
+  if (warp == NW) {                                  // ---- producer ----
+    if (lane == 0) {
+      for (int t = 0; t < a.T; ++t) {
+        const int slot = t % FD;
+        if (t >= FD) mtrec::sbar_wait(&empty[slot], (uint32_t)(t / FD - 1) & 1u);
+        mtrec::sbar_expect_tx(&full[slot], (uint32_t)STAGE);
+        const uint32_t d = mtrec::s_u32(stages + (size_t)slot * STAGE);
+        tma_load_3d(d, &maps.m[0], 0, t, b0, &full[slot]);                // gate pre-activations (batched part)
+        tma_load_3d(d + MBOX, &maps.m[1], 0, t, b0, &full[slot]);         // cHat
+      }
+    }
+    return;
+  }
+  if (warp > NW) {                                   // ---- storers ----
+    const int tid = threadIdx.x - (NW + 1) * 32;
+    StoreJobs<6> jgm; StoreJobs<2> jgh, jmp, jml;
+    jgm.build(TRAIN ? a.gm : nullptr, 4ll * 2 * MEM, 0, 64, GMS, 0, 16, b0, a.B, a.sb, a.st, tid);
+    jgh.build(TRAIN ? a.gh_op : nullptr, 2ll * G2, 0, 16, LDK * 2, 0, 16, b0, a.B, a.sb, a.st, tid);
+    jmp.build(TRAIN ? a.memprev_op : nullptr, 2ll * MEM, 0, 16, LDK * 2, 0, 16, b0, a.B, a.sb, a.st, tid);
+    jml.build(a.last_op, 2ll * LW, 2ll * a.Hs, 16, LDK * 2, 0, 16, b0, a.B, a.sb, a.st, tid);
+    const uint32_t gm_s = mtrec::s_u32(&gmS[0][0]), gh_s = mtrec::s_u32(&ghS[0][0]), mem_s = mtrec::s_u32(&memS[0][0]);
+    int r0 = 0;
+    for (int t = 0; t < a.T; ++t) {
+      const int slot = t & 1, r1 = r0 == HRING - 1 ? 0 : r0 + 1;
+      nb_sync(2 + slot, NSYNC2);
+      uint4 vg[6], vh[2], vp[2], vl[2];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) if (jgm.dst[j] >= 0) vg[j] = lds16(gm_s + slot * NB * GMS + jgm.src[j]);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (jgh.dst[j] >= 0) vh[j] = lds16(gh_s + slot * NB * LDK * 2 + jgh.src[j]);
+        if (jmp.dst[j] >= 0) vp[j] = lds16(mem_s + r0 * NB * LDK * 2 + jmp.src[j]);
+        if (jml.dst[j] >= 0) vl[j] = lds16(mem_s + r1 * NB * LDK * 2 + jml.src[j]);
+      }
+      const unsigned long long tg = jgm.base + (unsigned long long)(t * jgm.inc), th = jgh.base + (unsigned long long)(t * jgh.inc);
+      const unsigned long long tp = jmp.base + (unsigned long long)(t * jmp.inc), tl = jml.base + (unsigned long long)(t * jml.inc);
+#pragma unroll
+      for (int j = 0; j < 6; ++j) if (jgm.dst[j] >= 0) stg16(tg + jgm.dst[j], vg[j]);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (jgh.dst[j] >= 0) stg16(th + jgh.dst[j], vh[j]);
+        if (jmp.dst[j] >= 0) stg16(tp + jmp.dst[j], vp[j]);
+        if (jml.dst[j] >= 0) stg16(tl + jml.dst[j], vl[j]);
+      }
+      if (t + 2 < a.T) nb_arrive(4 + slot, NSYNC2);
+      r0 = r1;
+    }
+    return;
+  }
+  // ---- compute warps: warp w owns features f0 = 16 w + gid, f1 = f0 + 8 of narratives n0 = 2 q, n1 = n0 + 1 in every layer ----
+  const int f0 = warp * 16 + gid, f1 = f0 + 8;
+  const int ldw1 = 2 * a.Hs + MEM;
+  uint32_t A1[8][4], A2a[4][4], A2b[4][4];
+  {
+    const bf16* w1 = reinterpret_cast<const bf16*>(warp < 4 ? a.g1_fc1_w : a.g2_fc1_w) + 2 * a.Hs;      // mem columns of gamma{1,2}_fc1
+    const int rb = (warp & 3) * 16;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) frag_a(A1[ks], rb, ks * 16, lane, [&](int r, int c) { return bf(w1 + (size_t)r * ldw1 + c); });
+    const bf16* v1 = reinterpret_cast<const bf16*>(a.g1_fc2_w);
+    const bf16* v2 = reinterpret_cast<const bf16*>(a.g2_fc2_w);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      frag_a(A2a[ks], warp * 16, ks * 16, lane, [&](int r, int c) { return bf(v1 + (size_t)r * G + c); });
+      frag_a(A2b[ks], warp * 16, ks * 16, lane, [&](int r, int c) { return bf(v2 + (size_t)r * G + c); });
+    }
+  }
+  const float bias1[2] = {a.g1_fc2_b[f0], a.g1_fc2_b[f1]}, bias2[2] = {a.g2_fc2_b[f0], a.g2_fc2_b[f1]};
+  const DropCfg drop = mt_drop_resolve(warp < 4 ? a.drop_g1 : a.drop_g2);
+  const int jg[2] = {f0 & 63, f1 & 63};              // index inside the gate's own [T,B,G] dropout tensor
+  int of[4], ob[4], og[4];                           // byte offsets: fp32 feed box, bf16 [n][LDK] tiles, gamma staging
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const int n = 2 * q + (v & 1), f = (v >> 1) ? f1 : f0;
+    of[v] = n * MROW + f * 4; ob[v] = (n * LDK + f) * 2; og[v] = n * GMS + f * 4;
+  }
+  const uint32_t lm_off = (uint32_t)(((lane & 7) * LDK + (lane >> 3) * 8) * 2);      // ldmatrix.x4 row of this lane inside a [n][LDK] tile
+  const uint32_t mem_s = mtrec::s_u32(&memS[0][0]) + lm_off, gh_s = mtrec::s_u32(&ghS[0][0]) + lm_off;
+  float mem[4] = {0.f, 0.f, 0.f, 0.f};
+  int r0 = 0;
+  mtrec::sbar_wait(&full[0], 0u);
+  for (int t = 0; t < a.T; ++t) {
+    const int slot = t & 1, r1 = r0 == HRING - 1 ? 0 : r0 + 1;
+    const char* sg = stages + (t % FD) * STAGE;
+    float acc[2][4], df[4], ch[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      acc[0][v] = lds_f32(sg + of[v]); acc[1][v] = 0.f;
+      ch[v] = lds_f32(sg + MBOX + of[v]);
+      // element index of the gate's [T,B,G] tensor (oracle/mt_oracle.py:_drop_t)
+      df[v] = mt_drop_factor(drop, ((uint64_t)t * a.B + (uint64_t)(b0 + 2 * q + (v & 1))) * (uint64_t)G + (uint64_t)jg[v >> 1]);
+    }
+    consumers_sync();                                // mem_{t-1} of every warp is in ring slot r0
+    // ---- layer 1: gh = drop(relu(gpre_t + Wm mem_{t-1})) ----
+#pragma unroll
+    for (int kp = 0; kp < 4; ++kp) {
+      uint32_t b[4];
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(mem_s + r0 * NB * LDK * 2 + kp * 64));
+      mma16816(acc[0], A1[2 * kp], b[0], b[1]);
+      mma16816(acc[1], A1[2 * kp + 1], b[2], b[3]);
+    }
+    release_slot(&empty[t % FD], lane);
+    if (t + 1 < a.T) mtrec::sbar_wait(&full[(t + 1) % FD], (uint32_t)((t + 1) / FD) & 1u);      // long complete: overlaps the mma
+    if (t >= 2) nb_sync(4 + slot, NSYNC2);           // the storers are done with this staging slot and with ring slot r1
+    char* gho = reinterpret_cast<char*>(ghS[slot]);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) *reinterpret_cast<bf16*>(gho + ob[v]) = __float2bfloat16(fmaxf(acc[0][v] + acc[1][v], 0.f) * df[v]);
+    consumers_sync();
+    // ---- layer 2: gamma1 from hidden[0:64), gamma2 from hidden[64:128) ----
+    float c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int kp = 0; kp < 2; ++kp) {
+      uint32_t x[4], y[4];
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]) : "r"(gh_s + slot * NB * LDK * 2 + kp * 64));
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(y[0]), "=r"(y[1]), "=r"(y[2]), "=r"(y[3]) : "r"(gh_s + slot * NB * LDK * 2 + 128 + kp * 64));
+      mma16816(c1, A2a[2 * kp], x[0], x[1]); mma16816(c2, A2b[2 * kp], y[0], y[1]);
+      mma16816(c1, A2a[2 * kp + 1], x[2], x[3]); mma16816(c2, A2b[2 * kp + 1], y[2], y[3]);
+    }
+    char* mo = reinterpret_cast<char*>(memS[r1]);
+    char* go = reinterpret_cast<char*>(gmS[slot]);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const float g1 = act_tanh(c1[v] + bias1[v >> 1], 0.5f, 0.5f, 0.5f), g2 = act_tanh(c2[v] + bias2[v >> 1], 0.5f, 0.5f, 0.5f);
+      mem[v] = g1 * mem[v] + g2 * ch[v];
+      *reinterpret_cast<bf16*>(mo + ob[v]) = __float2bfloat16(mem[v]);
+      if (TRAIN) { *reinterpret_cast<float*>(go + og[v]) = g1; *reinterpret_cast<float*>(go + og[v] + MEM * 4) = g2; }
+    }
+    nb_arrive(2 + slot, NSYNC2);                     // staged: the storers take step t from here
+    r0 = r1;
+  }
+  if (a.mem_last) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int n = 2 * q + (v & 1);
+      if (b0 + n < a.B) a.mem_last[(size_t)(b0 + n) * MEM + ((v >> 1) ? f1 : f0)] = mem[v];
+    }
+  }
+}
+
+// backward:  g = dmem + d(mem_t from the head);  dzg1 = g mem_{t-1} g1 (1 - g1);  dzg2 = g cHat g2 (1 - g2);  dzchat = g g2 (1 - cHat^2);
+//            dmem = g g1;  dgh = [gh > 0] sc * (W21^T dzg1 | W22^T dzg2);  dmem += Wm^T dgh
+__global__ void __launch_bounds__(NTH2, 1) mem_bwd_mma2_kernel(const __grid_constant__ MemArgs a, const __grid_constant__ MemMaps maps) {
+  __shared__ __align__(16) bf16 dzS[2][2][NB * LDK];       // [slot][gate]: dzg1 / dzg2, B operands and the dzg stash rows
+  __shared__ __align__(16) bf16 dghS[2][NB * LDK];
+  __shared__ __align__(16) bf16 dcS[2][NB * LDK];          // dzchat stash rows
+  extern __shared__ __align__(128) unsigned char feed_smem[];
+  __shared__ __align__(8) uint64_t full[FD], empty[FD];
+  const int MEM = 128, G = 64, G2 = 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, q = lane & 3;
+  const int b0 = blockIdx.x * NB;
+  char* stages = reinterpret_cast<char*>(feed_smem);
+  constexpr int STAGE = 4 * MBOX + 2 * MBOXH;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < FD; ++i) { mtrec::sbar_init(&full[i], 1); mtrec::sbar_init(&empty[i], NW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int e = threadIdx.x; e < 4 * NB * LDK; e += NTH2) dzS[0][0][e] = __float2bfloat16(0.f);
+  for (int e = threadIdx.x; e < 2 * NB * LDK; e += NTH2) { dghS[0][e] = __float2bfloat16(0.f); dcS[0][e] = __float2bfloat16(0.f); }
+  __syncthreads();
+  if (warp == NW) {                                  // ---- producer ----
+    if (lane == 0) {
+      for (int i = 0; i < a.T; ++i) {
+        const int slot = i % FD, t = a.T - 1 - i;
+        if (i >= FD) mtrec::sbar_wait(&empty[slot], (uint32_t)(i / FD - 1) & 1u);
+        mtrec::sbar_expect_tx(&full[slot], (uint32_t)STAGE);
+        const uint32_t d = mtrec::s_u32(stages + (size_t)slot * STAGE);
+        tma_load_3d(d, &maps.m[0], 0, t, b0, &full[slot]);                        // d mem_t from the head
+        tma_load_3d(d + MBOX, &maps.m[1], 0, t, b0, &full[slot]);                 // gamma1
+        tma_load_3d(d + 2 * MBOX, &maps.m[1], MEM, t, b0, &full[slot]);           // gamma2
+        tma_load_3d(d + 3 * MBOX, &maps.m[2], 0, t, b0, &full[slot]);             // cHat
+        tma_load_3d(d + 4 * MBOX, &maps.m[3], 0, t, b0, &full[slot]);             // mem_{t-1} (bf16)
+        tma_load_3d(d + 4 * MBOX + MBOXH, &maps.m[4], 0, t, b0, &full[slot]);     // gamma hidden (bf16)
+      }
+    }
+    return;
+  }
+  if (warp > NW) {                                   // ---- storers ----
+    const int tid = threadIdx.x - (NW + 1) * 32;
+    StoreJobs<2> j1, j2, jc, jh;
+    j1.build(a.dzg_op, 2ll * 2 * MEM, 0, 16, LDK * 2, 0, 16, b0, a.B, a.sb, a.st, tid);
+    j2.build(a.dzg_op, 2ll * 2 * MEM, 2ll * MEM, 16, LDK * 2, 0, 16, b0, a.B, a.sb, a.st, tid);
+    jc.build(a.dzchat_op, 2ll * MEM, 0, 16, LDK * 2, 0, 16, b0, a.B, a.sb, a.st, tid);
+    jh.build(a.dgh_op, 2ll * G2, 0, 16, LDK * 2, 0, 16, b0, a.B, a.sb, a.st, tid);
+    const uint32_t dz_s = mtrec::s_u32(&dzS[0][0][0]), dgh_s = mtrec::s_u32(&dghS[0][0]), dc_s = mtrec::s_u32(&dcS[0][0]);
+    for (int i = 0; i < a.T; ++i) {
+      const int slot = i & 1;
+      const long long t = a.T - 1 - i;
+      nb_sync(2 + slot, NSYNC2);
+      uint4 v1[2], v2[2], vc[2], vh[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (j1.dst[j] >= 0) v1[j] = lds16(dz_s + (slot * 2) * NB * LDK * 2 + j1.src[j]);
+        if (j2.dst[j] >= 0) v2[j] = lds16(dz_s + (slot * 2 + 1) * NB * LDK * 2 + j2.src[j]);
+        if (jc.dst[j] >= 0) vc[j] = lds16(dc_s + slot * NB * LDK * 2 + jc.src[j]);
+        if (jh.dst[j] >= 0) vh[j] = lds16(dgh_s + slot * NB * LDK * 2 + jh.src[j]);
+      }
+      const unsigned long long t1 = j1.base + (unsigned long long)(t * j1.inc), tc = jc.base + (unsigned long long)(t * jc.inc);
+      const unsigned long long th = jh.base + (unsigned long long)(t * jh.inc);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (j1.dst[j] >= 0) stg16(t1 + j1.dst[j], v1[j]);
+        if (j2.dst[j] >= 0) stg16(t1 + j2.dst[j], v2[j]);
+        if (jc.dst[j] >= 0) stg16(tc + jc.dst[j], vc[j]);
+        if (jh.dst[j] >= 0) stg16(th + jh.dst[j], vh[j]);
+      }
+      if (i + 2 < a.T) nb_arrive(4 + slot, NSYNC2);
+    }
+    return;
+  }
+  // ---- compute warps ----
+  const int f0 = warp * 16 + gid, f1 = f0 + 8;
+  const int ldw1 = 2 * a.Hs + MEM;
+  // A3: rows = hidden index n (warp's 16), k = mem feature: n < G: gamma1_fc2[k][n], else gamma2_fc2[k][n - G]
+  // A4: rows = mem feature (warp's 16), k = hidden index: k < G: gamma1_fc1[k][2Hs + row], else gamma2_fc1[k - G][2Hs + row]
+  uint32_t A3[8][4], A4[8][4];
+  {
+    const bf16* v = reinterpret_cast<const bf16*>(warp < 4 ? a.g1_fc2_w : a.g2_fc2_w);
+    const int nb = (warp & 3) * 16;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) frag_a(A3[ks], nb, ks * 16, lane, [&](int r, int c) { return bf(v + (size_t)c * G + r); });
+    const bf16* w1 = reinterpret_cast<const bf16*>(a.g1_fc1_w) + 2 * a.Hs;
+    const bf16* w2 = reinterpret_cast<const bf16*>(a.g2_fc1_w) + 2 * a.Hs;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+      frag_a(A4[ks], warp * 16, ks * 16, lane, [&](int r, int c) { return c < G ? bf(w1 + (size_t)c * ldw1 + r) : bf(w2 + (size_t)(c - G) * ldw1 + r); });
+  }
+  int of[4], oh[4], ob[4];
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const int n = 2 * q + (v & 1), f = (v >> 1) ? f1 : f0;
+    of[v] = n * MROW + f * 4; oh[v] = n * MROWH + f * 2; ob[v] = (n * LDK + f) * 2;
+  }
+  const uint32_t lm_off = (uint32_t)(((lane & 7) * LDK + (lane >> 3) * 8) * 2);
+  const uint32_t dz_s = mtrec::s_u32(&dzS[0][0][0]) + lm_off, dgh_s = mtrec::s_u32(&dghS[0][0]) + lm_off;
+  const float sc_g = a.drop_g1.scale;
+  float dmem[4] = {0.f, 0.f, 0.f, 0.f};
+  mtrec::sbar_wait(&full[0], 0u);
+  for (int i = 0; i < a.T; ++i) {
+    const int slot = i & 1;
+    const char* sg = stages + (i % FD) * STAGE;
+    float d1[4], d2[4], dcv[4], ghv[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const float dl = lds_f32(sg + of[v]), g1 = lds_f32(sg + MBOX + of[v]), g2 = lds_f32(sg + 2 * MBOX + of[v]), ch = lds_f32(sg + 3 * MBOX + of[v]);
+      const float mp = __bfloat162float(*reinterpret_cast<const bf16*>(sg + 4 * MBOX + oh[v]));
+      ghv[v] = __bfloat162float(*reinterpret_cast<const bf16*>(sg + 4 * MBOX + MBOXH + oh[v]));
+      const float g = dmem[v] + dl;
+      d1[v] = g * mp * g1 * (1.f - g1);
+      d2[v] = g * ch * g2 * (1.f - g2);
+      dcv[v] = g * g2 * (1.f - ch * ch);
+      dmem[v] = g * g1;
+    }
+    release_slot(&empty[i % FD], lane);
+    if (i + 1 < a.T) mtrec::sbar_wait(&full[(i + 1) % FD], (uint32_t)((i + 1) / FD) & 1u);
+    if (i >= 2) nb_sync(4 + slot, NSYNC2);           // the storers are done with this slot's dz / dgh / dzchat tiles
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      *reinterpret_cast<bf16*>(reinterpret_cast<char*>(dzS[slot][0]) + ob[v]) = __float2bfloat16(d1[v]);
+      *reinterpret_cast<bf16*>(reinterpret_cast<char*>(dzS[slot][1]) + ob[v]) = __float2bfloat16(d2[v]);
+      *reinterpret_cast<bf16*>(reinterpret_cast<char*>(dcS[slot]) + ob[v]) = __float2bfloat16(dcv[v]);
+    }
+    consumers_sync();
+    // ---- d hidden (hidden index = this thread's f0 / f1: warps 0-3 gate 1, warps 4-7 gate 2) ----
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    const uint32_t src = dz_s + (uint32_t)((slot * 2 + (warp < 4 ? 0 : 1)) * NB * LDK * 2);
+#pragma unroll
+    for (int kp = 0; kp < 4; ++kp) {
+      uint32_t b[4];
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(src + kp * 64));
+      mma16816(acc[0], A3[2 * kp], b[0], b[1]);
+      mma16816(acc[1], A3[2 * kp + 1], b[2], b[3]);
+    }
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+      *reinterpret_cast<bf16*>(reinterpret_cast<char*>(dghS[slot]) + ob[v]) = __float2bfloat16(ghv[v] > 0.f ? (acc[0][v] + acc[1][v]) * sc_g : 0.f);
+    consumers_sync();
+    nb_arrive(2 + slot, NSYNC2);                     // staged: dzg, dzchat and dgh of step t
+    // ---- d mem_{t-1} += gamma_fc1[:, 2H:]^T d hidden ----
+    float ac2[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    const uint32_t sr2 = dgh_s + (uint32_t)(slot * NB * LDK * 2);
+#pragma unroll
+    for (int kp = 0; kp < 4; ++kp) {
+      uint32_t b[4];
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(sr2 + kp * 64));
+      mma16816(ac2[0], A4[2 * kp], b[0], b[1]);
+      mma16816(ac2[1], A4[2 * kp + 1], b[2], b[3]);
+    }
+#pragma unroll
+    for (int v = 0; v < 4; ++v) dmem[v] += ac2[0][v] + ac2[1][v];
+  }
+}
+
 }  // namespace
 
 // fp32 [B, T, cols] view of a stash tensor (row (b, t) at (b * sb + t * st) * pitch) as a 3-D tensor map, box {box_cols, 1, NB}
-static int make_map_rows(CUtensorMap* map, const float* base, long long cols, long long pitch, int T, int B, long long sb, long long st, int box_cols) {
+static int make_map_rows(CUtensorMap* map, const void* base, long long cols, long long pitch, int T, int B, long long sb, long long st, int box_cols,
+                         int esize = 4) {
   tc5::EncodeTiledFn enc = tc5::get_encode();
   if (!enc) return MT_ERR_UNSUPPORTED;
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)T, (cuuint64_t)B};
-  cuuint64_t strides[2] = {(cuuint64_t)(st * pitch * 4), (cuuint64_t)(sb * pitch * 4)};
+  cuuint64_t strides[2] = {(cuuint64_t)(st * pitch * esize), (cuuint64_t)(sb * pitch * esize)};
   cuuint32_t box[3] = {(cuuint32_t)box_cols, 1u, (cuuint32_t)NB}, estr[3] = {1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = enc(map, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_mt_cuda_err, sizeof(g_mt_cuda_err), "cuTensorMapEncodeTiled (recurrence feed) failed with CUresult %d", (int)r);
@@ -1128,6 +1452,17 @@ bool mt_mfn_mma_mem_supported(const MemArgs& a) { return a.MEM == 128 && a.G == 
 
 int mt_mfn_mma_mem_fwd(const MemArgs& a, cudaStream_t st) {
   const int grid = (a.B + NB - 1) / NB;
+  if (a.Hs % 8 == 0 && !(a.dbg & 64)) {
+    MemMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    MT_TRY(make_map_rows(&maps.m[0], a.gpre, 128, 128, a.T, a.B, a.sb, a.st, 132));
+    MT_TRY(make_map_rows(&maps.m[1], a.chat, 128, 128, a.T, a.B, a.sb, a.st, 132));
+    const size_t smem2 = (size_t)FD * 2 * MBOX;
+    if (a.training) { MT_TRY(mtrec::set_smem(mem_fwd_mma2_kernel<true>, smem2)); mem_fwd_mma2_kernel<true><<<grid, NTH2, smem2, st>>>(a, maps); }
+    else { MT_TRY(mtrec::set_smem(mem_fwd_mma2_kernel<false>, smem2)); mem_fwd_mma2_kernel<false><<<grid, NTH2, smem2, st>>>(a, maps); }
+    MT_LAUNCH_CHECK();
+    return MT_OK;
+  }
   const size_t smem = feed_bytes(2 * 128 * 4, 2);
   if (a.training) { MT_TRY(mtrec::set_smem(mem_fwd_mma_kernel<true>, smem)); mem_fwd_mma_kernel<true><<<grid, NTH + 32, smem, st>>>(a); }
   else { MT_TRY(mtrec::set_smem(mem_fwd_mma_kernel<false>, smem)); mem_fwd_mma_kernel<false><<<grid, NTH + 32, smem, st>>>(a); }
@@ -1137,6 +1472,20 @@ int mt_mfn_mma_mem_fwd(const MemArgs& a, cudaStream_t st) {
 
 int mt_mfn_mma_mem_bwd(const MemArgs& a, cudaStream_t st) {
   const int grid = (a.B + NB - 1) / NB;
+  if (a.Hs % 8 == 0 && !(a.dbg & 64)) {
+    MemMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    MT_TRY(make_map_rows(&maps.m[0], a.dlast + a.Hs, 128, a.Hs + 128, a.T, a.B, a.sb, a.st, 132));
+    MT_TRY(make_map_rows(&maps.m[1], a.gm, 256, 256, a.T, a.B, a.sb, a.st, 132));
+    MT_TRY(make_map_rows(&maps.m[2], a.chat, 128, 128, a.T, a.B, a.sb, a.st, 132));
+    MT_TRY(make_map_rows(&maps.m[3], a.memprev_op, 128, 128, a.T, a.B, a.sb, a.st, 136, 2));
+    MT_TRY(make_map_rows(&maps.m[4], a.gh_op, 128, 128, a.T, a.B, a.sb, a.st, 136, 2));
+    const size_t smem2 = (size_t)FD * (4 * MBOX + 2 * MBOXH);
+    MT_TRY(mtrec::set_smem(mem_bwd_mma2_kernel, smem2));
+    mem_bwd_mma2_kernel<<<grid, NTH2, smem2, st>>>(a, maps);
+    MT_LAUNCH_CHECK();
+    return MT_OK;
+  }
   const size_t smem = feed_bytes(128 * 4 + 256 * 4 + 128 * 4 + 128 * 2 + 128 * 2, 5);
   MT_TRY(mtrec::set_smem(mem_bwd_mma_kernel, smem));
   mem_bwd_mma_kernel<<<grid, NTH + 32, smem, st>>>(a);
