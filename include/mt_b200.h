@@ -325,6 +325,14 @@ int mt_comm_unique_id(char* id128);
 int mt_comm_init(const char* id128, int rank, int world, void** comm);
 int mt_comm_destroy(void* comm);
 int mt_allreduce_grads(void* comm, float* const* bufs, const size_t* counts, int n_bufs, void* stream);
+/* Overlapped form ("overlap with the remaining backward").  mt_comm_overlap_arm arms the NEXT mt_encoder_group_bwd call: as
+ * soon as that call has enqueued the weight gradients of layers >= split_layer (split_layer < 0: n_layers / 3) and of the final norm of
+ * every stack, they are all-reduced (SUM, fp32) on the library's communication stream while the backward of the remaining layers still
+ * runs on the caller's stream.  mt_comm_overlap_join makes `stream` wait for that all-reduce and reports the ranges it covered (room for
+ * MT_MAX_MODS entries; *n_ranges = 0 when none was started), so the caller passes only the rest to mt_allreduce_grads.  Both streams may
+ * be under CUDA-graph capture (fork / join through events). */
+int mt_comm_overlap_arm(void* comm, int split_layer);
+int mt_comm_overlap_join(void* stream, float** ptrs, size_t* counts, int* n_ranges);
 
 /* test hook: keep the bf16 LSTM-decoder forward (mt_lstm_head_fwd) on the FFMA kernel instead of the cluster / tensor-core kernel
  * (csrc/mt_lstm_head_mma.cu: E == 256, bf16 mode); returns the previous setting. */

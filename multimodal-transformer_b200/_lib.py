@@ -81,6 +81,8 @@ _PROTOS = {
     'mt_comm_init': (c_int, [c_char_p, c_int, c_int, POINTER(c_void_p)]),
     'mt_comm_destroy': (c_int, [P]),
     'mt_allreduce_grads': (c_int, [P, POINTER(c_void_p), POINTER(c_size_t), c_int, P]),
+    'mt_comm_overlap_arm': (c_int, [P, c_int]),
+    'mt_comm_overlap_join': (c_int, [P, POINTER(c_void_p), POINTER(c_size_t), POINTER(c_int)]),
     'mt_mfn_param_count': (c_size_t, [POINTER(MtMfnCfg)]),
     'mt_mfn_ws_bytes': (c_size_t, [POINTER(MtMfnCfg)]),
     'mt_mfn_fwd': (c_int, [POINTER(MtMfnCfg), P, P, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int64), P, P, P, P, P, P, c_size_t, P]),

@@ -40,6 +40,9 @@ void mt_prof_tag(const char* tag);                   // ... and with a shape tag
 // tuning knobs (mt_tune): [0] GEMM grid share, [1] attention grid share, [2] LayerNorm grid share -- a share of s launches 1/s of the
 // resident CTA slots so that kernels of concurrent streams (the three modality stacks) co-reside instead of queueing
 extern int g_mt_tune[8];
+// overlapped gradient all-reduce of the grouped encoder backward (mt_comm.cu)
+int mt_comm_overlap_split(int n_layers);
+int mt_comm_overlap_fire(float* grads, size_t pstride, int G, size_t tail_off, size_t total, cudaStream_t st);
 #define MT_TUNE_GEMM_SHARE 0
 #define MT_TUNE_ATTN_SHARE 1
 #define MT_TUNE_LN_SHARE 2

@@ -65,6 +65,7 @@ struct Groups {
   size_t pstride = 0;
   uint64_t seed[MT_RS_MAX_GROUPS] = {};
   int stack_id[MT_RS_MAX_GROUPS] = {};
+  bool grouped = false;      // came in through mt_encoder_group_*: the only entry that takes part in the overlapped all-reduce
 };
 
 int carve(const MtEncoderCfg& c, int G, void* ws, EncWs& w) {
@@ -328,6 +329,7 @@ int encoder_bwd_impl(const MtEncoderCfg& c, const Groups& gr, const float* param
     }
   }
 
+  const int ar_split = gr.grouped ? mt_comm_overlap_split(c.n_layers) : -1;
   for (int l = c.n_layers - 1; l >= 0; --l) {
     const size_t base = P.layer_stride * l;
     LayerBufs& b = w.L[l];
@@ -373,6 +375,9 @@ int encoder_bwd_impl(const MtEncoderCfg& c, const Groups& gr, const float* param
     MT_TRY(mt_ln_bwd_run(M, d, x_l, params + base + P.ln1_a, 1e-6f, w.dact2, lp, g_nxt, out, grads + base + P.ln1_a, grads + base + P.ln1_b, st, &nx,
                          G, gr.pstride, drops));
     // g_cur now holds dL/dx_l (g_nxt is free again)
+    // data-parallel training: every gradient of layers >= l and of the final norm is enqueued -- their all-reduce may start now, on the
+    // communication stream, under the backward of layers l - 1 .. 0 (mt_comm_overlap_arm)
+    if (gr.grouped && l == ar_split) MT_TRY(mt_comm_overlap_fire(grads, gr.pstride, G, base, P.total, st));
   }
   return MT_OK;
 }
@@ -447,6 +452,7 @@ int mt_encoder_group_bwd(const MtEncoderCfg* cfg, int n_stacks, const uint64_t* 
   if (mt_encoder_group_ws_bytes(cfg, n_stacks) == 0) return MT_ERR_ARG;
   Groups g;
   MT_TRY(make_groups(*cfg, n_stacks, seeds, stack_ids, param_stride, g));
+  g.grouped = true;
   return encoder_bwd_impl(*cfg, g, params, params_lp, x, mask, dy, dx, grads, ws, ws_bytes, (cudaStream_t)stream);
 }
 

@@ -7,6 +7,8 @@ flat gradient buffers (one process per GPU, torch.distributed; the reference has
     loss = train_step_loss(pred, target, global_sum_lengths)      # backward() included
     opt.step()                                                    # all-reduces first when torch.distributed is up
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -45,6 +47,22 @@ def shard_batch(inputs, mask, target, lengths, rank, world):
     return ({m: take(v) for m, v in inputs.items()}, take(mask), take(target), [lengths[i] for i in mine], float(sum(lengths)))
 
 
+def subtract_ranges(bufs, done):
+    """bufs, done: lists of (address, n_floats).  Returns the parts of `bufs` not covered by `done` (fp32 elements)."""
+    out = []
+    for p, n in bufs:
+        lo, hi = p, p + 4 * n
+        cuts = sorted((max(lo, q), min(hi, q + 4 * c)) for q, c in done if q < hi and q + 4 * c > lo)
+        cur = lo
+        for a, b in cuts:
+            if a > cur:
+                out.append((cur, (a - cur) // 4))
+            cur = max(cur, b)
+        if hi > cur:
+            out.append((cur, (hi - cur) // 4))
+    return out
+
+
 def all_reduce_flat_(bufs, group=None):
     """SUM-all-reduce every flat gradient buffer in place (one collective per arena; NCCL on GPUs, gloo in the CPU tests).
     No-op without an initialised process group or with a single rank."""
@@ -77,6 +95,8 @@ class FlatAdam:
         self.state = {}          # id(arena) -> (m, v)
         self.misc = None
         self._comm_tried, self._comm_handle = False, None
+        self.last_overlap_ranges = 0
+        self.overlap = os.environ.get('MT_AR_OVERLAP', '1') != '0'      # overlap the all-reduce of the upper encoder layers with the rest of the backward (prepare_backward)
         self.param_groups = [dict(lr=lr)]      # ReduceLROnPlateau-style schedulers poke this
 
     def _all_arenas(self):
@@ -143,9 +163,14 @@ class FlatAdam:
         if comm is not None:
             import ctypes
             from . import _lib
-            n = len(flats)
-            bufs = (ctypes.c_void_p * n)(*[g.data_ptr() for _, g in flats])
-            counts = (ctypes.c_size_t * n)(*[g.numel() for _, g in flats])
+            # ranges the armed backward already reduced on the communication stream (prepare_backward): join it, reduce only the rest
+            done_p, done_n, nd = (ctypes.c_void_p * 4)(), (ctypes.c_size_t * 4)(), ctypes.c_int(0)
+            _lib.check(_lib.lib().mt_comm_overlap_join(_lib.stream(), done_p, done_n, ctypes.byref(nd)))
+            self.last_overlap_ranges = nd.value        # how many ranges the backward had already reduced (0: not armed / not grouped)
+            rest = subtract_ranges([(g.data_ptr(), g.numel()) for _, g in flats], [(done_p[i], done_n[i]) for i in range(nd.value)])
+            n = len(rest)
+            bufs = (ctypes.c_void_p * n)(*[p for p, _ in rest])
+            counts = (ctypes.c_size_t * n)(*[c for _, c in rest])
             _lib.check(_lib.lib().mt_allreduce_grads(comm, bufs, counts, n, _lib.stream()))
         else:
             all_reduce_flat_([g for _, g in flats], self.group)
@@ -194,6 +219,16 @@ class FlatAdam:
     def zero_grad(self):
         for p in self.model.parameters():
             p.grad = None
+        self.prepare_backward()
+
+    def prepare_backward(self):
+        """Data-parallel runs: arm the overlapped all-reduce for the next backward (C ABI mt_comm_overlap_arm): the grouped encoder
+        backward hands the gradients of its upper layers to the communication stream as soon as they are enqueued, all_reduce_grads
+        joins and reduces the rest.  Called by zero_grad(), i.e. once per step of the usual loop; a step that was not armed simply
+        reduces everything at the end.  No-op on one rank or without the library communicator."""
+        if self.overlap and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1 and self._comm_handle is not None:
+            from . import _lib
+            _lib.check(_lib.lib().mt_comm_overlap_arm(self._comm_handle, -1))
 
 
 class GraphedTrainStep:

@@ -72,6 +72,18 @@ def test_shard_batch_takes_raw_window_batches():
             assert m[b, :l].all() and not m[b, l:].any() and not x['linguistic'][b, l:].any()
 
 
+def test_subtract_ranges_leaves_what_the_overlapped_all_reduce_did_not_cover():
+    from multimodal_transformer_b200.training import subtract_ranges
+    # one arena of three stacks (stride 100 floats) whose tails [60, 100) were reduced early; a second arena untouched
+    base, other = 4096, 1 << 20
+    done = [(base + 4 * (100 * g + 60), 40) for g in range(3)]
+    rest = subtract_ranges([(base, 300), (other, 17)], done)
+    assert rest == [(base, 60), (base + 400, 60), (base + 800, 60), (other, 17)]
+    assert subtract_ranges([(base, 300)], []) == [(base, 300)]
+    assert subtract_ranges([(base, 40)], [(base, 40)]) == []
+    assert sum(c for _, c in rest) + sum(c for _, c in done) == 317
+
+
 def test_all_reduce_is_noop_without_process_group():
     g = torch.ones(5)
     assert all_reduce_flat_([g])[0] is g and torch.equal(g, torch.ones(5))

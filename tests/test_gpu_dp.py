@@ -23,3 +23,4 @@ def test_sharded_gradients_equal_full_batch_on_real_gpus():
                           '--master-port', '29571', os.path.join(ROOT, 'tools', 'dp_check.py')], capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, (out.stdout[-2000:], out.stderr[-2000:])
     assert out.stdout.count('C-ABI all-reduce used: True') == world
+    assert out.stdout.count('overlapped all-reduce ranges: 3') == world

@@ -44,6 +44,25 @@ for k, v in full.items():
     err = (part[k] - v).abs().max().item() / max(v.abs().max().item(), 1e-3 * gmax)
     worst = max(worst, err)
 print(f'rank {rank}/{world}: C-ABI all-reduce used: {used_c}; worst relative gradient error vs full batch: {worst:.2e}', flush=True)
+
+# overlapped form: one optimizer over two steps -- the first creates the communicator, zero_grad() arms the second, whose grouped encoder
+# backward all-reduces its upper layers on the communication stream (mt_comm_overlap_arm / _join); the sum must not change
+opt = FlatAdam(model)
+xs = {k: torch.from_numpy(v).to(dev) for k, v in x.items()}
+worst2, ranges = 0.0, 0
+for step in range(2):
+    pred = model(xs, torch.from_numpy(m).to(dev), ls)
+    train_step_loss(pred, torch.from_numpy(tg).to(dev), norm)
+    opt.all_reduce_grads()
+    torch.cuda.synchronize()
+    if step == 1:
+        ranges = opt.last_overlap_ranges
+        for k, p in model.named_parameters():
+            if p.grad is not None:
+                worst2 = max(worst2, (p.grad - full[k]).abs().max().item() / max(full[k].abs().max().item(), 1e-3 * gmax))
+    opt.zero_grad()
+print(f'rank {rank}/{world}: overlapped all-reduce ranges: {ranges}; worst relative gradient error vs full batch: {worst2:.2e}', flush=True)
+opt.close()
 dist.barrier()
 dist.destroy_process_group()
-sys.exit(0 if worst < 1e-4 and used_c else 1)
+sys.exit(0 if worst < 1e-4 and used_c and worst2 < 1e-4 and ranges == len(MODS) else 1)
