@@ -73,6 +73,13 @@ size_t mt_linear_ws_bytes(int dtype, int M, int N, int K, int x_f32, float in_dr
 int mt_linear_bwd(int dtype, int M, int N, int K, const void* x, int x_f32, const float* W, const void* y, int y_f32, const void* dy,
                   int dy_f32, int act, const float* rowmask, float in_drop_p, uint64_t seed, uint32_t site, void* dx, float* dW,
                   float* db, void* ws, size_t ws_bytes, void* stream);
+/* Modality concat in front of the early-fusion / embed Linear (SFT/models.py:136-138, B2-Trans/models.py:130-132 torch.cat(outputs, 2)):
+ * dst[:, off_s : off_s + widths[s]] = srcs[s] ([M, widths[s]] contiguous, fp32 if src_f32[s] else bf16), converted to dst's dtype
+ * (row stride ld_dst elements); mt_concat_bwd hands each modality its contiguous slice of the gradient.  dsrcs[s] may be NULL. */
+int mt_concat_fwd(int M, int n_src, const void* const* srcs, const int* widths, const int* src_f32, void* dst, int ld_dst, int dst_f32,
+                  void* stream);
+int mt_concat_bwd(int M, int n_src, void* const* dsrcs, const int* widths, const int* dsrc_f32, const void* ddst, int ld, int ddst_f32,
+                  void* stream);
 size_t mt_linear_bwd_ws_bytes(int dtype, int M, int N, int K, int x_f32, float in_drop_p);
 
 /* ---------------------------------------------------------------------------------------------------

@@ -102,6 +102,8 @@ _PROTOS = {
     'mt_residual_dropout_fwd': (c_int, [P, P, P, c_size_t, c_float, c_uint64, c_uint32, P]),
     'mt_dropout_bwd': (c_int, [P, P, c_size_t, c_float, c_uint64, c_uint32, P]),
     'mt_cast_f32_to_bf16': (c_int, [P, P, c_size_t, P]),
+    'mt_concat_fwd': (c_int, [c_int, c_int, POINTER(c_void_p), POINTER(c_int), POINTER(c_int), P, c_int, c_int, P]),
+    'mt_concat_bwd': (c_int, [c_int, c_int, POINTER(c_void_p), POINTER(c_int), POINTER(c_int), P, c_int, c_int, P]),
     'mt_cast_bf16_to_f32': (c_int, [P, P, c_size_t, P]),
     'mt_mse_loss_fwd_bwd': (c_int, [P, P, c_size_t, c_float, P, P, P]),
     'mt_adam_step': (c_int, [P, P, P, P, c_size_t, c_float, c_float, c_float, c_float, c_float, c_int, P]),

@@ -217,22 +217,22 @@ __global__ void residual_dropout_kernel(size_t n, const float* __restrict__ x, c
 }
 
 template <typename TS, typename TD>
-__global__ void cast2d_kernel(const TS* __restrict__ src, int lds, TD* __restrict__ dst, int ldd, int rows, int cols, DropCfg drop_in) {
+__global__ void cast2d_kernel(const TS* __restrict__ src, int lds, TD* __restrict__ dst, int ldd, int rows, int cols, int dcols, DropCfg drop_in) {
   const DropCfg drop = mt_drop_resolve(drop_in);
-  size_t n = (size_t)rows * ldd;
+  size_t n = (size_t)rows * dcols;                            // destination columns [cols, dcols) are zeroed, [dcols, ldd) left alone
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    int r = (int)(i / ldd), c = (int)(i % ldd);
+    int r = (int)(i / dcols), c = (int)(i % dcols);
     float v = 0.f;
     if (c < cols) v = to_f(src[(size_t)r * lds + c]) * mt_drop_factor(drop, (uint64_t)r * cols + c);
-    dst[i] = from_f<TD>(v);
+    dst[(size_t)r * ldd + c] = from_f<TD>(v);
   }
 }
 
-// vectorised cast2d: 4 columns per thread (cols, lds, ldd multiples of 4; 16-byte aligned rows); pad columns [cols, ldd) are zeroed
+// vectorised cast2d: 4 columns per thread (cols, dcols, lds, ldd multiples of 4; 16-byte aligned rows); pad columns [cols, dcols) are zeroed
 template <typename TS, typename TD>
-__global__ void cast2d_vec_kernel(const TS* __restrict__ src, int lds, TD* __restrict__ dst, int ldd, int rows, int cols, DropCfg drop_in) {
+__global__ void cast2d_vec_kernel(const TS* __restrict__ src, int lds, TD* __restrict__ dst, int ldd, int rows, int cols, int dcols, DropCfg drop_in) {
   const DropCfg drop = mt_drop_resolve(drop_in);
-  const int qpr = ldd >> 2;                                   // quads per destination row
+  const int qpr = dcols >> 2;                                 // quads written per destination row
   const size_t n = (size_t)rows * qpr;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / qpr), c = (int)(i - (size_t)r * qpr) * 4;
@@ -414,25 +414,26 @@ int mt_drop_grad_run(int M, int N, const float* g, void* out, bool out_bf16, Dro
 }
 
 int mt_cast2d_run(const void* src, bool src_bf16, int lds, void* dst, bool dst_bf16, int ldd, int rows, int cols, DropCfg drop,
-                  cudaStream_t st) {
-  if (rows <= 0 || cols <= 0 || ldd < cols || lds < cols) return MT_ERR_ARG;
-  size_t n = (size_t)rows * ldd;
+                  cudaStream_t st, int dcols) {
+  if (dcols < 0) dcols = ldd;                                 // default: zero the whole row tail (a padded staging buffer)
+  if (rows <= 0 || cols <= 0 || ldd < dcols || dcols < cols || lds < cols) return MT_ERR_ARG;
+  size_t n = (size_t)rows * dcols;
   const size_t ses = src_bf16 ? 2 : 4, des = dst_bf16 ? 2 : 4;
-  if (cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && ((uintptr_t)src % (4 * ses)) == 0 && ((uintptr_t)dst % (4 * des)) == 0) {
+  if (cols % 4 == 0 && dcols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && ((uintptr_t)src % (4 * ses)) == 0 && ((uintptr_t)dst % (4 * des)) == 0) {
     const int gridv = ew_grid(n / 4, 256);
-    mt_prof_work(0.0, (double)rows * cols * ses + (double)n * des);
-    if (!src_bf16 && dst_bf16) cast2d_vec_kernel<float, bf16><<<gridv, 256, 0, st>>>((const float*)src, lds, (bf16*)dst, ldd, rows, cols, drop);
-    else if (!src_bf16 && !dst_bf16) cast2d_vec_kernel<float, float><<<gridv, 256, 0, st>>>((const float*)src, lds, (float*)dst, ldd, rows, cols, drop);
-    else if (src_bf16 && dst_bf16) cast2d_vec_kernel<bf16, bf16><<<gridv, 256, 0, st>>>((const bf16*)src, lds, (bf16*)dst, ldd, rows, cols, drop);
-    else cast2d_vec_kernel<bf16, float><<<gridv, 256, 0, st>>>((const bf16*)src, lds, (float*)dst, ldd, rows, cols, drop);
+    mt_prof_work(0.0, (double)rows * cols * ses + (double)rows * dcols * des);
+    if (!src_bf16 && dst_bf16) cast2d_vec_kernel<float, bf16><<<gridv, 256, 0, st>>>((const float*)src, lds, (bf16*)dst, ldd, rows, cols, dcols, drop);
+    else if (!src_bf16 && !dst_bf16) cast2d_vec_kernel<float, float><<<gridv, 256, 0, st>>>((const float*)src, lds, (float*)dst, ldd, rows, cols, dcols, drop);
+    else if (src_bf16 && dst_bf16) cast2d_vec_kernel<bf16, bf16><<<gridv, 256, 0, st>>>((const bf16*)src, lds, (bf16*)dst, ldd, rows, cols, dcols, drop);
+    else cast2d_vec_kernel<bf16, float><<<gridv, 256, 0, st>>>((const bf16*)src, lds, (float*)dst, ldd, rows, cols, dcols, drop);
     MT_LAUNCH_CHECK();
     return MT_OK;
   }
   int grid = ew_grid(n, 256);
-  if (!src_bf16 && dst_bf16) cast2d_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)src, lds, (bf16*)dst, ldd, rows, cols, drop);
-  else if (!src_bf16 && !dst_bf16) cast2d_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, lds, (float*)dst, ldd, rows, cols, drop);
-  else if (src_bf16 && dst_bf16) cast2d_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)src, lds, (bf16*)dst, ldd, rows, cols, drop);
-  else cast2d_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)src, lds, (float*)dst, ldd, rows, cols, drop);
+  if (!src_bf16 && dst_bf16) cast2d_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)src, lds, (bf16*)dst, ldd, rows, cols, dcols, drop);
+  else if (!src_bf16 && !dst_bf16) cast2d_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, lds, (float*)dst, ldd, rows, cols, dcols, drop);
+  else if (src_bf16 && dst_bf16) cast2d_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)src, lds, (bf16*)dst, ldd, rows, cols, dcols, drop);
+  else cast2d_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)src, lds, (float*)dst, ldd, rows, cols, dcols, drop);
   MT_LAUNCH_CHECK();
   return MT_OK;
 }

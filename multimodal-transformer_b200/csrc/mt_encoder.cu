@@ -509,6 +509,36 @@ int mt_linear_fwd(int dtype, int M, int N, int K, const void* x, int x_f32, cons
   return mt_gemm_run(dtype, g, st);
 }
 
+/* Modality concat (SFT/models.py:136-138, B2-Trans/models.py:130-132: torch.cat(outputs, dim=2) in front of the fusion / embed Linear):
+ * dst[:, off_s : off_s + width_s] = src_s, converting to dst's dtype on the way -- the concatenated operand of the following GEMM is
+ * assembled by the library's own strided cast kernel (one launch per modality), no framework copy kernel runs. */
+int mt_concat_fwd(int M, int n_src, const void* const* srcs, const int* widths, const int* src_f32, void* dst, int ld_dst, int dst_f32,
+                  void* stream) {
+  if (M <= 0 || n_src <= 0 || n_src > 8 || !srcs || !widths || !src_f32 || !dst) return MT_ERR_ARG;
+  size_t off = 0;
+  for (int s = 0; s < n_src; ++s) {
+    if (!srcs[s] || widths[s] <= 0 || off + widths[s] > (size_t)ld_dst) return MT_ERR_ARG;
+    MT_TRY(mt_cast2d_run(srcs[s], !src_f32[s], widths[s], (char*)dst + off * (dst_f32 ? 4 : 2), !dst_f32, ld_dst, M, widths[s],
+                         mt_make_drop(0.f, 0, 0), (cudaStream_t)stream, widths[s]));
+    off += widths[s];
+  }
+  return MT_OK;
+}
+/* gradient of the concat: dsrc_s = ddst[:, off_s : off_s + width_s] (contiguous per modality, in dsrc's dtype) */
+int mt_concat_bwd(int M, int n_src, void* const* dsrcs, const int* widths, const int* dsrc_f32, const void* ddst, int ld, int ddst_f32,
+                  void* stream) {
+  if (M <= 0 || n_src <= 0 || n_src > 8 || !dsrcs || !widths || !dsrc_f32 || !ddst) return MT_ERR_ARG;
+  size_t off = 0;
+  for (int s = 0; s < n_src; ++s) {
+    if (widths[s] <= 0 || off + widths[s] > (size_t)ld) return MT_ERR_ARG;
+    if (dsrcs[s])
+      MT_TRY(mt_cast2d_run((const char*)ddst + off * (ddst_f32 ? 4 : 2), !ddst_f32, ld, dsrcs[s], !dsrc_f32[s], widths[s], M, widths[s],
+                           mt_make_drop(0.f, 0, 0), (cudaStream_t)stream));
+    off += widths[s];
+  }
+  return MT_OK;
+}
+
 size_t mt_linear_bwd_ws_bytes(int dtype, int M, int N, int K, int x_f32, float in_drop_p) {
   WsCarver k(nullptr);
   k.take_bytes((size_t)M * N * mt_esize(dtype));

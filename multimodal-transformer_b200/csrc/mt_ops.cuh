@@ -38,7 +38,7 @@ int mt_ln_bwd_run(int M, int d, const float* x, const float* a, float eps, const
 int mt_drop_grad_run(int M, int N, const float* g, void* out, bool out_bf16, DropCfg drop, cudaStream_t st);
 // 2-D cast with zero padding / optional input dropout: dst[r, c] = c < cols ? src[r*lds + c] * drop(r*cols + c) : 0
 int mt_cast2d_run(const void* src, bool src_bf16, int lds, void* dst, bool dst_bf16, int ldd, int rows, int cols, DropCfg drop,
-                  cudaStream_t st);
+                  cudaStream_t st, int dcols = -1);
 // dz = dy * act'(y) * rowmask   (y = post-activation output)
 int mt_act_bwd_run(int M, int N, const void* dy, bool dy_bf16, const void* y, bool y_bf16, int act, const float* rowmask, void* dz,
                    bool dz_bf16, cudaStream_t st);

@@ -222,6 +222,55 @@ class LinearFn(torch.autograd.Function):
         return dx, dW, db, None, None, None, None
 
 
+class ConcatFn(torch.autograd.Function):
+    """torch.cat(feats, dim=-1) in front of the fusion / embed Linear (SFT/models.py:136-138, B2-Trans/models.py:130-132), assembled by
+    the library's strided cast kernel in the compute dtype (mt_concat_fwd / mt_concat_bwd)."""
+
+    @staticmethod
+    def forward(ctx, *feats):
+        import ctypes
+        dt = _state['dtype']
+        shp = feats[0].shape[:-1]
+        widths = [int(f.shape[-1]) for f in feats]
+        xs = []
+        for f in feats:
+            if f.shape[:-1] != shp:
+                raise RuntimeError('concat: leading dimensions differ')
+            f2 = f.reshape(-1, f.shape[-1])
+            f2 = require(f2 if f2.is_contiguous() else f2.contiguous(), name='concat input')
+            if f2.dtype not in (torch.float32, torch.bfloat16):
+                raise RuntimeError(f'concat input dtype {f2.dtype}')
+            xs.append(f2)
+        _lib.check_device(xs[0].device.index)
+        M, n, Kt = xs[0].shape[0], len(xs), sum(widths)
+        out = torch.empty((M, Kt), dtype=torch.float32 if dt == MT_F32 else torch.bfloat16, device=xs[0].device)
+        srcs = (ctypes.c_void_p * n)(*[x.data_ptr() for x in xs])
+        wd = (ctypes.c_int * n)(*widths)
+        f32 = (ctypes.c_int * n)(*[int(x.dtype == torch.float32) for x in xs])
+        check(lib().mt_concat_fwd(M, n, srcs, wd, f32, ptr(out), Kt, int(out.dtype == torch.float32), stream()))
+        ctx.meta = (M, widths, [x.dtype for x in xs], [f.shape for f in feats])
+        return out.view(*shp, Kt)
+
+    @staticmethod
+    def backward(ctx, dy):
+        import ctypes
+        M, widths, dtypes, shapes = ctx.meta
+        Kt = sum(widths)
+        dy2 = dy.reshape(M, Kt)
+        dy2 = require(dy2 if dy2.is_contiguous() else dy2.contiguous(), name='dy')
+        n = len(widths)
+        outs = [torch.empty((M, w), dtype=d, device=dy2.device) if ctx.needs_input_grad[i] else None for i, (w, d) in enumerate(zip(widths, dtypes))]
+        dsts = (ctypes.c_void_p * n)(*[o.data_ptr() if o is not None else None for o in outs])
+        wd = (ctypes.c_int * n)(*widths)
+        f32 = (ctypes.c_int * n)(*[int(d == torch.float32) for d in dtypes])
+        check(lib().mt_concat_bwd(M, n, dsts, wd, f32, ptr(dy2), Kt, int(dy2.dtype == torch.float32), stream()))
+        return tuple(o.view(s) if o is not None else None for o, s in zip(outs, shapes))
+
+
+def concat_features(feats):
+    return ConcatFn.apply(*feats)
+
+
 def linear(x, W, b=None, act=ACT_NONE, rowmask=None, in_drop_p=0.0, out_f32=False):
     return LinearFn.apply(x, W, b, act, rowmask, float(in_drop_p), out_f32)
 

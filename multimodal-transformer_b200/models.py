@@ -162,5 +162,5 @@ class B2MultiCNNTransformer(_FrontEnd):
     def forward(self, inputs, length, mask=None):
         outputs = self._front(inputs)
         if len(outputs) > 1:
-            return self.Transformer(torch.cat([outputs[m] for m in self.mods], 2), mask, length)
+            return self.Transformer(K.concat_features([outputs[m] for m in self.mods]), mask, length)
         return self.Transformer(outputs[self.mods[0]], mask, length)

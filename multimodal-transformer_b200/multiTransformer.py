@@ -479,5 +479,5 @@ class NLPTransformer(nn.Module, _LstmDecoderMixin):
 
 def fusion_layer(feats, weight, bias):
     """Early-fusion head of SFT (SFT/models.py:136-138): tanh(Linear(cat(mods, dim=2)))."""
-    x = torch.cat(list(feats), dim=2)
+    x = K.concat_features(list(feats))       # the library's strided cast kernel assembles the GEMM operand: no framework copy kernel
     return K.linear(x, weight, bias, act=ACT_TANH, out_f32=True)

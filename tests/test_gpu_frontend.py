@@ -501,3 +501,35 @@ def test_graphed_forward_with_window_front_end():
     out = gf({k: t(v) for k, v in inputs.items()}, t(mask))
     torch.cuda.synchronize()
     assert_close(out, ref, 1e-5, 'pred', 1e-7)
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_modality_concat_kernel_equals_torch_cat_and_launches_no_framework_copy(mode):
+    """SFT/models.py:136-138, B2-Trans/models.py:130-132: torch.cat(outputs, 2) in front of the fusion / embed Linear is assembled by the
+    library's strided cast kernel (mt_concat_fwd / _bwd): same values and gradients as torch.cat, at the reference's odd widths."""
+    mtb.set_compute_dtype(mode)
+    try:
+        torch.manual_seed(4)
+        dt = torch.float32 if mode == 'fp32' else torch.bfloat16
+        widths = [88, 256, 300]
+        feats = [torch.randn(5, 7, w, device='cuda').to(dt).requires_grad_(True) for w in widths]
+        L = _lib.lib()
+        n0 = L.mt_launch_count()
+        out = K.concat_features(feats)
+        assert L.mt_launch_count() - n0 == len(widths)
+        ref = torch.cat([f.detach() for f in feats], 2)
+        assert out.dtype == dt and torch.equal(out, ref)
+        g = torch.randn_like(out)
+        n0 = L.mt_launch_count()
+        out.backward(g)
+        assert L.mt_launch_count() - n0 == len(widths)
+        o = 0
+        for f, w in zip(feats, widths):
+            assert f.grad.is_contiguous() and torch.equal(f.grad, g[..., o:o + w])
+            o += w
+        # mixed input dtypes (fp32 features into a bf16 operand) are converted on the way
+        if mode == 'bf16':
+            mixed = [feats[0].detach().float(), feats[1].detach()]
+            assert torch.equal(K.concat_features(mixed), torch.cat([mixed[0].bfloat16(), mixed[1]], 2))
+    finally:
+        mtb.set_compute_dtype('fp32')
