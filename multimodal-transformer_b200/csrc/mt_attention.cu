@@ -338,12 +338,12 @@ static int g_attn_force_ffma = 0;
 
 // G stacks back to back in one call: one launch on the tcgen05 engine, one call per stack otherwise
 int mt_attn_group_fwd_run(int dtype, int G, int B, int T_, int d, int h, const void* qkv, const float* mask, void* out, float* lse,
-                          const DropCfg* drops, cudaStream_t st, const int* klen) {
+                          const DropCfg* drops, cudaStream_t st, const int* klen, const uint32_t* dbits) {
   MT_TRY(check_shape(B, T_, d, h));
   if (!qkv || !out || G < 1 || G > 4) return MT_ERR_ARG;
-  if (G > 1 && dtype == MT_BF16 && !g_attn_force_ffma && !g_mt_attn_no_tc && !mt_attn_force_tiled_on() && mt_attn_tc_supported(B, T_, d, h) &&
+  if ((G > 1 || dbits) && dtype == MT_BF16 && !g_attn_force_ffma && !g_mt_attn_no_tc && !mt_attn_force_tiled_on() && mt_attn_tc_supported(B, T_, d, h) &&
       !(((uintptr_t)qkv | (uintptr_t)out) & 15)) {
-    const int rc = mt_attn_tc_fwd_run(B, T_, d, h, qkv, mask, out, lse, drops[0], st, klen, G, drops);
+    const int rc = mt_attn_tc_fwd_run(B, T_, d, h, qkv, mask, out, lse, drops[0], st, klen, G, drops, dbits);
     if (rc != MT_ERR_UNSUPPORTED) return rc;
   }
   const size_t es = dtype == MT_BF16 ? 2 : 4, M = (size_t)B * T_;
@@ -362,11 +362,11 @@ bool mt_attn_group_bwd_uses_tc(int dtype, int G, int B, int T_, int d, int h, co
 
 int mt_attn_group_bwd_run(int dtype, int G, int B, int T_, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse,
                           const void* dout, void* dqkv, const DropCfg* drops, float* Dws, cudaStream_t st, float* dbias, size_t dbias_gstride,
-                          bool d_ready) {
+                          bool d_ready, const uint32_t* dbits) {
   MT_TRY(check_shape(B, T_, d, h));
   if (!qkv || !out || !lse || !dout || !dqkv || !Dws || G < 1 || G > 4) return MT_ERR_ARG;
-  if ((G > 1 || d_ready) && mt_attn_group_bwd_uses_tc(dtype, G, B, T_, d, h, qkv, out, dout, dqkv, Dws, dbias)) {
-    const int rc = mt_attn_tc_bwd_run(B, T_, d, h, qkv, mask, out, lse, dout, dqkv, drops[0], dbias, Dws, st, G, drops, dbias_gstride, d_ready);
+  if ((G > 1 || d_ready || dbits) && mt_attn_group_bwd_uses_tc(dtype, G, B, T_, d, h, qkv, out, dout, dqkv, Dws, dbias)) {
+    const int rc = mt_attn_tc_bwd_run(B, T_, d, h, qkv, mask, out, lse, dout, dqkv, drops[0], dbias, Dws, st, G, drops, dbias_gstride, d_ready, dbits);
     if (rc != MT_ERR_UNSUPPORTED || d_ready) return rc;
   }
   if (d_ready) return MT_ERR_UNSUPPORTED;      // the caller skipped the full preparation: only the tcgen05 engine can continue

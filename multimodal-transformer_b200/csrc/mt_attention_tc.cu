@@ -45,6 +45,7 @@ struct FwdArgs {
   bf16* out;
   float* lse;
   const int* klen;
+  const uint32_t* dbits;   // optional precomputed keep bits (attn_tc_dropbits_kernel): [G*B][h][4][128] words, bit i of word (c, q) = key 32 c + i of query q
   DropCfg drop[MAXG];
 };
 struct ItemWalk {          // items of this CTA: global item = base + it * step, it < n
@@ -66,7 +67,7 @@ constexpr int FWD_STAGE_BYTES = 3 * TILE_BYTES;
 constexpr int FWD_SMEM = FWD_STAGES * FWD_STAGE_BYTES + 256 + 1024;     // 99.6 KB: two CTAs per SM
 constexpr int FWD_TMEM = 256;                // head w: S at w * 128 (P packed over its first 64 columns), O at w * 128 + 64
 
-template <bool FULL>
+template <bool FULL, bool BITS>
 __global__ void __launch_bounds__(FWD_NT, 2) attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ FwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -164,6 +165,11 @@ __global__ void __launch_bounds__(FWD_NT, 2) attn_tc_fwd_kernel(const __grid_con
       const int Tk = (!FULL && a.klen != nullptr) ? max(1, min(a.klen[bl], a.T)) : a.T;
       const uint32_t bh = (uint32_t)(b * a.h + hd);
       const uint32_t dbase = ((uint32_t)(bl * a.h + hd) * (uint32_t)a.T + (uint32_t)min(r, a.T - 1)) * P2;      // pair-index base of this row, group-local (fits: see host check)
+      uint32_t kw0 = 0u, kw1 = 0u, kw2 = 0u, kw3 = 0u;      // BITS: this row's 128 keep bits, drawn once per step by attn_tc_dropbits_kernel
+      if (BITS && dropping) {
+        const uint32_t* kp = a.dbits + (size_t)bh * 512 + r;
+        kw0 = __ldg(kp); kw1 = __ldg(kp + 128); kw2 = __ldg(kp + 256); kw3 = __ldg(kp + 384);
+      }
       mbar_wait(&s_full[w], par);
       fence_after();
       float mraw = -INFINITY;
@@ -188,6 +194,7 @@ __global__ void __launch_bounds__(FWD_NT, 2) attn_tc_fwd_kernel(const __grid_con
         ld32(t_s + (uint32_t)(c * 32), v);
         ld_wait();
         const uint32_t pbase = dbase + (uint32_t)(c * 16);
+        const uint32_t kw = c == 0 ? kw0 : (c == 1 ? kw1 : (c == 2 ? kw2 : kw3));
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           const int j = c * 32 + i;
@@ -197,9 +204,14 @@ __global__ void __launch_bounds__(FWD_NT, 2) attn_tc_fwd_kernel(const __grid_con
           p1 = (FULL || j + 1 < Tk) ? ex2(p1) : 0.f;
           l2 = add2(l2, pk2(p0, p1));
           if (dropping) {        // one draw per pair of keys: low half -> key j, high half -> key j + 1; the keep scale is applied with 1 / l
-            const uint32_t bits = mt_mix32((pbase + (uint32_t)(i >> 1)) ^ drop.key);
-            p0 = (bits << 16) >= thr_hi ? p0 : 0.f;
-            p1 = bits >= thr_hi ? p1 : 0.f;
+            if (BITS) {
+              p0 = (kw & (1u << i)) ? p0 : 0.f;
+              p1 = (kw & (2u << i)) ? p1 : 0.f;
+            } else {
+              const uint32_t bits = mt_mix32((pbase + (uint32_t)(i >> 1)) ^ drop.key);
+              p0 = (bits << 16) >= thr_hi ? p0 : 0.f;
+              p1 = bits >= thr_hi ? p1 : 0.f;
+            }
           }
           pk[i >> 1] = pack_bf2(p0, p1);
         }
@@ -253,13 +265,15 @@ struct BwdArgs {
   bf16* dqkv;
   float* dbias;           // optional fp32 [3d] per group (dbias_gstride floats apart), accumulated
   size_t dbias_gstride;
+  const uint32_t* dbits;  // optional precomputed keep bits, see FwdArgs
   DropCfg drop[MAXG];
 };
 
 constexpr int BWD_NT = 576;                                             // warps 0-15 compute, 16 TMA, 17 MMA issue + TMEM
 constexpr int BWD_STAGES = 2;
 constexpr int BWD_AUX_BYTES = 2 * 4 * TM * 4;                           // two heads x four per-query vectors
-constexpr int BWD_STAGE_BYTES = 4 * TILE_BYTES + BWD_AUX_BYTES;         // Q | K | V | dO | aux
+constexpr int BWD_BITS_BYTES = 2 * 4 * TM * 4;                          // two heads x 128 keep bits per query (optional)
+constexpr int BWD_STAGE_BYTES = 4 * TILE_BYTES + BWD_AUX_BYTES + BWD_BITS_BYTES;      // Q | K | V | dO | aux | keep bits
 constexpr int BWD_DS_BYTES = TM * TM * 2;                               // dS of one head as an MN-major A operand
 constexpr int BWD_SMEM = BWD_STAGES * BWD_STAGE_BYTES + 2 * BWD_DS_BYTES + 256 + 1024;
 
@@ -381,7 +395,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         const int stage = it & 1;
         mbar_wait(&empty[stage], (((uint32_t)it >> 1) & 1u) ^ 1u);
         uint8_t* sb = stage_base + stage * BWD_STAGE_BYTES;
-        mbar_expect_tx(&full[stage], (uint32_t)BWD_STAGE_BYTES);
+        mbar_expect_tx(&full[stage], (uint32_t)(4 * TILE_BYTES + BWD_AUX_BYTES));
 #pragma unroll
         for (int k = 0; k < 3; ++k) tma_load_2d(sb + k * TILE_BYTES, &map_qkv, k * a.d + hp * 64, b * T, &full[stage]);
         tma_load_2d(sb + 3 * TILE_BYTES, &map_do, hp * 64, b * T, &full[stage]);
@@ -624,7 +638,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
 // next block are issued in front of the gradient MMAs of this one and the compute warps never wait for them; dQ / dK / dV of a block
 // are drained (8 columns per thread) while the next block's gradient MMAs run.
 // TMEM columns: S^T [0,128) | dP^T [128,256) | P^T packed bf16 [256,320) | dV [320,352) | dK [352,384) | dQ [384,416)
-template <bool FULL>
+template <bool FULL, bool BITS>
 __global__ void __launch_bounds__(BWD_NT, 1)
 attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do, const __grid_constant__ BwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -673,11 +687,12 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         const int stage = it & 1;
         mbar_wait(&empty[stage], (((uint32_t)it >> 1) & 1u) ^ 1u);
         uint8_t* sb = stage_base + stage * BWD_STAGE_BYTES;
-        mbar_expect_tx(&full[stage], (uint32_t)BWD_STAGE_BYTES);
+        mbar_expect_tx(&full[stage], (uint32_t)(4 * TILE_BYTES + BWD_AUX_BYTES + (BITS ? BWD_BITS_BYTES : 0)));
 #pragma unroll
         for (int k = 0; k < 3; ++k) tma_load_2d(sb + k * TILE_BYTES, &map_qkv, k * a.d + hp * 64, b * T, &full[stage]);
         tma_load_2d(sb + 3 * TILE_BYTES, &map_do, hp * 64, b * T, &full[stage]);
         bulk_load(sb + 4 * TILE_BYTES, a.aux + ((size_t)b * a.h + 2 * hp) * 4 * TM, (uint32_t)BWD_AUX_BYTES, &full[stage]);
+        if (BITS) bulk_load(sb + 4 * TILE_BYTES + BWD_AUX_BYTES, a.dbits + ((size_t)b * a.h + 2 * hp) * 4 * TM, (uint32_t)BWD_BITS_BYTES, &full[stage]);
       }
     }
   } else if (warp == 17) {
@@ -807,6 +822,9 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
       const int item = iw.base + it * iw.step;
       const int b = item / hp_count, hp = item % hp_count, hd = 2 * hp + w;
       const float* ax = reinterpret_cast<const float*>(stage_base + stage * BWD_STAGE_BYTES + 4 * TILE_BYTES) + w * 4 * TM;
+      // BITS: keep bits of this head, word (c, q) = keys 32 c .. 32 c + 31 of query q; this thread's key is bit (j & 31) of word c = j / 32
+      const uint32_t* kbits = reinterpret_cast<const uint32_t*>(stage_base + stage * BWD_STAGE_BYTES + 4 * TILE_BYTES + BWD_AUX_BYTES) + w * 4 * TM + (j >> 5) * TM;
+      const uint32_t kbit = 1u << (j & 31);
       uint8_t* dsb = ds_smem + (blk & 1) * BWD_DS_BYTES + (g >> 1) * TILE_BYTES;      // this group's 64-query tile of the dS^T operand
       // pair index of (query q, key pair j >> 1) = (bh T + q) P2 + (j >> 1), group-local bh; this lane draws for the queries q + (j & 1)
       const uint32_t bh = (uint32_t)((b - iw.grp * a.B) * a.h + hd);
@@ -838,16 +856,27 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
           upk2(fma2(pk2(__uint_as_float(dp[e + 2]), __uint_as_float(dp[e + 3])), ds2, pk2(-D.z, -D.w)), t[2], t[3]);
           float pd[4] = {p[0], p[1], p[2], p[3]};
           if (dropping) {
+            if (BITS) {
+              const uint4 kw = *reinterpret_cast<const uint4*>(kbits + q);
+              const uint32_t kq[4] = {kw.x, kw.y, kw.z, kw.w};
 #pragma unroll
-            for (int k = 0; k < 4; k += 2) {
-              const uint32_t mine = mt_mix32((pidx0 + (uint32_t)(cc * 16 + e + k) * P2) ^ drop.key);
-              const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
-              const uint32_t b0 = odd ? other : mine, b1 = odd ? mine : other;
-              const bool k0 = odd ? (b0 >= thr_hi) : ((b0 << 16) >= thr_hi), k1 = odd ? (b1 >= thr_hi) : ((b1 << 16) >= thr_hi);
-              pd[k] = k0 ? p[k] : 0.f;
-              t[k] = k0 ? t[k] : -Dk[k];
-              pd[k + 1] = k1 ? p[k + 1] : 0.f;
-              t[k + 1] = k1 ? t[k + 1] : -Dk[k + 1];
+              for (int k = 0; k < 4; ++k) {
+                const bool keep = (kq[k] & kbit) != 0u;
+                pd[k] = keep ? p[k] : 0.f;
+                t[k] = keep ? t[k] : -Dk[k];
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; k += 2) {
+                const uint32_t mine = mt_mix32((pidx0 + (uint32_t)(cc * 16 + e + k) * P2) ^ drop.key);
+                const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+                const uint32_t b0 = odd ? other : mine, b1 = odd ? mine : other;
+                const bool k0 = odd ? (b0 >= thr_hi) : ((b0 << 16) >= thr_hi), k1 = odd ? (b1 >= thr_hi) : ((b1 << 16) >= thr_hi);
+                pd[k] = k0 ? p[k] : 0.f;
+                t[k] = k0 ? t[k] : -Dk[k];
+                pd[k + 1] = k1 ? p[k + 1] : 0.f;
+                t[k + 1] = k1 ? t[k + 1] : -Dk[k + 1];
+              }
             }
           }
           float ev[4];
@@ -890,6 +919,41 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
   }
 }
 
+// Keep bits of the attention-probability dropout for a whole launch, drawn ONCE per step and layer (forward and backward read the same
+// words): bits[bh][c][q], bit i of word (c, q) = key 32 c + i of query q, from exactly the pair-hash draws the kernels make themselves
+// (pair index ((b_local h + hd) T + q) P2 + (j >> 1), low half -> even key).  One thread per word: 16 draws.
+struct BitsArgs { int B, T, h, G; DropCfg drop[MAXG]; };
+__global__ void __launch_bounds__(256) attn_tc_dropbits_kernel(const __grid_constant__ BitsArgs a, uint32_t* __restrict__ bits) {
+  const uint32_t per_group = (uint32_t)(a.B * a.h) * 512u;               // words of one group
+  const uint32_t n = per_group * (uint32_t)a.G;
+  const uint32_t P2 = (uint32_t)(a.T + 1) >> 1;
+  uint32_t key[MAXG], thr[MAXG];
+#pragma unroll
+  for (int g = 0; g < MAXG; ++g) {
+    const DropCfg d = mt_drop_resolve(a.drop[g < a.G ? g : 0]);
+    key[g] = d.key; thr[g] = d.thresh != 0u ? (d.thresh >> 16) : 0x10000u;      // 16-bit threshold; 0x10000: dropout off, every draw is below it
+  }
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+    const uint32_t q = idx & (TM - 1), c = (idx >> 7) & 3u;
+    const uint32_t grp = idx / per_group;
+    const uint32_t blh = (idx - grp * per_group) >> 9;                   // group-local narrative * h + head
+    const uint32_t k = grp == 0 ? key[0] : (grp == 1 ? key[1] : (grp == 2 ? key[2] : key[3]));
+    const uint32_t t16 = grp == 0 ? thr[0] : (grp == 1 ? thr[1] : (grp == 2 ? thr[2] : thr[3]));
+    uint32_t word = 0xffffffffu;
+    if (t16 != 0x10000u && q < (uint32_t)a.T) {
+      word = 0u;
+      const uint32_t pbase = (blh * (uint32_t)a.T + q) * P2 + c * 16u;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const uint32_t b = mt_mix32((pbase + (uint32_t)i) ^ k);
+        word |= ((b & 0xffffu) >= t16 ? 1u : 0u) << (2 * i);
+        word |= ((b >> 16) >= t16 ? 2u : 0u) << (2 * i);
+      }
+    }
+    bits[idx] = word;
+  }
+}
+
 // one-time (per device) opt-in to the large dynamic shared-memory carve-out
 template <typename K>
 int set_smem_attr(K kernel, int bytes, MtPerDeviceOnce& once) {
@@ -913,8 +977,23 @@ bool mt_attn_tc_supported(int B, int T, int d, int h) {
   return d % 64 == 0;
 }
 
+size_t mt_attn_tc_dropbits_words(int G, int B, int h) { return (size_t)G * B * h * 4 * TM; }
+
+int mt_attn_tc_dropbits_run(int G, int B, int T, int h, const DropCfg* drops, uint32_t* bits, cudaStream_t st) {
+  if (G < 1 || G > MAXG || !drops || !bits || T < 1 || T > TM || (unsigned long long)G * B * h * 512ull >= 0xffffffffull) return MT_ERR_ARG;
+  BitsArgs a;
+  a.B = B; a.T = T; a.h = h; a.G = G;
+  for (int i = 0; i < MAXG; ++i) a.drop[i] = drops[i < G ? i : 0];
+  const size_t n = mt_attn_tc_dropbits_words(G, B, h);
+  mt_prof_work(0.0, (double)n * 4.0);
+  const size_t cap = (size_t)num_sms() * 8;
+  attn_tc_dropbits_kernel<<<(unsigned)((n + 255) / 256 < cap ? (n + 255) / 256 : cap), 256, 0, st>>>(a, bits);
+  MT_LAUNCH_CHECK();
+  return MT_OK;
+}
+
 int mt_attn_tc_fwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop, cudaStream_t st,
-                       const int* klen, int G, const DropCfg* drops) {
+                       const int* klen, int G, const DropCfg* drops, const uint32_t* dbits) {
   if (!mt_attn_tc_supported(B, T, d, h) || G < 1 || G > MAXG || (long long)G * B * T > 0x7fffffffLL / (3LL * d)) return MT_ERR_UNSUPPORTED;
   if (((uintptr_t)qkv & 15) || ((uintptr_t)out & 15)) return MT_ERR_ALIGN;
   CUtensorMap map;
@@ -922,19 +1001,20 @@ int mt_attn_tc_fwd_run(int B, int T, int d, int h, const void* qkv, const float*
   FwdArgs a;
   a.B = B; a.T = T; a.d = d; a.h = h; a.G = G;
   a.scale_log2 = LOG2E / sqrtf((float)HD);
-  a.mask = mask; a.out = (bf16*)out; a.lse = lse; a.klen = klen;
+  a.mask = mask; a.out = (bf16*)out; a.lse = lse; a.klen = klen; a.dbits = dbits;
   for (int i = 0; i < MAXG; ++i) a.drop[i] = drops && i < G ? drops[i] : drop;
   static MtPerDeviceOnce attr_full, attr_part;
   const int slots = 2 * num_sms(), n_items = B * (h / 2);
   const int cpg = n_items < slots / G ? n_items : slots / G;      // CTAs per group
   const int grid = cpg * G;
   mt_prof_work(4.0 * G * B * (double)T * T * d, (double)G * B * T * d * 4.0 * 2.0);
+  static MtPerDeviceOnce attr_full_b, attr_part_b;
   if (T == TM && !klen) {
-    MT_TRY(set_smem_attr(attn_tc_fwd_kernel<true>, FWD_SMEM, attr_full));
-    attn_tc_fwd_kernel<true><<<grid, FWD_NT, FWD_SMEM, st>>>(map, a);
+    if (dbits) { MT_TRY(set_smem_attr(attn_tc_fwd_kernel<true, true>, FWD_SMEM, attr_full_b)); attn_tc_fwd_kernel<true, true><<<grid, FWD_NT, FWD_SMEM, st>>>(map, a); }
+    else { MT_TRY(set_smem_attr(attn_tc_fwd_kernel<true, false>, FWD_SMEM, attr_full)); attn_tc_fwd_kernel<true, false><<<grid, FWD_NT, FWD_SMEM, st>>>(map, a); }
   } else {
-    MT_TRY(set_smem_attr(attn_tc_fwd_kernel<false>, FWD_SMEM, attr_part));
-    attn_tc_fwd_kernel<false><<<grid, FWD_NT, FWD_SMEM, st>>>(map, a);
+    if (dbits) { MT_TRY(set_smem_attr(attn_tc_fwd_kernel<false, true>, FWD_SMEM, attr_part_b)); attn_tc_fwd_kernel<false, true><<<grid, FWD_NT, FWD_SMEM, st>>>(map, a); }
+    else { MT_TRY(set_smem_attr(attn_tc_fwd_kernel<false, false>, FWD_SMEM, attr_part)); attn_tc_fwd_kernel<false, false><<<grid, FWD_NT, FWD_SMEM, st>>>(map, a); }
   }
   MT_LAUNCH_CHECK();
   return MT_OK;
@@ -942,7 +1022,7 @@ int mt_attn_tc_fwd_run(int B, int T, int d, int h, const void* qkv, const float*
 
 int mt_attn_tc_bwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse, const void* dout,
                        void* dqkv, DropCfg drop, float* dbias, float* aux, cudaStream_t st, int G, const DropCfg* drops, size_t dbias_gstride,
-                       bool d_ready) {
+                       bool d_ready, const uint32_t* dbits) {
   if (!mt_attn_tc_supported(B, T, d, h) || G < 1 || G > MAXG || (long long)G * B * T > 0x7fffffffLL / (3LL * d)) return MT_ERR_UNSUPPORTED;
   if (dbias != nullptr && h > 8) return MT_ERR_UNSUPPORTED;
   if (!aux || ((uintptr_t)aux & 15) || ((uintptr_t)qkv & 15) || ((uintptr_t)dout & 15) || ((uintptr_t)dqkv & 15) || ((uintptr_t)out & 15))
@@ -965,7 +1045,7 @@ int mt_attn_tc_bwd_run(int B, int T, int d, int h, const void* qkv, const float*
   MT_TRY(make_map_2d(&map_do, dout, (uint64_t)d, (uint64_t)G * B * T, (uint64_t)d, 64, TM));
   BwdArgs a;
   a.B = B; a.T = T; a.d = d; a.h = h; a.G = G;
-  a.aux = aux; a.dqkv = (bf16*)dqkv; a.dbias = dbias; a.dbias_gstride = dbias_gstride;
+  a.aux = aux; a.dqkv = (bf16*)dqkv; a.dbias = dbias; a.dbias_gstride = dbias_gstride; a.dbits = dbits;
   for (int i = 0; i < MAXG; ++i) a.drop[i] = drops && i < G ? drops[i] : drop;
   static MtPerDeviceOnce attr_full, attr_part;
   const int sms = num_sms(), n_items = B * (h / 2);
@@ -982,11 +1062,13 @@ int mt_attn_tc_bwd_run(int B, int T, int d, int h, const void* qkv, const float*
       attn_tc_bwd_kernel<false><<<grid, BWD_NT, BWD_SMEM, st>>>(map_qkv, map_do, a);
     }
   } else if (T == TM) {
-    MT_TRY(set_smem_attr(attn_tc_bwd2_kernel<true>, BWD_SMEM, attr2_full));
-    attn_tc_bwd2_kernel<true><<<grid, BWD_NT, BWD_SMEM, st>>>(map_qkv, map_do, a);
+    static MtPerDeviceOnce attr2_full_b;
+    if (dbits) { MT_TRY(set_smem_attr(attn_tc_bwd2_kernel<true, true>, BWD_SMEM, attr2_full_b)); attn_tc_bwd2_kernel<true, true><<<grid, BWD_NT, BWD_SMEM, st>>>(map_qkv, map_do, a); }
+    else { MT_TRY(set_smem_attr(attn_tc_bwd2_kernel<true, false>, BWD_SMEM, attr2_full)); attn_tc_bwd2_kernel<true, false><<<grid, BWD_NT, BWD_SMEM, st>>>(map_qkv, map_do, a); }
   } else {
-    MT_TRY(set_smem_attr(attn_tc_bwd2_kernel<false>, BWD_SMEM, attr2_part));
-    attn_tc_bwd2_kernel<false><<<grid, BWD_NT, BWD_SMEM, st>>>(map_qkv, map_do, a);
+    static MtPerDeviceOnce attr2_part_b;
+    if (dbits) { MT_TRY(set_smem_attr(attn_tc_bwd2_kernel<false, true>, BWD_SMEM, attr2_part_b)); attn_tc_bwd2_kernel<false, true><<<grid, BWD_NT, BWD_SMEM, st>>>(map_qkv, map_do, a); }
+    else { MT_TRY(set_smem_attr(attn_tc_bwd2_kernel<false, false>, BWD_SMEM, attr2_part)); attn_tc_bwd2_kernel<false, false><<<grid, BWD_NT, BWD_SMEM, st>>>(map_qkv, map_do, a); }
   }
   MT_LAUNCH_CHECK();
   return MT_OK;

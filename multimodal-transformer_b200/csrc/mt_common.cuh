@@ -39,7 +39,7 @@ void mt_prof_tag(const char* tag);                   // ... and with a shape tag
 
 // tuning knobs (mt_tune): [0] GEMM grid share, [1] attention grid share, [2] LayerNorm grid share -- a share of s launches 1/s of the
 // resident CTA slots so that kernels of concurrent streams (the three modality stacks) co-reside instead of queueing
-extern int g_mt_tune[8];
+extern int g_mt_tune[16];
 // overlapped gradient all-reduce of the grouped encoder backward (mt_comm.cu)
 int mt_comm_overlap_split(int n_layers);
 int mt_comm_overlap_fire(float* grads, size_t pstride, int G, size_t tail_off, size_t total, cudaStream_t st);
@@ -49,6 +49,9 @@ int mt_comm_overlap_fire(float* grads, size_t pstride, int G, size_t tail_off, s
 #define MT_TUNE_PDL 3          // [3] programmatic dependent launch of the tcgen05 GEMM (prologue overlaps the previous kernel's tail)
 #define MT_TUNE_NO_RS 5        // [5] != 0: the encoder's projections skip the row-stream engine (A/B against the streaming engine)
 #define MT_TUNE_NO_BIG_TILES 7 // [7] != 0: no 256-row / 256-wide tiles for the L2-bound GEMMs (split-K wgrads, long-K dgrad)
+#define MT_TUNE_REC_DEBUG 8    // [8] MFN recurrences: bit 5 clock trace of one CTA, bit 6 first-cut kernels (A/B), bits 0-3 timing experiments of the first cut
+#define MT_TUNE_NO_DROPBITS 9  // [9] != 0: the tcgen05 attention kernels draw their dropout hashes themselves instead of reading precomputed keep bits
+#define MT_TUNE_NO_MGROUPS 10  // [10] != 0: streaming GEMMs of the stacked modality rows launch per stack instead of once with row groups
 #define MT_TUNE_NO_LNFUSE 6    // [6] != 0: no LayerNorm fused into the FFN output projection's epilogue
 
 // one-time-per-DEVICE guard for cudaFuncSetAttribute-style opt-ins (a process may drive several GPUs): true the first time the

@@ -44,6 +44,7 @@ struct LayerBufs {
   float* xp;      // x + attn sublayer [M,d]   fp32
   void* v;        // LN2(xp)           [M,d]   dtype
   void* hid;      // relu/dropout FFN hidden [M,dff] dtype
+  uint32_t* dbits; // keep bits of the attention-probability dropout (tcgen05 attention, training): drawn once, read by forward and backward
 };
 
 struct EncWs {
@@ -83,6 +84,7 @@ int carve(const MtEncoderCfg& c, int G, void* ws, EncWs& w) {
     b.xp = k.take<float>(M * d);
     b.v = k.take_bytes(M * d * es);
     b.hid = k.take_bytes(M * c.dff * es);
+    b.dbits = (c.training && c.dtype == MT_BF16 && mt_attn_tc_supported(c.B, c.T, c.d, c.h)) ? k.take<uint32_t>(mt_attn_tc_dropbits_words(G, c.B, c.h)) : nullptr;
   }
   float* x_alt = c.training ? nullptr : k.take<float>(M * d);   // inference ping-pong of the residual stream
   for (int l = sets; l < c.n_layers; ++l) {
@@ -196,6 +198,17 @@ struct Proj {
       if (!g_mt_tune[MT_TUNE_NO_RS] && mt_gemm_rs_supported(r)) return mt_gemm_rs_run(r, st);
     }
     const size_t es = mt_esize(c.dtype);
+    // a projection the row-stream engine does not take (the long-K input gradient of the QKV projection) with nothing per group but its
+    // weight matrix: ONE streaming launch over the stacked rows, tile -> weight matrix of its stack (GemmDesc.mgroups)
+    if (lp && gr.G > 1 && b_off < 0 && act == MT_ACT_NONE && p == 0.f && colsum_off < 0 && !ln_out && !g_mt_tune[MT_TUNE_NO_MGROUPS]) {
+      const void* W0 = wptr(c, params, params_lp, w_off);
+      GemmDesc d = dgrad ? dgrad_gemm(gr.G * M, K, N, A, W0, C, c_f32) : fwd_gemm(gr.G * M, N, K, A, W0, C, c_f32);
+      d.mgroups = gr.G; d.b_gstride = (long long)gr.pstride;
+      if (gate) { d.epi.gate = gate; d.epi.ldg = N; d.epi.gate_scale = gate_scale; }
+      if (residual) { d.epi.residual = residual; d.epi.ldr = N; }
+      const int rc = mt_gemm_run(c.dtype, d, st);
+      if (rc != MT_ERR_UNSUPPORTED) return rc;
+    }
     for (int g = 0; g < gr.G; ++g) {
       const size_t ro = (size_t)g * M;
       const void* Ag = (const char*)A + ro * K * es;
@@ -251,6 +264,10 @@ int encoder_fwd_impl(const MtEncoderCfg& c, const Groups& gr, const float* param
   // GEMM whenever its output has the operand dtype and the row-stream engine takes the shape
   const bool y_lp = lp && !c.y_f32;
   bool u_ready = false;
+  // Keep bits of the attention-probability dropout (tcgen05 engine, training): drawn once per layer, right before its attention; the
+  // backward kernel reads the same words.  (Measured: drawing all layers up front on a side stream buys nothing -- the row-stream GEMMs
+  // and LayerNorm kernels it would run under own every register of their SMs, so the ALU-bound draw kernel cannot co-reside.)
+  const bool use_bits = c.training && c.p_drop > 0.f && !c.key_len && !g_mt_tune[MT_TUNE_NO_DROPBITS] && w.L[0].dbits != nullptr;
   for (int l = 0; l < c.n_layers; ++l) {
     const size_t base = P.layer_stride * l;
     LayerBufs& b = w.L[l];
@@ -261,7 +278,9 @@ int encoder_fwd_impl(const MtEncoderCfg& c, const Groups& gr, const float* param
     {
       DropCfg ad[MT_RS_MAX_GROUPS];
       for (int g = 0; g < G; ++g) ad[g] = mt_make_drop(c.p_drop, gr.seed[g], mt_enc_site(gr.stack_id[g], l, MT_SITE_ATTN_P));
-      MT_TRY(mt_attn_group_fwd_run(c.dtype, G, c.B, c.T, d, c.h, b.qkv, mask, b.att, b.lse, ad, st, c.key_len));
+      const uint32_t* bits = use_bits ? b.dbits : nullptr;
+      if (bits) MT_TRY(mt_attn_tc_dropbits_run(G, c.B, c.T, c.h, ad, b.dbits, st));
+      MT_TRY(mt_attn_group_fwd_run(c.dtype, G, c.B, c.T, d, c.h, b.qkv, mask, b.att, b.lse, ad, st, c.key_len, bits));
     }
     MT_TRY(pj.run(false, d, d, b.att, base + P.w_o, b.xp, true, (long long)(base + P.b_o), MT_ACT_NONE, l, MT_SITE_SUB0, nullptr, 1.f, xin, -1));
     // sublayer 1: x + dropout(w_2(dropout(relu(w_1(LN(x))))))
@@ -364,8 +383,9 @@ int encoder_bwd_impl(const MtEncoderCfg& c, const Groups& gr, const float* param
     {
       DropCfg ad[MT_RS_MAX_GROUPS];
       for (int g = 0; g < G; ++g) ad[g] = mt_make_drop(p, gr.seed[g], mt_enc_site(gr.stack_id[g], l, MT_SITE_ATTN_P));
+      const uint32_t* bits = (b.dbits && p > 0.f && !c.key_len && !g_mt_tune[MT_TUNE_NO_DROPBITS]) ? b.dbits : nullptr;      // drawn by the forward
       MT_TRY(mt_attn_group_bwd_run(c.dtype, G, c.B, c.T, d, c.h, b.qkv, mask, b.att, b.lse, w.dact2, w.dqkv, ad, w.Dws, st,
-                                   grads + base + P.b_qkv, gr.pstride, d_ready));
+                                   grads + base + P.b_qkv, gr.pstride, d_ready, bits));
     }
     MT_TRY(pj.wgrad(3 * d, d, w.dqkv, b.u, base + P.w_qkv));
     MT_TRY(pj.run(true, d, 3 * d, w.dqkv, base + P.w_qkv, w.dact2, !lp, -1, MT_ACT_NONE, l, -1, nullptr, 1.f, nullptr, -1));

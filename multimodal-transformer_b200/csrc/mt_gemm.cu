@@ -23,7 +23,7 @@ int mt_gemm_run(int dtype, const GemmDesc& g, cudaStream_t st) {
 #if MT_HAVE_TC
   if (dtype == MT_BF16 && !g_force_simt && mt_gemm_tc_supported(g)) return mt_gemm_tc_run(g, st);
 #endif
-  if (g.groups > 1) return MT_ERR_UNSUPPORTED;      // grouped split-K exists on the tcgen05 engine only: the caller launches per group
+  if (g.groups > 1 || g.mgroups > 1) return MT_ERR_UNSUPPORTED;      // grouped forms exist on the tcgen05 engine only: the caller launches per group
   if (g.epi.colsum) {        // the FFMA engine has no fused column sum: run it, then one column-sum pass over C
     if (g.split_k > 1) return MT_ERR_ARG;
     GemmDesc g2 = g;

@@ -32,6 +32,8 @@ struct GemmDesc {
   int split_k = 1;                 // >1: partial sums are atomically added into fp32 C (caller zeroes C)
   int groups = 1;                  // >1 (tcgen05 split-K wgrad form only, both operands mn-major): group g contracts rows [g*K, (g+1)*K) of
   long long c_gstride = 0;         //     A / B into C + g * c_gstride -- the weight gradients of several modality stacks in one launch
+  int mgroups = 1;                 // >1 (tcgen05 engine only): the M rows are mgroups equal blocks (modality stacks back to back), block g
+  long long b_gstride = 0;         //     multiplies by the weight matrix at B + g * b_gstride elements; no bias / colsum / dropout
   GemmEpi epi;
 };
 

@@ -40,6 +40,8 @@ constexpr int KB_RES = 4;              // weight-resident mode: at most this man
 constexpr int MAX_STAGES = 8;
 constexpr uint32_t SPIN_LIMIT = 1u << 27;
 
+struct TcMapsB { CUtensorMap m[4]; };      // B operand per row group (one entry unless TcArgs.mgroups > 1)
+
 struct TcArgs {
   int M, N, K;
   int tiles_m, tiles_n, splits, kb_total, kb_per;
@@ -47,6 +49,7 @@ struct TcArgs {
   void* C; int ldc; int c_f32; int atomic;
   GemmEpi epi;
   int gate_bf16;
+  int mgroups, tiles_m_group;          // row groups (input gradients of several stacks): rows of group g = tiles [g * tiles_m_group, +tiles_m_group) use B map g
   int groups, kb_group;                // grouped split-K (wgrads of several modality stacks): group g contracts k-blocks [g*kb_group, +kb_total)
   long long c_gstride;                 // ... into C + g * c_gstride (fp32 elements)
   unsigned long long* trace;           // debug: per-tile clock64 stamps of CTA 0 (mt_gemm_debug_trace), else null
@@ -194,7 +197,7 @@ __device__ __forceinline__ bool get_work(const TcArgs& g, int i, int& tm, int& t
 
 template <int BN, uint32_t F, bool RES, int OCC, int MT>
 __global__ void __launch_bounds__(Smem<BN, OCC, MT>::THREADS, OCC)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ TcArgs g) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ TcMapsB maps_b, const __grid_constant__ TcArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // 1 KB aligned, still a shared-space pointer
   using S = Smem<BN, OCC, MT>;
@@ -220,7 +223,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps_b.m[0]) : "memory");
     for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], S::EW); }
     mbar_init(b_full, 1);
@@ -250,15 +253,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           uint8_t* sb = res_b + kb * S::B_BYTES;
           if (b_mn) {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), &map_b, tn * BN + 64 * j, kb * BK, b_full);
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), &maps_b.m[0], tn * BN + 64 * j, kb * BK, b_full);
           } else {
-            tma_load_2d(sb, &map_b, kb * BK, tn * BN, b_full);
+            tma_load_2d(sb, &maps_b.m[0], kb * BK, tn * BN, b_full);
           }
         }
       }
       int stage = 0; uint32_t phase = 0;
       for (int i = 0; get_work<RES>(g, i, tm, tn, split, grp); ++i) {
         const int m0 = tm * TM_ROWS, n0 = tn * BN;
+        const CUtensorMap* map_b = &maps_b.m[g.mgroups > 1 ? tm / g.tiles_m_group : 0];
         const int kbase = grp * g.kb_group;
         const int kb0 = kbase + split * kb_per, kb1 = min(kbase + kb_total, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -279,9 +283,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             uint8_t* sb = sa + S::A_BYTES;
             if (b_mn) {
 #pragma unroll
-              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), &map_b, n0 + 64 * j, k0, &full[stage]);
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), map_b, n0 + 64 * j, k0, &full[stage]);
             } else {
-              tma_load_2d(sb, &map_b, k0, n0, &full[stage]);
+              tma_load_2d(sb, map_b, k0, n0, &full[stage]);
             }
           }
           if (++stage == NS) { stage = 0; phase ^= 1; }
@@ -587,7 +591,7 @@ unsigned long long* g_trace = nullptr;
 int g_tc_mode = 2;       // 0 = 256-wide tiles where they apply, 1 = one CTA per SM everywhere, 2 = never use the 256-wide tile (default: measured fastest)
 
 template <int BN, uint32_t F, bool RES, int OCC = 1, int MT = 1>
-int launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& g, int grid, cudaStream_t st) {
+int launch_inst(const CUtensorMap& ma, const TcMapsB& mb, const TcArgs& g, int grid, cudaStream_t st) {
   static MtPerDeviceOnce once;
   static_assert(Smem<BN, OCC, MT>::TOTAL <= 227 * 1024, "shared memory budget");
   if (once.first()) MT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, F, RES, OCC, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN, OCC, MT>::TOTAL));
@@ -645,9 +649,15 @@ int launch_tc(const GemmDesc& d, cudaStream_t st) {
   g.gate_bf16 = 1;
   g.groups = groups; g.kb_group = groups > 1 ? d.K / BK : 0; g.c_gstride = d.c_gstride;
   g.trace = g_trace;
-  CUtensorMap ma, mb;
+  const int mgroups = d.mgroups > 1 ? d.mgroups : 1;
+  if (mgroups > 1 && (mgroups > 4 || d.M % mgroups != 0 || (d.M / mgroups) % (MT * BM) != 0)) return MT_ERR_UNSUPPORTED;
+  g.mgroups = mgroups; g.tiles_m_group = g.tiles_m / mgroups;
+  CUtensorMap ma;
+  TcMapsB mb;
+  memset(&mb, 0, sizeof(mb));
   MT_TRY(make_map(&ma, d.A, d.M, d.K * groups, d.lda, d.a_kmajor, BM));
-  MT_TRY(make_map(&mb, d.B, d.N, d.K * groups, d.ldb, d.b_kmajor, BN));
+  for (int i = 0; i < mgroups; ++i)
+    MT_TRY(make_map(&mb.m[i], (const bf16*)d.B + (size_t)i * (size_t)d.b_gstride, d.N, d.K * groups, d.ldb, d.b_kmajor, BN));
   const int n_work = g.tiles_m * g.tiles_n * g.splits * groups;
   // g_tc_share > 1: launch only 1/share of the resident CTA slots so that GEMMs of concurrent streams (the three modality stacks)
   // co-reside on every SM instead of queueing behind each other (mt_tune)
@@ -656,7 +666,7 @@ int launch_tc(const GemmDesc& d, cudaStream_t st) {
   const int grid = n_work < slots ? n_work : slots;
   const uint32_t f = needed_features<BN, MT>(d, g);
   // weight-resident mode: short K, no split, and at least one CTA per column slice
-  const bool res = OCC == 1 && g.splits == 1 && g.kb_total <= KB_RES && grid >= g.tiles_n;
+  const bool res = OCC == 1 && g.splits == 1 && g.kb_total <= KB_RES && grid >= g.tiles_n && mgroups == 1;
   if constexpr (MT == 2) {      // 256-row tiles: the L2-bound shapes only (see mt_gemm_tc_run)
     switch (f) {
       case F_ATOMIC | F_CF32: return launch_inst<BN, F_ATOMIC | F_CF32, false, 1, 2>(ma, mb, g, grid, st);
@@ -699,6 +709,9 @@ bool mt_gemm_tc_supported(const GemmDesc& d) {
   if (((uintptr_t)d.A & 15) || ((uintptr_t)d.B & 15) || ((uintptr_t)d.C & 15)) return false;
   if (d.epi.accumulate) return false;
   if (d.groups > 1 && (d.split_k <= 1 || d.a_kmajor || d.b_kmajor || d.K % BK != 0)) return false;      // grouping: split-K wgrad form only
+  if (d.mgroups > 1 && (d.groups > 1 || d.split_k > 1 || d.mgroups > 4 || d.M % d.mgroups != 0 || (d.b_gstride & 7) || d.epi.bias || d.epi.colsum ||
+                        d.epi.drop.thresh != 0u))
+    return false;                                         // row groups: one weight matrix per group, nothing else per group
   if (d.split_k > 1 && !d.c_f32) return false;
   if (d.epi.colsum && (d.split_k > 1 || d.N > 1024)) return false;
   if (d.epi.bias && ((uintptr_t)d.epi.bias & 15)) return false;

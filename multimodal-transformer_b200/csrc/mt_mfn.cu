@@ -843,7 +843,7 @@ static void fill_lstm_args(LstmArgs& a, const MtMfnCfg& c, const Dims& D, const 
   a.h_last = a.c_last = nullptr;
   a.training = c.training;
   a.dlast = S.dlast; a.dcstar = S.datt; a.dz_op = S.dz_op;
-  a.dbg = g_mt_tune[7];
+  a.dbg = g_mt_tune[MT_TUNE_REC_DEBUG];
 }
 
 static void fill_mem_args(MemArgs& a, const MtMfnCfg& c, const Dims& D, const Stash& S, const float* params, const void* params_lp,
@@ -860,7 +860,7 @@ static void fill_mem_args(MemArgs& a, const MtMfnCfg& c, const Dims& D, const St
   a.drop_g2 = mt_make_drop(c.p_gamma, c.seed, MT_SITE_MFN_G2);
   a.training = c.training;
   a.dlast = S.dlast; a.dzg_op = S.dzg_op; a.dzchat_op = S.dzchat_op; a.dgh_op = S.dgh_op;
-  a.dbg = g_mt_tune[7];
+  a.dbg = g_mt_tune[MT_TUNE_REC_DEBUG];
 }
 
 int mt_mfn_fwd(const MtMfnCfg* cfg, const float* params, const void* params_lp, const void* const* x, const int64_t* stride_b,

@@ -20,7 +20,7 @@ struct LstmArgs {
   const float* dlast;                // backward: [M,Hs+MEM]
   const float* dcstar;               //           [M,2Hs]
   void* dz_op;                       //           ST [M,4Hs]
-  int dbg;                           // timing experiments (mt_tune key 7): bit 0 no gate stash, 1 no state stores, 2 no feed, 3 no mma
+  int dbg;                           // timing experiments (mt_tune key 8): bit 0 no gate stash, 1 no state stores, 2 no feed, 3 no mma
 };
 
 struct MemArgs {

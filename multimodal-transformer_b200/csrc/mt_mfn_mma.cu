@@ -21,7 +21,7 @@
 #include "mt_recurrent.cuh"
 #include "mt_tcgen05.cuh"
 
-// timing experiment (mt_tune key 7, bit 5): clock64 stamps of warp 0 / lane 0 of one CTA, 8 per step
+// timing experiment (mt_tune key 8, bit 5): clock64 stamps of warp 0 / lane 0 of one CTA, 8 per step
 __device__ unsigned long long g_rec_trace[4][128][8];
 __device__ unsigned long long g_rec_trace2[8][128][8];      // [compute warp][step][stamp] of the second-cut LSTM forward
 

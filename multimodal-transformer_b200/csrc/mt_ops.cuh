@@ -70,12 +70,15 @@ bool mt_attn_tc_supported(int B, int T, int d, int h);
 // G > 1: G modality stacks back to back (B narratives each; qkv / out / lse hold G*B narratives, mask / klen are shared), drops[g] = the
 // dropout stream of group g (pair indices local to the group)
 int mt_attn_tc_fwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop, cudaStream_t st,
-                       const int* klen = nullptr, int G = 1, const DropCfg* drops = nullptr);
+                       const int* klen = nullptr, int G = 1, const DropCfg* drops = nullptr, const uint32_t* dbits = nullptr);
+// keep bits of the probability dropout of one launch (G * B * h * 512 words), drawn once and read by both the forward and the backward kernel
+size_t mt_attn_tc_dropbits_words(int G, int B, int h);
+int mt_attn_tc_dropbits_run(int G, int B, int T, int h, const DropCfg* drops, uint32_t* bits, cudaStream_t st);
 // aux: fp32 workspace of mt_attn_bwd_ws_floats(B, T, h) floats (per-query scalars); dbias as in mt_attn_mma_bwd_run (h <= 8)
 // G > 1 as in mt_attn_tc_fwd_run; aux holds G * mt_attn_bwd_ws_floats(B, T, h) floats, dbias of group g at dbias + g * dbias_gstride
 int mt_attn_tc_bwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse, const void* dout,
                        void* dqkv, DropCfg drop, float* dbias, float* aux, cudaStream_t st, int G = 1, const DropCfg* drops = nullptr,
-                       size_t dbias_gstride = 0, bool d_ready = false);      // d_ready: aux row 1 (D) was written by the caller
+                       size_t dbias_gstride = 0, bool d_ready = false, const uint32_t* dbits = nullptr);      // d_ready: aux row 1 (D) was written by the caller
 // ---- tcgen05 / TMEM flash attention for long sequences, 64-wide heads (mt_attention_flash.cu), bf16 ------------------------
 bool mt_attn_flash_supported(int B, int T, int d, int h);
 int mt_attn_flash_fwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop, cudaStream_t st);
@@ -97,10 +100,10 @@ int mt_attn_bwd_run(int dtype, int B, int T, int d, int h, const void* qkv, cons
 // G modality stacks back to back (B narratives each; mask / klen shared; drops[g] = stack g's dropout stream; Dws: G * mt_attn_bwd_ws_floats;
 // dbias of stack g at dbias + g * dbias_gstride): one launch on the tcgen05 engine, one call per stack on the other engines
 int mt_attn_group_fwd_run(int dtype, int G, int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse,
-                          const DropCfg* drops, cudaStream_t st, const int* klen = nullptr);
+                          const DropCfg* drops, cudaStream_t st, const int* klen = nullptr, const uint32_t* dbits = nullptr);
 int mt_attn_group_bwd_run(int dtype, int G, int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse,
                           const void* dout, void* dqkv, const DropCfg* drops, float* Dws, cudaStream_t st, float* dbias, size_t dbias_gstride,
-                          bool d_ready = false);
+                          bool d_ready = false, const uint32_t* dbits = nullptr);
 // true when mt_attn_group_bwd_run will take the tcgen05 engine for these arguments (then the caller may pre-fill D = rowsum(dout . out)
 // into Dws[((b * h + head) * 4 + 1) * 128 + q] and pass d_ready)
 bool mt_attn_group_bwd_uses_tc(int dtype, int G, int B, int T, int d, int h, const void* qkv, const void* out, const void* dout,

@@ -1,5 +1,5 @@
 """Per-kernel times of the four MFN recurrence kernels (bf16 mode) through the library's per-launch profiler, optionally under the
-timing-experiment switches of mt_tune key 7 (bit 0: no gate stash, 1: no per-step state stores, 2: no input feed, 3: no mma).
+timing-experiment switches of mt_tune key 8 (bit 0: no gate stash, 1: no per-step state stores, 2: no input feed, 3: no mma).
     python tools/mfn_rec_probe.py [B] [T] [dbg,dbg,...]"""
 import ctypes
 import os
@@ -27,7 +27,7 @@ def step():
 
 
 for dbg in dbgs:
-    L.mt_tune(7, dbg)
+    L.mt_tune(8, dbg)
     for _ in range(2):
         step()
     torch.cuda.synchronize()
@@ -49,12 +49,12 @@ for dbg in dbgs:
     tot = sum(agg.values())
     print(f'dbg {dbg:2d}  B={B} T={T}: ' + '  '.join(f'{k} {v * 1e3:7.1f} us ({v * 1e3 / T:5.2f}/step)' for k, v in sorted(rec.items()))
           + f'   all MFN launches {tot:.3f} ms', flush=True)
-L.mt_tune(7, 0)
+L.mt_tune(8, 0)
 if os.environ.get('MT_REC_TRACE'):
     import numpy as np
-    L.mt_tune(7, 32 | int(os.environ['MT_REC_TRACE']))
+    L.mt_tune(8, 32 | int(os.environ['MT_REC_TRACE']))
     step(); torch.cuda.synchronize()
-    L.mt_tune(7, 0)
+    L.mt_tune(8, 0)
     buf = np.zeros((4, 128, 8), dtype=np.uint64)
     fn = ctypes.CDLL(_lib.LIB_PATH).mt_mfn_rec_trace
     fn.argtypes = [ctypes.c_void_p]; fn.restype = ctypes.c_int
