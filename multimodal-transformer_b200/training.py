@@ -96,7 +96,10 @@ class FlatAdam:
         self.misc = None
         self._comm_tried, self._comm_handle = False, None
         self.last_overlap_ranges = 0
-        self.overlap = os.environ.get('MT_AR_OVERLAP', '1') != '0'      # overlap the all-reduce of the upper encoder layers with the rest of the backward (prepare_backward)
+        # opt-in (MT_AR_OVERLAP=1): all-reduce the upper encoder layers under the rest of the backward (prepare_backward).  Measured on 2 and 4
+        # B200s it does not pay: 6.70 vs 6.66 ms and 6.57 vs 6.53 ms per step -- the step's kernels are persistent and sized to every SM, so
+        # the NCCL kernel that runs under them takes as much from the backward as it saves after it (31 MB cost 0.17 ms un-overlapped)
+        self.overlap = os.environ.get('MT_AR_OVERLAP', '0') == '1'
         self.param_groups = [dict(lr=lr)]      # ReduceLROnPlateau-style schedulers poke this
 
     def _all_arenas(self):

@@ -17,6 +17,7 @@ def test_sharded_gradients_equal_full_batch_on_real_gpus():
         pytest.skip(f'needs >= 2 GPUs, have {n}')
     world = 2 if n < 4 else 4
     env = dict(os.environ)
+    env['MT_AR_OVERLAP'] = '1'      # the overlapped all-reduce is opt-in: cover it here
     for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK'):
         env.pop(k, None)
     out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={world}', '--master-addr', '127.0.0.1',
