@@ -282,9 +282,14 @@ int encoder_fwd_impl(const MtEncoderCfg& c, const Groups& gr, const float* param
       if (bits) MT_TRY(mt_attn_tc_dropbits_run(G, c.B, c.T, c.h, ad, b.dbits, st));
       MT_TRY(mt_attn_group_fwd_run(c.dtype, G, c.B, c.T, d, c.h, b.qkv, mask, b.att, b.lse, ad, st, c.key_len, bits));
     }
-    MT_TRY(pj.run(false, d, d, b.att, base + P.w_o, b.xp, true, (long long)(base + P.b_o), MT_ACT_NONE, l, MT_SITE_SUB0, nullptr, 1.f, xin, -1));
+    // mt_tune(11, 1): ... with the sublayer-1 LayerNorm in its epilogue (the two 128-column slices of a row tile are a CTA pair that exchanges
+    // the row moments through distributed shared memory, mt_gemm_rs.cu R_LNX).  Opt-in: measured 78.7 us per three stacks against 49.7 + 32
+    // for projection + LayerNorm pass -- the per-tile exchange and the second sweep sit on the epilogue, which already paces this kernel.
+    const bool ln2_fused = lp && !g_mt_tune[MT_TUNE_NO_LNFUSE] && g_mt_tune[MT_TUNE_LNX];
+    MT_TRY(pj.run(false, d, d, b.att, base + P.w_o, b.xp, true, (long long)(base + P.b_o), MT_ACT_NONE, l, MT_SITE_SUB0, nullptr, 1.f, xin, -1,
+                  ln2_fused ? b.v : nullptr, base + P.ln2_a, base + P.ln2_b));
     // sublayer 1: x + dropout(w_2(dropout(relu(w_1(LN(x))))))
-    MT_TRY(mt_ln_fwd_run(M, d, b.xp, params + base + P.ln2_a, params + base + P.ln2_b, 1e-6f, b.v, lp, st, G, gr.pstride));
+    if (!ln2_fused) MT_TRY(mt_ln_fwd_run(M, d, b.xp, params + base + P.ln2_a, params + base + P.ln2_b, 1e-6f, b.v, lp, st, G, gr.pstride));
     MT_TRY(pj.run(false, dff, d, b.v, base + P.w_1, b.hid, !lp, (long long)(base + P.b_1), MT_ACT_RELU, l, MT_SITE_FFN_H, nullptr, 1.f, nullptr, -1));
     void* ln_out = nullptr;
     size_t la = 0, lb = 0;

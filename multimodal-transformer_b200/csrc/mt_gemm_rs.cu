@@ -26,6 +26,39 @@ namespace {
 
 using namespace tc5;
 
+// ---- thread-block-cluster helpers of the LayerNorm that spans a CTA pair (R_LNX) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f2(uint32_t raddr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(raddr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t rbar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > SPIN_LIMIT) __trap();
+  }
+}
+
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int BOX = BM * 128;            // every staged box is [128 rows x 128 bytes] = 16 KB
@@ -34,7 +67,7 @@ constexpr int EPI_THREADS = 128;         // per epilogue warp group
 constexpr int MAXG = MT_RS_MAX_GROUPS;
 constexpr int SMEM_LIMIT = 227 * 1024;
 
-enum : uint32_t { R_BIAS = 1u, R_RELU = 2u, R_DROP = 4u, R_GATE = 8u, R_RES = 16u, R_CF32 = 32u, R_COLSUM = 64u, R_LN = 128u, R_ATTD = 256u };
+enum : uint32_t { R_BIAS = 1u, R_RELU = 2u, R_DROP = 4u, R_GATE = 8u, R_RES = 16u, R_CF32 = 32u, R_COLSUM = 64u, R_LN = 128u, R_ATTD = 256u, R_LNX = 512u };
 
 struct RsMaps {
   CUtensorMap a, c, r, g, ln;
@@ -56,7 +89,7 @@ struct RsArgs {
 template <int BN, int KB, uint32_t F>
 struct Cfg {
   static constexpr int W_BYTES = KB * BN * 128;
-  static constexpr int AUX_BYTES = 1024 + 4 * BN * 4 + 4096;      // barriers | bias | column sums | LayerNorm a_2, b_2 | row moments
+  static constexpr int AUX_BYTES = 1024 + 4 * BN * 4 + 4096 + 2048;   // barriers | bias | column sums | LayerNorm a_2, b_2 | row moments | the peer CTA's moments (R_LNX)
   static constexpr int BOXES = (SMEM_LIMIT - 1024 - AUX_BYTES - W_BYTES) / BOX;      // 16 KB boxes left beside the resident weights
   static constexpr bool TIGHT = BOXES < 8;                        // the 96 / 128 KB weight slices
   static constexpr int NSO = (TIGHT || (F & (R_RES | R_GATE | R_ATTD))) ? 1 : 2;   // output staging boxes PER epilogue warp group
@@ -99,6 +132,8 @@ __global__ void __launch_bounds__(NT, 1) gemm_rs_kernel(const __grid_constant__ 
   float* lna_s = cs_s + BN;
   float* lnb_s = lna_s + BN;
   float2* mom_s = reinterpret_cast<float2*>(lnb_s + BN);      // [tile parity][warp group][row] (mean, M2) of a row's column half
+  float2* mom_x = mom_s + 2 * 2 * BM;                         // R_LNX: [tile parity][row] (mean, M2) of the PEER CTA's BN columns, written by the peer
+  uint64_t* x_full = bars + 44;                               // [2] R_LNX: the peer's moments of this tile parity have arrived (128 remote arrivals)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // this CTA's (group, column slice) pair and its share of the group's row tiles
@@ -114,12 +149,14 @@ __global__ void __launch_bounds__(NT, 1) gemm_rs_kernel(const __grid_constant__ 
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
     mbar_init(w_full, 1);
     for (int s = 0; s < 4; ++s) { mbar_init(&full_r[s], 1); mbar_init(&empty_r[s], 4); mbar_init(&full_g[s], 1); mbar_init(&empty_g[s], 4); }
+    if (F & R_LNX) { mbar_init(&x_full[0], EPI_THREADS); mbar_init(&x_full[1], EPI_THREADS); }
     mbar_init_fence();
   }
   if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
   fence_before();
   __syncthreads();
   fence_after();
+  if (F & R_LNX) cluster_sync_all();      // the peer's barriers exist before anything is sent to them
   const uint32_t tmem_base = *tmem_slot;
   asm volatile("griddepcontrol.wait;" ::: "memory");
   // (the producer / MMA warps start at once; bias, column-sum and LayerNorm-gain staging is the epilogue warps' own business, below)
@@ -394,8 +431,24 @@ __global__ void __launch_bounds__(NT, 1) gemm_rs_kernel(const __grid_constant__ 
         bar_sync(3, 2 * EPI_THREADS);
         const float2 other = mom[(wg ^ 1) * BM + row];
         const float dm = m_w - other.x;
-        const float mean = 0.5f * (m_w + other.x);
-        const float var = (M2_w + other.y + dm * dm * (half_n * 0.5f)) * (1.0f / (float)(BN - 1));
+        float mean = 0.5f * (m_w + other.x);
+        float M2 = M2_w + other.y + dm * dm * (half_n * 0.5f);
+        float var = M2 * (1.0f / (float)(BN - 1));
+        if (F & R_LNX) {
+          // the row continues in the peer CTA of the pair (the other 128-column slice of the same row tile): exchange (mean, M2) of the
+          // BN columns through distributed shared memory -- warp group 0 writes into the peer's mom_x and arrives on the peer's barrier
+          const uint32_t peer = cluster_ctarank() ^ 1u;
+          if (wg == 0) {
+            st_cluster_f2(mapa_u32(smem_u32(&mom_x[(it & 1) * BM + row]), peer), mean, M2);
+            mbar_arrive_cluster(mapa_u32(smem_u32(&x_full[it & 1]), peer));
+          }
+          mbar_wait_cluster(&x_full[it & 1], (uint32_t)(it >> 1) & 1u);
+          const float2 px = mom_x[(it & 1) * BM + row];
+          const float dx = mean - px.x;
+          M2 = M2 + px.y + dx * dx * ((float)BN * 0.5f);
+          mean = 0.5f * (mean + px.x);
+          var = M2 * (1.0f / (float)(2 * BN - 1));
+        }
         const float inv = 1.0f / (sqrtf(var) + g.ln_eps);
 #pragma unroll 1
         for (int pr = wg; pr < C::PAIRS; pr += 2) {
@@ -440,6 +493,7 @@ __global__ void __launch_bounds__(NT, 1) gemm_rs_kernel(const __grid_constant__ 
   }
   fence_before();
   __syncthreads();
+  if (F & R_LNX) cluster_sync_all();      // neither CTA of the pair leaves while the other may still write into its shared memory
   if (F & R_COLSUM) {
     for (int i = threadIdx.x; i < BN; i += NT) atomicAdd(g.colsum[grp] + n0 + i, cs_s[i]);
   }
@@ -495,10 +549,16 @@ int launch(const RsDesc& d, cudaStream_t st) {
   if (once.first()) MT_CUDA(cudaFuncSetAttribute(gemm_rs_kernel<BN, KB, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(cnt * P)); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = C::TOTAL; cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = g_mt_tune[MT_TUNE_PDL] ? 1 : 0;
   cfg.attrs = at; cfg.numAttrs = 1;
+  if (F & R_LNX) {      // the two column slices of a row tile are adjacent CTAs: one cluster
+    if (g.tiles_n != 2) return MT_ERR_UNSUPPORTED;
+    at[1].id = cudaLaunchAttributeClusterDimension;
+    at[1].val.clusterDim.x = 2; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  }
   MT_CUDA(cudaLaunchKernelEx(&cfg, gemm_rs_kernel<BN, KB, F>, maps, g));
   MT_LAUNCH_CHECK();
   return MT_OK;
@@ -513,7 +573,7 @@ uint32_t features(const RsDesc& d) {
   if (d.residual) f |= R_RES;
   if (d.c_f32) f |= R_CF32;
   if (d.colsum[0]) f |= R_COLSUM;
-  if (d.ln_out) f |= R_LN;
+  if (d.ln_out) f |= (d.N == 256 && d.K == 256) ? (R_LN | R_LNX) : R_LN;      // K = 256: two 128-column slices, the LayerNorm spans the CTA pair
   if (d.attd_aux) f |= R_ATTD;
   return f;
 }
@@ -529,6 +589,8 @@ int dispatch(const RsDesc& d, cudaStream_t st, bool probe_only) {
   RS_PROBE(768, 256, 256, R_BIAS);                                         // QKV projection
   RS_PROBE(256, 256, 128, R_BIAS | R_DROP | R_RES | R_CF32);               // output projection, train
   RS_PROBE(256, 256, 128, R_BIAS | R_RES | R_CF32);                        // output projection, eval
+  RS_PROBE(256, 256, 128, R_BIAS | R_DROP | R_RES | R_CF32 | R_LN | R_LNX);   // output projection + LayerNorm 2 across a CTA pair, train
+  RS_PROBE(256, 256, 128, R_BIAS | R_RES | R_CF32 | R_LN | R_LNX);            // ... eval
   RS_PROBE(128, 256, 128, R_BIAS | R_RELU | R_DROP);                       // FFN w_1, train
   RS_PROBE(128, 256, 128, R_BIAS | R_RELU);                                // FFN w_1, eval
   RS_PROBE(256, 128, 256, R_BIAS | R_DROP | R_RES | R_CF32);               // FFN w_2, train

@@ -85,6 +85,9 @@ BWD = [
 LN = [
     (256, 128, dict(bias=True, c_f32=1, res=True, ln=True)),
     (256, 128, dict(bias=True, c_f32=1, res=True, ln=True, p=0.1)),
+    # output projection + LayerNorm: two 128-column slices per row tile, the row moments cross the CTA pair through distributed shared memory
+    (256, 256, dict(bias=True, c_f32=1, res=True, ln=True)),
+    (256, 256, dict(bias=True, c_f32=1, res=True, ln=True, p=0.1)),
 ]
 
 
@@ -112,6 +115,7 @@ def test_rs_two_groups_one_tile():
 def test_rs_layernorm_offset_rows():
     """Rows with a mean far from zero relative to their spread: the shifted single-pass moments must not cancel."""
     _run(1, 256, 256, 128, bias=True, c_f32=1, res=True, ln=True, scale=0.01, res_off=30.0, res_scale=0.5)
+    _run(1, 256, 256, 256, bias=True, c_f32=1, res=True, ln=True, scale=0.01, res_off=30.0, res_scale=0.5)
 
 
 def test_rs_rejects_unsupported():
