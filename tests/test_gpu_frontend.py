@@ -451,7 +451,10 @@ def test_graphed_train_step_with_window_front_end(mode):
         for k, p in model_g.named_parameters():
             if k.startswith(('Transformer.attn', 'Transformer.ff')):
                 continue
-            assert_close(p, pe[k], 2e-4, k, 1e-6)
+            # fp32 split-K weight gradients are summed with atomics (order varies between the eager and the captured run); Adam's g / sqrt(v)
+            # turns a sign flip of a round-off-level gradient into a +-lr step, so the floor is a small fraction of what three steps at
+            # lr 1e-3 can move a weight (seen: 4.4e-5 on highway_acoustic.linear_projection.weight in 1 of 4 runs)
+            assert_close(p, pe[k], 2e-4, k, 2e-4)
 
 
 def test_batch_into_static_buffers_equals_batch():
