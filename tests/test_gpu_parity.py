@@ -946,6 +946,8 @@ def test_prefetch_path_follows_lr_changes():
     direct, pre, pre_const = run(False, True), run(True, True), run(True, False)
     moved = 0.0
     for k in direct:
-        assert_close(pre[k], direct[k], 1e-4, k, 2e-4)      # Adam turns round-off of analytically-zero gradients (key bias) into +-lr steps
+        # Adam turns round-off of analytically-zero gradients (key bias) into +-lr steps, and the atomically summed weight gradients differ in
+        # their last bits from run to run: the floor is a fraction of one lr = 1e-2 step (a missed lr change moves active weights by ~1e-2)
+        assert_close(pre[k], direct[k], 1e-4, k, 2e-3)
         moved = max(moved, (pre[k] - pre_const[k]).abs().max().item())
     assert moved > 1e-4          # the halved lr really changed the trajectory
