@@ -951,3 +951,73 @@ def test_prefetch_path_follows_lr_changes():
         assert_close(pre[k], direct[k], 1e-4, k, 2e-3)
         moved = max(moved, (pre[k] - pre_const[k]).abs().max().item())
     assert moved > 1e-4          # the halved lr really changed the trajectory
+
+
+def _mft_bf16_train_step(tune=None, B=9, T=128, N=2, seed=123):
+    """One bf16 train-mode forward + backward of MultiTransformer (grouped stacks, tcgen05 attention, tensor-core recurrences) under the
+    given mt_tune settings; returns (prediction, gradients)."""
+    L = _lib.lib()
+    dims = {'acoustic': 88, 'image': 256, 'linguistic': 300}
+    sd = util.filled_sd(util.mods_shapes('MFT.MultiTransformer', N), 21)
+    inputs, mask, target, lengths = fill.make_batch(B, T, dims, 17)
+    old = {k: L.mt_tune(k, v) for k, v in (tune or {}).items()}
+    mtb.set_compute_dtype('bf16')
+    try:
+        model = mtb.MultiTransformer(MODS, dims, N=N).to(DEV); model.load_state_dict(sd); model.train()
+        mtb.fix_seed(seed)
+        pred = model({k: t(v).to(DEV) for k, v in inputs.items()}, t(mask).to(DEV), lengths)
+        (((pred - t(target).to(DEV)) ** 2).sum() / sum(lengths)).backward()
+        torch.cuda.synchronize()
+        return pred.detach().float().cpu(), {k: p.grad.detach().float().cpu() for k, p in model.named_parameters() if p.grad is not None}
+    finally:
+        mtb.set_compute_dtype('fp32')
+        for k, v in old.items():
+            L.mt_tune(k, v)
+
+
+def test_attention_keep_bits_reproduce_the_in_kernel_hash():
+    """The dropout keep bits drawn once per step and layer (attn_tc_dropbits_kernel) are exactly the draws the tcgen05 attention kernels
+    make themselves (mt_tune key 9): identical predictions, gradients equal up to the order of their atomic bias-gradient sums."""
+    p_bits, g_bits = _mft_bf16_train_step()
+    p_hash, g_hash = _mft_bf16_train_step({9: 1})
+    assert torch.equal(p_bits, p_hash)
+    for k in g_bits:
+        assert_close(g_bits[k], g_hash[k], 1e-5, k, 1e-9)
+
+
+def test_grouped_qkv_input_gradient_equals_per_stack_launches():
+    """GemmDesc.mgroups: the long-K input gradient of the QKV projection as one streaming launch over the stacked rows (per-tile weight
+    map) against one launch per stack (mt_tune key 10)."""
+    p_grp, g_grp = _mft_bf16_train_step()
+    p_per, g_per = _mft_bf16_train_step({10: 1})
+    assert torch.equal(p_grp, p_per)
+    for k in g_grp:
+        assert_close(g_grp[k], g_per[k], 1e-5, k, 1e-9)
+
+
+def test_second_cut_recurrences_match_the_first_cut():
+    """mt_tune key 8, bit 6 selects the first-cut MFN recurrence kernels: same stash layouts, same math except the sigmoid (tanh unit vs
+    ex2 + rcp, ~3e-4 absolute), so predictions and gradients agree far inside the bf16 budget."""
+    p2, g2 = _mft_bf16_train_step()
+    p1, g1 = _mft_bf16_train_step({8: 64})
+    assert (p2 - p1).abs().max().item() < 5e-3
+    gmax = max(v.abs().max().item() for v in g1.values())
+    for k in g2:
+        if g1[k].abs().max().item() < 1e-3 * gmax:      # analytically zero (key-projection bias): round-off on both sides
+            continue
+        cos = torch.nn.functional.cosine_similarity(g2[k].flatten(), g1[k].flatten(), dim=0).item()
+        assert cos > 0.995, (k, cos)
+
+
+def test_layernorm_across_a_cta_pair_in_the_model():
+    """mt_tune key 11: the output projection fuses the sublayer-1 LayerNorm across a 2-CTA cluster (row moments through distributed shared
+    memory); same model step as the separate LayerNorm pass up to bf16 rounding of the normalised operand."""
+    p0, g0 = _mft_bf16_train_step()
+    p1, g1 = _mft_bf16_train_step({11: 1})
+    assert (p0 - p1).abs().max().item() < 5e-3
+    gmax = max(v.abs().max().item() for v in g0.values())
+    for k in g0:
+        if g0[k].abs().max().item() < 1e-3 * gmax:
+            continue
+        cos = torch.nn.functional.cosine_similarity(g0[k].flatten(), g1[k].flatten(), dim=0).item()
+        assert cos > 0.995, (k, cos)
