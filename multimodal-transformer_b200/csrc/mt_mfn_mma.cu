@@ -807,7 +807,7 @@ __global__ void __launch_bounds__(NTH2, 1) lstm_fwd_mma2_kernel(const __grid_con
     return;
   }
   // ---- compute warps: the loop is instantiated per (tiles of this warp, k-steps) ----
-  const bool trace = (a.dbg & 32) && blockIdx.x == 0 && m == a.n_mods - 1 && lane == 0;
+  const bool trace = (a.dbg & 32) && !(a.dbg & 16) && blockIdx.x == 0 && m == a.n_mods - 1 && lane == 0;
   const int nt = (H / 4 - warp + NW - 1) / NW;       // 16-row tiles 4 * (warp + 8 i) < H
 #define LSTM2_GO(NT_, KS_) lstm_fwd2_compute<TRAIN, NT_, KS_>(a, m, hS, stages, stag, SBY, FST, GST, CST, SLOT, full, empty, trace)
   if (H <= 48) {
@@ -1153,6 +1153,7 @@ __global__ void __launch_bounds__(NTH2, 1) mem_fwd_mma2_kernel(const __grid_cons
     for (int t = 0; t < a.T; ++t) {
       const int slot = t & 1, r1 = r0 == HRING - 1 ? 0 : r0 + 1;
       nb_sync(2 + slot, NSYNC2);
+      if (a.dbg & 2) { if (t + 2 < a.T) nb_arrive(4 + slot, NSYNC2); r0 = r1; continue; }
       uint4 vg[6], vh[2], vp[2], vl[2];
 #pragma unroll
       for (int j = 0; j < 6; ++j) if (jgm.dst[j] >= 0) vg[j] = lds16(gm_s + slot * NB * GMS + jgm.src[j]);
@@ -1207,9 +1208,11 @@ __global__ void __launch_bounds__(NTH2, 1) mem_fwd_mma2_kernel(const __grid_cons
   const uint32_t mem_s = mtrec::s_u32(&memS[0][0]) + lm_off, gh_s = mtrec::s_u32(&ghS[0][0]) + lm_off;
   float mem[4] = {0.f, 0.f, 0.f, 0.f};
   int r0 = 0;
+  const bool trace = (a.dbg & 32) && (a.dbg & 16) && blockIdx.x == 0 && lane == 0;
   mtrec::sbar_wait(&full[0], 0u);
   for (int t = 0; t < a.T; ++t) {
     const int slot = t & 1, r1 = r0 == HRING - 1 ? 0 : r0 + 1;
+    REC_STAMP2(t, 0, 0.f);
     const char* sg = stages + (t % FD) * STAGE;
     float acc[2][4], df[4], ch[4];
 #pragma unroll
@@ -1219,6 +1222,7 @@ __global__ void __launch_bounds__(NTH2, 1) mem_fwd_mma2_kernel(const __grid_cons
       // element index of the gate's [T,B,G] tensor (oracle/mt_oracle.py:_drop_t)
       df[v] = mt_drop_factor(drop, ((uint64_t)t * a.B + (uint64_t)(b0 + 2 * q + (v & 1))) * (uint64_t)G + (uint64_t)jg[v >> 1]);
     }
+    REC_STAMP2(t, 1, df[0] + df[3] + acc[0][0]);
     consumers_sync();                                // mem_{t-1} of every warp is in ring slot r0
     // ---- layer 1: gh = drop(relu(gpre_t + Wm mem_{t-1})) ----
 #pragma unroll
@@ -1228,12 +1232,15 @@ __global__ void __launch_bounds__(NTH2, 1) mem_fwd_mma2_kernel(const __grid_cons
       mma16816(acc[0], A1[2 * kp], b[0], b[1]);
       mma16816(acc[1], A1[2 * kp + 1], b[2], b[3]);
     }
+    REC_STAMP2(t, 2, 0.f);
     release_slot(&empty[t % FD], lane);
     if (t + 1 < a.T) mtrec::sbar_wait(&full[(t + 1) % FD], (uint32_t)((t + 1) / FD) & 1u);      // long complete: overlaps the mma
     if (t >= 2) nb_sync(4 + slot, NSYNC2);           // the storers are done with this staging slot and with ring slot r1
+    REC_STAMP2(t, 3, acc[0][0] + acc[1][0]);
     char* gho = reinterpret_cast<char*>(ghS[slot]);
 #pragma unroll
     for (int v = 0; v < 4; ++v) *reinterpret_cast<bf16*>(gho + ob[v]) = __float2bfloat16(fmaxf(acc[0][v] + acc[1][v], 0.f) * df[v]);
+    REC_STAMP2(t, 4, 0.f);
     consumers_sync();
     // ---- layer 2: gamma1 from hidden[0:64), gamma2 from hidden[64:128) ----
     float c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
@@ -1245,6 +1252,7 @@ __global__ void __launch_bounds__(NTH2, 1) mem_fwd_mma2_kernel(const __grid_cons
       mma16816(c1, A2a[2 * kp], x[0], x[1]); mma16816(c2, A2b[2 * kp], y[0], y[1]);
       mma16816(c1, A2a[2 * kp + 1], x[2], x[3]); mma16816(c2, A2b[2 * kp + 1], y[2], y[3]);
     }
+    REC_STAMP2(t, 5, c1[0] + c2[0]);
     char* mo = reinterpret_cast<char*>(memS[r1]);
     char* go = reinterpret_cast<char*>(gmS[slot]);
 #pragma unroll
@@ -1254,7 +1262,9 @@ __global__ void __launch_bounds__(NTH2, 1) mem_fwd_mma2_kernel(const __grid_cons
       *reinterpret_cast<bf16*>(mo + ob[v]) = __float2bfloat16(mem[v]);
       if (TRAIN) { *reinterpret_cast<float*>(go + og[v]) = g1; *reinterpret_cast<float*>(go + og[v] + MEM * 4) = g2; }
     }
+    REC_STAMP2(t, 6, mem[0]);
     nb_arrive(2 + slot, NSYNC2);                     // staged: the storers take step t from here
+    REC_STAMP2(t, 7, 0.f);
     r0 = r1;
   }
   if (a.mem_last) {
