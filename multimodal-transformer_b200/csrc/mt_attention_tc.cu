@@ -642,7 +642,8 @@ template <bool FULL, bool BITS>
 __global__ void __launch_bounds__(BWD_NT, 1)
 attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do, const __grid_constant__ BwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ float s_cs[4 * 2 * 96];                  // [head pair][w][dQ | dK | dV][32]: bias-gradient column sums of this CTA
+  __shared__ float s_cs[4 * 4 * 2 * 96];              // [warp & 3][head pair][w][dQ | dK | dV][32]: bias-gradient column sums of this CTA, one slice per
+                                                      // row quarter so that every address has ONE writing warp (plain adds, no CAS loops)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stage_base = smem;
   uint8_t* ds_smem = smem + BWD_STAGES * BWD_STAGE_BYTES;      // two dS^T buffers (block parity)
@@ -661,7 +662,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int hp_count = a.h >> 1;
   const int T = a.T;
-  for (int i = threadIdx.x; i < 4 * 2 * 96; i += BWD_NT) s_cs[i] = 0.f;
+  for (int i = threadIdx.x; i < 4 * 4 * 2 * 96; i += BWD_NT) s_cs[i] = 0.f;
   if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&map_qkv);
     tma_prefetch_desc(&map_do);
@@ -775,26 +776,23 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
       for (int i = 0; i < 8; ++i) { v[i] = __uint_as_float(rq[i]); v[8 + i] = __uint_as_float(rk[i]); }
 #pragma unroll
       for (int i = 0; i < 8; i += 2) upk2(mul2(pk2(__uint_as_float(rv[i]), __uint_as_float(rv[i + 1])), ds2), v[16 + i], v[17 + i]);      // dV still lacks the keep scale
-      if (key_ok) {           // row j is query j of dQ and key j of dK / dV; rows beyond T are exact zeros
-        bf16* gp = a.dqkv + ((size_t)b * T + j) * (3 * a.d) + hd * HD + g * 8;
+      // pack first, reduce, store LAST: the 16-byte stores of a warp go to 32 different rows and drain slowly, and whatever overwrites
+      // their source registers waits for them -- behind the butterfly nothing does until the next block's TMEM loads
+      uint4 u[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          uint4 u;
-          u.x = pack_bf2(v[8 * k], v[8 * k + 1]); u.y = pack_bf2(v[8 * k + 2], v[8 * k + 3]);
-          u.z = pack_bf2(v[8 * k + 4], v[8 * k + 5]); u.w = pack_bf2(v[8 * k + 6], v[8 * k + 7]);
-          __stcs(reinterpret_cast<uint4*>(gp + (size_t)k * a.d), u);
-        }
+      for (int k = 0; k < 3; ++k) {
+        u[k].x = pack_bf2(v[8 * k], v[8 * k + 1]); u[k].y = pack_bf2(v[8 * k + 2], v[8 * k + 3]);
+        u[k].z = pack_bf2(v[8 * k + 4], v[8 * k + 5]); u[k].w = pack_bf2(v[8 * k + 6], v[8 * k + 7]);
       }
       if (a.dbias != nullptr) {
         // column sums over the warp's 32 rows: a butterfly that halves the number of live columns per lane at every step
-        int ln;
-        asm volatile("mov.u32 %0, %%laneid;" : "=r"(ln));
+        // (lane = j & 31: reading %laneid costs an S2R round trip per block)
         int col = 0;
 #pragma unroll
         for (int step = 0; step < 3; ++step) {
           const int n2 = 12 >> step;                // 12, 6, 3
           const int m = 16 >> step;
-          const bool up = (ln & m) != 0;
+          const bool up = (j & m) != 0;
 #pragma unroll
           for (int i = 0; i < n2; ++i) {
             const float send = up ? v[i] : v[i + n2], keep = up ? v[i + n2] : v[i];
@@ -807,14 +805,19 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
           v[i] += __shfl_xor_sync(0xffffffffu, v[i], 2);
           v[i] += __shfl_xor_sync(0xffffffffu, v[i], 1);
         }
-        if ((ln & 3) == 0) {
-          float* cs = s_cs + ((hp & 3) * 2 + w) * 96;
+        if ((j & 3) == 0) {
+          float* cs = s_cs + (((warp & 3) * 4 + (hp & 3)) * 2 + w) * 96;      // this warp is the only writer of its columns in this slice
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
             const int cidx = col + i;      // 0..23: [dQ | dK | dV] x 8 columns of this warp group
-            atomicAdd(cs + (cidx >> 3) * 32 + g * 8 + (cidx & 7), v[i]);
+            cs[(cidx >> 3) * 32 + g * 8 + (cidx & 7)] += v[i];
           }
         }
+      }
+      if (key_ok) {           // row j is query j of dQ and key j of dK / dV; rows beyond T are exact zeros
+        bf16* gp = a.dqkv + ((size_t)b * T + j) * (3 * a.d) + hd * HD + g * 8;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) __stcs(reinterpret_cast<uint4*>(gp + (size_t)k * a.d), u[k]);
       }
     };
     for (int blk = 0; blk < n_blk; ++blk) {
@@ -855,7 +858,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
           upk2(fma2(pk2(__uint_as_float(dp[e]), __uint_as_float(dp[e + 1])), ds2, pk2(-D.x, -D.y)), t[0], t[1]);
           upk2(fma2(pk2(__uint_as_float(dp[e + 2]), __uint_as_float(dp[e + 3])), ds2, pk2(-D.z, -D.w)), t[2], t[3]);
           float pd[4] = {p[0], p[1], p[2], p[3]};
-          if (dropping) {
+          if (BITS || dropping) {           // keep bits exist only when the launch drops: no run-time branch around their loads
             if (BITS) {
               const uint4 kw = *reinterpret_cast<const uint4*>(kbits + q);
               const uint32_t kq[4] = {kw.x, kw.y, kw.z, kw.w};
@@ -913,7 +916,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
   if (a.dbias != nullptr) {
     for (int i = threadIdx.x; i < hp_count * 2 * 96; i += BWD_NT) {
       const int hp = i / 192, w = (i / 96) & 1, k = (i % 96) / 32, c = i % 32;
-      const float val = s_cs[i];
+      const float val = (s_cs[i] + s_cs[4 * 2 * 96 + i]) + (s_cs[2 * 4 * 2 * 96 + i] + s_cs[3 * 4 * 2 * 96 + i]);
       if (val != 0.f) atomicAdd(a.dbias + iw.grp * a.dbias_gstride + (size_t)k * a.d + (2 * hp + w) * HD + c, val);
     }
   }
@@ -1047,6 +1050,7 @@ int mt_attn_tc_bwd_run(int B, int T, int d, int h, const void* qkv, const float*
   a.B = B; a.T = T; a.d = d; a.h = h; a.G = G;
   a.aux = aux; a.dqkv = (bf16*)dqkv; a.dbias = dbias; a.dbias_gstride = dbias_gstride; a.dbits = dbits;
   for (int i = 0; i < MAXG; ++i) a.drop[i] = drops && i < G ? drops[i] : drop;
+  if (a.drop[0].thresh == 0u) { a.dbits = nullptr; dbits = nullptr; }      // keep bits mean something only when the launch drops
   static MtPerDeviceOnce attr_full, attr_part;
   const int sms = num_sms(), n_items = B * (h / 2);
   const int cpg = n_items < sms / G ? n_items : sms / G;
