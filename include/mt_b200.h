@@ -371,8 +371,9 @@ int mt_gemm_force_simt(int on);
 int mt_gemm_tc_mode(int mode);
 /* tuning knobs; returns the previous value (-1: bad key).  key 0 / 1 / 2 = grid share of the tcgen05 GEMM / the T <= 128 attention /
  * the LayerNorm kernels: a share s > 1 launches 1/s of the resident CTA slots, so kernels of concurrent streams (the modality stacks
- * of MultiTransformer) co-reside on the SMs instead of queueing behind each other.  key 3 = programmatic dependent launch of the tcgen05
- * GEMM (its prologue may overlap the tail of the previous kernel of the stream; default 0: measured gain 0.4 % inside the captured step).
+ * of MultiTransformer) co-reside on the SMs instead of queueing behind each other.  key 3 = programmatic dependent launch of the encoder
+ * chain (LayerNorm, tcgen05 GEMMs, tcgen05 attention, keep-bit draw: grid launch and prologue overlap the previous kernel's tail): 0 off,
+ * 1 = launches outside stream capture only (default; eager MFT step 7.27 -> 7.05 ms), 2 = always (a captured graph gets 1 % slower).
  * key 5 != 0: the encoder's projections skip the weight-resident row-stream engine (A/B against the streaming engine); key 6 != 0: no
  * LayerNorm fused into the FFN output projection's epilogue; key 7 != 0: no 256-row / 256-wide tiles for the L2-bound GEMMs; key 8: debug mask of the
  * MFN recurrence kernels (bit 6: the first-cut kernels, for A/B timing; bit 5: clock trace); key 9 != 0: the tcgen05 attention kernels hash

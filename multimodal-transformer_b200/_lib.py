@@ -139,6 +139,10 @@ def lib():
             f = getattr(L, name)          # AttributeError here means the header and the library disagree
             f.restype = res
             f.argtypes = args
+        # MT_B200_TUNE="key=value,..." presets mt_tune knobs for the whole process (A/B runs of the test suite, e.g. "3=0")
+        for kv in filter(None, os.environ.get('MT_B200_TUNE', '').split(',')):
+            k_, v_ = kv.split('=')
+            L.mt_tune(int(k_), int(v_))
         _lib = L
     return _lib
 

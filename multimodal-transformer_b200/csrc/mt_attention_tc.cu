@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(FWD_NT, 2) attn_tc_fwd_kernel(const __grid_con
   __syncthreads();
   fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  mt_pdl_gate();      // everything above touches no global memory
 
   if (warp == 8) {
     // ===== TMA producer: Q | K | V boxes of the item's head pair =====
@@ -334,6 +335,7 @@ __global__ void __launch_bounds__(256) attn_tc_prep_kernel(int B, int Bg, int T,
 // mt_gemm_rs.cu R_ATTD): one thread per (b, hd, q), q fastest -- 4 bytes read, 12 written per query
 __global__ void attn_tc_prep_light_kernel(int B, int Bg, int T, int h, const float* __restrict__ lse, const float* __restrict__ mask,
                                           float* __restrict__ aux, float scale) {
+  mt_pdl_gate();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * h * T) return;
   const int q = (int)(idx % T);
@@ -676,6 +678,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
   __syncthreads();
   fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  mt_pdl_gate();      // everything above touches no global memory
   const ItemWalk iw = item_walk(a.G, a.B, hp_count);
   const int n_my = iw.n;
 
@@ -927,6 +930,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
 // (pair index ((b_local h + hd) T + q) P2 + (j >> 1), low half -> even key).  One thread per word: 16 draws.
 struct BitsArgs { int B, T, h, G; DropCfg drop[MAXG]; };
 __global__ void __launch_bounds__(256) attn_tc_dropbits_kernel(const __grid_constant__ BitsArgs a, uint32_t* __restrict__ bits) {
+  mt_pdl_gate();
   const uint32_t per_group = (uint32_t)(a.B * a.h) * 512u;               // words of one group
   const uint32_t n = per_group * (uint32_t)a.G;
   const uint32_t P2 = (uint32_t)(a.T + 1) >> 1;
@@ -990,7 +994,7 @@ int mt_attn_tc_dropbits_run(int G, int B, int T, int h, const DropCfg* drops, ui
   const size_t n = mt_attn_tc_dropbits_words(G, B, h);
   mt_prof_work(0.0, (double)n * 4.0);
   const size_t cap = (size_t)num_sms() * 8;
-  attn_tc_dropbits_kernel<<<(unsigned)((n + 255) / 256 < cap ? (n + 255) / 256 : cap), 256, 0, st>>>(a, bits);
+  MT_CUDA(mt_launch_dep(attn_tc_dropbits_kernel, dim3((unsigned)((n + 255) / 256 < cap ? (n + 255) / 256 : cap)), dim3(256), 0, st, a, bits));
   MT_LAUNCH_CHECK();
   return MT_OK;
 }
@@ -1013,11 +1017,11 @@ int mt_attn_tc_fwd_run(int B, int T, int d, int h, const void* qkv, const float*
   mt_prof_work(4.0 * G * B * (double)T * T * d, (double)G * B * T * d * 4.0 * 2.0);
   static MtPerDeviceOnce attr_full_b, attr_part_b;
   if (T == TM && !klen) {
-    if (dbits) { MT_TRY(set_smem_attr(attn_tc_fwd_kernel<true, true>, FWD_SMEM, attr_full_b)); attn_tc_fwd_kernel<true, true><<<grid, FWD_NT, FWD_SMEM, st>>>(map, a); }
-    else { MT_TRY(set_smem_attr(attn_tc_fwd_kernel<true, false>, FWD_SMEM, attr_full)); attn_tc_fwd_kernel<true, false><<<grid, FWD_NT, FWD_SMEM, st>>>(map, a); }
+    if (dbits) { MT_TRY(set_smem_attr(attn_tc_fwd_kernel<true, true>, FWD_SMEM, attr_full_b)); MT_CUDA(mt_launch_dep(attn_tc_fwd_kernel<true, true>, dim3(grid), dim3(FWD_NT), FWD_SMEM, st, map, a)); }
+    else { MT_TRY(set_smem_attr(attn_tc_fwd_kernel<true, false>, FWD_SMEM, attr_full)); MT_CUDA(mt_launch_dep(attn_tc_fwd_kernel<true, false>, dim3(grid), dim3(FWD_NT), FWD_SMEM, st, map, a)); }
   } else {
-    if (dbits) { MT_TRY(set_smem_attr(attn_tc_fwd_kernel<false, true>, FWD_SMEM, attr_part_b)); attn_tc_fwd_kernel<false, true><<<grid, FWD_NT, FWD_SMEM, st>>>(map, a); }
-    else { MT_TRY(set_smem_attr(attn_tc_fwd_kernel<false, false>, FWD_SMEM, attr_part)); attn_tc_fwd_kernel<false, false><<<grid, FWD_NT, FWD_SMEM, st>>>(map, a); }
+    if (dbits) { MT_TRY(set_smem_attr(attn_tc_fwd_kernel<false, true>, FWD_SMEM, attr_part_b)); MT_CUDA(mt_launch_dep(attn_tc_fwd_kernel<false, true>, dim3(grid), dim3(FWD_NT), FWD_SMEM, st, map, a)); }
+    else { MT_TRY(set_smem_attr(attn_tc_fwd_kernel<false, false>, FWD_SMEM, attr_part)); MT_CUDA(mt_launch_dep(attn_tc_fwd_kernel<false, false>, dim3(grid), dim3(FWD_NT), FWD_SMEM, st, map, a)); }
   }
   MT_LAUNCH_CHECK();
   return MT_OK;
@@ -1033,7 +1037,7 @@ int mt_attn_tc_bwd_run(int B, int T, int d, int h, const void* qkv, const float*
   const float scale = 1.0f / sqrtf((float)HD);
   if (d_ready) {
     const long long n = (long long)G * B * h * T;
-    attn_tc_prep_light_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(G * B, B, T, h, lse, mask, aux, scale);
+    MT_CUDA(mt_launch_dep(attn_tc_prep_light_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, G * B, B, T, h, lse, mask, aux, scale));
     MT_LAUNCH_CHECK();
   } else {
     const long long rows = (long long)G * B * T;
@@ -1067,12 +1071,12 @@ int mt_attn_tc_bwd_run(int B, int T, int d, int h, const void* qkv, const float*
     }
   } else if (T == TM) {
     static MtPerDeviceOnce attr2_full_b;
-    if (dbits) { MT_TRY(set_smem_attr(attn_tc_bwd2_kernel<true, true>, BWD_SMEM, attr2_full_b)); attn_tc_bwd2_kernel<true, true><<<grid, BWD_NT, BWD_SMEM, st>>>(map_qkv, map_do, a); }
-    else { MT_TRY(set_smem_attr(attn_tc_bwd2_kernel<true, false>, BWD_SMEM, attr2_full)); attn_tc_bwd2_kernel<true, false><<<grid, BWD_NT, BWD_SMEM, st>>>(map_qkv, map_do, a); }
+    if (dbits) { MT_TRY(set_smem_attr(attn_tc_bwd2_kernel<true, true>, BWD_SMEM, attr2_full_b)); MT_CUDA(mt_launch_dep(attn_tc_bwd2_kernel<true, true>, dim3(grid), dim3(BWD_NT), BWD_SMEM, st, map_qkv, map_do, a)); }
+    else { MT_TRY(set_smem_attr(attn_tc_bwd2_kernel<true, false>, BWD_SMEM, attr2_full)); MT_CUDA(mt_launch_dep(attn_tc_bwd2_kernel<true, false>, dim3(grid), dim3(BWD_NT), BWD_SMEM, st, map_qkv, map_do, a)); }
   } else {
     static MtPerDeviceOnce attr2_part_b;
-    if (dbits) { MT_TRY(set_smem_attr(attn_tc_bwd2_kernel<false, true>, BWD_SMEM, attr2_part_b)); attn_tc_bwd2_kernel<false, true><<<grid, BWD_NT, BWD_SMEM, st>>>(map_qkv, map_do, a); }
-    else { MT_TRY(set_smem_attr(attn_tc_bwd2_kernel<false, false>, BWD_SMEM, attr2_part)); attn_tc_bwd2_kernel<false, false><<<grid, BWD_NT, BWD_SMEM, st>>>(map_qkv, map_do, a); }
+    if (dbits) { MT_TRY(set_smem_attr(attn_tc_bwd2_kernel<false, true>, BWD_SMEM, attr2_part_b)); MT_CUDA(mt_launch_dep(attn_tc_bwd2_kernel<false, true>, dim3(grid), dim3(BWD_NT), BWD_SMEM, st, map_qkv, map_do, a)); }
+    else { MT_TRY(set_smem_attr(attn_tc_bwd2_kernel<false, false>, BWD_SMEM, attr2_part)); MT_CUDA(mt_launch_dep(attn_tc_bwd2_kernel<false, false>, dim3(grid), dim3(BWD_NT), BWD_SMEM, st, map_qkv, map_do, a)); }
   }
   MT_LAUNCH_CHECK();
   return MT_OK;

@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(int M, const floa
                                                                const float* __restrict__ b, float eps, TY* __restrict__ y, size_t pstride) {
   constexpr int d = NCH * 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  mt_pdl_gate();
   // grouped launch (gridDim.y = modality stacks): group g owns rows [g*M, (g+1)*M) and the parameters at a + g*pstride
   x += (size_t)blockIdx.y * M * d; y += (size_t)blockIdx.y * M * d; a += blockIdx.y * pstride; b += blockIdx.y * pstride;
   float4 av[NCH], bv[NCH];
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(int M, const floa
                                                                size_t pstride) {
   constexpr int d = NCH * 128;
   __shared__ float s_da[d], s_db[d], s_dn[NEXT ? d : 1];
+  mt_pdl_gate();
   const DropCfg nx_drop = mt_drop_resolve(nx_drops.d[blockIdx.y]);
   {   // grouped launch: see ln_fwd_kernel; gradients of parameters are laid out like the parameters
     const size_t ro = (size_t)blockIdx.y * M * d, po = blockIdx.y * pstride;
@@ -262,6 +264,48 @@ __global__ void act_bwd_kernel(size_t n, int N, const TG* __restrict__ dy, const
   }
 }
 
+// The same gradient with the bias gradient fused in: db[n] += sum_m dz[m][n] (fp32 values, before dz is rounded), four columns per
+// thread, 8 row phases per CTA, four rows in flight per thread -- replaces an act_bwd pass + a column-sum pass over dz (N % 4 == 0).
+template <typename TG, typename TY, typename TZ>
+__global__ void __launch_bounds__(256) act_bwd_colsum_kernel(int M, int N, const TG* __restrict__ dy, const TY* __restrict__ y, int act,
+                                                             const float* __restrict__ rowmask, TZ* __restrict__ dz, float* __restrict__ db,
+                                                             int rows_per_block) {
+  __shared__ float4 red[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 128 + tx * 4;
+  const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto one = [&](int m, float4 g, float4 t) {
+    if (rowmask) { const float r = rowmask[m]; g.x *= r; g.y *= r; g.z *= r; g.w *= r; }
+    if (act == MT_ACT_RELU) { g.x = t.x > 0.f ? g.x : 0.f; g.y = t.y > 0.f ? g.y : 0.f; g.z = t.z > 0.f ? g.z : 0.f; g.w = t.w > 0.f ? g.w : 0.f; }
+    else if (act == MT_ACT_TANH) { g.x *= 1.0f - t.x * t.x; g.y *= 1.0f - t.y * t.y; g.z *= 1.0f - t.z * t.z; g.w *= 1.0f - t.w * t.w; }
+    st4(dz + (size_t)m * N + n, g);
+    s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
+  };
+  if (n < N) {
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    int m = m0 + ty;
+    for (; m + 24 < m1; m += 32) {
+      float4 g[4], t[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        g[k] = ld4(dy + (size_t)(m + 8 * k) * N + n);
+        t[k] = act != MT_ACT_NONE ? ld4(y + (size_t)(m + 8 * k) * N + n) : zero;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) one(m + 8 * k, g[k], t[k]);
+    }
+    for (; m < m1; m += 8) one(m, ld4(dy + (size_t)m * N + n), act != MT_ACT_NONE ? ld4(y + (size_t)m * N + n) : zero);
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+#pragma unroll
+    for (int q = 1; q < 8; ++q) { float4 o = red[q][tx]; s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w; }
+    atomicAdd(db + n, s.x); atomicAdd(db + n + 1, s.y); atomicAdd(db + n + 2, s.z); atomicAdd(db + n + 3, s.w);
+  }
+}
+
 struct TransposeJobs { TransposeJob j[16]; };
 template <typename TD>
 __global__ void transpose_pack_kernel(TransposeJobs jobs) {
@@ -344,12 +388,12 @@ int ln_fwd_dispatch(int M, int d, const float* x, const float* a, const float* b
   const dim3 grid((unsigned)gx, (unsigned)G);
   mt_prof_work(0.0, (double)G * M * d * (4.0 + sizeof(TY)));
   switch (d / 128) {
-    case 1: ln_fwd_kernel<TY, 1><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, b, eps, y, pstride); break;
-    case 2: ln_fwd_kernel<TY, 2><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, b, eps, y, pstride); break;
-    case 3: ln_fwd_kernel<TY, 3><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, b, eps, y, pstride); break;
-    case 4: ln_fwd_kernel<TY, 4><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, b, eps, y, pstride); break;
-    case 6: ln_fwd_kernel<TY, 6><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, b, eps, y, pstride); break;
-    case 8: ln_fwd_kernel<TY, 8><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, b, eps, y, pstride); break;
+    case 1: MT_CUDA(mt_launch_dep(ln_fwd_kernel<TY, 1>, grid, dim3(LN_WARPS * 32), 0, st, M, x, a, b, eps, y, pstride)); break;
+    case 2: MT_CUDA(mt_launch_dep(ln_fwd_kernel<TY, 2>, grid, dim3(LN_WARPS * 32), 0, st, M, x, a, b, eps, y, pstride)); break;
+    case 3: MT_CUDA(mt_launch_dep(ln_fwd_kernel<TY, 3>, grid, dim3(LN_WARPS * 32), 0, st, M, x, a, b, eps, y, pstride)); break;
+    case 4: MT_CUDA(mt_launch_dep(ln_fwd_kernel<TY, 4>, grid, dim3(LN_WARPS * 32), 0, st, M, x, a, b, eps, y, pstride)); break;
+    case 6: MT_CUDA(mt_launch_dep(ln_fwd_kernel<TY, 6>, grid, dim3(LN_WARPS * 32), 0, st, M, x, a, b, eps, y, pstride)); break;
+    case 8: MT_CUDA(mt_launch_dep(ln_fwd_kernel<TY, 8>, grid, dim3(LN_WARPS * 32), 0, st, M, x, a, b, eps, y, pstride)); break;
     default: return MT_ERR_UNSUPPORTED;
   }
   MT_LAUNCH_CHECK();
@@ -364,7 +408,7 @@ int ln_bwd_dispatch(int M, int d, const float* x, const float* a, float eps, con
   if (gx > cap2) gx = cap2 > 0 ? cap2 : 1;
   const dim3 grid((unsigned)gx, (unsigned)G);
   mt_prof_work(0.0, (double)G * M * d * (8.0 + sizeof(TY) + (dres ? 4.0 : 0.0) + (NEXT ? sizeof(TY) : 0.0)));
-#define MT_LNB(NCH) ln_bwd_kernel<TY, NCH, NEXT><<<grid, LN_WARPS * 32, 0, st>>>(M, x, a, eps, dy, dres, dx, da, db, nx_out, nx_db, nx_drop, pstride)
+#define MT_LNB(NCH) MT_CUDA(mt_launch_dep(ln_bwd_kernel<TY, NCH, NEXT>, grid, dim3(LN_WARPS * 32), 0, st, M, x, a, eps, dy, dres, dx, da, db, nx_out, nx_db, nx_drop, pstride))
   switch (d / 128) {
     case 1: MT_LNB(1); break;
     case 2: MT_LNB(2); break;
@@ -439,10 +483,33 @@ int mt_cast2d_run(const void* src, bool src_bf16, int lds, void* dst, bool dst_b
 }
 
 int mt_act_bwd_run(int M, int N, const void* dy, bool dy_bf16, const void* y, bool y_bf16, int act, const float* rowmask, void* dz,
-                   bool dz_bf16, cudaStream_t st) {
+                   bool dz_bf16, cudaStream_t st, float* db, bool* db_done) {
   size_t n = (size_t)M * N;
   if (n == 0) return MT_ERR_ARG;
   if (act != MT_ACT_NONE && !y) return MT_ERR_ARG;
+  if (db_done) *db_done = false;
+  if (db && db_done && N % 4 == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dz & 15) == 0 && (!y || ((uintptr_t)y & 15) == 0)) {
+    // fused bias gradient (overwrites db): one pass instead of act_bwd + colsum
+    MT_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)N, st));
+    const int gx = (N + 127) / 128;
+    int gy = (148 * 8 + gx - 1) / gx;
+    int rpb = ((M + gy - 1) / gy + 31) / 32 * 32;
+    if (rpb < 64) rpb = 64;
+    const dim3 gridv(gx, (M + rpb - 1) / rpb);
+    mt_prof_work(0.0, (double)n * ((dy_bf16 ? 2.0 : 4.0) + (act != MT_ACT_NONE ? (y_bf16 ? 2.0 : 4.0) : 0.0) + (dz_bf16 ? 2.0 : 4.0)));
+#define MT_ABC(TG, TYY, TZ) act_bwd_colsum_kernel<TG, TYY, TZ><<<gridv, 256, 0, st>>>(M, N, (const TG*)dy, (const TYY*)y, act, rowmask, (TZ*)dz, db, rpb)
+    if (dy_bf16) {
+      if (y_bf16) { if (dz_bf16) MT_ABC(bf16, bf16, bf16); else MT_ABC(bf16, bf16, float); }
+      else { if (dz_bf16) MT_ABC(bf16, float, bf16); else MT_ABC(bf16, float, float); }
+    } else {
+      if (y_bf16) { if (dz_bf16) MT_ABC(float, bf16, bf16); else MT_ABC(float, bf16, float); }
+      else { if (dz_bf16) MT_ABC(float, float, bf16); else MT_ABC(float, float, float); }
+    }
+#undef MT_ABC
+    MT_LAUNCH_CHECK();
+    *db_done = true;
+    return MT_OK;
+  }
   int grid = ew_grid(n, 256);
 #define MT_AB(TG, TYY, TZ) act_bwd_kernel<TG, TYY, TZ><<<grid, 256, 0, st>>>(n, N, (const TG*)dy, (const TYY*)y, act, rowmask, (TZ*)dz)
   if (dy_bf16) {

@@ -591,8 +591,9 @@ int mt_linear_bwd(int dtype, int M, int N, int K, const void* x, int x_f32, cons
   void* wl = lp ? k.take_bytes((size_t)N * K * 2) : nullptr;
   const bool dy_lp = lp && !dy_f32;
   const void* dzp = dy;
+  bool db_done = false;
   if (act != MT_ACT_NONE || rowmask != nullptr || (lp && dy_f32)) {
-    MT_TRY(mt_act_bwd_run(M, N, dy, dy_lp, y, lp && !y_f32, act, rowmask, dz, lp, st));
+    MT_TRY(mt_act_bwd_run(M, N, dy, dy_lp, y, lp && !y_f32, act, rowmask, dz, lp, st, db, &db_done));
     dzp = dz;
   }
   const void* xa = x;
@@ -603,7 +604,7 @@ int mt_linear_bwd(int dtype, int M, int N, int K, const void* x, int x_f32, cons
   }
   MT_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)N * K, st));
   MT_TRY(mt_gemm_run(dtype, wgrad_gemm(M, N, K, dzp, N, xa, ldx, dW, K), st));
-  if (db) MT_TRY(mt_colsum_run(lp, M, N, dzp, N, db, 0, st));
+  if (db && !db_done) MT_TRY(mt_colsum_run(lp, M, N, dzp, N, db, 0, st));
   if (dx) {
     const void* wa = W;
     if (lp) {

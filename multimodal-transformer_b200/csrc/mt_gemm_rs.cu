@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(NT, 1) gemm_rs_kernel(const __grid_constant__ 
   fence_after();
   if (F & R_LNX) cluster_sync_all();      // the peer's barriers exist before anything is sent to them
   const uint32_t tmem_base = *tmem_slot;
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  mt_pdl_gate();
   // (the producer / MMA warps start at once; bias, column-sum and LayerNorm-gain staging is the epilogue warps' own business, below)
 
   if (warp == 0) {
@@ -551,7 +551,7 @@ int launch(const RsDesc& d, cudaStream_t st) {
   cfg.gridDim = dim3((unsigned)(cnt * P)); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = C::TOTAL; cfg.stream = st;
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = g_mt_tune[MT_TUNE_PDL] ? 1 : 0;
+  at[0].val.programmaticStreamSerializationAllowed = mt_pdl_enabled(st);
   cfg.attrs = at; cfg.numAttrs = 1;
   if (F & R_LNX) {      // the two column slices of a row tile are adjacent CTAs: one cluster
     if (g.tiles_n != 2) return MT_ERR_UNSUPPORTED;

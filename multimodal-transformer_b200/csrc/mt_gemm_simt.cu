@@ -224,6 +224,15 @@ __global__ void __launch_bounds__(256) colsum_multi_kernel(int M, ColsumJobs job
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (n < N) {
     int m = m0 + ty;
+    for (; m + 56 < m1; m += 64) {      // eight 8 / 16-byte loads in flight per thread: the kernel is latency-bound below that
+      float4 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = ld4(X + (size_t)(m + 8 * k) * ldx + n);
+      s.x += ((v[0].x + v[1].x) + (v[2].x + v[3].x)) + ((v[4].x + v[5].x) + (v[6].x + v[7].x));
+      s.y += ((v[0].y + v[1].y) + (v[2].y + v[3].y)) + ((v[4].y + v[5].y) + (v[6].y + v[7].y));
+      s.z += ((v[0].z + v[1].z) + (v[2].z + v[3].z)) + ((v[4].z + v[5].z) + (v[6].z + v[7].z));
+      s.w += ((v[0].w + v[1].w) + (v[2].w + v[3].w)) + ((v[4].w + v[5].w) + (v[6].w + v[7].w));
+    }
     for (; m + 24 < m1; m += 32) {
       float4 a = ld4(X + (size_t)m * ldx + n), b = ld4(X + (size_t)(m + 8) * ldx + n);
       float4 c = ld4(X + (size_t)(m + 16) * ldx + n), d = ld4(X + (size_t)(m + 24) * ldx + n);
@@ -252,7 +261,7 @@ int mt_colsum_multi_run(int x_is_bf16, int M, const ColsumJob* jobs, int n_jobs,
   if (n_jobs > MT_COLSUM_MAX_JOBS) return MT_ERR_ARG;
   const size_t es = x_is_bf16 ? 2 : 4;
   ColsumJobs J;
-  int maxN = 0;
+  int maxN = 0, col_blocks = 0;
   double bytes = 0;
   for (int i = 0; i < n_jobs; ++i) {
     const ColsumJob& b = jobs[i];
@@ -262,12 +271,14 @@ int mt_colsum_multi_run(int x_is_bf16, int M, const ColsumJob* jobs, int n_jobs,
     }
     J.j[i] = b;
     maxN = b.N > maxN ? b.N : maxN;
+    col_blocks += (b.N + 127) / 128;
     bytes += (double)M * b.N * es;
   }
   const int gx = (maxN + 127) / 128;
-  int gy = (148 * 4 + gx * n_jobs - 1) / (gx * n_jobs);
+  // CTAs beyond a job's own width exit at once: size the row split by the column blocks that do work (8 CTAs of 256 threads per SM)
+  int gy = (148 * 8 + col_blocks - 1) / col_blocks;
   if (gy < 1) gy = 1;
-  int rpb = ((M + gy - 1) / gy + 31) / 32 * 32;
+  int rpb = ((M + gy - 1) / gy + 63) / 64 * 64;
   if (rpb < 64) rpb = 64;
   dim3 grid(gx, (M + rpb - 1) / rpb, n_jobs);
   mt_prof_work(0.0, bytes);

@@ -239,7 +239,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may run while the
   // previous kernel of the stream is still draining; from here on global memory is touched, so wait for it to complete.
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  mt_pdl_gate();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -599,7 +599,7 @@ int launch_inst(const CUtensorMap& ma, const TcMapsB& mb, const TcArgs& g, int g
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Smem<BN, OCC, MT>::THREADS); cfg.dynamicSmemBytes = Smem<BN, OCC, MT>::TOTAL; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = g_mt_tune[MT_TUNE_PDL] ? 1 : 0;
+  at[0].val.programmaticStreamSerializationAllowed = mt_pdl_enabled(st);
   cfg.attrs = at; cfg.numAttrs = 1;
   MT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, F, RES, OCC, MT>, ma, mb, g));
   MT_LAUNCH_CHECK();

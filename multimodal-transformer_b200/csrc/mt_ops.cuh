@@ -40,8 +40,10 @@ int mt_drop_grad_run(int M, int N, const float* g, void* out, bool out_bf16, Dro
 int mt_cast2d_run(const void* src, bool src_bf16, int lds, void* dst, bool dst_bf16, int ldd, int rows, int cols, DropCfg drop,
                   cudaStream_t st, int dcols = -1);
 // dz = dy * act'(y) * rowmask   (y = post-activation output)
+// db + db_done given: the bias gradient db[n] = sum_m dz[m][n] is fused into the pass where the shape allows (N % 4 == 0, 16-byte aligned
+// operands) and *db_done says whether it was
 int mt_act_bwd_run(int M, int N, const void* dy, bool dy_bf16, const void* y, bool y_bf16, int act, const float* rowmask, void* dz,
-                   bool dz_bf16, cudaStream_t st);
+                   bool dz_bf16, cudaStream_t st, float* db = nullptr, bool* db_done = nullptr);
 // batched transposes for the MFN forward weight pack: dst[c*ldd + r] = src[r*C + c]
 struct TransposeJob { const float* src; void* dst; int R, C, ldd; };
 int mt_transpose_pack_run(const TransposeJob* jobs, int n_jobs, bool dst_bf16, cudaStream_t st);
