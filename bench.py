@@ -94,7 +94,33 @@ class ClockSampler:
         self.proc = None
         self.index = index
 
+    # NVML bit masks of nvmlDeviceGetCurrentClocksEventReasons (nvml.h: nvmlClocksEventReason*)
+    NVML_REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap'}
+
+    def _nvml_loop(self, nv, h):
+        get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                bits = int(get_reasons(h))
+                self.nvml_rows.append((float(sm), bits))
+            except Exception:                                       # noqa: BLE001 -- a failed sample is skipped
+                pass
+            time.sleep(0.01)
+
     def start(self):
+        # NVML (nvidia_ml_py) every 10 ms: the default timed region is ~0.13 s, which nvidia-smi's 200 ms loop samples once or twice;
+        # nvidia-smi keeps running beside it as the recipe's own clocks line
+        self.nvml_rows, self._stop, self.nvml_thread, self.nvml_max = [], threading.Event(), None, None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.nvml_thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.nvml_thread.start()
+        except Exception:                                           # noqa: BLE001 -- no NVML: nvidia-smi alone
+            self.nvml_thread = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
                                           '-lms', '200'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -108,8 +134,13 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(',')])
 
     def stop(self):
-        if self.proc is None:
+        if getattr(self, 'nvml_thread', None) is not None:
+            self._stop.set()
+            self.nvml_thread.join(timeout=1)
+        if self.proc is None and not getattr(self, 'nvml_rows', None):
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        if self.proc is None:
+            return self._summary([], [], set())
         time.sleep(0.25)
         self.proc.terminate()
         try:
@@ -126,8 +157,20 @@ class ClockSampler:
             for n, v in zip(names, r[3:7]):
                 if v.lower().startswith('active'):
                     reasons.add(n)
+        return self._summary(sm, mx, reasons)
+
+    def _summary(self, sm, mx, reasons):
+        n_smi = len(sm)
+        rows = getattr(self, 'nvml_rows', None) or []
+        for clk, bits in rows:
+            sm.append(clk)
+            for bit, name in self.NVML_REASONS.items():
+                if bits & bit:
+                    reasons.add(name)
+        if getattr(self, 'nvml_max', None):
+            mx.append(self.nvml_max)
         return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons),
-                    samples=len(sm))
+                    samples=len(sm), samples_nvml=len(rows), samples_nvidia_smi=n_smi)
 
 
 # ---------------------------------------------------------------------------------------------------------

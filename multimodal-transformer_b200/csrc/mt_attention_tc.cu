@@ -18,6 +18,7 @@
 //             with a halving butterfly and leaves with one atomic per column per CTA.
 // The instruction stream of both kernels is dominated by the per-probability work (exp2, dropout hash, conversions), not by the MMAs:
 // packed fp32 pairs (FFMA2 / FADD2 / FMUL2), the dropout scale folded into the row normaliser, 32-bit pair indices.
+#include "mt_dropbits.cuh"
 #include "mt_ops.cuh"
 #include "mt_tcgen05.cuh"
 
@@ -37,7 +38,7 @@ constexpr float LN2 = 0.6931471805599453f;
 // Grouped launches (G modality stacks back to back, B narratives each): a CTA is pinned to ONE group -- blockIdx % G -- and walks that
 // group's (narrative, head pair) items, so the dropout key, the mask / key-length rows (shared by the groups) and the bias-gradient block
 // are fixed per CTA; global narrative index g * B + b addresses qkv / out / lse / aux, the LOCAL b the mask and the dropout stream.
-constexpr int MAXG = 4;
+constexpr int MAXG = MT_BITS_MAXG;
 struct FwdArgs {
   int B, T, d, h, G;      // B = narratives per group
   float scale_log2;
@@ -928,37 +929,10 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
 // Keep bits of the attention-probability dropout for a whole launch, drawn ONCE per step and layer (forward and backward read the same
 // words): bits[bh][c][q], bit i of word (c, q) = key 32 c + i of query q, from exactly the pair-hash draws the kernels make themselves
 // (pair index ((b_local h + hd) T + q) P2 + (j >> 1), low half -> even key).  One thread per word: 16 draws.
-struct BitsArgs { int B, T, h, G; DropCfg drop[MAXG]; };
-__global__ void __launch_bounds__(256) attn_tc_dropbits_kernel(const __grid_constant__ BitsArgs a, uint32_t* __restrict__ bits) {
+__global__ void __launch_bounds__(256) attn_tc_dropbits_kernel(const __grid_constant__ MtBitsArgs a, uint32_t* __restrict__ bits) {
   mt_pdl_gate();
-  const uint32_t per_group = (uint32_t)(a.B * a.h) * 512u;               // words of one group
-  const uint32_t n = per_group * (uint32_t)a.G;
-  const uint32_t P2 = (uint32_t)(a.T + 1) >> 1;
-  uint32_t key[MAXG], thr[MAXG];
-#pragma unroll
-  for (int g = 0; g < MAXG; ++g) {
-    const DropCfg d = mt_drop_resolve(a.drop[g < a.G ? g : 0]);
-    key[g] = d.key; thr[g] = d.thresh != 0u ? (d.thresh >> 16) : 0x10000u;      // 16-bit threshold; 0x10000: dropout off, every draw is below it
-  }
-  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
-    const uint32_t q = idx & (TM - 1), c = (idx >> 7) & 3u;
-    const uint32_t grp = idx / per_group;
-    const uint32_t blh = (idx - grp * per_group) >> 9;                   // group-local narrative * h + head
-    const uint32_t k = grp == 0 ? key[0] : (grp == 1 ? key[1] : (grp == 2 ? key[2] : key[3]));
-    const uint32_t t16 = grp == 0 ? thr[0] : (grp == 1 ? thr[1] : (grp == 2 ? thr[2] : thr[3]));
-    uint32_t word = 0xffffffffu;
-    if (t16 != 0x10000u && q < (uint32_t)a.T) {
-      word = 0u;
-      const uint32_t pbase = (blh * (uint32_t)a.T + q) * P2 + c * 16u;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const uint32_t b = mt_mix32((pbase + (uint32_t)i) ^ k);
-        word |= ((b & 0xffffu) >= t16 ? 1u : 0u) << (2 * i);
-        word |= ((b >> 16) >= t16 ? 2u : 0u) << (2 * i);
-      }
-    }
-    bits[idx] = word;
-  }
+  const MtBitsKeys k = mt_bits_resolve(a);
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < k.n; idx += gridDim.x * blockDim.x) bits[idx] = mt_bits_word(a, k, idx);
 }
 
 // one-time (per device) opt-in to the large dynamic shared-memory carve-out
@@ -986,9 +960,17 @@ bool mt_attn_tc_supported(int B, int T, int d, int h) {
 
 size_t mt_attn_tc_dropbits_words(int G, int B, int h) { return (size_t)G * B * h * 4 * TM; }
 
+int mt_attn_tc_dropbits_job(int G, int B, int T, int h, const DropCfg* drops, uint32_t* bits, MtBitsJob* job) {
+  if (G < 1 || G > MAXG || !drops || !bits || !job || T < 1 || T > TM || (unsigned long long)G * B * h * 512ull >= 0xffffffffull) return MT_ERR_ARG;
+  job->a.B = B; job->a.T = T; job->a.h = h; job->a.G = G;
+  for (int i = 0; i < MAXG; ++i) job->a.drop[i] = drops[i < G ? i : 0];
+  job->bits = bits;
+  return MT_OK;
+}
+
 int mt_attn_tc_dropbits_run(int G, int B, int T, int h, const DropCfg* drops, uint32_t* bits, cudaStream_t st) {
   if (G < 1 || G > MAXG || !drops || !bits || T < 1 || T > TM || (unsigned long long)G * B * h * 512ull >= 0xffffffffull) return MT_ERR_ARG;
-  BitsArgs a;
+  MtBitsArgs a;
   a.B = B; a.T = T; a.h = h; a.G = G;
   for (int i = 0; i < MAXG; ++i) a.drop[i] = drops[i < G ? i : 0];
   const size_t n = mt_attn_tc_dropbits_words(G, B, h);

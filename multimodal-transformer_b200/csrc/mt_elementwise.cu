@@ -11,12 +11,30 @@ constexpr int LN_WARPS = 8;
 // LayerNorm forward: one warp per row, NCH float4 chunks per lane (d = NCH * 128).
 //   y = a * (x - mean) / (std_unbiased + eps) + b                    MFT/multiTransformer.py:88-91
 // ------------------------------------------------------------------------------------------------------
-template <typename TY, int NCH>
+//   DRAW: every warp also draws its share of an attention dropout's keep bits (mt_dropbits.cuh), 32 consecutive words per chunk, the
+//   chunks spread over the row iterations so that the hash arithmetic sits between the loads of the next row and their first use
+template <typename TY, int NCH, bool DRAW>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(int M, const float* __restrict__ x, const float* __restrict__ a,
-                                                               const float* __restrict__ b, float eps, TY* __restrict__ y, size_t pstride) {
+                                                               const float* __restrict__ b, float eps, TY* __restrict__ y, size_t pstride,
+                                                               const __grid_constant__ MtBitsArgs ba, uint32_t* __restrict__ bits) {
   constexpr int d = NCH * 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   mt_pdl_gate();
+  MtBitsKeys bk;
+  uint32_t chunk = 0, n_chunks = 0, chunk_stride = 1, cpi = 0;
+  if (DRAW) {
+    bk = mt_bits_resolve(ba);
+    n_chunks = (bk.n + 31u) >> 5;
+    chunk_stride = gridDim.x * gridDim.y * LN_WARPS;
+    chunk = (blockIdx.y * gridDim.x + blockIdx.x) * LN_WARPS + warp;
+    const uint32_t row_iters = (uint32_t)M * gridDim.y;      // row iterations of the whole launch
+    cpi = (n_chunks + row_iters - 1) / row_iters;
+  }
+  auto draw_chunk = [&]() {
+    const uint32_t idx = chunk * 32u + lane;
+    if (idx < bk.n) bits[idx] = mt_bits_word(ba, bk, idx);
+    chunk += chunk_stride;
+  };
   // grouped launch (gridDim.y = modality stacks): group g owns rows [g*M, (g+1)*M) and the parameters at a + g*pstride
   x += (size_t)blockIdx.y * M * d; y += (size_t)blockIdx.y * M * d; a += blockIdx.y * pstride; b += blockIdx.y * pstride;
   float4 av[NCH], bv[NCH];
@@ -42,6 +60,9 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(int M, const floa
 #pragma unroll
       for (int c = 0; c < NCH; ++c) nv[c] = ld4(x + (size_t)(row + stride) * d + c * 128 + lane * 4);
     }
+    if (DRAW) {
+      for (uint32_t k = 0; k < cpi && chunk < n_chunks; ++k) draw_chunk();
+    }
 #pragma unroll
     for (int c = 0; c < NCH; ++c) s += (v[c].x + v[c].y) + (v[c].z + v[c].w);
     const float mean = warp_sum(s) * (1.0f / d);
@@ -63,6 +84,9 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(int M, const floa
       o.w = av[c].w * v[c].w * inv + bv[c].w;
       st4(yr + c * 128 + lane * 4, o);
     }
+  }
+  if (DRAW) {      // whatever the row loop left (warps without rows, more chunks than row iterations)
+    while (chunk < n_chunks) draw_chunk();
   }
 }
 
@@ -285,15 +309,15 @@ __global__ void __launch_bounds__(256) act_bwd_colsum_kernel(int M, int N, const
   if (n < N) {
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     int m = m0 + ty;
-    for (; m + 24 < m1; m += 32) {
-      float4 g[4], t[4];
+    for (; m + 56 < m1; m += 64) {
+      float4 g[8], t[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < 8; ++k) {
         g[k] = ld4(dy + (size_t)(m + 8 * k) * N + n);
         t[k] = act != MT_ACT_NONE ? ld4(y + (size_t)(m + 8 * k) * N + n) : zero;
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) one(m + 8 * k, g[k], t[k]);
+      for (int k = 0; k < 8; ++k) one(m + 8 * k, g[k], t[k]);
     }
     for (; m < m1; m += 8) one(m, ld4(dy + (size_t)m * N + n), act != MT_ACT_NONE ? ld4(y + (size_t)m * N + n) : zero);
   }
@@ -381,21 +405,31 @@ inline int ew_grid(size_t n, int threads) {
 }
 
 template <typename TY>
-int ln_fwd_dispatch(int M, int d, const float* x, const float* a, const float* b, float eps, TY* y, cudaStream_t st, int G, size_t pstride) {
+int ln_fwd_dispatch(int M, int d, const float* x, const float* a, const float* b, float eps, TY* y, cudaStream_t st, int G, size_t pstride,
+                    const MtBitsJob* draw) {
   int gx = (M + LN_WARPS - 1) / LN_WARPS;
   const int cap4 = 148 * 4 / (g_mt_tune[MT_TUNE_LN_SHARE] > 1 ? g_mt_tune[MT_TUNE_LN_SHARE] : 1) / G;
   if (gx > cap4) gx = cap4 > 0 ? cap4 : 1;
   const dim3 grid((unsigned)gx, (unsigned)G);
   mt_prof_work(0.0, (double)G * M * d * (4.0 + sizeof(TY)));
+  MtBitsArgs ba = {};
+  uint32_t* bits = nullptr;
+  if (draw) { ba = draw->a; bits = draw->bits; }
+#define MT_LNF(NCH)                                                                                                                      \
+  do {                                                                                                                                   \
+    if (draw) MT_CUDA(mt_launch_dep(ln_fwd_kernel<TY, NCH, true>, grid, dim3(LN_WARPS * 32), 0, st, M, x, a, b, eps, y, pstride, ba, bits)); \
+    else MT_CUDA(mt_launch_dep(ln_fwd_kernel<TY, NCH, false>, grid, dim3(LN_WARPS * 32), 0, st, M, x, a, b, eps, y, pstride, ba, bits));     \
+  } while (0)
   switch (d / 128) {
-    case 1: MT_CUDA(mt_launch_dep(ln_fwd_kernel<TY, 1>, grid, dim3(LN_WARPS * 32), 0, st, M, x, a, b, eps, y, pstride)); break;
-    case 2: MT_CUDA(mt_launch_dep(ln_fwd_kernel<TY, 2>, grid, dim3(LN_WARPS * 32), 0, st, M, x, a, b, eps, y, pstride)); break;
-    case 3: MT_CUDA(mt_launch_dep(ln_fwd_kernel<TY, 3>, grid, dim3(LN_WARPS * 32), 0, st, M, x, a, b, eps, y, pstride)); break;
-    case 4: MT_CUDA(mt_launch_dep(ln_fwd_kernel<TY, 4>, grid, dim3(LN_WARPS * 32), 0, st, M, x, a, b, eps, y, pstride)); break;
-    case 6: MT_CUDA(mt_launch_dep(ln_fwd_kernel<TY, 6>, grid, dim3(LN_WARPS * 32), 0, st, M, x, a, b, eps, y, pstride)); break;
-    case 8: MT_CUDA(mt_launch_dep(ln_fwd_kernel<TY, 8>, grid, dim3(LN_WARPS * 32), 0, st, M, x, a, b, eps, y, pstride)); break;
+    case 1: MT_LNF(1); break;
+    case 2: MT_LNF(2); break;
+    case 3: MT_LNF(3); break;
+    case 4: MT_LNF(4); break;
+    case 6: MT_LNF(6); break;
+    case 8: MT_LNF(8); break;
     default: return MT_ERR_UNSUPPORTED;
   }
+#undef MT_LNF
   MT_LAUNCH_CHECK();
   return MT_OK;
 }
@@ -426,10 +460,11 @@ int ln_bwd_dispatch(int M, int d, const float* x, const float* a, float eps, con
 }  // namespace
 
 int mt_ln_fwd_run(int M, int d, const float* x, const float* a, const float* b, float eps, void* y, bool y_bf16, cudaStream_t st, int G,
-                  size_t pstride) {
+                  size_t pstride, const MtBitsJob* draw) {
   if (M <= 0 || d <= 0 || d % 128 != 0 || d > 1024 || !x || !a || !b || !y || G < 1 || G > MT_LN_MAX_GROUPS) return MT_ERR_ARG;
-  if (y_bf16) return ln_fwd_dispatch<bf16>(M, d, x, a, b, eps, (bf16*)y, st, G, pstride);
-  return ln_fwd_dispatch<float>(M, d, x, a, b, eps, (float*)y, st, G, pstride);
+  if (draw && !draw->bits) return MT_ERR_ARG;
+  if (y_bf16) return ln_fwd_dispatch<bf16>(M, d, x, a, b, eps, (bf16*)y, st, G, pstride, draw);
+  return ln_fwd_dispatch<float>(M, d, x, a, b, eps, (float*)y, st, G, pstride, draw);
 }
 
 int mt_ln_bwd_run(int M, int d, const float* x, const float* a, float eps, const void* dy, bool dy_bf16, const float* dres, float* dx,
@@ -492,8 +527,8 @@ int mt_act_bwd_run(int M, int N, const void* dy, bool dy_bf16, const void* y, bo
     // fused bias gradient (overwrites db): one pass instead of act_bwd + colsum
     MT_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)N, st));
     const int gx = (N + 127) / 128;
-    int gy = (148 * 8 + gx - 1) / gx;
-    int rpb = ((M + gy - 1) / gy + 31) / 32 * 32;
+    int gy = (148 * 4 + gx - 1) / gx;      // four CTAs per SM: every CTA ends in 128 same-address atomics, twice as many cost more than they hide
+    int rpb = ((M + gy - 1) / gy + 63) / 64 * 64;
     if (rpb < 64) rpb = 64;
     const dim3 gridv(gx, (M + rpb - 1) / rpb);
     mt_prof_work(0.0, (double)n * ((dy_bf16 ? 2.0 : 4.0) + (act != MT_ACT_NONE ? (y_bf16 ? 2.0 : 4.0) : 0.0) + (dz_bf16 ? 2.0 : 4.0)));

@@ -268,18 +268,36 @@ int encoder_fwd_impl(const MtEncoderCfg& c, const Groups& gr, const float* param
   // backward kernel reads the same words.  (Measured: drawing all layers up front on a side stream buys nothing -- the row-stream GEMMs
   // and LayerNorm kernels it would run under own every register of their SMs, so the ALU-bound draw kernel cannot co-reside.)
   const bool use_bits = c.training && c.p_drop > 0.f && !c.key_len && !g_mt_tune[MT_TUNE_NO_DROPBITS] && w.L[0].dbits != nullptr;
+  // ... so the draw rides inside an HBM-bound kernel instead: the stand-alone LayerNorm pass that precedes an attention in program order
+  // (layer 0's first norm, every layer's second norm for the NEXT layer) hashes that attention's keep bits between its row loads and
+  // their first use (ln_fwd_kernel<.., DRAW>); only an attention without such a pass in front of it gets the draw kernel
+  const bool ln_draws = use_bits && !g_mt_tune[MT_TUNE_NO_LNDRAW];
+  bool bits_ready = false;
+  auto attn_drops = [&](int layer, DropCfg* ad) {
+    for (int g = 0; g < G; ++g) ad[g] = mt_make_drop(c.p_drop, gr.seed[g], mt_enc_site(gr.stack_id[g], layer, MT_SITE_ATTN_P));
+  };
+  MtBitsJob job;
+  auto draw_job = [&](int layer) -> const MtBitsJob* {
+    if (!ln_draws) return nullptr;
+    DropCfg ad[MT_RS_MAX_GROUPS];
+    attn_drops(layer, ad);
+    if (mt_attn_tc_dropbits_job(G, c.B, c.T, c.h, ad, w.L[layer].dbits, &job) != MT_OK) return nullptr;
+    bits_ready = true;
+    return &job;
+  };
   for (int l = 0; l < c.n_layers; ++l) {
     const size_t base = P.layer_stride * l;
     LayerBufs& b = w.L[l];
     const bool last = l == c.n_layers - 1;
     // sublayer 0: x + dropout(self_attn(LN(x)))
-    if (!u_ready) MT_TRY(mt_ln_fwd_run(M, d, xin, params + base + P.ln1_a, params + base + P.ln1_b, 1e-6f, b.u, lp, st, G, gr.pstride));
+    if (!u_ready) MT_TRY(mt_ln_fwd_run(M, d, xin, params + base + P.ln1_a, params + base + P.ln1_b, 1e-6f, b.u, lp, st, G, gr.pstride, draw_job(l)));
     MT_TRY(pj.run(false, 3 * d, d, b.u, base + P.w_qkv, b.qkv, !lp, (long long)(base + P.b_qkv), MT_ACT_NONE, l, -1, nullptr, 1.f, nullptr, -1));
     {
       DropCfg ad[MT_RS_MAX_GROUPS];
-      for (int g = 0; g < G; ++g) ad[g] = mt_make_drop(c.p_drop, gr.seed[g], mt_enc_site(gr.stack_id[g], l, MT_SITE_ATTN_P));
+      attn_drops(l, ad);
       const uint32_t* bits = use_bits ? b.dbits : nullptr;
-      if (bits) MT_TRY(mt_attn_tc_dropbits_run(G, c.B, c.T, c.h, ad, b.dbits, st));
+      if (bits && !bits_ready) MT_TRY(mt_attn_tc_dropbits_run(G, c.B, c.T, c.h, ad, b.dbits, st));
+      bits_ready = false;
       MT_TRY(mt_attn_group_fwd_run(c.dtype, G, c.B, c.T, d, c.h, b.qkv, mask, b.att, b.lse, ad, st, c.key_len, bits));
     }
     // mt_tune(11, 1): ... with the sublayer-1 LayerNorm in its epilogue (the two 128-column slices of a row tile are a CTA pair that exchanges
@@ -289,7 +307,8 @@ int encoder_fwd_impl(const MtEncoderCfg& c, const Groups& gr, const float* param
     MT_TRY(pj.run(false, d, d, b.att, base + P.w_o, b.xp, true, (long long)(base + P.b_o), MT_ACT_NONE, l, MT_SITE_SUB0, nullptr, 1.f, xin, -1,
                   ln2_fused ? b.v : nullptr, base + P.ln2_a, base + P.ln2_b));
     // sublayer 1: x + dropout(w_2(dropout(relu(w_1(LN(x))))))
-    if (!ln2_fused) MT_TRY(mt_ln_fwd_run(M, d, b.xp, params + base + P.ln2_a, params + base + P.ln2_b, 1e-6f, b.v, lp, st, G, gr.pstride));
+    if (!ln2_fused) MT_TRY(mt_ln_fwd_run(M, d, b.xp, params + base + P.ln2_a, params + base + P.ln2_b, 1e-6f, b.v, lp, st, G, gr.pstride,
+                                         last ? nullptr : draw_job(l + 1)));
     MT_TRY(pj.run(false, dff, d, b.v, base + P.w_1, b.hid, !lp, (long long)(base + P.b_1), MT_ACT_RELU, l, MT_SITE_FFN_H, nullptr, 1.f, nullptr, -1));
     void* ln_out = nullptr;
     size_t la = 0, lb = 0;

@@ -1,6 +1,7 @@
 // Internal (non-ABI) entry points shared between the translation units of libmt_b200.
 #pragma once
 #include "mt_gemm.cuh"
+#include "mt_dropbits.cuh"
 
 // ---- workspace carving: the same sequence of take() calls yields the same offsets in fwd and bwd ------
 struct WsCarver {
@@ -24,8 +25,10 @@ static inline size_t mt_esize(int dtype) { return dtype == MT_BF16 ? 2 : 4; }
 // G > 1: grouped launch over G modality stacks -- x / y are [G*M, d] (rows of group g at g*M), a / b of group g at a + g*pstride floats
 #define MT_LN_MAX_GROUPS 4
 struct DropGroups { DropCfg d[MT_LN_MAX_GROUPS]; };
+// draw != nullptr: the same launch also draws the keep bits of an attention dropout (mt_dropbits.cuh) -- the hash work of the
+// ALU-bound draw runs under the memory latency of the HBM-bound norm instead of as a kernel of its own
 int mt_ln_fwd_run(int M, int d, const float* x, const float* a, const float* b, float eps, void* y, bool y_bf16, cudaStream_t st, int G = 1,
-                  size_t pstride = 0);
+                  size_t pstride = 0, const MtBitsJob* draw = nullptr);
 // optional second output of the LayerNorm backward: out = dx * dropout_factor(drop, row*d + col) in the operand dtype
 // (same dtype as dy) and dbias[d] += colsum(out) -- what the sublayer below needs first (see ln_bwd_kernel)
 struct LnBwdNext { void* out; float* dbias; DropCfg drop; };
@@ -76,6 +79,8 @@ int mt_attn_tc_fwd_run(int B, int T, int d, int h, const void* qkv, const float*
 // keep bits of the probability dropout of one launch (G * B * h * 512 words), drawn once and read by both the forward and the backward kernel
 size_t mt_attn_tc_dropbits_words(int G, int B, int h);
 int mt_attn_tc_dropbits_run(int G, int B, int T, int h, const DropCfg* drops, uint32_t* bits, cudaStream_t st);
+// the same draw as a job description for a kernel that draws on the side (mt_ln_fwd_run)
+int mt_attn_tc_dropbits_job(int G, int B, int T, int h, const DropCfg* drops, uint32_t* bits, MtBitsJob* job);
 // aux: fp32 workspace of mt_attn_bwd_ws_floats(B, T, h) floats (per-query scalars); dbias as in mt_attn_mma_bwd_run (h <= 8)
 // G > 1 as in mt_attn_tc_fwd_run; aux holds G * mt_attn_bwd_ws_floats(B, T, h) floats, dbias of group g at dbias + g * dbias_gstride
 int mt_attn_tc_bwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse, const void* dout,

@@ -985,6 +985,18 @@ def test_attention_keep_bits_reproduce_the_in_kernel_hash():
         assert_close(g_bits[k], g_hash[k], 1e-5, k, 1e-9)
 
 
+def test_keep_bits_drawn_inside_the_layernorm_pass_equal_the_draw_kernel():
+    """The keep bits of an attention ride in the LayerNorm forward pass that precedes it (ln_fwd_kernel<.., DRAW>); mt_tune key 12 sends
+    them back to the stand-alone draw kernel: identical predictions, gradients equal up to the order of atomic sums.  B = 9 and B = 3
+    give more 32-word chunks than row iterations and the reverse (the tail loop of warps that run out of rows)."""
+    for B, T in ((9, 128), (3, 40)):
+        p_ln, g_ln = _mft_bf16_train_step(B=B, T=T)
+        p_k, g_k = _mft_bf16_train_step({12: 1}, B=B, T=T)
+        assert torch.equal(p_ln, p_k)
+        for k in g_ln:
+            assert_close(g_ln[k], g_k[k], 1e-5, k, 1e-9)
+
+
 def test_grouped_qkv_input_gradient_equals_per_stack_launches():
     """GemmDesc.mgroups: the long-K input gradient of the QKV projection as one streaming launch over the stacked rows (per-tile weight
     map) against one launch per stack (mt_tune key 10)."""
