@@ -379,7 +379,8 @@ int mt_gemm_tc_mode(int mode);
  * MFN recurrence kernels (bit 6: the first-cut kernels, for A/B timing; bit 5: clock trace); key 9 != 0: the tcgen05 attention kernels hash
  * their dropout draws themselves instead of reading the keep bits drawn once per step and layer; key 10 != 0: streaming GEMMs over the stacked
  * modality rows launch per stack; key 11 != 0: the output projection fuses the sublayer-1 LayerNorm across a CTA pair (opt-in); key 12 != 0: the keep bits are
- * drawn by the stand-alone kernel instead of inside the LayerNorm forward pass that precedes the attention. */
+ * drawn by the stand-alone kernel instead of inside the LayerNorm forward pass that precedes the attention; key 13 != 0: bf16 mode carries the residual-stream gradient
+ * between the sublayers of a stack in bf16 instead of fp32 (opt-in: fewer bytes, measured slower). */
 int mt_tune(int key, int value);
 /* debug hook: CTA 0 of every tcgen05 GEMM writes per-tile clock64 stamps (8 x uint64 per tile, first 64 tiles: TMA issue, MMA
  * tile start, first operands landed, last k-block landed, epilogue sees the accumulator, accumulator released, last pass

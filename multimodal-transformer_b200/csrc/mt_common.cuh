@@ -54,6 +54,7 @@ int mt_comm_overlap_fire(float* grads, size_t pstride, int G, size_t tail_off, s
 #define MT_TUNE_NO_MGROUPS 10  // [10] != 0: streaming GEMMs of the stacked modality rows launch per stack instead of once with row groups
 #define MT_TUNE_LNX 11         // [11] != 0: the output projection fuses the sublayer-1 LayerNorm across a CTA pair (opt-in: measured no faster than the pass)
 #define MT_TUNE_NO_LNDRAW 12   // [12] != 0: the attention keep bits come from the stand-alone draw kernel instead of riding in a LayerNorm forward pass
+#define MT_TUNE_BF16_GSTREAM 13 // [13] != 0: bf16 mode carries the residual-stream gradient between the sublayers in bf16 (opt-in: 12 instead of 16 bytes per element, but measured SLOWER -- the LayerNorm backward is bound by its memory-instruction rate, and 8-byte accesses halve the bytes per instruction)
 #define MT_TUNE_NO_LNFUSE 6    // [6] != 0: no LayerNorm fused into the FFN output projection's epilogue
 
 // one-time-per-DEVICE guard for cudaFuncSetAttribute-style opt-ins (a process may drive several GPUs): true the first time the

@@ -1,6 +1,7 @@
 // HBM-bound row-wise / element-wise kernels: LayerNorm (reference semantics: unbiased std, eps on std),
 // dropout-gradient, casts, activation backward, MSE loss, Adam, transposed weight packs.
 // All of them are one pass over their operands with 16-byte vector accesses; warp-shuffle reductions.
+#include <type_traits>
 #include "mt_ops.cuh"
 
 namespace {
@@ -98,10 +99,15 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(int M, const floa
 //   NEXT: the same pass also emits what the layer below consumes first -- nx_out = dx * dropout_factor(site, row*d + col)
 //   in the operand dtype (the gradient through that sublayer's output dropout) and nx_db += colsum(nx_out) (the bias
 //   gradient of the Linear that produced the dropped tensor) -- instead of a drop_grad pass + a colsum pass over dx.
-template <typename TY, int NCH, bool NEXT>
+//   GM: dtype of the residual-stream gradient, 0 = dres and dx fp32, 1 = both bf16 (inside a bf16-mode stack: it is an activation
+//   gradient like dy, and half of this HBM-bound kernel's bytes), 2 = dres bf16, dx fp32 (the stack's bottom: dx leaves the library)
+template <int GM> struct LnG { typedef float R; typedef float X; };
+template <> struct LnG<1> { typedef bf16 R; typedef bf16 X; };
+template <> struct LnG<2> { typedef bf16 R; typedef float X; };
+template <typename TY, int NCH, bool NEXT, int GM>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(int M, const float* __restrict__ x, const float* __restrict__ a, float eps,
-                                                               const TY* __restrict__ dy, const float* __restrict__ dres,
-                                                               float* __restrict__ dx, float* __restrict__ da, float* __restrict__ db,
+                                                               const TY* __restrict__ dy, const typename LnG<GM>::R* __restrict__ dres,
+                                                               typename LnG<GM>::X* __restrict__ dx, float* __restrict__ da, float* __restrict__ db,
                                                                TY* __restrict__ nx_out, float* __restrict__ nx_db, DropGroups nx_drops,
                                                                size_t pstride) {
   constexpr int d = NCH * 128;
@@ -125,34 +131,32 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(int M, const floa
     pb[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (NEXT) pn[c] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  // software pipeline: the next row's x / dy / dres are in flight while this row goes through its three dependent
-  // warp reductions (one row per warp leaves too few bytes in flight otherwise)
+  // software pipeline (d <= 256): TWO rows' x / dy / dres are in flight per warp while a row goes through its three dependent warp reductions
+  // (16 warps per SM at 110-120 registers: one row in flight is 2-2.5 KB per warp, too few bytes for the HBM latency once the
+  // residual-stream gradient is bf16)
   const int stride = gridDim.x * LN_WARPS;
-  int row = blockIdx.x * LN_WARPS + warp;
-  float4 nv[NCH], nr[NCH];
-  typename Raw4<TY>::type ng[NCH];
-  if (row < M) {
+  struct RowBuf {
+    float4 v[NCH];
+    typename Raw4<TY>::type g[NCH];
+    typename Raw4<typename LnG<GM>::R>::type r[NCH];
+  };
+  auto load_row = [&](RowBuf& rb, int row) {
+    if (row < M) {
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      nv[c] = ld4(x + (size_t)row * d + c * 128 + lane * 4);
-      ng[c] = ld4raw(dy + (size_t)row * d + c * 128 + lane * 4);
-      nr[c] = dres ? ld4(dres + (size_t)row * d + c * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < NCH; ++c) {
+        rb.v[c] = ld4(x + (size_t)row * d + c * 128 + lane * 4);
+        rb.g[c] = ld4raw(dy + (size_t)row * d + c * 128 + lane * 4);
+        if (dres) rb.r[c] = ld4raw(dres + (size_t)row * d + c * 128 + lane * 4);
+      }
     }
-  }
-  for (; row < M; row += stride) {
+  };
+  // consumes rb (row `row`), refills it with row `next` before the arithmetic starts
+  auto do_row = [&](RowBuf& rb, int row, int next) {
     float4 v[NCH], g[NCH], r[NCH];
     float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) { v[c] = nv[c]; g[c] = cvt4(ng[c]); r[c] = nr[c]; }
-    const int nrow = row + stride;
-    if (nrow < M) {
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        nv[c] = ld4(x + (size_t)nrow * d + c * 128 + lane * 4);
-        ng[c] = ld4raw(dy + (size_t)nrow * d + c * 128 + lane * 4);
-        if (dres) nr[c] = ld4(dres + (size_t)nrow * d + c * 128 + lane * 4);
-      }
-    }
+    for (int c = 0; c < NCH; ++c) { v[c] = rb.v[c]; g[c] = cvt4(rb.g[c]); r[c] = dres ? cvt4(rb.r[c]) : make_float4(0.f, 0.f, 0.f, 0.f); }
+    load_row(rb, next);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) s += (v[c].x + v[c].y) + (v[c].z + v[c].w);
     const float mean = warp_sum(s) * (1.0f / d);
@@ -178,7 +182,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(int M, const floa
     const float gm = warp_sum(gs) * (1.0f / d);
     dot = warp_sum(dot);
     const float k = dot / ((float)(d - 1) * sd * (sd + eps));
-    float* dxr = dx + (size_t)row * d;
+    typename LnG<GM>::X* dxr = dx + (size_t)row * d;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       float4 o;
@@ -197,6 +201,20 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(int M, const floa
         pn[c].x += o.x; pn[c].y += o.y; pn[c].z += o.z; pn[c].w += o.w;
       }
     }
+  };
+  int row = blockIdx.x * LN_WARPS + warp;
+  constexpr bool DEEP = NCH <= 2;      // wider rows carry enough bytes per row (and have no registers for a second buffer)
+  RowBuf b0;
+  load_row(b0, row);
+  if (DEEP) {
+    RowBuf b1;
+    load_row(b1, row + stride);
+    for (; row < M; row += 2 * stride) {
+      do_row(b0, row, row + 2 * stride);
+      if (row + stride < M) do_row(b1, row + stride, row + 3 * stride);
+    }
+  } else {
+    for (; row < M; row += stride) do_row(b0, row, row + stride);
   }
   if (NEXT) {
 #pragma unroll
@@ -435,14 +453,26 @@ int ln_fwd_dispatch(int M, int d, const float* x, const float* a, const float* b
 }
 
 template <typename TY, bool NEXT>
-int ln_bwd_dispatch(int M, int d, const float* x, const float* a, float eps, const TY* dy, const float* dres, float* dx, float* da,
+int ln_bwd_dispatch(int M, int d, const float* x, const float* a, float eps, const TY* dy, const void* dres, void* dx, int gm, float* da,
                     float* db, TY* nx_out, float* nx_db, const DropGroups& nx_drop, cudaStream_t st, int G, size_t pstride) {
   int gx = (M + LN_WARPS - 1) / LN_WARPS;
   const int cap2 = 148 * 2 / (g_mt_tune[MT_TUNE_LN_SHARE] > 1 ? g_mt_tune[MT_TUNE_LN_SHARE] : 1) / G;
   if (gx > cap2) gx = cap2 > 0 ? cap2 : 1;
   const dim3 grid((unsigned)gx, (unsigned)G);
-  mt_prof_work(0.0, (double)G * M * d * (8.0 + sizeof(TY) + (dres ? 4.0 : 0.0) + (NEXT ? sizeof(TY) : 0.0)));
-#define MT_LNB(NCH) MT_CUDA(mt_launch_dep(ln_bwd_kernel<TY, NCH, NEXT>, grid, dim3(LN_WARPS * 32), 0, st, M, x, a, eps, dy, dres, dx, da, db, nx_out, nx_db, nx_drop, pstride))
+  const double gr_b = gm == 0 ? 4.0 : 2.0, gx_b = gm == 1 ? 2.0 : 4.0;
+  mt_prof_work(0.0, (double)G * M * d * (4.0 + gx_b + sizeof(TY) + (dres ? gr_b : 0.0) + (NEXT ? sizeof(TY) : 0.0)));
+  if (gm != 0 && !std::is_same<TY, bf16>::value) return MT_ERR_ARG;      // a bf16 gradient stream exists in bf16 mode only
+#define MT_LNB_G(NCH, GMV)                                                                                                                \
+  MT_CUDA(mt_launch_dep(ln_bwd_kernel<TY, NCH, NEXT, GMV>, grid, dim3(LN_WARPS * 32), 0, st, M, x, a, eps, dy,                             \
+                        (const typename LnG<GMV>::R*)dres, (typename LnG<GMV>::X*)dx, da, db, nx_out, nx_db, nx_drop, pstride))
+#define MT_LNB(NCH)                                                                          \
+  do {                                                                                       \
+    if constexpr (std::is_same<TY, bf16>::value) {                                           \
+      if (gm == 1) { MT_LNB_G(NCH, 1); break; }                                              \
+      if (gm == 2) { MT_LNB_G(NCH, 2); break; }                                              \
+    }                                                                                        \
+    MT_LNB_G(NCH, 0);                                                                        \
+  } while (0)
   switch (d / 128) {
     case 1: MT_LNB(1); break;
     case 2: MT_LNB(2); break;
@@ -453,6 +483,7 @@ int ln_bwd_dispatch(int M, int d, const float* x, const float* a, float eps, con
     default: return MT_ERR_UNSUPPORTED;
   }
 #undef MT_LNB
+#undef MT_LNB_G
   MT_LAUNCH_CHECK();
   return MT_OK;
 }
@@ -467,19 +498,20 @@ int mt_ln_fwd_run(int M, int d, const float* x, const float* a, const float* b, 
   return ln_fwd_dispatch<float>(M, d, x, a, b, eps, (float*)y, st, G, pstride, draw);
 }
 
-int mt_ln_bwd_run(int M, int d, const float* x, const float* a, float eps, const void* dy, bool dy_bf16, const float* dres, float* dx,
-                  float* da, float* db, cudaStream_t st, const LnBwdNext* nx, int G, size_t pstride, const DropCfg* nx_drops) {
+int mt_ln_bwd_run(int M, int d, const float* x, const float* a, float eps, const void* dy, bool dy_bf16, const void* dres, void* dx,
+                  float* da, float* db, cudaStream_t st, const LnBwdNext* nx, int G, size_t pstride, const DropCfg* nx_drops, int gmode) {
   if (M <= 0 || d <= 0 || d % 128 != 0 || d > 1024 || !x || !a || !dy || !dx || !da || !db || G < 1 || G > MT_LN_MAX_GROUPS) return MT_ERR_ARG;
+  if (gmode < 0 || gmode > 2 || (gmode != 0 && !dy_bf16)) return MT_ERR_ARG;
   DropGroups dg;
   for (int i = 0; i < MT_LN_MAX_GROUPS; ++i) dg.d[i] = mt_make_drop(0.f, 0, 0);
   if (nx && nx->out) {
     if (!nx->dbias || nx->out == dy) return MT_ERR_ARG;
     for (int i = 0; i < G; ++i) dg.d[i] = nx_drops ? nx_drops[i] : nx->drop;
-    if (dy_bf16) return ln_bwd_dispatch<bf16, true>(M, d, x, a, eps, (const bf16*)dy, dres, dx, da, db, (bf16*)nx->out, nx->dbias, dg, st, G, pstride);
-    return ln_bwd_dispatch<float, true>(M, d, x, a, eps, (const float*)dy, dres, dx, da, db, (float*)nx->out, nx->dbias, dg, st, G, pstride);
+    if (dy_bf16) return ln_bwd_dispatch<bf16, true>(M, d, x, a, eps, (const bf16*)dy, dres, dx, gmode, da, db, (bf16*)nx->out, nx->dbias, dg, st, G, pstride);
+    return ln_bwd_dispatch<float, true>(M, d, x, a, eps, (const float*)dy, dres, dx, gmode, da, db, (float*)nx->out, nx->dbias, dg, st, G, pstride);
   }
-  if (dy_bf16) return ln_bwd_dispatch<bf16, false>(M, d, x, a, eps, (const bf16*)dy, dres, dx, da, db, nullptr, nullptr, dg, st, G, pstride);
-  return ln_bwd_dispatch<float, false>(M, d, x, a, eps, (const float*)dy, dres, dx, da, db, nullptr, nullptr, dg, st, G, pstride);
+  if (dy_bf16) return ln_bwd_dispatch<bf16, false>(M, d, x, a, eps, (const bf16*)dy, dres, dx, gmode, da, db, nullptr, nullptr, dg, st, G, pstride);
+  return ln_bwd_dispatch<float, false>(M, d, x, a, eps, (const float*)dy, dres, dx, gmode, da, db, nullptr, nullptr, dg, st, G, pstride);
 }
 
 int mt_drop_grad_run(int M, int N, const float* g, void* out, bool out_bf16, DropCfg drop, cudaStream_t st) {

@@ -343,6 +343,12 @@ int encoder_bwd_impl(const MtEncoderCfg& c, const Groups& gr, const float* param
   const Proj pj{c, gr, params, params_lp, grads, st, M};
   for (int g = 0; g < G; ++g) MT_CUDA(cudaMemsetAsync(grads + g * gr.pstride, 0, sizeof(float) * P.total, st));
 
+  // The residual-stream gradient dL/dx_l between the sublayers stays fp32.  mt_tune(13, 1) carries it in bf16 inside a bf16-mode stack
+  // (ln_bwd_kernel GM = 1 / 2; only the stack's own dx leaves in fp32): 12 instead of 16 bytes per element of the LayerNorm backward, but
+  // measured slower on B200 (1.00 ms vs 0.94 ms per step over the 13 launches: the kernel is bound by its memory-instruction rate, not
+  // by bytes, and 8-byte accesses carry half as much per instruction) -- kept as an A/B switch with its parity test.
+  const bool dy_lp = lp && !c.y_f32;
+  const bool g_lp = lp && dy_lp && g_mt_tune[MT_TUNE_BF16_GSTREAM];
   float* g_cur = w.g0;
   float* g_nxt = w.g1;
   const float* x_last = w.L[c.n_layers - 1].x_out;
@@ -357,10 +363,9 @@ int encoder_bwd_impl(const MtEncoderCfg& c, const Groups& gr, const float* param
     const size_t bl = P.layer_stride * (c.n_layers - 1);
     const DropCfg dr = site_drops(c.n_layers - 1, MT_SITE_SUB1);
     LnBwdNext nx{w.dact, grads + bl + P.b_2, dr};
-    const bool dy_lp = lp && !c.y_f32;
     if (dy_lp == lp) {
       MT_TRY(mt_ln_bwd_run(M, d, x_last, params + P.lnf_a, 1e-6f, dy, dy_lp, nullptr, g_cur, grads + P.lnf_a, grads + P.lnf_b, st, &nx, G,
-                           gr.pstride, drops));
+                           gr.pstride, drops, g_lp ? 1 : 0));
     } else {      // fp32 dy in bf16 mode: the fused second output has dy's dtype, so take the two-pass route once
       MT_TRY(mt_ln_bwd_run(M, d, x_last, params + P.lnf_a, 1e-6f, dy, dy_lp, nullptr, g_cur, grads + P.lnf_a, grads + P.lnf_b, st, nullptr, G,
                            gr.pstride));
@@ -386,7 +391,7 @@ int encoder_bwd_impl(const MtEncoderCfg& c, const Groups& gr, const float* param
     {
       LnBwdNext nx{w.dact, grads + base + P.b_o, site_drops(l, MT_SITE_SUB0)};
       MT_TRY(mt_ln_bwd_run(M, d, b.xp, params + base + P.ln2_a, 1e-6f, w.dact2, lp, g_cur, g_nxt, grads + base + P.ln2_a, grads + base + P.ln2_b, st,
-                           &nx, G, gr.pstride, drops));
+                           &nx, G, gr.pstride, drops, g_lp ? 1 : 0));
     }
     // ---- attention sublayer: xp = x + drop(att w_o + b_o); w.dact = drop' . g_nxt and db_o are already there ---------
     MT_TRY(pj.wgrad(d, d, w.dact, b.att, base + P.w_o));
@@ -417,7 +422,7 @@ int encoder_bwd_impl(const MtEncoderCfg& c, const Groups& gr, const float* param
     LnBwdNext nx{nullptr, nullptr, mt_make_drop(0.f, 0, 0)};
     if (l > 0) nx = LnBwdNext{w.dact, grads + base - P.layer_stride + P.b_2, site_drops(l - 1, MT_SITE_SUB1)};
     MT_TRY(mt_ln_bwd_run(M, d, x_l, params + base + P.ln1_a, 1e-6f, w.dact2, lp, g_nxt, out, grads + base + P.ln1_a, grads + base + P.ln1_b, st, &nx,
-                         G, gr.pstride, drops));
+                         G, gr.pstride, drops, g_lp ? (l == 0 ? 2 : 1) : 0));
     // g_cur now holds dL/dx_l (g_nxt is free again)
     // data-parallel training: every gradient of layers >= l and of the final norm is enqueued -- their all-reduce may start now, on the
     // communication stream, under the backward of layers l - 1 .. 0 (mt_comm_overlap_arm)

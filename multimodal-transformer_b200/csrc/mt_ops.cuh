@@ -34,9 +34,10 @@ int mt_ln_fwd_run(int M, int d, const float* x, const float* a, const float* b, 
 struct LnBwdNext { void* out; float* dbias; DropCfg drop; };
 // G > 1: grouped like mt_ln_fwd_run (dy / dres / dx / nx->out rows of group g at g*M; a / da / db / nx->dbias at + g*pstride;
 // nx_drops[g] = that group's dropout stream, element index local to the group)
-int mt_ln_bwd_run(int M, int d, const float* x, const float* a, float eps, const void* dy, bool dy_bf16, const float* dres,
-                  float* dx, float* da, float* db, cudaStream_t st, const LnBwdNext* nx = nullptr, int G = 1, size_t pstride = 0,
-                  const DropCfg* nx_drops = nullptr);
+// gmode: dtype of the residual-stream gradient -- 0: dres / dx fp32; 1: both bf16; 2: dres bf16, dx fp32 (1 and 2 with bf16 dy only)
+int mt_ln_bwd_run(int M, int d, const float* x, const float* a, float eps, const void* dy, bool dy_bf16, const void* dres,
+                  void* dx, float* da, float* db, cudaStream_t st, const LnBwdNext* nx = nullptr, int G = 1, size_t pstride = 0,
+                  const DropCfg* nx_drops = nullptr, int gmode = 0);
 // out[M,N] (bf16 or f32) = g[M,N] (f32) * dropout_factor(site, m*N+n)      (gradient through an output dropout)
 int mt_drop_grad_run(int M, int N, const float* g, void* out, bool out_bf16, DropCfg drop, cudaStream_t st);
 // 2-D cast with zero padding / optional input dropout: dst[r, c] = c < cols ? src[r*lds + c] * drop(r*cols + c) : 0

@@ -997,6 +997,24 @@ def test_keep_bits_drawn_inside_the_layernorm_pass_equal_the_draw_kernel():
             assert_close(g_ln[k], g_k[k], 1e-5, k, 1e-9)
 
 
+def test_bf16_gradient_stream_against_the_fp32_stream():
+    """mt_tune key 13 carries the residual-stream gradient between the sublayers of a bf16-mode stack in bf16 (ln_bwd_kernel GM = 1 / 2)
+    instead of fp32 (opt-in).  Forward identical; every gradient within 1 % of its tensor's scale of the fp32-stream run (bf16 rounding
+    of a stream that passes 2 N sublayers) -- far inside the 4 % bound the bf16 step is held to against the fp64 oracle."""
+    for N in (2, 6):
+        p32, g32 = _mft_bf16_train_step(N=N, B=5, T=64)
+        p16, g16 = _mft_bf16_train_step({13: 1}, N=N, B=5, T=64)
+        assert torch.equal(p16, p32)
+        gmax = max(v.abs().max().item() for v in g32.values())
+        differs = False
+        for k in g32:
+            scale = max(g32[k].abs().max().item(), 1e-3 * gmax)
+            err = (g16[k] - g32[k]).abs().max().item() / scale
+            assert err < 1e-2, (N, k, err)
+            differs = differs or err > 1e-6
+        assert differs          # the switch really changed the stream's dtype
+
+
 def test_grouped_qkv_input_gradient_equals_per_stack_launches():
     """GemmDesc.mgroups: the long-K input gradient of the QKV projection as one streaming launch over the stacked rows (per-tile weight
     map) against one launch per stack (mt_tune key 10)."""
