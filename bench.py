@@ -67,6 +67,7 @@ def parse():
     ap.add_argument('--no-profile', action='store_true')
     ap.add_argument('--gemm-mode', type=int, default=0, help='tcgen05 GEMM CTAs per SM (tuning; 0 = library default)')
     ap.add_argument('--tune', default='', help='library tuning knobs, e.g. 0=2,1=2 (mt_tune key=value)')
+    ap.add_argument('--sync-e2e', action='store_true', help='e2e: drain the stream after every step instead of reading results one step late')
     ap.add_argument('--serial-stacks', action='store_true', help='run the modality stacks on one stream')
     a = ap.parse_args()
     c = CONFIGS[a.config]
@@ -444,7 +445,13 @@ def run_ours(args, rank, local_rank, world):
 
     # e2e: every step copies its inputs from pinned host memory and reads its result back.  The public API pipelines the
     # input copy: batch k + 1 crosses PCIe on a copy stream while batch k computes (GraphedTrainStep.prefetch).
+    # The result goes the other way the same way: every step's loss / predictions are copied to pinned host memory behind the step and
+    # read on the host one step later (training.ResultPipe), so the host enqueues step k + 1 while step k runs; timed() drains the pipe
+    # before it stops the clock.  --sync-e2e drains the stream after every step instead (the pre-pipeline measurement).
+    from multimodal_transformer_b200.training import ResultPipe
     pending = {'train': 0, 'infer': 0}
+    pipes = {'train': ResultPipe(loss_host, dev), 'infer': ResultPipe(pred_host, dev)}
+    host_seen = {'train': 0, 'infer': 0}
 
     def g_train(e2e):
         if not e2e:
@@ -453,8 +460,12 @@ def run_ours(args, rank, local_rank, world):
             gstep.prefetch(host, host_mask, host_target, lengths); pending['train'] += 1
         gstep.prefetch(host, host_mask, host_target, lengths)          # next step's inputs: pinned host -> staging, async
         loss = gstep.step_prefetched()
-        loss_host.copy_(loss, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        if args.sync_e2e:
+            loss_host.copy_(loss, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            host_seen['train'] += 1
+        elif pipes['train'].push(loss) is not None:
+            host_seen['train'] += 1
         return loss
 
     def g_infer(e2e):
@@ -465,9 +476,18 @@ def run_ours(args, rank, local_rank, world):
             gfwd.prefetch(host, host_mask); pending['infer'] += 1
         gfwd.prefetch(host, host_mask)
         pred = gfwd.forward_prefetched()
-        pred_host.copy_(pred, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        if args.sync_e2e:
+            pred_host.copy_(pred, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            host_seen['infer'] += 1
+        elif pipes['infer'].push(pred) is not None:
+            host_seen['infer'] += 1
         return pred
+
+    def drain_pipes():
+        for k, p_ in pipes.items():
+            if p_.n > host_seen[k] and p_.drain() is not None:
+                host_seen[k] += 1
 
     def timed(fn, e2e, warm, steps):
         for _ in range(warm):
@@ -480,6 +500,8 @@ def run_ours(args, rank, local_rank, world):
         e0.record()
         for _ in range(steps):
             fn(e2e)
+        if e2e:
+            drain_pipes()               # the last step's result is on the host before the clock stops
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -602,7 +624,12 @@ def run_ours(args, rank, local_rank, world):
             'inference': {'value': gb / (ms_inf * 1e-3), 'unit': 'narratives/s', 'ms_per_step': ms_inf,
                           'e2e_value': gb / (ms_inf_e2e * 1e-3), 'd2h_bytes_per_step': B * T * 4},
             'e2e': {'value': gb / (ms_train_e2e * 1e-3), 'unit': 'narratives/s', 'ms_per_step': ms_train_e2e, 'h2d_bytes_per_step': h2d,
-                    'd2h_bytes_per_step': 4 if is_train else B * T * 4},
+                    'd2h_bytes_per_step': 4 if is_train else B * T * 4,
+                    'results_on_host': host_seen['train' if is_train else 'infer'],
+                    'readback': ('stream drained after every step' if args.sync_e2e else
+                                 'every step: inputs pinned host -> device on a copy stream (one step ahead), result device -> pinned host '
+                                 'behind the step and read on the host one step later (training.ResultPipe); the pipe is drained inside '
+                                 'the timed region')},
             'gpu_launches': int(launches),
             'launch_mode': f'one CUDA graph per step ({int(launches_per_step)} kernel nodes from libmt_b200.so, captured once); '
                            f'eager launch of the same step: {ms_eager:.2f} ms',

@@ -44,23 +44,21 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(int M, const floa
     av[c] = ld4(a + c * 128 + lane * 4);
     bv[c] = ld4(b + c * 128 + lane * 4);
   }
-  // software pipeline: the next row is in flight while this one goes through its two dependent warp reductions
+  // software pipeline: the next TWO rows (d <= 256; one beyond) are in flight while this one goes through its two dependent warp
+  // reductions -- 32 warps per SM with one 1 KB row each are too few bytes for the HBM latency
   const int stride = gridDim.x * LN_WARPS;
-  int row = blockIdx.x * LN_WARPS + warp;
-  float4 nv[NCH];
-  if (row < M) {
+  auto load_row = [&](float4* nv, int row) {
+    if (row < M) {
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) nv[c] = ld4(x + (size_t)row * d + c * 128 + lane * 4);
-  }
-  for (; row < M; row += stride) {
+      for (int c = 0; c < NCH; ++c) nv[c] = ld4(x + (size_t)row * d + c * 128 + lane * 4);
+    }
+  };
+  auto do_row = [&](float4* nv, int row, int next) {
     float4 v[NCH];
     float s = 0.f;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) v[c] = nv[c];
-    if (row + stride < M) {
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) nv[c] = ld4(x + (size_t)(row + stride) * d + c * 128 + lane * 4);
-    }
+    load_row(nv, next);
     if (DRAW) {
       for (uint32_t k = 0; k < cpi && chunk < n_chunks; ++k) draw_chunk();
     }
@@ -85,6 +83,20 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(int M, const floa
       o.w = av[c].w * v[c].w * inv + bv[c].w;
       st4(yr + c * 128 + lane * 4, o);
     }
+  };
+  int row = blockIdx.x * LN_WARPS + warp;
+  constexpr bool DEEP = NCH <= 2;
+  float4 n0[NCH];
+  load_row(n0, row);
+  if (DEEP) {
+    float4 n1[NCH];
+    load_row(n1, row + stride);
+    for (; row < M; row += 2 * stride) {
+      do_row(n0, row, row + 2 * stride);
+      if (row + stride < M) do_row(n1, row + stride, row + 3 * stride);
+    }
+  } else {
+    for (; row < M; row += stride) do_row(n0, row, row + stride);
   }
   if (DRAW) {      // whatever the row loop left (warps without rows, more chunks than row iterations)
     while (chunk < n_chunks) draw_chunk();

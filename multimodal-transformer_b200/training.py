@@ -408,6 +408,37 @@ class GraphedTrainStep:
         return self.replay()
 
 
+class ResultPipe:
+    """Read a step's result (loss, predictions) back to the host WITHOUT draining the stream every step: push(t) enqueues the
+    device -> pinned-host copy of t behind the step that produced it and returns the host copy of the PREVIOUS push (complete by its
+    own event, usually long since), so the host enqueues step k + 1 while step k runs.  drain() returns the last one.  Every step's
+    result still reaches the host, one step late -- what a training loop that logs its losses does (MFT/train.py:143 reads loss.item()
+    for the epoch average only)."""
+
+    def __init__(self, like, device):
+        self.host = [torch.empty(like.shape, dtype=like.dtype).pin_memory() for _ in range(2)]
+        self.done = [torch.cuda.Event(), torch.cuda.Event()]
+        self.device = device
+        self.n = 0
+
+    def push(self, t):
+        k = self.n & 1
+        self.host[k].copy_(t, non_blocking=True)
+        self.done[k].record(torch.cuda.current_stream(self.device))
+        self.n += 1
+        if self.n == 1:
+            return None
+        self.done[k ^ 1].synchronize()
+        return self.host[k ^ 1]
+
+    def drain(self):
+        if self.n == 0:
+            return None
+        k = (self.n - 1) & 1
+        self.done[k].synchronize()
+        return self.host[k]
+
+
 class GraphedForward:
     """eval() forward captured into a CUDA graph for a fixed (B, T); returns the static prediction buffer [B,T,1]."""
 

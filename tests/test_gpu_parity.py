@@ -997,6 +997,25 @@ def test_keep_bits_drawn_inside_the_layernorm_pass_equal_the_draw_kernel():
             assert_close(g_ln[k], g_k[k], 1e-5, k, 1e-9)
 
 
+def test_result_pipe_returns_every_result_one_step_late():
+    """training.ResultPipe: push() hands back the host copy of the previous push, drain() the last one -- every step's result reaches
+    the host, in order, although the producing buffer is overwritten every step (the graph's static loss tensor)."""
+    from multimodal_transformer_b200.training import ResultPipe
+    buf = torch.zeros(3, device=DEV)
+    pipe = ResultPipe(torch.zeros(3), torch.device(DEV))
+    assert pipe.drain() is None
+    seen = []
+    for i in range(7):
+        buf.fill_(float(i))                     # the "step" overwrites its static result buffer
+        r = pipe.push(buf)
+        assert (r is None) == (i == 0)
+        if r is not None:
+            seen.append(r.clone())
+    seen.append(pipe.drain().clone())
+    assert [int(v[0].item()) for v in seen] == list(range(7))
+    assert all(bool((v == v[0]).all()) for v in seen)
+
+
 def test_bf16_gradient_stream_against_the_fp32_stream():
     """mt_tune key 13 carries the residual-stream gradient between the sublayers of a bf16-mode stack in bf16 (ln_bwd_kernel GM = 1 / 2)
     instead of fp32 (opt-in).  Forward identical; every gradient within 1 % of its tensor's scale of the fp32-stream run (bf16 rounding
