@@ -372,8 +372,10 @@ int mt_gemm_tc_mode(int mode);
 /* tuning knobs; returns the previous value (-1: bad key).  key 0 / 1 / 2 = grid share of the tcgen05 GEMM / the T <= 128 attention /
  * the LayerNorm kernels: a share s > 1 launches 1/s of the resident CTA slots, so kernels of concurrent streams (the modality stacks
  * of MultiTransformer) co-reside on the SMs instead of queueing behind each other.  key 3 = programmatic dependent launch of the encoder
- * chain (LayerNorm, tcgen05 GEMMs, tcgen05 attention, keep-bit draw: grid launch and prologue overlap the previous kernel's tail): 0 off,
- * 1 = launches outside stream capture only (default; eager MFT step 7.27 -> 7.05 ms), 2 = always (a captured graph gets 1 % slower).
+ * chain (LayerNorm, tcgen05 GEMMs, tcgen05 attention, keep-bit draw: grid launch and prologue overlap the previous kernel's tail): 0 off
+ * (default), 1 = launches outside stream capture only (eager MFT step 7.27 -> 7.05 ms), 2 = always (a captured graph gets 1 % slower);
+ * EXPERIMENTAL -- with a row-stream GEMM and the attention forward both launched this way the bf16 forward was measured run-to-run
+ * non-deterministic (csrc/mt_common.cuh, tools/fwd_determinism.py); key 14 = bit mask of the kernel families key 3 applies to.
  * key 5 != 0: the encoder's projections skip the weight-resident row-stream engine (A/B against the streaming engine); key 6 != 0: no
  * LayerNorm fused into the FFN output projection's epilogue; key 7 != 0: no 256-row / 256-wide tiles for the L2-bound GEMMs; key 8: debug mask of the
  * MFN recurrence kernels (bit 6: the first-cut kernels, for A/B timing; bit 5: clock trace); key 9 != 0: the tcgen05 attention kernels hash

@@ -114,7 +114,7 @@ const char* mt_last_cuda_error(void) { return g_mt_cuda_err; }
 int mt_version(void) { return 100; }
 
 /* tuning knobs (see include/mt_b200.h: mt_tune) */
-int g_mt_tune[16] = {1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+int g_mt_tune[16] = {1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0xff, 0};
 int mt_tune(int key, int value) {
   if (key < 0 || key >= 16) return -1;
   int old = g_mt_tune[key];

@@ -271,7 +271,10 @@ struct BwdArgs {
   DropCfg drop[MAXG];
 };
 
-constexpr int BWD_NT = 576;                                             // warps 0-15 compute, 16 TMA, 17 MMA issue + TMEM
+constexpr int BWD_NT = 640;                                             // warps 0-15 compute, 16 TMA, 17 MMA issue + TMEM, 18-19 idle (they
+                                                                            // complete the fifth warpgroup for setmaxnreg, second formulation)
+constexpr int BWD1_NT = 576;                                            // first formulation (A/B): 18 warps
+constexpr int BWD_REGS_COMPUTE = 112, BWD_REGS_SPECIAL = 32;               // balanced inside the CTA's own allocation: 20 x 96 = 16 x 112 + 4 x 32
 constexpr int BWD_STAGES = 2;
 constexpr int BWD_AUX_BYTES = 2 * 4 * TM * 4;                           // two heads x four per-query vectors
 constexpr int BWD_BITS_BYTES = 2 * 4 * TM * 4;                          // two heads x 128 keep bits per query (optional)
@@ -354,7 +357,7 @@ __global__ void attn_tc_prep_light_kernel(int B, int Bg, int T, int h, const flo
 //   [128,256) dP^T (fp32)  -> dS^T packed bf16 at [128,160) and [192,224)
 //   accumulators of the second round in the gaps: dV [32,64), dK [96,128), dQ [160,192)
 template <bool FULL>
-__global__ void __launch_bounds__(BWD_NT, 1)      // 18 warps are allocated as 20: 96 registers per thread is the ceiling
+__global__ void __launch_bounds__(BWD1_NT, 1)      // 18 warps are allocated as 20: 96 registers per thread is the ceiling
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do, const __grid_constant__ BwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ float s_cs[4 * 2 * 96];                  // [head pair][w][dQ | dK | dV][32]: bias-gradient column sums of this CTA
@@ -373,7 +376,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int hp_count = a.h >> 1;
   const int T = a.T;
-  for (int i = threadIdx.x; i < 4 * 2 * 96; i += BWD_NT) s_cs[i] = 0.f;
+  for (int i = threadIdx.x; i < 4 * 2 * 96; i += BWD1_NT) s_cs[i] = 0.f;
   if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&map_qkv);
     tma_prefetch_desc(&map_do);
@@ -625,7 +628,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
   }
   if (a.dbias != nullptr) {
     // s_cs[hp][w][k][c] -> dbias[k * d + (2 hp + w) * 32 + c]   (h <= 8: at most 4 head pairs)
-    for (int i = threadIdx.x; i < hp_count * 2 * 96; i += BWD_NT) {
+    for (int i = threadIdx.x; i < hp_count * 2 * 96; i += BWD1_NT) {
       const int hp = i / 192, w = (i / 96) & 1, k = (i % 96) / 32, c = i % 32;
       const float val = s_cs[i];
       if (val != 0.f) atomicAdd(a.dbias + iw.grp * a.dbias_gstride + (size_t)k * a.d + (2 * hp + w) * HD + c, val);
@@ -680,9 +683,13 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
   fence_after();
   const uint32_t tmem_base = *tmem_slot;
   mt_pdl_gate();      // everything above touches no global memory
+  // register re-allocation between the warpgroups: the 16 compute warps are register-starved at the launch ceiling of 96 (20 resident
+  // warps), the TMA / MMA issuing threads need a fraction of that
+  // (the setmaxnreg instructions head the role branches below: the register budget of a region follows the one that dominates it)
   const ItemWalk iw = item_walk(a.G, a.B, hp_count);
   const int n_my = iw.n;
 
+  if (warp >= 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(BWD_REGS_SPECIAL));
   if (warp == 16) {
     // ===== TMA producer =====
     if (lane == 0) {
@@ -749,8 +756,9 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
       }
       if (n_blk > 0) round2(n_blk - 1);
     }
-  } else {
+  } else if (warp < 16) {
     // ===== compute: warp group g owns the queries [32 g, 32 g + 32) of every block, thread = key row j =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(BWD_REGS_COMPUTE));
     const DropCfg drop = mt_drop_resolve(a.drop[iw.grp]);
     const int g = warp >> 2, j = threadIdx.x & 127;
     const uint32_t tl = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
@@ -976,7 +984,7 @@ int mt_attn_tc_dropbits_run(int G, int B, int T, int h, const DropCfg* drops, ui
   const size_t n = mt_attn_tc_dropbits_words(G, B, h);
   mt_prof_work(0.0, (double)n * 4.0);
   const size_t cap = (size_t)num_sms() * 8;
-  MT_CUDA(mt_launch_dep(attn_tc_dropbits_kernel, dim3((unsigned)((n + 255) / 256 < cap ? (n + 255) / 256 : cap)), dim3(256), 0, st, a, bits));
+  MT_CUDA(mt_launch_dep(MT_PDL_MISC, attn_tc_dropbits_kernel, dim3((unsigned)((n + 255) / 256 < cap ? (n + 255) / 256 : cap)), dim3(256), 0, st, a, bits));
   MT_LAUNCH_CHECK();
   return MT_OK;
 }
@@ -999,11 +1007,11 @@ int mt_attn_tc_fwd_run(int B, int T, int d, int h, const void* qkv, const float*
   mt_prof_work(4.0 * G * B * (double)T * T * d, (double)G * B * T * d * 4.0 * 2.0);
   static MtPerDeviceOnce attr_full_b, attr_part_b;
   if (T == TM && !klen) {
-    if (dbits) { MT_TRY(set_smem_attr(attn_tc_fwd_kernel<true, true>, FWD_SMEM, attr_full_b)); MT_CUDA(mt_launch_dep(attn_tc_fwd_kernel<true, true>, dim3(grid), dim3(FWD_NT), FWD_SMEM, st, map, a)); }
-    else { MT_TRY(set_smem_attr(attn_tc_fwd_kernel<true, false>, FWD_SMEM, attr_full)); MT_CUDA(mt_launch_dep(attn_tc_fwd_kernel<true, false>, dim3(grid), dim3(FWD_NT), FWD_SMEM, st, map, a)); }
+    if (dbits) { MT_TRY(set_smem_attr(attn_tc_fwd_kernel<true, true>, FWD_SMEM, attr_full_b)); MT_CUDA(mt_launch_dep(MT_PDL_ATTN_FWD, attn_tc_fwd_kernel<true, true>, dim3(grid), dim3(FWD_NT), FWD_SMEM, st, map, a)); }
+    else { MT_TRY(set_smem_attr(attn_tc_fwd_kernel<true, false>, FWD_SMEM, attr_full)); MT_CUDA(mt_launch_dep(MT_PDL_ATTN_FWD, attn_tc_fwd_kernel<true, false>, dim3(grid), dim3(FWD_NT), FWD_SMEM, st, map, a)); }
   } else {
-    if (dbits) { MT_TRY(set_smem_attr(attn_tc_fwd_kernel<false, true>, FWD_SMEM, attr_part_b)); MT_CUDA(mt_launch_dep(attn_tc_fwd_kernel<false, true>, dim3(grid), dim3(FWD_NT), FWD_SMEM, st, map, a)); }
-    else { MT_TRY(set_smem_attr(attn_tc_fwd_kernel<false, false>, FWD_SMEM, attr_part)); MT_CUDA(mt_launch_dep(attn_tc_fwd_kernel<false, false>, dim3(grid), dim3(FWD_NT), FWD_SMEM, st, map, a)); }
+    if (dbits) { MT_TRY(set_smem_attr(attn_tc_fwd_kernel<false, true>, FWD_SMEM, attr_part_b)); MT_CUDA(mt_launch_dep(MT_PDL_ATTN_FWD, attn_tc_fwd_kernel<false, true>, dim3(grid), dim3(FWD_NT), FWD_SMEM, st, map, a)); }
+    else { MT_TRY(set_smem_attr(attn_tc_fwd_kernel<false, false>, FWD_SMEM, attr_part)); MT_CUDA(mt_launch_dep(MT_PDL_ATTN_FWD, attn_tc_fwd_kernel<false, false>, dim3(grid), dim3(FWD_NT), FWD_SMEM, st, map, a)); }
   }
   MT_LAUNCH_CHECK();
   return MT_OK;
@@ -1019,7 +1027,7 @@ int mt_attn_tc_bwd_run(int B, int T, int d, int h, const void* qkv, const float*
   const float scale = 1.0f / sqrtf((float)HD);
   if (d_ready) {
     const long long n = (long long)G * B * h * T;
-    MT_CUDA(mt_launch_dep(attn_tc_prep_light_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, G * B, B, T, h, lse, mask, aux, scale));
+    MT_CUDA(mt_launch_dep(MT_PDL_MISC, attn_tc_prep_light_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, G * B, B, T, h, lse, mask, aux, scale));
     MT_LAUNCH_CHECK();
   } else {
     const long long rows = (long long)G * B * T;
@@ -1046,19 +1054,19 @@ int mt_attn_tc_bwd_run(int B, int T, int d, int h, const void* qkv, const float*
   if (g_mt_tune[4] == 3) {                    // A/B hook: the first formulation (two heads side by side, P^T / dS^T over S^T / dP^T)
     if (T == TM) {
       MT_TRY(set_smem_attr(attn_tc_bwd_kernel<true>, BWD_SMEM, attr_full));
-      attn_tc_bwd_kernel<true><<<grid, BWD_NT, BWD_SMEM, st>>>(map_qkv, map_do, a);
+      attn_tc_bwd_kernel<true><<<grid, BWD1_NT, BWD_SMEM, st>>>(map_qkv, map_do, a);
     } else {
       MT_TRY(set_smem_attr(attn_tc_bwd_kernel<false>, BWD_SMEM, attr_part));
-      attn_tc_bwd_kernel<false><<<grid, BWD_NT, BWD_SMEM, st>>>(map_qkv, map_do, a);
+      attn_tc_bwd_kernel<false><<<grid, BWD1_NT, BWD_SMEM, st>>>(map_qkv, map_do, a);
     }
   } else if (T == TM) {
     static MtPerDeviceOnce attr2_full_b;
-    if (dbits) { MT_TRY(set_smem_attr(attn_tc_bwd2_kernel<true, true>, BWD_SMEM, attr2_full_b)); MT_CUDA(mt_launch_dep(attn_tc_bwd2_kernel<true, true>, dim3(grid), dim3(BWD_NT), BWD_SMEM, st, map_qkv, map_do, a)); }
-    else { MT_TRY(set_smem_attr(attn_tc_bwd2_kernel<true, false>, BWD_SMEM, attr2_full)); MT_CUDA(mt_launch_dep(attn_tc_bwd2_kernel<true, false>, dim3(grid), dim3(BWD_NT), BWD_SMEM, st, map_qkv, map_do, a)); }
+    if (dbits) { MT_TRY(set_smem_attr(attn_tc_bwd2_kernel<true, true>, BWD_SMEM, attr2_full_b)); MT_CUDA(mt_launch_dep(MT_PDL_ATTN_BWD, attn_tc_bwd2_kernel<true, true>, dim3(grid), dim3(BWD_NT), BWD_SMEM, st, map_qkv, map_do, a)); }
+    else { MT_TRY(set_smem_attr(attn_tc_bwd2_kernel<true, false>, BWD_SMEM, attr2_full)); MT_CUDA(mt_launch_dep(MT_PDL_ATTN_BWD, attn_tc_bwd2_kernel<true, false>, dim3(grid), dim3(BWD_NT), BWD_SMEM, st, map_qkv, map_do, a)); }
   } else {
     static MtPerDeviceOnce attr2_part_b;
-    if (dbits) { MT_TRY(set_smem_attr(attn_tc_bwd2_kernel<false, true>, BWD_SMEM, attr2_part_b)); MT_CUDA(mt_launch_dep(attn_tc_bwd2_kernel<false, true>, dim3(grid), dim3(BWD_NT), BWD_SMEM, st, map_qkv, map_do, a)); }
-    else { MT_TRY(set_smem_attr(attn_tc_bwd2_kernel<false, false>, BWD_SMEM, attr2_part)); MT_CUDA(mt_launch_dep(attn_tc_bwd2_kernel<false, false>, dim3(grid), dim3(BWD_NT), BWD_SMEM, st, map_qkv, map_do, a)); }
+    if (dbits) { MT_TRY(set_smem_attr(attn_tc_bwd2_kernel<false, true>, BWD_SMEM, attr2_part_b)); MT_CUDA(mt_launch_dep(MT_PDL_ATTN_BWD, attn_tc_bwd2_kernel<false, true>, dim3(grid), dim3(BWD_NT), BWD_SMEM, st, map_qkv, map_do, a)); }
+    else { MT_TRY(set_smem_attr(attn_tc_bwd2_kernel<false, false>, BWD_SMEM, attr2_part)); MT_CUDA(mt_launch_dep(MT_PDL_ATTN_BWD, attn_tc_bwd2_kernel<false, false>, dim3(grid), dim3(BWD_NT), BWD_SMEM, st, map_qkv, map_do, a)); }
   }
   MT_LAUNCH_CHECK();
   return MT_OK;

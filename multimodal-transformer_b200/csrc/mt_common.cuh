@@ -46,7 +46,7 @@ int mt_comm_overlap_fire(float* grads, size_t pstride, int G, size_t tail_off, s
 #define MT_TUNE_GEMM_SHARE 0
 #define MT_TUNE_ATTN_SHARE 1
 #define MT_TUNE_LN_SHARE 2
-#define MT_TUNE_PDL 3          // [3] programmatic dependent launch of the encoder-chain kernels (mt_launch_dep below): 0 off, 1 eager launches only (default), 2 always
+#define MT_TUNE_PDL 3          // [3] programmatic dependent launch of the encoder-chain kernels (mt_launch_dep below): 0 off (default), 1 eager launches only, 2 always
 #define MT_TUNE_NO_RS 5        // [5] != 0: the encoder's projections skip the row-stream engine (A/B against the streaming engine)
 #define MT_TUNE_NO_BIG_TILES 7 // [7] != 0: no 256-row / 256-wide tiles for the L2-bound GEMMs (split-K wgrads, long-K dgrad)
 #define MT_TUNE_REC_DEBUG 8    // [8] MFN recurrences: bit 5 clock trace of one CTA, bit 6 first-cut kernels (A/B), bits 0-3 timing experiments of the first cut
@@ -55,6 +55,7 @@ int mt_comm_overlap_fire(float* grads, size_t pstride, int G, size_t tail_off, s
 #define MT_TUNE_LNX 11         // [11] != 0: the output projection fuses the sublayer-1 LayerNorm across a CTA pair (opt-in: measured no faster than the pass)
 #define MT_TUNE_NO_LNDRAW 12   // [12] != 0: the attention keep bits come from the stand-alone draw kernel instead of riding in a LayerNorm forward pass
 #define MT_TUNE_BF16_GSTREAM 13 // [13] != 0: bf16 mode carries the residual-stream gradient between the sublayers in bf16 (opt-in: 12 instead of 16 bytes per element, but measured SLOWER -- the LayerNorm backward is bound by its memory-instruction rate, and 8-byte accesses halve the bytes per instruction)
+#define MT_TUNE_PDL_MASK 14    // [14] kernel families that may launch programmatically (MT_PDL_* bits below; default all)
 #define MT_TUNE_NO_LNFUSE 6    // [6] != 0: no LayerNorm fused into the FFN output projection's epilogue
 
 // one-time-per-DEVICE guard for cudaFuncSetAttribute-style opt-ins (a process may drive several GPUs): true the first time the
@@ -82,10 +83,16 @@ __device__ __forceinline__ void mt_pdl_gate() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
-// MT_TUNE_PDL: 0 = never, 1 (default) = launches outside stream capture only, 2 = always.  Measured on B200 (MFT-VAL train step, 184
-// kernels): eager 7.27 -> 7.05 ms, but the captured graph 6.32 -> 6.38 ms -- a graph's kernel-to-kernel edges already cost less than the
-// programmatic hand-shake, so captured launches stay plain by default.
-static inline int mt_pdl_enabled(cudaStream_t st) {
+// MT_TUNE_PDL: 0 = never (default), 1 = launches outside stream capture only, 2 = always; MT_TUNE_PDL_MASK selects the kernel families.
+// OFF by default, for two measured reasons (B200, MFT-VAL train step, 184 kernels): (a) a captured graph gets slower with it (6.32 ->
+// 6.38 ms: a graph's kernel-to-kernel edges already cost less than the programmatic hand-shake), only the eager step gains (7.27 ->
+// 7.05 ms); (b) tools/fwd_determinism.py found the bf16 train-mode forward at B = 40 run-to-run NON-deterministic (|d pred| up to 3e-2)
+// whenever a row-stream GEMM and the tcgen05 attention forward that follows it BOTH launch programmatically -- each family alone, and
+// every other combination tried, reproduces bit for bit.  Every kernel here executes the gate before its first global access, so the
+// chain should be safe by the documented semantics of griddepcontrol.wait; until that pair is understood the switch is an experiment.
+enum { MT_PDL_LN_FWD = 1, MT_PDL_LN_BWD = 2, MT_PDL_GEMM_RS = 4, MT_PDL_GEMM_TC = 8, MT_PDL_ATTN_FWD = 16, MT_PDL_ATTN_BWD = 32, MT_PDL_MISC = 64 };
+static inline int mt_pdl_enabled(cudaStream_t st, int family) {
+  if ((g_mt_tune[MT_TUNE_PDL_MASK] & family) == 0) return 0;
   const int mode = g_mt_tune[MT_TUNE_PDL];
   if (mode != 1) return mode ? 1 : 0;
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -93,12 +100,12 @@ static inline int mt_pdl_enabled(cudaStream_t st) {
   return cs == cudaStreamCaptureStatusNone ? 1 : 0;
 }
 template <typename... KA, typename... A>
-static inline cudaError_t mt_launch_dep(void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+static inline cudaError_t mt_launch_dep(int family, void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = mt_pdl_enabled(st);
+  at[0].val.programmaticStreamSerializationAllowed = mt_pdl_enabled(st, family);
   cfg.attrs = at; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KA>(args)...);
 }

@@ -447,8 +447,8 @@ int ln_fwd_dispatch(int M, int d, const float* x, const float* a, const float* b
   if (draw) { ba = draw->a; bits = draw->bits; }
 #define MT_LNF(NCH)                                                                                                                      \
   do {                                                                                                                                   \
-    if (draw) MT_CUDA(mt_launch_dep(ln_fwd_kernel<TY, NCH, true>, grid, dim3(LN_WARPS * 32), 0, st, M, x, a, b, eps, y, pstride, ba, bits)); \
-    else MT_CUDA(mt_launch_dep(ln_fwd_kernel<TY, NCH, false>, grid, dim3(LN_WARPS * 32), 0, st, M, x, a, b, eps, y, pstride, ba, bits));     \
+    if (draw) MT_CUDA(mt_launch_dep(MT_PDL_LN_FWD, ln_fwd_kernel<TY, NCH, true>, grid, dim3(LN_WARPS * 32), 0, st, M, x, a, b, eps, y, pstride, ba, bits)); \
+    else MT_CUDA(mt_launch_dep(MT_PDL_LN_FWD, ln_fwd_kernel<TY, NCH, false>, grid, dim3(LN_WARPS * 32), 0, st, M, x, a, b, eps, y, pstride, ba, bits));     \
   } while (0)
   switch (d / 128) {
     case 1: MT_LNF(1); break;
@@ -475,7 +475,7 @@ int ln_bwd_dispatch(int M, int d, const float* x, const float* a, float eps, con
   mt_prof_work(0.0, (double)G * M * d * (4.0 + gx_b + sizeof(TY) + (dres ? gr_b : 0.0) + (NEXT ? sizeof(TY) : 0.0)));
   if (gm != 0 && !std::is_same<TY, bf16>::value) return MT_ERR_ARG;      // a bf16 gradient stream exists in bf16 mode only
 #define MT_LNB_G(NCH, GMV)                                                                                                                \
-  MT_CUDA(mt_launch_dep(ln_bwd_kernel<TY, NCH, NEXT, GMV>, grid, dim3(LN_WARPS * 32), 0, st, M, x, a, eps, dy,                             \
+  MT_CUDA(mt_launch_dep(MT_PDL_LN_BWD, ln_bwd_kernel<TY, NCH, NEXT, GMV>, grid, dim3(LN_WARPS * 32), 0, st, M, x, a, eps, dy,                             \
                         (const typename LnG<GMV>::R*)dres, (typename LnG<GMV>::X*)dx, da, db, nx_out, nx_db, nx_drop, pstride))
 #define MT_LNB(NCH)                                                                          \
   do {                                                                                       \

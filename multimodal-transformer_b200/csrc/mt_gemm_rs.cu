@@ -551,7 +551,7 @@ int launch(const RsDesc& d, cudaStream_t st) {
   cfg.gridDim = dim3((unsigned)(cnt * P)); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = C::TOTAL; cfg.stream = st;
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = mt_pdl_enabled(st);
+  at[0].val.programmaticStreamSerializationAllowed = mt_pdl_enabled(st, MT_PDL_GEMM_RS);
   cfg.attrs = at; cfg.numAttrs = 1;
   if (F & R_LNX) {      // the two column slices of a row tile are adjacent CTAs: one cluster
     if (g.tiles_n != 2) return MT_ERR_UNSUPPORTED;

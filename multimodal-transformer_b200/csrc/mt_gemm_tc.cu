@@ -599,7 +599,7 @@ int launch_inst(const CUtensorMap& ma, const TcMapsB& mb, const TcArgs& g, int g
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Smem<BN, OCC, MT>::THREADS); cfg.dynamicSmemBytes = Smem<BN, OCC, MT>::TOTAL; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = mt_pdl_enabled(st);
+  at[0].val.programmaticStreamSerializationAllowed = mt_pdl_enabled(st, MT_PDL_GEMM_TC);
   cfg.attrs = at; cfg.numAttrs = 1;
   MT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, F, RES, OCC, MT>, ma, mb, g));
   MT_LAUNCH_CHECK();

@@ -687,6 +687,29 @@ def test_mft_train_mode_medium_batch_both_dtypes_same_masks():
                 assert_close(p.grad, want, 4e-2, k, 4e-5 * gmax)
 
 
+def test_bf16_train_mode_forward_is_run_to_run_deterministic():
+    """Same weights, inputs and dropout seed -> bit-identical bf16 train-mode predictions, at the size where several persistent kernels
+    walk many work items (the forward has no atomics).  Guards the launch chain: tools/fwd_determinism.py measured differences up to
+    3e-2 at this size with programmatic dependent launch on a row-stream GEMM + attention-forward pair (mt_tune key 3, off by default)."""
+    N, B, T = 1, 40, 128
+    dims = {'acoustic': 88, 'image': 256, 'linguistic': 300}
+    sd = util.filled_sd(util.mods_shapes('MFT.MultiTransformer', N), 23)
+    inputs, mask, _, lengths = fill.make_batch(B, T, dims, 23)
+    mtb.set_compute_dtype('bf16')
+    try:
+        model = mtb.MultiTransformer(MODS, dims, N=N).to(DEV).train(); model.load_state_dict(sd)
+        x = {k: t(v).to(DEV) for k, v in inputs.items()}; m = t(mask).to(DEV)
+        preds = []
+        for _ in range(6):
+            mtb.fix_seed(4711)
+            with torch.no_grad():
+                preds.append(model(x, m, lengths).float().cpu())
+    finally:
+        mtb.set_compute_dtype('fp32')
+    for p_ in preds[1:]:
+        assert torch.equal(p_, preds[0])
+
+
 def test_bf16_mode_valence_within_2e2_and_ccc():
     from oracle.ccc import eval_ccc
     N, B, T = 6, 6, 40
