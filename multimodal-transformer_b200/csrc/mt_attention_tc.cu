@@ -847,70 +847,83 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
       if (w == 0) mbar_wait(&full[stage], ((uint32_t)it >> 1) & 1u);       // per-query vectors (the MMA warp waits on the same phase for the tiles)
       mbar_wait(s_full, (uint32_t)blk & 1u);
       fence_after();
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
+      // The block's 32 queries go through in two halves of 16 (cc).  The TMEM loads of the second half are issued as soon as the first
+      // half's arithmetic has consumed its registers, so their latency passes under the barrier waits and the P^T / dS^T stores of the
+      // first half instead of in front of the second half's arithmetic.
+      uint32_t s[16], dp[16], pkp[8], pks[8];
+      auto load_half = [&](int cc) {
+        ld16(tl + (uint32_t)(g * 32 + cc * 16), s);
+        ld16(tl + (uint32_t)(128 + g * 32 + cc * 16), dp);
+      };
+      auto math_half = [&](int cc) {
         const int q0 = g * 32 + cc * 16;
-        uint32_t s[16], dp[16], pkp[8], pks[8];
-        ld16(tl + (uint32_t)q0, s);
-        ld16(tl + (uint32_t)(128 + q0), dp);
-        ld_wait();
-        if (cc == 1) { fence_before(); mbar_arrive(s_free); }      // this thread's last read of S^T / dP^T
 #pragma unroll
         for (int e = 0; e < 16; e += 4) {
-          const int q = q0 + e;
-          const float4 L = *reinterpret_cast<const float4*>(ax + q), D = *reinterpret_cast<const float4*>(ax + TM + q);
-          const float4 rs = *reinterpret_cast<const float4*>(ax + 2 * TM + q), gs = *reinterpret_cast<const float4*>(ax + 3 * TM + q);
-          const float Dk[4] = {D.x, D.y, D.z, D.w};
-          float p[4], t[4];
-          upk2(fma2(pk2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), pk2(rs.x, rs.y), pk2(-L.x, -L.y)), p[0], p[1]);
-          upk2(fma2(pk2(__uint_as_float(s[e + 2]), __uint_as_float(s[e + 3])), pk2(rs.z, rs.w), pk2(-L.z, -L.w)), p[2], p[3]);
+            const int q = q0 + e;
+            const float4 L = *reinterpret_cast<const float4*>(ax + q), D = *reinterpret_cast<const float4*>(ax + TM + q);
+            const float4 rs = *reinterpret_cast<const float4*>(ax + 2 * TM + q), gs = *reinterpret_cast<const float4*>(ax + 3 * TM + q);
+            const float Dk[4] = {D.x, D.y, D.z, D.w};
+            float p[4], t[4];
+            upk2(fma2(pk2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), pk2(rs.x, rs.y), pk2(-L.x, -L.y)), p[0], p[1]);
+            upk2(fma2(pk2(__uint_as_float(s[e + 2]), __uint_as_float(s[e + 3])), pk2(rs.z, rs.w), pk2(-L.z, -L.w)), p[2], p[3]);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) p[k] = (key_ok && (FULL || q + k < T)) ? ex2(p[k]) : 0.f;
-          // t = dP . keep-scale - D ; without a kept draw the probability's gradient is -D
-          upk2(fma2(pk2(__uint_as_float(dp[e]), __uint_as_float(dp[e + 1])), ds2, pk2(-D.x, -D.y)), t[0], t[1]);
-          upk2(fma2(pk2(__uint_as_float(dp[e + 2]), __uint_as_float(dp[e + 3])), ds2, pk2(-D.z, -D.w)), t[2], t[3]);
-          float pd[4] = {p[0], p[1], p[2], p[3]};
-          if (BITS || dropping) {           // keep bits exist only when the launch drops: no run-time branch around their loads
-            if (BITS) {
-              const uint4 kw = *reinterpret_cast<const uint4*>(kbits + q);
-              const uint32_t kq[4] = {kw.x, kw.y, kw.z, kw.w};
+            for (int k = 0; k < 4; ++k) p[k] = (key_ok && (FULL || q + k < T)) ? ex2(p[k]) : 0.f;
+            // t = dP . keep-scale - D ; without a kept draw the probability's gradient is -D
+            upk2(fma2(pk2(__uint_as_float(dp[e]), __uint_as_float(dp[e + 1])), ds2, pk2(-D.x, -D.y)), t[0], t[1]);
+            upk2(fma2(pk2(__uint_as_float(dp[e + 2]), __uint_as_float(dp[e + 3])), ds2, pk2(-D.z, -D.w)), t[2], t[3]);
+            float pd[4] = {p[0], p[1], p[2], p[3]};
+            if (BITS || dropping) {           // keep bits exist only when the launch drops: no run-time branch around their loads
+              if (BITS) {
+                const uint4 kw = *reinterpret_cast<const uint4*>(kbits + q);
+                const uint32_t kq[4] = {kw.x, kw.y, kw.z, kw.w};
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const bool keep = (kq[k] & kbit) != 0u;
-                pd[k] = keep ? p[k] : 0.f;
-                t[k] = keep ? t[k] : -Dk[k];
-              }
-            } else {
+                for (int k = 0; k < 4; ++k) {
+                  const bool keep = (kq[k] & kbit) != 0u;
+                  pd[k] = keep ? p[k] : 0.f;
+                  t[k] = keep ? t[k] : -Dk[k];
+                }
+              } else {
 #pragma unroll
-              for (int k = 0; k < 4; k += 2) {
-                const uint32_t mine = mt_mix32((pidx0 + (uint32_t)(cc * 16 + e + k) * P2) ^ drop.key);
-                const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
-                const uint32_t b0 = odd ? other : mine, b1 = odd ? mine : other;
-                const bool k0 = odd ? (b0 >= thr_hi) : ((b0 << 16) >= thr_hi), k1 = odd ? (b1 >= thr_hi) : ((b1 << 16) >= thr_hi);
-                pd[k] = k0 ? p[k] : 0.f;
-                t[k] = k0 ? t[k] : -Dk[k];
-                pd[k + 1] = k1 ? p[k + 1] : 0.f;
-                t[k + 1] = k1 ? t[k + 1] : -Dk[k + 1];
+                for (int k = 0; k < 4; k += 2) {
+                  const uint32_t mine = mt_mix32((pidx0 + (uint32_t)(cc * 16 + e + k) * P2) ^ drop.key);
+                  const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+                  const uint32_t b0 = odd ? other : mine, b1 = odd ? mine : other;
+                  const bool k0 = odd ? (b0 >= thr_hi) : ((b0 << 16) >= thr_hi), k1 = odd ? (b1 >= thr_hi) : ((b1 << 16) >= thr_hi);
+                  pd[k] = k0 ? p[k] : 0.f;
+                  t[k] = k0 ? t[k] : -Dk[k];
+                  pd[k + 1] = k1 ? p[k + 1] : 0.f;
+                  t[k + 1] = k1 ? t[k + 1] : -Dk[k + 1];
+                }
               }
             }
+            float ev[4];
+            upk2(mul2(mul2(pk2(p[0], p[1]), pk2(gs.x, gs.y)), pk2(t[0], t[1])), ev[0], ev[1]);
+            upk2(mul2(mul2(pk2(p[2], p[3]), pk2(gs.z, gs.w)), pk2(t[2], t[3])), ev[2], ev[3]);
+            pkp[e >> 1] = pack_bf2(pd[0], pd[1]);
+            pkp[(e >> 1) + 1] = pack_bf2(pd[2], pd[3]);
+            pks[e >> 1] = pack_bf2(ev[0], ev[1]);
+            pks[(e >> 1) + 1] = pack_bf2(ev[2], ev[3]);
           }
-          float ev[4];
-          upk2(mul2(mul2(pk2(p[0], p[1]), pk2(gs.x, gs.y)), pk2(t[0], t[1])), ev[0], ev[1]);
-          upk2(mul2(mul2(pk2(p[2], p[3]), pk2(gs.z, gs.w)), pk2(t[2], t[3])), ev[2], ev[3]);
-          pkp[e >> 1] = pack_bf2(pd[0], pd[1]);
-          pkp[(e >> 1) + 1] = pack_bf2(pd[2], pd[3]);
-          pks[e >> 1] = pack_bf2(ev[0], ev[1]);
-          pks[(e >> 1) + 1] = pack_bf2(ev[2], ev[3]);
-        }
-        if (cc == 0) {      // first writes of the block: the previous block's dV MMAs have read P^T, the dK / dQ MMAs of block blk - 2 this dS^T buffer
-          if (blk > 0) mbar_wait(pt_free, (uint32_t)(blk - 1) & 1u);
-          if (blk > 1) mbar_wait(&ds_free[blk & 1], (uint32_t)((blk >> 1) - 1) & 1u);
-          fence_after();
-        }
+      };
+      auto store_half = [&](int cc) {
         st8(tl + (uint32_t)(256 + g * 16 + cc * 8), pkp);
         *reinterpret_cast<uint4*>(dsb + sw128_off(j, (g & 1) * 4 + cc * 2)) = make_uint4(pks[0], pks[1], pks[2], pks[3]);
         *reinterpret_cast<uint4*>(dsb + sw128_off(j, (g & 1) * 4 + cc * 2 + 1)) = make_uint4(pks[4], pks[5], pks[6], pks[7]);
-      }
+      };
+      load_half(0);
+      ld_wait();
+      math_half(0);
+      load_half(1);
+      // first writes of the block: the previous block's dV MMAs have read P^T, the dK / dQ MMAs of block blk - 2 this dS^T buffer
+      if (blk > 0) mbar_wait(pt_free, (uint32_t)(blk - 1) & 1u);
+      if (blk > 1) mbar_wait(&ds_free[blk & 1], (uint32_t)((blk >> 1) - 1) & 1u);
+      fence_after();
+      store_half(0);
+      ld_wait();
+      fence_before();
+      mbar_arrive(s_free);      // this thread's last read of S^T / dP^T
+      math_half(1);
+      store_half(1);
       st_wait();
       fence_proxy_async();
       fence_before();
