@@ -48,6 +48,7 @@ struct FwdArgs {
   const int* klen;
   const uint32_t* dbits;   // optional precomputed keep bits (attn_tc_dropbits_kernel): [G*B][h][4][128] words, bit i of word (c, q) = key 32 c + i of query q
   DropCfg drop[MAXG];
+  int early_trigger;       // programmatic launch: let the next kernel be scheduled as soon as this grid is resident (mt_tune 15 bit 0 clears it)
 };
 struct ItemWalk {          // items of this CTA: global item = base + it * step, it < n
   int grp, base, step, n;
@@ -96,7 +97,8 @@ __global__ void __launch_bounds__(FWD_NT, 2) attn_tc_fwd_kernel(const __grid_con
   __syncthreads();
   fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  mt_pdl_gate();      // everything above touches no global memory
+  mt_pdl_wait();      // everything above touches no global memory
+  if (a.early_trigger) mt_pdl_trigger();
 
   if (warp == 8) {
     // ===== TMA producer: Q | K | V boxes of the item's head pair =====
@@ -1012,6 +1014,7 @@ int mt_attn_tc_fwd_run(int B, int T, int d, int h, const void* qkv, const float*
   a.B = B; a.T = T; a.d = d; a.h = h; a.G = G;
   a.scale_log2 = LOG2E / sqrtf((float)HD);
   a.mask = mask; a.out = (bf16*)out; a.lse = lse; a.klen = klen; a.dbits = dbits;
+  a.early_trigger = (g_mt_tune[15] & 1) ? 0 : 1;
   for (int i = 0; i < MAXG; ++i) a.drop[i] = drops && i < G ? drops[i] : drop;
   static MtPerDeviceOnce attr_full, attr_part;
   const int slots = 2 * num_sms(), n_items = B * (h / 2);

@@ -56,6 +56,7 @@ int mt_comm_overlap_fire(float* grads, size_t pstride, int G, size_t tail_off, s
 #define MT_TUNE_NO_LNDRAW 12   // [12] != 0: the attention keep bits come from the stand-alone draw kernel instead of riding in a LayerNorm forward pass
 #define MT_TUNE_BF16_GSTREAM 13 // [13] != 0: bf16 mode carries the residual-stream gradient between the sublayers in bf16 (opt-in: 12 instead of 16 bytes per element, but measured SLOWER -- the LayerNorm backward is bound by its memory-instruction rate, and 8-byte accesses halve the bytes per instruction)
 #define MT_TUNE_PDL_MASK 14    // [14] kernel families that may launch programmatically (MT_PDL_* bits below; default all)
+#define MT_TUNE_PDL_DEBUG 15   // [15] bit 0: the attention forward does not trigger its dependents early (bisecting aid, see mt_pdl_enabled)
 #define MT_TUNE_NO_LNFUSE 6    // [6] != 0: no LayerNorm fused into the FFN output projection's epilogue
 
 // one-time-per-DEVICE guard for cudaFuncSetAttribute-style opt-ins (a process may drive several GPUs): true the first time the
@@ -79,6 +80,8 @@ static inline size_t mt_align_up(size_t x, size_t a) { return (x + a - 1) / a * 
 // mt_pdl_gate() sits in front of its FIRST global-memory access (read or write): it waits until the previous kernel has completed and
 // flushed, then lets the next kernel of the stream be scheduled.  Gate after wait keeps the look-ahead at exactly one kernel.  Kernels
 // launched with plain <<< >>> serialise fully on both sides, so the two kinds mix freely.
+__device__ __forceinline__ void mt_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void mt_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void mt_pdl_gate() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -87,9 +90,12 @@ __device__ __forceinline__ void mt_pdl_gate() {
 // OFF by default, for two measured reasons (B200, MFT-VAL train step, 184 kernels): (a) a captured graph gets slower with it (6.32 ->
 // 6.38 ms: a graph's kernel-to-kernel edges already cost less than the programmatic hand-shake), only the eager step gains (7.27 ->
 // 7.05 ms); (b) tools/fwd_determinism.py found the bf16 train-mode forward at B = 40 run-to-run NON-deterministic (|d pred| up to 3e-2)
-// whenever a row-stream GEMM and the tcgen05 attention forward that follows it BOTH launch programmatically -- each family alone, and
-// every other combination tried, reproduces bit for bit.  Every kernel here executes the gate before its first global access, so the
-// chain should be safe by the documented semantics of griddepcontrol.wait; until that pair is understood the switch is an experiment.
+// whenever the tcgen05 attention forward AND the output-projection GEMM behind it both launch programmatically -- each family alone, and
+// every other combination tried, reproduces bit for bit.  Bisected further: launching only that GEMM shape plainly, or letting the
+// attention forward NOT trigger early (mt_tune(15, 1): its dependents launch at its completion), restores determinism; a proxy fence
+// behind the wait, a 20 us sleep behind the GEMM's gate and a 20 us sleep in front of the attention's exit do not.  Every kernel here
+// executes the gate before its first global access, so the chain should be safe by the documented semantics of griddepcontrol.wait;
+// until that pair is understood the switch is an experiment.
 enum { MT_PDL_LN_FWD = 1, MT_PDL_LN_BWD = 2, MT_PDL_GEMM_RS = 4, MT_PDL_GEMM_TC = 8, MT_PDL_ATTN_FWD = 16, MT_PDL_ATTN_BWD = 32, MT_PDL_MISC = 64 };
 static inline int mt_pdl_enabled(cudaStream_t st, int family) {
   if ((g_mt_tune[MT_TUNE_PDL_MASK] & family) == 0) return 0;

@@ -20,6 +20,8 @@ for N, B, T in ((1, 40, 128), (2, 9, 128)):
     fam = {'ln_fwd': 1, 'ln_bwd': 2, 'gemm_rs': 4, 'gemm_tc': 8, 'attn_fwd': 16, 'attn_bwd': 32, 'misc': 64}
     presets += [(f'PDL only {k}', {14: v}) for k, v in fam.items()]
     presets += [(f'PDL all but {k}', {14: 0xff ^ v}) for k, v in fam.items() if k in ('ln_fwd', 'gemm_rs', 'attn_fwd')]
+    presets += [('PDL, attn fwd never triggers early', {15: 1})]
+    presets = [(n_, {**{3: 1}, **t_}) if n_ not in ('no PDL',) else (n_, t_) for n_, t_ in presets]      # the default is off: switch it on
     if N != 1:
         presets = presets[:2]
     for name, tune in presets:
