@@ -7,6 +7,12 @@
 namespace {
 
 constexpr int LN_WARPS = 8;
+// sqrt.approx.f32: maximum relative error 2^-23, no slow-path call (the IEEE sqrtf's range check + subroutine are ~12 instructions a row)
+__device__ __forceinline__ float ln_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 
 // ------------------------------------------------------------------------------------------------------
 // LayerNorm forward: one warp per row, NCH float4 chunks per lane (d = NCH * 128).
@@ -71,8 +77,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(int M, const floa
       v[c].x -= mean; v[c].y -= mean; v[c].z -= mean; v[c].w -= mean;
       q += (v[c].x * v[c].x + v[c].y * v[c].y) + (v[c].z * v[c].z + v[c].w * v[c].w);
     }
-    const float sd = sqrtf(warp_sum(q) * (1.0f / (d - 1)));
-    const float inv = 1.0f / (sd + eps);
+    const float sd = ln_sqrt(warp_sum(q) * (1.0f / (d - 1)));
+    const float inv = __fdividef(1.0f, sd + eps);      // 2 ulp: the IEEE division's slow path is ~15 of the row's instructions
     TY* yr = y + (size_t)row * d;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
@@ -178,8 +184,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(int M, const floa
       v[c].x -= mean; v[c].y -= mean; v[c].z -= mean; v[c].w -= mean;
       q += (v[c].x * v[c].x + v[c].y * v[c].y) + (v[c].z * v[c].z + v[c].w * v[c].w);
     }
-    const float sd = sqrtf(warp_sum(q) * (1.0f / (d - 1)));
-    const float inv = 1.0f / (sd + eps);
+    const float sd = ln_sqrt(warp_sum(q) * (1.0f / (d - 1)));
+    const float inv = __fdividef(1.0f, sd + eps);      // 2 ulp: the IEEE division's slow path is ~15 of the row's instructions
     float gs = 0.f, dot = 0.f;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
@@ -193,7 +199,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(int M, const floa
     }
     const float gm = warp_sum(gs) * (1.0f / d);
     dot = warp_sum(dot);
-    const float k = dot / ((float)(d - 1) * sd * (sd + eps));
+    const float k = __fdividef(dot, (float)(d - 1) * sd * (sd + eps));
     typename LnG<GM>::X* dxr = dx + (size_t)row * d;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
