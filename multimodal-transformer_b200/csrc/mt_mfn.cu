@@ -23,6 +23,7 @@
 // FMAs.  Stash row order follows the inputs: row(b,t) = b*sb + t*st with (sb,st) = (T,1) for [B,T,D] inputs and
 // (1,B) for the reference's permuted [T,B,D] views.  ST is the GEMM operand type (float / bf16): tensors that only
 // feed GEMMs are kept in ST, recurrent state and everything entering a transcendental stays fp32.
+#include <algorithm>
 #include "mt_recurrent.cuh"
 #include "mt_mfn.cuh"
 
@@ -695,6 +696,46 @@ __global__ void __launch_bounds__(256) mfn_head_fwd_kernel(int B, int T, long lo
   }
 }
 
+// The same with LPR = O / 4 lanes per row (O = 32 / 64 / 128): 16-byte loads of pre, 32 / LPR rows per warp instruction, the dot product
+// closed by a butterfly inside the row's lane group (the one-row-per-warp kernel above moves 64-256 bytes per warp instruction).
+template <typename ST, int LPR>
+__global__ void __launch_bounds__(256) mfn_head_fwd_vec_kernel(int B, int T, long long sb, long long st, const float* __restrict__ pre,
+                                                                const float* __restrict__ w2, const float* __restrict__ b2,
+                                                                const float* __restrict__ mask, DropCfg drop_in, ST* __restrict__ oh,
+                                                                float* __restrict__ out) {
+  constexpr int O = 4 * LPR, RPW = 32 / LPR;
+  const DropCfg drop = mt_drop_resolve(drop_in);
+  const int lane = threadIdx.x & 31, sub = lane % LPR, rsub = lane / LPR;
+  const float4 w = ld4(w2 + sub * 4);
+  const float bias = b2[0];
+  const long long total = (long long)B * T;
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5) * RPW;
+  for (long long i0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW; i0 < total; i0 += wstride) {      // warp-uniform trip count
+    const long long i = i0 + rsub;
+    const bool ok = i < total;
+    float acc = 0.f;
+    if (ok) {
+      const int b = (int)(i / T), t = (int)(i - (long long)b * T);
+      const long long row = (long long)b * sb + (long long)t * st;
+      float4 v = ld4(pre + row * O + sub * 4);
+      const uint64_t e0 = ((uint64_t)t * B + (uint64_t)b) * (uint64_t)O + (uint64_t)(sub * 4);      // [T,B,O] element index (even)
+      float f0, f1, f2, f3;
+      mt_drop_pair(drop, e0, f0, f1);
+      mt_drop_pair(drop, e0 + 2, f2, f3);
+      v.x *= f0; v.y *= f1; v.z *= f2; v.w *= f3;
+      if (oh) st4(oh + row * O + sub * 4, v);
+      acc = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, v.w * w.w)));
+    }
+#pragma unroll
+    for (int m = LPR / 2; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+    if (ok && sub == 0) {
+      float y = acc + bias;
+      if (mask) y *= mask[i];
+      out[i] = y;
+    }
+  }
+}
+
 // dzoh = (oh > 0) * dy * w2 * keep_scale; dW_o2 += sum dy * oh; db_o2 += sum dy   (dy = dout * mask)
 template <typename ST>
 __global__ void __launch_bounds__(256) mfn_head_bwd_kernel(int B, int T, long long sb, long long st, int O, const float* __restrict__ dout,
@@ -987,8 +1028,16 @@ int mt_mfn_fwd(const MtMfnCfg* cfg, const float* params, const void* params_lp, 
     const int wpb = 8;
     const DropCfg dr = mt_make_drop(c.p_out, c.seed, MT_SITE_MFN_OUT);
     mt_prof_work(0.0, (double)M * D.O * (4.0 + wsz));
-    if (lp) mfn_head_fwd_kernel<bf16><<<(M + wpb - 1) / wpb, wpb * 32, 0, st>>>(c.B, c.T, sb, stt, D.O, S.pre, params + D.out_fc2.w, params + D.out_fc2.b, mask, dr, (bf16*)S.oh_op, out);
+#define MT_HEADF(ST_, LPR_) mfn_head_fwd_vec_kernel<ST_, LPR_><<<gridv, 256, 0, st>>>(c.B, c.T, sb, stt, S.pre, params + D.out_fc2.w, params + D.out_fc2.b, mask, dr, (ST_*)S.oh_op, out)
+    const bool vec_ok = (D.O == 32 || D.O == 64 || D.O == 128) && (((uintptr_t)S.pre | (uintptr_t)S.oh_op | (uintptr_t)(params + D.out_fc2.w)) & 15) == 0;
+    if (vec_ok) {
+      const int rpw = 128 / D.O, rows_per_cta = 8 * rpw;
+      const int gridv = (int)std::min<long long>(((long long)M + rows_per_cta - 1) / rows_per_cta, 148 * 8);
+      if (lp) { if (D.O == 32) MT_HEADF(bf16, 8); else if (D.O == 64) MT_HEADF(bf16, 16); else MT_HEADF(bf16, 32); }
+      else { if (D.O == 32) MT_HEADF(float, 8); else if (D.O == 64) MT_HEADF(float, 16); else MT_HEADF(float, 32); }
+    } else if (lp) mfn_head_fwd_kernel<bf16><<<(M + wpb - 1) / wpb, wpb * 32, 0, st>>>(c.B, c.T, sb, stt, D.O, S.pre, params + D.out_fc2.w, params + D.out_fc2.b, mask, dr, (bf16*)S.oh_op, out);
     else mfn_head_fwd_kernel<float><<<(M + wpb - 1) / wpb, wpb * 32, 0, st>>>(c.B, c.T, sb, stt, D.O, S.pre, params + D.out_fc2.w, params + D.out_fc2.b, mask, dr, (float*)S.oh_op, out);
+#undef MT_HEADF
     MT_LAUNCH_CHECK();
   }
   return MT_OK;
