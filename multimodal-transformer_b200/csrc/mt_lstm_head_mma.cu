@@ -228,6 +228,11 @@ int launch_cluster(const ClArgs& a, cudaStream_t st) {
   static MtPerDeviceOnce once;
   if (once.first()) MT_CUDA(cudaFuncSetAttribute(head_fwd_cluster_kernel<NTL, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int clusters = (a.B + NB - 1) / NB;
+  // algorithmic work of the recurrence: one [4E x E] mat-vec per narrative and step; per (narrative, step) the pre-projected gates come
+  // in (4E fp32) and h_t goes out (E bf16), plus the training stash (gates back out and four E-wide fp32 states).  A latency chain of T
+  // dependent steps: neither figure is a roof it could reach.
+  mt_prof_work(2.0 * a.B * (double)a.T * 4.0 * EH * EH,
+               (double)a.B * a.T * (4.0 * EH * 4.0 + EH * 2.0 + (TRAIN ? 4.0 * EH * 4.0 + 4.0 * EH * 4.0 : 0.0)));
   head_fwd_cluster_kernel<NTL, TRAIN><<<clusters * CL, (NWC + 1) * 32, smem, st>>>(a);
   MT_LAUNCH_CHECK();
   return MT_OK;
