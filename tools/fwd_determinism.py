@@ -1,5 +1,8 @@
 """Run-to-run determinism of the bf16 train-mode MFT forward (same seed, same masks) under mt_tune presets: prints, per preset, the largest
-difference between repeated forwards and the first one.  Usage: python tools/fwd_determinism.py [reps]   (GPU box)"""
+difference between repeated forwards and the first one.  Every preset except 'no PDL' switches programmatic dependent launch ON (mt_tune
+key 3 = 1; the library default is off) and then narrows it by kernel family (key 14) or removes the attention forward's early trigger
+(key 15) -- this is the tool that bisected the launch race described in csrc/mt_common.cuh.
+Usage: python tools/fwd_determinism.py [reps]   (GPU box)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -16,7 +19,7 @@ t = torch.from_numpy
 for N, B, T in ((1, 40, 128), (2, 9, 128)):
     sd = util.filled_sd(util.mods_shapes('MFT.MultiTransformer', N), 23)
     inputs, mask, target, lengths = fill.make_batch(B, T, dims, 23)
-    presets = [('default', {}), ('no PDL', {3: 0})]
+    presets = [('PDL, every family', {}), ('no PDL', {3: 0})]
     fam = {'ln_fwd': 1, 'ln_bwd': 2, 'gemm_rs': 4, 'gemm_tc': 8, 'attn_fwd': 16, 'attn_bwd': 32, 'misc': 64}
     presets += [(f'PDL only {k}', {14: v}) for k, v in fam.items()]
     presets += [(f'PDL all but {k}', {14: 0xff ^ v}) for k, v in fam.items() if k in ('ln_fwd', 'gemm_rs', 'attn_fwd')]
