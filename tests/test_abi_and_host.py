@@ -130,3 +130,56 @@ def test_encoder_rejects_unsupported_shapes_at_construction():
     with pytest.raises(NotImplementedError):
         mtb.Encoder(mtb.EncoderLayer(16, mtb.MultiHeadedAttention(8, 16), mtb.PositionwiseFeedForward(16, 128), 0.1), 2)
     mtb.MFN(['emotient', 'linguistic'], {'emotient': 16, 'linguistic': 256}, 1)      # the MFN alone takes it
+
+
+def _load_bench():
+    import importlib.util
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('mt_bench_module', os.path.join(root, 'bench.py'))
+    mod = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ['bench.py']
+    try:
+        spec.loader.exec_module(mod)
+    finally:
+        sys.argv = argv
+    return mod
+
+
+def test_bench_clock_summary_merges_nvml_and_nvidia_smi_samples():
+    """bench.py's ClockSampler: NVML samples (10 ms) and nvidia-smi rows (200 ms) land in one record -- median SM clock over both,
+    throttle reasons from either source (NVML bit masks of nvmlClocksEventReason*), counts per source; no sampler at all is said so."""
+    b = _load_bench()
+    cs = b.ClockSampler(0)
+    cs.nvml_rows = [(1965.0, 0), (1965.0, 0x4), (1950.0, 0)]          # one sample under sw_power_cap
+    cs.nvml_max = 1965.0
+    out = cs._summary([1965.0], [1965.0], set())
+    assert out['samples'] == 4 and out['samples_nvml'] == 3 and out['samples_nvidia_smi'] == 1
+    assert out['sm_mhz'] == 1965.0 and out['sm_max_mhz'] == 1965.0
+    assert out['reasons'] == ['sw_power_cap']
+    cs.nvml_rows = [(1200.0, 0x40 | 0x8)]
+    out = cs._summary([], [], {'sw_thermal_slowdown'})
+    assert out['reasons'] == ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown'] and out['sm_mhz'] == 1200.0
+    cs2 = b.ClockSampler(0)
+    cs2.start()                                                        # no GPU here: neither NVML nor nvidia-smi
+    rec = cs2.stop()
+    assert rec['sm_mhz'] is None or rec.get('samples', 0) >= 0
+
+
+def test_bench_parses_its_contract_flags():
+    """`python bench.py --gpus N --steps K --warmup W [--impl reference]` is the driver's contract; defaults are N = 1 and a K / W that
+    finish within minutes; --sync-e2e keeps the drain-every-step e2e measurement available."""
+    import sys
+    b = _load_bench()
+    argv, sys.argv = sys.argv, ['bench.py', '--gpus', '2', '--steps', '7', '--warmup', '4', '--impl', 'reference', '--sync-e2e']
+    try:
+        a = b.parse()
+    finally:
+        sys.argv = argv
+    assert (a.gpus, a.steps, a.warmup, a.impl, a.sync_e2e) == (2, 7, 4, 'reference', True)
+    argv, sys.argv = sys.argv, ['bench.py']
+    try:
+        d = b.parse()
+    finally:
+        sys.argv = argv
+    assert d.gpus == 1 and d.impl == 'ours' and d.config == 'c2' and d.steps <= 50 and d.warmup >= 3 and not d.sync_e2e
