@@ -376,7 +376,8 @@ int mt_gemm_tc_mode(int mode);
  * (default), 1 = launches outside stream capture only (eager MFT step 7.27 -> 7.05 ms), 2 = always (a captured graph gets 1 % slower);
  * EXPERIMENTAL -- with a row-stream GEMM and the attention forward both launched this way the bf16 forward was measured run-to-run
  * non-deterministic (csrc/mt_common.cuh, tools/fwd_determinism.py); key 14 = bit mask of the kernel families key 3 applies to; key 15 bit 0: the attention forward does not
- * trigger its dependents early (with it the chain was measured deterministic again).
+ * trigger its dependents early (with it the chain was measured deterministic again); key 15 bit 1: the attention backward keeps its light
+ * preparation launch (A/B; by default the output projection's input-gradient GEMM writes all four per-query scalars from its epilogue).
  * key 5 != 0: the encoder's projections skip the weight-resident row-stream engine (A/B against the streaming engine); key 6 != 0: no
  * LayerNorm fused into the FFN output projection's epilogue; key 7 != 0: no 256-row / 256-wide tiles for the L2-bound GEMMs; key 8: debug mask of the
  * MFN recurrence kernels (bit 6: the first-cut kernels, for A/B timing; bit 5: clock trace); key 9 != 0: the tcgen05 attention kernels hash

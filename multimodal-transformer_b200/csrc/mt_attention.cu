@@ -362,7 +362,7 @@ bool mt_attn_group_bwd_uses_tc(int dtype, int G, int B, int T_, int d, int h, co
 
 int mt_attn_group_bwd_run(int dtype, int G, int B, int T_, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse,
                           const void* dout, void* dqkv, const DropCfg* drops, float* Dws, cudaStream_t st, float* dbias, size_t dbias_gstride,
-                          bool d_ready, const uint32_t* dbits) {
+                          int d_ready, const uint32_t* dbits) {
   MT_TRY(check_shape(B, T_, d, h));
   if (!qkv || !out || !lse || !dout || !dqkv || !Dws || G < 1 || G > 4) return MT_ERR_ARG;
   if ((G > 1 || d_ready || dbits) && mt_attn_group_bwd_uses_tc(dtype, G, B, T_, d, h, qkv, out, dout, dqkv, Dws, dbias)) {

@@ -1035,13 +1035,15 @@ int mt_attn_tc_fwd_run(int B, int T, int d, int h, const void* qkv, const float*
 
 int mt_attn_tc_bwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse, const void* dout,
                        void* dqkv, DropCfg drop, float* dbias, float* aux, cudaStream_t st, int G, const DropCfg* drops, size_t dbias_gstride,
-                       bool d_ready, const uint32_t* dbits) {
+                       int d_ready, const uint32_t* dbits) {
   if (!mt_attn_tc_supported(B, T, d, h) || G < 1 || G > MAXG || (long long)G * B * T > 0x7fffffffLL / (3LL * d)) return MT_ERR_UNSUPPORTED;
   if (dbias != nullptr && h > 8) return MT_ERR_UNSUPPORTED;
   if (!aux || ((uintptr_t)aux & 15) || ((uintptr_t)qkv & 15) || ((uintptr_t)dout & 15) || ((uintptr_t)dqkv & 15) || ((uintptr_t)out & 15))
     return MT_ERR_ALIGN;
   const float scale = 1.0f / sqrtf((float)HD);
-  if (d_ready) {
+  if (d_ready == 2) {
+    // all four rows of the per-query scalars are the caller's (mt_gemm_rs.cu R_ATTD with attd_lse): no preparation launch
+  } else if (d_ready) {
     const long long n = (long long)G * B * h * T;
     MT_CUDA(mt_launch_dep(MT_PDL_MISC, attn_tc_prep_light_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, G * B, B, T, h, lse, mask, aux, scale));
     MT_LAUNCH_CHECK();

@@ -56,7 +56,7 @@ int mt_comm_overlap_fire(float* grads, size_t pstride, int G, size_t tail_off, s
 #define MT_TUNE_NO_LNDRAW 12   // [12] != 0: the attention keep bits come from the stand-alone draw kernel instead of riding in a LayerNorm forward pass
 #define MT_TUNE_BF16_GSTREAM 13 // [13] != 0: bf16 mode carries the residual-stream gradient between the sublayers in bf16 (opt-in: 12 instead of 16 bytes per element, but measured SLOWER -- the LayerNorm backward is bound by its memory-instruction rate, and 8-byte accesses halve the bytes per instruction)
 #define MT_TUNE_PDL_MASK 14    // [14] kernel families that may launch programmatically (MT_PDL_* bits below; default all)
-#define MT_TUNE_PDL_DEBUG 15   // [15] bit 0: the attention forward does not trigger its dependents early (bisecting aid, see mt_pdl_enabled)
+#define MT_TUNE_PDL_DEBUG 15   // [15] bit 0: the attention forward does not trigger its dependents early (bisecting aid, see mt_pdl_enabled); bit 1: the attention backward keeps its light preparation launch (A/B: by default the output projection's input-gradient GEMM writes all four per-query scalars)
 #define MT_TUNE_NO_LNFUSE 6    // [6] != 0: no LayerNorm fused into the FFN output projection's epilogue
 
 // one-time-per-DEVICE guard for cudaFuncSetAttribute-style opt-ins (a process may drive several GPUs): true the first time the

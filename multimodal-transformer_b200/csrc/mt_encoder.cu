@@ -397,7 +397,7 @@ int encoder_bwd_impl(const MtEncoderCfg& c, const Groups& gr, const float* param
     MT_TRY(pj.wgrad(d, d, w.dact, b.att, base + P.w_o));
     // d att = d out . w_o; when the tcgen05 attention backward follows, the same GEMM leaves D = rowsum(d att . att) per head in the
     // attention kernel's per-query scalars (no separate pass over att and d att)
-    bool d_ready = false;
+    int d_ready = 0;
     if (lp && !g_mt_tune[MT_TUNE_NO_RS] && d == 32 * c.h &&
         mt_attn_group_bwd_uses_tc(c.dtype, G, c.B, c.T, d, c.h, b.qkv, b.att, w.dact2, w.dqkv, w.Dws, grads + base + P.b_qkv)) {
       RsDesc r;
@@ -405,8 +405,10 @@ int encoder_bwd_impl(const MtEncoderCfg& c, const Groups& gr, const float* param
       r.A = w.dact; r.lda = d; r.ldb = d; r.b_kmajor = false;
       r.C = w.dact2; r.ldc = d; r.c_f32 = false;
       r.attd_src = b.att; r.attd_ld = d; r.attd_aux = w.Dws; r.attd_T = c.T;
+      const bool all_rows = !(g_mt_tune[MT_TUNE_PDL_DEBUG] & 2);      // the epilogue writes the other three per-query scalars as well (no light pass)
+      if (all_rows) { r.attd_lse = b.lse; r.attd_mask = mask; r.attd_scale = 1.0f / sqrtf(32.0f); }
       for (int g = 0; g < G; ++g) { r.B[g] = (const bf16*)params_lp + g * gr.pstride + base + P.w_o; r.drop[g] = mt_make_drop(0.f, 0, 0); }
-      if (mt_gemm_rs_supported(r)) { MT_TRY(mt_gemm_rs_run(r, st)); d_ready = true; }
+      if (mt_gemm_rs_supported(r)) { MT_TRY(mt_gemm_rs_run(r, st)); d_ready = all_rows ? 2 : 1; }
     }
     if (!d_ready) MT_TRY(pj.run(true, d, d, w.dact, base + P.w_o, w.dact2, !lp, -1, MT_ACT_NONE, l, -1, nullptr, 1.f, nullptr, -1));
     {

@@ -83,6 +83,7 @@ struct RsArgs {
   const float* ln_b[MAXG];
   DropCfg drop[MAXG];
   float* attd_aux; int attd_T;      // R_ATTD: see RsDesc
+  const float* attd_lse; const float* attd_mask; float attd_scale;   // R_ATTD, optional: the other three per-query scalars
   unsigned long long* trace;      // debug (mt_gemm_rs_trace): clock64 stamps of CTA 0, 16 words per tile, first 32 tiles
 };
 
@@ -270,6 +271,15 @@ __global__ void __launch_bounds__(NT, 1) gemm_rs_kernel(const __grid_constant__ 
       const int tm = rank + it * g.cnt;
       const int row0 = grp * g.rows_per_group + tm * BM;
       const int acc = it & 1;
+      // R_ATTD with attd_lse: the scalars of this warp group's first column pair are fetched in front of the accumulator wait
+      float pf_lse0 = 0.f, pf_lse1 = 0.f, pf_mask = 1.f;
+      if ((F & R_ATTD) && g.attd_lse != nullptr && tm * BM + row < g.rows_per_group) {
+        const int m = tm * BM + row, bl = m / g.attd_T, tq = m - bl * g.attd_T;
+        const size_t bh = ((size_t)grp * (g.rows_per_group / g.attd_T) + bl) * (size_t)(g.N >> 5) + (size_t)((n0 >> 5) + 2 * wg);
+        pf_lse0 = __ldg(g.attd_lse + bh * (size_t)g.attd_T + tq);
+        pf_lse1 = __ldg(g.attd_lse + (bh + 1) * (size_t)g.attd_T + tq);
+        if (g.attd_mask != nullptr) pf_mask = __ldg(g.attd_mask + (size_t)bl * g.attd_T + tq);
+      }
       mbar_wait(&acc_full[acc], (uint32_t)(it >> 1) & 1u);
       fence_after();
       const bool tr = g.trace && blockIdx.x == 0 && it < 32 && storer;
@@ -338,6 +348,13 @@ __global__ void __launch_bounds__(NT, 1) gemm_rs_kernel(const __grid_constant__ 
             const int ug = it * C::PAIRS + pr, gs = ug % (C::NSG ? C::NSG : 1);
             if (cc == 0) mbar_wait(&full_g[gs], (uint32_t)(ug / (C::NSG ? C::NSG : 1)) & 1u);
             const uint8_t* gb = g_ring + gs * BOX;
+            // the other three per-query scalars of the attention backward (attd_lse given): their loads fly under the D sum
+            const int m = tm * BM + row;                          // row inside the group
+            const bool live = m < g.rows_per_group;
+            const int bl = m / g.attd_T, q = m - bl * g.attd_T;
+            const size_t bh = ((size_t)grp * (g.rows_per_group / g.attd_T) + bl) * (size_t)(g.N >> 5) + (size_t)((n0 >> 5) + c);
+            float lse_q = cc ? pf_lse1 : pf_lse0, mask_q = pf_mask;
+            if (g.attd_lse != nullptr && live && pr != wg) lse_q = __ldg(g.attd_lse + bh * (size_t)g.attd_T + q);      // later pairs (BN > 128): in place
             float D = 0.f;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -354,11 +371,16 @@ __global__ void __launch_bounds__(NT, 1) gemm_rs_kernel(const __grid_constant__ 
               __syncwarp();
               if (lane == 0) mbar_arrive(&empty_g[gs]);
             }
-            const int m = tm * BM + row;                          // row inside the group
-            if (m < g.rows_per_group) {
-              const int bl = m / g.attd_T, q = m - bl * g.attd_T;
-              const size_t bh = ((size_t)grp * (g.rows_per_group / g.attd_T) + bl) * (size_t)(g.N >> 5) + (size_t)((n0 >> 5) + c);
-              g.attd_aux[(bh * 4 + 1) * 128 + q] = D;
+            if (live) {
+              float* ax = g.attd_aux + bh * 4 * 128 + q;
+              ax[128] = D;
+              if (g.attd_lse != nullptr) {                        // what attn_tc_prep_light_kernel would write (mt_attention_tc.cu)
+                constexpr float LOG2E = 1.4426950408889634f;
+                const bool masked = mask_q == 0.f;
+                ax[0] = lse_q * LOG2E;
+                ax[2 * 128] = masked ? 0.f : g.attd_scale * LOG2E;
+                ax[3 * 128] = masked ? 0.f : g.attd_scale;
+              }
             }
           }
           if (F & R_RES) {         // residual box use number: one per chunk
@@ -539,6 +561,7 @@ int launch(const RsDesc& d, cudaStream_t st) {
   g.b_mn = d.b_kmajor ? 0 : 1;
   g.gate_scale = d.gate_scale; g.ln_eps = d.ln_eps;
   g.attd_aux = d.attd_aux; g.attd_T = d.attd_T > 0 ? d.attd_T : 1;
+  g.attd_lse = d.attd_lse; g.attd_mask = d.attd_mask; g.attd_scale = d.attd_scale;
   g.trace = g_rs_trace;
   const int P = d.G * g.tiles_n;
   int cnt = num_sms() / P;

@@ -31,6 +31,10 @@ struct RsDesc {
   // with b = row / attd_T (global narrative index), q = row % attd_T, h = N / 32: row 1 of mt_attention_tc.cu's per-query scalars
   const void* attd_src = nullptr; int attd_ld = 0;
   float* attd_aux = nullptr; int attd_T = 0;
+  // optional: with attd_lse (fp32 [G*B, h, attd_T], natural log) the same epilogue also writes rows 0 / 2 / 3 of the scalars -- lse * log2e,
+  // score scale * log2e and score-gradient scale (both 0 where attd_mask[b LOCAL to the group, q] == 0; attd_mask may be null) --
+  // so that the attention backward needs no preparation launch at all
+  const float* attd_lse = nullptr; const float* attd_mask = nullptr; float attd_scale = 0.f;
 };
 
 bool mt_gemm_rs_supported(const RsDesc& d);

@@ -86,7 +86,7 @@ int mt_attn_tc_dropbits_job(int G, int B, int T, int h, const DropCfg* drops, ui
 // G > 1 as in mt_attn_tc_fwd_run; aux holds G * mt_attn_bwd_ws_floats(B, T, h) floats, dbias of group g at dbias + g * dbias_gstride
 int mt_attn_tc_bwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse, const void* dout,
                        void* dqkv, DropCfg drop, float* dbias, float* aux, cudaStream_t st, int G = 1, const DropCfg* drops = nullptr,
-                       size_t dbias_gstride = 0, bool d_ready = false, const uint32_t* dbits = nullptr);      // d_ready: aux row 1 (D) was written by the caller
+                       size_t dbias_gstride = 0, int d_ready = 0, const uint32_t* dbits = nullptr);      // d_ready: 1 = aux row 1 (D) was written by the caller, 2 = all four rows were
 // ---- tcgen05 / TMEM flash attention for long sequences, 64-wide heads (mt_attention_flash.cu), bf16 ------------------------
 bool mt_attn_flash_supported(int B, int T, int d, int h);
 int mt_attn_flash_fwd_run(int B, int T, int d, int h, const void* qkv, const float* mask, void* out, float* lse, DropCfg drop, cudaStream_t st);
@@ -111,7 +111,7 @@ int mt_attn_group_fwd_run(int dtype, int G, int B, int T, int d, int h, const vo
                           const DropCfg* drops, cudaStream_t st, const int* klen = nullptr, const uint32_t* dbits = nullptr);
 int mt_attn_group_bwd_run(int dtype, int G, int B, int T, int d, int h, const void* qkv, const float* mask, const void* out, const float* lse,
                           const void* dout, void* dqkv, const DropCfg* drops, float* Dws, cudaStream_t st, float* dbias, size_t dbias_gstride,
-                          bool d_ready = false, const uint32_t* dbits = nullptr);
+                          int d_ready = 0, const uint32_t* dbits = nullptr);
 // true when mt_attn_group_bwd_run will take the tcgen05 engine for these arguments (then the caller may pre-fill D = rowsum(dout . out)
 // into Dws[((b * h + head) * 4 + 1) * 128 + q] and pass d_ready)
 bool mt_attn_group_bwd_uses_tc(int dtype, int G, int B, int T, int d, int h, const void* qkv, const void* out, const void* dout,

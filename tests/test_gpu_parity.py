@@ -1067,6 +1067,19 @@ def test_grouped_qkv_input_gradient_equals_per_stack_launches():
         assert_close(g_grp[k], g_per[k], 1e-5, k, 1e-9)
 
 
+def test_attention_backward_scalars_from_the_projection_epilogue_equal_the_light_pass():
+    """By default the input-gradient GEMM of the output projection writes all four per-query scalars of the tcgen05 attention backward
+    (lse * log2e, D, the two masked score scales) from its epilogue (mt_gemm_rs.cu R_ATTD with attd_lse); mt_tune key 15 bit 1 keeps the
+    light preparation launch for rows 0 / 2 / 3 instead.  Same numbers either way (ragged lengths: masked query rows included), full
+    (T = 128) and partial (T = 64) key tiles."""
+    for T in (128, 64):
+        p_epi, g_epi = _mft_bf16_train_step(T=T)
+        p_light, g_light = _mft_bf16_train_step({15: 2}, T=T)
+        assert torch.equal(p_epi, p_light)
+        for k in g_epi:
+            assert_close(g_epi[k], g_light[k], 1e-5, k, 1e-9)
+
+
 def test_second_cut_recurrences_match_the_first_cut():
     """mt_tune key 8, bit 6 selects the first-cut MFN recurrence kernels: same stash layouts, same math except the sigmoid (tanh unit vs
     ex2 + rcp, ~3e-4 absolute), so predictions and gradients agree far inside the bf16 budget."""
